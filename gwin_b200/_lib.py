@@ -1,0 +1,262 @@
+"""ctypes binding of ``libgwin_b200.so`` (C ABI declared in ``include/gwin_b200.h``).
+
+There is no CPU fallback: if the shared library is missing or no sm_100 device is
+present every entry point raises.  ``build()`` compiles the library in-tree with
+nvcc for sm_100a (cross-compiles without a GPU).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "libgwin_b200.so")
+SOURCES = [os.path.join(_HERE, "csrc", "gwin_cuda.cu")]
+HEADER = os.path.join(ROOT, "include", "gwin_b200.h")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
+              "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
+
+GWIN_NPARAM = 11
+GWIN_MAX_DET = 4
+MODE_GAUSSIAN = 0
+MODE_MARG_PHASE = 1
+KERNEL_AUTO, KERNEL_DIRECT, KERNEL_RECURRENCE = 0, 1, 2
+
+# Every symbol include/gwin_b200.h declares (checked by tests/test_abi.py).
+SYMBOLS = (
+    "gwin_plan_create", "gwin_plan_destroy", "gwin_plan_cutoffs",
+    "gwin_plan_lognl", "gwin_plan_configure", "gwin_loglr_batch",
+    "gwin_loglr_batch_host", "gwin_generate_host", "gwin_plan_last_launches",
+    "gwin_fp64_peak", "gwin_last_error", "gwin_version",
+)
+
+_lock = threading.Lock()
+_lib = None
+
+
+class GwinCudaError(RuntimeError):
+    """Raised when the CUDA library reports a failure (or is missing)."""
+
+
+def _stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(s) > t for s in SOURCES + [HEADER]
+               if os.path.exists(s))
+
+
+def build(force=False, verbose=False):
+    """Compile ``libgwin_b200.so`` in-tree for sm_100a."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + SOURCES
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise GwinCudaError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr))
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+def load():
+    """Load the shared library (building it first if the source is newer)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            try:
+                build()
+            except (OSError, GwinCudaError) as e:
+                raise GwinCudaError(
+                    "libgwin_b200.so is not built and could not be compiled "
+                    "(%s); gwin_b200 has no CPU fallback" % e)
+        lib = C.CDLL(LIB_PATH)
+        dp = C.POINTER(C.c_double)
+        lib.gwin_plan_create.restype = C.c_int
+        lib.gwin_plan_create.argtypes = [
+            C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int64, C.c_double,
+            C.c_double, C.c_double, C.c_double, C.c_double,
+            dp, dp, dp, dp, C.c_double]
+        lib.gwin_plan_destroy.restype = None
+        lib.gwin_plan_destroy.argtypes = [C.c_void_p]
+        lib.gwin_plan_cutoffs.restype = C.c_int
+        lib.gwin_plan_cutoffs.argtypes = [C.c_void_p, C.POINTER(C.c_int64),
+                                          C.POINTER(C.c_int64)]
+        lib.gwin_plan_lognl.restype = C.c_int
+        lib.gwin_plan_lognl.argtypes = [C.c_void_p, dp, dp]
+        lib.gwin_plan_configure.restype = C.c_int
+        lib.gwin_plan_configure.argtypes = [C.c_void_p, C.c_int, C.c_double,
+                                            C.c_double]
+        lib.gwin_loglr_batch.restype = C.c_int
+        lib.gwin_loglr_batch.argtypes = [
+            C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
+            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.gwin_loglr_batch_host.restype = C.c_int
+        lib.gwin_loglr_batch_host.argtypes = [
+            C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
+            C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.gwin_generate_host.restype = C.c_int
+        lib.gwin_generate_host.argtypes = [C.c_void_p, dp, dp,
+                                           C.POINTER(C.c_int64)]
+        lib.gwin_plan_last_launches.restype = C.c_int
+        lib.gwin_plan_last_launches.argtypes = [C.c_void_p]
+        lib.gwin_fp64_peak.restype = C.c_int
+        lib.gwin_fp64_peak.argtypes = [C.c_int, dp]
+        lib.gwin_last_error.restype = C.c_char_p
+        lib.gwin_version.restype = C.c_char_p
+        _lib = lib
+        return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().gwin_last_error().decode("utf-8", "replace")
+        if rc == -1:
+            raise ValueError(msg)
+        raise GwinCudaError("gwin_b200 error %d: %s" % (rc, msg))
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class Plan(object):
+    """Owns one ``gwin_plan`` (device tables + workspace) on one GPU."""
+
+    def __init__(self, device, delta_f, epoch, f_lower, f_upper, f_lower_wf,
+                 det_response, det_location, data, psd, norm):
+        lib = load()
+        data = np.ascontiguousarray(data, dtype=np.complex128)
+        n_det, n_f = data.shape
+        resp = np.ascontiguousarray(det_response, dtype=np.float64).reshape(n_det, 9)
+        loc = np.ascontiguousarray(det_location, dtype=np.float64).reshape(n_det, 3)
+        if psd is not None:
+            psd = np.ascontiguousarray(psd, dtype=np.float64)
+            if psd.shape != (n_det, n_f):
+                raise ValueError("psd shape %r does not match data %r"
+                                 % (psd.shape, data.shape))
+        handle = C.c_void_p()
+        rc = lib.gwin_plan_create(
+            C.byref(handle), int(device), int(n_det), int(n_f), float(delta_f),
+            float(epoch), float(f_lower or 0.0), float(f_upper or 0.0),
+            float(f_lower_wf), _dptr(resp), _dptr(loc),
+            _dptr(data.view(np.float64)),
+            _dptr(psd) if psd is not None else None,
+            float(norm) if norm is not None else 0.0)
+        check(rc)
+        self._h = handle
+        self._lib = lib
+        self.device = int(device)
+        self.n_det = int(n_det)
+        self.n_f = int(n_f)
+        kmin, kmax = C.c_int64(), C.c_int64()
+        check(lib.gwin_plan_cutoffs(self._h, C.byref(kmin), C.byref(kmax)))
+        self.kmin, self.kmax = kmin.value, kmax.value
+        tot = C.c_double()
+        per = np.zeros(n_det)
+        check(lib.gwin_plan_lognl(self._h, C.byref(tot), _dptr(per)))
+        self.lognl = tot.value
+        self.det_lognl = per
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gwin_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def configure(self, kernel=KERNEL_AUTO, phase_tol=0.0, mchirp_min=0.0):
+        check(self._lib.gwin_plan_configure(self._h, int(kernel),
+                                            float(phase_tol), float(mchirp_min)))
+
+    @property
+    def last_launches(self):
+        return self._lib.gwin_plan_last_launches(self._h)
+
+    def loglr_host(self, params, mode=MODE_GAUSSIAN, skip=None):
+        """params: [W, 11] float64 host array.  Returns loglr[W],
+        hd[W, n_det] complex128, hh[W, n_det]."""
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        if params.ndim != 2 or params.shape[1] != GWIN_NPARAM:
+            raise ValueError("params must be [W, %d]" % GWIN_NPARAM)
+        W = params.shape[0]
+        loglr = np.empty(W)
+        hd = np.empty((W, self.n_det), dtype=np.complex128)
+        hh = np.empty((W, self.n_det))
+        sk = None
+        if skip is not None:
+            sk = np.ascontiguousarray(skip, dtype=np.uint8)
+            if sk.shape != (W,):
+                raise ValueError("skip must be [W]")
+        check(self._lib.gwin_loglr_batch_host(
+            self._h, int(mode), W, params.ctypes.data,
+            sk.ctypes.data if sk is not None else None,
+            loglr.ctypes.data, hd.ctypes.data, hh.ctypes.data))
+        return loglr, hd, hh
+
+    def loglr_device(self, params, mode=MODE_GAUSSIAN, skip=None, out=None,
+                     stream=None):
+        """Device-resident variant: ``params`` is a CUDA float64 torch tensor
+        [W, 11]; returns torch tensors (loglr, hd[W,n_det,2], hh) on the same
+        device.  Asynchronous on ``stream`` (default: torch's current stream).
+        torch is only the owner of the device memory here."""
+        import torch
+        if not params.is_cuda or params.dtype != torch.float64:
+            raise ValueError("params must be a CUDA float64 tensor")
+        params = params.contiguous()
+        W = params.shape[0]
+        if out is None:
+            loglr = torch.empty(W, dtype=torch.float64, device=params.device)
+            hd = torch.empty((W, self.n_det, 2), dtype=torch.float64,
+                             device=params.device)
+            hh = torch.empty((W, self.n_det), dtype=torch.float64,
+                             device=params.device)
+        else:
+            loglr, hd, hh = out
+        if stream is None:
+            stream = torch.cuda.current_stream(params.device).cuda_stream
+        sk = None
+        if skip is not None:
+            sk = skip.to(torch.uint8).contiguous()
+        check(self._lib.gwin_loglr_batch(
+            self._h, int(mode), W, params.data_ptr(),
+            sk.data_ptr() if sk is not None else None,
+            loglr.data_ptr(), hd.data_ptr(), hh.data_ptr(), stream))
+        return loglr, hd, hh
+
+    def generate(self, params):
+        """One detector-frame waveform set: returns (h[n_det, n_f] complex128,
+        length)."""
+        p = np.ascontiguousarray(params, dtype=np.float64).reshape(GWIN_NPARAM)
+        h = np.zeros((self.n_det, self.n_f), dtype=np.complex128)
+        n = C.c_int64()
+        check(self._lib.gwin_generate_host(self._h, _dptr(p),
+                                           _dptr(h.view(np.float64)),
+                                           C.byref(n)))
+        return h, n.value
+
+
+def fp64_peak(device=0):
+    """Measured FP64 FMA lane-ops/s of the device (independent DFMA chains)."""
+    r = C.c_double()
+    check(load().gwin_fp64_peak(int(device), C.byref(r)))
+    return r.value
+
+
+def version():
+    return load().gwin_version().decode()

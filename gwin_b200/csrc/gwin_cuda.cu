@@ -1,0 +1,1153 @@
+// gwin_b200 -- batched TaylorF2 log-likelihood-ratio on B200 (sm_100a).
+//
+// Replaces, for a whole ensemble of walkers at once, the per-walker chain the
+// reference runs on the CPU:
+//   waveform_generator.generate(**params)      gaussian_noise.py:322
+//   h[kmin:kmax] *= weight                     gaussian_noise.py:337
+//   <d|h> = data.inner(h)                      gaussian_noise.py:339
+//   <h|h> = h.inner(h).real                    gaussian_noise.py:340
+//   loglr combine                              gaussian_noise.py:341-350
+//   marginalised-phase combine                 marginalized_gaussian_noise.py:456-511
+// No intermediate waveform array is ever materialised: one thread owns one
+// walker, a warp shares (broadcast) loads of the pre-weighted data table, and the
+// frequency axis is cut into chunks so that the grid fills all 148 SMs.
+//
+// Three kernels per batch:  walker_setup -> loglr_{direct|recur} -> combine.
+// (+ a CUB radix sort of walkers by their last frequency bin so that the lanes
+// of a warp finish together.)
+//
+// Work is FP64-pipe bound: there is no dense contraction here, so no
+// tensor cores; the tables are L2-resident and read with warp-uniform 128-bit
+// loads.
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/gwin_b200.h"
+
+// ---------------------------------------------------------------------------
+// constants (LAL values; see oracle/gwin_oracle.py for provenance)
+// ---------------------------------------------------------------------------
+#define G_PI      3.141592653589793238462643383279502884
+#define G_TWOPI   6.283185307179586476925286766559005768
+#define G_GAMMA   0.577215664901532860606512090082402431
+#define G_C_SI    299792458.0
+#define G_MTSUN   4.925491025543575903411922162094833998e-6
+#define G_MRSUN   1.476625061404649406193430731479084713e3
+#define G_PC_SI   3.085677581491367278913937957796471611e16
+
+#define WARP 32
+#define CTA_THREADS 128
+#define RESYNC 64            // direct kernel: detector phasor re-sync interval
+#define MAX_BLOCK 256        // recurrence kernel: longest polynomial block
+#define MIN_BLOCK 8
+
+// per-walker coefficient rows (SoA: wc[row * wpad + walker])
+enum {
+    C_A0 = 0, C_A2, C_A3, C_A4, C_A5, C_B5, C_A6, C_B6, C_A7,   // phase [turns]
+    C_DET0                                                        // then 4 per detector
+};
+enum { D_TAUHI = 0, D_TAULO, D_ARE, D_AIM, D_NROW };
+#define NCOEF(nd) (C_DET0 + D_NROW * (nd))
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+    return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail(GWIN_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
+
+struct PlanDev {
+    int n_det;
+    int n_f;
+    int kmin, kmax;          // likelihood band [kmin, kmax)
+    int istart;              // first non-zero waveform bin
+    double delta_f;
+    double f_lower_wf;       // waveform generator's f_lower
+    double epoch;
+    double gps_utc;          // GPS-UTC leap seconds at the epoch
+    double resp[GWIN_MAX_DET][9];
+    double loc[GWIN_MAX_DET][3];
+    const double4* basis;    // [n_f] {f^(1/3), f^(-5/3), ln f^(1/3), 0}
+    const double2* T;        // [n_f][n_det] norm*conj(d)*f^(-7/6)/S
+    const double*  C;        // [n_det][n_f+1] prefix sums of norm*f^(-7/3)/S
+};
+
+struct gwin_plan {
+    int device;
+    PlanDev d;
+    double norm;
+    double lognl_det[GWIN_MAX_DET];
+    double lognl;
+    // tuning
+    int kernel;
+    double phase_tol;
+    double mchirp_min;
+    bool auto_mchirp;        // host API: derive mchirp_min from each batch
+    // recurrence schedule
+    std::vector<int> blk_start;      // host copy, nblk+1 entries
+    int* d_blk_start;
+    int n_blk;
+    bool sched_dirty;
+    // workspace
+    int64_t w_cap;
+    int chunk_cap;
+    double* d_wc;
+    int *d_ks, *d_ke, *d_key_in, *d_key_out, *d_perm_in, *d_perm_out;
+    double2* d_partial;
+    size_t partial_cap;
+    void* d_cub; size_t cub_bytes;
+    // staging for the host API
+    double *h_params, *h_out; uint8_t* h_skip;
+    double *d_params, *d_out; uint8_t* d_skip;
+    int64_t stage_cap;
+    cudaStream_t stream;
+    int last_launches;
+};
+
+// ---------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double round_magic(double x) {
+    // round-to-nearest-integer for |x| < 2^51 on the FP64 add pipe
+    const double M = 6755399441055744.0;
+    return __dadd_rn(__dadd_rn(x, M), -M);
+}
+__device__ __forceinline__ double frac1(double x) { return x - round_magic(x); }
+
+// e^{-2 pi i y} for y in turns (any magnitude < 2^51): returns (cos, -sin)
+__device__ __forceinline__ double2 phasor_neg(double y) {
+    double s, c;
+    sincospi(2.0 * frac1(y), &s, &c);
+    return make_double2(c, -s);
+}
+__device__ __forceinline__ double2 phasor_pos(double y) {
+    double s, c;
+    sincospi(2.0 * frac1(y), &s, &c);
+    return make_double2(c, s);
+}
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
+}
+// a*b + c
+__device__ __forceinline__ double2 cfma(double2 a, double2 b, double2 c) {
+    return make_double2(fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y)));
+}
+
+__device__ __forceinline__ double4 ld_basis(const double4* p) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+    const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+
+// TaylorF2 phase in turns at one bin, basis = {x, x^-5, ln x}
+struct PhaseCoef { double a0, a2, a3, a4, a5, b5, a6, b6, a7; };
+__device__ __forceinline__ double phase_turns(const PhaseCoef& c, double4 b) {
+    const double x = b.x, xm5 = b.y, lx = b.z;
+    double lo = fma(fma(c.a4, x, c.a3), x, c.a2);
+    lo = fma(lo, x * x, c.a0) * xm5;
+    const double l5 = fma(c.b5, lx, c.a5);
+    const double l6 = fma(c.b6, lx, c.a6);
+    const double hi = fma(fma(c.a7, x, l6), x, l5);
+    return lo + hi;
+}
+
+__device__ __forceinline__ void load_phase_coef(PhaseCoef& c, const double* wc, int wpad, int w) {
+    c.a0 = wc[C_A0 * wpad + w]; c.a2 = wc[C_A2 * wpad + w]; c.a3 = wc[C_A3 * wpad + w];
+    c.a4 = wc[C_A4 * wpad + w]; c.a5 = wc[C_A5 * wpad + w]; c.b5 = wc[C_B5 * wpad + w];
+    c.a6 = wc[C_A6 * wpad + w]; c.b6 = wc[C_B6 * wpad + w]; c.a7 = wc[C_A7 * wpad + w];
+}
+
+// ---------------------------------------------------------------------------
+// kernel 0: sort key = last bin of each walker's waveform (depends on total mass only)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool params_ok(const double* p) {
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < GWIN_NPARAM; ++i) ok = ok && isfinite(p[i]);
+    return ok && p[0] > 0.0 && p[1] > 0.0 && p[4] > 0.0;
+}
+__device__ __forceinline__ double f_isco(double mtot) {
+    const double piM = G_PI * (mtot * G_MTSUN);
+    const double vISCO = 1.0 / sqrt(6.0);
+    return vISCO * vISCO * vISCO / piM;
+}
+// lalsimulation refuses f_max <= fStart; pycbc turns that into NoWaveformError and
+// the reference into loglr = -inf (gaussian_noise.py:293-302, 321-324)
+__device__ __forceinline__ bool has_waveform(const double* p, double f_lower_wf) {
+    return f_isco(p[0] + p[1]) > f_lower_wf;
+}
+__device__ __forceinline__ int waveform_len(double mtot, double delta_f) {
+    // XLALSimInspiralTaylorF2: n = (size_t)(fISCO/deltaF + 1), fISCO = 6^-3/2/(pi M)
+    const double piM = G_PI * (mtot * G_MTSUN);
+    const double vISCO = 1.0 / sqrt(6.0);
+    const double fISCO = vISCO * vISCO * vISCO / piM;
+    const double n = fISCO / delta_f + 1.0;
+    return n > 2.0e9 ? 2000000000 : (int)n;
+}
+
+__global__ void sort_key_kernel(PlanDev P, int W, const double* __restrict__ params,
+                                const uint8_t* __restrict__ skip, int* __restrict__ key,
+                                int* __restrict__ idx) {
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    const double* p = params + (size_t)w * GWIN_NPARAM;
+    int ke = 0;
+    if (!(skip && skip[w]) && params_ok(p) && has_waveform(p, P.f_lower_wf)) {
+        int n = waveform_len(p[0] + p[1], P.delta_f);
+        ke = min(n, P.kmax);
+    }
+    key[w] = ke;
+    idx[w] = w;
+}
+
+// ---------------------------------------------------------------------------
+// kernel 1: per-walker coefficients.  Thread t handles walker perm[t] and writes
+// its rows at sorted position t.
+// ---------------------------------------------------------------------------
+__global__ void walker_setup_kernel(PlanDev P, int W, int wpad,
+                                    const double* __restrict__ params,
+                                    const uint8_t* __restrict__ skip,
+                                    const int* __restrict__ perm,
+                                    double* __restrict__ wc, int* __restrict__ ks_arr,
+                                    int* __restrict__ ke_arr,
+                                    double* __restrict__ hh_sorted /*[n_det][wpad]*/) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= W) return;
+    const int w = perm ? perm[t] : t;
+    const double* p = params + (size_t)w * GWIN_NPARAM;
+    const int nd = P.n_det;
+    const bool ok = !(skip && skip[w]) && params_ok(p) && has_waveform(p, P.f_lower_wf);
+    if (!ok) {
+        // no bins; combine() turns this into -inf via ks = -1
+        ks_arr[t] = -1; ke_arr[t] = -1;
+        for (int r = 0; r < NCOEF(nd); ++r) wc[r * wpad + t] = 0.0;
+        for (int d = 0; d < nd; ++d) hh_sorted[d * wpad + t] = 0.0;
+        return;
+    }
+    const double m1 = p[0], m2 = p[1], chi1 = p[2], chi2 = p[3], dist = p[4];
+    const double incl = p[5], phic = p[6], ra = p[7], dec = p[8], psi = p[9], tc = p[10];
+
+    // --- XLALSimInspiralPNPhasing_F2 (3.5PN, aligned spins) ---------------------
+    const double mtot = m1 + m2;
+    const double dm = (m1 - m2) / (m1 + m2);
+    const double eta = m1 * m2 / mtot / mtot;
+    const double m1M = m1 / mtot, m2M = m2 / mtot;
+    const double pfaN = 3.0 / (128.0 * eta);
+    double v2 = 5.0 * (743.0 / 84.0 + 11.0 * eta) / 9.0;
+    double v3 = -16.0 * G_PI;
+    double v4 = 5.0 * (3058.673 / 7.056 + 5429.0 / 7.0 * eta + 617.0 * eta * eta) / 72.0;
+    double v5 = 5.0 / 9.0 * (7729.0 / 84.0 - 13.0 * eta) * G_PI;
+    double vl5 = 5.0 / 3.0 * (7729.0 / 84.0 - 13.0 * eta) * G_PI;
+    double v6 = (11583.231236531 / 4.694215680 - 640.0 / 3.0 * G_PI * G_PI - 6848.0 / 21.0 * G_GAMMA)
+              + eta * (-15737.765635 / 3.048192 + 2255.0 / 12.0 * G_PI * G_PI)
+              + eta * eta * 76055.0 / 1728.0 - eta * eta * eta * 127825.0 / 1296.0;
+    v6 += (-6848.0 / 21.0) * 1.3862943611198906188;   // log(4)
+    const double vl6 = -6848.0 / 21.0;
+    double v7 = G_PI * (77096675.0 / 254016.0 + 378515.0 / 1512.0 * eta - 74045.0 / 756.0 * eta * eta);
+    {
+        const double chi1sq = chi1 * chi1, chi2sq = chi2 * chi2;
+        const double SL = m1M * m1M * chi1 + m2M * m2M * chi2;
+        const double dSigmaL = dm * (m2M * chi2 - m1M * chi1);
+        double pn_sigma = eta * (721.0 / 48.0 * chi1 * chi2 - 247.0 / 48.0 * chi1 * chi2);
+        pn_sigma += (720.0 - 1.0) / 96.0 * m1M * m1M * chi1 * chi1;
+        pn_sigma += (720.0 - 1.0) / 96.0 * m2M * m2M * chi2 * chi2;
+        pn_sigma -= (240.0 - 7.0) / 96.0 * m1M * m1M * chi1sq;
+        pn_sigma -= (240.0 - 7.0) / 96.0 * m2M * m2M * chi2sq;
+        double pn_ss3 = (326.75 / 1.12 + 557.5 / 1.8 * eta) * eta * chi1 * chi2;
+        pn_ss3 += ((4703.5 / 8.4 + 2935.0 / 6.0 * m1M - 120.0 * m1M * m1M)
+                   + (-4108.25 / 6.72 - 108.5 / 1.2 * m1M + 125.5 / 3.6 * m1M * m1M)) * m1M * m1M * chi1sq;
+        pn_ss3 += ((4703.5 / 8.4 + 2935.0 / 6.0 * m2M - 120.0 * m2M * m2M)
+                   + (-4108.25 / 6.72 - 108.5 / 1.2 * m2M + 125.5 / 3.6 * m2M * m2M)) * m2M * m2M * chi2sq;
+        const double pn_gamma = (554345.0 / 1134.0 + 110.0 * eta / 9.0) * SL
+                              + (13915.0 / 84.0 - 10.0 * eta / 3.0) * dSigmaL;
+        v7 += (-8980424995.0 / 762048.0 + 6586595.0 * eta / 756.0 - 305.0 * eta * eta / 36.0) * SL
+            - (170978035.0 / 48384.0 - 2876425.0 * eta / 672.0 - 4735.0 * eta * eta / 144.0) * dSigmaL;
+        v6 += G_PI * (3760.0 * SL + 1490.0 * dSigmaL) / 3.0 + pn_ss3;
+        v5 += -1.0 * pn_gamma;
+        vl5 += -3.0 * pn_gamma;
+        v4 += -10.0 * pn_sigma;
+        v3 += 188.0 * SL / 3.0 + 25.0 * dSigmaL;
+    }
+    // --- fold v = (pi M f)^(1/3) = m3 * x,  x = f^(1/3), into coefficients [turns] --
+    const double m_sec = mtot * G_MTSUN;
+    const double piM = G_PI * m_sec;
+    const double m3 = cbrt(piM);
+    const double lm3 = log(m3);
+    const double s = pfaN / G_TWOPI;
+    const double im3 = 1.0 / m3;
+    const double im3_2 = im3 * im3, im3_3 = im3_2 * im3, im3_5 = im3_3 * im3_2;
+    wc[C_A0 * wpad + t] = s * im3_5;
+    wc[C_A2 * wpad + t] = s * v2 * im3_3;
+    wc[C_A3 * wpad + t] = s * v3 * im3_2;
+    wc[C_A4 * wpad + t] = s * v4 * im3;
+    // constant term also absorbs -2 phi_c - pi/4
+    wc[C_A5 * wpad + t] = s * (v5 + vl5 * lm3) - (2.0 * phic + 0.25 * G_PI) / G_TWOPI;
+    wc[C_B5 * wpad + t] = s * vl5;
+    wc[C_A6 * wpad + t] = s * (v6 + vl6 * lm3) * m3;
+    wc[C_B6 * wpad + t] = s * vl6 * m3;
+    wc[C_A7 * wpad + t] = s * v7 * m3 * m3;
+
+    // --- band ------------------------------------------------------------------
+    const int n = waveform_len(mtot, P.delta_f);
+    const int ke = min(n, P.kmax);
+    const int ks = max(P.kmin, P.istart);
+    ks_arr[t] = ks;
+    ke_arr[t] = ke;        // ke <= ks means "detectors contribute 0" (gaussian_noise.py:329-333)
+
+    // --- amplitude: amp0 * sqrt(5/(32 eta)) * (pi M)^(-7/6) -------------------------
+    const double r = dist * 1e6 * G_PC_SI;
+    const double amp0 = -4.0 * m1 * m2 / r * G_MRSUN * G_MTSUN * sqrt(G_PI / 12.0);
+    const double ampfac = amp0 * sqrt(5.0 / (32.0 * eta)) * (im3_3 / sqrt(m3));
+    const double cfac = cos(incl);
+    const double pfac = 0.5 * (1.0 + cfac * cfac);
+
+    // --- XLALGreenwichMeanSiderealTime(tc), bit-faithful to LAL's arithmetic: the
+    // Julian day is formed from INTEGER UTC seconds in a double (ulp 4.7e-10 d = 40 us),
+    // the nanoseconds enter separately; no FMA contraction.
+    double gmst;
+    {
+        const double sec_f = floor(tc);
+        double nsd = rint((tc - sec_f) * 1e9);
+        long long sec = (long long)sec_f;
+        if (nsd >= 1e9) { sec += 1; nsd -= 1e9; }
+        const long long utc = sec - (long long)P.gps_utc;
+        long long days = utc / 86400;
+        long long sod = utc - days * 86400;
+        if (sod < 0) { sod += 86400; days -= 1; }
+        // XLALConvertCivilTimeToJD: jd(int) + sec/86400. - 0.5 ; GPS 0 = 1980-01-06 -> 2444245
+        const double jd = __dadd_rn(__dadd_rn((double)(2444245LL + days), __ddiv_rn((double)sod, 86400.0)), -0.5);
+        const double t_hi = __ddiv_rn(__dadd_rn(jd, -2451545.0), 36525.0);
+        const double t_lo = __ddiv_rn(nsd, 1e9 * 36525.0 * 86400.0);
+        const double tj = __dadd_rn(t_hi, t_lo);
+        double sid = __dadd_rn(__dmul_rn(-6.2e-6, tj), 0.093104);
+        sid = __dadd_rn(__dmul_rn(__dmul_rn(sid, tj), tj), 67310.54841);
+        sid = __dadd_rn(sid, __dmul_rn(8640184.812866, t_lo));
+        sid = __dadd_rn(sid, __dmul_rn(3155760000.0, t_lo));
+        sid = __dadd_rn(sid, __dmul_rn(8640184.812866, t_hi));
+        sid = __dadd_rn(sid, __dmul_rn(3155760000.0, t_hi));
+        gmst = __ddiv_rn(__dmul_rn(sid, G_PI), 43200.0);
+    }
+    const double gha = gmst - ra;
+    double singha, cosgha, sindec, cosdec, sinpsi, cospsi;
+    sincos(gha, &singha, &cosgha);
+    sincos(dec, &sindec, &cosdec);
+    sincos(psi, &sinpsi, &cospsi);
+    const double X[3] = { -cospsi * singha - sinpsi * cosgha * sindec,
+                          -cospsi * cosgha + sinpsi * singha * sindec,
+                           sinpsi * cosdec };
+    const double Y[3] = {  sinpsi * singha - cospsi * cosgha * sindec,
+                           sinpsi * cosgha + cospsi * singha * sindec,
+                           cospsi * cosdec };
+    const double eh[3] = { cosdec * cosgha, cosdec * -singha, sindec };
+
+    for (int d = 0; d < nd; ++d) {
+        double fp = 0.0, fc = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double dx = P.resp[d][3 * i] * X[0] + P.resp[d][3 * i + 1] * X[1] + P.resp[d][3 * i + 2] * X[2];
+            const double dy = P.resp[d][3 * i] * Y[0] + P.resp[d][3 * i + 1] * Y[1] + P.resp[d][3 * i + 2] * Y[2];
+            fp += X[i] * dx - Y[i] * dy;
+            fc += X[i] * dy + Y[i] * dx;
+        }
+        // time_delay_from_earth_center: (0 - loc).ehat / c
+        const double delay = (-P.loc[d][0] * eh[0] - P.loc[d][1] * eh[1] - P.loc[d][2] * eh[2]) / G_C_SI;
+        // generator.py: tc_det = tc + delay; apply_fd_time_shift: dt = tc_det - epoch
+        const double tcd = tc + delay;
+        const double dt = tcd - P.epoch;
+        double tau = dt * P.delta_f;                 // turns per bin
+        tau = tau - rint(tau);
+        const double tau_hi = rint(tau * 1073741824.0) / 1073741824.0;   // 2^30: k*tau_hi exact
+        const double tau_lo = tau - tau_hi;
+        // h_det = (F+ pfac - i Fx cfac) * ampfac * f^(-7/6) * e^{-i(...)}
+        const double are = fp * pfac * ampfac;
+        const double aim = -fc * cfac * ampfac;
+        double* row = wc + (size_t)(C_DET0 + D_NROW * d) * wpad + t;
+        row[D_TAUHI * wpad] = tau_hi;
+        row[D_TAULO * wpad] = tau_lo;
+        row[D_ARE * wpad] = are;
+        row[D_AIM * wpad] = aim;
+        // <h|h> closed form: |A|^2 * sum_{ks<=k<ke} norm f^(-7/3)/S  (phase-free)
+        double hh = 0.0;
+        if (ke > ks) {
+            const double* C = P.C + (size_t)d * (P.n_f + 1);
+            hh = (are * are + aim * aim) * (C[ke] - C[ks]);
+        }
+        hh_sorted[d * wpad + t] = hh;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// kernel 2a: direct evaluation.  One thread = one walker; CTA = 128 walkers x
+// one frequency chunk.  Per bin: FP64 phase polynomial, sincospi, and per
+// detector a delay-phasor recurrence (exact re-sync every RESYNC bins), a
+// rotation and a complex MAC against T.
+// ---------------------------------------------------------------------------
+template <int ND>
+__global__ void __launch_bounds__(CTA_THREADS)
+loglr_direct_kernel(PlanDev P, int W, int wpad, int chunk_bins, int n_chunks,
+                    const double* __restrict__ wc, const int* __restrict__ ks_arr,
+                    const int* __restrict__ ke_arr, double2* __restrict__ partial) {
+    const int t = blockIdx.x * CTA_THREADS + threadIdx.x;
+    const int chunk = blockIdx.y;
+    const int band0 = max(P.kmin, P.istart);
+    const int k0 = band0 + chunk * chunk_bins;
+    const int k1 = min(k0 + chunk_bins, P.kmax);
+    const bool live = t < W;
+    const int ks = live ? ks_arr[t] : 0, ke = live ? ke_arr[t] : 0;
+    const int lo = max(k0, ks), hi = min(k1, ke);
+    const bool has = lo < hi;
+    int wlo = has ? lo : 0x7fffffff, whi = has ? hi : 0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        wlo = min(wlo, __shfl_xor_sync(0xffffffffu, wlo, o));
+        whi = max(whi, __shfl_xor_sync(0xffffffffu, whi, o));
+    }
+    double2 acc[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) acc[d] = make_double2(0.0, 0.0);
+
+    if (wlo < whi) {
+        const int tt = live ? t : 0;
+        PhaseCoef pc;
+        load_phase_coef(pc, wc, wpad, tt);
+        double tau_hi[ND], tau_lo[ND];
+        double2 step[ND], ph[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            const double* row = wc + (size_t)(C_DET0 + D_NROW * d) * wpad + tt;
+            tau_hi[d] = row[D_TAUHI * wpad];
+            tau_lo[d] = row[D_TAULO * wpad];
+            step[d] = phasor_neg(tau_hi[d] + tau_lo[d]);
+            ph[d] = make_double2(1.0, 0.0);
+        }
+        const double4* __restrict__ basis = P.basis;
+        const double2* __restrict__ T = P.T;
+        for (int k = wlo; k < whi; ++k) {
+            if (k == wlo || (k & (RESYNC - 1)) == 0) {
+                const double kd = (double)k;
+#pragma unroll
+                for (int d = 0; d < ND; ++d)
+                    ph[d] = phasor_neg(fma(kd, tau_lo[d], frac1(kd * tau_hi[d])));
+            }
+            const double4 b = ld_basis(basis + k);
+            const double2 u = phasor_neg(phase_turns(pc, b));
+            const bool on = (k >= lo) && (k < hi);
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                const double2 Tk = __ldg(T + (size_t)k * ND + d);
+                const double2 wv = cmul(u, ph[d]);
+                if (on) acc[d] = cfma(Tk, wv, acc[d]);
+                ph[d] = cmul(ph[d], step[d]);
+            }
+        }
+    }
+    if (live) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+            partial[((size_t)chunk * ND + d) * wpad + t] = acc[d];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// kernel 2b: block-anchored chirp-phasor recurrence.
+//
+// The band is cut (once per plan) into blocks of B_b <= MAX_BLOCK bins, short at
+// low frequency where the chirp phase curves fastest.  Inside a block the
+// detector phase Theta_d(j) = Psi(k0+j) + (k0+j) tau_d is replaced by the quartic
+// through 5 exact samples (both block ends are nodes), whose error is bounded by
+// the plan's phase_tol for every chirp mass >= mchirp_min.  The quartic's
+// forward differences D1..D4 become unit phasors g, r, s, t with
+//      acc <- acc * g + T[j] ;  g <- g * r ;  r <- r * s ;  s <- s * t
+// (Horner form of sum_j T_j e^{2 pi i (Theta(B-1) - Theta(j))}), so that one bin
+// costs 8 + 8*ND FP64 issue slots instead of a phase polynomial and a sincos.
+// The block sum is then rotated by the exact anchor phasor e^{-2 pi i Theta_d(B-1)}.
+// ---------------------------------------------------------------------------
+template <int ND, bool MASKED>
+__device__ __forceinline__ void recur_block(
+        const PhaseCoef& pc, const double (&tau_hi)[ND], const double (&tau_lo)[ND],
+        const double4* __restrict__ basis, const double2* __restrict__ T,
+        int kb, int B, int lo, int hi, double2 (&acc_out)[ND]) {
+    if (B < 5) {
+        // too short to carry 5 distinct nodes: evaluate these bins directly
+        for (int k = kb; k < kb + B; ++k) {
+            if (k < lo || k >= hi) continue;
+            const double psi = phase_turns(pc, ld_basis(basis + k));
+            const double kd = (double)k;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                const double2 u = phasor_neg(psi + fma(kd, tau_lo[d], frac1(kd * tau_hi[d])));
+                acc_out[d] = cfma(__ldg(T + (size_t)k * ND + d), u, acc_out[d]);
+            }
+        }
+        return;
+    }
+    // nodes 0, t1, t2, t3, B-1
+    const int e = B - 1;
+    const int t1 = (e + 4) / 8;                // ~ (1-cos(pi/4))/2 = 0.1464
+    const int t2 = e / 2;
+    const int t3 = e - t1;
+    const double f0 = phase_turns(pc, ld_basis(basis + kb));
+    const double f1 = phase_turns(pc, ld_basis(basis + kb + t1));
+    const double f2 = phase_turns(pc, ld_basis(basis + kb + t2));
+    const double f3 = phase_turns(pc, ld_basis(basis + kb + t3));
+    const double f4 = phase_turns(pc, ld_basis(basis + kb + e));
+    // Newton divided differences on integer nodes
+    const double x1 = (double)t1, x2 = (double)t2, x3 = (double)t3, x4 = (double)e;
+    const double d01 = (f1 - f0) / x1;
+    const double d12 = (f2 - f1) / (x2 - x1);
+    const double d23 = (f3 - f2) / (x3 - x2);
+    const double d34 = (f4 - f3) / (x4 - x3);
+    const double d012 = (d12 - d01) / x2;
+    const double d123 = (d23 - d12) / (x3 - x1);
+    const double d234 = (d34 - d23) / (x4 - x2);
+    const double d0123 = (d123 - d012) / x3;
+    const double d1234 = (d234 - d123) / (x4 - x1);
+    const double n4 = (d1234 - d0123) / x4;
+    const double n1 = d01, n2 = d012, n3 = d0123;
+    // Newton -> monomial:  P(j) = f0 + c1 j + c2 j^2 + c3 j^3 + c4 j^4
+    //   j(j-x1)(j-x2)(j-x3) = j^4 - e1 j^3 + e2 j^2 - e3 j
+    const double e1 = x1 + x2 + x3, e2 = x1 * x2 + x1 * x3 + x2 * x3, e3 = x1 * x2 * x3;
+    const double c4 = n4;
+    const double c3 = n3 - n4 * e1;
+    const double c2 = n2 - n3 * (x1 + x2) + n4 * e2;
+    const double c1 = n1 - n2 * x1 + n3 * (x1 * x2) - n4 * e3;
+    // forward differences: D1(0), D2(1), D3(2), D4
+    //   D1(j) = c1 + c2(2j+1) + c3(3j^2+3j+1) + c4(4j^3+6j^2+4j+1)
+    //   D2(j) = D1(j)-D1(j-1) = 2c2 + 6c3 j + c4(12 j^2 + 2)
+    //   D3(j) = D2(j)-D2(j-1) = 6c3 + c4(24 j - 12)
+    //   D4    = 24 c4
+    const double D1_0 = c1 + c2 + c3 + c4;
+    const double D2_1 = 2.0 * c2 + 6.0 * c3 + 14.0 * c4;
+    const double D3_2 = 6.0 * c3 + 36.0 * c4;
+    const double D4 = 24.0 * c4;
+    const double2 tq = phasor_pos(D4);
+    double2 sq = phasor_pos(D3_2);
+    double2 rq = phasor_pos(D2_1);
+    double2 g[ND], acc[ND];
+    const double kend = (double)(kb + e);
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        g[d] = phasor_pos(D1_0 + (tau_hi[d] + tau_lo[d]));
+        double2 T0 = __ldg(T + (size_t)kb * ND + d);
+        if (MASKED && !(kb >= lo && kb < hi)) T0 = make_double2(0.0, 0.0);
+        acc[d] = T0;
+    }
+#pragma unroll 4
+    for (int j = 1; j < B; ++j) {
+        const int k = kb + j;
+        const bool on = !MASKED || ((k >= lo) && (k < hi));
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            double2 Tk = __ldg(T + (size_t)k * ND + d);
+            if (MASKED && !on) Tk = make_double2(0.0, 0.0);
+            acc[d] = cfma(acc[d], g[d], Tk);
+            g[d] = cmul(g[d], rq);
+        }
+        rq = cmul(rq, sq);
+        sq = cmul(sq, tq);
+    }
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        const double anchor = f4 + fma(kend, tau_lo[d], frac1(kend * tau_hi[d]));
+        acc_out[d] = cfma(acc[d], phasor_neg(anchor), acc_out[d]);
+    }
+}
+
+template <int ND>
+__global__ void __launch_bounds__(CTA_THREADS)
+loglr_recur_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_blk,
+                   const int* __restrict__ blk_start,
+                   const double* __restrict__ wc, const int* __restrict__ ks_arr,
+                   const int* __restrict__ ke_arr, double2* __restrict__ partial) {
+    const int t = blockIdx.x * CTA_THREADS + threadIdx.x;
+    const int chunk = blockIdx.y;
+    const int b0 = chunk * blocks_per_chunk;
+    const int b1 = min(b0 + blocks_per_chunk, n_blk);
+    const bool live = t < W;
+    const int ks = live ? ks_arr[t] : 0, ke = live ? ke_arr[t] : 0;
+    const int k0 = blk_start[b0], k1 = blk_start[b1];
+    const int lo = max(k0, ks), hi = min(k1, ke);
+    const bool has = lo < hi;
+    int wlo = has ? lo : 0x7fffffff, whi = has ? hi : 0;      // union over the warp
+    int ilo = has ? lo : 0x7fffffff, ihi = has ? hi : 0;      // intersection over the warp
+    const unsigned any_idle = __ballot_sync(0xffffffffu, !has);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        wlo = min(wlo, __shfl_xor_sync(0xffffffffu, wlo, o));
+        whi = max(whi, __shfl_xor_sync(0xffffffffu, whi, o));
+        ilo = max(ilo, __shfl_xor_sync(0xffffffffu, ilo, o));
+        ihi = min(ihi, __shfl_xor_sync(0xffffffffu, ihi, o));
+    }
+    if (any_idle) { ilo = 0x7fffffff; ihi = 0; }
+    double2 acc[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) acc[d] = make_double2(0.0, 0.0);
+
+    if (wlo < whi) {
+        const int tt = live ? t : 0;
+        PhaseCoef pc;
+        load_phase_coef(pc, wc, wpad, tt);
+        double tau_hi[ND], tau_lo[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            const double* row = wc + (size_t)(C_DET0 + D_NROW * d) * wpad + tt;
+            tau_hi[d] = row[D_TAUHI * wpad];
+            tau_lo[d] = row[D_TAULO * wpad];
+        }
+        for (int b = b0; b < b1; ++b) {
+            const int kb = blk_start[b], kn = blk_start[b + 1];
+            if (kn <= wlo || kb >= whi) continue;       // nobody in this warp needs it
+            if (kb >= ilo && kn <= ihi)
+                recur_block<ND, false>(pc, tau_hi, tau_lo, P.basis, P.T, kb, kn - kb, lo, hi, acc);
+            else
+                recur_block<ND, true>(pc, tau_hi, tau_lo, P.basis, P.T, kb, kn - kb, lo, hi, acc);
+        }
+    }
+    if (live) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+            partial[((size_t)chunk * ND + d) * wpad + t] = acc[d];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// kernel 3: combine chunk partials, scale by the walker amplitude, form loglr,
+// scatter back to the caller's walker order.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double log_i0(double x) {
+    // log I0(x); the reference's numpy.log(special.i0(x)) (marginalized_gaussian_noise.py:459)
+    // overflows for x >~ 713 -- identical below, finite above.
+    if (x < 400.0) return log(cyl_bessel_i0(x));
+    const double y = 1.0 / (8.0 * x);
+    // I0(x) ~ e^x/sqrt(2 pi x) * sum_n ((2n-1)!!)^2 / n! * y^n
+    const double ser = 1.0 + y * (1.0 + y * (4.5 + y * (37.5 + y * (459.375 + y * (7441.875 + y * 150077.8125)))));
+    return x - 0.5 * log(G_TWOPI * x) + log(ser);
+}
+
+__global__ void combine_kernel(int n_det, int W, int wpad, int n_chunks, int mode,
+                               const int* __restrict__ perm, const double* __restrict__ wc,
+                               const int* __restrict__ ks_arr,
+                               const double2* __restrict__ partial,
+                               const double* __restrict__ hh_sorted,
+                               double* __restrict__ loglr, double* __restrict__ hd_out,
+                               double* __restrict__ hh_out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= W) return;
+    const int w = perm ? perm[t] : t;
+    const bool invalid = ks_arr[t] < 0;
+    double lr = 0.0, sre = 0.0, sim = 0.0, shh = 0.0;
+    for (int d = 0; d < n_det; ++d) {
+        double re = 0.0, im = 0.0;
+        for (int c = 0; c < n_chunks; ++c) {
+            const double2 p = partial[((size_t)c * n_det + d) * wpad + t];
+            re += p.x; im += p.y;
+        }
+        const double* row = wc + (size_t)(C_DET0 + D_NROW * d) * wpad + t;
+        const double are = row[D_ARE * wpad], aim = row[D_AIM * wpad];
+        const double hre = are * re - aim * im;
+        const double him = are * im + aim * re;
+        const double hh = hh_sorted[d * wpad + t];
+        if (hd_out) {
+            hd_out[((size_t)w * n_det + d) * 2 + 0] = invalid ? 0.0 : hre;
+            hd_out[((size_t)w * n_det + d) * 2 + 1] = invalid ? 0.0 : him;
+        }
+        if (hh_out) hh_out[(size_t)w * n_det + d] = invalid ? 0.0 : hh;
+        lr += hre - 0.5 * hh;
+        sre += hre; sim += him; shh += hh;
+    }
+    if (mode == GWIN_MODE_MARG_PHASE) lr = log_i0(hypot(sre, sim)) - 0.5 * shh;
+    if (invalid || isnan(lr)) lr = -INFINITY;
+    loglr[w] = lr;
+}
+
+// ---------------------------------------------------------------------------
+// waveform dump (FDomainDetFrameGenerator.generate for one point)
+// ---------------------------------------------------------------------------
+__global__ void generate_kernel(PlanDev P, int wpad, const double* __restrict__ wc,
+                                const int* __restrict__ ke_arr, double2* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= P.n_f) return;
+    PhaseCoef pc;
+    load_phase_coef(pc, wc, wpad, 0);
+    // un-clipped waveform length is stored in ke_arr[1]
+    const int n = ke_arr[1];
+    for (int d = 0; d < P.n_det; ++d) {
+        double2 h = make_double2(0.0, 0.0);
+        if (k >= P.istart && k < n && k > 0) {
+            const double* row = wc + (size_t)(C_DET0 + D_NROW * d) * wpad;
+            const double kd = (double)k;
+            const double ph = phase_turns(pc, ld_basis(P.basis + k)) +
+                              fma(kd, row[D_TAULO * wpad], frac1(kd * row[D_TAUHI * wpad]));
+            const double2 u = phasor_neg(ph);
+            const double f = kd * P.delta_f;
+            const double a = pow(f, -7.0 / 6.0);
+            const double2 A = make_double2(row[D_ARE * wpad] * a, row[D_AIM * wpad] * a);
+            h = cmul(A, u);
+        }
+        out[(size_t)d * P.n_f + k] = h;
+    }
+}
+__global__ void generate_len_kernel(PlanDev P, const double* __restrict__ params, int* __restrict__ ke_arr) {
+    ke_arr[1] = (params_ok(params) && has_waveform(params, P.f_lower_wf)) ? waveform_len(params[0] + params[1], P.delta_f) : 0;
+}
+
+// FP64 issue-rate probe: 8 independent DFMA chains per thread
+__global__ void dfma_probe_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+    double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999999, c = 1e-12;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static const int64_t LEAPS_GPS[] = {
+    46828800, 78364801, 109900802, 173059203, 252028804, 315187205, 346723206,
+    394156807, 425692808, 457228809, 504489610, 551750411, 599184012, 820108813,
+    914803214, 1025136015, 1119744016, 1167264017 };
+
+static void build_schedule(gwin_plan* p) {
+    // Blocks over [band0, kmax).  Quartic through 5 nodes {0, ~.15, .5, ~.85, 1}(B-1):
+    // |err| <= max|Psi^(5)| / 5! * max|prod (j - t_i)|, with max|prod| <= 0.005 (B-1)^5
+    // for these nodes (Chebyshev-Lobatto-like).  Leading-order chirp:
+    //   Psi(f) = 3/128 (pi Mc f)^(-5/3)  =>  |Psi^(5)(f)| = 3/128 (pi Mc)^(-5/3) * K5 * f^(-20/3)
+    //   K5 = (5/3)(8/3)(11/3)(14/3)(17/3); x2 safety for the higher PN orders.
+    const PlanDev& d = p->d;
+    const int band0 = std::max(d.kmin, d.istart);
+    p->blk_start.clear();
+    const double K5 = (5.0 / 3) * (8.0 / 3) * (11.0 / 3) * (14.0 / 3) * (17.0 / 3);
+    const double pref = 2.0 * (3.0 / 128.0) * pow(G_PI * p->mchirp_min * G_MTSUN, -5.0 / 3.0) * K5
+                        * pow(d.delta_f, 5.0);
+    int k = std::max(band0, 1);
+    while (k < d.kmax) {
+        const double f = k * d.delta_f;
+        const double d5 = pref * pow(f, -20.0 / 3.0);            // rad / bin^5
+        double B = pow(p->phase_tol * 120.0 / (0.005 * d5), 0.2) + 1.0;
+        int Bi = (int)std::min<double>(B, MAX_BLOCK);
+        // too curved for an 8-bin quartic: 4-bin blocks take the direct path in the kernel
+        Bi = Bi >= MIN_BLOCK ? (Bi & ~3) : 4;
+        if (k + Bi > d.kmax) Bi = d.kmax - k;
+        p->blk_start.push_back(k);
+        k += Bi;
+    }
+    p->blk_start.push_back(d.kmax);
+    p->n_blk = (int)p->blk_start.size() - 1;
+    // a trailing block shorter than 5 bins cannot carry 5 distinct nodes: merge it
+    if (p->n_blk >= 2) {
+        const int last = p->blk_start[p->n_blk] - p->blk_start[p->n_blk - 1];
+        const int prev = p->blk_start[p->n_blk - 1] - p->blk_start[p->n_blk - 2];
+        if (last < MIN_BLOCK && prev >= MIN_BLOCK) {
+            p->blk_start.erase(p->blk_start.end() - 2);
+            p->n_blk--;
+        }
+    }
+}
+
+static int upload_schedule(gwin_plan* p) {
+    build_schedule(p);
+    if (p->d_blk_start) cudaFree(p->d_blk_start);
+    p->d_blk_start = nullptr;
+    CK(cudaMalloc(&p->d_blk_start, sizeof(int) * p->blk_start.size()));
+    CK(cudaMemcpy(p->d_blk_start, p->blk_start.data(), sizeof(int) * p->blk_start.size(),
+                  cudaMemcpyHostToDevice));
+    p->sched_dirty = false;
+    return GWIN_OK;
+}
+
+extern "C" const char* gwin_last_error(void) { return g_err; }
+extern "C" const char* gwin_version(void) { return "gwin_b200 0.1 (sm_100a)"; }
+
+extern "C" int gwin_plan_create(gwin_plan** out, int device, int n_det, int64_t n_f,
+                                double delta_f, double epoch_gps,
+                                double f_lower, double f_upper, double f_lower_wf,
+                                const double* det_response, const double* det_location,
+                                const double* data, const double* psd, double norm) {
+    if (!out) return fail(GWIN_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (n_det < 1 || n_det > GWIN_MAX_DET) return fail(GWIN_EINVAL, "n_det must be 1..%d", GWIN_MAX_DET);
+    if (n_f < 4 || n_f > (1 << 22)) return fail(GWIN_EINVAL, "n_f out of range");
+    if (!(delta_f > 0.0)) return fail(GWIN_EINVAL, "delta_f must be > 0");
+    if (!det_response || !det_location || !data) return fail(GWIN_EINVAL, "NULL input array");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(GWIN_ENODEVICE, "no CUDA device: gwin_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(GWIN_EINVAL, "device %d not present", device);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(GWIN_ENODEVICE, "device %s is sm_%d%d; this library is built for sm_100a only",
+                                     prop.name, prop.major, prop.minor);
+
+    // pycbc.filter.get_cutoff_indices(f_lower, f_upper, df, (n_f-1)*2)   gaussian_noise.py:247
+    const int64_t N = (n_f - 1) * 2;
+    int64_t kmin = f_lower ? (int64_t)(f_lower / delta_f) : 1;
+    if (kmin < 0) return fail(GWIN_EINVAL, "low frequency cutoff must be >= 0");
+    int64_t kmax = (int64_t)((N + 1) / 2.);
+    if (f_upper > 0.0) kmax = std::min<int64_t>((int64_t)(f_upper / delta_f), kmax);
+    if (kmax <= kmin) return fail(GWIN_EINVAL, "kmax (%lld) <= kmin (%lld)", (long long)kmax, (long long)kmin);
+    if (!(norm > 0.0)) norm = 4.0 * delta_f;
+
+    gwin_plan* p = new (std::nothrow) gwin_plan();
+    if (!p) return fail(GWIN_ENOMEM, "out of host memory");
+    p->device = device;
+    p->norm = norm;
+    p->kernel = GWIN_KERNEL_AUTO;
+    p->phase_tol = 1e-10;
+    p->mchirp_min = 0.5;
+    p->auto_mchirp = true;
+    p->sched_dirty = true;
+    PlanDev& d = p->d;
+    d.n_det = n_det; d.n_f = (int)n_f; d.kmin = (int)kmin; d.kmax = (int)kmax;
+    d.istart = (int)std::ceil(f_lower_wf / delta_f);
+    if (d.istart < 1) d.istart = 1;
+    d.delta_f = delta_f; d.epoch = epoch_gps; d.f_lower_wf = f_lower_wf;
+    int leaps = 0;
+    for (int64_t t : LEAPS_GPS) if ((int64_t)std::floor(epoch_gps) >= t) ++leaps;
+    d.gps_utc = leaps;
+    for (int i = 0; i < n_det; ++i) {
+        memcpy(d.resp[i], det_response + 9 * i, sizeof(double) * 9);
+        memcpy(d.loc[i], det_location + 3 * i, sizeof(double) * 3);
+    }
+
+    // tables (built once per plan, on the host, in extended precision)
+    std::vector<double> basis((size_t)n_f * 4), T((size_t)n_f * n_det * 2, 0.0), C((size_t)n_det * (n_f + 1), 0.0);
+    std::vector<long double> f76(n_f, 0.0L), f73(n_f, 0.0L);
+    basis[0] = 1.0; basis[1] = 1.0; basis[2] = 0.0; basis[3] = 0.0;
+    for (int64_t k = 1; k < n_f; ++k) {
+        const long double f = (long double)k * (long double)delta_f;
+        const long double x = cbrtl(f);
+        const long double lx = logl(x);
+        basis[4 * k + 0] = (double)x;
+        basis[4 * k + 1] = (double)(1.0L / (x * x * x * x * x));
+        basis[4 * k + 2] = (double)lx;
+        basis[4 * k + 3] = 0.0;
+        if (k >= kmin && k < kmax) {
+            const long double x2 = x * x, x7 = x2 * x2 * x2 * x;
+            f73[k] = 1.0L / x7;                 // f^(-7/3)
+            f76[k] = 1.0L / sqrtl(x7);          // f^(-7/6)
+        }
+    }
+    for (int det = 0; det < n_det; ++det) {
+        long double csum = 0.0L, nl = 0.0L;
+        const double* dd = data + (size_t)det * n_f * 2;
+        const double* S = psd ? psd + (size_t)det * n_f : nullptr;
+        double* Cd = C.data() + (size_t)det * (n_f + 1);
+        for (int64_t k = 0; k < n_f; ++k) {
+            Cd[k] = (double)csum;
+            if (k >= kmin && k < kmax) {
+                const long double w2 = S ? (long double)norm / (long double)S[k] : (long double)norm;
+                const long double re = dd[2 * k], im = dd[2 * k + 1];
+                nl += (re * re + im * im) * w2;
+                csum += f73[k] * w2;
+                T[((size_t)k * n_det + det) * 2 + 0] = (double)(re * w2 * f76[k]);
+                T[((size_t)k * n_det + det) * 2 + 1] = (double)(-im * w2 * f76[k]);
+            }
+        }
+        Cd[n_f] = (double)csum;
+        p->lognl_det[det] = (double)(-0.5L * nl);
+    }
+    p->lognl = 0.0;
+    for (int det = 0; det < n_det; ++det) p->lognl += p->lognl_det[det];
+
+    double4* db = nullptr; double2* dT = nullptr; double* dC = nullptr;
+    CK(cudaMalloc(&db, basis.size() * sizeof(double)));
+    CK(cudaMalloc(&dT, T.size() * sizeof(double)));
+    CK(cudaMalloc(&dC, C.size() * sizeof(double)));
+    CK(cudaMemcpy(db, basis.data(), basis.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dT, T.data(), T.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dC, C.data(), C.size() * sizeof(double), cudaMemcpyHostToDevice));
+    d.basis = db; d.T = dT; d.C = dC;
+    CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    *out = p;
+    return GWIN_OK;
+}
+
+extern "C" void gwin_plan_destroy(gwin_plan* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaFree((void*)p->d.basis); cudaFree((void*)p->d.T); cudaFree((void*)p->d.C);
+    cudaFree(p->d_blk_start);
+    cudaFree(p->d_wc); cudaFree(p->d_ks); cudaFree(p->d_ke);
+    cudaFree(p->d_key_in); cudaFree(p->d_key_out); cudaFree(p->d_perm_in); cudaFree(p->d_perm_out);
+    cudaFree(p->d_partial); cudaFree(p->d_cub);
+    cudaFree(p->d_params); cudaFree(p->d_out); cudaFree(p->d_skip);
+    cudaFreeHost(p->h_params); cudaFreeHost(p->h_out); cudaFreeHost(p->h_skip);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+extern "C" int gwin_plan_cutoffs(const gwin_plan* p, int64_t* kmin, int64_t* kmax) {
+    if (!p) return fail(GWIN_EINVAL, "plan is NULL");
+    if (kmin) *kmin = p->d.kmin;
+    if (kmax) *kmax = p->d.kmax;
+    return GWIN_OK;
+}
+
+extern "C" int gwin_plan_lognl(const gwin_plan* p, double* total, double* per_det) {
+    if (!p) return fail(GWIN_EINVAL, "plan is NULL");
+    if (total) *total = p->lognl;
+    if (per_det) for (int i = 0; i < p->d.n_det; ++i) per_det[i] = p->lognl_det[i];
+    return GWIN_OK;
+}
+
+extern "C" int gwin_plan_configure(gwin_plan* p, int kernel, double phase_tol, double mchirp_min) {
+    if (!p) return fail(GWIN_EINVAL, "plan is NULL");
+    if (kernel < GWIN_KERNEL_AUTO || kernel > GWIN_KERNEL_RECURRENCE) return fail(GWIN_EINVAL, "bad kernel id");
+    p->kernel = kernel;
+    if (phase_tol > 0.0 && phase_tol != p->phase_tol) { p->phase_tol = phase_tol; p->sched_dirty = true; }
+    if (mchirp_min > 0.0) {
+        p->auto_mchirp = false;
+        if (mchirp_min != p->mchirp_min) { p->mchirp_min = mchirp_min; p->sched_dirty = true; }
+    }
+    return GWIN_OK;
+}
+
+extern "C" int gwin_plan_last_launches(const gwin_plan* p) { return p ? p->last_launches : 0; }
+
+static int ensure_workspace(gwin_plan* p, int64_t W, int n_chunks) {
+    const int nd = p->d.n_det;
+    if (W > p->w_cap) {
+        int64_t cap = std::max<int64_t>(W, 1024);
+        cap = (cap + CTA_THREADS - 1) / CTA_THREADS * CTA_THREADS;
+        cudaFree(p->d_wc); cudaFree(p->d_ks); cudaFree(p->d_ke);
+        cudaFree(p->d_key_in); cudaFree(p->d_key_out); cudaFree(p->d_perm_in); cudaFree(p->d_perm_out);
+        cudaFree(p->d_cub);
+        p->d_wc = nullptr; p->d_ks = p->d_ke = p->d_key_in = p->d_key_out = p->d_perm_in = p->d_perm_out = nullptr;
+        p->d_cub = nullptr; p->w_cap = 0;
+        // coefficient rows + n_det rows of hh
+        CK(cudaMalloc(&p->d_wc, sizeof(double) * (NCOEF(nd) + nd) * cap));
+        CK(cudaMalloc(&p->d_ks, sizeof(int) * cap));
+        CK(cudaMalloc(&p->d_ke, sizeof(int) * cap));
+        CK(cudaMalloc(&p->d_key_in, sizeof(int) * cap));
+        CK(cudaMalloc(&p->d_key_out, sizeof(int) * cap));
+        CK(cudaMalloc(&p->d_perm_in, sizeof(int) * cap));
+        CK(cudaMalloc(&p->d_perm_out, sizeof(int) * cap));
+        p->cub_bytes = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, p->cub_bytes, p->d_key_in, p->d_key_out,
+                                           p->d_perm_in, p->d_perm_out, (int)cap, 0, 23));
+        CK(cudaMalloc(&p->d_cub, p->cub_bytes));
+        p->w_cap = cap;
+        p->partial_cap = 0;
+    }
+    const size_t need = (size_t)n_chunks * nd * p->w_cap;
+    if (need > p->partial_cap) {
+        cudaFree(p->d_partial); p->d_partial = nullptr; p->partial_cap = 0;
+        CK(cudaMalloc(&p->d_partial, sizeof(double2) * need));
+        p->partial_cap = need;
+    }
+    return GWIN_OK;
+}
+
+template <int ND>
+static void launch_main(gwin_plan* p, bool recur, int W, int wpad, int n_chunks, int per_chunk,
+                        double* hh_rows, cudaStream_t st) {
+    (void)hh_rows;
+    dim3 grid((W + CTA_THREADS - 1) / CTA_THREADS, n_chunks);
+    if (recur)
+        loglr_recur_kernel<ND><<<grid, CTA_THREADS, 0, st>>>(p->d, W, wpad, per_chunk, p->n_blk, p->d_blk_start,
+                                                            p->d_wc, p->d_ks, p->d_ke, p->d_partial);
+    else
+        loglr_direct_kernel<ND><<<grid, CTA_THREADS, 0, st>>>(p->d, W, wpad, per_chunk, n_chunks,
+                                                             p->d_wc, p->d_ks, p->d_ke, p->d_partial);
+}
+
+extern "C" int gwin_loglr_batch(gwin_plan* p, int mode, int64_t W64,
+                                const double* params, const uint8_t* skip,
+                                double* loglr, double* hd, double* hh, void* stream) {
+    if (!p) return fail(GWIN_EINVAL, "plan is NULL");
+    if (mode != GWIN_MODE_GAUSSIAN && mode != GWIN_MODE_MARG_PHASE) return fail(GWIN_EINVAL, "bad mode %d", mode);
+    if (W64 < 0 || W64 > (1 << 26)) return fail(GWIN_EINVAL, "W out of range");
+    p->last_launches = 0;
+    if (W64 == 0) return GWIN_OK;
+    if (!params || !loglr) return fail(GWIN_EINVAL, "params/loglr is NULL");
+    CK(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int W = (int)W64;
+    const PlanDev& d = p->d;
+    const int nd = d.n_det;
+    const bool recur = p->kernel != GWIN_KERNEL_DIRECT;
+    if (recur && p->sched_dirty) { int rc = upload_schedule(p); if (rc) return rc; }
+
+    // frequency chunking: enough CTAs to fill 148 SMs x ~5 resident CTAs several times over
+    const int band0 = std::max(d.kmin, d.istart);
+    const int nbins = std::max(d.kmax - band0, 1);
+    const int groups = (W + CTA_THREADS - 1) / CTA_THREADS;
+    const int want_chunks = std::max(1, (148 * 48 + groups - 1) / groups);
+    int n_chunks, per_chunk;
+    if (recur) {
+        const int min_blocks = 2;
+        per_chunk = std::max(min_blocks, (p->n_blk + want_chunks - 1) / want_chunks);
+        n_chunks = (p->n_blk + per_chunk - 1) / per_chunk;
+    } else {
+        per_chunk = std::max(RESYNC, (nbins + want_chunks - 1) / want_chunks);
+        per_chunk = (per_chunk + RESYNC - 1) / RESYNC * RESYNC;
+        n_chunks = (nbins + per_chunk - 1) / per_chunk;
+    }
+    int rc = ensure_workspace(p, W, n_chunks);
+    if (rc) return rc;
+    const int wpad = (int)p->w_cap;
+    double* hh_rows = p->d_wc + (size_t)NCOEF(nd) * wpad;
+
+    const int tb = 128, gb = (W + tb - 1) / tb;
+    const int* perm = nullptr;
+    if (W > WARP) {
+        sort_key_kernel<<<gb, tb, 0, st>>>(d, W, params, skip, p->d_key_in, p->d_perm_in);
+        size_t bytes = p->cub_bytes;
+        CK(cub::DeviceRadixSort::SortPairs(p->d_cub, bytes, p->d_key_in, p->d_key_out,
+                                           p->d_perm_in, p->d_perm_out, W, 0, 23, st));
+        perm = p->d_perm_out;
+        p->last_launches += 2;   // + CUB's own passes (library code, not counted)
+    }
+    walker_setup_kernel<<<gb, tb, 0, st>>>(d, W, wpad, params, skip, perm, p->d_wc, p->d_ks, p->d_ke, hh_rows);
+    switch (nd) {
+        case 1: launch_main<1>(p, recur, W, wpad, n_chunks, per_chunk, hh_rows, st); break;
+        case 2: launch_main<2>(p, recur, W, wpad, n_chunks, per_chunk, hh_rows, st); break;
+        case 3: launch_main<3>(p, recur, W, wpad, n_chunks, per_chunk, hh_rows, st); break;
+        default: launch_main<4>(p, recur, W, wpad, n_chunks, per_chunk, hh_rows, st); break;
+    }
+    combine_kernel<<<gb, tb, 0, st>>>(nd, W, wpad, n_chunks, mode, perm, p->d_wc, p->d_ks, p->d_partial,
+                                      hh_rows, loglr, hd, hh);
+    p->last_launches += 3;
+    CK(cudaGetLastError());
+    return GWIN_OK;
+}
+
+static int ensure_stage(gwin_plan* p, int64_t W) {
+    if (W <= p->stage_cap) return GWIN_OK;
+    const int nd = p->d.n_det;
+    int64_t cap = std::max<int64_t>(W, 1024);
+    cudaFree(p->d_params); cudaFree(p->d_out); cudaFree(p->d_skip);
+    cudaFreeHost(p->h_params); cudaFreeHost(p->h_out); cudaFreeHost(p->h_skip);
+    p->d_params = p->d_out = nullptr; p->d_skip = nullptr;
+    p->h_params = p->h_out = nullptr; p->h_skip = nullptr; p->stage_cap = 0;
+    const size_t out_row = 1 + 3 * (size_t)nd;
+    CK(cudaMalloc(&p->d_params, sizeof(double) * GWIN_NPARAM * cap));
+    CK(cudaMalloc(&p->d_out, sizeof(double) * out_row * cap));
+    CK(cudaMalloc(&p->d_skip, cap));
+    CK(cudaMallocHost(&p->h_params, sizeof(double) * GWIN_NPARAM * cap));
+    CK(cudaMallocHost(&p->h_out, sizeof(double) * out_row * cap));
+    CK(cudaMallocHost(&p->h_skip, cap));
+    p->stage_cap = cap;
+    return GWIN_OK;
+}
+
+extern "C" int gwin_loglr_batch_host(gwin_plan* p, int mode, int64_t W,
+                                     const double* params, const uint8_t* skip,
+                                     double* loglr, double* hd, double* hh) {
+    if (!p) return fail(GWIN_EINVAL, "plan is NULL");
+    if (W < 0) return fail(GWIN_EINVAL, "W < 0");
+    if (W == 0) { p->last_launches = 0; return GWIN_OK; }
+    if (!params || !loglr) return fail(GWIN_EINVAL, "params/loglr is NULL");
+    CK(cudaSetDevice(p->device));
+    int rc = ensure_stage(p, W);
+    if (rc) return rc;
+    const int nd = p->d.n_det;
+    cudaStream_t st = p->stream;
+    memcpy(p->h_params, params, sizeof(double) * GWIN_NPARAM * W);
+    if (p->auto_mchirp && p->kernel != GWIN_KERNEL_DIRECT) {
+        // the block schedule must cover the smallest chirp mass of the batch: quantise it
+        // down to a quarter octave so the (cheap) schedule rebuild is rare
+        double mc_min = 1e300;
+        for (int64_t i = 0; i < W; ++i) {
+            if (skip && skip[i]) continue;
+            const double m1 = params[i * GWIN_NPARAM], m2 = params[i * GWIN_NPARAM + 1];
+            if (!(m1 > 0.0) || !(m2 > 0.0) || !std::isfinite(m1 + m2)) continue;
+            const double mc = std::pow(m1 * m2, 0.6) / std::pow(m1 + m2, 0.2);
+            mc_min = std::min(mc_min, mc);
+        }
+        if (mc_min < 1e300) {
+            mc_min = std::min(std::max(mc_min, 0.02), 1e4);
+            const double q = std::exp2(std::floor(4.0 * std::log2(mc_min)) / 4.0);
+            if (q != p->mchirp_min) { p->mchirp_min = q; p->sched_dirty = true; }
+        }
+    }
+    CK(cudaMemcpyAsync(p->d_params, p->h_params, sizeof(double) * GWIN_NPARAM * W, cudaMemcpyHostToDevice, st));
+    if (skip) {
+        memcpy(p->h_skip, skip, W);
+        CK(cudaMemcpyAsync(p->d_skip, p->h_skip, W, cudaMemcpyHostToDevice, st));
+    }
+    double* d_lr = p->d_out;
+    double* d_hd = p->d_out + p->stage_cap;
+    double* d_hh = d_hd + 2 * (size_t)nd * p->stage_cap;
+    rc = gwin_loglr_batch(p, mode, W, p->d_params, skip ? p->d_skip : nullptr, d_lr, d_hd, d_hh, st);
+    if (rc) return rc;
+    double* h_lr = p->h_out;
+    double* h_hd = p->h_out + p->stage_cap;
+    double* h_hh = h_hd + 2 * (size_t)nd * p->stage_cap;
+    CK(cudaMemcpyAsync(h_lr, d_lr, sizeof(double) * W, cudaMemcpyDeviceToHost, st));
+    if (hd) CK(cudaMemcpyAsync(h_hd, d_hd, sizeof(double) * 2 * nd * W, cudaMemcpyDeviceToHost, st));
+    if (hh) CK(cudaMemcpyAsync(h_hh, d_hh, sizeof(double) * nd * W, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(loglr, h_lr, sizeof(double) * W);
+    if (hd) memcpy(hd, h_hd, sizeof(double) * 2 * nd * W);
+    if (hh) memcpy(hh, h_hh, sizeof(double) * nd * W);
+    return GWIN_OK;
+}
+
+extern "C" int gwin_generate_host(gwin_plan* p, const double* params, double* h_out, int64_t* length) {
+    if (!p || !params || !h_out) return fail(GWIN_EINVAL, "NULL argument");
+    CK(cudaSetDevice(p->device));
+    int rc = ensure_stage(p, 1); if (rc) return rc;
+    rc = ensure_workspace(p, 2, 1); if (rc) return rc;
+    const PlanDev& d = p->d;
+    const int wpad = (int)p->w_cap;
+    cudaStream_t st = p->stream;
+    memcpy(p->h_params, params, sizeof(double) * GWIN_NPARAM);
+    CK(cudaMemcpyAsync(p->d_params, p->h_params, sizeof(double) * GWIN_NPARAM, cudaMemcpyHostToDevice, st));
+    double* hh_rows = p->d_wc + (size_t)NCOEF(d.n_det) * wpad;
+    walker_setup_kernel<<<1, 32, 0, st>>>(d, 1, wpad, p->d_params, nullptr, nullptr, p->d_wc, p->d_ks, p->d_ke, hh_rows);
+    generate_len_kernel<<<1, 1, 0, st>>>(d, p->d_params, p->d_ke);
+    double2* dout = nullptr;
+    CK(cudaMalloc(&dout, sizeof(double2) * (size_t)d.n_det * d.n_f));
+    generate_kernel<<<(d.n_f + 255) / 256, 256, 0, st>>>(d, wpad, p->d_wc, p->d_ke, dout);
+    int n = 0;
+    CK(cudaMemcpyAsync(h_out, dout, sizeof(double2) * (size_t)d.n_det * d.n_f, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&n, p->d_ke + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFree(dout);
+    if (length) *length = n;
+    p->last_launches = 3;
+    return GWIN_OK;
+}
+
+extern "C" int gwin_fp64_peak(int device, double* dfma_per_sec) {
+    if (!dfma_per_sec) return fail(GWIN_EINVAL, "NULL argument");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 1 << 15;
+    double* out = nullptr;
+    CK(cudaMalloc(&out, sizeof(double) * threads * blocks));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    dfma_probe_kernel<<<blocks, threads>>>(out, 1024);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(e0));
+        dfma_probe_kernel<<<blocks, threads>>>(out, iters);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double rate = (double)threads * blocks * iters * 8.0 / (ms * 1e-3);
+        best = std::max(best, rate);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    *dfma_per_sec = best;
+    return GWIN_OK;
+}

@@ -1,0 +1,192 @@
+"""``GaussianNoise``: stationary-Gaussian-noise likelihood, evaluated for whole
+batches of walkers by the sm_100a kernel.
+
+Constructor, error behaviour, stat names and properties follow the reference
+class (``gwin/models/gaussian_noise.py:219-434``).  What differs is *where* the
+arithmetic runs: ``__init__`` builds a CUDA plan (the reference's whitening of
+the data, :247-265, becomes a one-off table build), ``_loglr`` /
+``evaluate_batch`` call ``gwin_loglr_batch`` through the C ABI.  There is no CPU
+implementation of the likelihood in this package.
+"""
+import os
+from collections import OrderedDict
+
+import numpy
+
+from .. import _lib
+from ..waveform import param_matrix
+from .base_data import BaseDataModel
+
+
+def _default_device():
+    return int(os.environ.get("LOCAL_RANK", "0"))
+
+
+class GaussianNoise(BaseDataModel):
+    name = 'gaussian_noise'
+    _mode = _lib.MODE_GAUSSIAN
+
+    def __init__(self, variable_params, data, waveform_generator,
+                 f_lower, psds=None, f_upper=None, norm=None, device=None,
+                 **kwargs):
+        super(GaussianNoise, self).__init__(variable_params, data,
+                                            waveform_generator, **kwargs)
+        # same detectors in data and generator (reference :227-233)
+        if (sorted(waveform_generator.detectors.keys()) !=
+                sorted(self._data.keys())):
+            raise ValueError(
+                "waveform generator's detectors ({0}) does not "
+                "match data ({1})".format(
+                    ','.join(sorted(waveform_generator.detector_names)),
+                    ','.join(sorted(self._data.keys()))))
+        # same epoch (reference :235-238)
+        if any(waveform_generator.epoch != d.epoch
+               for d in self._data.values()):
+            raise ValueError("waveform generator does not have the same epoch "
+                             "as all of the data sets.")
+        # same lengths (reference :240-242)
+        dlens = numpy.array([len(d) for d in data.values()])
+        if not all(dlens == dlens[0]):
+            raise ValueError("all data must be of the same length")
+        self._dets = list(self._data.keys())
+        d = self._data[self._dets[0]]
+        N = len(d)
+        delta_f = d.delta_f
+        if norm is None:
+            norm = 4 * delta_f
+        psd_arr = None
+        if psds is not None:
+            psd_arr = numpy.stack([numpy.asarray(psds[det], dtype=numpy.float64)
+                                   for det in self._dets])
+            if psd_arr.shape[1] != N:
+                raise ValueError("psds must have the same length as the data")
+        gen = waveform_generator
+        self._device = _default_device() if device is None else int(device)
+        # plan build == kmin/kmax, weight, whitening (reference :247-265)
+        self._plan = _lib.Plan(
+            self._device, delta_f, gen.epoch, f_lower, f_upper, gen.f_lower,
+            numpy.stack([gen.detectors[det].response for det in self._dets]),
+            numpy.stack([gen.detectors[det].location for det in self._dets]),
+            numpy.stack([numpy.asarray(self._data[det].numpy(),
+                                       dtype=numpy.complex128)
+                         for det in self._dets]),
+            psd_arr, norm)
+        self._kmin = self._plan.kmin
+        self._kmax = self._plan.kmax
+        self._f_lower = f_lower
+        self._f_upper = f_upper
+        self._norm = norm
+        # keep the reference's visible side effect: ``model.data`` is whitened
+        kmin, kmax = self._kmin, self._kmax
+        if psds is None:
+            self._weight = {det: numpy.sqrt(norm) * numpy.ones(N)
+                            for det in self._dets}
+        else:
+            with numpy.errstate(divide='ignore'):
+                self._weight = {det: numpy.sqrt(norm / psd_arr[i])
+                                for i, det in enumerate(self._dets)}
+        for det in self._dets:
+            self._data[det][kmin:kmax] = self._data[det][kmin:kmax] * \
+                self._weight[det][kmin:kmax]
+
+    # -- introspection ------------------------------------------------------
+    @property
+    def plan(self):
+        """The CUDA plan (device tables + workspace) behind this model."""
+        return self._plan
+
+    @property
+    def detectors(self):
+        return list(self._dets)
+
+    @property
+    def _extra_stats(self):
+        return ['loglr'] + \
+               ['{}_cplx_loglr'.format(det) for det in self._data] + \
+               ['{}_optimal_snrsq'.format(det) for det in self._data]
+
+    # -- lognl ------------------------------------------------------------
+    def _lognl(self):
+        return float(self._plan.lognl)
+
+    def det_lognl(self, det):
+        return float(self._plan.det_lognl[self._dets.index(det)])
+
+    # -- scalar protocol ----------------------------------------------------
+    def _static_for_kernel(self):
+        static = dict(self._waveform_generator.frozen_params)
+        static.update(self._static_params)
+        return static
+
+    def _kernel_call(self, params, W, skip=None):
+        P = param_matrix(params, W, static=self._static_for_kernel())
+        return self._plan.loglr_host(P, mode=self._mode, skip=skip)
+
+    def _nowaveform_loglr(self):
+        for det in self._data:
+            setattr(self._current_stats, 'loglikelihood', -numpy.inf)
+            setattr(self._current_stats, '{}_cplx_loglr'.format(det),
+                    -numpy.inf)
+            setattr(self._current_stats, '{}_optimal_snrsq'.format(det), 0.)
+        return -numpy.inf
+
+    def _loglr(self):
+        lr, hd, hh = self._kernel_call(self.current_params, 1)
+        if lr[0] == -numpy.inf:
+            return self._nowaveform_loglr()
+        for i, det in enumerate(self._dets):
+            setattr(self._current_stats, '{}_optimal_snrsq'.format(det),
+                    float(hh[0, i]))
+            setattr(self._current_stats, '{}_cplx_loglr'.format(det),
+                    complex(hd[0, i] - 0.5 * hh[0, i]))
+        self._current_stats.loglikelihood = float(lr[0]) + self.lognl
+        return float(lr[0])
+
+    def _loglikelihood(self):
+        return self.loglr + self.lognl
+
+    def det_cplx_loglr(self, det):
+        try:
+            return getattr(self._current_stats, '{}_cplx_loglr'.format(det))
+        except AttributeError:
+            self.loglr
+            return getattr(self._current_stats, '{}_cplx_loglr'.format(det))
+
+    def det_optimal_snrsq(self, det):
+        try:
+            return getattr(self._current_stats, '{}_optimal_snrsq'.format(det))
+        except AttributeError:
+            self.loglr
+            return getattr(self._current_stats, '{}_optimal_snrsq'.format(det))
+
+    # -- batched protocol -----------------------------------------------------
+    def _det_stats(self, hd, hh, dead):
+        out = OrderedDict()
+        for i, det in enumerate(self._dets):
+            c = hd[:, i] - 0.5 * hh[:, i]
+            c[dead] = -numpy.inf
+            out['{}_cplx_loglr'.format(det)] = c
+            out['{}_optimal_snrsq'.format(det)] = hh[:, i]
+        return out
+
+    def _batch_callstat(self, callstat, params, W, skip, logp, stats):
+        if callstat not in ('logposterior', 'loglikelihood', 'loglr', 'logplr'):
+            raise ValueError("unsupported callstat %r" % callstat)
+        lr, hd, hh = self._kernel_call(params, W, skip=skip)
+        lognl = self.lognl
+        dead = numpy.isneginf(lr)
+        logl = lr + lognl
+        extra = self._det_stats(hd, hh, dead)
+        extra['loglr'] = lr
+        extra['loglikelihood'] = logl
+        for k, v in extra.items():
+            if k in stats:
+                if skip is not None and skip.any():
+                    v = numpy.where(skip, numpy.nan, v)
+                stats[k] = v
+        if callstat == 'loglr':
+            return lr
+        if callstat == 'loglikelihood':
+            return logl
+        base = lr if callstat == 'logplr' else logl
+        return numpy.where(skip, -numpy.inf, logp + numpy.where(skip, 0., base))

@@ -1,0 +1,147 @@
+"""Waveform-generator shim with the interface of
+``pycbc.waveform.generator.FDomainDetFrameGenerator`` as the reference builds it
+(``gwin/models/base_data.py:224-230``, ``test/utils/waveform.py:64-65``).
+
+The object carries *configuration* (epoch, detectors, delta_f, f_lower,
+approximant, frozen parameters).  On the likelihood path nothing here generates
+an array: ``GaussianNoise`` hands the configuration to the CUDA plan, whose
+kernel produces ``h_det(f_k)`` on the fly per frequency bin.  ``generate`` is
+provided for the other users of the interface (building injections, plotting a
+waveform): it runs the ``generate_kernel`` of the same CUDA library and copies
+the detector-frame series back.
+"""
+import math
+from collections import OrderedDict
+
+import numpy
+
+from . import _lib
+from .detector import Detector
+from .types import FrequencySeries
+
+MTSUN_SI = 4.925491025543575903411922162094833998e-6
+
+#: waveform parameter order of a row of the kernel's parameter matrix, with the
+#: defaults pycbc's ``get_fd_waveform`` applies to parameters that are not given
+WAVEFORM_PARAMS = OrderedDict([
+    ("mass1", None), ("mass2", None), ("spin1z", 0.0), ("spin2z", 0.0),
+    ("distance", 1.0), ("inclination", 0.0), ("coa_phase", 0.0),
+    ("ra", None), ("dec", None), ("polarization", None), ("tc", None)])
+
+SUPPORTED_APPROXIMANTS = ("TaylorF2",)
+
+
+class NoWaveformError(Exception):
+    """No waveform could be generated for the given parameters
+    (``pycbc.waveform.NoWaveformError``, caught at gaussian_noise.py:323)."""
+
+
+class FDomainCBCGenerator(object):
+    """Marker for "radiation-frame frequency-domain CBC generator"."""
+    name = "fd_cbc"
+
+
+def select_waveform_generator(approximant):
+    """``pycbc.waveform.generator.select_waveform_generator``."""
+    if approximant in SUPPORTED_APPROXIMANTS:
+        return FDomainCBCGenerator
+    raise ValueError("approximant %r is not supported by the CUDA path "
+                     "(supported: %s)" % (approximant,
+                                          ", ".join(SUPPORTED_APPROXIMANTS)))
+
+
+def taylorf2_fisco(mass1, mass2):
+    """f_ISCO = 6^(-3/2) / (pi M) as lalsimulation's TaylorF2 computes it."""
+    piM = math.pi * ((mass1 + mass2) * MTSUN_SI)
+    v_isco = 1.0 / math.sqrt(6.0)
+    return v_isco * v_isco * v_isco / piM
+
+
+def taylorf2_length(mass1, mass2, delta_f):
+    """len(h) of the TaylorF2 series: ``int(f_ISCO/delta_f + 1)``."""
+    return int(taylorf2_fisco(mass1, mass2) / delta_f + 1)
+
+
+def param_matrix(params, W, static=None):
+    """Assemble the kernel's [W, 11] parameter matrix from a dict of scalars
+    and/or [W] arrays (plus ``static`` defaults)."""
+    out = numpy.empty((W, len(WAVEFORM_PARAMS)), dtype=numpy.float64)
+    for i, (name, default) in enumerate(WAVEFORM_PARAMS.items()):
+        if name in params:
+            v = params[name]
+        elif static is not None and name in static:
+            v = static[name]
+        elif default is not None:
+            v = default
+        else:
+            raise ValueError("waveform parameter %r was not provided" % name)
+        out[:, i] = v
+    return out
+
+
+class FDomainDetFrameGenerator(object):
+    location_args = set(['tc', 'ra', 'dec', 'polarization'])
+
+    def __init__(self, rframe_generator_class, epoch, detectors=None,
+                 variable_args=(), recalib=None, gates=None, **frozen_params):
+        if rframe_generator_class is not FDomainCBCGenerator:
+            raise ValueError("only FDomainCBCGenerator is supported")
+        if recalib or gates:
+            raise NotImplementedError("recalibration / gating are outside the "
+                                      "CUDA hot path (SURVEY.md 8f-4)")
+        if not detectors:
+            raise ValueError("at least one detector is required")
+        approximant = frozen_params.pop("approximant", "TaylorF2")
+        select_waveform_generator(approximant)
+        try:
+            self.delta_f = float(frozen_params.pop("delta_f"))
+            self.f_lower = float(frozen_params.pop("f_lower"))
+        except KeyError as e:
+            raise ValueError("%s must be provided" % e)
+        frozen_params.pop("delta_t", None)
+        self.approximant = approximant
+        self._epoch = float(epoch)
+        self.detectors = OrderedDict((d, Detector(d)) for d in detectors)
+        self.detector_names = list(self.detectors.keys())
+        self.variable_args = tuple(variable_args)
+        self.frozen_params = dict(frozen_params)
+        self.current_params = dict(frozen_params)
+        self._plans = {}
+
+    @property
+    def epoch(self):
+        return self._epoch
+
+    @property
+    def static_args(self):
+        return self.frozen_params
+
+    def _plan_for(self, n_f, device):
+        key = (n_f, device)
+        if key not in self._plans:
+            nd = len(self.detectors)
+            self._plans.clear()
+            self._plans[key] = _lib.Plan(
+                device, self.delta_f, self._epoch, self.f_lower, None,
+                self.f_lower,
+                numpy.stack([d.response for d in self.detectors.values()]),
+                numpy.stack([d.location for d in self.detectors.values()]),
+                numpy.zeros((nd, n_f), dtype=numpy.complex128), None, None)
+        return self._plans[key]
+
+    def generate(self, device=0, **kwargs):
+        """Returns ``{det: FrequencySeries}`` of length ``int(f_ISCO/df + 1)``
+        (CUDA ``generate_kernel``)."""
+        self.current_params.update(kwargs)
+        row = param_matrix(self.current_params, 1)
+        n = taylorf2_length(row[0, 0], row[0, 1], self.delta_f)
+        if not (row[0, 0] > 0 and row[0, 1] > 0) or \
+                taylorf2_fisco(row[0, 0], row[0, 1]) <= self.f_lower:
+            # lalsimulation: "f_max <= fStart" is a domain error
+            raise NoWaveformError("f_ISCO is not above f_lower for these masses")
+        n_f = max(((n + 1023) // 1024) * 1024 + 1,
+                  int(self.f_lower / self.delta_f) + 9)
+        h, length = self._plan_for(n_f, device).generate(row[0])
+        return OrderedDict(
+            (det, FrequencySeries(h[i, :length], self.delta_f, self._epoch))
+            for i, det in enumerate(self.detector_names))

@@ -1,0 +1,136 @@
+/*
+ * gwin_b200 -- C ABI of the B200-native batched log-likelihood-ratio path.
+ *
+ * The reference (gwastro/gwin) is pure Python and has no FFI; its "plugin API"
+ * for this path is the model protocol (gwin/models/gaussian_noise.py:219-350,
+ * gwin/models/marginalized_gaussian_noise.py:456-511) called through
+ * CallModel (gwin/models/__init__.py:101-137) by pool.map.  This header is the
+ * C boundary a maintainer would bind beneath those classes (ctypes stub in
+ * INTEGRATION.md).  Plain pointers and sizes only; no torch types.
+ *
+ * All functions return 0 on success or a negative GWIN_E* code; the message of
+ * the last failure on the calling thread is available from gwin_last_error().
+ * No exceptions cross the ABI.
+ */
+#ifndef GWIN_B200_H
+#define GWIN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GWIN_OK            0
+#define GWIN_EINVAL       -1   /* bad argument (mirrors the reference's ValueError) */
+#define GWIN_ECUDA        -2   /* CUDA runtime failure */
+#define GWIN_ENOMEM       -3
+#define GWIN_ENODEVICE    -4   /* no usable sm_100 device: there is NO CPU fallback */
+
+#define GWIN_MAX_DET       4
+#define GWIN_NPARAM       11   /* per-walker parameter row, see gwin_loglr_batch */
+
+/* loglr flavour */
+#define GWIN_MODE_GAUSSIAN     0  /* gaussian_noise.py:304-350:  sum_det Re<d|h> - <h|h>/2        */
+#define GWIN_MODE_MARG_PHASE   1  /* marginalized_gaussian_noise.py:456-459, 461-511:
+                                     log I0(|sum_det <d|h>|) - sum_det <h|h>/2                     */
+
+/* kernel selection (diagnostic; production uses GWIN_KERNEL_AUTO) */
+#define GWIN_KERNEL_AUTO       0
+#define GWIN_KERNEL_DIRECT     1  /* per-bin FP64 phase + sincos                                  */
+#define GWIN_KERNEL_RECURRENCE 2  /* block-anchored chirp-phasor recurrence + Horner accumulation */
+
+typedef struct gwin_plan gwin_plan;
+
+/*
+ * Plan build == GaussianNoise.__init__ (gaussian_noise.py:219-265):
+ *   kmin,kmax = get_cutoff_indices(f_lower, f_upper, delta_f, (n_f-1)*2)   :247
+ *   weight    = sqrt(norm/psd), norm defaults to 4*delta_f                  :251-262
+ *   data[kmin:kmax] *= weight[kmin:kmax]                                    :264-265
+ * and the lazily cached lognl (:275-291).  The plan keeps device replicas of
+ * the (over-whitened, conjugated, amplitude-pre-scaled) data tables; the
+ * caller's arrays are only read (the reference copies them, base_data.py:87).
+ *
+ *   device          CUDA ordinal
+ *   n_det           1..GWIN_MAX_DET detectors
+ *   n_f             bins per frequency series (all detectors equal, :240-242)
+ *   delta_f         bin spacing [Hz]
+ *   epoch_gps       data epoch == waveform-generator epoch (:235-238)
+ *   f_lower         likelihood low-frequency cutoff; f_upper <= 0 means None
+ *   f_lower_wf      waveform generator's f_lower (bins < ceil(f_lower_wf/df) are 0)
+ *   det_response    [n_det][9] row-major detector response tensors
+ *   det_location    [n_det][3] vertex locations [m], Earth-fixed frame
+ *   data            [n_det][n_f][2] host, (re,im) interleaved, un-whitened d~(f)
+ *   psd             [n_det][n_f] host, or NULL for unit PSD (:254-256)
+ *   norm            <= 0 selects the default 4*delta_f
+ */
+int gwin_plan_create(gwin_plan** out, int device, int n_det, int64_t n_f,
+                     double delta_f, double epoch_gps,
+                     double f_lower, double f_upper, double f_lower_wf,
+                     const double* det_response, const double* det_location,
+                     const double* data, const double* psd, double norm);
+
+void gwin_plan_destroy(gwin_plan* plan);
+
+/* kmin, kmax as computed by the plan (gaussian_noise.py:247-250). */
+int gwin_plan_cutoffs(const gwin_plan* plan, int64_t* kmin, int64_t* kmax);
+
+/* lognl (gaussian_noise.py:275-291): total and per detector [n_det]. */
+int gwin_plan_lognl(const gwin_plan* plan, double* lognl_total, double* lognl_det);
+
+/* Tuning knobs: kernel = GWIN_KERNEL_*, phase_tol = max block-polynomial phase
+ * error [rad] of the recurrence kernel (default 1e-11), mchirp_min [Msun] =
+ * smallest chirp mass the block schedule must cover (default 0.5). */
+int gwin_plan_configure(gwin_plan* plan, int kernel, double phase_tol, double mchirp_min);
+
+/*
+ * One batched evaluation of GaussianNoise._loglr / MarginalizedGaussianNoise._loglr
+ * for W parameter points (what pool.map(CallModel, points) computes one point at a
+ * time in the reference).  All pointers are DEVICE pointers on the plan's device.
+ *
+ *   params  [W][GWIN_NPARAM] row-major:
+ *           mass1, mass2 [Msun], spin1z, spin2z, distance [Mpc], inclination,
+ *           coa_phase, ra, dec, polarization [rad], tc [GPS s]
+ *   skip    [W] or NULL; nonzero = prior was -inf, do not evaluate
+ *           (base.py:556-568 / base_data.py:128-141 short-circuit): loglr=-inf
+ *   loglr   [W]
+ *   hd      [W][n_det][2] complex <d|h> per detector ({det}_cplx_loglr + hh/2, or
+ *           {det}_matchedfilter_snrsq); may be NULL
+ *   hh      [W][n_det] <h|h> per detector ({det}_optimal_snrsq); may be NULL
+ *   stream  cudaStream_t (0 = legacy default stream).  Asynchronous.
+ *
+ * Calls on one plan share its workspace and must be issued on one stream at a time.
+ * Points with non-finite / non-physical parameters return loglr = -inf, never NaN.
+ */
+int gwin_loglr_batch(gwin_plan* plan, int mode, int64_t W,
+                     const double* params, const uint8_t* skip,
+                     double* loglr, double* hd, double* hh, void* stream);
+
+/* Same, with HOST buffers: pinned staging, H2D, kernels, D2H, synchronise. */
+int gwin_loglr_batch_host(gwin_plan* plan, int mode, int64_t W,
+                          const double* params, const uint8_t* skip,
+                          double* loglr, double* hd, double* hh);
+
+/*
+ * FDomainDetFrameGenerator.generate (the call at gaussian_noise.py:322) for ONE
+ * parameter point: writes the detector-frame waveforms h_det(f_k), un-whitened,
+ * to a host buffer [n_det][n_f][2]; bins at and beyond the waveform's own length
+ * are zero.  *length receives that length (len(h) in gaussian_noise.py:328).
+ */
+int gwin_generate_host(gwin_plan* plan, const double* params, double* h_out,
+                       int64_t* length);
+
+/* Kernel launches issued by the last gwin_loglr_batch* call on this plan. */
+int gwin_plan_last_launches(const gwin_plan* plan);
+
+/* FP64 issue-rate micro-benchmark on the plan's device: runs a dependent-chain-free
+ * DFMA loop and returns achieved FP64 FMA lane-ops per second. */
+int gwin_fp64_peak(int device, double* dfma_per_sec);
+
+const char* gwin_last_error(void);
+const char* gwin_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GWIN_B200_H */

@@ -1,0 +1,314 @@
+"""numpy model of the CUDA kernels' arithmetic (test aid, runs without a GPU).
+
+Mirrors ``gwin_b200/csrc/gwin_cuda.cu`` step by step -- table build, per-walker
+coefficient folding, the direct per-bin evaluation and the block-anchored
+quartic phasor recurrence with its block schedule -- so that the *algorithm*
+(not the CUDA code generation) can be checked against the oracle on the CPU:
+coefficient folding, node placement, forward differences, the phase-error bound
+of the schedule.  It is not part of the product and is not an oracle.
+"""
+import math
+
+import numpy as np
+
+PI = math.pi
+TWOPI = 2 * math.pi
+GAMMA = 0.577215664901532860606512090082402431
+C_SI = 299792458.0
+MTSUN = 4.925491025543575903411922162094833998e-6
+MRSUN = 1.476625061404649406193430731479084713e3
+PC_SI = 3.085677581491367278913937957796471611e16
+LEAPS = (46828800, 78364801, 109900802, 173059203, 252028804, 315187205,
+         346723206, 394156807, 425692808, 457228809, 504489610, 551750411,
+         599184012, 820108813, 914803214, 1025136015, 1119744016, 1167264017)
+MAX_BLOCK, MIN_BLOCK = 256, 8
+
+
+class PlanModel(object):
+    def __init__(self, delta_f, epoch, f_lower, f_upper, f_lower_wf, resp, loc,
+                 data, psd, norm=None, phase_tol=1e-10, mchirp_min=0.5):
+        data = np.asarray(data, dtype=np.complex128)
+        self.n_det, self.n_f = data.shape
+        n_f = self.n_f
+        N = (n_f - 1) * 2
+        self.kmin = int(f_lower / delta_f) if f_lower else 1
+        self.kmax = int((N + 1) / 2.)
+        if f_upper:
+            self.kmax = min(int(f_upper / delta_f), self.kmax)
+        self.istart = max(int(math.ceil(f_lower_wf / delta_f)), 1)
+        self.f_lower_wf = f_lower_wf
+        self.delta_f, self.epoch = delta_f, epoch
+        self.gps_utc = sum(1 for t in LEAPS if math.floor(epoch) >= t)
+        self.resp = np.asarray(resp, dtype=float).reshape(self.n_det, 3, 3)
+        self.loc = np.asarray(loc, dtype=float).reshape(self.n_det, 3)
+        if norm is None:
+            norm = 4.0 * delta_f
+        ld = np.longdouble
+        k = np.arange(n_f)
+        f = k.astype(ld) * ld(delta_f)
+        f[0] = 1.0
+        x = np.cbrt(f)
+        self.bx = x.astype(float)
+        self.bxm5 = (1 / x ** 5).astype(float)
+        self.blx = np.log(x).astype(float)
+        band = (k >= self.kmin) & (k < self.kmax)
+        x7 = x ** 7
+        f73 = np.where(band, 1 / x7, 0)
+        f76 = np.where(band, 1 / np.sqrt(x7), 0)
+        self.T = np.zeros((self.n_det, n_f), dtype=np.complex128)
+        self.C = np.zeros((self.n_det, n_f + 1))
+        self.lognl_det = np.zeros(self.n_det)
+        for d in range(self.n_det):
+            w2 = np.where(band, ld(norm) / np.where(band, psd[d], 1).astype(ld)
+                          if psd is not None else ld(norm), 0)
+            dd = data[d]
+            self.T[d] = (dd.real.astype(ld) * w2 * f76).astype(float) - \
+                1j * (dd.imag.astype(ld) * w2 * f76).astype(float)
+            self.C[d, 1:] = np.cumsum(f73 * w2).astype(float)
+            self.lognl_det[d] = float(-0.5 * np.sum(
+                (dd.real.astype(ld) ** 2 + dd.imag.astype(ld) ** 2) * w2))
+        self.phase_tol, self.mchirp_min = phase_tol, mchirp_min
+        self.blk_start = self.build_schedule()
+
+    def build_schedule(self):
+        band0 = max(self.kmin, self.istart)
+        K5 = (5. / 3) * (8. / 3) * (11. / 3) * (14. / 3) * (17. / 3)
+        pref = 2.0 * (3. / 128.) * (PI * self.mchirp_min * MTSUN) ** (-5. / 3) * K5 \
+            * self.delta_f ** 5
+        out = []
+        k = max(band0, 1)
+        while k < self.kmax:
+            f = k * self.delta_f
+            d5 = pref * f ** (-20. / 3)
+            B = (self.phase_tol * 120.0 / (0.005 * d5)) ** 0.2 + 1.0
+            Bi = int(min(B, MAX_BLOCK))
+            # too curved for an 8-bin quartic: 4-bin blocks take the direct path
+            Bi = (Bi & ~3) if Bi >= MIN_BLOCK else 4
+            if k + Bi > self.kmax:
+                Bi = self.kmax - k
+            out.append(k)
+            k += Bi
+        out.append(self.kmax)
+        if len(out) - 1 >= 2 and out[-1] - out[-2] < MIN_BLOCK and \
+                out[-2] - out[-3] >= MIN_BLOCK:
+            del out[-2]
+        return out
+
+    # -- walker_setup_kernel --------------------------------------------------
+    def walker(self, p):
+        m1, m2, chi1, chi2, dist, incl, phic, ra, dec, psi, tc = [float(v) for v in p]
+        mtot = m1 + m2
+        dm = (m1 - m2) / (m1 + m2)
+        eta = m1 * m2 / mtot / mtot
+        m1M, m2M = m1 / mtot, m2 / mtot
+        pfaN = 3.0 / (128.0 * eta)
+        v2 = 5.0 * (743.0 / 84.0 + 11.0 * eta) / 9.0
+        v3 = -16.0 * PI
+        v4 = 5.0 * (3058.673 / 7.056 + 5429.0 / 7.0 * eta + 617.0 * eta * eta) / 72.0
+        v5 = 5.0 / 9.0 * (7729.0 / 84.0 - 13.0 * eta) * PI
+        vl5 = 5.0 / 3.0 * (7729.0 / 84.0 - 13.0 * eta) * PI
+        v6 = (11583.231236531 / 4.694215680 - 640.0 / 3.0 * PI * PI - 6848.0 / 21.0 * GAMMA) \
+            + eta * (-15737.765635 / 3.048192 + 2255.0 / 12.0 * PI * PI) \
+            + eta * eta * 76055.0 / 1728.0 - eta * eta * eta * 127825.0 / 1296.0
+        v6 += (-6848.0 / 21.0) * math.log(4.0)
+        vl6 = -6848.0 / 21.0
+        v7 = PI * (77096675.0 / 254016.0 + 378515.0 / 1512.0 * eta - 74045.0 / 756.0 * eta * eta)
+        SL = m1M * m1M * chi1 + m2M * m2M * chi2
+        dSigmaL = dm * (m2M * chi2 - m1M * chi1)
+        pn_sigma = eta * (721.0 / 48.0 * chi1 * chi2 - 247.0 / 48.0 * chi1 * chi2)
+        pn_sigma += 719.0 / 96.0 * m1M * m1M * chi1 * chi1
+        pn_sigma += 719.0 / 96.0 * m2M * m2M * chi2 * chi2
+        pn_sigma -= 233.0 / 96.0 * m1M * m1M * chi1 * chi1
+        pn_sigma -= 233.0 / 96.0 * m2M * m2M * chi2 * chi2
+        pn_ss3 = (326.75 / 1.12 + 557.5 / 1.8 * eta) * eta * chi1 * chi2
+        pn_ss3 += ((4703.5 / 8.4 + 2935.0 / 6.0 * m1M - 120.0 * m1M * m1M)
+                   + (-4108.25 / 6.72 - 108.5 / 1.2 * m1M + 125.5 / 3.6 * m1M * m1M)) * m1M * m1M * chi1 * chi1
+        pn_ss3 += ((4703.5 / 8.4 + 2935.0 / 6.0 * m2M - 120.0 * m2M * m2M)
+                   + (-4108.25 / 6.72 - 108.5 / 1.2 * m2M + 125.5 / 3.6 * m2M * m2M)) * m2M * m2M * chi2 * chi2
+        pn_gamma = (554345.0 / 1134.0 + 110.0 * eta / 9.0) * SL + (13915.0 / 84.0 - 10.0 * eta / 3.0) * dSigmaL
+        v7 += (-8980424995.0 / 762048.0 + 6586595.0 * eta / 756.0 - 305.0 * eta * eta / 36.0) * SL \
+            - (170978035.0 / 48384.0 - 2876425.0 * eta / 672.0 - 4735.0 * eta * eta / 144.0) * dSigmaL
+        v6 += PI * (3760.0 * SL + 1490.0 * dSigmaL) / 3.0 + pn_ss3
+        v5 += -pn_gamma
+        vl5 += -3.0 * pn_gamma
+        v4 += -10.0 * pn_sigma
+        v3 += 188.0 * SL / 3.0 + 25.0 * dSigmaL
+        piM = PI * (mtot * MTSUN)
+        m3 = piM ** (1. / 3)
+        m3 = float(np.cbrt(piM))
+        lm3 = math.log(m3)
+        s = pfaN / TWOPI
+        im3 = 1.0 / m3
+        w = {}
+        w['a0'] = s * im3 ** 5
+        w['a2'] = s * v2 * im3 ** 3
+        w['a3'] = s * v3 * im3 ** 2
+        w['a4'] = s * v4 * im3
+        w['a5'] = s * (v5 + vl5 * lm3) - (2.0 * phic + 0.25 * PI) / TWOPI
+        w['b5'] = s * vl5
+        w['a6'] = s * (v6 + vl6 * lm3) * m3
+        w['b6'] = s * vl6 * m3
+        w['a7'] = s * v7 * m3 * m3
+        vI = 1.0 / math.sqrt(6.0)
+        fisco = vI * vI * vI / piM
+        n = int(fisco / self.delta_f + 1.0)
+        w['valid'] = fisco > self.f_lower_wf
+        w['ke'] = min(n, self.kmax)
+        w['ks'] = max(self.kmin, self.istart)
+        r = dist * 1e6 * PC_SI
+        amp0 = -4.0 * m1 * m2 / r * MRSUN * MTSUN * math.sqrt(PI / 12.0)
+        ampfac = amp0 * math.sqrt(5.0 / (32.0 * eta)) * (im3 ** 3 / math.sqrt(m3))
+        cfac = math.cos(incl)
+        pfac = 0.5 * (1.0 + cfac * cfac)
+        # XLALGreenwichMeanSiderealTime with LAL's integer-second Julian day
+        sec = math.floor(tc)
+        ns = round((tc - sec) * 1e9)
+        if ns >= 1000000000:
+            sec += 1
+            ns -= 1000000000
+        utc = int(sec) - int(self.gps_utc)
+        days, sod = divmod(utc, 86400)
+        jd = (2444245 + days) + sod / 86400.0 - 0.5
+        t_hi = (jd - 2451545.0) / 36525.0
+        t_lo = ns / (1e9 * 36525.0 * 86400.0)
+        tj = t_hi + t_lo
+        sid = (-6.2e-6 * tj + 0.093104) * tj * tj + 67310.54841
+        sid += 8640184.812866 * t_lo
+        sid += 3155760000.0 * t_lo
+        sid += 8640184.812866 * t_hi
+        sid += 3155760000.0 * t_hi
+        gmst = sid * PI / 43200.0
+        gha = gmst - ra
+        sg, cg = math.sin(gha), math.cos(gha)
+        sd, cd = math.sin(dec), math.cos(dec)
+        sp, cp = math.sin(psi), math.cos(psi)
+        X = np.array([-cp * sg - sp * cg * sd, -cp * cg + sp * sg * sd, sp * cd])
+        Y = np.array([sp * sg - cp * cg * sd, sp * cg + cp * sg * sd, cp * cd])
+        eh = np.array([cd * cg, -cd * sg, sd])
+        w['tau'], w['A'], w['hh'] = [], [], []
+        for d in range(self.n_det):
+            dx, dy = self.resp[d].dot(X), self.resp[d].dot(Y)
+            fp = (X * dx - Y * dy).sum()
+            fc = (X * dy + Y * dx).sum()
+            delay = -(self.loc[d].dot(eh)) / C_SI
+            dt = (tc + delay) - self.epoch
+            tau = dt * self.delta_f
+            tau = tau - round(tau)
+            A = complex(fp * pfac * ampfac, -fc * cfac * ampfac)
+            w['tau'].append(tau)
+            w['A'].append(A)
+            hh = 0.0
+            if w['ke'] > w['ks']:
+                hh = abs(A) ** 2 * (self.C[d, w['ke']] - self.C[d, w['ks']])
+            w['hh'].append(hh)
+        return w
+
+    def phase_turns(self, w, k):
+        x, xm5, lx = self.bx[k], self.bxm5[k], self.blx[k]
+        lo = (w['a4'] * x + w['a3']) * x + w['a2']
+        lo = (lo * (x * x) + w['a0']) * xm5
+        l5 = w['b5'] * lx + w['a5']
+        l6 = w['b6'] * lx + w['a6']
+        return lo + ((w['a7'] * x + l6) * x + l5)
+
+    def finish(self, w, S, marg=False):
+        hd = np.array([w['A'][d] * S[d] for d in range(self.n_det)])
+        hh = np.array(w['hh'])
+        if marg:
+            from scipy import special
+            mf = abs(hd.sum())
+            lr = mf + math.log(special.i0e(mf)) - 0.5 * hh.sum()
+        else:
+            lr = float((hd.real - 0.5 * hh).sum())
+        return lr, hd, hh
+
+    # -- loglr_direct_kernel ------------------------------------------------------
+    def loglr_direct(self, p, marg=False):
+        w = self.walker(p)
+        if not w['valid']:
+            return -np.inf, None, None
+        ks, ke = w['ks'], w['ke']
+        S = np.zeros(self.n_det, dtype=complex)
+        if ke > ks:
+            k = np.arange(ks, ke)
+            psi = self.phase_turns(w, k)
+            for d in range(self.n_det):
+                ph = psi + np.modf(k * w['tau'][d])[0]
+                ph = ph - np.rint(ph)
+                S[d] = np.sum(self.T[d, ks:ke] * np.exp(-2j * PI * ph))
+        return self.finish(w, S, marg)
+
+    # -- loglr_recur_kernel -------------------------------------------------------
+    def loglr_recur(self, p, marg=False, return_phase_err=False):
+        w = self.walker(p)
+        if not w['valid']:
+            return -np.inf, None, None
+        ks, ke = w['ks'], w['ke']
+        S = np.zeros(self.n_det, dtype=complex)
+        max_err = 0.0
+        bs = self.blk_start
+        for b in range(len(bs) - 1):
+            kb, kn = bs[b], bs[b + 1]
+            if kn <= ks or kb >= ke:
+                continue
+            B = kn - kb
+            j = np.arange(B)
+            k = kb + j
+            on = (k >= ks) & (k < ke)
+            if B < 5:
+                psi = self.phase_turns(w, k)
+                for d in range(self.n_det):
+                    ph = psi + k * w['tau'][d]
+                    S[d] += np.sum(np.where(on, self.T[d, k], 0) * np.exp(-2j * PI * ph))
+                continue
+            e = B - 1
+            t1 = (e + 4) // 8
+            t2 = e // 2
+            t3 = e - t1
+            nodes = np.array([0, t1, t2, t3, e])
+            fv = self.phase_turns(w, kb + nodes)
+            x1, x2, x3, x4 = float(t1), float(t2), float(t3), float(e)
+            d01 = (fv[1] - fv[0]) / x1
+            d12 = (fv[2] - fv[1]) / (x2 - x1)
+            d23 = (fv[3] - fv[2]) / (x3 - x2)
+            d34 = (fv[4] - fv[3]) / (x4 - x3)
+            d012 = (d12 - d01) / x2
+            d123 = (d23 - d12) / (x3 - x1)
+            d234 = (d34 - d23) / (x4 - x2)
+            d0123 = (d123 - d012) / x3
+            d1234 = (d234 - d123) / (x4 - x1)
+            n4 = (d1234 - d0123) / x4
+            n1, n2, n3 = d01, d012, d0123
+            e1, e2, e3 = x1 + x2 + x3, x1 * x2 + x1 * x3 + x2 * x3, x1 * x2 * x3
+            c4 = n4
+            c3 = n3 - n4 * e1
+            c2 = n2 - n3 * (x1 + x2) + n4 * e2
+            c1 = n1 - n2 * x1 + n3 * (x1 * x2) - n4 * e3
+            D1 = c1 + c2 + c3 + c4
+            D2 = 2.0 * c2 + 6.0 * c3 + 14.0 * c4
+            D3 = 6.0 * c3 + 36.0 * c4
+            D4 = 24.0 * c4
+            if return_phase_err:
+                exact = self.phase_turns(w, k)
+                poly = fv[0] + j * (c1 + j * (c2 + j * (c3 + j * c4)))
+                max_err = max(max_err, float(np.max(np.abs(exact - poly)[on])) * TWOPI
+                              if on.any() else 0.0)
+            tq = np.exp(2j * PI * D4)
+            for d in range(self.n_det):
+                Tk = np.where(on, self.T[d, k], 0)
+                g = np.exp(2j * PI * (D1 + w['tau'][d]))
+                rq = np.exp(2j * PI * D2)
+                sq = np.exp(2j * PI * D3)
+                acc = Tk[0]
+                for jj in range(1, B):
+                    acc = acc * g + Tk[jj]
+                    g = g * rq
+                    rq = rq * sq
+                    sq = sq * tq
+                kend = kb + e
+                anchor = fv[4] + np.modf(kend * w['tau'][d])[0]
+                S[d] += acc * np.exp(-2j * PI * anchor)
+        out = self.finish(w, S, marg)
+        if return_phase_err:
+            return out + (max_err,)
+        return out

@@ -1,0 +1,258 @@
+"""CUDA path vs the CPU oracle, through the C ABI (``-m gpu``).
+
+Tolerance (BASELINE.json north_star): |d loglr| <= 1e-6 absolute, 1e-9 relative
+for loglr >> 1.  Both kernels (direct per-bin sincos, block recurrence) are held
+to it, and to each other at sizes the oracle cannot reach.
+"""
+import numpy as np
+import pytest
+
+import util
+from util import PARAM_ORDER, tol
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = {"direct": 1, "recurrence": 2}
+
+
+def _oracle_batch(orc, P):
+    import gwin_oracle as O
+    return O.batch_loglr(orc, P)
+
+
+def _check(lr, hd, hh, lr0, hd0, hh0, what=""):
+    assert np.all(np.isfinite(lr)), what
+    err = np.abs(lr - lr0)
+    assert np.all(err <= tol(lr0)), "%s: max |dloglr| %.3e at %d (loglr %.6f)" % (
+        what, err.max(), err.argmax(), lr0[err.argmax()])
+    # the per-detector stats obey the same bound
+    assert np.all(np.abs(hh - hh0) <= np.maximum(1e-6, 1e-9 * np.abs(hh0))), what
+    assert np.all(np.abs(hd - hd0) <= np.maximum(2e-6, 2e-9 * np.abs(hh0))), what
+
+
+@pytest.fixture(scope="module")
+def cfg1():
+    return util.c1()
+
+
+@pytest.fixture(scope="module")
+def cfg2():
+    return util.c2()
+
+
+@pytest.fixture(scope="module")
+def cfg3():
+    return util.c3()
+
+
+@pytest.mark.parametrize("kernel", sorted(KERNELS))
+def test_c1_gaussian_200_walkers(cfg1, kernel):
+    """C1: GaussianNoise loglr, H1+L1, 8 s @ 2048 Hz, 200 emcee walkers."""
+    model = cfg1.cuda_model()
+    model.plan.configure(kernel=KERNELS[kernel])
+    rng = np.random.default_rng(20182)
+    P = util.draw_bbh(rng, 200, cfg1)
+    P[0] = util.inj_row(cfg1)
+    lr, hd, hh = model.plan.loglr_host(P)
+    lr0, hd0, hh0 = _oracle_batch(cfg1.oracle(), P)
+    _check(lr, hd, hh, lr0, hd0, hh0, "C1 " + kernel)
+    assert abs(model.lognl - cfg1.oracle().lognl()) <= 1e-9 * abs(model.lognl)
+
+
+@pytest.mark.parametrize("kernel", sorted(KERNELS))
+def test_c2_marginalized_phase(cfg2, kernel):
+    """C2: phase-marginalised model, H1+L1+V1."""
+    from gwin_b200 import models
+    model = cfg2.cuda_model(cls=models.MarginalizedPhaseGaussianNoise)
+    model.plan.configure(kernel=KERNELS[kernel])
+    rng = np.random.default_rng(20183)
+    P = util.draw_bbh(rng, 256, cfg2)
+    P[0] = util.inj_row(cfg2)
+    lr, hd, hh = model.plan.loglr_host(P, mode=1)
+    lr0, hd0, hh0 = _oracle_batch(cfg2.oracle(phase_marginalization=True), P)
+    _check(lr, hd, hh, lr0, hd0, hh0, "C2 " + kernel)
+
+
+@pytest.mark.parametrize("kernel", sorted(KERNELS))
+def test_c3_bns_256s(cfg3, kernel):
+    """C3: BNS, 256 s @ 4096 Hz (524 289 bins), coloured noise, 3 detectors."""
+    model = cfg3.cuda_model()
+    model.plan.configure(kernel=KERNELS[kernel])
+    rng = np.random.default_rng(20184)
+    P = util.draw_bns(rng, 24, cfg3)
+    P[0] = util.inj_row(cfg3)
+    lr, hd, hh = model.plan.loglr_host(P)
+    lr0, hd0, hh0 = _oracle_batch(cfg3.oracle(), P)
+    _check(lr, hd, hh, lr0, hd0, hh0, "C3 " + kernel)
+    # and against the extended-precision oracle
+    lrT, _, _ = _oracle_batch(cfg3.oracle(mode="truth"), P[:6])
+    assert np.all(np.abs(lr[:6] - lrT) <= tol(lrT))
+
+
+def test_c3_kernels_agree_full_batch(cfg3):
+    """At BASELINE size (thousands of walkers x 524 289 bins) the oracle is too
+    slow; the two independent kernels must agree with each other instead."""
+    model = cfg3.cuda_model()
+    rng = np.random.default_rng(20185)
+    P = util.draw_bns(rng, 4096, cfg3)
+    model.plan.configure(kernel=1)
+    a = model.plan.loglr_host(P)
+    model.plan.configure(kernel=2)
+    b = model.plan.loglr_host(P)
+    assert np.all(np.abs(a[0] - b[0]) <= tol(a[0]))
+    assert np.all(np.abs(a[1] - b[1]) <= np.maximum(2e-6, 2e-9 * np.abs(a[2])))
+    np.testing.assert_array_equal(a[2], b[2])       # <h|h> is the same closed form
+    # determinism: same call, same bits
+    c = model.plan.loglr_host(P)
+    for x, y in zip(b, c):
+        np.testing.assert_array_equal(x, y)
+    # order invariance: a permuted batch gives permuted, bit-identical results
+    perm = rng.permutation(len(P))
+    d = model.plan.loglr_host(P[perm])
+    np.testing.assert_array_equal(d[0], b[0][perm])
+
+
+def test_gps_epoch(cfg1):
+    """GPS-scale epoch: leap seconds in GMST and the reference's
+    ``tc + time_delay`` rounding at ulp(1e9 s) are reproduced."""
+    cfg = util.c2(epoch=1126259462.0, seed=7)
+    model = cfg.cuda_model()
+    rng = np.random.default_rng(5)
+    P = util.draw_bbh(rng, 64, cfg)
+    for kernel in (1, 2):
+        model.plan.configure(kernel=kernel)
+        lr, hd, hh = model.plan.loglr_host(P)
+        lr0, hd0, hh0 = _oracle_batch(cfg.oracle(), P)
+        _check(lr, hd, hh, lr0, hd0, hh0, "gps epoch k%d" % kernel)
+
+
+def test_zero_noise_identity():
+    """loglr(theta_inj) = 1/2 sum <h|h> in zero noise (cf. the reference
+    docstring gaussian_noise.py:158-164)."""
+    cfg = util.c2(noise=False)
+    model = cfg.cuda_model()
+    lr, hd, hh = model.plan.loglr_host(util.inj_row(cfg)[None, :])
+    assert abs(lr[0] - 0.5 * hh[0].sum()) <= 1e-9 * lr[0]
+    assert np.all(np.abs(hd[0].imag) <= 1e-6 * hh[0])
+
+
+def test_reference_tc_grid_argmax():
+    """The reference's only numeric pin (test/test_models.py:105-117): zero-noise
+    data = injected waveform, 4 s @ 2048 Hz, fmin 30, H1/L1/V1; logplr over the
+    grid tc = 1.1 + arange(8192)/2048 peaks at tc = 3.1."""
+    import gwin_oracle as O
+    from gwin_b200 import models
+    inj = dict(util.BBH_INJ)
+    inj["tc"] = 3.1
+    cfg = util.Config("ref", 4, 2048., 30., ["H1", "L1", "V1"], inj, noise=False)
+    model = cfg.cuda_model(variable_params=("tc",),
+                           static_params={k: v for k, v in inj.items() if k != "tc"})
+    times = 1.1 + np.arange(8192) / 2048.
+    call = models.CallModel(model, "logplr", return_all_stats=False)
+    vals = call.batch(times[:, None]).values
+    assert np.isclose(times[np.argmax(vals)], 3.1)
+    call.callstat = "logposterior"
+    vals = call.batch(times[:, None]).values
+    assert np.isclose(times[np.argmax(vals)], 3.1)
+    # scalar protocol, as the reference test calls it
+    assert np.isclose(call([3.1]), vals[np.argmin(np.abs(times - 3.1))])
+
+
+def test_edge_cases(cfg2):
+    model = cfg2.cuda_model()
+    orc = cfg2.oracle()
+    base = util.inj_row(cfg2)
+    P = np.tile(base, (12, 1))
+    P[1, 0] = P[1, 1] = 150.    # f_ISCO = 14.7 Hz < f_lower: NoWaveformError -> -inf
+    P[2, 0] = P[2, 1] = 100.    # f_ISCO ~ 22 Hz: a handful of bins
+    P[3, 0] = np.nan
+    P[4, 4] = -1.               # negative distance
+    P[5, 1] = 0.
+    P[6, 10] = np.inf
+    P[7, 0], P[7, 1] = 1.0, 1.0  # BNS-like in an 8 s segment: clipped at kmax
+    skip = np.zeros(12, dtype=np.uint8)
+    skip[8] = 1
+    for kernel in (1, 2):
+        model.plan.configure(kernel=kernel)
+        lr, hd, hh = model.plan.loglr_host(P, skip=skip)
+        assert not np.any(np.isnan(lr))
+        for i in (1, 3, 4, 5, 6, 8):
+            assert lr[i] == -np.inf and np.all(hh[i] == 0) and np.all(hd[i] == 0)
+        for i in (0, 2, 7, 9, 10, 11):
+            l0, d0, h0 = orc.loglr(**dict(zip(PARAM_ORDER, P[i])))
+            assert abs(lr[i] - l0) <= tol(l0), (kernel, i, lr[i], l0)
+            assert np.allclose(hh[i], list(h0.values()), rtol=1e-9, atol=1e-9)
+    # W = 0 and W = 1
+    lr, hd, hh = model.plan.loglr_host(np.empty((0, 11)))
+    assert lr.shape == (0,)
+    lr1, _, _ = model.plan.loglr_host(P[:1])
+    assert abs(lr1[0] - orc.loglr(**dict(zip(PARAM_ORDER, P[0])))[0]) <= tol(lr1[0])
+
+
+def test_waveform_below_kmin():
+    """Model f_lower above the end of the waveform: every detector contributes
+    0 and loglr = 0 (gaussian_noise.py:328-333)."""
+    import gwin_oracle as O
+    cfg = util.c1()
+    from gwin_b200 import models
+    from gwin_b200.types import FrequencySeries
+    from gwin_b200.waveform import FDomainCBCGenerator, FDomainDetFrameGenerator
+    gen = FDomainDetFrameGenerator(FDomainCBCGenerator, cfg.epoch, detectors=cfg.dets,
+                                   variable_args=PARAM_ORDER, delta_f=cfg.delta_f,
+                                   f_lower=20., approximant="TaylorF2")
+    data = {d: FrequencySeries(cfg.data[d], cfg.delta_f, cfg.epoch) for d in cfg.dets}
+    model = models.GaussianNoise(PARAM_ORDER, data, gen, 100., psds=cfg.psds())
+    row = util.inj_row(cfg)        # 30+30: f_ISCO = 73 Hz < 100 Hz
+    lr, hd, hh = model.plan.loglr_host(row[None, :])
+    assert lr[0] == 0.0 and np.all(hh == 0) and np.all(hd == 0)
+    orc = O.GaussianNoiseOracle(cfg.data, cfg.delta_f, cfg.epoch, 100., psds=cfg.psds(),
+                                waveform_f_lower=20.)
+    assert orc.loglr(**dict(zip(PARAM_ORDER, row)))[0] == 0.0
+
+
+@pytest.mark.parametrize("dets", [["H1"], ["H1", "L1"], ["L1", "V1", "H1"]])
+def test_detector_counts_unit_psd_fupper(dets):
+    """1/2/3 detectors, psds=None (unit weight, gaussian_noise.py:254-256) and a
+    finite f_upper."""
+    import gwin_oracle as O
+    from gwin_b200 import models
+    from gwin_b200.types import FrequencySeries
+    from gwin_b200.waveform import FDomainCBCGenerator, FDomainDetFrameGenerator
+    cfg = util.Config("u", 8, 2048., 20., dets, util.BBH_INJ, psd=False, seed=3)
+    # scale the white noise so that loglr is O(100)
+    scale = 1e-22
+    for d in dets:
+        cfg.data[d] *= scale
+    gen = FDomainDetFrameGenerator(FDomainCBCGenerator, cfg.epoch, detectors=dets,
+                                   variable_args=PARAM_ORDER, delta_f=cfg.delta_f,
+                                   f_lower=20., approximant="TaylorF2")
+    data = {d: FrequencySeries(cfg.data[d], cfg.delta_f, cfg.epoch) for d in dets}
+    norm = 4 * cfg.delta_f / scale ** 2
+    model = models.GaussianNoise(PARAM_ORDER, data, gen, 20., f_upper=60., norm=norm)
+    orc = O.GaussianNoiseOracle(cfg.data, cfg.delta_f, cfg.epoch, 20., f_upper=60., norm=norm)
+    assert (model._kmin, model._kmax) == (orc._kmin, orc._kmax)
+    rng = np.random.default_rng(11)
+    P = util.draw_bbh(rng, 40, cfg)
+    for kernel in (1, 2):
+        model.plan.configure(kernel=kernel)
+        lr, hd, hh = model.plan.loglr_host(P)
+        lr0, hd0, hh0 = O.batch_loglr(orc, P)
+        _check(lr, hd, hh, lr0, hd0, hh0, "unit psd %s k%d" % (dets, kernel))
+    assert abs(model.lognl - orc.lognl()) <= 1e-9 * abs(orc.lognl())
+
+
+def test_linearity_in_data(cfg2):
+    """Size-independent property: <d|h> is linear in the data, <h|h> does not
+    depend on it."""
+    rng = np.random.default_rng(2)
+    P = util.draw_bbh(rng, 64, cfg2)
+    a = cfg2.cuda_model().plan.loglr_host(P)
+    cfgb = util.c2(seed=99)
+    b = cfgb.cuda_model().plan.loglr_host(P)
+    cfgs = util.c2(seed=99)
+    for d in cfgs.dets:
+        cfgs.data[d] = cfg2.data[d] + cfgb.data[d]
+    s = cfgs.cuda_model().plan.loglr_host(P)
+    scale = np.abs(a[1]) + np.abs(b[1]) + 1.0
+    assert np.all(np.abs(s[1] - (a[1] + b[1])) <= 1e-12 * scale)
+    np.testing.assert_allclose(s[2], a[2], rtol=1e-14)
