@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- loglr evals/sec of the batched TaylorF2 likelihood (BASELINE.json metric).
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): TaylorF2
+BNS, 256 s @ 4096 Hz (524 289 frequency bins), H1+L1+V1, coloured Gaussian noise from the
+analytic aLIGO ZDHP PSD plus a 1.4+1.4 Msun injection; GaussianNoise loglr for a batch of
+16 384 walkers drawn in a box around the injection.
+
+One "step" = one pass of the hot path over one batch of walkers.  With N GPUs every rank
+holds a replica of the data tables and evaluates its own 16 384-walker slice (weak
+scaling); the per-walker results [W, 1+3*n_det] are exchanged with one NCCL all-gather per
+step, which is the only exchange the ensemble step needs.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]           # CUDA arm
+  python bench.py --impl reference [...]                        # CPU arm: the oracle port of the
+                                                                # reference path on all host cores
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "loglr evals/sec (TaylorF2, H1/L1/V1, 256 s @4096 Hz)"
+UNIT = "evals/s"
+SEGLEN, SRATE, F_LOWER = 256, 4096.0, 20.0
+DETS = ["H1", "L1", "V1"]
+WALKERS = 16384
+W_ALG_SLOTS = 32 + 12 * len(DETS)      # FP64 issue slots per (walker, bin): SURVEY.md 8d
+TABLE_BYTES_PER_BIN = 16 * len(DETS) + 24
+MTSUN = 4.925491025543575903411922162094833998e-6
+PARAMS = ("mass1", "mass2", "spin1z", "spin2z", "distance", "inclination",
+          "coa_phase", "ra", "dec", "polarization", "tc")
+INJ = dict(mass1=1.4, mass2=1.4, spin1z=0.0, spin2z=0.0, distance=40.0,
+           inclination=0.5, coa_phase=1.1, ra=1.3, dec=-0.4, polarization=0.7,
+           tc=SEGLEN - 6.0)
+
+
+def draw_walkers(rng, W):
+    P = np.empty((W, 11))
+    P[:, 0] = rng.uniform(1.2, 1.6, W)
+    P[:, 1] = rng.uniform(1.2, 1.6, W)
+    P[:, 2] = 0.0
+    P[:, 3] = 0.0
+    P[:, 4] = rng.uniform(10.0, 100.0, W)
+    P[:, 5] = np.arccos(rng.uniform(-1, 1, W))
+    P[:, 6] = rng.uniform(0, 2 * np.pi, W)
+    P[:, 7] = rng.uniform(0, 2 * np.pi, W)
+    P[:, 8] = np.arcsin(rng.uniform(-1, 1, W))
+    P[:, 9] = rng.uniform(0, 2 * np.pi, W)
+    P[:, 10] = INJ["tc"] + rng.uniform(-0.05, 0.05, W)
+    return P
+
+
+def bins_used(P, kmin, kmax, delta_f):
+    """Frequency bins each walker's inner products run over (per detector)."""
+    fisco = 1.0 / (6.0 ** 1.5 * np.pi * (P[:, 0] + P[:, 1]) * MTSUN)
+    n = (fisco / delta_f + 1).astype(np.int64)
+    return np.clip(np.minimum(n, kmax) - kmin, 0, None)
+
+
+def synthetic_noise(n_f, delta_f, seed=20181):
+    from gwin_b200.psd import aLIGOZeroDetHighPower, colored_noise
+    psd = aLIGOZeroDetHighPower(n_f, delta_f, F_LOWER)
+    rng = np.random.default_rng(seed)
+    return psd, {d: colored_noise(psd, delta_f, rng) for d in DETS}
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.proc = None
+        self.device = device
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, power = [], [], []
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load" = samples in the upper half of the power range
+        pw = np.array(power)
+        load = pw >= 0.5 * (pw.min() + pw.max()) if pw.max() > pw.min() else np.ones(len(pw), bool)
+        return {"sm_mhz": float(np.median(np.array(sm)[load])), "sm_max_mhz": float(max(smax)),
+                "power_w_max": float(pw.max()), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------
+# CPU arm / cpu_baseline: the oracle's C port of the reference path
+# ---------------------------------------------------------------------------
+def cpu_model(psd, data, delta_f):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import gwin_oracle as O
+    from c_oracle import COracle
+    gen = O.FDomainDetFrameGenerator(0.0, DETS, delta_f, F_LOWER)
+    wf = gen.generate(**INJ)
+    d2 = {}
+    for d in DETS:
+        x = data[d].copy()
+        n = min(len(wf[d]), len(x))
+        x[:n] += wf[d][:n]
+        d2[d] = x
+    return COracle(d2, delta_f, 0.0, F_LOWER, psds={d: psd for d in DETS})
+
+
+def cpu_time(co, P, threads, target_s):
+    """Times a bounded sample of the workload; returns (evals/s, n_evaluated, seconds)."""
+    probe = P[:max(threads, 8)]
+    co.batch_loglr(probe, nthreads=threads)       # cold: page-faults the scratch arrays
+    t0 = time.perf_counter()
+    co.batch_loglr(probe, nthreads=threads)
+    dt = time.perf_counter() - t0
+    n = int(min(len(P), max(len(probe), target_s / (dt / len(probe)))))
+    n = max(threads, n // threads * threads)
+    t0 = time.perf_counter()
+    co.batch_loglr(P[:n], nthreads=threads)
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_f = int(SEGLEN * SRATE) // 2 + 1
+    delta_f = 1.0 / SEGLEN
+    psd, data = synthetic_noise(n_f, delta_f)
+    co = cpu_model(psd, data, delta_f)
+    threads = os.cpu_count() or 1
+    P = draw_walkers(np.random.default_rng(20182), WALKERS)
+    # size one step to ~4 s of wall time
+    rate, n, dt = cpu_time(co, P, threads, 4.0)
+    per_step = n
+    for _ in range(args.warmup):
+        co.batch_loglr(P[:per_step], nthreads=threads)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        lo = (s * per_step) % (WALKERS - per_step + 1)
+        co.batch_loglr(P[lo:lo + per_step], nthreads=threads)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    sample = "%d of %d walkers per step, %d host threads, C port of the reference path (oracle/loglr_ref.c)" % (
+        per_step, WALKERS, threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(per_step),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(walkers_per_step):
+    return {"workload": "C3: TaylorF2 BNS loglr (GaussianNoise), 256 s @ 4096 Hz, 524289 bins, "
+                        "H1+L1+V1, coloured Gaussian noise + 1.4+1.4 Msun injection",
+            "walkers_per_gpu_per_step": walkers_per_step, "f_lower_hz": F_LOWER,
+            "mass_box_msun": [1.2, 1.6]}
+
+
+# ---------------------------------------------------------------------------
+# CUDA arm
+# ---------------------------------------------------------------------------
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    from gwin_b200 import _lib, models
+    from gwin_b200.types import FrequencySeries
+    from gwin_b200.waveform import FDomainCBCGenerator, FDomainDetFrameGenerator
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_f = int(SEGLEN * SRATE) // 2 + 1
+    delta_f = 1.0 / SEGLEN
+    psd, noise = synthetic_noise(n_f, delta_f)
+    gen = FDomainDetFrameGenerator(FDomainCBCGenerator, 0.0, detectors=DETS,
+                                   variable_args=PARAMS, delta_f=delta_f, f_lower=F_LOWER,
+                                   approximant="TaylorF2")
+    inj = gen.generate(device=local, **INJ)       # CUDA generate_kernel
+    data = {}
+    for d in DETS:
+        x = noise[d].copy()
+        h = inj[d].numpy()
+        x[:len(h)] += h[:n_f]
+        data[d] = FrequencySeries(x, delta_f, 0.0)
+    model = models.GaussianNoise(PARAMS, data, gen, F_LOWER, psds={d: psd for d in DETS},
+                                 device=local)
+    plan = model.plan
+    plan.configure(kernel=_lib.KERNEL_AUTO, mchirp_min=1.0)   # mass box [1.2,1.6] => Mc >= 1.04
+    call = models.CallModel(model, "loglr", return_all_stats=False)
+
+    W = args.walkers
+    rng = np.random.default_rng(20182 + rank)
+    P_host = draw_walkers(rng, W)
+    bins = bins_used(P_host, plan.kmin, plan.kmax, delta_f)
+    P_dev = torch.tensor(P_host, device=dev)
+    nd = len(DETS)
+    out = (torch.empty(W, dtype=torch.float64, device=dev),
+           torch.empty((W, nd, 2), dtype=torch.float64, device=dev),
+           torch.empty((W, nd), dtype=torch.float64, device=dev))
+    packed = torch.empty((W, 1 + 3 * nd), dtype=torch.float64, device=dev)
+    gathered = torch.empty((world * W, 1 + 3 * nd), dtype=torch.float64, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step():
+        plan.loglr_device(P_dev, out=out)
+        if world > 1:
+            packed[:, 0] = out[0]
+            packed[:, 1:1 + 2 * nd] = out[1].reshape(W, 2 * nd)
+            packed[:, 1 + 2 * nd:] = out[2]
+            dist.all_gather_into_tensor(gathered, packed)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    fp64_peak = _lib.fp64_peak(local)       # DFMA lane-ops/s, measured live on this GPU
+    plan.kernel_timing(True)
+
+    clocks = ClockSampler(local) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    sync_all()
+    for e0, e1 in ev:
+        flush.fill_(1)                      # evict the tables from L2 between timed steps
+        e0.record()
+        step()
+        e1.record()
+    sync_all()
+    clk = clocks.stop() if clocks else None
+    total_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    kern_ms, kern_n = plan.kernel_timing(False)
+    launches = plan.last_launches * args.steps
+
+    # end to end through the plugin call with HOST buffers (CallModel.batch -> C ABI host
+    # entry: pinned staging, H2D of the parameter rows, kernels, D2H of loglr/hd/hh)
+    call.batch(P_host)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = call.batch(P_host)
+    e2e_s = time.perf_counter() - t0
+    assert np.all(np.isfinite(res.values))
+    sync_all()
+
+    t = torch.tensor([total_ms, e2e_s, float(bins.sum())], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        total_ms, e2e_s = float(tmax[0]), float(tmax[1])
+        bins_total = float(tsum[2])
+    else:
+        bins_total = float(bins.sum())
+
+    if rank == 0:
+        evals = world * W * args.steps
+        value = evals / (total_ms * 1e-3)
+        e2e = evals / e2e_s
+        # roofline of the dominant kernel (this rank): algorithmic FP64 work / its own duration
+        slots = float(bins.sum()) * W_ALG_SLOTS                 # per launch
+        achieved = 2.0 * slots / (kern_ms * 1e-3) / 1e12          # TFLOP/s (1 slot = 2 flop)
+        peak = 2.0 * fp64_peak / 1e12
+        nominal = 2.0 * 148 * 64 * 1.965e9 / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        # every table byte has to come from HBM once per launch (L2 was flushed); the
+        # 128 walker tiles that re-read it are served by the 126 MB L2
+        alg_bytes = float(plan.kmax - plan.kmin) * TABLE_BYTES_PER_BIN + W * (11 + 1 + 3 * nd) * 8.0
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(workload_config(W), l2="flushed between timed steps (256 MiB write)",
+                           kernel="block recurrence (quartic phasor, Horner)",
+                           mean_bins_per_eval=float(bins.mean())),
+            "clocks": clk,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": world * W * 11 * 8,
+                    "d2h_bytes_per_step": world * W * (1 + 3 * nd) * 8,
+                    "path": "CallModel.batch(points) -> gwin_loglr_batch_host"},
+            "gpu_launches": launches,
+            "roofline": {
+                "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak,
+                "peak_source": "live DFMA probe on this GPU (MEASURED_PEAKS.json has no FP64 entry); "
+                               "nominal 148 SM x 64 lanes x 1.965 GHz = %.1f TFLOP/s" % nominal,
+                "frac_of_nominal": achieved / nominal,
+                "work_model": "W_alg = 32 + 12*n_det = %d FP64 issue slots per (walker, bin) "
+                              "(SURVEY.md 8d); the kernel itself issues 8 + 8*n_det" % W_ALG_SLOTS,
+                "kernel": "loglr_recur_kernel<3>", "kernel_ms": kern_ms, "kernel_launches": kern_n,
+                "kernel_share_of_step": kern_ms / (total_ms / args.steps),
+                "hbm": {"algorithmic_bytes_per_launch": alg_bytes,
+                        "achieved_gbs": alg_bytes / (kern_ms * 1e-3) / 1e9,
+                        "peak_gbs": hbm, "frac": alg_bytes / (kern_ms * 1e-3) / 1e9 / hbm},
+                "traffic": None,
+            },
+        }
+        if world == 1 and not args.no_cpu:
+            co = cpu_model(psd, noise, delta_f)
+            threads = os.cpu_count() or 1
+            rate, n, dt = cpu_time(co, P_host, threads, 12.0)
+            line["cpu_baseline"] = {
+                "value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": "%d of the %d walkers of one step in %.1f s on %d host threads; "
+                          "C port of the reference path (oracle/loglr_ref.c), not pycbc/lalsimulation"
+                          % (n, W, dt, threads)}
+            # spot parity on the bench data itself
+            lr_c = co.batch_loglr(P_host[:8], nthreads=min(8, threads))[0]
+            lr_g = plan.loglr_host(P_host[:8])[0]
+            line["parity_spot_max_abs_dloglr"] = float(np.max(np.abs(lr_c - lr_g)))
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--walkers", type=int, default=WALKERS)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 10 if args.impl == "cuda" else 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

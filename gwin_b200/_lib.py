@@ -33,6 +33,7 @@ SYMBOLS = (
     "gwin_plan_create", "gwin_plan_destroy", "gwin_plan_cutoffs",
     "gwin_plan_lognl", "gwin_plan_configure", "gwin_loglr_batch",
     "gwin_loglr_batch_host", "gwin_generate_host", "gwin_plan_last_launches",
+    "gwin_plan_kernel_timing",
     "gwin_fp64_peak", "gwin_last_error", "gwin_version",
 )
 
@@ -111,6 +112,9 @@ def load():
                                            C.POINTER(C.c_int64)]
         lib.gwin_plan_last_launches.restype = C.c_int
         lib.gwin_plan_last_launches.argtypes = [C.c_void_p]
+        lib.gwin_plan_kernel_timing.restype = C.c_int
+        lib.gwin_plan_kernel_timing.argtypes = [C.c_void_p, C.c_int, dp,
+                                                C.POINTER(C.c_int)]
         lib.gwin_fp64_peak.restype = C.c_int
         lib.gwin_fp64_peak.argtypes = [C.c_int, dp]
         lib.gwin_last_error.restype = C.c_char_p
@@ -187,6 +191,14 @@ class Plan(object):
     @property
     def last_launches(self):
         return self._lib.gwin_plan_last_launches(self._h)
+
+    def kernel_timing(self, enable=True):
+        """(mean ms, launches) of the loglr kernel since the last call; see
+        ``gwin_plan_kernel_timing``."""
+        ms, n = C.c_double(), C.c_int()
+        check(self._lib.gwin_plan_kernel_timing(self._h, int(bool(enable)),
+                                                C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def loglr_host(self, params, mode=MODE_GAUSSIAN, skip=None):
         """params: [W, 11] float64 host array.  Returns loglr[W],

@@ -112,6 +112,12 @@ struct gwin_plan {
     int64_t stage_cap;
     cudaStream_t stream;
     int last_launches;
+    // optional timing of the dominant kernel on the launching stream
+    bool timing;
+    cudaEvent_t ev0, ev1;
+    double kernel_ms_sum;
+    int kernel_ms_n;
+    bool ev_pending;
 };
 
 // ---------------------------------------------------------------------------
@@ -887,6 +893,7 @@ extern "C" void gwin_plan_destroy(gwin_plan* p) {
     cudaFree(p->d_partial); cudaFree(p->d_cub);
     cudaFree(p->d_params); cudaFree(p->d_out); cudaFree(p->d_skip);
     cudaFreeHost(p->h_params); cudaFreeHost(p->h_out); cudaFreeHost(p->h_skip);
+    if (p->timing) { cudaEventDestroy(p->ev0); cudaEventDestroy(p->ev1); }
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
 }
@@ -918,6 +925,29 @@ extern "C" int gwin_plan_configure(gwin_plan* p, int kernel, double phase_tol, d
 }
 
 extern "C" int gwin_plan_last_launches(const gwin_plan* p) { return p ? p->last_launches : 0; }
+
+extern "C" int gwin_plan_kernel_timing(gwin_plan* p, int enable, double* mean_ms, int* n_launches) {
+    if (!p) return fail(GWIN_EINVAL, "plan is NULL");
+    CK(cudaSetDevice(p->device));
+    if (p->timing && p->ev_pending) {
+        float ms = 0.f;
+        CK(cudaEventSynchronize(p->ev1));
+        CK(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+        p->kernel_ms_sum += ms; p->kernel_ms_n++;
+        p->ev_pending = false;
+    }
+    if (mean_ms) *mean_ms = p->kernel_ms_n ? p->kernel_ms_sum / p->kernel_ms_n : 0.0;
+    if (n_launches) *n_launches = p->kernel_ms_n;
+    if (enable && !p->timing) {
+        CK(cudaEventCreate(&p->ev0)); CK(cudaEventCreate(&p->ev1));
+        p->timing = true;
+    } else if (!enable && p->timing) {
+        cudaEventDestroy(p->ev0); cudaEventDestroy(p->ev1);
+        p->timing = false;
+    }
+    p->kernel_ms_sum = 0.0; p->kernel_ms_n = 0;
+    return GWIN_OK;
+}
 
 static int ensure_workspace(gwin_plan* p, int64_t W, int n_chunks) {
     const int nd = p->d.n_det;
@@ -1011,15 +1041,25 @@ extern "C" int gwin_loglr_batch(gwin_plan* p, int mode, int64_t W64,
         CK(cub::DeviceRadixSort::SortPairs(p->d_cub, bytes, p->d_key_in, p->d_key_out,
                                            p->d_perm_in, p->d_perm_out, W, 0, 23, st));
         perm = p->d_perm_out;
-        p->last_launches += 2;   // + CUB's own passes (library code, not counted)
+        p->last_launches += 1;   // + CUB's radix-sort passes (library code, not counted)
     }
     walker_setup_kernel<<<gb, tb, 0, st>>>(d, W, wpad, params, skip, perm, p->d_wc, p->d_ks, p->d_ke, hh_rows);
+    if (p->timing) {
+        if (p->ev_pending) {            // harvest the previous launch (it has long finished)
+            float ms = 0.f;
+            if (cudaEventSynchronize(p->ev1) == cudaSuccess &&
+                cudaEventElapsedTime(&ms, p->ev0, p->ev1) == cudaSuccess) { p->kernel_ms_sum += ms; p->kernel_ms_n++; }
+            p->ev_pending = false;
+        }
+        CK(cudaEventRecord(p->ev0, st));
+    }
     switch (nd) {
         case 1: launch_main<1>(p, recur, W, wpad, n_chunks, per_chunk, hh_rows, st); break;
         case 2: launch_main<2>(p, recur, W, wpad, n_chunks, per_chunk, hh_rows, st); break;
         case 3: launch_main<3>(p, recur, W, wpad, n_chunks, per_chunk, hh_rows, st); break;
         default: launch_main<4>(p, recur, W, wpad, n_chunks, per_chunk, hh_rows, st); break;
     }
+    if (p->timing) { CK(cudaEventRecord(p->ev1, st)); p->ev_pending = true; }
     combine_kernel<<<gb, tb, 0, st>>>(nd, W, wpad, n_chunks, mode, perm, p->d_wc, p->d_ks, p->d_partial,
                                       hh_rows, loglr, hd, hh);
     p->last_launches += 3;

@@ -123,6 +123,11 @@ int gwin_generate_host(gwin_plan* plan, const double* params, double* h_out,
 /* Kernel launches issued by the last gwin_loglr_batch* call on this plan. */
 int gwin_plan_last_launches(const gwin_plan* plan);
 
+/* Device-side timing of the dominant (loglr) kernel with CUDA events recorded on the
+ * launching stream.  enable != 0 switches it on; every call returns the mean duration
+ * [ms] and count of the loglr-kernel launches since the previous call, then resets. */
+int gwin_plan_kernel_timing(gwin_plan* plan, int enable, double* mean_ms, int* n_launches);
+
 /* FP64 issue-rate micro-benchmark on the plan's device: runs a dependent-chain-free
  * DFMA loop and returns achieved FP64 FMA lane-ops per second. */
 int gwin_fp64_peak(int device, double* dfma_per_sec);
