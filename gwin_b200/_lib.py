@@ -15,7 +15,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libgwin_b200.so")
+LIB_PATH = os.environ.get("GWIN_B200_LIB") or os.path.join(_HERE, "libgwin_b200.so")
 SOURCES = [os.path.join(_HERE, "csrc", "gwin_cuda.cu")]
 HEADER = os.path.join(ROOT, "include", "gwin_b200.h")
 
@@ -34,7 +34,7 @@ SYMBOLS = (
     "gwin_plan_lognl", "gwin_plan_configure", "gwin_loglr_batch",
     "gwin_loglr_batch_host", "gwin_generate_host", "gwin_plan_last_launches",
     "gwin_plan_kernel_timing",
-    "gwin_fp64_peak", "gwin_last_error", "gwin_version",
+    "gwin_fp64_peak", "gwin_fp64_probe", "gwin_last_error", "gwin_version",
 )
 
 _lock = threading.Lock()
@@ -117,6 +117,8 @@ def load():
                                                 C.POINTER(C.c_int)]
         lib.gwin_fp64_peak.restype = C.c_int
         lib.gwin_fp64_peak.argtypes = [C.c_int, dp]
+        lib.gwin_fp64_probe.restype = C.c_int
+        lib.gwin_fp64_probe.argtypes = [C.c_int, C.c_int, dp]
         lib.gwin_last_error.restype = C.c_char_p
         lib.gwin_version.restype = C.c_char_p
         _lib = lib
@@ -267,6 +269,13 @@ def fp64_peak(device=0):
     """Measured FP64 FMA lane-ops/s of the device (independent DFMA chains)."""
     r = C.c_double()
     check(load().gwin_fp64_peak(int(device), C.byref(r)))
+    return r.value
+
+
+def fp64_probe(device=0, variant=0):
+    """Diagnostic FP64 rate probes, see ``gwin_fp64_probe``."""
+    r = C.c_double()
+    check(load().gwin_fp64_probe(int(device), int(variant), C.byref(r)))
     return r.value
 
 

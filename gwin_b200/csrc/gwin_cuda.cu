@@ -47,7 +47,9 @@
 #define WARP 32
 #define CTA_THREADS 128
 #define RESYNC 64            // direct kernel: detector phasor re-sync interval
+#ifndef MAX_BLOCK
 #define MAX_BLOCK 256        // recurrence kernel: longest polynomial block
+#endif
 #define MIN_BLOCK 8
 
 // per-walker coefficient rows (SoA: wc[row * wpad + walker])
@@ -82,6 +84,16 @@ struct PlanDev {
     const double*  C;        // [n_det][n_f+1] prefix sums of norm*f^(-7/3)/S
 };
 
+// Per distinct (block length, degree): node offsets and the linear map from the exact
+// phase samples to the polynomial's forward differences.  Built on the host in extended
+// precision; read with warp-uniform loads.
+struct BlockMat {
+    double m[16];   // D_r = sum_i m[4r+i] (f_{i+1} - f_0):  D1(0), D2(1), D3(2), D4
+    int node[4];    // offsets of nodes 1..deg from the block start (node 0 is 0, node deg is B-1)
+    int deg;        // 4 = quartic, 3 = cubic, 0 = evaluate the bins directly
+    int pad[3];
+};
+
 struct gwin_plan {
     int device;
     PlanDev d;
@@ -95,7 +107,11 @@ struct gwin_plan {
     bool auto_mchirp;        // host API: derive mchirp_min from each batch
     // recurrence schedule
     std::vector<int> blk_start;      // host copy, nblk+1 entries
+    std::vector<int> blk_mat;        // nblk entries: index into mats
+    std::vector<BlockMat> mats;
     int* d_blk_start;
+    int* d_blk_mat;
+    BlockMat* d_mats;
     int n_blk;
     bool sched_dirty;
     // workspace
@@ -478,101 +494,144 @@ loglr_direct_kernel(PlanDev P, int W, int wpad, int chunk_bins, int n_chunks,
 // costs 8 + 8*ND FP64 issue slots instead of a phase polynomial and a sincos.
 // The block sum is then rotated by the exact anchor phasor e^{-2 pi i Theta_d(B-1)}.
 // ---------------------------------------------------------------------------
-template <int ND, bool MASKED>
-__device__ __forceinline__ void recur_block(
-        const PhaseCoef& pc, const double (&tau_hi)[ND], const double (&tau_lo)[ND],
-        const double4* __restrict__ basis, const double2* __restrict__ T,
-        int kb, int B, int lo, int hi, double2 (&acc_out)[ND]) {
-    if (B < 5) {
-        // too short to carry 5 distinct nodes: evaluate these bins directly
-        for (int k = kb; k < kb + B; ++k) {
-            if (k < lo || k >= hi) continue;
-            const double psi = phase_turns(pc, ld_basis(basis + k));
-            const double kd = (double)k;
-#pragma unroll
-            for (int d = 0; d < ND; ++d) {
-                const double2 u = phasor_neg(psi + fma(kd, tau_lo[d], frac1(kd * tau_hi[d])));
-                acc_out[d] = cfma(__ldg(T + (size_t)k * ND + d), u, acc_out[d]);
-            }
-        }
-        return;
-    }
-    // nodes 0, t1, t2, t3, B-1
-    const int e = B - 1;
-    const int t1 = (e + 4) / 8;                // ~ (1-cos(pi/4))/2 = 0.1464
-    const int t2 = e / 2;
-    const int t3 = e - t1;
-    const double f0 = phase_turns(pc, ld_basis(basis + kb));
-    const double f1 = phase_turns(pc, ld_basis(basis + kb + t1));
-    const double f2 = phase_turns(pc, ld_basis(basis + kb + t2));
-    const double f3 = phase_turns(pc, ld_basis(basis + kb + t3));
-    const double f4 = phase_turns(pc, ld_basis(basis + kb + e));
-    // Newton divided differences on integer nodes
-    const double x1 = (double)t1, x2 = (double)t2, x3 = (double)t3, x4 = (double)e;
-    const double d01 = (f1 - f0) / x1;
-    const double d12 = (f2 - f1) / (x2 - x1);
-    const double d23 = (f3 - f2) / (x3 - x2);
-    const double d34 = (f4 - f3) / (x4 - x3);
-    const double d012 = (d12 - d01) / x2;
-    const double d123 = (d23 - d12) / (x3 - x1);
-    const double d234 = (d34 - d23) / (x4 - x2);
-    const double d0123 = (d123 - d012) / x3;
-    const double d1234 = (d234 - d123) / (x4 - x1);
-    const double n4 = (d1234 - d0123) / x4;
-    const double n1 = d01, n2 = d012, n3 = d0123;
-    // Newton -> monomial:  P(j) = f0 + c1 j + c2 j^2 + c3 j^3 + c4 j^4
-    //   j(j-x1)(j-x2)(j-x3) = j^4 - e1 j^3 + e2 j^2 - e3 j
-    const double e1 = x1 + x2 + x3, e2 = x1 * x2 + x1 * x3 + x2 * x3, e3 = x1 * x2 * x3;
-    const double c4 = n4;
-    const double c3 = n3 - n4 * e1;
-    const double c2 = n2 - n3 * (x1 + x2) + n4 * e2;
-    const double c1 = n1 - n2 * x1 + n3 * (x1 * x2) - n4 * e3;
-    // forward differences: D1(0), D2(1), D3(2), D4
-    //   D1(j) = c1 + c2(2j+1) + c3(3j^2+3j+1) + c4(4j^3+6j^2+4j+1)
-    //   D2(j) = D1(j)-D1(j-1) = 2c2 + 6c3 j + c4(12 j^2 + 2)
-    //   D3(j) = D2(j)-D2(j-1) = 6c3 + c4(24 j - 12)
-    //   D4    = 24 c4
-    const double D1_0 = c1 + c2 + c3 + c4;
-    const double D2_1 = 2.0 * c2 + 6.0 * c3 + 14.0 * c4;
-    const double D3_2 = 6.0 * c3 + 36.0 * c4;
-    const double D4 = 24.0 * c4;
-    const double2 tq = phasor_pos(D4);
-    double2 sq = phasor_pos(D3_2);
-    double2 rq = phasor_pos(D2_1);
-    double2 g[ND], acc[ND];
-    const double kend = (double)(kb + e);
+// Per-thread walker coefficients live in shared memory (one column per thread, no
+// sharing, hence no barrier): they are only needed in the per-block set-up, and keeping
+// them out of the register file buys a third/fourth resident CTA per SM.
+#define RC_ROWS(nd) (9 + 2 * (nd))
+template <int ND>
+__device__ __forceinline__ void load_block_coef(const double* sc, PhaseCoef& pc,
+                                                double (&tau_hi)[ND], double (&tau_lo)[ND]) {
+    asm volatile("" ::: "memory");      // re-read per block: do not hoist into registers
+    pc.a0 = sc[0 * CTA_THREADS]; pc.a2 = sc[1 * CTA_THREADS]; pc.a3 = sc[2 * CTA_THREADS];
+    pc.a4 = sc[3 * CTA_THREADS]; pc.a5 = sc[4 * CTA_THREADS]; pc.b5 = sc[5 * CTA_THREADS];
+    pc.a6 = sc[6 * CTA_THREADS]; pc.b6 = sc[7 * CTA_THREADS]; pc.a7 = sc[8 * CTA_THREADS];
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
-        g[d] = phasor_pos(D1_0 + (tau_hi[d] + tau_lo[d]));
-        double2 T0 = __ldg(T + (size_t)kb * ND + d);
-        if (MASKED && !(kb >= lo && kb < hi)) T0 = make_double2(0.0, 0.0);
-        acc[d] = T0;
-    }
-#pragma unroll 4
-    for (int j = 1; j < B; ++j) {
-        const int k = kb + j;
-        const bool on = !MASKED || ((k >= lo) && (k < hi));
-#pragma unroll
-        for (int d = 0; d < ND; ++d) {
-            double2 Tk = __ldg(T + (size_t)k * ND + d);
-            if (MASKED && !on) Tk = make_double2(0.0, 0.0);
-            acc[d] = cfma(acc[d], g[d], Tk);
-            g[d] = cmul(g[d], rq);
-        }
-        rq = cmul(rq, sq);
-        sq = cmul(sq, tq);
-    }
-#pragma unroll
-    for (int d = 0; d < ND; ++d) {
-        const double anchor = f4 + fma(kend, tau_lo[d], frac1(kend * tau_hi[d]));
-        acc_out[d] = cfma(acc[d], phasor_neg(anchor), acc_out[d]);
+        tau_hi[d] = sc[(9 + 2 * d) * CTA_THREADS];
+        tau_lo[d] = sc[(10 + 2 * d) * CTA_THREADS];
     }
 }
 
 template <int ND>
-__global__ void __launch_bounds__(CTA_THREADS)
+__device__ __forceinline__ void direct_block(const double* sc, const double4* __restrict__ basis,
+                                             const double2* __restrict__ T, int kb, int B, int lo, int hi,
+                                             double2 (&acc_out)[ND]) {
+    // too curved / too short for a polynomial block: evaluate these bins directly
+    PhaseCoef pc;
+    double tau_hi[ND], tau_lo[ND];
+    load_block_coef<ND>(sc, pc, tau_hi, tau_lo);
+    for (int k = kb; k < kb + B; ++k) {
+        if (k < lo || k >= hi) continue;
+        const double psi = phase_turns(pc, ld_basis(basis + k));
+        const double kd = (double)k;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            const double2 u = phasor_neg(psi + fma(kd, tau_lo[d], frac1(kd * tau_hi[d])));
+            acc_out[d] = cfma(__ldg(T + (size_t)k * ND + d), u, acc_out[d]);
+        }
+    }
+}
+
+template <int ND, bool MASKED, int DEG>
+__device__ __forceinline__ void recur_block(
+        const double* sc, const double4* __restrict__ basis, const double2* __restrict__ T,
+        const BlockMat* __restrict__ M, int kb, int B, int lo, int hi, double2 (&acc_out)[ND]) {
+    PhaseCoef pc;
+    double tau_hi[ND], tau_lo[ND];
+    load_block_coef<ND>(sc, pc, tau_hi, tau_lo);
+    // exact phase at the DEG+1 nodes (both block ends are nodes)
+    const double f0 = phase_turns(pc, ld_basis(basis + kb));
+    double fn[DEG];
+#pragma unroll
+    for (int i = 0; i < DEG; ++i) fn[i] = phase_turns(pc, ld_basis(basis + kb + M->node[i]));
+    const double fend = fn[DEG - 1];
+    // forward differences of the interpolating polynomial: D1(0), D2(1), D3(2), D4
+    double D[4];
+#pragma unroll
+    for (int r = 0; r < DEG; ++r) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < DEG; ++i) acc = fma(M->m[4 * r + i], fn[i] - f0, acc);
+        D[r] = acc;
+    }
+    double2 tq = make_double2(1.0, 0.0);
+    if (DEG == 4) tq = phasor_pos(D[3]);
+    double2 sq = phasor_pos(D[2]);
+    double2 rq = phasor_pos(D[1]);
+    double2 g[ND], acc[ND];
+    const double kend = (double)(kb + B - 1);
+    // Software-pipelined table reads: the rows of bins j+2 / j+3 are requested while bins
+    // j / j+1 are consumed, so the latency of the warp-uniform LDG.128s is covered by >= 64
+    // FP64 instructions of this warp (ncu r1: 48 % of stall samples were long_scoreboard on
+    // loads consumed in the iteration that issued them).  Rows up to kb+B+1 are touched; the
+    // table is padded by 4 rows past kmax.
+    const double2* __restrict__ Tp = T + (size_t)kb * ND;
+    double2 Ta[ND], Tb[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        g[d] = phasor_pos(D[0] + (tau_hi[d] + tau_lo[d]));
+        double2 T0 = __ldg(Tp + d);
+        Ta[d] = __ldg(Tp + ND + d);
+        Tb[d] = __ldg(Tp + 2 * ND + d);
+        if (MASKED && !(kb >= lo && kb < hi)) T0 = make_double2(0.0, 0.0);
+        acc[d] = T0;
+    }
+    Tp += 3 * ND;                         // -> row of bin 3
+    int j = 1;
+#pragma unroll 2
+    for (; j + 1 < B; j += 2) {
+        {
+            const bool on = !MASKED || ((kb + j >= lo) && (kb + j < hi));
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                double2 Tk = Ta[d];
+                Ta[d] = __ldg(Tp + d);                      // bin j+2
+                if (MASKED && !on) Tk = make_double2(0.0, 0.0);
+                acc[d] = cfma(acc[d], g[d], Tk);
+                g[d] = cmul(g[d], rq);
+            }
+            rq = cmul(rq, sq);
+            if (DEG == 4) sq = cmul(sq, tq);
+        }
+        {
+            const bool on = !MASKED || ((kb + j + 1 >= lo) && (kb + j + 1 < hi));
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                double2 Tk = Tb[d];
+                Tb[d] = __ldg(Tp + ND + d);                 // bin j+3
+                if (MASKED && !on) Tk = make_double2(0.0, 0.0);
+                acc[d] = cfma(acc[d], g[d], Tk);
+                g[d] = cmul(g[d], rq);
+            }
+            rq = cmul(rq, sq);
+            if (DEG == 4) sq = cmul(sq, tq);
+        }
+        Tp += 2 * ND;
+    }
+    if (j < B) {                          // odd tail: bin B-1 sits in Ta
+        const bool on = !MASKED || ((kb + j >= lo) && (kb + j < hi));
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            double2 Tk = Ta[d];
+            if (MASKED && !on) Tk = make_double2(0.0, 0.0);
+            acc[d] = cfma(acc[d], g[d], Tk);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        const double anchor = fend + fma(kend, tau_lo[d], frac1(kend * tau_hi[d]));
+        acc_out[d] = cfma(acc[d], phasor_neg(anchor), acc_out[d]);
+    }
+}
+
+#ifndef RECUR_MIN_CTAS
+#define RECUR_MIN_CTAS 5
+#endif
+template <int ND>
+__global__ void __launch_bounds__(CTA_THREADS, RECUR_MIN_CTAS)
 loglr_recur_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_blk,
-                   const int* __restrict__ blk_start,
+                   const int* __restrict__ blk_start, const int* __restrict__ blk_mat,
+                   const BlockMat* __restrict__ mats,
                    const double* __restrict__ wc, const int* __restrict__ ks_arr,
                    const int* __restrict__ ke_arr, double2* __restrict__ partial) {
     const int t = blockIdx.x * CTA_THREADS + threadIdx.x;
@@ -599,24 +658,56 @@ loglr_recur_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_blk,
 #pragma unroll
     for (int d = 0; d < ND; ++d) acc[d] = make_double2(0.0, 0.0);
 
+    __shared__ double s_coef[RC_ROWS(ND) * CTA_THREADS];
     if (wlo < whi) {
         const int tt = live ? t : 0;
-        PhaseCoef pc;
-        load_phase_coef(pc, wc, wpad, tt);
-        double tau_hi[ND], tau_lo[ND];
+        double* sc = s_coef + threadIdx.x;
+#pragma unroll
+        for (int r = 0; r < 9; ++r) sc[r * CTA_THREADS] = wc[(size_t)r * wpad + tt];
 #pragma unroll
         for (int d = 0; d < ND; ++d) {
             const double* row = wc + (size_t)(C_DET0 + D_NROW * d) * wpad + tt;
-            tau_hi[d] = row[D_TAUHI * wpad];
-            tau_lo[d] = row[D_TAULO * wpad];
+            sc[(9 + 2 * d) * CTA_THREADS] = row[D_TAUHI * wpad];
+            sc[(10 + 2 * d) * CTA_THREADS] = row[D_TAULO * wpad];
         }
+        const int lane = threadIdx.x & (WARP - 1);
         for (int b = b0; b < b1; ++b) {
             const int kb = blk_start[b], kn = blk_start[b + 1];
             if (kn <= wlo || kb >= whi) continue;       // nobody in this warp needs it
-            if (kb >= ilo && kn <= ihi)
-                recur_block<ND, false>(pc, tau_hi, tau_lo, P.basis, P.T, kb, kn - kb, lo, hi, acc);
-            else
-                recur_block<ND, true>(pc, tau_hi, tau_lo, P.basis, P.T, kb, kn - kb, lo, hi, acc);
+#ifndef NO_L2_PREFETCH
+            // Pull the NEXT block's table rows (and its 5 basis nodes) into L2 now, one
+            // 128-byte line per lane: every line of the table is first touched by a whole
+            // wave-front of CTAs at once, and an un-prefetched first touch parks all of
+            // them on a DRAM round trip (ncu r1b: 7 % L2 misses, long_scoreboard top stall).
+            if (b + 1 < b1 && kn < whi) {
+                const int kn2 = blk_start[b + 2];
+                const char* base = reinterpret_cast<const char*>(P.T + (size_t)kn * ND);
+                const int bytes = (kn2 - kn) * ND * (int)sizeof(double2);
+                for (int off = lane * 128; off < bytes; off += WARP * 128)
+#ifdef PREFETCH_L1
+                    asm volatile("prefetch.global.L1 [%0];" :: "l"(base + off));
+#else
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(base + off));
+#endif
+                if (lane < 5) {
+                    const BlockMat* M2 = mats + blk_mat[b + 1];
+                    const int node = lane == 0 ? 0 : M2->node[lane - 1];
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(P.basis + kn + node));
+                }
+            }
+#endif
+            const BlockMat* M = mats + blk_mat[b];
+            const int deg = M->deg;
+            const bool full = kb >= ilo && kn <= ihi;       // every lane covers the whole block
+            if (deg == 4) {
+                if (full) recur_block<ND, false, 4>(sc, P.basis, P.T, M, kb, kn - kb, lo, hi, acc);
+                else      recur_block<ND, true, 4>(sc, P.basis, P.T, M, kb, kn - kb, lo, hi, acc);
+            } else if (deg == 3) {
+                if (full) recur_block<ND, false, 3>(sc, P.basis, P.T, M, kb, kn - kb, lo, hi, acc);
+                else      recur_block<ND, true, 3>(sc, P.basis, P.T, M, kb, kn - kb, lo, hi, acc);
+            } else {
+                direct_block<ND>(sc, P.basis, P.T, kb, kn - kb, lo, hi, acc);
+            }
         }
     }
     if (live) {
@@ -707,16 +798,44 @@ __global__ void generate_len_kernel(PlanDev P, const double* __restrict__ params
     ke_arr[1] = (params_ok(params) && has_waveform(params, P.f_lower_wf)) ? waveform_len(params[0] + params[1], P.delta_f) : 0;
 }
 
-// FP64 issue-rate probe: 8 independent DFMA chains per thread
+// FP64 issue-rate probes.  variant 0: 8 independent DFMA chains sharing the multiplier and
+// addend registers (operand-reuse friendly, the classical "peak" loop); variant 1: every DFMA
+// reads three registers no neighbouring instruction reads (no reuse-cache help); variant 2:
+// the hot loop's own pattern, 4 independent unit-phasor complex multiplications per step
+// (2 DMUL + 2 DFMA each).
+template <int VARIANT>
 __global__ void dfma_probe_kernel(double* out, int iters) {
-    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
-    double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
-    const double m = 0.999999999, c = 1e-12;
-    for (int i = 0; i < iters; ++i) {
-        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
-        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    const double t0 = threadIdx.x * 1e-9;
+    if (VARIANT == 0) {
+        double a0 = t0, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+        const double m = 0.999999999, c = 1e-12;
+        for (int i = 0; i < iters; ++i) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+        out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    } else if (VARIANT == 1) {
+        double a[8], b[8], c[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a[i] = t0 + i; b[i] = 0.999999999 - 1e-12 * i - t0; c[i] = 1e-12 * (i + 1) + t0; }
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) a[q] = fma(a[q], b[q], c[q]);
+        }
+        double r = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r += a[i];
+        out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+    } else {
+        double2 z[4], w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { z[i] = make_double2(1.0 - t0, t0 + i * 1e-9); w[i] = make_double2(cos(1e-3 * (i + 1) + t0), sin(1e-3 * (i + 1) + t0)); }
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) z[q] = cmul(z[q], w[q]);
+        }
+        out[blockIdx.x * blockDim.x + threadIdx.x] = z[0].x + z[1].y + z[2].x + z[3].y;
     }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
 // ---------------------------------------------------------------------------
@@ -727,50 +846,97 @@ static const int64_t LEAPS_GPS[] = {
     394156807, 425692808, 457228809, 504489610, 551750411, 599184012, 820108813,
     914803214, 1025136015, 1119744016, 1167264017 };
 
+// Linear map (f_1-f_0, ..., f_deg-f_0) -> forward differences of the interpolating polynomial
+// through nodes 0 = x_0 < x_1 < ... < x_deg = B-1:  Newton divided differences -> monomial
+// coefficients c1..c4 -> D1(0) = c1+c2+c3+c4, D2(1) = 2c2+6c3+14c4, D3(2) = 6c3+36c4, D4 = 24c4.
+static BlockMat make_block_mat(int B, int deg) {
+    BlockMat M;
+    memset(&M, 0, sizeof M);
+    M.deg = deg;
+    if (deg == 0) return M;
+    const int e = B - 1;
+    int x[5] = {0, 0, 0, 0, 0};
+    if (deg == 4) { const int q = (e + 4) / 8; x[1] = q; x[2] = e / 2; x[3] = e - q; x[4] = e; }   // ~Chebyshev-Lobatto
+    else          { const int q = (e + 2) / 4; x[1] = q; x[2] = e - q; x[3] = e; }
+    for (int i = 0; i < deg; ++i) M.node[i] = x[i + 1];
+    for (int col = 1; col <= deg; ++col) {
+        long double dd[5] = {0, 0, 0, 0, 0};
+        dd[col] = 1.0L;                         // samples g_i = f_i - f_0 of the unit vector
+        long double nw[5];                      // Newton coefficients
+        nw[0] = dd[0];
+        for (int lvl = 1; lvl <= deg; ++lvl) {
+            for (int i = 0; i + lvl <= deg; ++i)
+                dd[i] = (dd[i + 1] - dd[i]) / (long double)(x[i + lvl] - x[i]);
+            nw[lvl] = dd[0];
+        }
+        // Newton -> monomial: P(j) = sum_l nw[l] prod_{i<l} (j - x_i)
+        long double c[5] = {0, 0, 0, 0, 0}, basis[6] = {1, 0, 0, 0, 0, 0};
+        for (int lvl = 0; lvl <= deg; ++lvl) {
+            for (int q = 0; q <= lvl; ++q) c[q] += nw[lvl] * basis[q];
+            // basis *= (j - x_lvl)
+            long double nb[6] = {0, 0, 0, 0, 0, 0};
+            for (int q = 0; q <= lvl; ++q) { nb[q + 1] += basis[q]; nb[q] -= basis[q] * (long double)x[lvl]; }
+            for (int q = 0; q < 6; ++q) basis[q] = nb[q];
+        }
+        const long double c1 = c[1], c2 = c[2], c3 = c[3], c4 = deg == 4 ? c[4] : 0.0L;
+        M.m[4 * 0 + col - 1] = (double)(c1 + c2 + c3 + c4);
+        M.m[4 * 1 + col - 1] = (double)(2 * c2 + 6 * c3 + 14 * c4);
+        M.m[4 * 2 + col - 1] = (double)(6 * c3 + 36 * c4);
+        M.m[4 * 3 + col - 1] = (double)(24 * c4);
+    }
+    return M;
+}
+
 static void build_schedule(gwin_plan* p) {
-    // Blocks over [band0, kmax).  Quartic through 5 nodes {0, ~.15, .5, ~.85, 1}(B-1):
-    // |err| <= max|Psi^(5)| / 5! * max|prod (j - t_i)|, with max|prod| <= 0.005 (B-1)^5
-    // for these nodes (Chebyshev-Lobatto-like).  Leading-order chirp:
-    //   Psi(f) = 3/128 (pi Mc f)^(-5/3)  =>  |Psi^(5)(f)| = 3/128 (pi Mc)^(-5/3) * K5 * f^(-20/3)
-    //   K5 = (5/3)(8/3)(11/3)(14/3)(17/3); x2 safety for the higher PN orders.
+    // Blocks over [band0, kmax).  Inside a block the chirp phase is replaced by the polynomial
+    // through deg+1 exact samples at (rounded) Chebyshev-Lobatto nodes; with the leading-order
+    // chirp Psi(f) = 3/128 (pi Mc f)^(-5/3) the interpolation error is bounded by
+    //   quartic: |Psi^(5)|/5! * 0.005    (B-1)^5      cubic: |Psi^(4)|/4! * 0.015625 (B-1)^4
+    // (x2 safety for the higher PN orders).  Each block takes whichever degree is cheaper per
+    // bin: the cubic saves one complex multiply per bin but needs shorter blocks.
     const PlanDev& d = p->d;
     const int band0 = std::max(d.kmin, d.istart);
-    p->blk_start.clear();
-    const double K5 = (5.0 / 3) * (8.0 / 3) * (11.0 / 3) * (14.0 / 3) * (17.0 / 3);
-    const double pref = 2.0 * (3.0 / 128.0) * pow(G_PI * p->mchirp_min * G_MTSUN, -5.0 / 3.0) * K5
-                        * pow(d.delta_f, 5.0);
+    p->blk_start.clear(); p->blk_mat.clear(); p->mats.clear();
+    std::vector<int> mat_of((MAX_BLOCK + MIN_BLOCK + 8) * 2, -1);
+    auto mat_index = [&](int B, int deg) {
+        if (deg == 0) { B = 0; }
+        int& slot = mat_of[(size_t)B * 2 + (deg == 3 ? 1 : 0)];
+        if (slot < 0) { slot = (int)p->mats.size(); p->mats.push_back(make_block_mat(B, deg)); }
+        return slot;
+    };
+    const double K4 = (5.0 / 3) * (8.0 / 3) * (11.0 / 3) * (14.0 / 3), K5 = K4 * (17.0 / 3);
+    const double chirp = 2.0 * (3.0 / 128.0) * pow(G_PI * p->mchirp_min * G_MTSUN, -5.0 / 3.0);
+    const double setup_cost = 450.0, bin4 = 80.0, bin3 = 71.0;      // FP64-pipe cycles (ncu r1b)
     int k = std::max(band0, 1);
     while (k < d.kmax) {
         const double f = k * d.delta_f;
-        const double d5 = pref * pow(f, -20.0 / 3.0);            // rad / bin^5
-        double B = pow(p->phase_tol * 120.0 / (0.005 * d5), 0.2) + 1.0;
-        int Bi = (int)std::min<double>(B, MAX_BLOCK);
-        // too curved for an 8-bin quartic: 4-bin blocks take the direct path in the kernel
-        Bi = Bi >= MIN_BLOCK ? (Bi & ~3) : 4;
+        const double d5 = chirp * K5 * pow(d.delta_f, 5.0) * pow(f, -20.0 / 3.0);   // rad / bin^5
+        const double d4 = chirp * K4 * pow(d.delta_f, 4.0) * pow(f, -17.0 / 3.0);   // rad / bin^4
+        const double B4 = std::min<double>(pow(p->phase_tol * 120.0 / (0.005 * d5), 0.2) + 1.0, MAX_BLOCK);
+        const double B3 = std::min<double>(pow(p->phase_tol * 24.0 / (0.015625 * d4), 0.25) + 1.0, MAX_BLOCK);
+        int deg = 4, Bi = (int)B4;
+        if (B3 >= MIN_BLOCK && bin3 + setup_cost / B3 < bin4 + setup_cost / B4) { deg = 3; Bi = (int)B3; }
+        if (Bi >= MIN_BLOCK) Bi &= ~3; else { Bi = 4; deg = 0; }    // too curved: direct evaluation
         if (k + Bi > d.kmax) Bi = d.kmax - k;
+        if (Bi < MIN_BLOCK) deg = 0;
         p->blk_start.push_back(k);
+        p->blk_mat.push_back(mat_index(Bi, deg));
         k += Bi;
     }
     p->blk_start.push_back(d.kmax);
-    p->n_blk = (int)p->blk_start.size() - 1;
-    // a trailing block shorter than 5 bins cannot carry 5 distinct nodes: merge it
-    if (p->n_blk >= 2) {
-        const int last = p->blk_start[p->n_blk] - p->blk_start[p->n_blk - 1];
-        const int prev = p->blk_start[p->n_blk - 1] - p->blk_start[p->n_blk - 2];
-        if (last < MIN_BLOCK && prev >= MIN_BLOCK) {
-            p->blk_start.erase(p->blk_start.end() - 2);
-            p->n_blk--;
-        }
-    }
+    p->n_blk = (int)p->blk_mat.size();
 }
 
 static int upload_schedule(gwin_plan* p) {
     build_schedule(p);
-    if (p->d_blk_start) cudaFree(p->d_blk_start);
-    p->d_blk_start = nullptr;
+    cudaFree(p->d_blk_start); cudaFree(p->d_blk_mat); cudaFree(p->d_mats);
+    p->d_blk_start = p->d_blk_mat = nullptr; p->d_mats = nullptr;
     CK(cudaMalloc(&p->d_blk_start, sizeof(int) * p->blk_start.size()));
-    CK(cudaMemcpy(p->d_blk_start, p->blk_start.data(), sizeof(int) * p->blk_start.size(),
-                  cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&p->d_blk_mat, sizeof(int) * (p->blk_mat.size() + 1)));
+    CK(cudaMalloc(&p->d_mats, sizeof(BlockMat) * p->mats.size()));
+    CK(cudaMemcpy(p->d_blk_start, p->blk_start.data(), sizeof(int) * p->blk_start.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(p->d_blk_mat, p->blk_mat.data(), sizeof(int) * p->blk_mat.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(p->d_mats, p->mats.data(), sizeof(BlockMat) * p->mats.size(), cudaMemcpyHostToDevice));
     p->sched_dirty = false;
     return GWIN_OK;
 }
@@ -831,7 +997,7 @@ extern "C" int gwin_plan_create(gwin_plan** out, int device, int n_det, int64_t 
     }
 
     // tables (built once per plan, on the host, in extended precision)
-    std::vector<double> basis((size_t)n_f * 4), T((size_t)n_f * n_det * 2, 0.0), C((size_t)n_det * (n_f + 1), 0.0);
+    std::vector<double> basis((size_t)n_f * 4), T((size_t)(n_f + 4) * n_det * 2, 0.0), C((size_t)n_det * (n_f + 1), 0.0);
     std::vector<long double> f76(n_f, 0.0L), f73(n_f, 0.0L);
     basis[0] = 1.0; basis[1] = 1.0; basis[2] = 0.0; basis[3] = 0.0;
     for (int64_t k = 1; k < n_f; ++k) {
@@ -887,7 +1053,7 @@ extern "C" void gwin_plan_destroy(gwin_plan* p) {
     if (!p) return;
     cudaSetDevice(p->device);
     cudaFree((void*)p->d.basis); cudaFree((void*)p->d.T); cudaFree((void*)p->d.C);
-    cudaFree(p->d_blk_start);
+    cudaFree(p->d_blk_start); cudaFree(p->d_blk_mat); cudaFree(p->d_mats);
     cudaFree(p->d_wc); cudaFree(p->d_ks); cudaFree(p->d_ke);
     cudaFree(p->d_key_in); cudaFree(p->d_key_out); cudaFree(p->d_perm_in); cudaFree(p->d_perm_out);
     cudaFree(p->d_partial); cudaFree(p->d_cub);
@@ -990,6 +1156,7 @@ static void launch_main(gwin_plan* p, bool recur, int W, int wpad, int n_chunks,
     dim3 grid((W + CTA_THREADS - 1) / CTA_THREADS, n_chunks);
     if (recur)
         loglr_recur_kernel<ND><<<grid, CTA_THREADS, 0, st>>>(p->d, W, wpad, per_chunk, p->n_blk, p->d_blk_start,
+                                                            p->d_blk_mat, p->d_mats,
                                                             p->d_wc, p->d_ks, p->d_ke, p->d_partial);
     else
         loglr_direct_kernel<ND><<<grid, CTA_THREADS, 0, st>>>(p->d, W, wpad, per_chunk, n_chunks,
@@ -1165,29 +1332,44 @@ extern "C" int gwin_generate_host(gwin_plan* p, const double* params, double* h_
     return GWIN_OK;
 }
 
-extern "C" int gwin_fp64_peak(int device, double* dfma_per_sec) {
-    if (!dfma_per_sec) return fail(GWIN_EINVAL, "NULL argument");
+template <int V>
+static int run_probe(int device, double* rate) {
     CK(cudaSetDevice(device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 1 << 15;
+    const double per_iter = V == 2 ? 16.0 : 8.0;      // FP64 instructions per thread per iteration
     double* out = nullptr;
     CK(cudaMalloc(&out, sizeof(double) * threads * blocks));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    dfma_probe_kernel<<<blocks, threads>>>(out, 1024);
+    dfma_probe_kernel<V><<<blocks, threads>>>(out, 1024);
     double best = 0.0;
     for (int rep = 0; rep < 5; ++rep) {
         CK(cudaEventRecord(e0));
-        dfma_probe_kernel<<<blocks, threads>>>(out, iters);
+        dfma_probe_kernel<V><<<blocks, threads>>>(out, iters);
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, e0, e1));
-        const double rate = (double)threads * blocks * iters * 8.0 / (ms * 1e-3);
-        best = std::max(best, rate);
+        best = std::max(best, (double)threads * blocks * iters * per_iter / (ms * 1e-3));
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
-    *dfma_per_sec = best;
+    *rate = best;
     return GWIN_OK;
+}
+
+extern "C" int gwin_fp64_peak(int device, double* dfma_per_sec) {
+    if (!dfma_per_sec) return fail(GWIN_EINVAL, "NULL argument");
+    return run_probe<0>(device, dfma_per_sec);
+}
+
+extern "C" int gwin_fp64_probe(int device, int variant, double* ops_per_sec) {
+    if (!ops_per_sec) return fail(GWIN_EINVAL, "NULL argument");
+    switch (variant) {
+        case 0: return run_probe<0>(device, ops_per_sec);
+        case 1: return run_probe<1>(device, ops_per_sec);
+        case 2: return run_probe<2>(device, ops_per_sec);
+        default: return fail(GWIN_EINVAL, "variant must be 0..2");
+    }
 }

@@ -132,6 +132,12 @@ int gwin_plan_kernel_timing(gwin_plan* plan, int enable, double* mean_ms, int* n
  * DFMA loop and returns achieved FP64 FMA lane-ops per second. */
 int gwin_fp64_peak(int device, double* dfma_per_sec);
 
+/* Diagnostic variants of the probe (FP64 instructions x 32 lanes per second):
+ * 0 = gwin_fp64_peak; 1 = DFMAs whose three source registers are all private to the
+ * instruction (no operand-reuse cache help); 2 = the hot loop's pattern, independent
+ * complex multiplications (2 DMUL + 2 DFMA each). */
+int gwin_fp64_probe(int device, int variant, double* ops_per_sec);
+
 const char* gwin_last_error(void);
 const char* gwin_version(void);
 

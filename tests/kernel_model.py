@@ -70,28 +70,75 @@ class PlanModel(object):
         self.phase_tol, self.mchirp_min = phase_tol, mchirp_min
         self.blk_start = self.build_schedule()
 
+    @staticmethod
+    def block_mat(B, deg):
+        """make_block_mat: nodes and the linear map samples -> forward differences."""
+        if deg == 0:
+            return None
+        e = B - 1
+        if deg == 4:
+            q = (e + 4) // 8
+            x = [0, q, e // 2, e - q, e]
+        else:
+            q = (e + 2) // 4
+            x = [0, q, e - q, e]
+        ld = np.longdouble
+        m = np.zeros((4, 4))
+        for col in range(1, deg + 1):
+            dd = [ld(0)] * (deg + 1)
+            dd[col] = ld(1)
+            nw = [dd[0]]
+            for lvl in range(1, deg + 1):
+                for i in range(0, deg + 1 - lvl):
+                    dd[i] = (dd[i + 1] - dd[i]) / ld(x[i + lvl] - x[i])
+                nw.append(dd[0])
+            c = [ld(0)] * 6
+            basis = [ld(1)] + [ld(0)] * 5
+            for lvl in range(deg + 1):
+                for q_ in range(lvl + 1):
+                    c[q_] += nw[lvl] * basis[q_]
+                nb = [ld(0)] * 6
+                for q_ in range(lvl + 1):
+                    nb[q_ + 1] += basis[q_]
+                    nb[q_] -= basis[q_] * ld(x[lvl])
+                basis = nb
+            c1, c2, c3 = c[1], c[2], c[3]
+            c4 = c[4] if deg == 4 else ld(0)
+            m[0, col - 1] = float(c1 + c2 + c3 + c4)
+            m[1, col - 1] = float(2 * c2 + 6 * c3 + 14 * c4)
+            m[2, col - 1] = float(6 * c3 + 36 * c4)
+            m[3, col - 1] = float(24 * c4)
+        return {"deg": deg, "node": x[1:], "m": m}
+
     def build_schedule(self):
         band0 = max(self.kmin, self.istart)
-        K5 = (5. / 3) * (8. / 3) * (11. / 3) * (14. / 3) * (17. / 3)
-        pref = 2.0 * (3. / 128.) * (PI * self.mchirp_min * MTSUN) ** (-5. / 3) * K5 \
-            * self.delta_f ** 5
-        out = []
+        K4 = (5. / 3) * (8. / 3) * (11. / 3) * (14. / 3)
+        K5 = K4 * (17. / 3)
+        chirp = 2.0 * (3. / 128.) * (PI * self.mchirp_min * MTSUN) ** (-5. / 3)
+        setup_cost, bin4, bin3 = 450.0, 80.0, 71.0
+        out, self.blk_deg = [], []
         k = max(band0, 1)
         while k < self.kmax:
             f = k * self.delta_f
-            d5 = pref * f ** (-20. / 3)
-            B = (self.phase_tol * 120.0 / (0.005 * d5)) ** 0.2 + 1.0
-            Bi = int(min(B, MAX_BLOCK))
-            # too curved for an 8-bin quartic: 4-bin blocks take the direct path
-            Bi = (Bi & ~3) if Bi >= MIN_BLOCK else 4
+            d5 = chirp * K5 * self.delta_f ** 5 * f ** (-20. / 3)
+            d4 = chirp * K4 * self.delta_f ** 4 * f ** (-17. / 3)
+            B4 = min((self.phase_tol * 120.0 / (0.005 * d5)) ** 0.2 + 1.0, MAX_BLOCK)
+            B3 = min((self.phase_tol * 24.0 / (0.015625 * d4)) ** 0.25 + 1.0, MAX_BLOCK)
+            deg, Bi = 4, int(B4)
+            if B3 >= MIN_BLOCK and bin3 + setup_cost / B3 < bin4 + setup_cost / B4:
+                deg, Bi = 3, int(B3)
+            if Bi >= MIN_BLOCK:
+                Bi &= ~3
+            else:
+                Bi, deg = 4, 0
             if k + Bi > self.kmax:
                 Bi = self.kmax - k
+            if Bi < MIN_BLOCK:
+                deg = 0
             out.append(k)
+            self.blk_deg.append(deg)
             k += Bi
         out.append(self.kmax)
-        if len(out) - 1 >= 2 and out[-1] - out[-2] < MIN_BLOCK and \
-                out[-2] - out[-3] >= MIN_BLOCK:
-            del out[-2]
         return out
 
     # -- walker_setup_kernel --------------------------------------------------
@@ -255,42 +302,24 @@ class PlanModel(object):
             j = np.arange(B)
             k = kb + j
             on = (k >= ks) & (k < ke)
-            if B < 5:
+            M = self.block_mat(B, self.blk_deg[b])
+            if M is None:
                 psi = self.phase_turns(w, k)
                 for d in range(self.n_det):
                     ph = psi + k * w['tau'][d]
                     S[d] += np.sum(np.where(on, self.T[d, k], 0) * np.exp(-2j * PI * ph))
                 continue
-            e = B - 1
-            t1 = (e + 4) // 8
-            t2 = e // 2
-            t3 = e - t1
-            nodes = np.array([0, t1, t2, t3, e])
-            fv = self.phase_turns(w, kb + nodes)
-            x1, x2, x3, x4 = float(t1), float(t2), float(t3), float(e)
-            d01 = (fv[1] - fv[0]) / x1
-            d12 = (fv[2] - fv[1]) / (x2 - x1)
-            d23 = (fv[3] - fv[2]) / (x3 - x2)
-            d34 = (fv[4] - fv[3]) / (x4 - x3)
-            d012 = (d12 - d01) / x2
-            d123 = (d23 - d12) / (x3 - x1)
-            d234 = (d34 - d23) / (x4 - x2)
-            d0123 = (d123 - d012) / x3
-            d1234 = (d234 - d123) / (x4 - x1)
-            n4 = (d1234 - d0123) / x4
-            n1, n2, n3 = d01, d012, d0123
-            e1, e2, e3 = x1 + x2 + x3, x1 * x2 + x1 * x3 + x2 * x3, x1 * x2 * x3
-            c4 = n4
-            c3 = n3 - n4 * e1
-            c2 = n2 - n3 * (x1 + x2) + n4 * e2
-            c1 = n1 - n2 * x1 + n3 * (x1 * x2) - n4 * e3
-            D1 = c1 + c2 + c3 + c4
-            D2 = 2.0 * c2 + 6.0 * c3 + 14.0 * c4
-            D3 = 6.0 * c3 + 36.0 * c4
-            D4 = 24.0 * c4
+            deg = M["deg"]
+            f0 = self.phase_turns(w, kb)
+            fn = self.phase_turns(w, kb + np.array(M["node"]))
+            D = M["m"][:, :deg].dot(fn - f0)
+            D1, D2, D3, D4 = D
             if return_phase_err:
                 exact = self.phase_turns(w, k)
-                poly = fv[0] + j * (c1 + j * (c2 + j * (c3 + j * c4)))
+                # the polynomial the differences describe, by summation
+                d1 = D1 + np.concatenate([[0.], np.cumsum(D2 + np.concatenate([[0.], np.cumsum(
+                    D3 + D4 * np.arange(B - 2))])[:B - 1])])[:B - 1] if B > 2 else np.array([D1])
+                poly = f0 + np.concatenate([[0.], np.cumsum(d1)])
                 max_err = max(max_err, float(np.max(np.abs(exact - poly)[on])) * TWOPI
                               if on.any() else 0.0)
             tq = np.exp(2j * PI * D4)
@@ -304,9 +333,10 @@ class PlanModel(object):
                     acc = acc * g + Tk[jj]
                     g = g * rq
                     rq = rq * sq
-                    sq = sq * tq
-                kend = kb + e
-                anchor = fv[4] + np.modf(kend * w['tau'][d])[0]
+                    if deg == 4:
+                        sq = sq * tq
+                kend = kb + B - 1
+                anchor = fn[-1] + np.modf(kend * w['tau'][d])[0]
                 S[d] += acc * np.exp(-2j * PI * anchor)
         out = self.finish(w, S, marg)
         if return_phase_err:

@@ -1,0 +1,61 @@
+"""The CUDA kernels' arithmetic, modelled in numpy (tests/kernel_model.py), against
+the oracle: coefficient folding, closed-form <h|h>, and the block recurrence with
+its schedule.  Runs without a GPU; the GPU tests check the real kernels."""
+import numpy as np
+import pytest
+
+import gwin_oracle as O
+import util
+from kernel_model import PlanModel
+
+
+def _plan(cfg, **kw):
+    D = [O.Detector(d) for d in cfg.dets]
+    return PlanModel(cfg.delta_f, cfg.epoch, cfg.f_lower, None, cfg.f_lower,
+                     [d.response for d in D], [d.location for d in D],
+                     np.stack([cfg.data[d] for d in cfg.dets]),
+                     np.stack([cfg.psd] * len(cfg.dets)), **kw)
+
+
+@pytest.mark.parametrize("epoch", [0.0, 1126259462.0])
+def test_direct_and_recurrence_match_oracle_bbh(epoch):
+    cfg = util.c2(epoch=epoch)
+    pm = _plan(cfg, mchirp_min=8.0)
+    orc = cfg.oracle()
+    rng = np.random.default_rng(1)
+    P = util.draw_bbh(rng, 5, cfg)
+    P[0] = util.inj_row(cfg)
+    for row in P:
+        lr0 = orc.loglr(**dict(zip(util.PARAM_ORDER, row)))[0]
+        assert abs(pm.loglr_direct(row)[0] - lr0) <= util.tol(lr0)
+        lr, hd, hh, perr = pm.loglr_recur(row, return_phase_err=True)
+        assert abs(lr - lr0) <= util.tol(lr0)
+        assert perr <= pm.phase_tol          # the schedule's bound holds
+
+
+def test_recurrence_bns_256s_schedule_bound():
+    """C3: quartic blocks sized for mchirp >= 1.0 keep the block-polynomial phase
+    error under phase_tol for walkers of the C3 mass box, and loglr within 1e-6."""
+    cfg = util.c3()
+    pm = _plan(cfg, mchirp_min=1.0)
+    bs = np.diff(pm.blk_start)
+    assert bs.sum() == pm.kmax - pm.kmin and bs.min() >= 4 and bs.max() <= 263
+    assert bs.mean() > 150                  # long blocks dominate: setup is amortised
+    orc = cfg.oracle()
+    rng = np.random.default_rng(2)
+    P = util.draw_bns(rng, 2, cfg)
+    P[0, :2] = 1.2, 1.2                     # lowest chirp mass of the box
+    for row in P:
+        lr0 = orc.loglr(**dict(zip(util.PARAM_ORDER, row)))[0]
+        lr, hd, hh, perr = pm.loglr_recur(row, return_phase_err=True)
+        assert perr <= pm.phase_tol
+        assert abs(lr - lr0) <= util.tol(lr0)
+
+
+def test_marginalized_phase_model():
+    cfg = util.c2()
+    pm = _plan(cfg, mchirp_min=8.0)
+    orc = cfg.oracle(phase_marginalization=True)
+    row = util.inj_row(cfg)
+    lr0 = orc.loglr(**dict(zip(util.PARAM_ORDER, row)))[0]
+    assert abs(pm.loglr_recur(row, marg=True)[0] - lr0) <= util.tol(lr0)

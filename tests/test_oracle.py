@@ -1,0 +1,254 @@
+"""Pins for the oracle.  The reference's own tests hold exactly one
+numeric pin for this path -- argmax over a tc grid (test/test_models.py:105-117);
+everything else here is an internal-consistency check of the restated
+[UPSTREAM] arithmetic, plus the committed golden vectors."""
+import glob
+import math
+import os
+
+import numpy as np
+import pytest
+from scipy import special
+
+import gwin_oracle as O
+import util
+from c_oracle import COracle
+from kernel_model import PlanModel
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_reference_tc_grid_argmax():
+    """(i) the reference's pin: zero-noise data = injected waveform, 4 s @ 2048 Hz,
+    fmin 30, H1/L1/V1, 30+30 Msun; argmax over tc = 1.1 + arange(8192)/2048 is 3.1."""
+    inj = dict(util.BBH_INJ)
+    inj["tc"] = 3.1
+    cfg = util.Config("ref", 4, 2048., 30., ["H1", "L1", "V1"], inj, noise=False)
+    orc = cfg.oracle()
+    times = 1.1 + np.arange(8192) / 2048.
+    idx = np.unique(np.concatenate([np.arange(0, 8192, 8), np.arange(4080, 4112)]))
+    vals = []
+    for t in times[idx]:
+        p = dict(cfg.inj)
+        p["tc"] = t
+        vals.append(orc.loglr(**p)[0])
+    assert np.isclose(times[idx][int(np.argmax(vals))], 3.1)
+
+
+@pytest.mark.parametrize("mk", [util.c1, util.c2])
+def test_zero_noise_identity(mk):
+    """(ii) loglr(theta_inj) = 1/2 sum_det <h|h> in zero noise."""
+    cfg = mk(noise=False)
+    lr, hd, hh = cfg.oracle().loglr(**cfg.inj)
+    assert abs(lr - 0.5 * sum(hh.values())) <= 1e-9 * lr
+    for d in cfg.dets:
+        assert abs(hd[d].imag) <= 1e-9 * hh[d]
+
+
+def test_hh_closed_form_and_tables():
+    """(iii) <h|h> = |A|^2 (C[ke] - C[ks]) equals the direct sum."""
+    cfg = util.c2()
+    orc = cfg.oracle()
+    D = [O.Detector(d) for d in cfg.dets]
+    pm = PlanModel(cfg.delta_f, cfg.epoch, cfg.f_lower, None, cfg.f_lower,
+                   [d.response for d in D], [d.location for d in D],
+                   np.stack([cfg.data[d] for d in cfg.dets]),
+                   np.stack([cfg.psd] * len(cfg.dets)), mchirp_min=8.0)
+    rng = np.random.default_rng(1)
+    P = util.draw_bbh(rng, 6, cfg)
+    for row in P:
+        lr0, hd0, hh0 = orc.loglr(**dict(zip(util.PARAM_ORDER, row)))
+        w = pm.walker(row)
+        for j, d in enumerate(cfg.dets):
+            assert abs(w['hh'][j] / hh0[d] - 1) < 1e-12
+    assert abs(pm.lognl_det.sum() / orc.lognl() - 1) < 1e-13
+
+
+def test_detector_geometry():
+    """(iv) the hard-coded arm vectors / response tensors against the detectors'
+    geodetic coordinates and arm azimuths (LALDetectors.h, radians; azimuth East of
+    North), and the tensor's algebraic properties."""
+    geo = {"H1": (0.81079526383, -2.08405676917, 5.65487724844, 4.08408092164, 142.554),
+           "L1": (0.53342313506, -1.58430937078, 4.40317772346, 2.83238139666, -6.574),
+           "V1": (0.76151183984, 0.18333805213, 0.33916285222, 5.05155183261, 51.884)}
+    a, b = 6378137.0, 6356752.314
+    for name, (lat, lon, xaz, yaz, h) in geo.items():
+        det = O.Detector(name)
+        eE = np.array([-math.sin(lon), math.cos(lon), 0.])
+        eN = np.array([-math.sin(lat) * math.cos(lon), -math.sin(lat) * math.sin(lon), math.cos(lat)])
+        xa = math.cos(xaz) * eN + math.sin(xaz) * eE
+        ya = math.cos(yaz) * eN + math.sin(yaz) * eE
+        resp = 0.5 * (np.outer(xa, xa) - np.outer(ya, ya))
+        # arm tilts (<= 7e-4 rad) are neglected here
+        assert np.max(np.abs(resp - det.response)) < 1.5e-3
+        # WGS-84 vertex
+        n = a * a / math.sqrt(a * a * math.cos(lat) ** 2 + b * b * math.sin(lat) ** 2)
+        loc = np.array([(n + h) * math.cos(lat) * math.cos(lon),
+                        (n + h) * math.cos(lat) * math.sin(lon),
+                        ((b * b) / (a * a) * n + h) * math.sin(lat)])
+        assert np.max(np.abs(loc - det.location)) < 5.0      # metres
+        assert np.allclose(det.response, det.response.T)
+        assert abs(np.trace(det.response)) < 1e-7
+    # survey's remembered tensor entries
+    assert abs(O.Detector("H1").response[0, 0] - (-0.3926141858)) < 1e-7
+    assert abs(O.Detector("L1").response[0, 0] - 0.4112809) < 1e-6
+    assert abs(O.Detector("V1").response[1, 1] - (-0.4478258)) < 1e-6
+
+
+def test_antenna_pattern_properties():
+    det = O.Detector("H1")
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        ra, dec, psi = rng.uniform(0, 6.28), rng.uniform(-1.5, 1.5), rng.uniform(0, 3.14)
+        t = 1e9 + rng.uniform(0, 1e6)
+        fp, fc = det.antenna_pattern(ra, dec, psi, t)
+        fp2, fc2 = det.antenna_pattern(ra, dec, psi + math.pi / 4, t)
+        # rotating the polarisation by 45 deg maps (F+, Fx) -> (Fx, -F+)
+        assert abs(fp2 - fc) < 1e-12 and abs(fc2 + fp) < 1e-12
+        assert fp * fp + fc * fc <= 1.0 + 1e-12
+        assert abs(det.time_delay_from_earth_center(ra, dec, t)) <= 6.4e6 / O.LAL_C_SI
+
+
+def test_gmst_and_leap_seconds():
+    assert O.gps_leap_seconds(0) == 0
+    assert O.gps_leap_seconds(1126259462) == 17
+    assert O.gps_leap_seconds(1187008882) == 18
+    # IAU-1982 GMST in hours: 18.697374558 + 24.06570982441908 D (D = JD_UT - 2451545.0)
+    for gps in (0.0, 1126259462.0, 1187008882.43):
+        utc = gps - O.gps_leap_seconds(int(gps))
+        D = 2444244.5 + utc / 86400.0 - 2451545.0
+        h = 18.697374558 + 24.06570982441908 * D
+        ref = (h % 24.0) * math.pi / 12.0
+        got = O.gmst(gps) % (2 * math.pi)
+        assert abs((got - ref + math.pi) % (2 * math.pi) - math.pi) < 2e-5
+
+
+def test_taylorf2_against_closed_forms():
+    """SPA amplitude and Newtonian chirp time (SURVEY.md A.2 'Check')."""
+    m1, m2, dist, df, flow = 1.4, 1.4, 40.0, 1.0 / 64, 20.0
+    hp, hc = O.taylorf2_hp_hc(m1, m2, 0, 0, dist, 0.0, 0.0, df, flow)
+    k = np.arange(int(flow / df) + 1, len(hp))
+    f = k * df
+    mc = (m1 * m2) ** 0.6 / (m1 + m2) ** 0.2 * O.LAL_MTSUN_SI
+    D = dist * 1e6 * O.LAL_PC_SI / O.LAL_C_SI
+    amp = math.sqrt(5. / 24.) * math.pi ** (-2. / 3.) * mc ** (5. / 6.) / D * f ** (-7. / 6.)
+    assert np.allclose(np.abs(hp[k]), amp, rtol=1e-12)
+    assert np.allclose(hc[k], -1j * hp[k])            # face-on
+    assert np.all(hp[:int(math.ceil(flow / df))] == 0)
+    assert len(hp) == int(1.0 / (6 ** 1.5 * math.pi * (m1 + m2) * O.LAL_MTSUN_SI) / df + 1)
+    # dPsi/df = -2 pi tau0(f) at leading order, tau0 = 5/(256 eta) M (pi M f)^(-8/3);
+    # the 1PN+ corrections are < 10 % at 20-40 Hz for a BNS
+    ph = O.taylorf2_phasing(m1, m2)
+    M = (m1 + m2) * O.LAL_MTSUN_SI
+
+    def psi(fr):
+        v = np.cbrt(math.pi * M * fr)
+        lv = np.log(v)
+        pv, pl = ph["v"], ph["vlogv"]
+        return (pv[0] + pv[2] * v ** 2 + pv[3] * v ** 3 + pv[4] * v ** 4 + (pv[5] + pl[5] * lv) * v ** 5
+                + (pv[6] + pl[6] * lv) * v ** 6 + pv[7] * v ** 7) / v ** 5
+    sel = (f > 22) & (f < 40)
+    dpsi = (psi(f[sel] + 1e-4) - psi(f[sel] - 1e-4)) / 2e-4
+    tau0 = 5. / (256. * 0.25) * M * (math.pi * M * f[sel]) ** (-8. / 3.)
+    assert np.all(np.abs(dpsi / (-2 * math.pi * tau0) - 1) < 0.1)
+    # and the generated series carries exactly that phase: h ~ exp(-i (Psi - pi/4))
+    kk = k[sel]
+    model = np.exp(-1j * (psi(kk * df) - math.pi / 4))
+    assert np.allclose(hp[kk] / np.abs(hp[kk]), -model, atol=1e-6)   # amp0 < 0
+
+
+def test_spin_terms_known_limits():
+    """1.5PN spin-orbit: equal masses, equal spins => 4 beta = (188/6) chi."""
+    a = O.taylorf2_phasing(10., 10., 0.3, 0.3)
+    b = O.taylorf2_phasing(10., 10., 0.0, 0.0)
+    pfaN = 3. / (128 * 0.25)
+    assert abs((a["v"][3] - b["v"][3]) / pfaN - 188. / 6. * 0.3) < 1e-12
+    # non-spinning coefficients are untouched by chi = 0
+    c = O.taylorf2_phasing(10., 7., 0.0, 0.0)
+    assert abs(c["v"][3] / (3. / (128 * c["eta"])) + 16 * math.pi) < 1e-12
+
+
+def test_cutoff_indices_and_psd():
+    assert O.get_cutoff_indices(20., None, 0.125, 16384) == (160, 8192)
+    assert O.get_cutoff_indices(30., None, 0.25, 8192) == (120, 4096)
+    assert O.get_cutoff_indices(20., 1000., 0.125, 16384) == (160, 8000)
+    assert O.get_cutoff_indices(None, None, 0.125, 16384)[0] == 1
+    with pytest.raises(ValueError):
+        O.get_cutoff_indices(100., 50., 0.125, 16384)
+    psd = O.aligo_zdhp_psd(4097, 0.25, 30.)
+    assert np.all(psd[:120] == 0) and np.all(psd[120:] > 0)
+    x = 245.0 / 245.4
+    ref = 1e-48 * (0.0152 * x ** -4 + 0.2935 * x ** 2.25 + 2.7951 * x ** 1.5 - 6.5080 * x ** 0.75 + 17.7622)
+    assert abs(psd[4 * 245] / ref - 1) < 1e-14
+    # minimum of the ZDHP curve sits near 245 Hz at ~ (3.8e-24)^2
+    assert 3.5e-24 < np.sqrt(psd[120:].min()) < 4.1e-24
+
+
+def test_log_i0():
+    """(vi) log I0 via i0e equals numpy.log(scipy.special.i0(x)) where finite."""
+    x = np.concatenate([np.linspace(0, 20, 101), np.linspace(20, 700, 97)])
+    assert np.allclose([O.log_i0(v) for v in x], np.log(special.i0(x)), rtol=1e-13, atol=1e-15)
+    assert np.isfinite(O.log_i0(5000.0))
+
+
+@pytest.mark.parametrize("mk,draw,W", [(util.c1, util.draw_bbh, 12), (util.c2, util.draw_bbh, 12),
+                                        (util.c3, util.draw_bns, 3)])
+def test_faithful_vs_truth_and_c_port(mk, draw, W):
+    """(v) float64-faithful vs extended-precision modes agree to < 1e-7; the C
+    restatement agrees with the numpy one."""
+    cfg = mk()
+    rng = np.random.default_rng(9)
+    P = draw(rng, W, cfg)
+    P[0] = util.inj_row(cfg)
+    a = O.batch_loglr(cfg.oracle(), P)
+    b = O.batch_loglr(cfg.oracle(mode="truth"), P)
+    assert np.max(np.abs(a[0] - b[0])) < 1e-7
+    co = COracle(cfg.data, cfg.delta_f, cfg.epoch, cfg.f_lower, psds=cfg.psds())
+    for mode, marg in ((0, False), (1, True)):
+        ref = O.batch_loglr(cfg.oracle(phase_marginalization=marg), P)
+        c = co.batch_loglr(P, mode=mode, nthreads=4)
+        assert np.max(np.abs(ref[0] - c[0])) < 1e-7
+        assert np.max(np.abs(ref[1] - c[1])) < 1e-7
+        assert np.allclose(ref[2], c[2], rtol=1e-12)
+    assert abs(co.lognl() / cfg.oracle().lognl() - 1) < 1e-13
+
+
+def test_no_waveform_and_short_waveform():
+    cfg = util.c1()
+    orc = cfg.oracle()
+    co = COracle(cfg.data, cfg.delta_f, cfg.epoch, cfg.f_lower, psds=cfg.psds())
+    p = dict(cfg.inj)
+    p["mass1"] = p["mass2"] = 100.        # f_ISCO ~ 22 Hz: 16 bins
+    lr, hd, hh = orc.loglr(**p)
+    assert np.isfinite(lr) and all(v > 0 for v in hh.values())
+    row = np.array([[p[k] for k in util.PARAM_ORDER]])
+    assert abs(co.batch_loglr(row)[0][0] - lr) < 1e-9
+    row[0, 0] = row[0, 1] = 150.          # f_ISCO < f_lower: lalsim refuses -> -inf
+    assert co.batch_loglr(row)[0][0] == -np.inf
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "*.npz"))))
+def test_golden_vectors(path):
+    """The committed golden vectors are reproduced bit-for-bit-ish by the numpy
+    oracle and to 1e-7 by the C restatement."""
+    g = np.load(path)
+    name = os.path.basename(path)
+    cfg = {"c1_gaussian_h1l1.npz": lambda: util.c1(),
+           "c2_margphase_h1l1v1.npz": lambda: util.c2(),
+           "c3_bns256_h1l1v1.npz": lambda: util.c3(),
+           "c2_gps_epoch.npz": lambda: util.c2(epoch=1126259462.0, seed=7)}[name]()
+    import hashlib
+    h = hashlib.sha256()
+    for d in cfg.dets:
+        h.update(np.ascontiguousarray(cfg.data[d]).tobytes())
+    assert h.hexdigest() == str(g["data_sha256"]), "synthetic data generator changed"
+    marg = bool(g["marg"])
+    orc = cfg.oracle(phase_marginalization=marg)
+    assert (orc._kmin, orc._kmax) == (int(g["kmin"]), int(g["kmax"]))
+    lr, hd, hh = O.batch_loglr(orc, g["params"])
+    assert np.max(np.abs(lr - g["loglr"])) <= 1e-9
+    assert np.allclose(hh, g["hh"], rtol=1e-12)
+    assert np.max(np.abs(lr - g["loglr_truth"])) <= 1e-7
+    co = COracle(cfg.data, cfg.delta_f, cfg.epoch, cfg.f_lower, psds=cfg.psds())
+    lc = co.batch_loglr(g["params"], mode=int(marg), nthreads=2)[0]
+    assert np.max(np.abs(lc - g["loglr"])) <= 1e-7

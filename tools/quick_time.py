@@ -1,4 +1,4 @@
-"""Development timing probe (not the bench): C3 batch, both kernels, CUDA events."""
+"""Development timing probe (not the bench): C3-style batch, CUDA events."""
 import os
 import sys
 import time
@@ -13,37 +13,46 @@ from gwin_b200 import _lib
 
 W = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 seglen = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+kernels = sys.argv[3].split(",") if len(sys.argv) > 3 else ["direct", "recurrence"]
 t0 = time.time()
 cfg = util.c3(seglen=seglen)
 model = cfg.cuda_model()
-print("setup %.1fs  kmin %d kmax %d" % (time.time() - t0, model._kmin, model._kmax))
-print("fp64 peak: %.3e DFMA/s" % _lib.fp64_peak(0))
+print("lib %s setup %.1fs  kmin %d kmax %d" % (os.path.basename(_lib.LIB_PATH), time.time() - t0, model._kmin, model._kmax))
 rng = np.random.default_rng(20182)
 P = util.draw_bns(rng, W, cfg)
 n = np.array([min(int(1.0 / (6 ** 1.5 * np.pi * (a + b) * 4.925491025543576e-06) / cfg.delta_f + 1), model._kmax) - model._kmin
               for a, b in P[:, :2]])
 bins = n.mean()
-print("mean bins/eval %.0f" % bins)
 Pd = torch.tensor(P, device="cuda")
 res = {}
-for name, kid in (("direct", 1), ("recurrence", 2)):
+for name in kernels:
+    kid = {"direct": 1, "recurrence": 2}[name]
     model.plan.configure(kernel=kid, mchirp_min=1.0)
     out = model.plan.loglr_device(Pd)
     torch.cuda.synchronize()
     res[name] = out[0].cpu().numpy()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 3
+    reps = 5
     e0.record()
     for _ in range(reps):
         model.plan.loglr_device(Pd, out=out)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
+    # cold-L2 variant (what bench.py times): flush between reps
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    cold = 0.0
+    for _ in range(reps):
+        flush.fill_(1)
+        e0.record()
+        model.plan.loglr_device(Pd, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        cold += e0.elapsed_time(e1) / reps
+    print("   cold-L2 %.3f ms/batch" % cold)
     evs = W / (ms * 1e-3)
-    print("%-10s W=%d  %.2f ms/batch  %.3e evals/s  %.3e bin-evals/s  (x68 slots = %.2f%% of 1.861e13)"
-          % (name, W, ms, evs, evs * bins, 100 * evs * bins * 68 / 1.861e13))
-d = np.abs(res["direct"] - res["recurrence"])
-print("max |direct - recurrence| = %.3e" % d.max())
-t0 = time.time()
-lr, hd, hh = model.plan.loglr_host(P)
-print("host API: %.2f ms" % ((time.time() - t0) * 1e3))
+    print("%-10s W=%d T=%d  %.3f ms/batch  %.3e evals/s  %.3e bin-evals/s  (x68 slots = %.1f%% of 1.861e13; x32 = %.1f%%)"
+          % (name, W, seglen, ms, evs, evs * bins, 100 * evs * bins * 68 / 1.861e13, 100 * evs * bins * 32 / 1.861e13))
+if len(res) == 2:
+    d = np.abs(res["direct"] - res["recurrence"])
+    print("max |direct - recurrence| = %.3e" % d.max())
