@@ -512,29 +512,108 @@ __device__ __forceinline__ void load_block_coef(const double* sc, PhaseCoef& pc,
     }
 }
 
+// ---------------------------------------------------------------------------
+// Per-warp table stream: the rows T[k][0..ND) the warp is about to consume are staged in
+// shared memory by the TMA engine (cp.async.bulk global->shared, completion on an mbarrier),
+// one 64-bin tile ahead of the arithmetic, double buffered.  The hot loop then reads
+// warp-uniform LDS.128 (broadcast, fixed ~30-cycle latency) instead of LDG, so no L1/L2
+// latency is ever exposed and no registers are spent on load pipelining.
+// (ncu r1c: with LDG the compiler, at 96 registers, placed one load 8 instructions ahead of
+// its use -- 31 % of hot-loop stall samples were long_scoreboard.)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+
+template <int ND>
+struct TileStream {
+    static constexpr int TILE = ND <= 3 ? 64 : 32;     // bins per tile
+    double2* buf;          // this warp's [2][TILE * ND] staging buffers
+    uint32_t bar;          // shared-memory address of this warp's 2 mbarriers
+    const double2* T;      // global table
+    int ka, kz;            // stream covers bins [ka, kz)
+    int cur;               // tile currently readable (-1: none yet)
+    int lane;
+
+    __device__ __forceinline__ void issue(int t) const {           // lane 0 only
+        const int k0 = ka + t * TILE;
+        if (k0 >= kz) return;
+        const uint32_t bytes = (uint32_t)(min(TILE, kz - k0) * ND * (int)sizeof(double2));
+        const uint32_t dst = smem_u32(buf + (size_t)(t & 1) * TILE * ND);
+        const uint32_t b = bar + 8u * (uint32_t)(t & 1);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(dst), "l"(T + (size_t)k0 * ND), "r"(bytes), "r"(b) : "memory");
+    }
+    __device__ __forceinline__ void open(double2* buf_, uint64_t* bars, const double2* T_, int ka_, int kz_, int lane_) {
+        buf = buf_; bar = smem_u32(bars); T = T_; ka = ka_; kz = kz_; cur = -1; lane = lane_;
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar + 8u) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            issue(0);
+        }
+        __syncwarp();
+    }
+    // make the tile holding bin k readable; bins are consumed in increasing order
+    __device__ __forceinline__ void ensure(int k) {
+        const int t = (k - ka) / TILE;
+        if (t == cur) return;
+        __syncwarp();                              // every lane is done with tile t-1 ...
+        if (lane == 0) issue(t + 1);               // ... so its buffer can take tile t+1
+        mbar_wait(bar + 8u * (uint32_t)(t & 1), (uint32_t)((t >> 1) & 1));
+        cur = t;
+    }
+    __device__ __forceinline__ const double2* row(int k) const {
+        const int r = k - ka;
+        return buf + (size_t)((r / TILE) & 1) * TILE * ND + (size_t)(r % TILE) * ND;
+    }
+    __device__ __forceinline__ int tile_end(int k) const {         // first bin of the next tile
+        return ka + ((k - ka) / TILE + 1) * TILE;
+    }
+    // no bulk copy may be in flight when the CTA retires
+    __device__ __forceinline__ void close() {
+        const int t = cur + 1;
+        if (ka + t * TILE < kz) mbar_wait(bar + 8u * (uint32_t)(t & 1), (uint32_t)((t >> 1) & 1));
+    }
+};
+
 template <int ND>
 __device__ __forceinline__ void direct_block(const double* sc, const double4* __restrict__ basis,
-                                             const double2* __restrict__ T, int kb, int B, int lo, int hi,
+                                             TileStream<ND>& S, int kb, int B, int lo, int hi,
                                              double2 (&acc_out)[ND]) {
     // too curved / too short for a polynomial block: evaluate these bins directly
     PhaseCoef pc;
     double tau_hi[ND], tau_lo[ND];
     load_block_coef<ND>(sc, pc, tau_hi, tau_lo);
     for (int k = kb; k < kb + B; ++k) {
+        S.ensure(k);
         if (k < lo || k >= hi) continue;
+        const double2* sp = S.row(k);
         const double psi = phase_turns(pc, ld_basis(basis + k));
         const double kd = (double)k;
 #pragma unroll
         for (int d = 0; d < ND; ++d) {
             const double2 u = phasor_neg(psi + fma(kd, tau_lo[d], frac1(kd * tau_hi[d])));
-            acc_out[d] = cfma(__ldg(T + (size_t)k * ND + d), u, acc_out[d]);
+            acc_out[d] = cfma(sp[d], u, acc_out[d]);
         }
     }
 }
 
 template <int ND, bool MASKED, int DEG>
 __device__ __forceinline__ void recur_block(
-        const double* sc, const double4* __restrict__ basis, const double2* __restrict__ T,
+        const double* sc, const double4* __restrict__ basis, TileStream<ND>& S,
         const BlockMat* __restrict__ M, int kb, int B, int lo, int hi, double2 (&acc_out)[ND]) {
     PhaseCoef pc;
     double tau_hi[ND], tau_lo[ND];
@@ -560,61 +639,36 @@ __device__ __forceinline__ void recur_block(
     double2 rq = phasor_pos(D[1]);
     double2 g[ND], acc[ND];
     const double kend = (double)(kb + B - 1);
-    // Software-pipelined table reads: the rows of bins j+2 / j+3 are requested while bins
-    // j / j+1 are consumed, so the latency of the warp-uniform LDG.128s is covered by >= 64
-    // FP64 instructions of this warp (ncu r1: 48 % of stall samples were long_scoreboard on
-    // loads consumed in the iteration that issued them).  Rows up to kb+B+1 are touched; the
-    // table is padded by 4 rows past kmax.
-    const double2* __restrict__ Tp = T + (size_t)kb * ND;
-    double2 Ta[ND], Tb[ND];
-#pragma unroll
-    for (int d = 0; d < ND; ++d) {
-        g[d] = phasor_pos(D[0] + (tau_hi[d] + tau_lo[d]));
-        double2 T0 = __ldg(Tp + d);
-        Ta[d] = __ldg(Tp + ND + d);
-        Tb[d] = __ldg(Tp + 2 * ND + d);
-        if (MASKED && !(kb >= lo && kb < hi)) T0 = make_double2(0.0, 0.0);
-        acc[d] = T0;
-    }
-    Tp += 3 * ND;                         // -> row of bin 3
-    int j = 1;
-#pragma unroll 2
-    for (; j + 1 < B; j += 2) {
-        {
-            const bool on = !MASKED || ((kb + j >= lo) && (kb + j < hi));
-#pragma unroll
-            for (int d = 0; d < ND; ++d) {
-                double2 Tk = Ta[d];
-                Ta[d] = __ldg(Tp + d);                      // bin j+2
-                if (MASKED && !on) Tk = make_double2(0.0, 0.0);
-                acc[d] = cfma(acc[d], g[d], Tk);
-                g[d] = cmul(g[d], rq);
-            }
-            rq = cmul(rq, sq);
-            if (DEG == 4) sq = cmul(sq, tq);
-        }
-        {
-            const bool on = !MASKED || ((kb + j + 1 >= lo) && (kb + j + 1 < hi));
-#pragma unroll
-            for (int d = 0; d < ND; ++d) {
-                double2 Tk = Tb[d];
-                Tb[d] = __ldg(Tp + ND + d);                 // bin j+3
-                if (MASKED && !on) Tk = make_double2(0.0, 0.0);
-                acc[d] = cfma(acc[d], g[d], Tk);
-                g[d] = cmul(g[d], rq);
-            }
-            rq = cmul(rq, sq);
-            if (DEG == 4) sq = cmul(sq, tq);
-        }
-        Tp += 2 * ND;
-    }
-    if (j < B) {                          // odd tail: bin B-1 sits in Ta
-        const bool on = !MASKED || ((kb + j >= lo) && (kb + j < hi));
+    S.ensure(kb);
+    {
+        const double2* sp = S.row(kb);
 #pragma unroll
         for (int d = 0; d < ND; ++d) {
-            double2 Tk = Ta[d];
-            if (MASKED && !on) Tk = make_double2(0.0, 0.0);
-            acc[d] = cfma(acc[d], g[d], Tk);
+            g[d] = phasor_pos(D[0] + (tau_hi[d] + tau_lo[d]));
+            double2 T0 = sp[d];
+            if (MASKED && !(kb >= lo && kb < hi)) T0 = make_double2(0.0, 0.0);
+            acc[d] = T0;
+        }
+    }
+    // Horner over the remaining bins, one shared-memory tile segment at a time
+    int k = kb + 1;
+    const int kn = kb + B;
+    while (k < kn) {
+        S.ensure(k);
+        const int ke = min(kn, S.tile_end(k));
+        const double2* sp = S.row(k);
+#pragma unroll 4
+        for (; k < ke; ++k, sp += ND) {
+            const bool on = !MASKED || ((k >= lo) && (k < hi));
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                double2 Tk = sp[d];
+                if (MASKED && !on) Tk = make_double2(0.0, 0.0);
+                acc[d] = cfma(acc[d], g[d], Tk);
+                g[d] = cmul(g[d], rq);
+            }
+            rq = cmul(rq, sq);
+            if (DEG == 4) sq = cmul(sq, tq);
         }
     }
 #pragma unroll
@@ -625,7 +679,7 @@ __device__ __forceinline__ void recur_block(
 }
 
 #ifndef RECUR_MIN_CTAS
-#define RECUR_MIN_CTAS 5
+#define RECUR_MIN_CTAS 4
 #endif
 template <int ND>
 __global__ void __launch_bounds__(CTA_THREADS, RECUR_MIN_CTAS)
@@ -658,7 +712,11 @@ loglr_recur_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_blk,
 #pragma unroll
     for (int d = 0; d < ND; ++d) acc[d] = make_double2(0.0, 0.0);
 
+    constexpr int TILE = TileStream<ND>::TILE;
+    constexpr int NWARP = CTA_THREADS / WARP;
     __shared__ double s_coef[RC_ROWS(ND) * CTA_THREADS];
+    __shared__ __align__(128) double2 s_tile[NWARP][2 * TILE * ND];
+    __shared__ __align__(8) uint64_t s_bar[NWARP][2];
     if (wlo < whi) {
         const int tt = live ? t : 0;
         double* sc = s_coef + threadIdx.x;
@@ -670,25 +728,26 @@ loglr_recur_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_blk,
             sc[(9 + 2 * d) * CTA_THREADS] = row[D_TAUHI * wpad];
             sc[(10 + 2 * d) * CTA_THREADS] = row[D_TAULO * wpad];
         }
-        const int lane = threadIdx.x & (WARP - 1);
+        const int lane = threadIdx.x & (WARP - 1), warp = threadIdx.x / WARP;
+        TileStream<ND> S;
+        bool opened = false;
         for (int b = b0; b < b1; ++b) {
             const int kb = blk_start[b], kn = blk_start[b + 1];
             if (kn <= wlo || kb >= whi) continue;       // nobody in this warp needs it
+            if (!opened) {                              // stream starts at the first needed block
+                S.open(s_tile[warp], s_bar[warp], P.T, kb, k1, lane);
+                opened = true;
+            }
 #ifndef NO_L2_PREFETCH
-            // Pull the NEXT block's table rows (and its 5 basis nodes) into L2 now, one
-            // 128-byte line per lane: every line of the table is first touched by a whole
-            // wave-front of CTAs at once, and an un-prefetched first touch parks all of
-            // them on a DRAM round trip (ncu r1b: 7 % L2 misses, long_scoreboard top stall).
+            // Pull the NEXT block's table rows (and its basis nodes) into L2 now, one 128-byte
+            // line per lane: every line of the table is first touched by a whole wave-front of
+            // CTAs at once, and an un-prefetched first touch parks all of them on DRAM.
             if (b + 1 < b1 && kn < whi) {
                 const int kn2 = blk_start[b + 2];
                 const char* base = reinterpret_cast<const char*>(P.T + (size_t)kn * ND);
                 const int bytes = (kn2 - kn) * ND * (int)sizeof(double2);
                 for (int off = lane * 128; off < bytes; off += WARP * 128)
-#ifdef PREFETCH_L1
-                    asm volatile("prefetch.global.L1 [%0];" :: "l"(base + off));
-#else
                     asm volatile("prefetch.global.L2 [%0];" :: "l"(base + off));
-#endif
                 if (lane < 5) {
                     const BlockMat* M2 = mats + blk_mat[b + 1];
                     const int node = lane == 0 ? 0 : M2->node[lane - 1];
@@ -700,15 +759,16 @@ loglr_recur_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_blk,
             const int deg = M->deg;
             const bool full = kb >= ilo && kn <= ihi;       // every lane covers the whole block
             if (deg == 4) {
-                if (full) recur_block<ND, false, 4>(sc, P.basis, P.T, M, kb, kn - kb, lo, hi, acc);
-                else      recur_block<ND, true, 4>(sc, P.basis, P.T, M, kb, kn - kb, lo, hi, acc);
+                if (full) recur_block<ND, false, 4>(sc, P.basis, S, M, kb, kn - kb, lo, hi, acc);
+                else      recur_block<ND, true, 4>(sc, P.basis, S, M, kb, kn - kb, lo, hi, acc);
             } else if (deg == 3) {
-                if (full) recur_block<ND, false, 3>(sc, P.basis, P.T, M, kb, kn - kb, lo, hi, acc);
-                else      recur_block<ND, true, 3>(sc, P.basis, P.T, M, kb, kn - kb, lo, hi, acc);
+                if (full) recur_block<ND, false, 3>(sc, P.basis, S, M, kb, kn - kb, lo, hi, acc);
+                else      recur_block<ND, true, 3>(sc, P.basis, S, M, kb, kn - kb, lo, hi, acc);
             } else {
-                direct_block<ND>(sc, P.basis, P.T, kb, kn - kb, lo, hi, acc);
+                direct_block<ND>(sc, P.basis, S, kb, kn - kb, lo, hi, acc);
             }
         }
+        if (opened) S.close();
     }
     if (live) {
 #pragma unroll
