@@ -34,7 +34,7 @@
 #include "../../include/gwin_b200.h"
 
 // ---------------------------------------------------------------------------
-// constants (LAL values; see oracle/gwin_oracle.py for provenance)
+// constants (LAL values; provenance in DESIGN.md)
 // ---------------------------------------------------------------------------
 #define G_PI      3.141592653589793238462643383279502884
 #define G_TWOPI   6.283185307179586476925286766559005768

@@ -1,0 +1,201 @@
+"""The drop-in boundary on the GPU: model protocol, CallModel, BatchPool, samplers
+(``-m gpu``).  The likelihood behind every call here is the CUDA library."""
+import numpy as np
+import pytest
+from scipy import stats
+
+import gwin_oracle as O
+import util
+from gwin_b200 import distributions as D
+from gwin_b200 import models
+from gwin_b200.pool import BatchPool
+from gwin_b200.sampler import EmceeEnsembleSampler, EmceePTSampler
+from gwin_b200.types import FrequencySeries
+from gwin_b200.waveform import (FDomainCBCGenerator, FDomainDetFrameGenerator,
+                                NoWaveformError)
+from oracle_model import OracleGaussianNoise
+from util import PARAM_ORDER, tol
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cfg():
+    return util.c2()
+
+
+def test_scalar_protocol_matches_oracle(cfg):
+    """update(**params) then the cached stat properties, as CallModel drives them."""
+    model = cfg.cuda_model()
+    orc = cfg.oracle()
+    p = dict(cfg.inj)
+    p["distance"] = 420.0
+    model.update(**p)
+    lr0, hd0, hh0 = orc.loglr(**p)
+    assert abs(model.loglr - lr0) <= tol(lr0)
+    assert abs(model.lognl - orc.lognl()) <= 1e-9 * abs(orc.lognl())
+    assert abs(model.loglikelihood - (lr0 + orc.lognl())) <= 1e-9 * abs(orc.lognl())
+    assert model.logprior == 0. and model.logjacobian == 0.
+    assert abs(model.logplr - lr0) <= tol(lr0)
+    for det in cfg.dets:
+        assert abs(model.det_optimal_snrsq(det) - hh0[det]) <= 1e-9 * hh0[det]
+        assert abs(model.det_cplx_loglr(det) - (hd0[det] - 0.5 * hh0[det])) <= 2e-6
+        assert abs(model.det_lognl(det) - orc.det_lognl(det)) <= 1e-9 * abs(orc.det_lognl(det))
+    names = model.default_stats
+    assert names[:4] == ['logjacobian', 'logprior', 'loglikelihood', 'loglr']
+    assert set(names[4:]) == set(['%s_cplx_loglr' % d for d in cfg.dets] +
+                                 ['%s_optimal_snrsq' % d for d in cfg.dets])
+    st = model.current_stats
+    assert abs(st['loglr'] - lr0) <= tol(lr0)
+    # the model whitened its own copy of the data, not the caller's
+    assert np.allclose(model.data['H1'].numpy()[200], cfg.data['H1'][200] * np.sqrt(4 * cfg.delta_f / cfg.psd[200]))
+    # no waveform -> -inf and the reference's placeholder stats (gaussian_noise.py:293-302)
+    model.update(**dict(p, mass1=200., mass2=200.))
+    assert model.loglr == -np.inf
+    assert model.current_stats['H1_optimal_snrsq'] == 0.
+
+
+def test_constructor_errors(cfg):
+    gen = FDomainDetFrameGenerator(FDomainCBCGenerator, 0., detectors=['H1', 'L1'],
+                                   variable_args=PARAM_ORDER, delta_f=cfg.delta_f, f_lower=20.)
+    data = {d: FrequencySeries(cfg.data[d], cfg.delta_f, 0.) for d in cfg.dets}
+    with pytest.raises(ValueError):        # detectors differ (gaussian_noise.py:227-233)
+        models.GaussianNoise(PARAM_ORDER, data, gen, 20.)
+    gen3 = FDomainDetFrameGenerator(FDomainCBCGenerator, 5., detectors=cfg.dets,
+                                    variable_args=PARAM_ORDER, delta_f=cfg.delta_f, f_lower=20.)
+    with pytest.raises(ValueError):        # epoch differs (:235-238)
+        models.GaussianNoise(PARAM_ORDER, data, gen3, 20.)
+    gen0 = FDomainDetFrameGenerator(FDomainCBCGenerator, 0., detectors=cfg.dets,
+                                    variable_args=PARAM_ORDER, delta_f=cfg.delta_f, f_lower=20.)
+    bad = dict(data)
+    bad['V1'] = FrequencySeries(cfg.data['V1'][:-10], cfg.delta_f, 0.)
+    with pytest.raises(ValueError):        # lengths differ (:240-242)
+        models.GaussianNoise(PARAM_ORDER, bad, gen0, 20.)
+    with pytest.raises(ValueError):        # kmax <= kmin
+        models.GaussianNoise(PARAM_ORDER, data, gen0, 20., f_upper=10.)
+    with pytest.raises(ValueError):
+        FDomainDetFrameGenerator(FDomainCBCGenerator, 0., detectors=cfg.dets, delta_f=1., f_lower=20.,
+                                 approximant="IMRPhenomPv2")
+    with pytest.raises(AttributeError):    # no marginalisation flag (marginalized...:258-261)
+        models.MarginalizedGaussianNoise(PARAM_ORDER, data, gen0, 20., psds=cfg.psds())
+    with pytest.raises(AttributeError):    # no marg_prior (:265-268)
+        models.MarginalizedGaussianNoise(PARAM_ORDER, data, gen0, 20., psds=cfg.psds(),
+                                         phase_marginalization=True)
+    with pytest.raises(NotImplementedError):
+        models.MarginalizedGaussianNoise(PARAM_ORDER, data, gen0, 20., psds=cfg.psds(),
+                                         time_marginalization=True,
+                                         marg_prior=[D.Uniform(time=(0., 1.))])
+
+
+def test_marginalized_model_reference_kwargs(cfg):
+    model = cfg.cuda_model(cls=models.MarginalizedGaussianNoise, phase_marginalization=True,
+                           marg_prior=[D.UniformAngle(phase=None)])
+    orc = cfg.oracle(phase_marginalization=True)
+    p = dict(cfg.inj)
+    model.update(**p)
+    lr0, hd0, hh0 = orc.loglr(**p)
+    assert abs(model.loglr - lr0) <= tol(lr0)
+    st = model.current_stats
+    for det in cfg.dets:
+        assert abs(st['%s_optimal_snrsq' % det] - hh0[det]) <= 1e-9 * hh0[det]
+        assert abs(st['%s_matchedfilter_snrsq' % det] - hd0[det]) <= 2e-6
+    assert model.phase_prior.shape == (10 ** 4,)
+    # coa_phase drops out of the marginalised statistic
+    model.update(**dict(p, coa_phase=2.9))
+    assert abs(model.loglr - lr0) <= 1e-6
+
+
+def test_pool_map_equals_scalar_calls(cfg):
+    prior = D.JointDistribution(
+        ['tc', 'distance', 'inclination'],
+        D.Uniform(tc=(cfg.inj['tc'] - 0.05, cfg.inj['tc'] + 0.05)),
+        D.UniformRadius(distance=(50., 1000.)), D.SinAngle(inclination=None))
+    static = {k: v for k, v in cfg.inj.items() if k not in ('tc', 'distance', 'inclination')}
+    model = cfg.cuda_model(variable_params=('tc', 'distance', 'inclination'),
+                           static_params=static, prior=prior)
+    rng = np.random.RandomState(4)
+    pts = np.column_stack([cfg.inj['tc'] + rng.uniform(-0.06, 0.06, 64), rng.uniform(20., 1100., 64),
+                           rng.uniform(-0.2, 3.3, 64)])
+    call = models.CallModel(model, 'logplr')
+    pool = BatchPool()
+    mapped = pool.map(call, pts)
+    assert pool.ncalls == 1 and model.plan.last_launches >= 3
+    for p, (v, blob) in zip(pts[:16], mapped[:16]):
+        v0, blob0 = call(p)
+        assert v == v0 or abs(v - v0) <= 1e-9 * abs(v0)
+        for a, b in zip(blob, blob0):
+            assert (np.isnan(a) and np.isnan(b)) or a == b or abs(a - b) <= 1e-9 * abs(a) + 1e-9
+    vals = np.array([m[0] for m in mapped])
+    assert np.isneginf(vals).any() and np.isfinite(vals).any()
+
+
+def test_generate_matches_oracle_waveform(cfg):
+    gen = FDomainDetFrameGenerator(FDomainCBCGenerator, 0., detectors=cfg.dets,
+                                   variable_args=PARAM_ORDER, delta_f=cfg.delta_f, f_lower=20.)
+    h = gen.generate(**cfg.inj)
+    ref = O.FDomainDetFrameGenerator(0., cfg.dets, cfg.delta_f, 20.).generate(**cfg.inj)
+    for d in cfg.dets:
+        assert len(h[d]) == len(ref[d])
+        scale = np.abs(ref[d]).max()
+        assert np.max(np.abs(h[d].numpy() - ref[d])) <= 1e-8 * scale
+    with pytest.raises(NoWaveformError):
+        gen.generate(**dict(cfg.inj, mass1=300., mass2=300.))
+
+
+def test_device_resident_call_equals_host_call(cfg):
+    import torch
+    model = cfg.cuda_model()
+    rng = np.random.default_rng(8)
+    P = util.draw_bbh(rng, 300, cfg)
+    a = model.plan.loglr_host(P)
+    lr, hd, hh = model.plan.loglr_device(torch.tensor(P, device="cuda"))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(lr.cpu().numpy(), a[0])
+    np.testing.assert_array_equal(hh.cpu().numpy(), a[2])
+    np.testing.assert_array_equal(hd.cpu().numpy()[..., 0], a[1].real)
+
+
+def test_posterior_consistency_ks_vs_oracle():
+    """Fixed-seed emcee-semantics run on C1 with the CUDA likelihood against the same
+    sampler driven by the CPU oracle: two-sample KS p > 0.01 per parameter
+    (BASELINE.json north_star; scipy.stats.ks_2samp as in gwin/burn_in.py:23,64)."""
+    cfg = util.c1()
+    names = ['tc', 'distance', 'inclination', 'coa_phase']
+    prior = D.JointDistribution(
+        names, D.Uniform(tc=(cfg.inj['tc'] - 0.02, cfg.inj['tc'] + 0.02)),
+        D.UniformRadius(distance=(100., 1500.)), D.SinAngle(inclination=None),
+        D.UniformAngle(coa_phase=None))
+    static = {k: v for k, v in cfg.inj.items() if k not in names}
+    cuda = cfg.cuda_model(variable_params=tuple(names), static_params=static, prior=prior)
+    orc = OracleGaussianNoise(names, cfg, static_params=static, prior=prior, nthreads=8)
+    chains = []
+    for m in (cuda, orc):
+        np.random.seed(20183)
+        s = EmceeEnsembleSampler(m, 200, model_call=models.CallModel(m, 'logplr'))
+        s.set_p0()
+        s.run(400)
+        chains.append(s.chain[:, 200::20, :].reshape(-1, len(names)))
+    for i, n in enumerate(names):
+        p = stats.ks_2samp(chains[0][:, i], chains[1][:, i]).pvalue
+        assert p > 0.01, (n, p)
+    # the two runs share a seed, so they should in fact follow each other closely
+    assert np.mean(np.all(np.isclose(chains[0], chains[1], rtol=1e-6, atol=1e-9), axis=1)) > 0.5
+    # and the sampler finds the injection
+    assert abs(np.median(chains[0][:, 0]) - cfg.inj['tc']) < 2e-3
+
+
+def test_pt_sampler_runs_on_gpu(cfg):
+    prior = D.JointDistribution(['tc', 'distance'],
+                                D.Uniform(tc=(cfg.inj['tc'] - 0.05, cfg.inj['tc'] + 0.05)),
+                                D.UniformRadius(distance=(50., 1000.)))
+    static = {k: v for k, v in cfg.inj.items() if k not in ('tc', 'distance')}
+    model = cfg.cuda_model(cls=models.MarginalizedPhaseGaussianNoise, variable_params=('tc', 'distance'),
+                           static_params=static, prior=prior)
+    np.random.seed(3)
+    pt = EmceePTSampler(model, 4, 64)
+    pt.set_p0()
+    pt.run(20)
+    assert pt.chain.shape == (4, 64, 20, 2)
+    assert np.all(np.isfinite(pt.lnpost))
+    ms = pt.model_stats
+    assert np.all(np.isfinite(ms['loglr']))

@@ -1,0 +1,185 @@
+"""Host-side logic that surrounds the kernel: priors, transforms, the model /
+CallModel / pool protocols and the ensemble steppers (no GPU needed; the data
+model is the oracle-backed test double)."""
+import numpy as np
+import pytest
+from scipy import stats
+
+import util
+from gwin_b200 import distributions as D
+from gwin_b200 import models, transforms as T
+from gwin_b200.pool import BatchPool
+from gwin_b200.sampler import (EmceeEnsembleSampler, EmceePTSampler,
+                               default_beta_ladder, samplers)
+from oracle_model import OracleGaussianNoise
+
+
+def test_no_prior_and_default_stats():
+    """reference test/test_models.py:30-81"""
+    p = models.base._NoPrior()
+    assert p.apply_boundary_conditions(a=1, b=2) == {'a': 1, 'b': 2}
+    assert p() == 0.
+    m = models.TestNormal('x')
+    call = models.CallModel(m, 'logposterior')
+    assert call.variable_params == ('x',)
+    assert isinstance(call.prior_distribution, models.base._NoPrior)
+    call.update(x=0.3)
+    assert call.logjacobian == 0.
+    assert call([0.3])[0] == m._dist.logpdf([0.3])
+    assert set(['logjacobian', 'logprior', 'loglikelihood']).issubset(call.default_stats)
+
+
+def test_registry_and_names():
+    assert set(models.models) >= {'gaussian_noise', 'marginalized_gaussian_noise', 'test_normal'}
+    assert models.models['gaussian_noise'] is models.GaussianNoise
+    assert set(samplers) == {'emcee', 'emcee_pt'}
+
+
+def test_distributions_vectorised():
+    rng = np.random.RandomState(0)
+    u = D.Uniform(a=(1., 3.), b=(-1., 1.))
+    x = {'a': np.array([0.5, 2., 3.5]), 'b': np.array([0., 0., 0.])}
+    assert np.allclose(u(**x), [-np.inf, np.log(0.25), -np.inf])
+    s = D.SinAngle(inclination=None)
+    th = np.linspace(0.01, np.pi - 0.01, 7)
+    assert np.allclose(s.pdf(inclination=th), 0.5 * np.sin(th))
+    assert np.allclose(s.apply_boundary_conditions(inclination=np.array([-0.1, np.pi + 0.2]))['inclination'],
+                       [0.1, np.pi - 0.2])
+    c = D.CosAngle(dec=None)
+    assert np.allclose(c.pdf(dec=np.array([0.0])), 0.5)
+    a = D.UniformAngle(ra=None)
+    assert np.allclose(a.apply_boundary_conditions(ra=np.array([-0.5, 7.0]))['ra'],
+                       [2 * np.pi - 0.5, 7.0 - 2 * np.pi])
+    r = D.UniformRadius(distance=(10., 100.))
+    d = r.rvs(20000, rng)['distance']
+    assert stats.kstest((d ** 3 - 1e3) / (1e6 - 1e3), 'uniform').pvalue > 1e-3
+    sky = D.UniformSky()
+    j = D.JointDistribution(['ra', 'dec', 'a', 'b'], sky, u)
+    draw = j.rvs(1000, rng)
+    assert draw.fieldnames == ('ra', 'dec', 'a', 'b')
+    assert np.all(np.isfinite(j(**{n: draw[n] for n in draw.fieldnames})))
+    with pytest.raises(ValueError):
+        D.JointDistribution(['ra'], u)
+    jc = D.JointDistribution(['a', 'b'], u, constraints=[lambda p: p['a'] > 2.0])
+    assert np.all(jc.rvs(200, rng)['a'] > 2.0)
+    assert jc(a=np.array([1.5]), b=np.array([0.]))[0] == -np.inf
+
+
+def test_transforms_roundtrip_and_jacobian():
+    t = T.MchirpQToMass1Mass2()
+    x = {'mchirp': np.array([1.2, 20.]), 'q': np.array([1.0, 3.0])}
+    y = t.transform(x)
+    z = t.inverse_transform(y)
+    assert np.allclose(z['mchirp'], x['mchirp']) and np.allclose(z['q'], x['q'])
+    assert np.all(y['mass1'] >= y['mass2'])
+    # numerical Jacobian
+    eps = 1e-6
+    for i in range(2):
+        def f(mc, q):
+            o = t.transform({'mchirp': mc, 'q': q})
+            return np.array([o['mass1'], o['mass2']])
+        mc, q = x['mchirp'][i], x['q'][i]
+        J = np.column_stack([(f(mc + eps, q) - f(mc - eps, q)) / (2 * eps),
+                             (f(mc, q + eps) - f(mc, q - eps)) / (2 * eps)])
+        assert abs(abs(np.linalg.det(J)) / t.jacobian(x)[i] - 1) < 1e-6
+        assert abs(t.jacobian(x)[i] * t.inverse_jacobian(y)[i] - 1) < 1e-9
+    lg = T.Logit('x', 'lx', domain=(0., 2.))
+    v = lg.inverse_transform(lg.transform({'x': np.array([0.3, 1.7])}))
+    assert np.allclose(v['x'], [0.3, 1.7])
+
+
+def _model(cfg, **kw):
+    prior = D.JointDistribution(
+        ['tc', 'distance'],
+        D.Uniform(tc=(cfg.inj['tc'] - 0.05, cfg.inj['tc'] + 0.05)),
+        D.UniformRadius(distance=(50., 1000.)))
+    static = {k: v for k, v in cfg.inj.items() if k not in ('tc', 'distance')}
+    return OracleGaussianNoise(['tc', 'distance'], cfg, static_params=static, prior=prior, **kw)
+
+
+def test_batch_equals_scalar_calls_and_short_circuit():
+    """evaluate_batch == W x CallModel.__call__ (reference models/__init__.py:101-137),
+    including the logprior = -inf short-circuit (base.py:556-568)."""
+    cfg = util.c1()
+    m = _model(cfg)
+    rng = np.random.RandomState(3)
+    pts = np.column_stack([cfg.inj['tc'] + rng.uniform(-0.06, 0.06, 12), rng.uniform(20., 1100., 12)])
+    for callstat in ('logposterior', 'logplr', 'loglikelihood', 'logprior'):
+        call = models.CallModel(m, callstat)
+        scalar = [call(p) for p in pts]
+        batch = call.batch(pts).rows()
+        pool = BatchPool().map(call, pts)
+        for (v0, s0), (v1, s1), (v2, s2) in zip(scalar, batch, pool):
+            assert v0 == v1 == v2 or abs(v0 - v1) <= 1e-9 * abs(v0)
+            for a, b in zip(s0, s1):
+                assert (np.isnan(a) and np.isnan(b)) or a == b or abs(a - b) <= 1e-9 * abs(a)
+    out = models.CallModel(m, 'logposterior').batch(pts)
+    outside = np.isneginf(out.stats['logprior'])
+    assert outside.any() and not outside.all()
+    assert np.all(np.isneginf(out.values[outside]))
+    assert np.all(np.isnan(out.stats['loglikelihood'][outside]))     # never evaluated
+    call = models.CallModel(m, 'logposterior', return_all_stats=False)
+    assert BatchPool().map(call, pts[:3]) == [call(p) for p in pts[:3]]
+
+
+def test_pool_falls_back_to_plain_map_and_global_model():
+    pool = BatchPool()
+    assert pool.map(lambda x: 2 * x, [1, 2, 3]) == [2, 4, 6]
+    assert pool.count == 1
+    m = models.TestNormal(['x'])
+    models._global_instance = models.CallModel(m, 'loglikelihood', return_all_stats=False)
+    try:
+        got = pool.map(models._call_global_model, [[0.], [1.]])
+        assert np.allclose(got, [m._dist.logpdf([0.]), m._dist.logpdf([1.])])
+    finally:
+        models._global_instance = None
+
+
+def test_ensemble_sampler_recovers_normal():
+    np.random.seed(11)
+    prior = D.JointDistribution(['x', 'y'], D.Uniform(x=(-20, 20), y=(-20, 20)))
+    cov = [[1., .5], [.5, 2.]]
+    m = models.TestNormal(['x', 'y'], mean=[1., -2.], cov=cov, prior=prior)
+    s = EmceeEnsembleSampler(m, 200)
+    p0 = s.set_p0()
+    assert p0.shape == (200, 2)
+    s.run(250)
+    assert s.chain.shape == (200, 250, 2) and s.lnpost.shape == (200, 250)
+    assert s.model_stats.shape == (200, 250)
+    c = s.chain[:, 120::10, :].reshape(-1, 2)
+    assert np.all(np.abs(c.mean(0) - [1., -2.]) < 0.1)
+    assert np.allclose(np.cov(c.T), cov, atol=0.25)
+    assert 0.5 < s.acceptance_fraction.mean() < 0.9
+    assert stats.kstest(c[:, 0] - 1., stats.norm.cdf).pvalue > 1e-3
+    s.clear_chain()
+    assert s.chain.shape[1] == 0 and s.niterations == 250
+
+
+def test_pt_sampler_and_ladder():
+    assert np.allclose(default_beta_ladder(2, 3), [1., 1 / 7., 1 / 49.])
+    np.random.seed(5)
+    prior = D.JointDistribution(['x'], D.Uniform(x=(-10, 10)))
+    m = models.TestNormal(['x'], mean=[0.5], cov=[0.25], prior=prior)
+    pt = EmceePTSampler(m, 3, 40)
+    assert pt.set_p0().shape == (3, 40, 1)
+    pt.run(300)
+    assert pt.chain.shape == (3, 40, 300, 1)
+    cold = pt.chain[0][:, 100:, 0].ravel()
+    assert abs(cold.mean() - 0.5) < 0.05 and abs(cold.std() - 0.5) < 0.06
+    hot = pt.chain[2][:, 100:, 0].ravel()
+    assert hot.std() > cold.std()
+    ms = pt.model_stats
+    assert ms['loglr'].shape == (3, 40, 300)
+
+
+def test_data_model_sampler_smoke():
+    """reference test/test_sampler.py: every sampler runs set_p0 -> run(4)."""
+    cfg = util.c1()
+    m = _model(cfg)
+    np.random.seed(2)
+    for s in (EmceeEnsembleSampler(m, 30, model_call=models.CallModel(m, 'logplr')),
+              EmceePTSampler(m, 2, 30)):
+        s.set_p0()
+        s.run(4)
+        assert s.niterations == 4
+        assert np.all(np.isfinite(s.lnpost))
