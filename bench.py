@@ -329,6 +329,13 @@ def run_cuda(args):
         except (OSError, ValueError):
             pass
         hbm = peaks.get("hbm_gbs", 6650.0)
+        traffic, traffic_src = None, None
+        try:        # dram bytes per launch of this kernel from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            traffic = float(tj["dram_bytes_read"] + tj["dram_bytes_write"])
+            traffic_src = tj["source"]
+        except (OSError, ValueError, KeyError):
+            pass
         # every table byte has to come from HBM once per launch (L2 was flushed); the
         # 128 walker tiles that re-read it are served by the 126 MB L2
         alg_bytes = float(plan.kmax - plan.kmin) * TABLE_BYTES_PER_BIN + W * (11 + 1 + 3 * nd) * 8.0
@@ -360,7 +367,8 @@ def run_cuda(args):
                 "hbm": {"algorithmic_bytes_per_launch": alg_bytes,
                         "achieved_gbs": alg_bytes / (kern_ms * 1e-3) / 1e9,
                         "peak_gbs": hbm, "frac": alg_bytes / (kern_ms * 1e-3) / 1e9 / hbm},
-                "traffic": None,
+                "traffic": traffic,
+                "traffic_source": traffic_src,
             },
         }
         if world == 1 and not args.no_cpu:
