@@ -57,7 +57,7 @@ enum {
     C_A0 = 0, C_A2, C_A3, C_A4, C_A5, C_B5, C_A6, C_B6, C_A7,   // phase [turns]
     C_DET0                                                        // then 4 per detector
 };
-enum { D_TAUHI = 0, D_TAULO, D_ARE, D_AIM, D_NROW };
+enum { D_TAUHI = 0, D_TAULO, D_ARE, D_AIM, D_ECOS, D_ESIN, D_NROW };   // E = e^{+2 pi i tau}
 #define NCOEF(nd) (C_DET0 + D_NROW * (nd))
 
 static thread_local char g_err[512] = "";
@@ -156,6 +156,17 @@ __device__ __forceinline__ double2 phasor_pos(double y) {
     double s, c;
     sincospi(2.0 * frac1(y), &s, &c);
     return make_double2(c, s);
+}
+// e^{+2 pi i y}: Taylor series when the angle is small (the higher forward differences of
+// the chirp phase are ~1e-3 .. 1e-9 turns), full sincospi otherwise.
+__device__ __forceinline__ double2 phasor_pos_small(double y) {
+    if (fabs(y) < 0.0125) {                      // |theta| < 0.0785 rad: next term < 3e-17
+        const double th = G_TWOPI * y, t2 = th * th;
+        const double c = fma(t2, fma(t2, fma(t2, fma(t2, 1.0 / 40320.0, -1.0 / 720.0), 1.0 / 24.0), -0.5), 1.0);
+        const double s = th * fma(t2, fma(t2, fma(t2, fma(t2, 1.0 / 362880.0, -1.0 / 5040.0), 1.0 / 120.0), -1.0 / 6.0), 1.0);
+        return make_double2(c, s);
+    }
+    return phasor_pos(y);
 }
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
     return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
@@ -398,6 +409,10 @@ __global__ void walker_setup_kernel(PlanDev P, int W, int wpad,
         row[D_TAULO * wpad] = tau_lo;
         row[D_ARE * wpad] = are;
         row[D_AIM * wpad] = aim;
+        double es, ec;
+        sincospi(2.0 * tau, &es, &ec);
+        row[D_ECOS * wpad] = ec;
+        row[D_ESIN * wpad] = es;
         // <h|h> closed form: |A|^2 * sum_{ks<=k<ke} norm f^(-7/3)/S  (phase-free)
         double hh = 0.0;
         if (ke > ks) {
@@ -497,7 +512,11 @@ loglr_direct_kernel(PlanDev P, int W, int wpad, int chunk_bins, int n_chunks,
 // Per-thread walker coefficients live in shared memory (one column per thread, no
 // sharing, hence no barrier): they are only needed in the per-block set-up, and keeping
 // them out of the register file buys a third/fourth resident CTA per SM.
-#define RC_ROWS(nd) (9 + 2 * (nd))
+#define RC_ROWS(nd) (9 + 4 * (nd))
+template <int ND>
+__device__ __forceinline__ double2 load_E(const double* sc, int d) {       // e^{+2 pi i tau_d}
+    return make_double2(sc[(9 + 2 * ND + 2 * d) * CTA_THREADS], sc[(10 + 2 * ND + 2 * d) * CTA_THREADS]);
+}
 template <int ND>
 __device__ __forceinline__ void load_block_coef(const double* sc, PhaseCoef& pc,
                                                 double (&tau_hi)[ND], double (&tau_lo)[ND]) {
@@ -634,9 +653,10 @@ __device__ __forceinline__ void recur_block(
         D[r] = acc;
     }
     double2 tq = make_double2(1.0, 0.0);
-    if (DEG == 4) tq = phasor_pos(D[3]);
-    double2 sq = phasor_pos(D[2]);
-    double2 rq = phasor_pos(D[1]);
+    if (DEG == 4) tq = phasor_pos_small(D[3]);
+    double2 sq = phasor_pos_small(D[2]);
+    double2 rq = phasor_pos_small(D[1]);
+    const double2 G = phasor_pos(D[0]);
     double2 g[ND], acc[ND];
     const double kend = (double)(kb + B - 1);
     S.ensure(kb);
@@ -644,7 +664,7 @@ __device__ __forceinline__ void recur_block(
         const double2* sp = S.row(kb);
 #pragma unroll
         for (int d = 0; d < ND; ++d) {
-            g[d] = phasor_pos(D[0] + (tau_hi[d] + tau_lo[d]));
+            g[d] = cmul(G, load_E<ND>(sc, d));          // e^{2 pi i (D1(0) + tau_d)}
             double2 T0 = sp[d];
             if (MASKED && !(kb >= lo && kb < hi)) T0 = make_double2(0.0, 0.0);
             acc[d] = T0;
@@ -679,7 +699,7 @@ __device__ __forceinline__ void recur_block(
 }
 
 #ifndef RECUR_MIN_CTAS
-#define RECUR_MIN_CTAS 4
+#define RECUR_MIN_CTAS 3
 #endif
 template <int ND>
 __global__ void __launch_bounds__(CTA_THREADS, RECUR_MIN_CTAS)
@@ -727,6 +747,8 @@ loglr_recur_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_blk,
             const double* row = wc + (size_t)(C_DET0 + D_NROW * d) * wpad + tt;
             sc[(9 + 2 * d) * CTA_THREADS] = row[D_TAUHI * wpad];
             sc[(10 + 2 * d) * CTA_THREADS] = row[D_TAULO * wpad];
+            sc[(9 + 2 * ND + 2 * d) * CTA_THREADS] = row[D_ECOS * wpad];
+            sc[(10 + 2 * ND + 2 * d) * CTA_THREADS] = row[D_ESIN * wpad];
         }
         const int lane = threadIdx.x & (WARP - 1), warp = threadIdx.x / WARP;
         TileStream<ND> S;
@@ -1244,7 +1266,8 @@ extern "C" int gwin_loglr_batch(gwin_plan* p, int mode, int64_t W64,
     const int band0 = std::max(d.kmin, d.istart);
     const int nbins = std::max(d.kmax - band0, 1);
     const int groups = (W + CTA_THREADS - 1) / CTA_THREADS;
-    const int want_chunks = std::max(1, (148 * 48 + groups - 1) / groups);
+    static const int chunk_mult = getenv("GWIN_CHUNK_MULT") ? atoi(getenv("GWIN_CHUNK_MULT")) : 192;
+    const int want_chunks = std::max(1, (148 * chunk_mult + groups - 1) / groups);
     int n_chunks, per_chunk;
     if (recur) {
         const int min_blocks = 2;
