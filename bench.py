@@ -88,7 +88,7 @@ class ClockSampler(object):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -400,7 +400,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.steps is None:
-        args.steps = 10 if args.impl == "cuda" else 3
+        args.steps = 30 if args.impl == "cuda" else 3
     if args.impl == "reference":
         run_reference(args)
     else:

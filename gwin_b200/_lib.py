@@ -32,7 +32,9 @@ KERNEL_AUTO, KERNEL_DIRECT, KERNEL_RECURRENCE = 0, 1, 2
 SYMBOLS = (
     "gwin_plan_create", "gwin_plan_destroy", "gwin_plan_cutoffs",
     "gwin_plan_lognl", "gwin_plan_configure", "gwin_loglr_batch",
-    "gwin_loglr_batch_host", "gwin_generate_host", "gwin_plan_last_launches",
+    "gwin_loglr_batch_host", "gwin_loglr_batch_strided",
+    "gwin_loglr_batch_host_strided", "gwin_generate_host",
+    "gwin_plan_last_launches",
     "gwin_plan_kernel_timing",
     "gwin_fp64_peak", "gwin_fp64_probe", "gwin_last_error", "gwin_version",
 )
@@ -107,6 +109,14 @@ def load():
         lib.gwin_loglr_batch_host.argtypes = [
             C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
             C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.gwin_loglr_batch_strided.restype = C.c_int
+        lib.gwin_loglr_batch_strided.argtypes = [
+            C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
+            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.gwin_loglr_batch_host_strided.restype = C.c_int
+        lib.gwin_loglr_batch_host_strided.argtypes = [
+            C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
+            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.gwin_generate_host.restype = C.c_int
         lib.gwin_generate_host.argtypes = [C.c_void_p, dp, dp,
                                            C.POINTER(C.c_int64)]
@@ -202,13 +212,22 @@ class Plan(object):
                                                 C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
-    def loglr_host(self, params, mode=MODE_GAUSSIAN, skip=None):
-        """params: [W, 11] float64 host array.  Returns loglr[W],
-        hd[W, n_det] complex128, hh[W, n_det]."""
+    def loglr_host(self, params, mode=MODE_GAUSSIAN, skip=None,
+                   param_major=False):
+        """params: [W, 11] float64 host array, or [11, W] with
+        ``param_major=True``.  Returns loglr[W], hd[W, n_det] complex128,
+        hh[W, n_det]."""
         params = np.ascontiguousarray(params, dtype=np.float64)
-        if params.ndim != 2 or params.shape[1] != GWIN_NPARAM:
-            raise ValueError("params must be [W, %d]" % GWIN_NPARAM)
-        W = params.shape[0]
+        if param_major:
+            if params.ndim != 2 or params.shape[0] != GWIN_NPARAM:
+                raise ValueError("params must be [%d, W]" % GWIN_NPARAM)
+            W = params.shape[1]
+            sw, si = 1, W
+        else:
+            if params.ndim != 2 or params.shape[1] != GWIN_NPARAM:
+                raise ValueError("params must be [W, %d]" % GWIN_NPARAM)
+            W = params.shape[0]
+            sw, si = GWIN_NPARAM, 1
         loglr = np.empty(W)
         hd = np.empty((W, self.n_det), dtype=np.complex128)
         hh = np.empty((W, self.n_det))
@@ -217,8 +236,8 @@ class Plan(object):
             sk = np.ascontiguousarray(skip, dtype=np.uint8)
             if sk.shape != (W,):
                 raise ValueError("skip must be [W]")
-        check(self._lib.gwin_loglr_batch_host(
-            self._h, int(mode), W, params.ctypes.data,
+        check(self._lib.gwin_loglr_batch_host_strided(
+            self._h, int(mode), W, params.ctypes.data, sw, si,
             sk.ctypes.data if sk is not None else None,
             loglr.ctypes.data, hd.ctypes.data, hh.ctypes.data))
         return loglr, hd, hh

@@ -203,6 +203,12 @@ __device__ __forceinline__ void load_phase_coef(PhaseCoef& c, const double* wc, 
 // ---------------------------------------------------------------------------
 // kernel 0: sort key = last bin of each walker's waveform (depends on total mass only)
 // ---------------------------------------------------------------------------
+// one walker's parameter row, gathered from either layout (walker-major or parameter-major)
+__device__ __forceinline__ void load_params(double (&p)[GWIN_NPARAM], const double* __restrict__ params,
+                                            int64_t w, int64_t sw, int64_t si) {
+#pragma unroll
+    for (int i = 0; i < GWIN_NPARAM; ++i) p[i] = params[w * sw + i * si];
+}
 __device__ __forceinline__ bool params_ok(const double* p) {
     bool ok = true;
 #pragma unroll
@@ -229,11 +235,13 @@ __device__ __forceinline__ int waveform_len(double mtot, double delta_f) {
 }
 
 __global__ void sort_key_kernel(PlanDev P, int W, const double* __restrict__ params,
+                                int64_t sw, int64_t si,
                                 const uint8_t* __restrict__ skip, int* __restrict__ key,
                                 int* __restrict__ idx) {
     int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= W) return;
-    const double* p = params + (size_t)w * GWIN_NPARAM;
+    double p[GWIN_NPARAM];
+    load_params(p, params, w, sw, si);
     int ke = 0;
     if (!(skip && skip[w]) && params_ok(p) && has_waveform(p, P.f_lower_wf)) {
         int n = waveform_len(p[0] + p[1], P.delta_f);
@@ -248,7 +256,7 @@ __global__ void sort_key_kernel(PlanDev P, int W, const double* __restrict__ par
 // its rows at sorted position t.
 // ---------------------------------------------------------------------------
 __global__ void walker_setup_kernel(PlanDev P, int W, int wpad,
-                                    const double* __restrict__ params,
+                                    const double* __restrict__ params, int64_t sw, int64_t si,
                                     const uint8_t* __restrict__ skip,
                                     const int* __restrict__ perm,
                                     double* __restrict__ wc, int* __restrict__ ks_arr,
@@ -257,7 +265,8 @@ __global__ void walker_setup_kernel(PlanDev P, int W, int wpad,
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= W) return;
     const int w = perm ? perm[t] : t;
-    const double* p = params + (size_t)w * GWIN_NPARAM;
+    double p[GWIN_NPARAM];
+    load_params(p, params, w, sw, si);
     const int nd = P.n_det;
     const bool ok = !(skip && skip[w]) && params_ok(p) && has_waveform(p, P.f_lower_wf);
     if (!ok) {
@@ -1236,8 +1245,12 @@ static void launch_main(gwin_plan* p, bool recur, int W, int wpad, int n_chunks,
                         double* hh_rows, cudaStream_t st) {
     (void)hh_rows;
     dim3 grid((W + CTA_THREADS - 1) / CTA_THREADS, n_chunks);
+    // diagnostic: GWIN_SMEM_PAD=<bytes> of unused dynamic shared memory lowers the occupancy
+    static const int smem_pad = getenv("GWIN_SMEM_PAD") ? atoi(getenv("GWIN_SMEM_PAD")) : 0;
+    if (recur && smem_pad > 0)
+        cudaFuncSetAttribute(loglr_recur_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pad);
     if (recur)
-        loglr_recur_kernel<ND><<<grid, CTA_THREADS, 0, st>>>(p->d, W, wpad, per_chunk, p->n_blk, p->d_blk_start,
+        loglr_recur_kernel<ND><<<grid, CTA_THREADS, smem_pad, st>>>(p->d, W, wpad, per_chunk, p->n_blk, p->d_blk_start,
                                                             p->d_blk_mat, p->d_mats,
                                                             p->d_wc, p->d_ks, p->d_ke, p->d_partial);
     else
@@ -1248,7 +1261,15 @@ static void launch_main(gwin_plan* p, bool recur, int W, int wpad, int n_chunks,
 extern "C" int gwin_loglr_batch(gwin_plan* p, int mode, int64_t W64,
                                 const double* params, const uint8_t* skip,
                                 double* loglr, double* hd, double* hh, void* stream) {
+    return gwin_loglr_batch_strided(p, mode, W64, params, GWIN_NPARAM, 1, skip, loglr, hd, hh, stream);
+}
+
+extern "C" int gwin_loglr_batch_strided(gwin_plan* p, int mode, int64_t W64,
+                                        const double* params, int64_t stride_walker, int64_t stride_param,
+                                        const uint8_t* skip,
+                                        double* loglr, double* hd, double* hh, void* stream) {
     if (!p) return fail(GWIN_EINVAL, "plan is NULL");
+    if (stride_walker < 1 || stride_param < 1) return fail(GWIN_EINVAL, "parameter strides must be >= 1");
     if (mode != GWIN_MODE_GAUSSIAN && mode != GWIN_MODE_MARG_PHASE) return fail(GWIN_EINVAL, "bad mode %d", mode);
     if (W64 < 0 || W64 > (1 << 26)) return fail(GWIN_EINVAL, "W out of range");
     p->last_launches = 0;
@@ -1286,14 +1307,14 @@ extern "C" int gwin_loglr_batch(gwin_plan* p, int mode, int64_t W64,
     const int tb = 128, gb = (W + tb - 1) / tb;
     const int* perm = nullptr;
     if (W > WARP) {
-        sort_key_kernel<<<gb, tb, 0, st>>>(d, W, params, skip, p->d_key_in, p->d_perm_in);
+        sort_key_kernel<<<gb, tb, 0, st>>>(d, W, params, stride_walker, stride_param, skip, p->d_key_in, p->d_perm_in);
         size_t bytes = p->cub_bytes;
         CK(cub::DeviceRadixSort::SortPairs(p->d_cub, bytes, p->d_key_in, p->d_key_out,
                                            p->d_perm_in, p->d_perm_out, W, 0, 23, st));
         perm = p->d_perm_out;
         p->last_launches += 1;   // + CUB's radix-sort passes (library code, not counted)
     }
-    walker_setup_kernel<<<gb, tb, 0, st>>>(d, W, wpad, params, skip, perm, p->d_wc, p->d_ks, p->d_ke, hh_rows);
+    walker_setup_kernel<<<gb, tb, 0, st>>>(d, W, wpad, params, stride_walker, stride_param, skip, perm, p->d_wc, p->d_ks, p->d_ke, hh_rows);
     if (p->timing) {
         if (p->ev_pending) {            // harvest the previous launch (it has long finished)
             float ms = 0.f;
@@ -1339,7 +1360,18 @@ static int ensure_stage(gwin_plan* p, int64_t W) {
 extern "C" int gwin_loglr_batch_host(gwin_plan* p, int mode, int64_t W,
                                      const double* params, const uint8_t* skip,
                                      double* loglr, double* hd, double* hh) {
+    return gwin_loglr_batch_host_strided(p, mode, W, params, GWIN_NPARAM, 1, skip, loglr, hd, hh);
+}
+
+// params is either [W][11] (stride_walker = 11, stride_param = 1) or [11][W] (1, W); the
+// buffer is copied as one contiguous block of 11*W doubles
+extern "C" int gwin_loglr_batch_host_strided(gwin_plan* p, int mode, int64_t W,
+                                             const double* params, int64_t stride_walker, int64_t stride_param,
+                                             const uint8_t* skip,
+                                             double* loglr, double* hd, double* hh) {
     if (!p) return fail(GWIN_EINVAL, "plan is NULL");
+    if (!((stride_walker == GWIN_NPARAM && stride_param == 1) || (stride_walker == 1 && stride_param == W)))
+        return fail(GWIN_EINVAL, "host parameters must be a dense [W][11] or [11][W] block");
     if (W < 0) return fail(GWIN_EINVAL, "W < 0");
     if (W == 0) { p->last_launches = 0; return GWIN_OK; }
     if (!params || !loglr) return fail(GWIN_EINVAL, "params/loglr is NULL");
@@ -1352,14 +1384,15 @@ extern "C" int gwin_loglr_batch_host(gwin_plan* p, int mode, int64_t W,
     if (p->auto_mchirp && p->kernel != GWIN_KERNEL_DIRECT) {
         // the block schedule must cover the smallest chirp mass of the batch: quantise it
         // down to a quarter octave so the (cheap) schedule rebuild is rare
-        double mc_min = 1e300;
+        double mc5_min = 1e300;                   // chirp mass^5 = (m1 m2)^3 / (m1 + m2): no pow per walker
         for (int64_t i = 0; i < W; ++i) {
             if (skip && skip[i]) continue;
-            const double m1 = params[i * GWIN_NPARAM], m2 = params[i * GWIN_NPARAM + 1];
+            const double m1 = params[i * stride_walker], m2 = params[i * stride_walker + stride_param];
             if (!(m1 > 0.0) || !(m2 > 0.0) || !std::isfinite(m1 + m2)) continue;
-            const double mc = std::pow(m1 * m2, 0.6) / std::pow(m1 + m2, 0.2);
-            mc_min = std::min(mc_min, mc);
+            const double pm = m1 * m2;
+            mc5_min = std::min(mc5_min, pm * pm * pm / (m1 + m2));
         }
+        double mc_min = mc5_min < 1e300 ? std::pow(mc5_min, 0.2) : 1e300;
         if (mc_min < 1e300) {
             mc_min = std::min(std::max(mc_min, 0.02), 1e4);
             const double q = std::exp2(std::floor(4.0 * std::log2(mc_min)) / 4.0);
@@ -1374,7 +1407,8 @@ extern "C" int gwin_loglr_batch_host(gwin_plan* p, int mode, int64_t W,
     double* d_lr = p->d_out;
     double* d_hd = p->d_out + p->stage_cap;
     double* d_hh = d_hd + 2 * (size_t)nd * p->stage_cap;
-    rc = gwin_loglr_batch(p, mode, W, p->d_params, skip ? p->d_skip : nullptr, d_lr, d_hd, d_hh, st);
+    rc = gwin_loglr_batch_strided(p, mode, W, p->d_params, stride_walker, stride_param,
+                                  skip ? p->d_skip : nullptr, d_lr, d_hd, d_hh, st);
     if (rc) return rc;
     double* h_lr = p->h_out;
     double* h_hd = p->h_out + p->stage_cap;
@@ -1400,7 +1434,7 @@ extern "C" int gwin_generate_host(gwin_plan* p, const double* params, double* h_
     memcpy(p->h_params, params, sizeof(double) * GWIN_NPARAM);
     CK(cudaMemcpyAsync(p->d_params, p->h_params, sizeof(double) * GWIN_NPARAM, cudaMemcpyHostToDevice, st));
     double* hh_rows = p->d_wc + (size_t)NCOEF(d.n_det) * wpad;
-    walker_setup_kernel<<<1, 32, 0, st>>>(d, 1, wpad, p->d_params, nullptr, nullptr, p->d_wc, p->d_ks, p->d_ke, hh_rows);
+    walker_setup_kernel<<<1, 32, 0, st>>>(d, 1, wpad, p->d_params, GWIN_NPARAM, 1, nullptr, nullptr, p->d_wc, p->d_ks, p->d_ke, hh_rows);
     generate_len_kernel<<<1, 1, 0, st>>>(d, p->d_params, p->d_ke);
     double2* dout = nullptr;
     CK(cudaMalloc(&dout, sizeof(double2) * (size_t)d.n_det * d.n_f));

@@ -83,9 +83,23 @@ class BatchResult(object):
     ``stats`` (OrderedDict name -> array [W]) for the model's default stats.
     ``rows()`` yields what W scalar ``CallModel`` calls would have returned."""
 
-    def __init__(self, values, stats):
+    def __init__(self, values, stats, names=None):
         self.values = values
-        self.stats = stats
+        self._stats = stats          # dict, or a callable building it on first use
+        self._names = names
+
+    @property
+    def stats(self):
+        if callable(self._stats):
+            self._stats = self._stats()
+        if self._names is not None:
+            W = len(self.values)
+            full = OrderedDict()
+            for n in self._names:
+                v = self._stats.get(n)
+                full[n] = numpy.full(W, numpy.nan) if v is None else v
+            self._stats, self._names = full, None
+        return self._stats
 
     def __len__(self):
         return len(self.values)
@@ -271,6 +285,7 @@ class BaseModel(object, metaclass=ABCMeta):
     def evaluate_batch(self, points, callstat='logposterior'):
         """Evaluate ``callstat`` for W points given in ``sampling_params`` order.
 
+        Returns a ``BatchResult`` whose ``stats`` are materialised on first use.
         Equivalent to W calls of ``CallModel.__call__`` (reference
         ``models/__init__.py:101-137``) including the ``logprior == -inf``
         short-circuit of ``logposterior``/``logplr``; stats that the scalar
@@ -286,8 +301,7 @@ class BaseModel(object, metaclass=ABCMeta):
                              % (len(names), ", ".join(names)))
         samples = {p: points[:, i] for i, p in enumerate(names)}
         params = self._transform_params(**samples)
-        stats = OrderedDict((n, numpy.full(W, numpy.nan))
-                            for n in self.default_stats)
+        stats = OrderedDict()
         need_prior = callstat in ('logposterior', 'logplr', 'logprior',
                                   'logjacobian')
         logp = None
@@ -295,24 +309,32 @@ class BaseModel(object, metaclass=ABCMeta):
             logj, logp = self._batch_logprior(params, W)
             stats['logjacobian'] = logj
             stats['logprior'] = logp
+        all_names = list(self.default_stats)
         if callstat == 'logprior':
-            return BatchResult(logp, stats)
+            return BatchResult(logp, stats, all_names)
         if callstat == 'logjacobian':
-            return BatchResult(stats['logjacobian'], stats)
+            return BatchResult(stats['logjacobian'], stats, all_names)
         skip = None
         if callstat in ('logposterior', 'logplr'):
             skip = numpy.isneginf(logp)
-        values = self._batch_callstat(callstat, params, W, skip, logp, stats)
-        return BatchResult(values, stats)
+        values, more = self._batch_callstat(callstat, params, W, skip, logp, stats)
+        if callable(more):
+            base = stats
+
+            def build(base=base, more=more):
+                out = OrderedDict(base)
+                out.update(more())
+                return out
+            return BatchResult(values, build, all_names)
+        stats.update(more)
+        return BatchResult(values, stats, all_names)
 
     def _batch_callstat(self, callstat, params, W, skip, logp, stats):
         if callstat not in ('logposterior', 'loglikelihood'):
             raise ValueError("unsupported callstat %r for this model" % callstat)
         logl, extra = self._batch_loglikelihood(params, W, skip)
-        stats['loglikelihood'] = logl
-        for k, v in extra.items():
-            if k in stats:
-                stats[k] = v
+        extra = OrderedDict(extra)
+        extra['loglikelihood'] = logl
         if callstat == 'loglikelihood':
-            return logl
-        return numpy.where(skip, -numpy.inf, logp + numpy.where(skip, 0., logl))
+            return logl, extra
+        return numpy.where(skip, -numpy.inf, logp + numpy.where(skip, 0., logl)), extra

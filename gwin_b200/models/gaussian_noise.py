@@ -14,7 +14,7 @@ from collections import OrderedDict
 import numpy
 
 from .. import _lib
-from ..waveform import param_matrix
+from ..waveform import param_rows
 from .base_data import BaseDataModel
 
 
@@ -119,8 +119,9 @@ class GaussianNoise(BaseDataModel):
         return static
 
     def _kernel_call(self, params, W, skip=None):
-        P = param_matrix(params, W, static=self._static_for_kernel())
-        return self._plan.loglr_host(P, mode=self._mode, skip=skip)
+        P = param_rows(params, W, static=self._static_for_kernel())
+        return self._plan.loglr_host(P, mode=self._mode, skip=skip,
+                                     param_major=True)
 
     def _nowaveform_loglr(self):
         for det in self._data:
@@ -174,19 +175,22 @@ class GaussianNoise(BaseDataModel):
             raise ValueError("unsupported callstat %r" % callstat)
         lr, hd, hh = self._kernel_call(params, W, skip=skip)
         lognl = self.lognl
-        dead = numpy.isneginf(lr)
         logl = lr + lognl
-        extra = self._det_stats(hd, hh, dead)
-        extra['loglr'] = lr
-        extra['loglikelihood'] = logl
-        for k, v in extra.items():
-            if k in stats:
-                if skip is not None and skip.any():
-                    v = numpy.where(skip, numpy.nan, v)
-                stats[k] = v
+
+        def extra():
+            dead = numpy.isneginf(lr)
+            out = self._det_stats(hd, hh, dead)
+            out['loglr'] = lr
+            out['loglikelihood'] = logl
+            if skip is not None and skip.any():
+                # the scalar path never evaluates these for prior-excluded points
+                for k in out:
+                    out[k] = numpy.where(skip, numpy.nan, out[k])
+            return out
         if callstat == 'loglr':
-            return lr
+            return lr, extra
         if callstat == 'loglikelihood':
-            return logl
+            return logl, extra
         base = lr if callstat == 'logplr' else logl
-        return numpy.where(skip, -numpy.inf, logp + numpy.where(skip, 0., base))
+        return numpy.where(skip, -numpy.inf,
+                           logp + numpy.where(skip, 0., base)), extra

@@ -79,6 +79,23 @@ def param_matrix(params, W, static=None):
     return out
 
 
+def param_rows(params, W, static=None):
+    """Parameter-major [11, W] variant of ``param_matrix``: one contiguous row per
+    waveform parameter (no transpose of the sampler's per-parameter arrays)."""
+    out = numpy.empty((len(WAVEFORM_PARAMS), W), dtype=numpy.float64)
+    for i, (name, default) in enumerate(WAVEFORM_PARAMS.items()):
+        if name in params:
+            v = params[name]
+        elif static is not None and name in static:
+            v = static[name]
+        elif default is not None:
+            v = default
+        else:
+            raise ValueError("waveform parameter %r was not provided" % name)
+        out[i] = v
+    return out
+
+
 class FDomainDetFrameGenerator(object):
     location_args = set(['tc', 'ra', 'dec', 'polarization'])
 

@@ -106,10 +106,25 @@ int gwin_loglr_batch(gwin_plan* plan, int mode, int64_t W,
                      const double* params, const uint8_t* skip,
                      double* loglr, double* hd, double* hh, void* stream);
 
+/* Same with an explicit parameter layout: element (walker w, parameter i) is
+ * params[w*stride_walker + i*stride_param].  (11, 1) is the row layout above; (1, W) is
+ * parameter-major [11][W], which a host that holds one array per parameter (as gwin's
+ * samplers do) can fill without a transpose and which the device reads coalesced. */
+int gwin_loglr_batch_strided(gwin_plan* plan, int mode, int64_t W,
+                             const double* params, int64_t stride_walker, int64_t stride_param,
+                             const uint8_t* skip,
+                             double* loglr, double* hd, double* hh, void* stream);
+
 /* Same, with HOST buffers: pinned staging, H2D, kernels, D2H, synchronise. */
 int gwin_loglr_batch_host(gwin_plan* plan, int mode, int64_t W,
                           const double* params, const uint8_t* skip,
                           double* loglr, double* hd, double* hh);
+
+/* Host buffers with layout; params must be a dense [W][11] or [11][W] block. */
+int gwin_loglr_batch_host_strided(gwin_plan* plan, int mode, int64_t W,
+                                  const double* params, int64_t stride_walker, int64_t stride_param,
+                                  const uint8_t* skip,
+                                  double* loglr, double* hd, double* hh);
 
 /*
  * FDomainDetFrameGenerator.generate (the call at gaussian_noise.py:322) for ONE

@@ -61,12 +61,12 @@ class OracleGaussianNoise(BaseModel):
         for i, d in enumerate(self._dets):
             extra['{}_cplx_loglr'.format(d)] = hd[:, i] - 0.5 * hh[:, i]
             extra['{}_optimal_snrsq'.format(d)] = hh[:, i]
-        for k, v in extra.items():
-            if k in stats:
-                stats[k] = np.where(skip, np.nan, v) if skip is not None else v
+        if skip is not None:
+            for k in extra:
+                extra[k] = np.where(skip, np.nan, extra[k])
         if callstat == 'loglr':
-            return lr
+            return lr, extra
         if callstat == 'loglikelihood':
-            return logl
+            return logl, extra
         base = lr if callstat == 'logplr' else logl
-        return np.where(skip, -np.inf, logp + np.where(skip, 0., base))
+        return np.where(skip, -np.inf, logp + np.where(skip, 0., base)), extra

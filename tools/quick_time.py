@@ -27,7 +27,7 @@ Pd = torch.tensor(P, device="cuda")
 res = {}
 for name in kernels:
     kid = {"direct": 1, "recurrence": 2}[name]
-    model.plan.configure(kernel=kid, mchirp_min=1.0)
+    model.plan.configure(kernel=kid, mchirp_min=1.0, phase_tol=float(os.environ.get("PHASE_TOL", "0")))
     out = model.plan.loglr_device(Pd)
     torch.cuda.synchronize()
     res[name] = out[0].cpu().numpy()
