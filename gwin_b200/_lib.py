@@ -16,7 +16,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("GWIN_B200_LIB") or os.path.join(_HERE, "libgwin_b200.so")
-SOURCES = [os.path.join(_HERE, "csrc", "gwin_cuda.cu")]
+SOURCES = [os.path.join(_HERE, "csrc", "gwin_cuda.cu"),
+           os.path.join(_HERE, "csrc", "gwin_ensemble.cu")]
 HEADER = os.path.join(ROOT, "include", "gwin_b200.h")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
@@ -36,8 +37,25 @@ SYMBOLS = (
     "gwin_loglr_batch_host_strided", "gwin_generate_host",
     "gwin_plan_last_launches",
     "gwin_plan_kernel_timing",
+    "gwin_ens_propose", "gwin_ens_prior", "gwin_ens_accept", "gwin_ens_swap",
     "gwin_fp64_peak", "gwin_fp64_probe", "gwin_last_error", "gwin_version",
 )
+
+ENS_MAXDIM = 16
+PRIOR_UNIFORM, PRIOR_UNIFORM_ANGLE, PRIOR_SIN_ANGLE, PRIOR_COS_ANGLE, \
+    PRIOR_UNIFORM_RADIUS = range(5)
+TARGET_MCHIRP, TARGET_Q = 100, 101
+
+
+class PriorSpec(C.Structure):
+    """``gwin_prior_spec`` of include/gwin_b200.h."""
+    _fields_ = [("ndim", C.c_int32),
+                ("type", C.c_int32 * ENS_MAXDIM),
+                ("target", C.c_int32 * ENS_MAXDIM),
+                ("lo", C.c_double * ENS_MAXDIM),
+                ("hi", C.c_double * ENS_MAXDIM),
+                ("fixed", C.c_double * GWIN_NPARAM)]
+
 
 _lock = threading.Lock()
 _lib = None
@@ -127,6 +145,16 @@ def load():
                                                 C.POINTER(C.c_int)]
         lib.gwin_fp64_peak.restype = C.c_int
         lib.gwin_fp64_peak.argtypes = [C.c_int, dp]
+        vp, u64, u32, ci, cd = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_double
+        lib.gwin_ens_propose.restype = ci
+        lib.gwin_ens_propose.argtypes = [u64, u32, ci, ci, ci, ci, cd, ci, ci, vp, vp, vp, vp]
+        lib.gwin_ens_prior.restype = ci
+        lib.gwin_ens_prior.argtypes = [C.POINTER(PriorSpec), C.c_int64, vp, vp, vp, vp, vp]
+        lib.gwin_ens_accept.restype = ci
+        lib.gwin_ens_accept.argtypes = [u64, u32, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp,
+                                        vp, vp, vp, vp, vp]
+        lib.gwin_ens_swap.restype = ci
+        lib.gwin_ens_swap.argtypes = [u64, u32, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp]
         lib.gwin_fp64_probe.restype = C.c_int
         lib.gwin_fp64_probe.argtypes = [C.c_int, C.c_int, dp]
         lib.gwin_last_error.restype = C.c_char_p

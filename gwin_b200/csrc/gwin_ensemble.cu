@@ -1,0 +1,304 @@
+// gwin_b200 -- device-resident ensemble / parallel-tempering step.
+//
+// The reference leaves the ensemble step to emcee (gwin/sampler/emcee.py:74-76, 286-289): per
+// half-step it proposes k/2 (or ntemps*k/2) points on the host, maps the likelihood over a pool and
+// accepts on the host.  With the likelihood at ~1 us per walker the host side of that loop is what
+// limits a multi-GPU run, so the three host stages are kernels here and the walkers never leave
+// the device:
+//
+//   ens_propose_kernel   stretch move (emcee 2.x EnsembleSampler / PTSampler variants)
+//   ens_prior_kernel     boundary conditions + log prior + waveform-parameter rows for the
+//                        likelihood kernel (the distributions gwin's docs use: uniform, sin/cos
+//                        angle, uniform angle (cyclic), uniform radius; optional mchirp,q -> m1,m2)
+//   ens_accept_kernel    Metropolis accept with beta*logl + logp
+//   ens_swap_kernel      adjacent-temperature swaps
+//
+// Randomness is counter based (Philox4x32-10 keyed by the seed, counter = (iteration, stage,
+// index)): every rank of a multi-GPU run regenerates the same numbers, so proposals and decisions
+// are identical everywhere without position traffic; only the sharded log-likelihoods are
+// all-gathered (by the caller, NCCL on device buffers).
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/gwin_b200.h"
+
+#define G_TWOPI 6.283185307179586476925286766559005768
+#define G_PI    3.141592653589793238462643383279502884
+
+extern int gwin_fail(int code, const char* fmt, ...);
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011)
+// ---------------------------------------------------------------------------
+struct Philox {
+    uint32_t c[4];
+};
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    const uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+    const uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+__device__ __forceinline__ void philox4x32(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                           uint32_t (&out)[4]) {
+    uint32_t c[4] = {c0, c1, c2, c3};
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c, k0, k1);
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+// two uniforms in (0, 1) with 52 random bits each
+__device__ __forceinline__ void uniform2(const uint32_t (&r)[4], double& u0, double& u1) {
+    const uint64_t a = ((uint64_t)r[0] << 32 | r[1]) >> 12, b = ((uint64_t)r[2] << 32 | r[3]) >> 12;
+    u0 = ((double)a + 0.5) * (1.0 / 4503599627370496.0);
+    u1 = ((double)b + 0.5) * (1.0 / 4503599627370496.0);
+}
+
+enum { STAGE_PROPOSE = 1, STAGE_ACCEPT = 2, STAGE_SWAP = 3 };
+
+// index of walker j of the half being updated / of the complementary half
+__device__ __forceinline__ int half_index(int j, int half, int nwalkers, int interleaved) {
+    return interleaved ? 2 * j + half : half * (nwalkers / 2) + j;
+}
+
+// ---------------------------------------------------------------------------
+// stretch-move proposal for one half of every temperature
+//   move 0: emcee EnsembleSampler  z = ((a-1)u+1)^2/a,      q = c - z (c - s),  factor (ndim-1) ln z
+//   move 1: emcee PTSampler        z = exp(U(-ln a, ln a)), q = c + z (s - c),  factor  ndim    ln z
+// ---------------------------------------------------------------------------
+__global__ void ens_propose_kernel(uint64_t seed, uint32_t iter, int half, int ntemps, int nwalkers, int ndim,
+                                   double a, int move, int interleaved,
+                                   const double* __restrict__ p, double* __restrict__ q,
+                                   double* __restrict__ logfac) {
+    const int nh = nwalkers / 2;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ntemps * nh) return;
+    const int k = i / nh, j = i % nh;
+    uint32_t r[4];
+    philox4x32(seed, iter, (uint32_t)(STAGE_PROPOSE * 4 + half), (uint32_t)i, 0u, r);
+    double u0, u1;
+    uniform2(r, u0, u1);
+    const int jc = min((int)(u1 * nh), nh - 1);
+    double z, lf;
+    if (move == 0) { const double t = (a - 1.0) * u0 + 1.0; z = t * t / a; lf = (ndim - 1.0) * log(z); }
+    else           { const double la = log(a); const double lz = la * (2.0 * u0 - 1.0); z = exp(lz); lf = ndim * lz; }
+    const double* s = p + ((size_t)k * nwalkers + half_index(j, half, nwalkers, interleaved)) * ndim;
+    const double* c = p + ((size_t)k * nwalkers + half_index(jc, 1 - half, nwalkers, interleaved)) * ndim;
+    double* out = q + (size_t)i * ndim;
+    for (int d = 0; d < ndim; ++d) out[d] = c[d] - z * (c[d] - s[d]);
+    logfac[i] = lf;
+}
+
+// ---------------------------------------------------------------------------
+// prior + parameter rows
+// ---------------------------------------------------------------------------
+struct gwin_prior_spec_dev {
+    int ndim;
+    int type[GWIN_ENS_MAXDIM];
+    int target[GWIN_ENS_MAXDIM];
+    double lo[GWIN_ENS_MAXDIM], hi[GWIN_ENS_MAXDIM];
+    double fixed[GWIN_NPARAM];
+};
+
+__device__ __forceinline__ double wrap_cyclic(double x, double lo, double hi) {
+    const double w = hi - lo;
+    double y = fmod(x - lo, w);
+    if (y < 0.0) y += w;
+    return y + lo;
+}
+__device__ __forceinline__ double wrap_reflect(double x, double lo, double hi) {
+    const double w = hi - lo, period = 2.0 * w;
+    double y = fmod(x - lo, period);
+    if (y < 0.0) y += period;
+    if (y > w) y = period - y;
+    return y + lo;
+}
+
+// q [W][ndim] (sampling parameters, untouched) -> logp [W], skip [W], params [11][W]
+__global__ void ens_prior_kernel(gwin_prior_spec_dev S, int W, const double* __restrict__ q,
+                                 double* __restrict__ logp, uint8_t* __restrict__ skip,
+                                 double* __restrict__ params) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    double row[GWIN_NPARAM];
+#pragma unroll
+    for (int i = 0; i < GWIN_NPARAM; ++i) row[i] = S.fixed[i];
+    double mchirp = 0.0, qratio = 0.0;
+    double lp = 0.0;
+    for (int d = 0; d < S.ndim; ++d) {
+        double x = q[(size_t)w * S.ndim + d];
+        const double lo = S.lo[d], hi = S.hi[d];
+        switch (S.type[d]) {
+            case GWIN_PRIOR_UNIFORM:
+                lp += (x >= lo && x <= hi) ? -log(hi - lo) : -INFINITY;
+                break;
+            case GWIN_PRIOR_UNIFORM_ANGLE:          // cyclic
+                x = wrap_cyclic(x, lo, hi);
+                lp += -log(hi - lo);
+                break;
+            case GWIN_PRIOR_SIN_ANGLE:              // p ~ sin x on [lo, hi] within [0, pi], reflected
+                x = wrap_reflect(x, 0.0, G_PI);
+                lp += (x >= lo && x <= hi) ? log(fabs(sin(x)) / fabs(cos(lo) - cos(hi))) : -INFINITY;
+                break;
+            case GWIN_PRIOR_COS_ANGLE:              // p ~ cos x on [lo, hi] within [-pi/2, pi/2], reflected
+                x = wrap_reflect(x, -0.5 * G_PI, 0.5 * G_PI);
+                lp += (x >= lo && x <= hi) ? log(fabs(cos(x)) / fabs(sin(hi) - sin(lo))) : -INFINITY;
+                break;
+            case GWIN_PRIOR_UNIFORM_RADIUS:         // p ~ x^2
+                lp += (x >= lo && x <= hi) ? log(3.0 * x * x / (hi * hi * hi - lo * lo * lo)) : -INFINITY;
+                break;
+            default:
+                lp = -INFINITY;
+        }
+        const int tg = S.target[d];
+        if (tg >= 0 && tg < GWIN_NPARAM) row[tg] = x;
+        else if (tg == GWIN_TARGET_MCHIRP) mchirp = x;
+        else if (tg == GWIN_TARGET_Q) qratio = x;
+    }
+    if (mchirp > 0.0 && qratio > 0.0) {             // waveform transform (mchirp, q = m1/m2) -> (m1, m2)
+        const double m2 = mchirp * pow(1.0 + qratio, 0.2) / pow(qratio, 0.6);
+        row[0] = qratio * m2;
+        row[1] = m2;
+    }
+    if (isnan(lp)) lp = -INFINITY;
+    logp[w] = lp;
+    skip[w] = (lp == -INFINITY) ? 1 : 0;
+#pragma unroll
+    for (int i = 0; i < GWIN_NPARAM; ++i) params[(size_t)i * W + w] = row[i];
+}
+
+// ---------------------------------------------------------------------------
+// accept:  ln r < logfac + (beta*logl_q + logp_q) - lnprob_s
+// ---------------------------------------------------------------------------
+__global__ void ens_accept_kernel(uint64_t seed, uint32_t iter, int half, int ntemps, int nwalkers, int ndim,
+                                  int interleaved, const double* __restrict__ betas,
+                                  const double* __restrict__ q, const double* __restrict__ logfac,
+                                  const double* __restrict__ q_logl, const double* __restrict__ q_logp,
+                                  double* __restrict__ p, double* __restrict__ logl,
+                                  double* __restrict__ lnprob, int* __restrict__ naccept) {
+    const int nh = nwalkers / 2;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ntemps * nh) return;
+    const int k = i / nh, j = i % nh;
+    uint32_t r[4];
+    philox4x32(seed, iter, (uint32_t)(STAGE_ACCEPT * 4 + half), (uint32_t)i, 0u, r);
+    double u0, u1;
+    uniform2(r, u0, u1);
+    const size_t wi = (size_t)k * nwalkers + half_index(j, half, nwalkers, interleaved);
+    const double lp = q_logp[i];
+    // emcee: points outside the prior are never evaluated and carry logl = 0
+    const double ll = (lp == -INFINITY) ? 0.0 : q_logl[i];
+    const double newprob = (lp == -INFINITY) ? -INFINITY : betas[k] * ll + lp;
+    const bool accept = log(u0) < logfac[i] + newprob - lnprob[wi];
+    if (accept && !isnan(newprob)) {
+        for (int d = 0; d < ndim; ++d) p[wi * ndim + d] = q[(size_t)i * ndim + d];
+        logl[wi] = ll;
+        lnprob[wi] = newprob;
+        naccept[wi] += 1;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// temperature swap between chains i and i-1 (emcee PTSampler._temperature_swaps); iperm / i1perm
+// are random permutations of the walkers supplied by the caller.
+// ---------------------------------------------------------------------------
+__global__ void ens_swap_kernel(uint64_t seed, uint32_t iter, int level, int nwalkers, int ndim,
+                                const double* __restrict__ betas, const int* __restrict__ iperm,
+                                const int* __restrict__ i1perm, double* __restrict__ p,
+                                double* __restrict__ logl, double* __restrict__ lnprob,
+                                int* __restrict__ nswap_accepted) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nwalkers) return;
+    uint32_t r[4];
+    philox4x32(seed, iter, (uint32_t)(STAGE_SWAP * 4), (uint32_t)(level * nwalkers + j), 0u, r);
+    double u0, u1;
+    uniform2(r, u0, u1);
+    const double dbeta = betas[level - 1] - betas[level];
+    const size_t a = (size_t)level * nwalkers + iperm[j], b = (size_t)(level - 1) * nwalkers + i1perm[j];
+    const double la = logl[a], lb = logl[b];
+    if (dbeta * (la - lb) > log(u0)) {
+        for (int d = 0; d < ndim; ++d) {
+            const double t = p[a * ndim + d];
+            p[a * ndim + d] = p[b * ndim + d];
+            p[b * ndim + d] = t;
+        }
+        const double pa = lnprob[a], pb = lnprob[b];
+        logl[a] = lb; logl[b] = la;
+        lnprob[a] = pb - dbeta * lb;
+        lnprob[b] = pa + dbeta * la;
+        atomicAdd(nswap_accepted + level, 1);
+        atomicAdd(nswap_accepted + level - 1, 1);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+#define CKE(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return gwin_fail(GWIN_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
+
+static int check_dims(int ntemps, int nwalkers, int ndim) {
+    if (ntemps < 1 || nwalkers < 2 || (nwalkers & 1) || ndim < 1 || ndim > GWIN_ENS_MAXDIM)
+        return gwin_fail(GWIN_EINVAL, "need ntemps >= 1, even nwalkers >= 2, 1 <= ndim <= %d", GWIN_ENS_MAXDIM);
+    return GWIN_OK;
+}
+
+extern "C" int gwin_ens_propose(uint64_t seed, uint32_t iter, int half, int ntemps, int nwalkers, int ndim,
+                                double a, int move, int interleaved,
+                                const double* p, double* q, double* logfac, void* stream) {
+    int rc = check_dims(ntemps, nwalkers, ndim);
+    if (rc) return rc;
+    if (!p || !q || !logfac) return gwin_fail(GWIN_EINVAL, "NULL buffer");
+    const int n = ntemps * (nwalkers / 2);
+    ens_propose_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(seed, iter, half, ntemps, nwalkers, ndim,
+                                                                           a, move, interleaved, p, q, logfac);
+    CKE(cudaGetLastError());
+    return GWIN_OK;
+}
+
+extern "C" int gwin_ens_prior(const gwin_prior_spec* spec, int64_t W, const double* q,
+                              double* logp, uint8_t* skip, double* params, void* stream) {
+    if (!spec || !q || !logp || !skip || !params) return gwin_fail(GWIN_EINVAL, "NULL argument");
+    if (spec->ndim < 1 || spec->ndim > GWIN_ENS_MAXDIM) return gwin_fail(GWIN_EINVAL, "bad ndim");
+    if (W <= 0) return GWIN_OK;
+    gwin_prior_spec_dev S;
+    S.ndim = spec->ndim;
+    for (int d = 0; d < GWIN_ENS_MAXDIM; ++d) {
+        S.type[d] = spec->type[d]; S.target[d] = spec->target[d];
+        S.lo[d] = spec->lo[d]; S.hi[d] = spec->hi[d];
+    }
+    for (int i = 0; i < GWIN_NPARAM; ++i) S.fixed[i] = spec->fixed[i];
+    ens_prior_kernel<<<(unsigned)((W + 127) / 128), 128, 0, (cudaStream_t)stream>>>(S, (int)W, q, logp, skip, params);
+    CKE(cudaGetLastError());
+    return GWIN_OK;
+}
+
+extern "C" int gwin_ens_accept(uint64_t seed, uint32_t iter, int half, int ntemps, int nwalkers, int ndim,
+                               int interleaved, const double* betas, const double* q, const double* logfac,
+                               const double* q_logl, const double* q_logp,
+                               double* p, double* logl, double* lnprob, int* naccept, void* stream) {
+    int rc = check_dims(ntemps, nwalkers, ndim);
+    if (rc) return rc;
+    const int n = ntemps * (nwalkers / 2);
+    ens_accept_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(seed, iter, half, ntemps, nwalkers, ndim,
+                                                                          interleaved, betas, q, logfac, q_logl, q_logp,
+                                                                          p, logl, lnprob, naccept);
+    CKE(cudaGetLastError());
+    return GWIN_OK;
+}
+
+extern "C" int gwin_ens_swap(uint64_t seed, uint32_t iter, int level, int nwalkers, int ndim,
+                             const double* betas, const int* iperm, const int* i1perm,
+                             double* p, double* logl, double* lnprob, int* nswap_accepted, void* stream) {
+    if (level < 1 || nwalkers < 1 || ndim < 1) return gwin_fail(GWIN_EINVAL, "bad swap arguments");
+    ens_swap_kernel<<<(nwalkers + 127) / 128, 128, 0, (cudaStream_t)stream>>>(seed, iter, level, nwalkers, ndim, betas,
+                                                                              iperm, i1perm, p, logl, lnprob,
+                                                                              nswap_accepted);
+    CKE(cudaGetLastError());
+    return GWIN_OK;
+}

@@ -1,0 +1,375 @@
+"""Device-resident ensemble / parallel-tempering samplers.
+
+Same step as ``EmceeEnsembleSampler`` / ``EmceePTSampler`` (emcee 2.x semantics,
+SURVEY.md appendix B) but the walkers never leave the GPU: proposal, boundary
+conditions + prior, likelihood, accept and temperature swaps are kernels of
+``libgwin_b200.so`` chained on one stream; with several GPUs each rank evaluates
+its slice of the proposals and ONE NCCL all-gather of the log-likelihoods per
+half-step (on device buffers) is the only communication -- the counter-based
+RNG regenerates identical proposals and decisions on every rank.
+
+torch is used for what the task allows it: owning device memory, the stream and
+``torch.distributed``.  Restrictions (use the host steppers otherwise): priors
+must be a ``JointDistribution`` of Uniform / UniformAngle / SinAngle / CosAngle /
+UniformRadius / UniformSky without constraints, no sampling transforms, and the
+only waveform transform understood is (mchirp, q) -> (mass1, mass2).
+"""
+import ctypes as C
+
+import numpy
+
+from .. import _lib
+from .. import distributions as D
+from .. import transforms as T
+from ..distributions import FieldArray
+from ..waveform import WAVEFORM_PARAMS
+from .base import BaseMCMCSampler
+from .ensemble import default_beta_ladder
+
+_TYPES = {D.Uniform: _lib.PRIOR_UNIFORM, D.UniformAngle: _lib.PRIOR_UNIFORM_ANGLE,
+          D.SinAngle: _lib.PRIOR_SIN_ANGLE, D.CosAngle: _lib.PRIOR_COS_ANGLE,
+          D.UniformRadius: _lib.PRIOR_UNIFORM_RADIUS}
+
+
+def prior_spec_from_model(model):
+    """Translate ``model.prior_distribution`` + static params into the
+    ``gwin_prior_spec`` the device kernels understand."""
+    if model.sampling_transforms is not None:
+        raise NotImplementedError("sampling transforms are not supported on the device path")
+    wt = getattr(model, "_waveform_transforms", None)
+    mchirp_q = False
+    if wt:
+        if len(wt) == 1 and isinstance(wt[0], T.MchirpQToMass1Mass2):
+            mchirp_q = True
+        else:
+            raise NotImplementedError("only the mchirp,q -> mass1,mass2 waveform transform "
+                                      "is supported on the device path")
+    prior = model.prior_distribution
+    if not isinstance(prior, D.JointDistribution) or prior._constraints:
+        raise NotImplementedError("the device path needs a JointDistribution without constraints")
+    per_param = {}
+    for dist in prior.distributions:
+        parts = [dist._az, dist._po] if isinstance(dist, D.UniformSky) else [dist]
+        for part in parts:
+            if type(part) not in _TYPES:
+                raise NotImplementedError("prior %s is not supported on the device path"
+                                          % type(part).__name__)
+            for name, b in part.bounds.items():
+                per_param[name] = (_TYPES[type(part)], b.min, b.max)
+    names = list(model.sampling_params)
+    if len(names) > _lib.ENS_MAXDIM:
+        raise NotImplementedError("more than %d sampling dimensions" % _lib.ENS_MAXDIM)
+    wf_names = list(WAVEFORM_PARAMS.keys())
+    spec = _lib.PriorSpec()
+    spec.ndim = len(names)
+    for d, name in enumerate(names):
+        kind, lo, hi = per_param[name]
+        spec.type[d], spec.lo[d], spec.hi[d] = kind, lo, hi
+        if name in wf_names:
+            spec.target[d] = wf_names.index(name)
+        elif mchirp_q and name == "mchirp":
+            spec.target[d] = _lib.TARGET_MCHIRP
+        elif mchirp_q and name == "q":
+            spec.target[d] = _lib.TARGET_Q
+        else:
+            raise NotImplementedError("sampling parameter %r does not map to a waveform parameter" % name)
+    static = dict(model.waveform_generator.frozen_params)
+    static.update(model.static_params)
+    for i, (name, default) in enumerate(WAVEFORM_PARAMS.items()):
+        if name in static:
+            spec.fixed[i] = float(static[name])
+        elif default is not None:
+            spec.fixed[i] = float(default)
+        elif name in names or (mchirp_q and name in ("mass1", "mass2")):
+            spec.fixed[i] = 0.0
+        else:
+            raise ValueError("waveform parameter %r is neither sampled nor static" % name)
+    return spec
+
+
+def _min_chirp_mass(spec):
+    """Smallest chirp mass inside the prior box (None if it cannot be told)."""
+    lo = {}
+    for d in range(spec.ndim):
+        lo[spec.target[d]] = spec.lo[d]
+    if _lib.TARGET_MCHIRP in lo:
+        return lo[_lib.TARGET_MCHIRP] if lo[_lib.TARGET_MCHIRP] > 0 else None
+    m1 = lo.get(0, spec.fixed[0])
+    m2 = lo.get(1, spec.fixed[1])
+    if m1 > 0 and m2 > 0:
+        return (m1 * m2) ** 0.6 / (m1 + m2) ** 0.2
+    return None
+
+
+class _DeviceEnsemble(BaseMCMCSampler):
+    """Common engine: ``ntemps`` tempered ensembles of ``nwalkers`` walkers."""
+
+    def __init__(self, model, ntemps, nwalkers, betas, move, interleaved, seed=None,
+                 process_group=None, a=2.0):
+        import torch
+        if nwalkers % 2:
+            raise ValueError("The number of walkers must be even.")
+        ndim = len(model.sampling_params)
+        if nwalkers < 2 * ndim:
+            raise ValueError("The number of walkers needs to be more than twice "
+                             "the dimension of your parameter space.")
+        self._torch = torch
+        self._lib = _lib.load()
+        self._spec = prior_spec_from_model(model)
+        super(_DeviceEnsemble, self).__init__(None, model)
+        self._nwalkers, self._ntemps, self._ndim = nwalkers, ntemps, ndim
+        self._move, self._interleaved, self._a = move, interleaved, float(a)
+        self._seed = int(numpy.random.randint(0, 2 ** 31 - 1) if seed is None else seed)
+        self._plan = model.plan
+        self._dev = torch.device("cuda", self._plan.device)
+        self._betas_host = numpy.asarray(betas, dtype=float)
+        f64 = dict(dtype=torch.float64, device=self._dev)
+        self._betas = torch.tensor(self._betas_host, **f64)
+        nh = nwalkers // 2
+        self._Wh = ntemps * nh
+        self._q = torch.empty((self._Wh, ndim), **f64)
+        self._logfac = torch.empty(self._Wh, **f64)
+        self._q_logp = torch.empty(self._Wh, **f64)
+        self._skip = torch.empty(self._Wh, dtype=torch.uint8, device=self._dev)
+        self._params = torch.empty((_lib.GWIN_NPARAM, self._Wh), **f64)
+        self._naccept = torch.zeros((ntemps, nwalkers), dtype=torch.int32, device=self._dev)
+        self._nswap_acc = torch.zeros(ntemps, dtype=torch.int32, device=self._dev)
+        self._nswap = 0
+        # walker sharding
+        self._group = process_group
+        self._world, self._rank = 1, 0
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self._world = torch.distributed.get_world_size(process_group)
+            self._rank = torch.distributed.get_rank(process_group)
+        self._wmax = -(-self._Wh // self._world)
+        self._gath = torch.empty(self._world * self._wmax, **f64)
+        self._local = torch.zeros(self._wmax, **f64)
+        self._p = None
+        self._iterations = 0
+        self._chain = self._lnprob_h = self._logl_h = None
+        self.likelihood_evals = 0
+        # the block schedule of the recurrence kernel must cover the smallest chirp mass the
+        # prior allows (the device entry point cannot look at the batch without a sync)
+        mc = _min_chirp_mass(self._spec)
+        if mc is not None:
+            self._plan.configure(mchirp_min=2.0 ** (numpy.floor(4.0 * numpy.log2(mc)) / 4.0))
+
+    # -- emcee-like attributes --------------------------------------------
+    @property
+    def iterations(self):
+        return self._iterations
+
+    @property
+    def niterations(self):
+        return self._iterations + self.lastclear
+
+    @property
+    def ntemps(self):
+        return self._ntemps
+
+    @property
+    def betas(self):
+        return self._betas_host
+
+    @property
+    def acceptance_fraction(self):
+        return self._naccept.cpu().numpy() / max(self._iterations, 1)
+
+    @property
+    def tswap_acceptance_fraction(self):
+        """Accepted / attempted swaps per temperature (end temperatures take part in one swap
+        per iteration, inner ones in two)."""
+        per_iter = numpy.full(self._ntemps, 2.0)
+        per_iter[0] = per_iter[-1] = 1.0
+        return self._nswap_acc.cpu().numpy() / numpy.maximum(self._nswap * per_iter, 1)
+
+    def _hist(self, t):
+        return numpy.empty((self._ntemps, self._nwalkers, 0) + ((self._ndim,) if t else ())) \
+            if self._chain is None else None
+
+    def _eval_q(self, W, q, q_logp, skip, params, out_loglr):
+        """prior + sharded likelihood for W points in q; result in out_loglr[:W]."""
+        torch, lib = self._torch, self._lib
+        st = torch.cuda.current_stream(self._dev).cuda_stream
+        _lib.check(lib.gwin_ens_prior(C.byref(self._spec), W, q.data_ptr(), q_logp.data_ptr(),
+                                      skip.data_ptr(), params.data_ptr(), st))
+        wmax = -(-W // self._world)
+        a = min(self._rank * wmax, W)
+        b = min(a + wmax, W)
+        if self._world == 1:
+            _lib.check(lib.gwin_loglr_batch_strided(
+                self._plan._h, self.model._mode, W, params.data_ptr(), 1, W, skip.data_ptr(),
+                out_loglr.data_ptr(), None, None, st))
+        else:
+            local = self._local[:wmax]
+            if b > a:
+                _lib.check(lib.gwin_loglr_batch_strided(
+                    self._plan._h, self.model._mode, b - a, params.data_ptr() + 8 * a, 1, W,
+                    skip.data_ptr() + a, local.data_ptr(), None, None, st))
+            gath = self._gath[:self._world * wmax]
+            torch.distributed.all_gather_into_tensor(gath, local, group=self._group)
+            out_loglr[:W].copy_(gath[:W])
+        self.likelihood_evals += W
+
+    def set_p0(self, samples_file=None, prior=None):
+        if samples_file is not None:
+            raise NotImplementedError("result files are outside the hot path")
+        nt, nw = self._ntemps, self._nwalkers
+        samples = self.model.prior_rvs(size=nw * nt, prior=prior)
+        p0 = numpy.ones((nt, nw, self._ndim))
+        for i, param in enumerate(self.sampling_params):
+            p0[..., i] = numpy.asarray(samples[param]).reshape((nt, nw))
+        self._p0 = p0 if nt > 1 or self._keep_temp_axis else p0[0]
+        return self._p0
+
+    _keep_temp_axis = True
+
+    def _initialise(self, p0):
+        torch = self._torch
+        nt, nw, nd = self._ntemps, self._nwalkers, self._ndim
+        p = torch.tensor(numpy.asarray(p0, dtype=float).reshape(nt, nw, nd), dtype=torch.float64,
+                         device=self._dev).contiguous()
+        W = nt * nw
+        f64 = dict(dtype=torch.float64, device=self._dev)
+        logp = torch.empty(W, **f64)
+        skip = torch.empty(W, dtype=torch.uint8, device=self._dev)
+        params = torch.empty((_lib.GWIN_NPARAM, W), **f64)
+        loglr = torch.empty(W, **f64)
+        if self._world > 1 and self._gath.numel() < self._world * (-(-W // self._world)):
+            self._gath = torch.empty(self._world * (-(-W // self._world)), **f64)
+            self._local = torch.zeros(-(-W // self._world), **f64)
+        self._eval_q(W, p.view(W, nd), logp, skip, params, loglr)
+        logl = torch.where(torch.isneginf(logp), torch.zeros_like(loglr), loglr).view(nt, nw)
+        lnprob = logl * self._betas.view(-1, 1) + logp.view(nt, nw)
+        if bool(torch.isposinf(lnprob).any()) or bool(torch.isnan(lnprob).any()):
+            raise ValueError("The initial lnprob was NaN or +inf.")
+        self._p, self._logl, self._lnprob = p, logl.contiguous(), lnprob.contiguous()
+
+    def run(self, niterations, **kwargs):
+        torch, lib = self._torch, self._lib
+        if self._p is None:
+            self._initialise(self.p0)
+        nt, nw, nd = self._ntemps, self._nwalkers, self._ndim
+        f64 = dict(dtype=torch.float64, device=self._dev)
+        chain = torch.empty((nt, nw, niterations, nd), **f64)
+        lnp_h = torch.empty((nt, nw, niterations), **f64)
+        lnl_h = torch.empty((nt, nw, niterations), **f64)
+        q_loglr = torch.empty(self._Wh, **f64)
+        perms = None
+        if nt > 1:
+            # replicated host RNG for the swap pairings: identical on every rank
+            rs = numpy.random.RandomState((self._seed + 7919 * self._iterations) % (2 ** 32))
+            perms = numpy.stack([[[rs.permutation(nw), rs.permutation(nw)] for _ in range(nt - 1)]
+                                 for _ in range(niterations)]).astype(numpy.int32)
+            perms = torch.tensor(perms, device=self._dev)
+        st = torch.cuda.current_stream(self._dev).cuda_stream
+        for it in range(niterations):
+            gi = self._iterations
+            for half in (0, 1):
+                _lib.check(lib.gwin_ens_propose(
+                    self._seed, gi, half, nt, nw, nd, self._a, self._move, self._interleaved,
+                    self._p.data_ptr(), self._q.data_ptr(), self._logfac.data_ptr(), st))
+                self._eval_q(self._Wh, self._q, self._q_logp, self._skip, self._params, q_loglr)
+                _lib.check(lib.gwin_ens_accept(
+                    self._seed, gi, half, nt, nw, nd, self._interleaved, self._betas.data_ptr(),
+                    self._q.data_ptr(), self._logfac.data_ptr(), q_loglr.data_ptr(),
+                    self._q_logp.data_ptr(), self._p.data_ptr(), self._logl.data_ptr(),
+                    self._lnprob.data_ptr(), self._naccept.data_ptr(), st))
+            for lvl in range(nt - 1, 0, -1):
+                pr = perms[it, nt - 1 - lvl]
+                _lib.check(lib.gwin_ens_swap(
+                    self._seed, gi, lvl, nw, nd, self._betas.data_ptr(), pr[0].data_ptr(),
+                    pr[1].data_ptr(), self._p.data_ptr(), self._logl.data_ptr(),
+                    self._lnprob.data_ptr(), self._nswap_acc.data_ptr(), st))
+            if nt > 1:
+                self._nswap += nw
+            chain[:, :, it, :].copy_(self._p)
+            lnp_h[:, :, it].copy_(self._lnprob)
+            lnl_h[:, :, it].copy_(self._logl)
+            self._iterations += 1
+        c, a, b = chain.cpu().numpy(), lnp_h.cpu().numpy(), lnl_h.cpu().numpy()     # one sync per run()
+        if self._chain is None:
+            self._chain, self._lnprob_h, self._logl_h = c, a, b
+        else:
+            self._chain = numpy.concatenate((self._chain, c), axis=2)
+            self._lnprob_h = numpy.concatenate((self._lnprob_h, a), axis=2)
+            self._logl_h = numpy.concatenate((self._logl_h, b), axis=2)
+        self._pos = self._p.cpu().numpy()
+        return self._pos, self._lnprob.cpu().numpy(), (self._seed, self._iterations)
+
+    def clear_chain(self):
+        self.lastclear = self.niterations
+        self._iterations = 0
+        self._chain = self._lnprob_h = self._logl_h = None
+        self._naccept.zero_()
+        self._nswap_acc.zero_()
+        self._nswap = 0
+
+
+class CudaPTSampler(_DeviceEnsemble):
+    """Device-resident counterpart of ``EmceePTSampler`` (``gwin/sampler/emcee.py:253-432``).
+    The tempered quantity is ``loglr`` (``lognl`` is a constant that cancels in every
+    acceptance ratio)."""
+    name = "emcee_pt_cuda"
+
+    def __init__(self, model, ntemps, nwalkers, pool=None, model_call=None, betas=None,
+                 seed=None, process_group=None):
+        ndim = len(model.sampling_params)
+        if betas is None:
+            betas = default_beta_ladder(ndim, ntemps)
+        super(CudaPTSampler, self).__init__(model, ntemps, nwalkers, betas, move=1, interleaved=1,
+                                            seed=seed, process_group=process_group)
+
+    @classmethod
+    def from_cli(cls, opts, model, pool=None, model_call=None):
+        return cls(model, opts.ntemps, opts.nwalkers)
+
+    @property
+    def chain(self):
+        """ntemps x nwalkers x niterations x ndim."""
+        return self._chain if self._chain is not None else \
+            numpy.empty((self._ntemps, self._nwalkers, 0, self._ndim))
+
+    @property
+    def lnpost(self):
+        return self._lnprob_h
+
+    @property
+    def model_stats(self):
+        logl = self._logl_h
+        logp = self._lnprob_h - logl * self._betas_host.reshape(-1, 1, 1)
+        return FieldArray.from_kwargs(loglr=logl, logprior=logp)
+
+
+class CudaEnsembleSampler(_DeviceEnsemble):
+    """Device-resident counterpart of ``EmceeEnsembleSampler`` (``gwin/sampler/emcee.py:46-194``):
+    stretch move on two contiguous half-ensembles, target ``logprior + loglr`` (= ``logplr``)."""
+    name = "emcee_cuda"
+    _keep_temp_axis = False
+
+    def __init__(self, model, nwalkers, pool=None, model_call=None, seed=None, process_group=None):
+        super(CudaEnsembleSampler, self).__init__(model, 1, nwalkers, [1.0], move=0, interleaved=0,
+                                                  seed=seed, process_group=process_group)
+
+    @classmethod
+    def from_cli(cls, opts, model, pool=None, model_call=None):
+        return cls(model, opts.nwalkers)
+
+    @property
+    def chain(self):
+        """nwalkers x niterations x ndim."""
+        return self._chain[0] if self._chain is not None else \
+            numpy.empty((self._nwalkers, 0, self._ndim))
+
+    @property
+    def lnpost(self):
+        return self._lnprob_h[0]
+
+    @property
+    def acceptance_fraction(self):
+        return super(CudaEnsembleSampler, self).acceptance_fraction[0]
+
+    @property
+    def model_stats(self):
+        logl = self._logl_h[0]
+        return FieldArray.from_kwargs(loglr=logl, logprior=self._lnprob_h[0] - logl)

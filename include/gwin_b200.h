@@ -143,6 +143,60 @@ int gwin_plan_last_launches(const gwin_plan* plan);
  * [ms] and count of the loglr-kernel launches since the previous call, then resets. */
 int gwin_plan_kernel_timing(gwin_plan* plan, int enable, double* mean_ms, int* n_launches);
 
+/* ------------------------------------------------------------------------------------------
+ * Device-resident ensemble step (replaces, on the device, what emcee does on the host between
+ * two pool.map calls -- gwin/sampler/emcee.py:74-76, 286-289; semantics of emcee 2.x, SURVEY.md
+ * appendix B).  All buffers are DEVICE pointers owned by the caller; all calls are asynchronous on
+ * `stream`.  Random numbers are Philox4x32-10(seed; iteration, stage, index): every rank of a
+ * multi-GPU run regenerates identical numbers, so only log-likelihoods need to be exchanged.
+ * ------------------------------------------------------------------------------------------ */
+#define GWIN_ENS_MAXDIM 16
+
+#define GWIN_PRIOR_UNIFORM        0   /* pycbc.distributions.Uniform                          */
+#define GWIN_PRIOR_UNIFORM_ANGLE  1   /* UniformAngle: cyclic on [lo, hi)                      */
+#define GWIN_PRIOR_SIN_ANGLE      2   /* SinAngle: p ~ sin x, reflected into [0, pi]           */
+#define GWIN_PRIOR_COS_ANGLE      3   /* CosAngle: p ~ cos x, reflected into [-pi/2, pi/2]     */
+#define GWIN_PRIOR_UNIFORM_RADIUS 4   /* UniformRadius: p ~ x^2                                */
+
+#define GWIN_TARGET_MCHIRP 100        /* sampling dim is mchirp ...                            */
+#define GWIN_TARGET_Q      101        /* ... / q = m1/m2: mapped to mass1, mass2 on the device */
+
+typedef struct gwin_prior_spec {
+    int32_t ndim;                       /* sampling dimensions                                   */
+    int32_t type[GWIN_ENS_MAXDIM];      /* GWIN_PRIOR_*                                          */
+    int32_t target[GWIN_ENS_MAXDIM];    /* waveform-parameter column 0..10, or GWIN_TARGET_*     */
+    double lo[GWIN_ENS_MAXDIM], hi[GWIN_ENS_MAXDIM];
+    double fixed[GWIN_NPARAM];          /* static values of the parameters that are not sampled  */
+} gwin_prior_spec;
+
+/* Stretch-move proposals for one half (0/1) of every temperature.
+ *   p [ntemps][nwalkers][ndim] -> q [ntemps][nwalkers/2][ndim], logfac [ntemps][nwalkers/2]
+ *   move 0: EnsembleSampler (z = ((a-1)u+1)^2/a, logfac = (ndim-1) ln z), halves are contiguous
+ *   move 1: PTSampler       (ln z ~ U(-ln a, ln a),  logfac = ndim ln z), halves are interleaved */
+int gwin_ens_propose(uint64_t seed, uint32_t iter, int half, int ntemps, int nwalkers, int ndim,
+                     double a, int move, int interleaved,
+                     const double* p, double* q, double* logfac, void* stream);
+
+/* Boundary conditions, log prior and the likelihood kernel's parameter rows for W points:
+ * q [W][ndim] -> logp [W], skip [W] (1 where logp = -inf), params [11][W] (parameter-major, feed to
+ * gwin_loglr_batch_strided with strides (1, W)).  Replaces _transform_params + logprior
+ * (gwin/models/base.py:543-554, 602-621) for the supported distributions. */
+int gwin_ens_prior(const gwin_prior_spec* spec, int64_t W, const double* q,
+                   double* logp, uint8_t* skip, double* params, void* stream);
+
+/* Accept/reject: ln u < logfac + (beta_k q_logl + q_logp) - lnprob; updates p, logl, lnprob
+ * ([ntemps][nwalkers]...) and the per-walker acceptance counters. */
+int gwin_ens_accept(uint64_t seed, uint32_t iter, int half, int ntemps, int nwalkers, int ndim,
+                    int interleaved, const double* betas, const double* q, const double* logfac,
+                    const double* q_logl, const double* q_logp,
+                    double* p, double* logl, double* lnprob, int* naccept, void* stream);
+
+/* Swap attempt between temperature `level` and `level-1` for the walker pairs
+ * (iperm[j], i1perm[j]) (emcee PTSampler._temperature_swaps). */
+int gwin_ens_swap(uint64_t seed, uint32_t iter, int level, int nwalkers, int ndim,
+                  const double* betas, const int* iperm, const int* i1perm,
+                  double* p, double* logl, double* lnprob, int* nswap_accepted, void* stream);
+
 /* FP64 issue-rate micro-benchmark on the plan's device: runs a dependent-chain-free
  * DFMA loop and returns achieved FP64 FMA lane-ops per second. */
 int gwin_fp64_peak(int device, double* dfma_per_sec);

@@ -1,0 +1,123 @@
+"""Device-resident ensemble step (``gwin_ens_*`` + ``CudaEnsembleSampler`` / ``CudaPTSampler``)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+from scipy import stats
+
+import util
+from gwin_b200 import _lib, distributions as D, models, transforms as T
+from gwin_b200.sampler import (CudaEnsembleSampler, CudaPTSampler, EmceeEnsembleSampler)
+from gwin_b200.sampler.cuda import prior_spec_from_model
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(cfg, names, prior, **kw):
+    static = {k: v for k, v in cfg.inj.items() if k not in names and k not in ('mass1', 'mass2') or
+              (k in ('mass1', 'mass2') and 'mchirp' not in names and k not in names)}
+    return cfg.cuda_model(variable_params=tuple(names), static_params=static, prior=prior, **kw)
+
+
+def test_device_prior_matches_host_distributions():
+    """gwin_ens_prior == boundary conditions + JointDistribution + parameter assembly on the host."""
+    import torch
+    cfg = util.c2()
+    names = ['mchirp', 'q', 'distance', 'inclination', 'coa_phase', 'ra', 'dec', 'polarization', 'tc']
+    prior = D.JointDistribution(
+        names, D.Uniform(mchirp=(20., 30.), q=(1., 3.)), D.UniformRadius(distance=(100., 1000.)),
+        D.SinAngle(inclination=None), D.UniformAngle(coa_phase=None), D.UniformSky(),
+        D.UniformAngle(polarization=(0., np.pi)), D.Uniform(tc=(cfg.inj['tc'] - 0.1, cfg.inj['tc'] + 0.1)))
+    model = _model(cfg, names, prior, waveform_transforms=[T.MchirpQToMass1Mass2()])
+    spec = prior_spec_from_model(model)
+    rng = np.random.RandomState(0)
+    W = 4000
+    q = np.column_stack([rng.uniform(18, 32, W), rng.uniform(0.8, 3.2, W), rng.uniform(50, 1100, W),
+                         rng.uniform(-1, 4, W), rng.uniform(-7, 14, W), rng.uniform(-7, 14, W),
+                         rng.uniform(-2.5, 2.5, W), rng.uniform(-4, 7, W),
+                         cfg.inj['tc'] + rng.uniform(-0.12, 0.12, W)])
+    qd = torch.tensor(q, device="cuda")
+    logp = torch.empty(W, dtype=torch.float64, device="cuda")
+    skip = torch.empty(W, dtype=torch.uint8, device="cuda")
+    params = torch.empty((11, W), dtype=torch.float64, device="cuda")
+    _lib.check(_lib.load().gwin_ens_prior(C.byref(spec), W, qd.data_ptr(), logp.data_ptr(),
+                                          skip.data_ptr(), params.data_ptr(), None))
+    torch.cuda.synchronize()
+    res = models.CallModel(model, 'logprior').batch(q)
+    host = res.values
+    dev = logp.cpu().numpy()
+    assert np.array_equal(np.isneginf(host), np.isneginf(dev))
+    ok = np.isfinite(host)
+    assert ok.sum() > 100 and (~ok).sum() > 100
+    assert np.allclose(host[ok], dev[ok], rtol=1e-13, atol=1e-13)
+    assert np.array_equal(skip.cpu().numpy().astype(bool), ~ok)
+    # the parameter rows equal what the host path hands to the kernel
+    from gwin_b200.waveform import param_rows
+    hp = param_rows(model._transform_params(**{n: q[:, i] for i, n in enumerate(names)}), W,
+                    static=model._static_for_kernel())
+    assert np.allclose(params.cpu().numpy()[:, ok], hp[:, ok], rtol=1e-13, atol=1e-13)
+
+
+def test_device_ensemble_sampler_matches_host_sampler_statistically():
+    """Same target, two implementations of the emcee step (host numpy RNG vs device Philox):
+    per-parameter two-sample KS p > 0.01."""
+    cfg = util.c1()
+    names = ['tc', 'distance', 'inclination', 'coa_phase']
+    prior = D.JointDistribution(
+        names, D.Uniform(tc=(cfg.inj['tc'] - 0.02, cfg.inj['tc'] + 0.02)),
+        D.UniformRadius(distance=(100., 1500.)), D.SinAngle(inclination=None),
+        D.UniformAngle(coa_phase=None))
+    model = _model(cfg, names, prior)
+    np.random.seed(77)
+    host = EmceeEnsembleSampler(model, 256, model_call=models.CallModel(model, 'logplr'))
+    host.set_p0()
+    host.run(500)
+    np.random.seed(78)
+    dev = CudaEnsembleSampler(model, 256, seed=1234)
+    dev.set_p0()
+    dev.run(500)
+    assert dev.chain.shape == (256, 500, 4) and dev.lnpost.shape == (256, 500)
+    assert 0.05 < dev.acceptance_fraction.mean() < 0.9
+    assert abs(dev.acceptance_fraction.mean() - host.acceptance_fraction.mean()) < 0.05
+    a = host.samples
+    b = dev.samples
+    for n in names:
+        x = np.asarray(a[n])[:, 250::25].ravel()
+        y = np.asarray(b[n])[:, 250::25].ravel()
+        assert stats.ks_2samp(x, y).pvalue > 0.01, n
+    # the chain's lnpost is the model's logplr at the stored positions
+    pts = dev.chain[:8, -1, :]
+    ref = models.CallModel(model, 'logplr').batch(pts).values
+    assert np.allclose(dev.lnpost[:8, -1], ref, rtol=1e-10, atol=1e-8)
+    # same seed -> same chain (counter-based RNG)
+    np.random.seed(78)
+    dev2 = CudaEnsembleSampler(model, 256, seed=1234)
+    dev2.set_p0()
+    dev2.run(20)
+    np.testing.assert_array_equal(dev2.chain, dev.chain[:, :20, :])
+
+
+def test_device_pt_sampler():
+    cfg = util.c2()
+    names = ['tc', 'distance']
+    prior = D.JointDistribution(names, D.Uniform(tc=(cfg.inj['tc'] - 0.05, cfg.inj['tc'] + 0.05)),
+                                D.UniformRadius(distance=(50., 2000.)))
+    model = _model(cfg, names, prior, cls=models.MarginalizedPhaseGaussianNoise)
+    np.random.seed(5)
+    pt = CudaPTSampler(model, 4, 64, seed=99)
+    assert pt.set_p0().shape == (4, 64, 2)
+    pt.run(60)
+    assert pt.chain.shape == (4, 64, 60, 2)
+    assert np.all(np.isfinite(pt.lnpost))
+    ms = pt.model_stats
+    # logl history is loglr at the stored positions; lnprob = beta*loglr + logprior
+    pts = pt.chain[1, :5, -1, :]
+    res = models.CallModel(model, 'logplr').batch(pts)
+    assert np.allclose(ms['loglr'][1, :5, -1], res.stats['loglr'], rtol=1e-10, atol=1e-8)
+    assert np.allclose(ms['logprior'][1, :5, -1], res.stats['logprior'], rtol=1e-10, atol=1e-8)
+    sw = pt.tswap_acceptance_fraction
+    assert np.all(sw >= 0) and np.all(sw <= 1) and sw.sum() > 0
+    # hotter chains explore more
+    assert pt.chain[3, :, 30:, 1].std() > pt.chain[0, :, 30:, 1].std()
+    with pytest.raises(NotImplementedError):
+        CudaPTSampler(_model(cfg, names, D.JointDistribution(names, D.Gaussian(tc=None), D.Uniform(distance=(1, 2)))), 2, 8)

@@ -32,7 +32,7 @@ def test_no_prior_and_default_stats():
 def test_registry_and_names():
     assert set(models.models) >= {'gaussian_noise', 'marginalized_gaussian_noise', 'test_normal'}
     assert models.models['gaussian_noise'] is models.GaussianNoise
-    assert set(samplers) == {'emcee', 'emcee_pt'}
+    assert set(samplers) == {'emcee', 'emcee_pt', 'emcee_cuda', 'emcee_pt_cuda'}
 
 
 def test_distributions_vectorised():
