@@ -58,33 +58,84 @@ def test_device_prior_matches_host_distributions():
     assert np.allclose(params.cpu().numpy()[:, ok], hp[:, ok], rtol=1e-13, atol=1e-13)
 
 
-def test_device_ensemble_sampler_matches_host_sampler_statistically():
-    """Same target, two implementations of the emcee step (host numpy RNG vs device Philox):
-    per-parameter two-sample KS p > 0.01."""
-    cfg = util.c1()
-    names = ['tc', 'distance', 'inclination', 'coa_phase']
+def test_device_sampler_recovers_the_prior_and_tracks_the_host_stepper():
+    """Noise-only data and sources at 1e7 Mpc: loglr = 0, the posterior is the prior.
+    (i) in a bounded 2-D problem the device step (stretch move, accept) reproduces the prior
+    exactly (KS against the analytic CDFs); (ii) in 6-D with cyclic / reflected angles, where
+    the stretch move itself mixes poorly within a few hundred steps, the device sampler and the
+    host stepper (emcee semantics) still produce the same distributions (two-sample KS)."""
+    inj = dict(util.BBH_INJ)
+    inj['distance'] = 1e12                 # noise-only data
+    cfg = util.Config("noise", 8, 2048., 20., ["H1", "L1", "V1"], inj)
+    lo, hi = cfg.inj['tc'] - 0.05, cfg.inj['tc'] + 0.05
+    names = ['distance', 'tc']
+    prior = D.JointDistribution(names, D.UniformRadius(distance=(1e7, 2e7)), D.Uniform(tc=(lo, hi)))
+    model = _model(cfg, names, prior)
+    np.random.seed(3)
+    dev = CudaEnsembleSampler(model, 512, seed=42)
+    dev.set_p0()
+    dev.run(300)
+    s = dev.samples
+    sel = (slice(None), slice(50, None, 25))
+    u = {'distance': (np.asarray(s['distance'])[sel].ravel() ** 3 - 1e21) / 7e21,
+         'tc': (np.asarray(s['tc'])[sel].ravel() - lo) / (hi - lo)}
+    for n, v in u.items():
+        assert np.all((v >= 0) & (v <= 1)), n
+        assert stats.kstest(v, 'uniform').pvalue > 1e-3, (n, stats.kstest(v, 'uniform'))
+    assert np.all(np.abs(dev.lnpost[:, -1] - np.asarray(
+        models.CallModel(model, 'logprior').batch(dev.chain[:, -1, :]).values)) < 0.05)
+    assert 0.5 < dev.acceptance_fraction.mean() < 0.75
+
+    names = ['distance', 'inclination', 'coa_phase', 'ra', 'dec', 'tc']
     prior = D.JointDistribution(
-        names, D.Uniform(tc=(cfg.inj['tc'] - 0.02, cfg.inj['tc'] + 0.02)),
-        D.UniformRadius(distance=(100., 1500.)), D.SinAngle(inclination=None),
-        D.UniformAngle(coa_phase=None))
+        names, D.UniformRadius(distance=(1e7, 2e7)), D.SinAngle(inclination=None),
+        D.UniformAngle(coa_phase=None), D.UniformSky(), D.Uniform(tc=(lo, hi)))
+    model = _model(cfg, names, prior)
+    np.random.seed(4)
+    host = EmceeEnsembleSampler(model, 512, model_call=models.CallModel(model, 'logplr'))
+    host.set_p0()
+    host.run(300)
+    np.random.seed(5)
+    dev = CudaEnsembleSampler(model, 512, seed=43)
+    dev.set_p0()
+    dev.run(300)
+    assert abs(dev.acceptance_fraction.mean() - host.acceptance_fraction.mean()) < 0.03
+    a, b = host.samples, dev.samples
+    for n in names:
+        x = np.asarray(a[n])[:, 100::50].ravel()
+        y = np.asarray(b[n])[:, 100::50].ravel()
+        assert stats.ks_2samp(x, y).pvalue > 1e-3, n
+    # boundary conditions were applied when reading the samples
+    assert np.all((np.asarray(b['coa_phase']) >= 0) & (np.asarray(b['coa_phase']) < 2 * np.pi))
+    assert np.all((np.asarray(b['inclination']) >= 0) & (np.asarray(b['inclination']) <= np.pi))
+
+
+def test_device_ensemble_sampler_matches_host_sampler_statistically():
+    """Same target, two implementations of the emcee step (host numpy RNG vs device Philox) on
+    a weak signal (broad, unimodal posterior): per-parameter two-sample KS p > 0.01."""
+    inj = dict(util.BBH_INJ)
+    inj['distance'] = 2500.
+    cfg = util.Config("weak", 8, 2048., 20., ["H1", "L1"], inj)
+    names = ['distance', 'inclination']
+    prior = D.JointDistribution(names, D.UniformRadius(distance=(500., 8000.)),
+                                D.SinAngle(inclination=None))
     model = _model(cfg, names, prior)
     np.random.seed(77)
     host = EmceeEnsembleSampler(model, 256, model_call=models.CallModel(model, 'logplr'))
     host.set_p0()
-    host.run(500)
+    host.run(600)
     np.random.seed(78)
     dev = CudaEnsembleSampler(model, 256, seed=1234)
     dev.set_p0()
-    dev.run(500)
-    assert dev.chain.shape == (256, 500, 4) and dev.lnpost.shape == (256, 500)
-    assert 0.05 < dev.acceptance_fraction.mean() < 0.9
+    dev.run(600)
+    assert dev.chain.shape == (256, 600, 2) and dev.lnpost.shape == (256, 600)
     assert abs(dev.acceptance_fraction.mean() - host.acceptance_fraction.mean()) < 0.05
     a = host.samples
     b = dev.samples
     for n in names:
-        x = np.asarray(a[n])[:, 250::25].ravel()
-        y = np.asarray(b[n])[:, 250::25].ravel()
-        assert stats.ks_2samp(x, y).pvalue > 0.01, n
+        x = np.asarray(a[n])[:, 200::40].ravel()
+        y = np.asarray(b[n])[:, 200::40].ravel()
+        assert stats.ks_2samp(x, y).pvalue > 0.01, (n, x.mean(), y.mean())
     # the chain's lnpost is the model's logplr at the stored positions
     pts = dev.chain[:8, -1, :]
     ref = models.CallModel(model, 'logplr').batch(pts).values

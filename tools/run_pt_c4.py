@@ -19,7 +19,7 @@ import util
 from gwin_b200 import distributions as D, models
 from gwin_b200.distributed import WalkerSharding
 from gwin_b200.pool import BatchPool
-from gwin_b200.sampler import EmceePTSampler
+from gwin_b200.sampler import CudaPTSampler, EmceePTSampler
 
 world = int(os.environ.get("WORLD_SIZE", "1"))
 rank = int(os.environ.get("RANK", "0"))
@@ -33,6 +33,7 @@ ntemps = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 nwalkers = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
 niter = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 seglen = int(sys.argv[4]) if len(sys.argv) > 4 else 256
+resident = (sys.argv[5] if len(sys.argv) > 5 else "device") == "device"
 
 cfg = util.c3(seglen=seglen)
 inj = cfg.inj
@@ -44,7 +45,7 @@ prior = D.JointDistribution(
 model = cfg.cuda_model(variable_params=tuple(names), static_params={'spin1z': 0., 'spin2z': 0.},
                        prior=prior, device=local)
 np.random.seed(20184)                       # replicated RNG: identical decisions on every rank
-pt = EmceePTSampler(model, ntemps, nwalkers, pool=pool)
+pt = CudaPTSampler(model, ntemps, nwalkers, seed=4242) if resident else EmceePTSampler(model, ntemps, nwalkers, pool=pool)
 pt.set_p0()
 pt.run(1)                                   # warm-up (also evaluates the initial ensemble)
 torch.cuda.synchronize()
@@ -66,10 +67,11 @@ if world > 1:
 else:
     same = True
 if rank == 0:
-    print("C4 PT: %d GPUs, %d temps x %d walkers, %d iterations, T=%d s: %.3f s -> %.4e likelihood evals/s "
+    sw = pt.tswap_acceptance_fraction if resident else pt.sampler.tswap_acceptance_fraction
+    print("C4 PT (%s stepper): %d GPUs, %d temps x %d walkers, %d iterations, T=%d s: %.3f s -> %.4e likelihood evals/s "
           "(whole sampler path); chains identical on all ranks: %s; cold-chain acceptance %.2f; swap acceptance %s"
-          % (world, ntemps, nwalkers, niter, seglen, dt, evals / dt, same,
-             pt.acceptance_fraction[0].mean(), np.round(pt.sampler.tswap_acceptance_fraction, 2)))
+          % ("device-resident" if resident else "host", world, ntemps, nwalkers, niter, seglen, dt, evals / dt, same,
+             pt.acceptance_fraction[0].mean(), np.round(sw, 2)))
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()
