@@ -827,24 +827,39 @@ __device__ __forceinline__ double log_i0(double x) {
     return x - 0.5 * log(G_TWOPI * x) + log(ser);
 }
 
-__global__ void combine_kernel(int n_det, int W, int wpad, int n_chunks, int mode,
-                               const int* __restrict__ perm, const double* __restrict__ wc,
-                               const int* __restrict__ ks_arr,
-                               const double2* __restrict__ partial,
-                               const double* __restrict__ hh_sorted,
-                               double* __restrict__ loglr, double* __restrict__ hd_out,
-                               double* __restrict__ hh_out) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= W) return;
+#define COMB_SEG 8      // chunk segments summed in parallel per walker (fixed order: deterministic)
+__global__ void __launch_bounds__(32 * COMB_SEG)
+combine_kernel(int n_det, int W, int wpad, int n_chunks, int mode,
+               const int* __restrict__ perm, const double* __restrict__ wc,
+               const int* __restrict__ ks_arr,
+               const double2* __restrict__ partial,
+               const double* __restrict__ hh_sorted,
+               double* __restrict__ loglr, double* __restrict__ hd_out,
+               double* __restrict__ hh_out) {
+    __shared__ double2 s_part[COMB_SEG][GWIN_MAX_DET][32];
+    const int lx = threadIdx.x, seg = threadIdx.y;
+    const int t = blockIdx.x * 32 + lx;
+    const bool live = t < W;
+    // stage 1: thread (lx, seg) sums chunks seg, seg + COMB_SEG, ... of walker t (coalesced in t)
+    for (int d = 0; d < n_det; ++d) {
+        double re = 0.0, im = 0.0;
+        if (live)
+            for (int c = seg; c < n_chunks; c += COMB_SEG) {
+                const double2 p = partial[((size_t)c * n_det + d) * wpad + t];
+                re += p.x; im += p.y;
+            }
+        s_part[seg][d][lx] = make_double2(re, im);
+    }
+    __syncthreads();
+    if (seg != 0 || !live) return;
+    // stage 2: one thread per walker finishes
     const int w = perm ? perm[t] : t;
     const bool invalid = ks_arr[t] < 0;
     double lr = 0.0, sre = 0.0, sim = 0.0, shh = 0.0;
     for (int d = 0; d < n_det; ++d) {
         double re = 0.0, im = 0.0;
-        for (int c = 0; c < n_chunks; ++c) {
-            const double2 p = partial[((size_t)c * n_det + d) * wpad + t];
-            re += p.x; im += p.y;
-        }
+#pragma unroll
+        for (int q = 0; q < COMB_SEG; ++q) { re += s_part[q][d][lx].x; im += s_part[q][d][lx].y; }
         const double* row = wc + (size_t)(C_DET0 + D_NROW * d) * wpad + t;
         const double are = row[D_ARE * wpad], aim = row[D_AIM * wpad];
         const double hre = are * re - aim * im;
@@ -1336,8 +1351,8 @@ extern "C" int gwin_loglr_batch_strided(gwin_plan* p, int mode, int64_t W64,
         default: launch_main<4>(p, recur, W, wpad, n_chunks, per_chunk, hh_rows, st); break;
     }
     if (p->timing) { CK(cudaEventRecord(p->ev1, st)); p->ev_pending = true; }
-    combine_kernel<<<gb, tb, 0, st>>>(nd, W, wpad, n_chunks, mode, perm, p->d_wc, p->d_ks, p->d_partial,
-                                      hh_rows, loglr, hd, hh);
+    combine_kernel<<<(W + 31) / 32, dim3(32, COMB_SEG), 0, st>>>(nd, W, wpad, n_chunks, mode, perm, p->d_wc, p->d_ks,
+                                                                 p->d_partial, hh_rows, loglr, hd, hh);
     p->last_launches += 3;
     CK(cudaGetLastError());
     return GWIN_OK;

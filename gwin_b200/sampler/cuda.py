@@ -147,6 +147,7 @@ class _DeviceEnsemble(BaseMCMCSampler):
         self._p = None
         self._iterations = 0
         self._chain = self._lnprob_h = self._logl_h = None
+        self._pending = []
         self.likelihood_evals = 0
         # the block schedule of the recurrence kernel must cover the smallest chirp mass the
         # prior allows (the device entry point cannot look at the batch without a sync)
@@ -287,20 +288,33 @@ class _DeviceEnsemble(BaseMCMCSampler):
             lnp_h[:, :, it].copy_(self._lnprob)
             lnl_h[:, :, it].copy_(self._logl)
             self._iterations += 1
-        c, a, b = chain.cpu().numpy(), lnp_h.cpu().numpy(), lnl_h.cpu().numpy()     # one sync per run()
-        if self._chain is None:
-            self._chain, self._lnprob_h, self._logl_h = c, a, b
-        else:
-            self._chain = numpy.concatenate((self._chain, c), axis=2)
-            self._lnprob_h = numpy.concatenate((self._lnprob_h, a), axis=2)
-            self._logl_h = numpy.concatenate((self._logl_h, b), axis=2)
-        self._pos = self._p.cpu().numpy()
-        return self._pos, self._lnprob.cpu().numpy(), (self._seed, self._iterations)
+        # histories stay on the device until somebody reads them (chain / lnpost / model_stats)
+        self._pending.append((chain, lnp_h, lnl_h))
+        self._pos = None
+        return self._p, self._lnprob, (self._seed, self._iterations)
+
+    def _flush(self):
+        """Bring pending device histories to the host (one D2H per history per run())."""
+        for chain, lnp_h, lnl_h in self._pending:
+            c, a, b = chain.cpu().numpy(), lnp_h.cpu().numpy(), lnl_h.cpu().numpy()
+            if self._chain is None:
+                self._chain, self._lnprob_h, self._logl_h = c, a, b
+            else:
+                self._chain = numpy.concatenate((self._chain, c), axis=2)
+                self._lnprob_h = numpy.concatenate((self._lnprob_h, a), axis=2)
+                self._logl_h = numpy.concatenate((self._logl_h, b), axis=2)
+        self._pending = []
+
+    @property
+    def pos(self):
+        """Current positions (host copy)."""
+        return None if self._p is None else self._p.cpu().numpy()
 
     def clear_chain(self):
         self.lastclear = self.niterations
         self._iterations = 0
         self._chain = self._lnprob_h = self._logl_h = None
+        self._pending = []
         self._naccept.zero_()
         self._nswap_acc.zero_()
         self._nswap = 0
@@ -327,15 +341,18 @@ class CudaPTSampler(_DeviceEnsemble):
     @property
     def chain(self):
         """ntemps x nwalkers x niterations x ndim."""
+        self._flush()
         return self._chain if self._chain is not None else \
             numpy.empty((self._ntemps, self._nwalkers, 0, self._ndim))
 
     @property
     def lnpost(self):
+        self._flush()
         return self._lnprob_h
 
     @property
     def model_stats(self):
+        self._flush()
         logl = self._logl_h
         logp = self._lnprob_h - logl * self._betas_host.reshape(-1, 1, 1)
         return FieldArray.from_kwargs(loglr=logl, logprior=logp)
@@ -358,11 +375,13 @@ class CudaEnsembleSampler(_DeviceEnsemble):
     @property
     def chain(self):
         """nwalkers x niterations x ndim."""
+        self._flush()
         return self._chain[0] if self._chain is not None else \
             numpy.empty((self._nwalkers, 0, self._ndim))
 
     @property
     def lnpost(self):
+        self._flush()
         return self._lnprob_h[0]
 
     @property
@@ -371,5 +390,6 @@ class CudaEnsembleSampler(_DeviceEnsemble):
 
     @property
     def model_stats(self):
+        self._flush()
         logl = self._logl_h[0]
         return FieldArray.from_kwargs(loglr=logl, logprior=self._lnprob_h[0] - logl)

@@ -52,12 +52,21 @@ torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
 n0 = pool.npoints
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+model.plan.kernel_timing(True)
+e0.record()
 t0 = time.perf_counter()
 pt.run(niter)
+t_issue = time.perf_counter() - t0
+e1.record()
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
+kms, kn = model.plan.kernel_timing(False)
+if rank == 0:
+    print("   wall %.1f ms, host issue %.1f ms, device span %.1f ms, loglr kernel %.3f ms x %d = %.1f ms"
+          % (dt * 1e3, t_issue * 1e3, e0.elapsed_time(e1), kms, kn, kms * kn))
 evals = ntemps * nwalkers * niter           # two half-steps of ntemps*nwalkers/2 points per iteration
-chk = float(np.sum(pt.chain[:, :, -1, :]))
+chk = float(np.sum(pt.chain[:, :, -1, :]))      # after the timed region: histories are flushed lazily
 if world > 1:
     t = torch.tensor([dt, chk], dtype=torch.float64, device="cuda")
     tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
