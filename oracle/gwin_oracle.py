@@ -309,6 +309,10 @@ _DETECTOR_GEOMETRY = {
     "V1": ((4.54637409900e+06, 8.42989697626e+05, 4.37857696241e+06),
            (-0.70045821479, +0.20848948619, +0.68256166277),
            (-0.05379255368, -0.96908180549, +0.24080451708)),
+    # KAGRA (LAL_KAGRA_*), used for the 4-detector code path
+    "K1": ((-3777336.024, 3484898.411, 3765313.697),
+           (-0.3759040, -0.8361583, 0.3994189),
+           (0.7164378, 0.01114076, 0.6975620)),
 }
 
 

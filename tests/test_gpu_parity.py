@@ -241,6 +241,35 @@ def test_detector_counts_unit_psd_fupper(dets):
     assert abs(model.lognl - orc.lognl()) <= 1e-9 * abs(orc.lognl())
 
 
+def test_four_detectors_and_large_batch():
+    """n_det = 4 (the narrower TMA tile variant of the kernels) and a 100k-walker batch that
+    grows the workspace: both kernels against the oracle on a sample and against each other on
+    everything."""
+    import gwin_oracle as O
+    cfg = util.Config("four", 8, 2048., 20., ["H1", "L1", "V1", "K1"], util.BBH_INJ, seed=5)
+    model = cfg.cuda_model()
+    rng = np.random.default_rng(6)
+    P = util.draw_bbh(rng, 100003, cfg)
+    model.plan.configure(kernel=1)
+    a = model.plan.loglr_host(P)
+    model.plan.configure(kernel=2)
+    b = model.plan.loglr_host(P)
+    assert a[1].shape == (100003, 4)
+    assert np.all(np.abs(a[0] - b[0]) <= tol(a[0]))
+    sel = rng.choice(len(P), 48, replace=False)
+    lr0, hd0, hh0 = O.batch_loglr(cfg.oracle(), P[sel])
+    _check(b[0][sel], b[1][sel], b[2][sel], lr0, hd0, hh0, "4 detectors")
+    # marginalised phase on the same batch
+    m = model.plan.loglr_host(P[sel], mode=1)
+    lrm = O.batch_loglr(cfg.oracle(phase_marginalization=True), P[sel])[0]
+    assert np.all(np.abs(m[0] - lrm) <= tol(lrm))
+    # a smaller batch after a larger one reuses the workspace; a different batch size means a
+    # different chunking (and block schedule) of the frequency axis, so results agree to
+    # rounding, not bit for bit
+    c = model.plan.loglr_host(P[:77])
+    assert np.all(np.abs(c[0] - b[0][:77]) <= 1e-9 * np.maximum(1.0, np.abs(c[0])))
+
+
 def test_linearity_in_data(cfg2):
     """Size-independent property: <d|h> is linear in the data, <h|h> does not
     depend on it."""
