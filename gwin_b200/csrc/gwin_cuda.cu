@@ -1147,15 +1147,23 @@ extern "C" int gwin_plan_create(gwin_plan** out, int device, int n_det, int64_t 
     p->lognl = 0.0;
     for (int det = 0; det < n_det; ++det) p->lognl += p->lognl_det[det];
 
-    double4* db = nullptr; double2* dT = nullptr; double* dC = nullptr;
-    CK(cudaMalloc(&db, basis.size() * sizeof(double)));
-    CK(cudaMalloc(&dT, T.size() * sizeof(double)));
-    CK(cudaMalloc(&dC, C.size() * sizeof(double)));
-    CK(cudaMemcpy(db, basis.data(), basis.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dT, T.data(), T.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dC, C.data(), C.size() * sizeof(double), cudaMemcpyHostToDevice));
-    d.basis = db; d.T = dT; d.C = dC;
-    CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    // device replicas; on any failure the partially built plan is torn down again
+    auto upload = [&]() -> int {
+        double4* db = nullptr; double2* dT = nullptr; double* dC = nullptr;
+        CK(cudaMalloc(&db, basis.size() * sizeof(double)));
+        d.basis = db;
+        CK(cudaMalloc(&dT, T.size() * sizeof(double)));
+        d.T = dT;
+        CK(cudaMalloc(&dC, C.size() * sizeof(double)));
+        d.C = dC;
+        CK(cudaMemcpy(db, basis.data(), basis.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dT, T.data(), T.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dC, C.data(), C.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+        return GWIN_OK;
+    };
+    const int rc = upload();
+    if (rc != GWIN_OK) { gwin_plan_destroy(p); return rc; }
     *out = p;
     return GWIN_OK;
 }
@@ -1460,10 +1468,15 @@ extern "C" int gwin_generate_host(gwin_plan* p, const double* params, double* h_
     CK(cudaMalloc(&dout, sizeof(double2) * (size_t)d.n_det * d.n_f));
     generate_kernel<<<(d.n_f + 255) / 256, 256, 0, st>>>(d, wpad, p->d_wc, p->d_ke, dout);
     int n = 0;
-    CK(cudaMemcpyAsync(h_out, dout, sizeof(double2) * (size_t)d.n_det * d.n_f, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&n, p->d_ke + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    auto fetch = [&]() -> int {
+        CK(cudaMemcpyAsync(h_out, dout, sizeof(double2) * (size_t)d.n_det * d.n_f, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&n, p->d_ke + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return GWIN_OK;
+    };
+    rc = fetch();
     cudaFree(dout);
+    if (rc) return rc;
     if (length) *length = n;
     p->last_launches = 3;
     return GWIN_OK;

@@ -157,6 +157,61 @@ def test_taylorf2_against_closed_forms():
     assert np.allclose(hp[kk] / np.abs(hp[kk]), -model, atol=1e-6)   # amp0 < 0
 
 
+def test_phasing_matches_literature_form():
+    """The LAL-form coefficients against the 3.5PN stationary-phase phasing as printed in the
+    literature (Buonanno, Iyer, Ochsner, Pan & Sathyaprakash 2009, eq. 3.18; Arun et al. 2005),
+    written here independently in its textbook form."""
+    g = O.LAL_GAMMA
+    pi = math.pi
+    for m1, m2 in ((1.4, 1.4), (30., 30.), (10., 1.4), (35., 7.)):
+        eta = m1 * m2 / (m1 + m2) ** 2
+        ph = O.taylorf2_phasing(m1, m2)
+        pref = 3. / (128. * eta)
+        lit = {2: 20. / 9. * (743. / 336. + 11. / 4. * eta),
+               3: -16. * pi,
+               4: 10. * (3058673. / 1016064. + 5429. / 1008. * eta + 617. / 144. * eta ** 2),
+               5: pi * (38645. / 756. - 65. / 9. * eta),                 # x (1 + 3 ln v)
+               7: pi * (77096675. / 254016. + 378515. / 1512. * eta - 74045. / 756. * eta ** 2)}
+        for n in (2, 3, 4, 5, 7):
+            assert abs(ph["v"][n] / pref / lit[n] - 1) < 1e-14, (n, m1, m2)
+        assert abs(ph["vlogv"][5] / pref / (3 * lit[5]) - 1) < 1e-14
+        # 3PN: constant + log(4 v) term
+        a6 = (11583231236531. / 4694215680. - 640. / 3. * pi ** 2 - 6848. / 21. * g
+              + (-15737765635. / 3048192. + 2255. / 12. * pi ** 2) * eta
+              + 76055. / 1728. * eta ** 2 - 127825. / 1296. * eta ** 3)
+        v = 0.2
+        lal6 = ph["v"][6] / pref + ph["vlogv"][6] / pref * math.log(v)
+        assert abs(lal6 / (a6 - 6848. / 21. * math.log(4 * v)) - 1) < 1e-14
+        assert ph["v"][0] == pref and ph["v"][1] == 0.
+
+
+def test_antenna_pattern_against_closed_form():
+    """An L-shaped detector with arms along the Earth-fixed x and y axes: the polarisation-
+    independent combination F+^2 + Fx^2 has the textbook closed form in the source's polar angle
+    theta = pi/2 - dec and azimuth phi = ra - GMST (no sign convention enters)."""
+    det = O.Detector("H1")
+    xa, ya = np.array([1., 0., 0.]), np.array([0., 1., 0.])
+    det.response = 0.5 * (np.outer(xa, xa) - np.outer(ya, ya))
+    rng = np.random.default_rng(1)
+    for _ in range(50):
+        ra, dec, psi = rng.uniform(0, 2 * np.pi), np.arcsin(rng.uniform(-1, 1)), rng.uniform(0, np.pi)
+        t = 1.1e9 + rng.uniform(0, 1e7)
+        fp, fc = det.antenna_pattern(ra, dec, psi, t)
+        th, phi = np.pi / 2 - dec, ra - O.gmst(t)
+        closed = (0.5 * (1 + np.cos(th) ** 2)) ** 2 * np.cos(2 * phi) ** 2 + np.cos(th) ** 2 * np.sin(2 * phi) ** 2
+        assert abs(fp * fp + fc * fc - closed) < 1e-12
+        # overhead source (along +z): |F+| = |cos 2(psi')|-like, F+^2 + Fx^2 = 1
+    fp, fc = det.antenna_pattern(0.3, np.pi / 2, 0.7, 1.1e9)
+    assert abs(fp * fp + fc * fc - 1) < 1e-12
+    # light travel time: a source along the detector's position vector arrives R/c early
+    d = O.Detector("L1")
+    r = d.location
+    dec = np.arcsin(r[2] / np.linalg.norm(r))
+    t = 1.1e9
+    ra = (np.arctan2(r[1], r[0]) + O.gmst(t)) % (2 * np.pi)
+    assert abs(d.time_delay_from_earth_center(ra, dec, t) + np.linalg.norm(r) / O.LAL_C_SI) < 1e-12
+
+
 def test_spin_terms_known_limits():
     """1.5PN spin-orbit: equal masses, equal spins => 4 beta = (188/6) chi."""
     a = O.taylorf2_phasing(10., 10., 0.3, 0.3)

@@ -1,0 +1,35 @@
+"""Model the FP64 operand-fetch cost of the hot loops from SASS: cycles per FP64 warp-instruction
+= max(2, number of 64-bit source registers not served by the operand-reuse cache), where a reuse
+hit needs the previous FP64 instruction to have flagged the same register in the same slot."""
+import re, subprocess, sys
+lib = sys.argv[1] if len(sys.argv) > 1 else "gwin_b200/libgwin_b200.so"
+pat = sys.argv[2] if len(sys.argv) > 2 else "loglr_recur_kernelILi3"
+out = subprocess.run("cuobjdump -sass %s | awk '/Function : .*%s/{f=1} /Function : /{if(!/%s/)f=0} f'" % (lib, pat, pat),
+                     shell=True, capture_output=True, text=True).stdout
+ins = []
+for l in out.splitlines():
+    m = re.search(r'/\*([0-9a-f]{4})\*/\s+(.*?);', l)
+    if m: ins.append((int(m.group(1), 16), m.group(2).strip()))
+for i, (a, t) in enumerate(ins):
+    m = re.search(r'BRA\s+(0x[0-9a-f]+)', t)
+    if not m or int(m.group(1), 16) >= a: continue
+    lo = int(m.group(1), 16)
+    body = [x for x in ins if lo <= x[0] <= a]
+    fp = [x for x in body if re.search(r'\b(DFMA|DMUL|DADD)\b', x[1])]
+    if len(fp) < 100 or len(body) > 260: continue
+    cost, prev, nre = 0, set(), 0
+    for _, t2 in body:
+        mm = re.match(r'(@!?P\d+\s+)?(DFMA|DMUL|DADD)\s+(\S+),\s*(.*)', t2)
+        if not mm:
+            continue
+        ops = [o.strip() for o in mm.group(4).split(',')]
+        regs = []
+        for slot, o in enumerate(ops):
+            r = re.match(r'[-|]?(R\d+)(\.reuse)?', o)
+            if r: regs.append((slot, r.group(1), bool(r.group(2))))
+        fresh = sum(1 for slot, r, ru in regs if (slot, r) not in prev)
+        nre += sum(1 for slot, r, ru in regs if (slot, r) in prev)
+        cost += max(2, fresh)
+        prev = set((slot, r) for slot, r, ru in regs if ru)
+    print("loop %#x..%#x: %d instr, %d FP64, reuse hits %d, modelled %d cycles (ideal %d) -> %.1f%% of DFMA rate"
+          % (lo, a, len(body), len(fp), nre, cost, 2 * len(fp), 200.0 * len(fp) / cost))
