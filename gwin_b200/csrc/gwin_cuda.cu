@@ -45,7 +45,9 @@
 #define G_PC_SI   3.085677581491367278913937957796471611e16
 
 #define WARP 32
+#ifndef CTA_THREADS
 #define CTA_THREADS 128
+#endif
 #define RESYNC 64            // direct kernel: detector phasor re-sync interval
 #ifndef MAX_BLOCK
 #define MAX_BLOCK 256        // recurrence kernel: longest polynomial block

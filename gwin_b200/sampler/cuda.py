@@ -146,6 +146,7 @@ class _DeviceEnsemble(BaseMCMCSampler):
         self._local = torch.zeros(self._wmax, **f64)
         self._p = None
         self._iterations = 0
+        self._iter0 = 0              # RNG counter offset (resume / cleared chains)
         self._chain = self._lnprob_h = self._logl_h = None
         self._pending = []
         self.likelihood_evals = 0
@@ -213,10 +214,13 @@ class _DeviceEnsemble(BaseMCMCSampler):
         self.likelihood_evals += W
 
     def set_p0(self, samples_file=None, prior=None):
-        if samples_file is not None:
-            raise NotImplementedError("result files are outside the hot path")
         nt, nw = self._ntemps, self._nwalkers
-        samples = self.model.prior_rvs(size=nw * nt, prior=prior)
+        if samples_file is not None:
+            samples = samples_file.read_samples(self.sampling_params, iteration=-1,
+                                                flatten=False, group='sampling_samples')
+        else:
+            samples = self.model.prior_rvs(size=nw * nt, prior=prior)
+        self._p = None
         p0 = numpy.ones((nt, nw, self._ndim))
         for i, param in enumerate(self.sampling_params):
             p0[..., i] = numpy.asarray(samples[param]).reshape((nt, nw))
@@ -259,13 +263,13 @@ class _DeviceEnsemble(BaseMCMCSampler):
         perms = None
         if nt > 1:
             # replicated host RNG for the swap pairings: identical on every rank
-            rs = numpy.random.RandomState((self._seed + 7919 * self._iterations) % (2 ** 32))
+            rs = numpy.random.RandomState((self._seed + 7919 * (self._iterations + self._iter0)) % (2 ** 32))
             perms = numpy.stack([[[rs.permutation(nw), rs.permutation(nw)] for _ in range(nt - 1)]
                                  for _ in range(niterations)]).astype(numpy.int32)
             perms = torch.tensor(perms, device=self._dev)
         st = torch.cuda.current_stream(self._dev).cuda_stream
         for it in range(niterations):
-            gi = self._iterations
+            gi = self._iterations + self._iter0
             for half in (0, 1):
                 _lib.check(lib.gwin_ens_propose(
                     self._seed, gi, half, nt, nw, nd, self._a, self._move, self._interleaved,
@@ -310,8 +314,19 @@ class _DeviceEnsemble(BaseMCMCSampler):
         """Current positions (host copy)."""
         return None if self._p is None else self._p.cpu().numpy()
 
+    def write_state(self, fp):
+        """The RNG is counter based: seed + iteration counter are the whole state."""
+        fp.attrs['philox_seed'] = int(self._seed)
+        fp.attrs['philox_iteration'] = int(self._iterations + self._iter0)
+
+    def set_state_from_file(self, fp):
+        self._seed = int(fp.attrs['philox_seed'])
+        self._iter0 = int(fp.attrs['philox_iteration']) - self._iterations
+        self.lastclear = int(fp.attrs.get('niterations', 0))
+
     def clear_chain(self):
         self.lastclear = self.niterations
+        self._iter0 += self._iterations
         self._iterations = 0
         self._chain = self._lnprob_h = self._logl_h = None
         self._pending = []

@@ -77,6 +77,7 @@ class EmceeEnsembleSampler(BaseMCMCSampler):
         p0 = super(EmceeEnsembleSampler, self).set_p0(samples_file=samples_file,
                                                       prior=prior)
         self._sampler.random_state = numpy.random.get_state()
+        self._pos = None
         return p0
 
     def run(self, niterations, **kwargs):
@@ -144,14 +145,17 @@ class EmceePTSampler(BaseMCMCSampler):
         return FieldArray.from_kwargs(loglr=logl - lognl, logprior=logp)
 
     def set_p0(self, samples_file=None, prior=None):
-        if samples_file is not None:
-            raise NotImplementedError("result files are outside the hot path")
         ntemps, nwalkers = self.ntemps, self.nwalkers
         p0 = numpy.ones((ntemps, nwalkers, len(self.variable_params)))
-        samples = self.model.prior_rvs(size=nwalkers * ntemps, prior=prior)
+        if samples_file is not None:
+            samples = samples_file.read_samples(self.sampling_params, iteration=-1,
+                                                flatten=False, group='sampling_samples')
+        else:
+            samples = self.model.prior_rvs(size=nwalkers * ntemps, prior=prior)
         for i, param in enumerate(self.sampling_params):
             p0[..., i] = numpy.asarray(samples[param]).reshape((ntemps, nwalkers))
         self._p0 = p0
+        self._pos = None
         self._sampler.random_state = numpy.random.get_state()
         return p0
 

@@ -172,3 +172,32 @@ def test_device_pt_sampler():
     assert pt.chain[3, :, 30:, 1].std() > pt.chain[0, :, 30:, 1].std()
     with pytest.raises(NotImplementedError):
         CudaPTSampler(_model(cfg, names, D.JointDistribution(names, D.Gaussian(tc=None), D.Uniform(distance=(1, 2)))), 2, 8)
+
+
+def test_device_sampler_checkpoint_resume(tmp_path):
+    """Counter-based RNG: seed + iteration counter + positions resume a run bit for bit."""
+    from gwin_b200.io import InferenceFile
+    cfg = util.c2()
+    names = ['tc', 'distance']
+    prior = D.JointDistribution(names, D.Uniform(tc=(cfg.inj['tc'] - 0.05, cfg.inj['tc'] + 0.05)),
+                                D.UniformRadius(distance=(50., 2000.)))
+    model = _model(cfg, names, prior)
+    np.random.seed(8)
+    ref = CudaPTSampler(model, 3, 32, seed=7)
+    ref.set_p0()
+    ref.run(12)
+    np.random.seed(8)
+    a = CudaPTSampler(model, 3, 32, seed=7)
+    a.set_p0()
+    a.run(6)
+    path = str(tmp_path / "pt.npz")
+    with InferenceFile(path, 'w') as fp:
+        a.write_results(fp)
+    fp = InferenceFile(path, 'r')
+    assert fp['samples/tc'].shape == (3, 32, 6) and fp.attrs['sampler'] == 'emcee_pt_cuda'
+    b = CudaPTSampler(model, 3, 32, seed=12345)
+    b.set_p0(samples_file=fp)
+    b.set_state_from_file(fp)
+    b.run(6)
+    assert b.niterations == 12
+    np.testing.assert_array_equal(b.chain, ref.chain[:, :, 6:, :])

@@ -183,3 +183,56 @@ def test_data_model_sampler_smoke():
         s.run(4)
         assert s.niterations == 4
         assert np.all(np.isfinite(s.lnpost))
+
+
+def test_checkpoint_resume_is_bit_identical(tmp_path):
+    """Result file with the reference's tree (samples/, model_stats/, acceptance_fraction,
+    sampler_states/) and resume: 10 iterations, write, resume in a NEW sampler for 10 more ==
+    20 iterations straight (the reference restores positions + RNG state the same way,
+    bin/gwin:263-285, sampler/emcee.py:160-167)."""
+    from gwin_b200.io import InferenceFile, check_integrity
+    prior = D.JointDistribution(['x', 'y'], D.Uniform(x=(-20, 20), y=(-20, 20)))
+
+    def make():
+        return models.TestNormal(['x', 'y'], mean=[1., -2.], cov=[[1., .5], [.5, 2.]], prior=prior)
+    np.random.seed(21)
+    ref = EmceeEnsembleSampler(make(), 40)
+    ref.set_p0()
+    ref.run(20)
+    path = str(tmp_path / "run.npz")
+    np.random.seed(21)
+    a = EmceeEnsembleSampler(make(), 40)
+    a.set_p0()
+    a.run(10)
+    with InferenceFile(path, 'w') as fp:
+        a.write_results(fp, approximant="none")
+    assert check_integrity(path)
+    fp = InferenceFile(path, 'r')
+    assert fp.sampler_name == 'emcee' and fp.niterations == 10 and fp.variable_params == ['x', 'y']
+    assert fp['samples/x'].shape == (40, 10) and fp['model_stats/loglikelihood'].shape == (40, 10)
+    assert fp['acceptance_fraction'].shape == (40,)
+    assert fp.read_samples(['x'], thin_start=4, thin_interval=2)['x'].shape == (40 * 3,)
+    np.random.seed(999)                       # whatever the global state is now ...
+    b = EmceeEnsembleSampler(make(), 40)
+    b.set_p0(samples_file=fp)
+    b.set_state_from_file(fp)                 # ... the stepper continues from the saved state
+    b.run(10)
+    assert b.niterations == 20
+    np.testing.assert_array_equal(b.chain, ref.chain[:, 10:, :])
+    with InferenceFile(path, 'a') as fp2:
+        b.write_results(fp2)
+    fp3 = InferenceFile(path, 'r')
+    assert fp3['samples/x'].shape == (40, 20) and fp3.niterations == 20
+    np.testing.assert_array_equal(fp3['samples/x'], ref.chain[..., 0])
+    assert check_integrity(path)
+    # PT layout: ntemps x nwalkers x niterations
+    np.random.seed(3)
+    pt = EmceePTSampler(make(), 2, 20)
+    pt.set_p0()
+    pt.run(5)
+    p2 = str(tmp_path / "pt.npz")
+    with InferenceFile(p2, 'w') as fp:
+        pt.write_results(fp)
+    fp = InferenceFile(p2, 'r')
+    assert fp['samples/y'].shape == (2, 20, 5) and fp.attrs['ntemps'] == 2
+    assert fp['model_stats/loglr'].shape == (2, 20, 5)
