@@ -262,10 +262,15 @@ class _DeviceEnsemble(BaseMCMCSampler):
         q_loglr = torch.empty(self._Wh, **f64)
         perms = None
         if nt > 1:
-            # replicated host RNG for the swap pairings: identical on every rank
-            rs = numpy.random.RandomState((self._seed + 7919 * (self._iterations + self._iter0)) % (2 ** 32))
-            perms = numpy.stack([[[rs.permutation(nw), rs.permutation(nw)] for _ in range(nt - 1)]
-                                 for _ in range(niterations)]).astype(numpy.int32)
+            # replicated host RNG for the swap pairings, keyed by (seed, global iteration):
+            # identical on every rank and independent of how a run is split into run() calls
+            g0 = self._iterations + self._iter0
+            perms = numpy.empty((niterations, nt - 1, 2, nw), dtype=numpy.int32)
+            for it in range(niterations):
+                rs = numpy.random.RandomState((self._seed * 1000003 + g0 + it) % (2 ** 32))
+                for lv in range(nt - 1):
+                    perms[it, lv, 0] = rs.permutation(nw)
+                    perms[it, lv, 1] = rs.permutation(nw)
             perms = torch.tensor(perms, device=self._dev)
         st = torch.cuda.current_stream(self._dev).cuda_stream
         for it in range(niterations):
