@@ -45,6 +45,10 @@
 #define G_PC_SI   3.085677581491367278913937957796471611e16
 
 #define WARP 32
+#ifndef RECUR_UNROLL
+#define RECUR_UNROLL 4        // bins per trip of the recurrence hot loop
+#endif
+static constexpr int kRecurUnroll = RECUR_UNROLL;
 #ifndef CTA_THREADS
 #define CTA_THREADS 128
 #endif
@@ -693,7 +697,7 @@ __device__ __forceinline__ void recur_block(
         S.ensure(k);
         const int ke = min(kn, S.tile_end(k));
         const double2* sp = S.row(k);
-#pragma unroll 4
+#pragma unroll kRecurUnroll
         for (; k < ke; ++k, sp += ND) {
             const bool on = !MASKED || ((k >= lo) && (k < hi));
 #pragma unroll

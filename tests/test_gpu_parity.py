@@ -241,6 +241,24 @@ def test_detector_counts_unit_psd_fupper(dets):
     assert abs(model.lognl - orc.lognl()) <= 1e-9 * abs(orc.lognl())
 
 
+@pytest.mark.parametrize("seglen", [4, 16, 64])
+def test_segment_lengths_bns(seglen):
+    """C5 regimes: short segments put the whole band (4 s) or its low-frequency part (16, 64 s)
+    into directly-evaluated / short quartic blocks; every schedule regime must hold the
+    tolerance."""
+    import gwin_oracle as O
+    cfg = util.c3(seglen=seglen)
+    model = cfg.cuda_model()
+    rng = np.random.default_rng(100 + seglen)
+    P = util.draw_bns(rng, 12, cfg)
+    P[0] = util.inj_row(cfg)
+    lr0, hd0, hh0 = O.batch_loglr(cfg.oracle(), P)
+    for kernel in (1, 2):
+        model.plan.configure(kernel=kernel)
+        lr, hd, hh = model.plan.loglr_host(P)
+        _check(lr, hd, hh, lr0, hd0, hh0, "T=%d k%d" % (seglen, kernel))
+
+
 def test_four_detectors_and_large_batch():
     """n_det = 4 (the narrower TMA tile variant of the kernels) and a 100k-walker batch that
     grows the workspace: both kernels against the oracle on a sample and against each other on
