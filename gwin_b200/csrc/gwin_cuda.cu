@@ -1014,7 +1014,7 @@ static void build_schedule(gwin_plan* p) {
     const PlanDev& d = p->d;
     const int band0 = std::max(d.kmin, d.istart);
     p->blk_start.clear(); p->blk_mat.clear(); p->mats.clear();
-    std::vector<int> mat_of((MAX_BLOCK + MIN_BLOCK + 8) * 2, -1);
+    std::vector<int> mat_of((MAX_BLOCK + MIN_BLOCK + 8) * 2, -1);      // (block length, degree) -> mats index
     auto mat_index = [&](int B, int deg) {
         if (deg == 0) { B = 0; }
         int& slot = mat_of[(size_t)B * 2 + (deg == 3 ? 1 : 0)];
@@ -1033,9 +1033,27 @@ static void build_schedule(gwin_plan* p) {
         const double B3 = std::min<double>(pow(p->phase_tol * 24.0 / (0.015625 * d4), 0.25) + 1.0, MAX_BLOCK);
         int deg = 4, Bi = (int)B4;
         if (B3 >= MIN_BLOCK && bin3 + setup_cost / B3 < bin4 + setup_cost / B4) { deg = 3; Bi = (int)B3; }
-        if (Bi >= MIN_BLOCK) Bi &= ~3; else { Bi = 4; deg = 0; }    // too curved: direct evaluation
+        if (Bi >= MIN_BLOCK) {
+            Bi &= ~3;
+        } else {
+            // Too curved for an 8-bin block.  A 5-bin quartic has every bin as a node and is exact;
+            // 6 or 7 bins are taken when the one or two interpolated bins still meet the bound
+            // (exact node polynomial instead of the Chebyshev estimate).
+            deg = 4;
+            for (Bi = 7; Bi > 5; --Bi) {
+                const int e = Bi - 1, q = (e + 4) / 8;
+                const int x[5] = {0, q, e / 2, e - q, e};
+                double worst = 0.0;
+                for (int j = 0; j <= e; ++j) {
+                    double prod = 1.0;
+                    for (int i = 0; i < 5; ++i) prod *= (double)(j - x[i]);
+                    worst = std::max(worst, std::fabs(prod));
+                }
+                if (d5 / 120.0 * worst <= p->phase_tol) break;
+            }
+        }
         if (k + Bi > d.kmax) Bi = d.kmax - k;
-        if (Bi < MIN_BLOCK) deg = 0;
+        if (Bi < 5) deg = 0;                                        // band remainder: direct evaluation
         p->blk_start.push_back(k);
         p->blk_mat.push_back(mat_index(Bi, deg));
         k += Bi;

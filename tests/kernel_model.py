@@ -130,10 +130,19 @@ class PlanModel(object):
             if Bi >= MIN_BLOCK:
                 Bi &= ~3
             else:
-                Bi, deg = 4, 0
+                deg = 4
+                for Bi in (7, 6, 5):
+                    if Bi == 5:
+                        break
+                    e = Bi - 1
+                    q = (e + 4) // 8
+                    x = [0, q, e // 2, e - q, e]
+                    worst = max(abs(np.prod([j - xi for xi in x])) for j in range(e + 1))
+                    if d5 / 120.0 * worst <= self.phase_tol:
+                        break
             if k + Bi > self.kmax:
                 Bi = self.kmax - k
-            if Bi < MIN_BLOCK:
+            if Bi < 5:
                 deg = 0
             out.append(k)
             self.blk_deg.append(deg)
