@@ -27,7 +27,6 @@ Two precision modes:
 """
 from __future__ import annotations
 
-import calendar
 import math
 from collections import OrderedDict
 
