@@ -9,16 +9,18 @@
 //   loglr combine                              gaussian_noise.py:341-350
 //   marginalised-phase combine                 marginalized_gaussian_noise.py:456-511
 // No intermediate waveform array is ever materialised: one thread owns one
-// walker, a warp shares (broadcast) loads of the pre-weighted data table, and the
+// walker, a warp shares (broadcast) reads of the pre-weighted data table, and the
 // frequency axis is cut into chunks so that the grid fills all 148 SMs.
 //
-// Three kernels per batch:  walker_setup -> loglr_{direct|recur} -> combine.
-// (+ a CUB radix sort of walkers by their last frequency bin so that the lanes
-// of a warp finish together.)
+// Kernels per batch:  sort_key -> [CUB radix sort of walkers by their last
+// frequency bin, so that the lanes of a warp finish together] -> walker_setup ->
+// loglr_recur (production) | loglr_direct (independent second implementation) ->
+// combine.
 //
-// Work is FP64-pipe bound: there is no dense contraction here, so no
-// tensor cores; the tables are L2-resident and read with warp-uniform 128-bit
-// loads.
+// Work is FP64-pipe bound -- more precisely bound by the register-file bandwidth that
+// feeds the FP64 pipe: there is no dense contraction here, so no
+// tensor cores; the tables are L2-resident, staged into shared memory per warp by
+// TMA bulk copies and read with warp-uniform 128-bit loads.
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
 
@@ -1294,8 +1296,7 @@ static int ensure_workspace(gwin_plan* p, int64_t W, int n_chunks) {
 
 template <int ND>
 static void launch_main(gwin_plan* p, bool recur, int W, int wpad, int n_chunks, int per_chunk,
-                        double* hh_rows, cudaStream_t st) {
-    (void)hh_rows;
+                        cudaStream_t st) {
     dim3 grid((W + CTA_THREADS - 1) / CTA_THREADS, n_chunks);
     // diagnostic: GWIN_SMEM_PAD=<bytes> of unused dynamic shared memory lowers the occupancy
     static const int smem_pad = getenv("GWIN_SMEM_PAD") ? atoi(getenv("GWIN_SMEM_PAD")) : 0;
@@ -1377,10 +1378,10 @@ extern "C" int gwin_loglr_batch_strided(gwin_plan* p, int mode, int64_t W64,
         CK(cudaEventRecord(p->ev0, st));
     }
     switch (nd) {
-        case 1: launch_main<1>(p, recur, W, wpad, n_chunks, per_chunk, hh_rows, st); break;
-        case 2: launch_main<2>(p, recur, W, wpad, n_chunks, per_chunk, hh_rows, st); break;
-        case 3: launch_main<3>(p, recur, W, wpad, n_chunks, per_chunk, hh_rows, st); break;
-        default: launch_main<4>(p, recur, W, wpad, n_chunks, per_chunk, hh_rows, st); break;
+        case 1: launch_main<1>(p, recur, W, wpad, n_chunks, per_chunk, st); break;
+        case 2: launch_main<2>(p, recur, W, wpad, n_chunks, per_chunk, st); break;
+        case 3: launch_main<3>(p, recur, W, wpad, n_chunks, per_chunk, st); break;
+        default: launch_main<4>(p, recur, W, wpad, n_chunks, per_chunk, st); break;
     }
     if (p->timing) { CK(cudaEventRecord(p->ev1, st)); p->ev_pending = true; }
     combine_kernel<<<(W + 31) / 32, dim3(32, COMB_SEG), 0, st>>>(nd, W, wpad, n_chunks, mode, perm, p->d_wc, p->d_ks,
