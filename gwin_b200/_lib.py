@@ -38,6 +38,7 @@ SYMBOLS = (
     "gwin_plan_last_launches",
     "gwin_plan_kernel_timing",
     "gwin_ens_propose", "gwin_ens_prior", "gwin_ens_accept", "gwin_ens_swap",
+    "gwin_ens_swap_all",
     "gwin_fp64_peak", "gwin_fp64_probe", "gwin_last_error", "gwin_version",
 )
 
@@ -155,6 +156,8 @@ def load():
                                         vp, vp, vp, vp, vp]
         lib.gwin_ens_swap.restype = ci
         lib.gwin_ens_swap.argtypes = [u64, u32, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp]
+        lib.gwin_ens_swap_all.restype = ci
+        lib.gwin_ens_swap_all.argtypes = [u64, u32, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp]
         lib.gwin_fp64_probe.restype = C.c_int
         lib.gwin_fp64_probe.argtypes = [C.c_int, C.c_int, dp]
         lib.gwin_last_error.restype = C.c_char_p

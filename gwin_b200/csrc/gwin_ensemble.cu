@@ -31,9 +31,6 @@ extern int gwin_fail(int code, const char* fmt, ...);
 // ---------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011)
 // ---------------------------------------------------------------------------
-struct Philox {
-    uint32_t c[4];
-};
 __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
     const uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
@@ -236,6 +233,44 @@ __global__ void ens_swap_kernel(uint64_t seed, uint32_t iter, int level, int nwa
     }
 }
 
+// All levels ntemps-1 .. 1 in ONE launch: a single CTA walks the levels in emcee's order
+// (hottest pair first) and synchronises between them, because level l-1 exchanges with chain
+// l-1 as level l left it.  perms: [ntemps-1][2][nwalkers]; entry (ntemps-1-level) holds the two
+// permutations whose elements are paired.
+__global__ void __launch_bounds__(1024)
+ens_swap_all_kernel(uint64_t seed, uint32_t iter, int ntemps, int nwalkers, int ndim,
+                    const double* __restrict__ betas, const int* __restrict__ perms,
+                    double* __restrict__ p, double* __restrict__ logl, double* __restrict__ lnprob,
+                    int* __restrict__ nswap_accepted) {
+    for (int level = ntemps - 1; level >= 1; --level) {
+        const int* iperm = perms + (size_t)(ntemps - 1 - level) * 2 * nwalkers;
+        const int* i1perm = iperm + nwalkers;
+        const double dbeta = betas[level - 1] - betas[level];
+        for (int j = threadIdx.x; j < nwalkers; j += blockDim.x) {
+            uint32_t r[4];
+            philox4x32(seed, iter, (uint32_t)(STAGE_SWAP * 4), (uint32_t)(level * nwalkers + j), 0u, r);
+            double u0, u1;
+            uniform2(r, u0, u1);
+            const size_t a = (size_t)level * nwalkers + iperm[j], b = (size_t)(level - 1) * nwalkers + i1perm[j];
+            const double la = logl[a], lb = logl[b];
+            if (dbeta * (la - lb) > log(u0)) {
+                for (int d = 0; d < ndim; ++d) {
+                    const double t = p[a * ndim + d];
+                    p[a * ndim + d] = p[b * ndim + d];
+                    p[b * ndim + d] = t;
+                }
+                const double pa = lnprob[a], pb = lnprob[b];
+                logl[a] = lb; logl[b] = la;
+                lnprob[a] = pb - dbeta * lb;
+                lnprob[b] = pa + dbeta * la;
+                atomicAdd(nswap_accepted + level, 1);
+                atomicAdd(nswap_accepted + level - 1, 1);
+            }
+        }
+        __syncthreads();            // level l-1 reads what level l wrote to chain l-1
+    }
+}
+
 // ---------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------
@@ -299,6 +334,19 @@ extern "C" int gwin_ens_swap(uint64_t seed, uint32_t iter, int level, int nwalke
     ens_swap_kernel<<<(nwalkers + 127) / 128, 128, 0, (cudaStream_t)stream>>>(seed, iter, level, nwalkers, ndim, betas,
                                                                               iperm, i1perm, p, logl, lnprob,
                                                                               nswap_accepted);
+    CKE(cudaGetLastError());
+    return GWIN_OK;
+}
+
+extern "C" int gwin_ens_swap_all(uint64_t seed, uint32_t iter, int ntemps, int nwalkers, int ndim,
+                                 const double* betas, const int* perms,
+                                 double* p, double* logl, double* lnprob, int* nswap_accepted, void* stream) {
+    if (ntemps < 2) return GWIN_OK;
+    if (nwalkers < 1 || ndim < 1 || !betas || !perms || !p || !logl || !lnprob || !nswap_accepted)
+        return gwin_fail(GWIN_EINVAL, "bad swap arguments");
+    const int threads = nwalkers >= 1024 ? 1024 : ((nwalkers + 31) / 32) * 32;
+    ens_swap_all_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(seed, iter, ntemps, nwalkers, ndim, betas, perms,
+                                                                 p, logl, lnprob, nswap_accepted);
     CKE(cudaGetLastError());
     return GWIN_OK;
 }

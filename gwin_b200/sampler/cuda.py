@@ -285,12 +285,11 @@ class _DeviceEnsemble(BaseMCMCSampler):
                     self._q.data_ptr(), self._logfac.data_ptr(), q_loglr.data_ptr(),
                     self._q_logp.data_ptr(), self._p.data_ptr(), self._logl.data_ptr(),
                     self._lnprob.data_ptr(), self._naccept.data_ptr(), st))
-            for lvl in range(nt - 1, 0, -1):
-                pr = perms[it, nt - 1 - lvl]
-                _lib.check(lib.gwin_ens_swap(
-                    self._seed, gi, lvl, nw, nd, self._betas.data_ptr(), pr[0].data_ptr(),
-                    pr[1].data_ptr(), self._p.data_ptr(), self._logl.data_ptr(),
-                    self._lnprob.data_ptr(), self._nswap_acc.data_ptr(), st))
+            if nt > 1:
+                _lib.check(lib.gwin_ens_swap_all(
+                    self._seed, gi, nt, nw, nd, self._betas.data_ptr(),
+                    perms.data_ptr() + it * (nt - 1) * 2 * nw * 4, self._p.data_ptr(),
+                    self._logl.data_ptr(), self._lnprob.data_ptr(), self._nswap_acc.data_ptr(), st))
             if nt > 1:
                 self._nswap += nw
             chain[:, :, it, :].copy_(self._p)

@@ -197,6 +197,12 @@ int gwin_ens_swap(uint64_t seed, uint32_t iter, int level, int nwalkers, int ndi
                   const double* betas, const int* iperm, const int* i1perm,
                   double* p, double* logl, double* lnprob, int* nswap_accepted, void* stream);
 
+/* All swap levels ntemps-1 .. 1 of one iteration in a single launch; perms is
+ * [ntemps-1][2][nwalkers] (entry ntemps-1-level holds iperm, i1perm of that level). */
+int gwin_ens_swap_all(uint64_t seed, uint32_t iter, int ntemps, int nwalkers, int ndim,
+                      const double* betas, const int* perms,
+                      double* p, double* logl, double* lnprob, int* nswap_accepted, void* stream);
+
 /* FP64 issue-rate micro-benchmark on the plan's device: runs a dependent-chain-free
  * DFMA loop and returns achieved FP64 FMA lane-ops per second. */
 int gwin_fp64_peak(int device, double* dfma_per_sec);
