@@ -835,7 +835,7 @@ __device__ __forceinline__ double log_i0(double x) {
     return x - 0.5 * log(G_TWOPI * x) + log(ser);
 }
 
-#define COMB_SEG 8      // chunk segments summed in parallel per walker (fixed order: deterministic)
+#define COMB_SEG 16     // chunk segments summed in parallel per walker (fixed order: deterministic)
 __global__ void __launch_bounds__(32 * COMB_SEG)
 combine_kernel(int n_det, int W, int wpad, int n_chunks, int mode,
                const int* __restrict__ perm, const double* __restrict__ wc,
@@ -1341,7 +1341,8 @@ extern "C" int gwin_loglr_batch_strided(gwin_plan* p, int mode, int64_t W64,
     const int nbins = std::max(d.kmax - band0, 1);
     const int groups = (W + CTA_THREADS - 1) / CTA_THREADS;
     static const int chunk_mult = getenv("GWIN_CHUNK_MULT") ? atoi(getenv("GWIN_CHUNK_MULT")) : 192;
-    const int want_chunks = std::max(1, (148 * chunk_mult + groups - 1) / groups);
+    // at most 512 chunks: every chunk costs one partial per walker and detector in the combine pass
+    const int want_chunks = std::min(512, std::max(1, (148 * chunk_mult + groups - 1) / groups));
     int n_chunks, per_chunk;
     if (recur) {
         const int min_blocks = 2;
