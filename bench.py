@@ -333,7 +333,7 @@ def run_cuda(args):
         try:        # dram bytes per launch of this kernel from the committed ncu --set full capture
             tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
             traffic = float(tj["dram_bytes_read"] + tj["dram_bytes_write"])
-            traffic_src = tj["source"]
+            traffic_src = tj["source"] + " -- " + tj.get("note", "")
         except (OSError, ValueError, KeyError):
             pass
         # every table byte has to come from HBM once per launch (L2 was flushed); the

@@ -510,7 +510,7 @@ loglr_direct_kernel(PlanDev P, int W, int wpad, int chunk_bins, int n_chunks,
             }
         }
     }
-    if (live) {
+    if (live && has) {          // chunks a walker does not reach are neither written nor read back
 #pragma unroll
         for (int d = 0; d < ND; ++d)
             partial[((size_t)chunk * ND + d) * wpad + t] = acc[d];
@@ -814,7 +814,7 @@ loglr_recur_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_blk,
         }
         if (opened) S.close();
     }
-    if (live) {
+    if (live && has) {          // chunks a walker does not reach are neither written nor read back
 #pragma unroll
         for (int d = 0; d < ND; ++d)
             partial[((size_t)chunk * ND + d) * wpad + t] = acc[d];
@@ -838,8 +838,9 @@ __device__ __forceinline__ double log_i0(double x) {
 #define COMB_SEG 16     // chunk segments summed in parallel per walker (fixed order: deterministic)
 __global__ void __launch_bounds__(32 * COMB_SEG)
 combine_kernel(int n_det, int W, int wpad, int n_chunks, int mode,
+               int per_chunk, int n_blk, const int* __restrict__ blk_start, int band0, int kmax,
                const int* __restrict__ perm, const double* __restrict__ wc,
-               const int* __restrict__ ks_arr,
+               const int* __restrict__ ks_arr, const int* __restrict__ ke_arr,
                const double2* __restrict__ partial,
                const double* __restrict__ hh_sorted,
                double* __restrict__ loglr, double* __restrict__ hd_out,
@@ -849,10 +850,17 @@ combine_kernel(int n_det, int W, int wpad, int n_chunks, int mode,
     const int t = blockIdx.x * 32 + lx;
     const bool live = t < W;
     // stage 1: thread (lx, seg) sums chunks seg, seg + COMB_SEG, ... of walker t (coalesced in t)
+    // (only the chunks that overlap the walker's band [ks, ke) were written by the main kernel;
+    //  blk_start != NULL: chunk c = blocks [c per_chunk, (c+1) per_chunk), else per_chunk bins)
+    const int ks = live ? ks_arr[t] : 0, ke = live ? ke_arr[t] : 0;
     for (int d = 0; d < n_det; ++d) {
         double re = 0.0, im = 0.0;
         if (live)
             for (int c = seg; c < n_chunks; c += COMB_SEG) {
+                int k0, k1;
+                if (blk_start) { k0 = blk_start[c * per_chunk]; k1 = blk_start[min((c + 1) * per_chunk, n_blk)]; }
+                else { k0 = band0 + c * per_chunk; k1 = min(k0 + per_chunk, kmax); }
+                if (max(k0, ks) >= min(k1, ke)) continue;
                 const double2 p = partial[((size_t)c * n_det + d) * wpad + t];
                 re += p.x; im += p.y;
             }
@@ -1385,7 +1393,9 @@ extern "C" int gwin_loglr_batch_strided(gwin_plan* p, int mode, int64_t W64,
         default: launch_main<4>(p, recur, W, wpad, n_chunks, per_chunk, st); break;
     }
     if (p->timing) { CK(cudaEventRecord(p->ev1, st)); p->ev_pending = true; }
-    combine_kernel<<<(W + 31) / 32, dim3(32, COMB_SEG), 0, st>>>(nd, W, wpad, n_chunks, mode, perm, p->d_wc, p->d_ks,
+    combine_kernel<<<(W + 31) / 32, dim3(32, COMB_SEG), 0, st>>>(nd, W, wpad, n_chunks, mode, per_chunk, p->n_blk,
+                                                                 recur ? p->d_blk_start : nullptr, band0, d.kmax,
+                                                                 perm, p->d_wc, p->d_ks, p->d_ke,
                                                                  p->d_partial, hh_rows, loglr, hd, hh);
     p->last_launches += 3;
     CK(cudaGetLastError());
