@@ -23,8 +23,10 @@ def _call_global_model(*args, **kwds):
 
 
 class CallModel(object):
-    """Wraps a model so that it can be called like a function of the
-    parameter values, in ``model.sampling_params`` order."""
+    """Callable view of a model for samplers: ``call_model(values)`` updates the model with
+    ``values`` (ordered like ``model.sampling_params``) and returns ``callstat`` -- together with
+    the tuple of the model's default stats when ``return_all_stats`` is set.  Every other
+    attribute is looked up on the wrapped model.  ``batch(points)`` is the vectorised form."""
 
     def __init__(self, model, callstat, return_all_stats=True):
         self.model = model
@@ -32,28 +34,21 @@ class CallModel(object):
         self.return_all_stats = return_all_stats
 
     def __getattr__(self, attr):
-        # only reached for attributes CallModel does not define itself
-        if attr == 'model':
+        if attr == 'model':                 # not yet set (e.g. during unpickling)
             raise AttributeError(attr)
         return getattr(self.model, attr)
 
     def __call__(self, param_values, callstat=None, return_all_stats=None):
-        if callstat is None:
-            callstat = self.callstat
-        if return_all_stats is None:
-            return_all_stats = self.return_all_stats
-        params = dict(zip(self.model.sampling_params, param_values))
-        self.model.update(**params)
-        val = getattr(self.model, callstat)
-        if return_all_stats:
-            return val, self.model.get_current_stats()
-        return val
+        stat = self.callstat if callstat is None else callstat
+        with_stats = self.return_all_stats if return_all_stats is None else return_all_stats
+        model = self.model
+        model.update(**dict(zip(model.sampling_params, param_values)))
+        value = getattr(model, stat)
+        return (value, model.get_current_stats()) if with_stats else value
 
     def batch(self, points, callstat=None):
         """All points at once: returns a ``BatchResult``."""
-        if callstat is None:
-            callstat = self.callstat
-        return self.model.evaluate_batch(points, callstat=callstat)
+        return self.model.evaluate_batch(points, callstat=callstat or self.callstat)
 
 
 models = {_cls.name: _cls for _cls in (
