@@ -335,6 +335,10 @@ class BaseModel(object, metaclass=ABCMeta):
         logl, extra = self._batch_loglikelihood(params, W, skip)
         extra = OrderedDict(extra)
         extra['loglikelihood'] = logl
+        if skip is not None and skip.any():
+            # the scalar path never evaluates the likelihood of a prior-excluded point
+            for k in extra:
+                extra[k] = numpy.where(skip, numpy.nan, extra[k])
         if callstat == 'loglikelihood':
             return logl, extra
         return numpy.where(skip, -numpy.inf, logp + numpy.where(skip, 0., logl)), extra

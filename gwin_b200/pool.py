@@ -26,7 +26,14 @@ class BatchPool(object):
 
     @staticmethod
     def _resolve(fn):
-        """The object with a ``batch(points)`` method behind ``fn`` (or None)."""
+        """The object with a ``batch(points)`` method behind ``fn`` (or None).
+
+        Looks through the two indirections a sampler library puts in front of the model:
+        emcee's ``_function_wrapper`` (attributes ``f``, ``args``, ``kwargs``; only when no extra
+        arguments are bound) and gwin's module-level ``_call_global_model`` used with fork pools
+        (reference ``models/__init__.py:28-34``)."""
+        if hasattr(fn, "f") and not getattr(fn, "args", None) and not getattr(fn, "kwargs", None):
+            fn = fn.f
         if fn is _models._call_global_model:
             fn = _models._global_instance
         return fn if hasattr(fn, "batch") else None

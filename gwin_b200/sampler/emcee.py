@@ -30,6 +30,35 @@ def _as_batch(model_call, pool):
     return run
 
 
+class _callprior(object):
+    """Calls the model's prior only (reference ``sampler/emcee.py:230-240``); handed to a
+    parallel-tempered sampler that wants prior and likelihood separately."""
+
+    def __init__(self, model_call):
+        self.callable = model_call
+        self.return_all_stats = False
+
+    def __call__(self, args):
+        return self.callable(args, callstat='logprior', return_all_stats=False)
+
+    def batch(self, points, callstat=None):
+        return self.callable.batch(points, callstat='logprior')
+
+
+class _callloglikelihood(object):
+    """Calls the model's log likelihood only (reference ``sampler/emcee.py:243-250``)."""
+
+    def __init__(self, model_call):
+        self.callable = model_call
+        self.return_all_stats = False
+
+    def __call__(self, args):
+        return self.callable(args, callstat='loglikelihood', return_all_stats=False)
+
+    def batch(self, points, callstat=None):
+        return self.callable.batch(points, callstat='loglikelihood')
+
+
 class EmceeEnsembleSampler(BaseMCMCSampler):
     name = "emcee"
 

@@ -135,6 +135,37 @@ def test_pool_falls_back_to_plain_map_and_global_model():
         models._global_instance = None
 
 
+def test_pool_sees_through_sampler_library_wrappers():
+    """emcee wraps the log-probability callable in ``_function_wrapper(f, args, kwargs)`` before
+    mapping it; a PT sampler maps separate prior / likelihood callables
+    (reference sampler/emcee.py:230-250).  Both must still reach the batched path."""
+    from gwin_b200.sampler.emcee import _callloglikelihood, _callprior
+
+    class FunctionWrapper(object):          # shape of emcee.ensemble._function_wrapper
+        def __init__(self, f, args=(), kwargs=None):
+            self.f, self.args, self.kwargs = f, args, kwargs or {}
+
+        def __call__(self, x):
+            return self.f(x, *self.args, **self.kwargs)
+
+    prior = D.JointDistribution(['x'], D.Uniform(x=(-5, 5)))
+    m = models.TestNormal(['x'], prior=prior)
+    call = models.CallModel(m, 'logposterior')
+    pts = np.linspace(-6, 6, 9)[:, None]
+    pool = BatchPool()
+    got = pool.map(FunctionWrapper(call), pts)
+    assert pool.ncalls == 1                                   # one batched evaluation
+    assert got == [call(p) for p in pts]
+    assert got[0][0] == -np.inf
+    bound = pool.map(FunctionWrapper(call, args=('logprior',)), pts)      # extra args: plain map
+    assert pool.ncalls == 1 and len(bound) == 9
+    ll = pool.map(_callloglikelihood(call), pts)
+    lp = pool.map(_callprior(call), pts)
+    assert pool.ncalls == 3
+    assert np.allclose(ll, [m._dist.logpdf(p) for p in pts])
+    assert lp == [call(p, callstat='logprior', return_all_stats=False) for p in pts]
+
+
 def test_ensemble_sampler_recovers_normal():
     np.random.seed(11)
     prior = D.JointDistribution(['x', 'y'], D.Uniform(x=(-20, 20), y=(-20, 20)))
