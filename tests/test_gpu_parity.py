@@ -259,6 +259,26 @@ def test_segment_lengths_bns(seglen):
         _check(lr, hd, hh, lr0, hd0, hh0, "T=%d k%d" % (seglen, kernel))
 
 
+def test_large_segment_two_million_bins():
+    """Size limit: 512 s @ 8192 Hz -> 2 097 153 bins per detector (bin index needs 22 bits: the
+    exact k*tau_hi reduction, the 23-bit sort key and the tile stream all run at their limits)."""
+    import gwin_oracle as O
+    inj = dict(util.BNS_INJ)
+    inj["tc"] = 500.0
+    cfg = util.Config("big", 512, 8192., 20., ["H1", "L1"], inj, seed=11)
+    assert cfg.n_f == 2097153
+    model = cfg.cuda_model()
+    rng = np.random.default_rng(12)
+    P = util.draw_bns(rng, 3, cfg)
+    P[0] = util.inj_row(cfg)
+    P[1, :2] = 1.0, 1.0            # waveform reaches 2199 Hz = bin 1.1 million
+    lr0, hd0, hh0 = O.batch_loglr(cfg.oracle(), P)
+    for kernel in (1, 2):
+        model.plan.configure(kernel=kernel)
+        lr, hd, hh = model.plan.loglr_host(P)
+        _check(lr, hd, hh, lr0, hd0, hh0, "2M bins k%d" % kernel)
+
+
 def test_four_detectors_and_large_batch():
     """n_det = 4 (the narrower TMA tile variant of the kernels) and a 100k-walker batch that
     grows the workspace: both kernels against the oracle on a sample and against each other on
