@@ -159,15 +159,41 @@ __device__ __forceinline__ double round_magic(double x) {
 }
 __device__ __forceinline__ double frac1(double x) { return x - round_magic(x); }
 
-// e^{-2 pi i y} for y in turns (any magnitude < 2^51): returns (cos, -sin)
+// sin / cos of 2 pi y for y in turns, |y| < 2^51: exact reduction to an octant
+// (y - rint(y), then quarter turns), fdlibm's kernel polynomials on |x| <= pi/4 (error < 1 ulp),
+// quadrant fix-up by selects.  ~24 FP64 instructions, no branches, no slow path -- the library
+// sincospi() costs ~55 and the recurrence kernel calls this 5 times per block.
+__device__ __forceinline__ void sincos_turns(double y, double& sn, double& cs) {
+    const double r = y - round_magic(y);                  // [-1/2, 1/2]
+    const double q = round_magic(4.0 * r);                // -2 .. 2 quarter turns
+    const double x = fma(-0.25, q, r) * G_TWOPI;          // [-pi/4, pi/4]
+    const double t = x * x;
+    double ps = fma(t, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(t, ps, 2.75573137070700676789e-06);
+    ps = fma(t, ps, -1.98412698298579493134e-04);
+    ps = fma(t, ps, 8.33333333332248946124e-03);
+    ps = fma(t, ps, -1.66666666666666324348e-01);
+    const double s0 = fma(x * t, ps, x);
+    double pc = fma(t, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(t, pc, -2.75573143513906633035e-07);
+    pc = fma(t, pc, 2.48015872894767294178e-05);
+    pc = fma(t, pc, -1.38888888888741095749e-03);
+    pc = fma(t, pc, 4.16666666666666019037e-02);
+    const double c0 = fma(t * t, pc, fma(-0.5, t, 1.0));
+    const int qi = (int)q & 3;
+    const double a = (qi & 1) ? s0 : c0, b = (qi & 1) ? c0 : s0;
+    cs = (qi == 1 || qi == 2) ? -a : a;
+    sn = (qi >= 2) ? -b : b;
+}
+// e^{-2 pi i y} for y in turns: returns (cos, -sin)
 __device__ __forceinline__ double2 phasor_neg(double y) {
     double s, c;
-    sincospi(2.0 * frac1(y), &s, &c);
+    sincos_turns(y, s, c);
     return make_double2(c, -s);
 }
 __device__ __forceinline__ double2 phasor_pos(double y) {
     double s, c;
-    sincospi(2.0 * frac1(y), &s, &c);
+    sincos_turns(y, s, c);
     return make_double2(c, s);
 }
 // e^{+2 pi i y}: Taylor series when the angle is small (the higher forward differences of
@@ -579,7 +605,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 template <int ND>
 struct TileStream {
-    static constexpr int TILE = ND <= 3 ? 64 : 32;     // bins per tile
+    static constexpr int TILE = ND <= 3 ? 128 : 64;    // bins per tile
     double2* buf;          // this warp's [2][TILE * ND] staging buffers
     uint32_t bar;          // shared-memory address of this warp's 2 mbarriers
     const double2* T;      // global table
@@ -754,11 +780,13 @@ loglr_recur_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_blk,
 #pragma unroll
     for (int d = 0; d < ND; ++d) acc[d] = make_double2(0.0, 0.0);
 
+    // dynamic shared memory: [per-warp tile buffers][per-thread coefficient columns][mbarriers]
     constexpr int TILE = TileStream<ND>::TILE;
     constexpr int NWARP = CTA_THREADS / WARP;
-    __shared__ double s_coef[RC_ROWS(ND) * CTA_THREADS];
-    __shared__ __align__(128) double2 s_tile[NWARP][2 * TILE * ND];
-    __shared__ __align__(8) uint64_t s_bar[NWARP][2];
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    double2 (*s_tile)[2 * TILE * ND] = reinterpret_cast<double2 (*)[2 * TILE * ND]>(s_dyn);
+    double* s_coef = reinterpret_cast<double*>(s_dyn + sizeof(double2) * NWARP * 2 * TILE * ND);
+    uint64_t (*s_bar)[2] = reinterpret_cast<uint64_t (*)[2]>(s_coef + RC_ROWS(ND) * CTA_THREADS);
     if (wlo < whi) {
         const int tt = live ? t : 0;
         double* sc = s_coef + threadIdx.x;
@@ -1308,10 +1336,16 @@ static void launch_main(gwin_plan* p, bool recur, int W, int wpad, int n_chunks,
     dim3 grid((W + CTA_THREADS - 1) / CTA_THREADS, n_chunks);
     // diagnostic: GWIN_SMEM_PAD=<bytes> of unused dynamic shared memory lowers the occupancy
     static const int smem_pad = getenv("GWIN_SMEM_PAD") ? atoi(getenv("GWIN_SMEM_PAD")) : 0;
-    if (recur && smem_pad > 0)
-        cudaFuncSetAttribute(loglr_recur_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pad);
+    constexpr int NWARP = CTA_THREADS / WARP;
+    const int smem = (int)(sizeof(double2) * NWARP * 2 * TileStream<ND>::TILE * ND
+                           + sizeof(double) * RC_ROWS(ND) * CTA_THREADS + sizeof(uint64_t) * NWARP * 2) + smem_pad;
+    static bool attr_set = false;           // one instantiation per ND: set once
+    if (recur && !attr_set) {
+        cudaFuncSetAttribute(loglr_recur_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
     if (recur)
-        loglr_recur_kernel<ND><<<grid, CTA_THREADS, smem_pad, st>>>(p->d, W, wpad, per_chunk, p->n_blk, p->d_blk_start,
+        loglr_recur_kernel<ND><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, per_chunk, p->n_blk, p->d_blk_start,
                                                             p->d_blk_mat, p->d_mats,
                                                             p->d_wc, p->d_ks, p->d_ke, p->d_partial);
     else
