@@ -38,14 +38,14 @@ W_ALG_SLOTS = 32 + 12 * len(DETS)      # FP64 issue slots per (walker, bin): SUR
 TABLE_BYTES_PER_BIN = 16 * len(DETS) + 24
 MTSUN = 4.925491025543575903411922162094833998e-6
 PARAMS = ("mass1", "mass2", "spin1z", "spin2z", "distance", "inclination",
-          "coa_phase", "ra", "dec", "polarization", "tc")
+          "coa_phase", "ra", "dec", "polarization", "tc", "lambda1", "lambda2")
 INJ = dict(mass1=1.4, mass2=1.4, spin1z=0.0, spin2z=0.0, distance=40.0,
            inclination=0.5, coa_phase=1.1, ra=1.3, dec=-0.4, polarization=0.7,
-           tc=SEGLEN - 6.0)
+           tc=SEGLEN - 6.0, lambda1=0.0, lambda2=0.0)
 
 
 def draw_walkers(rng, W):
-    P = np.empty((W, 11))
+    P = np.zeros((W, 13))
     P[:, 0] = rng.uniform(1.2, 1.6, W)
     P[:, 1] = rng.uniform(1.2, 1.6, W)
     P[:, 2] = 0.0
@@ -338,7 +338,7 @@ def run_cuda(args):
             pass
         # every table byte has to come from HBM once per launch (L2 was flushed); the
         # 128 walker tiles that re-read it are served by the 126 MB L2
-        alg_bytes = float(plan.kmax - plan.kmin) * TABLE_BYTES_PER_BIN + W * (11 + 1 + 3 * nd) * 8.0
+        alg_bytes = float(plan.kmax - plan.kmin) * TABLE_BYTES_PER_BIN + W * (13 + 1 + 3 * nd) * 8.0
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -348,7 +348,7 @@ def run_cuda(args):
                            kernel="loglr_recur_kernel: block-anchored cubic/quartic phasor recurrence (Horner), TMA-staged table tiles",
                            mean_bins_per_eval=float(bins.mean())),
             "clocks": clk,
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": world * W * 11 * 8,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": world * W * 13 * 8,
                     "d2h_bytes_per_step": world * W * (1 + 3 * nd) * 8,
                     "path": "CallModel.batch(points) -> gwin_loglr_batch_host"},
             "gpu_launches": launches,

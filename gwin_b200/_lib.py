@@ -23,7 +23,7 @@ HEADER = os.path.join(ROOT, "include", "gwin_b200.h")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
               "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
 
-GWIN_NPARAM = 11
+GWIN_NPARAM = 13
 GWIN_MAX_DET = 4
 MODE_GAUSSIAN = 0
 MODE_MARG_PHASE = 1
@@ -245,7 +245,7 @@ class Plan(object):
 
     def loglr_host(self, params, mode=MODE_GAUSSIAN, skip=None,
                    param_major=False):
-        """params: [W, 11] float64 host array, or [11, W] with
+        """params: [W, 13] float64 host array, or [13, W] with
         ``param_major=True``.  Returns loglr[W], hd[W, n_det] complex128,
         hh[W, n_det]."""
         params = np.ascontiguousarray(params, dtype=np.float64)
@@ -276,7 +276,7 @@ class Plan(object):
     def loglr_device(self, params, mode=MODE_GAUSSIAN, skip=None, out=None,
                      stream=None):
         """Device-resident variant: ``params`` is a CUDA float64 torch tensor
-        [W, 11]; returns torch tensors (loglr, hd[W,n_det,2], hh) on the same
+        [W, 13]; returns torch tensors (loglr, hd[W,n_det,2], hh) on the same
         device.  Asynchronous on ``stream`` (default: torch's current stream).
         torch is only the owner of the device memory here."""
         import torch

@@ -62,7 +62,7 @@ static constexpr int kRecurUnroll = RECUR_UNROLL;
 
 // per-walker coefficient rows (SoA: wc[row * wpad + walker])
 enum {
-    C_A0 = 0, C_A2, C_A3, C_A4, C_A5, C_B5, C_A6, C_B6, C_A7,   // phase [turns]
+    C_A0 = 0, C_A2, C_A3, C_A4, C_A5, C_B5, C_A6, C_B6, C_A7, C_A10, C_A12,   // phase [turns]
     C_DET0                                                        // then 4 per detector
 };
 enum { D_TAUHI = 0, D_TAULO, D_ARE, D_AIM, D_ECOS, D_ESIN, D_NROW };   // E = e^{+2 pi i tau}
@@ -222,14 +222,17 @@ __device__ __forceinline__ double4 ld_basis(const double4* p) {
 }
 
 // TaylorF2 phase in turns at one bin, basis = {x, x^-5, ln x}
-struct PhaseCoef { double a0, a2, a3, a4, a5, b5, a6, b6, a7; };
+struct PhaseCoef { double a0, a2, a3, a4, a5, b5, a6, b6, a7, a10, a12; };
+#define NPH 11                 // phase-coefficient rows
 __device__ __forceinline__ double phase_turns(const PhaseCoef& c, double4 b) {
     const double x = b.x, xm5 = b.y, lx = b.z;
     double lo = fma(fma(c.a4, x, c.a3), x, c.a2);
     lo = fma(lo, x * x, c.a0) * xm5;
     const double l5 = fma(c.b5, lx, c.a5);
     const double l6 = fma(c.b6, lx, c.a6);
-    const double hi = fma(fma(c.a7, x, l6), x, l5);
+    const double x2 = x * x;
+    const double tid = fma(c.a12, x2, c.a10) * (x2 * x);        // tidal: a10 x^5 + a12 x^7 = x^2 (x^3 (...))
+    const double hi = fma(fma(c.a7 + tid, x, l6), x, l5);
     return lo + hi;
 }
 
@@ -237,6 +240,7 @@ __device__ __forceinline__ void load_phase_coef(PhaseCoef& c, const double* wc, 
     c.a0 = wc[C_A0 * wpad + w]; c.a2 = wc[C_A2 * wpad + w]; c.a3 = wc[C_A3 * wpad + w];
     c.a4 = wc[C_A4 * wpad + w]; c.a5 = wc[C_A5 * wpad + w]; c.b5 = wc[C_B5 * wpad + w];
     c.a6 = wc[C_A6 * wpad + w]; c.b6 = wc[C_B6 * wpad + w]; c.a7 = wc[C_A7 * wpad + w];
+    c.a10 = wc[C_A10 * wpad + w]; c.a12 = wc[C_A12 * wpad + w];
 }
 
 // ---------------------------------------------------------------------------
@@ -377,6 +381,18 @@ __global__ void walker_setup_kernel(PlanDev P, int W, int wpad,
     wc[C_A6 * wpad + t] = s * (v6 + vl6 * lm3) * m3;
     wc[C_B6 * wpad + t] = s * vl6 * m3;
     wc[C_A7 * wpad + t] = s * v7 * m3 * m3;
+    {   // tidal terms (lalsimulation TaylorF2Phasing_10PN/12PNTidalCoeff): pfaN (pft10 v^10 + pft12 v^12) / v^5
+        const double lam1 = p[11], lam2 = p[12];
+        const double m1M4 = m1M * m1M * m1M * m1M, m2M4 = m2M * m2M * m2M * m2M;
+        const double pft10 = lam1 * (-288.0 + 264.0 * m1M) * m1M4 + lam2 * (-288.0 + 264.0 * m2M) * m2M4;
+        const double pft12 = lam1 * (-15895.0 / 28.0 + 4595.0 / 28.0 * m1M + 5715.0 / 14.0 * m1M * m1M
+                                     - 325.0 / 7.0 * m1M * m1M * m1M) * m1M4
+                           + lam2 * (-15895.0 / 28.0 + 4595.0 / 28.0 * m2M + 5715.0 / 14.0 * m2M * m2M
+                                     - 325.0 / 7.0 * m2M * m2M * m2M) * m2M4;
+        const double m3_2 = m3 * m3, m3_5 = m3_2 * m3_2 * m3;
+        wc[C_A10 * wpad + t] = s * pft10 * m3_5;
+        wc[C_A12 * wpad + t] = s * pft12 * m3_5 * m3_2;
+    }
 
     // --- band ------------------------------------------------------------------
     const int n = waveform_len(mtot, P.delta_f);
@@ -560,10 +576,10 @@ loglr_direct_kernel(PlanDev P, int W, int wpad, int chunk_bins, int n_chunks,
 // Per-thread walker coefficients live in shared memory (one column per thread, no
 // sharing, hence no barrier): they are only needed in the per-block set-up, and keeping
 // them out of the register file buys a third/fourth resident CTA per SM.
-#define RC_ROWS(nd) (9 + 4 * (nd))
+#define RC_ROWS(nd) (NPH + 4 * (nd))
 template <int ND>
 __device__ __forceinline__ double2 load_E(const double* sc, int d) {       // e^{+2 pi i tau_d}
-    return make_double2(sc[(9 + 2 * ND + 2 * d) * CTA_THREADS], sc[(10 + 2 * ND + 2 * d) * CTA_THREADS]);
+    return make_double2(sc[(NPH + 2 * ND + 2 * d) * CTA_THREADS], sc[(NPH + 1 + 2 * ND + 2 * d) * CTA_THREADS]);
 }
 template <int ND>
 __device__ __forceinline__ void load_block_coef(const double* sc, PhaseCoef& pc,
@@ -572,10 +588,11 @@ __device__ __forceinline__ void load_block_coef(const double* sc, PhaseCoef& pc,
     pc.a0 = sc[0 * CTA_THREADS]; pc.a2 = sc[1 * CTA_THREADS]; pc.a3 = sc[2 * CTA_THREADS];
     pc.a4 = sc[3 * CTA_THREADS]; pc.a5 = sc[4 * CTA_THREADS]; pc.b5 = sc[5 * CTA_THREADS];
     pc.a6 = sc[6 * CTA_THREADS]; pc.b6 = sc[7 * CTA_THREADS]; pc.a7 = sc[8 * CTA_THREADS];
+    pc.a10 = sc[9 * CTA_THREADS]; pc.a12 = sc[10 * CTA_THREADS];
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
-        tau_hi[d] = sc[(9 + 2 * d) * CTA_THREADS];
-        tau_lo[d] = sc[(10 + 2 * d) * CTA_THREADS];
+        tau_hi[d] = sc[(NPH + 2 * d) * CTA_THREADS];
+        tau_lo[d] = sc[(NPH + 1 + 2 * d) * CTA_THREADS];
     }
 }
 
@@ -791,14 +808,14 @@ loglr_recur_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_blk,
         const int tt = live ? t : 0;
         double* sc = s_coef + threadIdx.x;
 #pragma unroll
-        for (int r = 0; r < 9; ++r) sc[r * CTA_THREADS] = wc[(size_t)r * wpad + tt];
+        for (int r = 0; r < NPH; ++r) sc[r * CTA_THREADS] = wc[(size_t)r * wpad + tt];
 #pragma unroll
         for (int d = 0; d < ND; ++d) {
             const double* row = wc + (size_t)(C_DET0 + D_NROW * d) * wpad + tt;
-            sc[(9 + 2 * d) * CTA_THREADS] = row[D_TAUHI * wpad];
-            sc[(10 + 2 * d) * CTA_THREADS] = row[D_TAULO * wpad];
-            sc[(9 + 2 * ND + 2 * d) * CTA_THREADS] = row[D_ECOS * wpad];
-            sc[(10 + 2 * ND + 2 * d) * CTA_THREADS] = row[D_ESIN * wpad];
+            sc[(NPH + 2 * d) * CTA_THREADS] = row[D_TAUHI * wpad];
+            sc[(NPH + 1 + 2 * d) * CTA_THREADS] = row[D_TAULO * wpad];
+            sc[(NPH + 2 * ND + 2 * d) * CTA_THREADS] = row[D_ECOS * wpad];
+            sc[(NPH + 1 + 2 * ND + 2 * d) * CTA_THREADS] = row[D_ESIN * wpad];
         }
         const int lane = threadIdx.x & (WARP - 1), warp = threadIdx.x / WARP;
         TileStream<ND> S;
@@ -1461,15 +1478,15 @@ extern "C" int gwin_loglr_batch_host(gwin_plan* p, int mode, int64_t W,
     return gwin_loglr_batch_host_strided(p, mode, W, params, GWIN_NPARAM, 1, skip, loglr, hd, hh);
 }
 
-// params is either [W][11] (stride_walker = 11, stride_param = 1) or [11][W] (1, W); the
-// buffer is copied as one contiguous block of 11*W doubles
+// params is either [W][13] (stride_walker = 13, stride_param = 1) or [13][W] (1, W); the
+// buffer is copied as one contiguous block of 13*W doubles
 extern "C" int gwin_loglr_batch_host_strided(gwin_plan* p, int mode, int64_t W,
                                              const double* params, int64_t stride_walker, int64_t stride_param,
                                              const uint8_t* skip,
                                              double* loglr, double* hd, double* hh) {
     if (!p) return fail(GWIN_EINVAL, "plan is NULL");
     if (!((stride_walker == GWIN_NPARAM && stride_param == 1) || (stride_walker == 1 && stride_param == W)))
-        return fail(GWIN_EINVAL, "host parameters must be a dense [W][11] or [11][W] block");
+        return fail(GWIN_EINVAL, "host parameters must be a dense [W][13] or [13][W] block");
     if (W < 0) return fail(GWIN_EINVAL, "W < 0");
     if (W == 0) { p->last_launches = 0; return GWIN_OK; }
     if (!params || !loglr) return fail(GWIN_EINVAL, "params/loglr is NULL");

@@ -116,7 +116,7 @@ __device__ __forceinline__ double wrap_reflect(double x, double lo, double hi) {
     return y + lo;
 }
 
-// q [W][ndim] (sampling parameters, untouched) -> logp [W], skip [W], params [11][W]
+// q [W][ndim] (sampling parameters, untouched) -> logp [W], skip [W], params [13][W]
 __global__ void ens_prior_kernel(gwin_prior_spec_dev S, int W, const double* __restrict__ q,
                                  double* __restrict__ logp, uint8_t* __restrict__ skip,
                                  double* __restrict__ params) {

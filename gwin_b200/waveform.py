@@ -26,7 +26,8 @@ MTSUN_SI = 4.925491025543575903411922162094833998e-6
 WAVEFORM_PARAMS = OrderedDict([
     ("mass1", None), ("mass2", None), ("spin1z", 0.0), ("spin2z", 0.0),
     ("distance", 1.0), ("inclination", 0.0), ("coa_phase", 0.0),
-    ("ra", None), ("dec", None), ("polarization", None), ("tc", None)])
+    ("ra", None), ("dec", None), ("polarization", None), ("tc", None),
+    ("lambda1", 0.0), ("lambda2", 0.0)])
 
 SUPPORTED_APPROXIMANTS = ("TaylorF2",)
 
@@ -63,7 +64,7 @@ def taylorf2_length(mass1, mass2, delta_f):
 
 
 def param_matrix(params, W, static=None):
-    """Assemble the kernel's [W, 11] parameter matrix from a dict of scalars
+    """Assemble the kernel's [W, 13] parameter matrix from a dict of scalars
     and/or [W] arrays (plus ``static`` defaults)."""
     out = numpy.empty((W, len(WAVEFORM_PARAMS)), dtype=numpy.float64)
     for i, (name, default) in enumerate(WAVEFORM_PARAMS.items()):
@@ -80,7 +81,7 @@ def param_matrix(params, W, static=None):
 
 
 def param_rows(params, W, static=None):
-    """Parameter-major [11, W] variant of ``param_matrix``: one contiguous row per
+    """Parameter-major [13, W] variant of ``param_matrix``: one contiguous row per
     waveform parameter (no transpose of the sampler's per-parameter arrays)."""
     out = numpy.empty((len(WAVEFORM_PARAMS), W), dtype=numpy.float64)
     for i, (name, default) in enumerate(WAVEFORM_PARAMS.items()):

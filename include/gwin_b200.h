@@ -28,7 +28,7 @@ extern "C" {
 #define GWIN_ENODEVICE    -4   /* no usable sm_100 device: there is NO CPU fallback */
 
 #define GWIN_MAX_DET       4
-#define GWIN_NPARAM       11   /* per-walker parameter row, see gwin_loglr_batch */
+#define GWIN_NPARAM       13   /* per-walker parameter row, see gwin_loglr_batch */
 
 /* loglr flavour */
 #define GWIN_MODE_GAUSSIAN     0  /* gaussian_noise.py:304-350:  sum_det Re<d|h> - <h|h>/2        */
@@ -90,7 +90,8 @@ int gwin_plan_configure(gwin_plan* plan, int kernel, double phase_tol, double mc
  *
  *   params  [W][GWIN_NPARAM] row-major:
  *           mass1, mass2 [Msun], spin1z, spin2z, distance [Mpc], inclination,
- *           coa_phase, ra, dec, polarization [rad], tc [GPS s]
+ *           coa_phase, ra, dec, polarization [rad], tc [GPS s],
+ *           lambda1, lambda2 (dimensionless tidal deformabilities; 0 for black holes)
  *   skip    [W] or NULL; nonzero = prior was -inf, do not evaluate
  *           (base.py:556-568 / base_data.py:128-141 short-circuit): loglr=-inf
  *   loglr   [W]
@@ -107,8 +108,8 @@ int gwin_loglr_batch(gwin_plan* plan, int mode, int64_t W,
                      double* loglr, double* hd, double* hh, void* stream);
 
 /* Same with an explicit parameter layout: element (walker w, parameter i) is
- * params[w*stride_walker + i*stride_param].  (11, 1) is the row layout above; (1, W) is
- * parameter-major [11][W], which a host that holds one array per parameter (as gwin's
+ * params[w*stride_walker + i*stride_param].  (13, 1) is the row layout above; (1, W) is
+ * parameter-major [13][W], which a host that holds one array per parameter (as gwin's
  * samplers do) can fill without a transpose and which the device reads coalesced. */
 int gwin_loglr_batch_strided(gwin_plan* plan, int mode, int64_t W,
                              const double* params, int64_t stride_walker, int64_t stride_param,
@@ -120,7 +121,7 @@ int gwin_loglr_batch_host(gwin_plan* plan, int mode, int64_t W,
                           const double* params, const uint8_t* skip,
                           double* loglr, double* hd, double* hh);
 
-/* Host buffers with layout; params must be a dense [W][11] or [11][W] block. */
+/* Host buffers with layout; params must be a dense [W][13] or [13][W] block. */
 int gwin_loglr_batch_host_strided(gwin_plan* plan, int mode, int64_t W,
                                   const double* params, int64_t stride_walker, int64_t stride_param,
                                   const uint8_t* skip,
@@ -164,7 +165,7 @@ int gwin_plan_kernel_timing(gwin_plan* plan, int enable, double* mean_ms, int* n
 typedef struct gwin_prior_spec {
     int32_t ndim;                       /* sampling dimensions                                   */
     int32_t type[GWIN_ENS_MAXDIM];      /* GWIN_PRIOR_*                                          */
-    int32_t target[GWIN_ENS_MAXDIM];    /* waveform-parameter column 0..10, or GWIN_TARGET_*     */
+    int32_t target[GWIN_ENS_MAXDIM];    /* waveform-parameter column 0..12, or GWIN_TARGET_*     */
     double lo[GWIN_ENS_MAXDIM], hi[GWIN_ENS_MAXDIM];
     double fixed[GWIN_NPARAM];          /* static values of the parameters that are not sampled  */
 } gwin_prior_spec;
@@ -178,7 +179,7 @@ int gwin_ens_propose(uint64_t seed, uint32_t iter, int half, int ntemps, int nwa
                      const double* p, double* q, double* logfac, void* stream);
 
 /* Boundary conditions, log prior and the likelihood kernel's parameter rows for W points:
- * q [W][ndim] -> logp [W], skip [W] (1 where logp = -inf), params [11][W] (parameter-major, feed to
+ * q [W][ndim] -> logp [W], skip [W] (1 where logp = -inf), params [13][W] (parameter-major, feed to
  * gwin_loglr_batch_strided with strides (1, W)).  Replaces _transform_params + logprior
  * (gwin/models/base.py:543-554, 602-621) for the supported distributions. */
 int gwin_ens_prior(const gwin_prior_spec* spec, int64_t W, const double* q,

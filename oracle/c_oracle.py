@@ -81,7 +81,7 @@ class COracle(object):
         return self._lib.oracle_lognl(self._h, None)
 
     def batch_loglr(self, params, mode=0, nthreads=1):
-        P = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, 11)
+        P = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, 13)
         W = P.shape[0]
         lr = np.empty(W)
         hd = np.empty((W, self.n_det), dtype=np.complex128)

@@ -168,8 +168,20 @@ def taylorf2_length(m1, m2, delta_f):
     return int(fISCO / delta_f + 1)
 
 
+def taylorf2_tidal(m1, m2, lambda1, lambda2):
+    """[UPSTREAM] XLALSimInspiralTaylorF2Phasing_{10,12}PNTidalCoeff: returns (pft10, pft12)
+    WITHOUT the pfaN prefactor."""
+    mtot = m1 + m2
+    out = []
+    for coeff in (lambda x: (-288.0 + 264.0 * x) * x ** 4,
+                  lambda x: (-15895.0 / 28.0 + 4595.0 / 28.0 * x + 5715.0 / 14.0 * x * x
+                             - 325.0 / 7.0 * x * x * x) * x ** 4):
+        out.append(lambda1 * coeff(m1 / mtot) + lambda2 * coeff(m2 / mtot))
+    return tuple(out)
+
+
 def taylorf2_hp_hc(m1, m2, s1z, s2z, distance, inclination, coa_phase,
-                   delta_f, f_lower, mode="faithful"):
+                   delta_f, f_lower, mode="faithful", lambda1=0.0, lambda2=0.0):
     """[UPSTREAM] pycbc.waveform.get_fd_waveform(approximant='TaylorF2')
     = XLALSimInspiralChooseFDWaveform -> XLALSimInspiralTaylorF2 (+Core) with
     f_ref = 0, f_max = 0, 3.5PN phase, 0PN amplitude.  Returns complex128
@@ -178,6 +190,9 @@ def taylorf2_hp_hc(m1, m2, s1z, s2z, distance, inclination, coa_phase,
     """
     ph = taylorf2_phasing(m1, m2, s1z, s2z)
     pv, pl, eta = ph["v"], ph["vlogv"], ph["eta"]
+    pfaN = 3.0 / (128.0 * eta)
+    t10, t12 = taylorf2_tidal(m1, m2, lambda1, lambda2)
+    pft10, pft12 = pfaN * t10, pfaN * t12
     m = m1 + m2
     m_sec = m * LAL_MTSUN_SI
     piM = LAL_PI * m_sec
@@ -212,6 +227,8 @@ def taylorf2_hp_hc(m1, m2, s1z, s2z, distance, inclination, coa_phase,
             phasing = phasing + pv[2] * v2
             phasing = phasing + pv[1] * v
             phasing = phasing + pv[0]
+            phasing = phasing + pft12 * (v10 * v2)      # tidal terms
+            phasing = phasing + pft10 * v10
             phasing = phasing / v5
             flux = FTaN * v10
             dEnergy = dETaN * v
@@ -232,6 +249,7 @@ def taylorf2_hp_hc(m1, m2, s1z, s2z, distance, inclination, coa_phase,
             poly = poly * v + ld(pv[2])
             poly = poly * v + ld(pv[1])
             poly = poly * v + ld(pv[0])
+            poly = poly + ld(pft10) * v ** 10 + ld(pft12) * v ** 12
             phasing = poly / v ** 5
             # shft*f = -2 pi k exactly: drop it
             phasing = phasing - ld(2.0) * ld(coa_phase) - ld(LAL_PI) / 4
@@ -411,7 +429,8 @@ class FDomainDetFrameGenerator(object):
         hp, hc = taylorf2_hp_hc(
             p["mass1"], p["mass2"], p.get("spin1z", 0.0), p.get("spin2z", 0.0),
             p["distance"], p.get("inclination", 0.0), p.get("coa_phase", 0.0),
-            self.delta_f, self.f_lower, mode=self.mode)
+            self.delta_f, self.f_lower, mode=self.mode,
+            lambda1=p.get("lambda1", 0.0), lambda2=p.get("lambda2", 0.0))
         h = OrderedDict()
         for detname, det in self.detectors.items():
             fp, fc = det.antenna_pattern(p["ra"], p["dec"], p["polarization"],
@@ -529,11 +548,11 @@ class GaussianNoiseOracle(object):
 
 
 PARAM_ORDER = ("mass1", "mass2", "spin1z", "spin2z", "distance", "inclination",
-               "coa_phase", "ra", "dec", "polarization", "tc")
+               "coa_phase", "ra", "dec", "polarization", "tc", "lambda1", "lambda2")
 
 
 def batch_loglr(model, params):
-    """Evaluate an oracle model on a [W, 11] array in PARAM_ORDER.
+    """Evaluate an oracle model on a [W, 13] array in PARAM_ORDER.
     Returns loglr[W], hd[W, ndet] complex, hh[W, ndet]."""
     params = np.atleast_2d(np.asarray(params, dtype=np.float64))
     W = params.shape[0]

@@ -152,9 +152,10 @@ static double one_loglr(const oracle_model* m, int mode, const double* p, scratc
                         cplx* hd_out, double* hh_out) {
     const double m1 = p[0], m2 = p[1], chi1L = p[2], chi2L = p[3], distance = p[4];
     const double incl = p[5], phi_ref = p[6], ra = p[7], dec = p[8], psi = p[9], tc = p[10];
+    const double lambda1 = p[11], lambda2 = p[12];
     const int nd = m->n_det;
     for (int d = 0; d < nd; ++d) { hd_out[d] = 0; hh_out[d] = 0; }
-    for (int i = 0; i < 11; ++i) if (!isfinite(p[i])) return -INFINITY;
+    for (int i = 0; i < 13; ++i) if (!isfinite(p[i])) return -INFINITY;
     if (!(m1 > 0) || !(m2 > 0) || !(distance > 0)) return -INFINITY;
     /* ---- [UPSTREAM] XLALSimInspiralPNPhasing_F2 ---- */
     const double mtot = m1 + m2, dm = (m1 - m2) / (m1 + m2);
@@ -198,6 +199,11 @@ static double one_loglr(const oracle_model* m, int mode, const double* p, scratc
         v[3] += 188.0 * SL / 3.0 + 25.0 * dSigmaL;
     }
     for (int i = 0; i < 8; ++i) { v[i] *= pfaN; vl[i] *= pfaN; }
+    /* [UPSTREAM] tidal terms: XLALSimInspiralTaylorF2Phasing_{10,12}PNTidalCoeff */
+    const double m1M4 = m1M * m1M * m1M * m1M, m2M4 = m2M * m2M * m2M * m2M;
+    const double pft10 = pfaN * (lambda1 * (-288.0 + 264.0 * m1M) * m1M4 + lambda2 * (-288.0 + 264.0 * m2M) * m2M4);
+    const double pft12 = pfaN * (lambda1 * (-15895.0 / 28.0 + 4595.0 / 28.0 * m1M + 5715.0 / 14.0 * m1M * m1M - 325.0 / 7.0 * m1M * m1M * m1M) * m1M4
+                               + lambda2 * (-15895.0 / 28.0 + 4595.0 / 28.0 * m2M + 5715.0 / 14.0 * m2M * m2M - 325.0 / 7.0 * m2M * m2M * m2M) * m2M4);
     /* ---- [UPSTREAM] XLALSimInspiralTaylorF2 ---- */
     const double m_sec = mtot * LAL_MTSUN_SI, piM = LAL_PI * m_sec;
     const double vISCO = 1.0 / sqrt(6.0);
@@ -226,6 +232,8 @@ static double one_loglr(const oracle_model* m, int mode, const double* p, scratc
         phasing += v[2] * v2;
         phasing += v[1] * vv;
         phasing += v[0];
+        phasing += pft12 * (v10 * v2);
+        phasing += pft10 * v10;
         phasing /= v5;
         const double flux = FTaN * v10, dEnergy = dETaN * vv;
         phasing += shft * f - 2.0 * phi_ref;
@@ -303,7 +311,7 @@ static void* worker(void* arg) {
     s.hc = malloc(sizeof(cplx) * m->n_f); s.hd = malloc(sizeof(cplx) * m->n_f);
     cplx hd[MAX_DET]; double hh[MAX_DET];
     for (long w = j->w0; w < j->w1; ++w) {
-        j->loglr[w] = one_loglr(m, j->mode, j->params + 11 * w, &s, hd, hh);
+        j->loglr[w] = one_loglr(m, j->mode, j->params + 13 * w, &s, hd, hh);
         for (int d = 0; d < m->n_det; ++d) {
             if (j->hd) { j->hd[2 * (w * m->n_det + d)] = creal(hd[d]); j->hd[2 * (w * m->n_det + d) + 1] = cimag(hd[d]); }
             if (j->hh) j->hh[w * m->n_det + d] = hh[d];
@@ -313,7 +321,7 @@ static void* worker(void* arg) {
     return NULL;
 }
 
-/* params [W][11] in the order of include/gwin_b200.h; hd [W][n_det][2]; hh [W][n_det] */
+/* params [W][13] in the order of include/gwin_b200.h; hd [W][n_det][2]; hh [W][n_det] */
 int oracle_loglr(const oracle_model* m, int mode, long W, const double* params,
                  double* loglr, double* hd, double* hh, int nthreads) {
     if (nthreads < 1) nthreads = 1;

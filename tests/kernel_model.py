@@ -152,7 +152,7 @@ class PlanModel(object):
 
     # -- walker_setup_kernel --------------------------------------------------
     def walker(self, p):
-        m1, m2, chi1, chi2, dist, incl, phic, ra, dec, psi, tc = [float(v) for v in p]
+        m1, m2, chi1, chi2, dist, incl, phic, ra, dec, psi, tc, lam1, lam2 = [float(v) for v in p]
         mtot = m1 + m2
         dm = (m1 - m2) / (m1 + m2)
         eta = m1 * m2 / mtot / mtot
@@ -205,6 +205,10 @@ class PlanModel(object):
         w['a6'] = s * (v6 + vl6 * lm3) * m3
         w['b6'] = s * vl6 * m3
         w['a7'] = s * v7 * m3 * m3
+        c10 = lambda x: (-288.0 + 264.0 * x) * x ** 4
+        c12 = lambda x: (-15895.0 / 28.0 + 4595.0 / 28.0 * x + 5715.0 / 14.0 * x * x - 325.0 / 7.0 * x ** 3) * x ** 4
+        w['a10'] = s * (lam1 * c10(m1M) + lam2 * c10(m2M)) * m3 ** 5
+        w['a12'] = s * (lam1 * c12(m1M) + lam2 * c12(m2M)) * m3 ** 7
         vI = 1.0 / math.sqrt(6.0)
         fisco = vI * vI * vI / piM
         n = int(fisco / self.delta_f + 1.0)
@@ -265,7 +269,8 @@ class PlanModel(object):
         lo = (lo * (x * x) + w['a0']) * xm5
         l5 = w['b5'] * lx + w['a5']
         l6 = w['b6'] * lx + w['a6']
-        return lo + ((w['a7'] * x + l6) * x + l5)
+        tid = (w['a12'] * (x * x) + w['a10']) * (x * x * x)
+        return lo + (((w['a7'] + tid) * x + l6) * x + l5)
 
     def finish(self, w, S, marg=False):
         hd = np.array([w['A'][d] * S[d] for d in range(self.n_det)])

@@ -183,7 +183,7 @@ def test_edge_cases(cfg2):
             assert abs(lr[i] - l0) <= tol(l0), (kernel, i, lr[i], l0)
             assert np.allclose(hh[i], list(h0.values()), rtol=1e-9, atol=1e-9)
     # W = 0 and W = 1
-    lr, hd, hh = model.plan.loglr_host(np.empty((0, 11)))
+    lr, hd, hh = model.plan.loglr_host(np.empty((0, 13)))
     assert lr.shape == (0,)
     lr1, _, _ = model.plan.loglr_host(P[:1])
     assert abs(lr1[0] - orc.loglr(**dict(zip(PARAM_ORDER, P[0])))[0]) <= tol(lr1[0])
@@ -277,6 +277,33 @@ def test_large_segment_two_million_bins():
         model.plan.configure(kernel=kernel)
         lr, hd, hh = model.plan.loglr_host(P)
         _check(lr, hd, hh, lr0, hd0, hh0, "2M bins k%d" % kernel)
+
+
+def test_tidal_deformabilities(cfg3):
+    """lambda1, lambda2 (columns 11, 12 of the parameter row): both kernels against the oracle;
+    lambda = 0 reproduces the point-particle result bit for bit."""
+    model = cfg3.cuda_model()
+    rng = np.random.default_rng(31)
+    P = util.draw_bns(rng, 16, cfg3)
+    base = model.plan.loglr_host(P)
+    P2 = P.copy()
+    P2[:, 11] = rng.uniform(0., 3000., len(P))
+    P2[:, 12] = rng.uniform(0., 3000., len(P))
+    lr0, hd0, hh0 = _oracle_batch(cfg3.oracle(), P2)
+    for kernel in (1, 2):
+        model.plan.configure(kernel=kernel)
+        lr, hd, hh = model.plan.loglr_host(P2)
+        _check(lr, hd, hh, lr0, hd0, hh0, "tidal k%d" % kernel)
+    assert np.max(np.abs(lr0 - base[0])) > 1.0
+    model.plan.configure(kernel=0)
+    np.testing.assert_array_equal(model.plan.loglr_host(P)[0], base[0])
+    # through the model API with lambda as a sampled parameter
+    from gwin_b200 import models
+    static = {k: v for k, v in cfg3.inj.items() if k not in ("lambda1", "lambda2")}
+    m = cfg3.cuda_model(variable_params=("lambda1", "lambda2"), static_params=static)
+    vals = models.CallModel(m, "loglr", return_all_stats=False).batch(np.array([[0., 0.], [400., 900.]])).values
+    ref = [cfg3.oracle().loglr(**dict(cfg3.inj, lambda1=a, lambda2=b))[0] for a, b in ((0., 0.), (400., 900.))]
+    assert np.all(np.abs(vals - ref) <= tol(np.array(ref)))
 
 
 def test_four_detectors_and_large_batch():

@@ -39,7 +39,7 @@ def test_device_prior_matches_host_distributions():
     qd = torch.tensor(q, device="cuda")
     logp = torch.empty(W, dtype=torch.float64, device="cuda")
     skip = torch.empty(W, dtype=torch.uint8, device="cuda")
-    params = torch.empty((11, W), dtype=torch.float64, device="cuda")
+    params = torch.empty((13, W), dtype=torch.float64, device="cuda")
     _lib.check(_lib.load().gwin_ens_prior(C.byref(spec), W, qd.data_ptr(), logp.data_ptr(),
                                           skip.data_ptr(), params.data_ptr(), None))
     torch.cuda.synchronize()

@@ -59,3 +59,18 @@ def test_marginalized_phase_model():
     row = util.inj_row(cfg)
     lr0 = orc.loglr(**dict(zip(util.PARAM_ORDER, row)))[0]
     assert abs(pm.loglr_recur(row, marg=True)[0] - lr0) <= util.tol(lr0)
+
+
+def test_tidal_terms_in_the_kernel_arithmetic():
+    cfg = util.c3(seglen=32)
+    pm = _plan(cfg, mchirp_min=1.0)
+    orc = cfg.oracle()
+    rng = np.random.default_rng(3)
+    P = util.draw_bns(rng, 2, cfg)
+    P[:, 11] = 800., 2500.
+    P[:, 12] = 1500., 0.
+    for row in P:
+        lr0 = orc.loglr(**dict(zip(util.PARAM_ORDER, row)))[0]
+        assert abs(pm.loglr_direct(row)[0] - lr0) <= util.tol(lr0)
+        lr, hd, hh, perr = pm.loglr_recur(row, return_phase_err=True)
+        assert abs(lr - lr0) <= util.tol(lr0) and perr <= pm.phase_tol

@@ -212,6 +212,38 @@ def test_antenna_pattern_against_closed_form():
     assert abs(d.time_delay_from_earth_center(ra, dec, t) + np.linalg.norm(r) / O.LAL_C_SI) < 1e-12
 
 
+def test_tidal_terms():
+    """Tidal phasing: for equal masses and equal deformabilities the 5PN / 6PN coefficients are
+    the literature's -(39/2) Lambda~ and -(3115/64) Lambda~ (Vines, Flanagan & Hinderer 2011);
+    lambda = 0 leaves the waveform untouched; the C restatement agrees with the numpy one."""
+    t10, t12 = O.taylorf2_tidal(1.4, 1.4, 400., 400.)
+    assert abs(t10 / 400. + 39. / 2.) < 1e-12 and abs(t12 / 400. + 3115. / 64.) < 1e-12
+    a, _ = O.taylorf2_hp_hc(1.4, 1.3, 0, 0, 40., 0.3, 0.2, 1. / 16, 20.)
+    b, _ = O.taylorf2_hp_hc(1.4, 1.3, 0, 0, 40., 0.3, 0.2, 1. / 16, 20., lambda1=0., lambda2=0.)
+    c, _ = O.taylorf2_hp_hc(1.4, 1.3, 0, 0, 40., 0.3, 0.2, 1. / 16, 20., lambda1=500., lambda2=700.)
+    assert np.array_equal(a, b)
+    k = np.arange(400, len(a), 997)
+    dphi = np.angle(c[k] / a[k])
+    f = k / 16.
+    v = np.cbrt(math.pi * 2.7 * O.LAL_MTSUN_SI * f)
+    eta = 1.4 * 1.3 / 2.7 ** 2
+    t10, t12 = O.taylorf2_tidal(1.4, 1.3, 500., 700.)
+    expect = -(3. / (128 * eta)) * (t10 * v ** 5 + t12 * v ** 7)      # h ~ exp(-i Psi)
+    assert np.allclose(np.exp(1j * dphi), np.exp(1j * expect), atol=1e-7)
+    assert np.allclose(np.abs(c), np.abs(a), rtol=1e-14)
+    cfg = util.c3(seglen=32)
+    rng = np.random.default_rng(4)
+    P = util.draw_bns(rng, 4, cfg)
+    P[:, 11] = rng.uniform(0, 3000, 4)
+    P[:, 12] = rng.uniform(0, 3000, 4)
+    ref = O.batch_loglr(cfg.oracle(), P)
+    zero = O.batch_loglr(cfg.oracle(), np.column_stack([P[:, :11], np.zeros((4, 2))]))
+    assert np.max(np.abs(ref[0] - zero[0])) > 1e-3                # the tides matter here
+    co = COracle(cfg.data, cfg.delta_f, cfg.epoch, cfg.f_lower, psds=cfg.psds())
+    got = co.batch_loglr(P, nthreads=2)
+    assert np.max(np.abs(ref[0] - got[0])) < 1e-7 and np.allclose(ref[2], got[2], rtol=1e-12)
+
+
 def test_spin_terms_known_limits():
     """1.5PN spin-orbit: equal masses, equal spins => 4 beta = (188/6) chi."""
     a = O.taylorf2_phasing(10., 10., 0.3, 0.3)

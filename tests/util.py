@@ -21,12 +21,14 @@ PARAM_ORDER = O.PARAM_ORDER
 BBH_INJ = OrderedDict([  # reference fixture values, test/utils/waveform.py:25-35
     ("mass1", 30.0), ("mass2", 30.0), ("spin1z", 0.0), ("spin2z", 0.0),
     ("distance", 300.0), ("inclination", 0.1), ("coa_phase", 1.1),
-    ("ra", 0.1), ("dec", 0.1), ("polarization", 0.1), ("tc", 6.1)])
+    ("ra", 0.1), ("dec", 0.1), ("polarization", 0.1), ("tc", 6.1),
+    ("lambda1", 0.0), ("lambda2", 0.0)])
 
 BNS_INJ = OrderedDict([
     ("mass1", 1.4), ("mass2", 1.4), ("spin1z", 0.0), ("spin2z", 0.0),
     ("distance", 40.0), ("inclination", 0.5), ("coa_phase", 1.1),
-    ("ra", 1.3), ("dec", -0.4), ("polarization", 0.7), ("tc", 250.0)])
+    ("ra", 1.3), ("dec", -0.4), ("polarization", 0.7), ("tc", 250.0),
+    ("lambda1", 0.0), ("lambda2", 0.0)])
 
 
 class Config(object):
@@ -104,7 +106,7 @@ def c3(seglen=256, **kw):
 
 def draw_bbh(rng, W, cfg, spins=True):
     """Walkers around the test-suite priors (test/test_sampler.py:74-98)."""
-    P = np.empty((W, 11))
+    P = np.zeros((W, 13))
     P[:, 0] = rng.uniform(10., 40., W)
     P[:, 1] = rng.uniform(10., 40., W)
     P[:, 2] = rng.uniform(-0.5, 0.5, W) if spins else 0.
@@ -121,7 +123,7 @@ def draw_bbh(rng, W, cfg, spins=True):
 
 def draw_bns(rng, W, cfg):
     """Box around the BNS injection."""
-    P = np.empty((W, 11))
+    P = np.zeros((W, 13))
     P[:, 0] = rng.uniform(1.2, 1.6, W)
     P[:, 1] = rng.uniform(1.2, 1.6, W)
     P[:, 2] = 0.
