@@ -27,12 +27,15 @@ GWIN_NPARAM = 13
 GWIN_MAX_DET = 4
 MODE_GAUSSIAN = 0
 MODE_MARG_PHASE = 1
+MODE_MARG_DIST = 2
+MODE_MARG_DIST_PHASE = 3
 KERNEL_AUTO, KERNEL_DIRECT, KERNEL_RECURRENCE = 0, 1, 2
 
 # Every symbol include/gwin_b200.h declares (checked by tests/test_abi.py).
 SYMBOLS = (
     "gwin_plan_create", "gwin_plan_destroy", "gwin_plan_cutoffs",
-    "gwin_plan_lognl", "gwin_plan_configure", "gwin_loglr_batch",
+    "gwin_plan_lognl", "gwin_plan_configure", "gwin_plan_set_distance_marg",
+    "gwin_loglr_batch",
     "gwin_loglr_batch_host", "gwin_loglr_batch_strided",
     "gwin_loglr_batch_host_strided", "gwin_generate_host",
     "gwin_plan_last_launches",
@@ -117,6 +120,9 @@ def load():
                                           C.POINTER(C.c_int64)]
         lib.gwin_plan_lognl.restype = C.c_int
         lib.gwin_plan_lognl.argtypes = [C.c_void_p, dp, dp]
+        lib.gwin_plan_set_distance_marg.restype = C.c_int
+        lib.gwin_plan_set_distance_marg.argtypes = [C.c_void_p, C.c_int64,
+                                                    C.c_void_p, C.c_void_p]
         lib.gwin_plan_configure.restype = C.c_int
         lib.gwin_plan_configure.argtypes = [C.c_void_p, C.c_int, C.c_double,
                                             C.c_double]
@@ -230,6 +236,16 @@ class Plan(object):
     def configure(self, kernel=KERNEL_AUTO, phase_tol=0.0, mchirp_min=0.0):
         check(self._lib.gwin_plan_configure(self._h, int(kernel),
                                             float(phase_tol), float(mchirp_min)))
+
+    def set_distance_marg(self, dist, weight):
+        """Distance grid and logsumexp weights (``deltad * dist_prior``) of the
+        distance-marginalised modes; see ``gwin_plan_set_distance_marg``."""
+        dist = np.ascontiguousarray(dist, dtype=np.float64)
+        weight = np.ascontiguousarray(weight, dtype=np.float64)
+        if dist.shape != weight.shape or dist.ndim != 1:
+            raise ValueError("dist and weight must be 1-D arrays of one length")
+        check(self._lib.gwin_plan_set_distance_marg(
+            self._h, dist.size, dist.ctypes.data, weight.ctypes.data))
 
     @property
     def last_launches(self):

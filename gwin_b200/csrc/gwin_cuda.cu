@@ -135,6 +135,9 @@ struct gwin_plan {
     double2* d_partial;
     size_t partial_cap;
     void* d_cub; size_t cub_bytes;
+    // distance marginalisation grid (1/D_j, log w_j) and the per-walker (x, opt) hand-over
+    int n_marg;
+    double *d_marg_u, *d_marg_logw, *d_marg_opt;
     // staging for the host API
     double *h_params, *h_out; uint8_t* h_skip;
     double *d_params, *d_out; uint8_t* d_skip;
@@ -889,7 +892,7 @@ combine_kernel(int n_det, int W, int wpad, int n_chunks, int mode,
                const double2* __restrict__ partial,
                const double* __restrict__ hh_sorted,
                double* __restrict__ loglr, double* __restrict__ hd_out,
-               double* __restrict__ hh_out) {
+               double* __restrict__ hh_out, double* __restrict__ marg_opt) {
     __shared__ double2 s_part[COMB_SEG][GWIN_MAX_DET][32];
     const int lx = threadIdx.x, seg = threadIdx.y;
     const int t = blockIdx.x * 32 + lx;
@@ -935,8 +938,48 @@ combine_kernel(int n_det, int W, int wpad, int n_chunks, int mode,
         sre += hre; sim += him; shh += hh;
     }
     if (mode == GWIN_MODE_MARG_PHASE) lr = log_i0(hypot(sre, sim)) - 0.5 * shh;
+    if (mode >= GWIN_MODE_MARG_DIST) {
+        // hand (x, opt) to marg_dist_kernel: x travels in loglr[w]
+        const double mf = hypot(sre, sim);
+        lr = mode == GWIN_MODE_MARG_DIST ? mf : log_i0(mf);
+        marg_opt[w] = shh;
+    }
     if (invalid || isnan(lr)) lr = -INFINITY;
     loglr[w] = lr;
+}
+
+// ---------------------------------------------------------------------------
+// kernel 4 (distance marginalisation only): one warp per walker,
+//   loglr = log sum_j w_j exp(x u_j - opt u_j^2 / 2),  u_j = 1 / D_j
+// (marginalized_gaussian_noise.py:431-448; scipy.special.logsumexp(a, b=w)).  Two passes
+// over the grid: the maximum of a_j + log w_j, then the sum of exponentials below it.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+marg_dist_kernel(int W, int n, const double* __restrict__ u, const double* __restrict__ logw,
+                 const double* __restrict__ opt_arr, double* __restrict__ loglr) {
+    const int w = blockIdx.x * (blockDim.x / WARP) + threadIdx.x / WARP;
+    const int lane = threadIdx.x % WARP;
+    if (w >= W) return;
+    const double x = loglr[w];
+    if (!(x > -INFINITY)) return;                  // no waveform / skipped: stays -inf
+    const double mh = -0.5 * opt_arr[w];
+    double m = -INFINITY;
+    for (int j = lane; j < n; j += WARP) {
+        const double uj = __ldg(u + j);
+        m = fmax(m, fma(fma(mh, uj, x), uj, __ldg(logw + j)));
+    }
+#pragma unroll
+    for (int o = WARP / 2; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    double s = 0.0;
+    if (m > -INFINITY)
+        for (int j = lane; j < n; j += WARP) {
+            const double uj = __ldg(u + j);
+            const double a = fma(fma(mh, uj, x), uj, __ldg(logw + j)) - m;
+            if (a > -60.0) s += exp(a);            // below e^-60 of the largest term: < 1e-22 relative
+        }
+#pragma unroll
+    for (int o = WARP / 2; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) loglr[w] = m > -INFINITY ? m + log(s) : -INFINITY;
 }
 
 // ---------------------------------------------------------------------------
@@ -1255,6 +1298,7 @@ extern "C" void gwin_plan_destroy(gwin_plan* p) {
     cudaFree(p->d_wc); cudaFree(p->d_ks); cudaFree(p->d_ke);
     cudaFree(p->d_key_in); cudaFree(p->d_key_out); cudaFree(p->d_perm_in); cudaFree(p->d_perm_out);
     cudaFree(p->d_partial); cudaFree(p->d_cub);
+    cudaFree(p->d_marg_u); cudaFree(p->d_marg_logw); cudaFree(p->d_marg_opt);
     cudaFree(p->d_params); cudaFree(p->d_out); cudaFree(p->d_skip);
     cudaFreeHost(p->h_params); cudaFreeHost(p->h_out); cudaFreeHost(p->h_skip);
     if (p->timing) { cudaEventDestroy(p->ev0); cudaEventDestroy(p->ev1); }
@@ -1273,6 +1317,30 @@ extern "C" int gwin_plan_lognl(const gwin_plan* p, double* total, double* per_de
     if (!p) return fail(GWIN_EINVAL, "plan is NULL");
     if (total) *total = p->lognl;
     if (per_det) for (int i = 0; i < p->d.n_det; ++i) per_det[i] = p->lognl_det[i];
+    return GWIN_OK;
+}
+
+extern "C" int gwin_plan_set_distance_marg(gwin_plan* p, int64_t n, const double* dist, const double* weight) {
+    if (!p) return fail(GWIN_EINVAL, "plan is NULL");
+    if (n < 0 || n > (1 << 24)) return fail(GWIN_EINVAL, "distance grid size out of range");
+    if (n && (!dist || !weight)) return fail(GWIN_EINVAL, "dist/weight is NULL");
+    std::vector<double> u((size_t)n), lw((size_t)n);
+    for (int64_t j = 0; j < n; ++j) {
+        if (!(dist[j] > 0.0) || !std::isfinite(dist[j])) return fail(GWIN_EINVAL, "dist[%lld] must be positive and finite", (long long)j);
+        if (!(weight[j] >= 0.0) || !std::isfinite(weight[j])) return fail(GWIN_EINVAL, "weight[%lld] must be finite and >= 0", (long long)j);
+        u[j] = 1.0 / dist[j];
+        lw[j] = weight[j] > 0.0 ? std::log(weight[j]) : -INFINITY;
+    }
+    CK(cudaSetDevice(p->device));
+    CK(cudaDeviceSynchronize());
+    cudaFree(p->d_marg_u); cudaFree(p->d_marg_logw);
+    p->d_marg_u = p->d_marg_logw = nullptr; p->n_marg = 0;
+    if (n == 0) return GWIN_OK;
+    CK(cudaMalloc(&p->d_marg_u, sizeof(double) * n));
+    CK(cudaMalloc(&p->d_marg_logw, sizeof(double) * n));
+    CK(cudaMemcpy(p->d_marg_u, u.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(p->d_marg_logw, lw.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+    p->n_marg = (int)n;
     return GWIN_OK;
 }
 
@@ -1320,7 +1388,8 @@ static int ensure_workspace(gwin_plan* p, int64_t W, int n_chunks) {
         cap = (cap + CTA_THREADS - 1) / CTA_THREADS * CTA_THREADS;
         cudaFree(p->d_wc); cudaFree(p->d_ks); cudaFree(p->d_ke);
         cudaFree(p->d_key_in); cudaFree(p->d_key_out); cudaFree(p->d_perm_in); cudaFree(p->d_perm_out);
-        cudaFree(p->d_cub);
+        cudaFree(p->d_cub); cudaFree(p->d_marg_opt);
+        p->d_marg_opt = nullptr;
         p->d_wc = nullptr; p->d_ks = p->d_ke = p->d_key_in = p->d_key_out = p->d_perm_in = p->d_perm_out = nullptr;
         p->d_cub = nullptr; p->w_cap = 0;
         // coefficient rows + n_det rows of hh
@@ -1331,6 +1400,7 @@ static int ensure_workspace(gwin_plan* p, int64_t W, int n_chunks) {
         CK(cudaMalloc(&p->d_key_out, sizeof(int) * cap));
         CK(cudaMalloc(&p->d_perm_in, sizeof(int) * cap));
         CK(cudaMalloc(&p->d_perm_out, sizeof(int) * cap));
+        CK(cudaMalloc(&p->d_marg_opt, sizeof(double) * cap));
         p->cub_bytes = 0;
         CK(cub::DeviceRadixSort::SortPairs(nullptr, p->cub_bytes, p->d_key_in, p->d_key_out,
                                            p->d_perm_in, p->d_perm_out, (int)cap, 0, 23));
@@ -1382,7 +1452,9 @@ extern "C" int gwin_loglr_batch_strided(gwin_plan* p, int mode, int64_t W64,
                                         double* loglr, double* hd, double* hh, void* stream) {
     if (!p) return fail(GWIN_EINVAL, "plan is NULL");
     if (stride_walker < 1 || stride_param < 1) return fail(GWIN_EINVAL, "parameter strides must be >= 1");
-    if (mode != GWIN_MODE_GAUSSIAN && mode != GWIN_MODE_MARG_PHASE) return fail(GWIN_EINVAL, "bad mode %d", mode);
+    if (mode < GWIN_MODE_GAUSSIAN || mode > GWIN_MODE_MARG_DIST_PHASE) return fail(GWIN_EINVAL, "bad mode %d", mode);
+    if (mode >= GWIN_MODE_MARG_DIST && p && p->n_marg == 0)
+        return fail(GWIN_EINVAL, "distance marginalisation needs gwin_plan_set_distance_marg first");
     if (W64 < 0 || W64 > (1 << 26)) return fail(GWIN_EINVAL, "W out of range");
     p->last_launches = 0;
     if (W64 == 0) return GWIN_OK;
@@ -1447,8 +1519,12 @@ extern "C" int gwin_loglr_batch_strided(gwin_plan* p, int mode, int64_t W64,
     combine_kernel<<<(W + 31) / 32, dim3(32, COMB_SEG), 0, st>>>(nd, W, wpad, n_chunks, mode, per_chunk, p->n_blk,
                                                                  recur ? p->d_blk_start : nullptr, band0, d.kmax,
                                                                  perm, p->d_wc, p->d_ks, p->d_ke,
-                                                                 p->d_partial, hh_rows, loglr, hd, hh);
+                                                                 p->d_partial, hh_rows, loglr, hd, hh, p->d_marg_opt);
     p->last_launches += 3;
+    if (mode >= GWIN_MODE_MARG_DIST) {
+        marg_dist_kernel<<<(W + 7) / 8, 256, 0, st>>>(W, p->n_marg, p->d_marg_u, p->d_marg_logw, p->d_marg_opt, loglr);
+        p->last_launches += 1;
+    }
     CK(cudaGetLastError());
     return GWIN_OK;
 }

@@ -62,7 +62,7 @@ class _BoundedDist(object):
         ok = True
         for p, b in self._bounds.items():
             x = numpy.asarray(kwargs[p], dtype=float)
-            ok = ok & (x >= b.min) & (x <= b.max)
+            ok = ok & (x >= b.min) & (x < b.max)     # [UPSTREAM] pycbc Bounds: closed/open
         return ok
 
     def apply_boundary_conditions(self, **kwargs):

@@ -1,10 +1,12 @@
-"""Phase-marginalised Gaussian-noise likelihood.
+"""Gaussian-noise likelihood marginalised over phase and/or distance.
 
 Reference: ``gwin/models/marginalized_gaussian_noise.py`` -- constructor
-:232-272, ``_margphase_loglr`` :456-459, ``_loglr`` :461-511.  Only the *phase*
-branch is on the accelerated path: time
-marginalisation needs an FFT matched filter and distance marginalisation a
-1e4-point grid, neither of which ``north_star`` names; asking for them raises.
+:232-272, ``_setup_prior`` :355-389, ``_margdistphase_loglr`` :431-439,
+``_margdist_loglr`` :441-448, ``_margphase_loglr`` :456-459, ``_loglr`` :461-511.
+The phase, distance and distance+phase branches run on the CUDA path (the
+distance grid is a second small kernel after the inner products, one warp per
+walker over the reference's 10**4-point grid).  Time marginalisation needs an
+FFT matched filter -- a different hot path -- and raises.
 
 ``MarginalizedPhaseGaussianNoise`` is the later ``pycbc.inference`` spelling of
 the same model; it is the phase branch without the (unused, see reference
@@ -38,10 +40,13 @@ class MarginalizedGaussianNoise(GaussianNoise):
             raise AttributeError("This class requires that you marginalize "
                                  "over at least one parameter. You have not "
                                  "marginalized over any.")
-        if self._margtime or self._margdist:
+        if self._margtime:
             raise NotImplementedError(
-                "only phase marginalization runs on the CUDA path; time and "
-                "distance marginalization are out of scope (SURVEY.md 2, row 2)")
+                "time marginalization (an FFT matched filter per point) is not "
+                "on the CUDA path; phase and distance marginalization are")
+        self._mode = {(1, 1, 0): _lib.MODE_MARG_DIST_PHASE,
+                      (1, 0, 0): _lib.MODE_MARG_DIST,
+                      (0, 1, 0): _lib.MODE_MARG_PHASE}[self._args]
         if marg_prior is None:
             raise AttributeError("No priors are specified for the "
                                  "marginalization. This is needed to "
@@ -51,8 +56,9 @@ class MarginalizedGaussianNoise(GaussianNoise):
         self._setup_prior()
 
     def _setup_prior(self):
-        """Reference :355-389.  The phase prior grid is built for parity of
-        attributes only -- the reference never uses it (flat prior assumed)."""
+        """Reference :355-389.  The distance grid and ``deltad * dist_prior``
+        go to the plan; the phase prior grid is built for parity of attributes
+        only -- the reference never uses it (flat prior assumed)."""
         if len(self._marg_prior) == 0:
             raise ValueError("A prior must be specified for the parameters "
                              "that you wish to marginalize the likelihood "
@@ -61,12 +67,23 @@ class MarginalizedGaussianNoise(GaussianNoise):
         if len(self._marg_prior) != marg_number:
             raise AttributeError("There is not a prior for each keyword "
                                  "argument")
-        bounds = self._marg_prior["phase"].bounds
-        self._phase_array = numpy.linspace(bounds["phase"].min,
-                                           bounds["phase"].max, 10**4)
-        self._deltap = self._phase_array[1] - self._phase_array[0]
-        self.phase_prior = numpy.asarray(
-            self._marg_prior["phase"].pdf(phase=self._phase_array))
+        if self._margdist:
+            bounds = self._marg_prior["distance"].bounds
+            self._dist_array = numpy.linspace(bounds["distance"].min,
+                                              bounds["distance"].max, 10**4)
+            self._deltad = self._dist_array[1] - self._dist_array[0]
+            self.dist_prior = numpy.asarray(
+                self._marg_prior["distance"].pdf(distance=self._dist_array),
+                dtype=float)
+            self._plan.set_distance_marg(self._dist_array,
+                                         self._deltad * self.dist_prior)
+        if self._margphase:
+            bounds = self._marg_prior["phase"].bounds
+            self._phase_array = numpy.linspace(bounds["phase"].min,
+                                               bounds["phase"].max, 10**4)
+            self._deltap = self._phase_array[1] - self._phase_array[0]
+            self.phase_prior = numpy.asarray(
+                self._marg_prior["phase"].pdf(phase=self._phase_array))
 
     @property
     def _extra_stats(self):

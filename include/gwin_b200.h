@@ -34,6 +34,12 @@ extern "C" {
 #define GWIN_MODE_GAUSSIAN     0  /* gaussian_noise.py:304-350:  sum_det Re<d|h> - <h|h>/2        */
 #define GWIN_MODE_MARG_PHASE   1  /* marginalized_gaussian_noise.py:456-459, 461-511:
                                      log I0(|sum_det <d|h>|) - sum_det <h|h>/2                     */
+#define GWIN_MODE_MARG_DIST    2  /* marginalized_gaussian_noise.py:441-448 (_margdist_loglr):
+                                     logsumexp_j(mf/D_j - opt/(2 D_j^2), b = w_j),
+                                     mf = |sum_det <d|h>|, opt = sum_det <h|h>                     */
+#define GWIN_MODE_MARG_DIST_PHASE 3 /* :431-439 (_margdistphase_loglr): as above with
+                                     log I0(mf) in place of mf (the reference divides the LOG
+                                     by D_j; kept)                                                  */
 
 /* kernel selection (diagnostic; production uses GWIN_KERNEL_AUTO) */
 #define GWIN_KERNEL_AUTO       0
@@ -82,6 +88,15 @@ int gwin_plan_lognl(const gwin_plan* plan, double* lognl_total, double* lognl_de
  * error [rad] of the recurrence kernel (default 1e-11), mchirp_min [Msun] =
  * smallest chirp mass the block schedule must cover (default 0.5). */
 int gwin_plan_configure(gwin_plan* plan, int kernel, double phase_tol, double mchirp_min);
+
+/*
+ * Distance-marginalisation grid == MarginalizedGaussianNoise._setup_prior
+ * (marginalized_gaussian_noise.py:368-375): dist[n] = numpy.linspace(min, max, 10**4),
+ * weight[n] = deltad * dist_prior[j] (the ``b`` of the reference's logsumexp; entries
+ * that are 0 drop out).  HOST pointers, copied.  Required before a call with
+ * GWIN_MODE_MARG_DIST / GWIN_MODE_MARG_DIST_PHASE; n = 0 clears it.
+ */
+int gwin_plan_set_distance_marg(gwin_plan* plan, int64_t n, const double* dist, const double* weight);
 
 /*
  * One batched evaluation of GaussianNoise._loglr / MarginalizedGaussianNoise._loglr

@@ -464,7 +464,8 @@ def log_i0(x):
 
 class GaussianNoiseOracle(object):
     """Follows gwin/models/gaussian_noise.py:219-350 (and, for
-    ``phase_marginalization=True``, marginalized_gaussian_noise.py:456-511).
+    ``phase_marginalization=True`` / ``distance_marginalization=(grid, weights)``,
+    marginalized_gaussian_noise.py:431-511; time marginalisation is not restated).
 
     data : dict det -> complex128 array (frequency series, bin spacing delta_f)
     psds : dict det -> float64 array or None
@@ -472,8 +473,10 @@ class GaussianNoiseOracle(object):
 
     def __init__(self, data, delta_f, epoch, f_lower, psds=None, f_upper=None,
                  norm=None, phase_marginalization=False, mode="faithful",
-                 waveform_f_lower=None):
+                 waveform_f_lower=None, distance_marginalization=None):
         self.mode = mode
+        # marginalized_gaussian_noise.py:368-375: (dist_array, deltad * dist_prior)
+        self.distance_marginalization = distance_marginalization
         self.dets = list(data.keys())
         # base_data.py:87 -- the model keeps a copy
         self._data = OrderedDict(
@@ -537,7 +540,16 @@ class GaussianNoiseOracle(object):
                 hw = h[slc] * self._weight[det][slc]
                 hd[det] = _inner(self._data[det][slc], hw, self.mode)
                 hh[det] = _inner(hw, hw, self.mode).real
-        if self.phase_marginalization:
+        if self.distance_marginalization is not None:
+            # marginalized_gaussian_noise.py:431-448 (_margdistphase_loglr / _margdist_loglr),
+            # with mf_snr = abs(sum hd) for both (:508) and scipy's logsumexp as there
+            from scipy import special
+            dist, b = self.distance_marginalization
+            mf = abs(sum(hd.values()))
+            x = log_i0(mf) if self.phase_marginalization else mf
+            with np.errstate(divide="ignore"):
+                lr = special.logsumexp(x / dist - 0.5 * sum(hh.values()) / dist ** 2, b=b)
+        elif self.phase_marginalization:
             mf = abs(sum(hd.values()))
             lr = log_i0(mf) - 0.5 * sum(hh.values())
         else:

@@ -105,6 +105,36 @@ def test_marginalized_model_reference_kwargs(cfg):
     assert abs(model.loglr - lr0) <= 1e-6
 
 
+@pytest.mark.parametrize("phase", [False, True])
+def test_distance_marginalized_model(cfg, phase):
+    """marginalized_gaussian_noise.py:232-272, 355-389, 431-448 through the model protocol."""
+    priors = [D.Uniform(distance=(50, 5000))] + ([D.UniformAngle(phase=None)] if phase else [])
+    model = cfg.cuda_model(cls=models.MarginalizedGaussianNoise, distance_marginalization=True,
+                           phase_marginalization=phase, marg_prior=priors)
+    assert model._dist_array.shape == (10 ** 4,) and model.dist_prior[-1] == 0.
+    orc = cfg.oracle(phase_marginalization=phase,
+                     distance_marginalization=(model._dist_array, model._deltad * model.dist_prior))
+    p = dict(cfg.inj, distance=1.0)
+    model.update(**p)
+    lr0, hd0, hh0 = orc.loglr(**p)
+    assert abs(model.loglr - lr0) <= tol(lr0)
+    assert abs(model.loglikelihood - (lr0 + orc.lognl())) <= 1e-9 * abs(orc.lognl())
+    st = model.current_stats
+    for det in cfg.dets:
+        assert abs(st['%s_optimal_snrsq' % det] - hh0[det]) <= 1e-9 * hh0[det]
+        assert abs(st['%s_matchedfilter_snrsq' % det] - hd0[det]) <= 2e-9 * hh0[det]
+    # batch protocol
+    rng = np.random.default_rng(5)
+    P = util.draw_bbh(rng, 8, cfg)
+    P[:, 4] = 1.0
+    res = models.CallModel(model, "loglr", return_all_stats=False).batch(P)
+    ref = [orc.loglr(**dict(zip(PARAM_ORDER, row)))[0] for row in P]
+    assert np.all(np.abs(res.values - ref) <= tol(np.array(ref)))
+    with pytest.raises(AttributeError):    # one prior per marginalised parameter (:364-366)
+        cfg.cuda_model(cls=models.MarginalizedGaussianNoise, distance_marginalization=True,
+                       phase_marginalization=True, marg_prior=[D.Uniform(distance=(50, 5000))])
+
+
 def test_pool_map_equals_scalar_calls(cfg):
     prior = D.JointDistribution(
         ['tc', 'distance', 'inclination'],

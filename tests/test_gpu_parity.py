@@ -306,6 +306,78 @@ def test_tidal_deformabilities(cfg3):
     assert np.all(np.abs(vals - ref) <= tol(np.array(ref)))
 
 
+def _dist_grid(lo=50., hi=5000., n=10 ** 4):
+    """marginalized_gaussian_noise.py:368-375 with Uniform(distance=(lo, hi)): the prior is 0
+    at the closed-open upper bound, i.e. on the last grid point."""
+    dist = np.linspace(lo, hi, n)
+    b = (dist[1] - dist[0]) * np.where(dist < hi, 1. / (hi - lo), 0.)
+    return dist, b
+
+
+@pytest.mark.parametrize("phase", [False, True])
+def test_distance_marginalization(cfg2, phase):
+    """GWIN_MODE_MARG_DIST / _DIST_PHASE against the oracle's scipy logsumexp, for templates
+    at 1 Mpc (what the reference's x / D_j scaling means) and at their drawn distances (what
+    the reference's own test does, test/test_models.py:122-145)."""
+    model = cfg2.cuda_model()
+    dist, b = _dist_grid()
+    model.plan.set_distance_marg(dist, b)
+    orc = cfg2.oracle(phase_marginalization=phase, distance_marginalization=(dist, b))
+    rng = np.random.default_rng(77)
+    P = util.draw_bbh(rng, 12, cfg2)
+    P1 = P.copy()
+    P1[:, 4] = 1.0
+    P1[:3, 4] = 0.02                    # absurdly loud: the sum is dominated by the far end
+    mode = 3 if phase else 2
+    for what, Q in (("drawn", P), ("1 Mpc", P1)):
+        lr0, hd0, hh0 = _oracle_batch(orc, Q)
+        for kernel in (1, 2):
+            model.plan.configure(kernel=kernel)
+            lr, hd, hh = model.plan.loglr_host(Q, mode=mode)
+            _check(lr, hd, hh, lr0, hd0, hh0, "margdist %s k%d" % (what, kernel))
+    model.plan.configure(kernel=0)
+    assert np.ptp(lr0) > 10.
+    # skipped / invalid walkers stay -inf, no NaN
+    Q = P1.copy()
+    Q[1, 0] = np.nan
+    skip = np.zeros(len(Q), np.uint8)
+    skip[2] = 1
+    lr = model.plan.loglr_host(Q, mode=mode, skip=skip)[0]
+    assert lr[1] == -np.inf and lr[2] == -np.inf and np.all(np.isfinite(np.delete(lr, [1, 2])))
+    # the grid is required, and clearing it brings the error back
+    model.plan.set_distance_marg(np.empty(0), np.empty(0))
+    with pytest.raises(ValueError):
+        model.plan.loglr_host(P, mode=mode)
+
+
+def test_reference_tc_grid_argmax_distance_marginalized():
+    """The reference's second numeric pin (test/test_models.py:122-145 inheriting :105-117):
+    MarginalizedGaussianNoise(distance_marginalization=True, Uniform(distance=(50, 5000)))
+    peaks at tc = 3.1 on the same grid."""
+    from gwin_b200 import distributions as D
+    from gwin_b200 import models
+    inj = dict(util.BBH_INJ)
+    inj["tc"] = 3.1
+    cfg = util.Config("ref", 4, 2048., 30., ["H1", "L1", "V1"], inj, noise=False)
+    model = cfg.cuda_model(cls=models.MarginalizedGaussianNoise, variable_params=("tc",),
+                           static_params={k: v for k, v in inj.items() if k != "tc"},
+                           distance_marginalization=True,
+                           marg_prior=[D.Uniform(distance=(50, 5000))])
+    times = 1.1 + np.arange(8192) / 2048.
+    call = models.CallModel(model, "logplr", return_all_stats=False)
+    for callstat in ("logplr", "logposterior"):
+        call.callstat = callstat
+        vals = call.batch(times[:, None]).values
+        assert np.isclose(times[np.argmax(vals)], 3.1)
+    dist, b = _dist_grid()
+    assert np.array_equal(model._dist_array, dist) and np.allclose(model._deltad * model.dist_prior, b, rtol=1e-15)
+    orc = cfg.oracle(distance_marginalization=(dist, b))
+    call.callstat = "loglr"
+    for t in (3.1, 2.4):
+        lr0 = orc.loglr(**dict(inj, tc=t))[0]
+        assert abs(call([t]) - lr0) <= tol(lr0)
+
+
 def test_four_detectors_and_large_batch():
     """n_det = 4 (the narrower TMA tile variant of the kernels) and a 100k-walker batch that
     grows the workspace: both kernels against the oracle on a sample and against each other on

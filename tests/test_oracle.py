@@ -244,6 +244,31 @@ def test_tidal_terms():
     assert np.max(np.abs(ref[0] - got[0])) < 1e-7 and np.allclose(ref[2], got[2], rtol=1e-12)
 
 
+def test_distance_marginalization_restatement():
+    """marginalized_gaussian_noise.py:431-448: the oracle's logsumexp equals the plain sum
+    where that does not overflow, is the log of the prior-weighted integral of exp(x/D - opt/2D^2)
+    (trapezoid check on a smooth case), and the phase variant divides log I0 by D as the
+    reference does."""
+    from scipy import special
+    cfg = util.c1()
+    dist = np.linspace(50., 5000., 10 ** 4)
+    b = (dist[1] - dist[0]) * np.where(dist < 5000., 1. / 4950., 0.)
+    p = dict(cfg.inj, distance=1.0)
+    plain = cfg.oracle()
+    _, hd, hh = plain.loglr(**p)
+    mf, opt = abs(sum(hd.values())), sum(hh.values())
+    for phase in (False, True):
+        orc = cfg.oracle(phase_marginalization=phase, distance_marginalization=(dist, b))
+        lr = orc.loglr(**p)[0]
+        x = O.log_i0(mf) if phase else mf
+        a = x / dist - 0.5 * opt / dist ** 2
+        assert abs(lr - (a.max() + np.log(np.sum(b * np.exp(a - a.max()))))) < 1e-10
+        assert np.isfinite(lr) and lr > 0.5 * a.max()
+    # a quiet template: exp(a) ~ 1, the integral of the prior ~ 1 - one grid cell
+    q = dict(cfg.inj, distance=1e8)
+    assert abs(cfg.oracle(distance_marginalization=(dist, b)).loglr(**q)[0]) < 1e-3
+
+
 def test_spin_terms_known_limits():
     """1.5PN spin-orbit: equal masses, equal spins => 4 beta = (188/6) chi."""
     a = O.taylorf2_phasing(10., 10., 0.3, 0.3)
