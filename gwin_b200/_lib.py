@@ -35,6 +35,8 @@ KERNEL_AUTO, KERNEL_DIRECT, KERNEL_RECURRENCE = 0, 1, 2
 SYMBOLS = (
     "gwin_plan_create", "gwin_plan_destroy", "gwin_plan_cutoffs",
     "gwin_plan_lognl", "gwin_plan_configure", "gwin_plan_set_distance_marg",
+    "gwin_plan_set_calibration", "gwin_loglr_batch_calib",
+    "gwin_loglr_batch_calib_host", "gwin_generate_calib_host",
     "gwin_loglr_batch",
     "gwin_loglr_batch_host", "gwin_loglr_batch_strided",
     "gwin_loglr_batch_host_strided", "gwin_generate_host",
@@ -123,6 +125,21 @@ def load():
         lib.gwin_plan_set_distance_marg.restype = C.c_int
         lib.gwin_plan_set_distance_marg.argtypes = [C.c_void_p, C.c_int64,
                                                     C.c_void_p, C.c_void_p]
+        lib.gwin_plan_set_calibration.restype = C.c_int
+        lib.gwin_plan_set_calibration.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        lib.gwin_loglr_batch_calib.restype = C.c_int
+        lib.gwin_loglr_batch_calib.argtypes = [
+            C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
+            C.c_void_p, C.c_int64, C.c_int64,
+            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.gwin_loglr_batch_calib_host.restype = C.c_int
+        lib.gwin_loglr_batch_calib_host.argtypes = [
+            C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
+            C.c_void_p, C.c_int64, C.c_int64,
+            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.gwin_generate_calib_host.restype = C.c_int
+        lib.gwin_generate_calib_host.argtypes = [C.c_void_p, dp, C.c_void_p, dp,
+                                                 C.POINTER(C.c_int64)]
         lib.gwin_plan_configure.restype = C.c_int
         lib.gwin_plan_configure.argtypes = [C.c_void_p, C.c_int, C.c_double,
                                             C.c_double]
@@ -212,6 +229,7 @@ class Plan(object):
         self._lib = lib
         self.device = int(device)
         self.n_det = int(n_det)
+        self.n_cal = 0
         self.n_f = int(n_f)
         kmin, kmax = C.c_int64(), C.c_int64()
         check(lib.gwin_plan_cutoffs(self._h, C.byref(kmin), C.byref(kmax)))
@@ -247,6 +265,21 @@ class Plan(object):
         check(self._lib.gwin_plan_set_distance_marg(
             self._h, dist.size, dist.ctypes.data, weight.ctypes.data))
 
+    def set_calibration(self, spline_freqs):
+        """``spline_freqs`` [n_det, n_points]: ``CubicSpline.spline_points`` of
+        every detector, plan detector order; ``None`` clears.  See
+        ``gwin_plan_set_calibration``."""
+        if spline_freqs is None:
+            check(self._lib.gwin_plan_set_calibration(self._h, 0, None))
+            self.n_cal = 0
+            return
+        sf = np.ascontiguousarray(spline_freqs, dtype=np.float64)
+        if sf.ndim != 2 or sf.shape[0] != self.n_det:
+            raise ValueError("spline_freqs must be [n_det, n_points]")
+        check(self._lib.gwin_plan_set_calibration(self._h, sf.shape[1],
+                                                  sf.ctypes.data))
+        self.n_cal = sf.shape[1]
+
     @property
     def last_launches(self):
         return self._lib.gwin_plan_last_launches(self._h)
@@ -260,10 +293,11 @@ class Plan(object):
         return ms.value, n.value
 
     def loglr_host(self, params, mode=MODE_GAUSSIAN, skip=None,
-                   param_major=False):
+                   param_major=False, calib=None):
         """params: [W, 13] float64 host array, or [13, W] with
-        ``param_major=True``.  Returns loglr[W], hd[W, n_det] complex128,
-        hh[W, n_det]."""
+        ``param_major=True``; ``calib``: optional calibration values in the same
+        orientation, [W, n_det * 2 * n_points] (or its transpose).  Returns
+        loglr[W], hd[W, n_det] complex128, hh[W, n_det]."""
         params = np.ascontiguousarray(params, dtype=np.float64)
         if param_major:
             if params.ndim != 2 or params.shape[0] != GWIN_NPARAM:
@@ -283,6 +317,19 @@ class Plan(object):
             sk = np.ascontiguousarray(skip, dtype=np.uint8)
             if sk.shape != (W,):
                 raise ValueError("skip must be [W]")
+        if calib is not None:
+            nv = self.n_det * 2 * self.n_cal
+            calib = np.ascontiguousarray(calib, dtype=np.float64)
+            if calib.shape != ((nv, W) if param_major else (W, nv)) or nv == 0:
+                raise ValueError("calib must be [W, %d] (transposed with "
+                                 "param_major) after set_calibration" % nv)
+            csw, csv = (1, W) if param_major else (nv, 1)
+            check(self._lib.gwin_loglr_batch_calib_host(
+                self._h, int(mode), W, params.ctypes.data, sw, si,
+                calib.ctypes.data, csw, csv,
+                sk.ctypes.data if sk is not None else None,
+                loglr.ctypes.data, hd.ctypes.data, hh.ctypes.data))
+            return loglr, hd, hh
         check(self._lib.gwin_loglr_batch_host_strided(
             self._h, int(mode), W, params.ctypes.data, sw, si,
             sk.ctypes.data if sk is not None else None,
@@ -290,11 +337,12 @@ class Plan(object):
         return loglr, hd, hh
 
     def loglr_device(self, params, mode=MODE_GAUSSIAN, skip=None, out=None,
-                     stream=None):
+                     stream=None, calib=None):
         """Device-resident variant: ``params`` is a CUDA float64 torch tensor
-        [W, 13]; returns torch tensors (loglr, hd[W,n_det,2], hh) on the same
-        device.  Asynchronous on ``stream`` (default: torch's current stream).
-        torch is only the owner of the device memory here."""
+        [W, 13] (``calib``: optional [W, n_det * 2 * n_points]); returns torch
+        tensors (loglr, hd[W,n_det,2], hh) on the same device.  Asynchronous on
+        ``stream`` (default: torch's current stream).  torch is only the owner
+        of the device memory here."""
         import torch
         if not params.is_cuda or params.dtype != torch.float64:
             raise ValueError("params must be a CUDA float64 tensor")
@@ -313,21 +361,38 @@ class Plan(object):
         sk = None
         if skip is not None:
             sk = skip.to(torch.uint8).contiguous()
+        if calib is not None:
+            nv = self.n_det * 2 * self.n_cal
+            if (not calib.is_cuda or calib.dtype != torch.float64
+                    or tuple(calib.shape) != (W, nv) or nv == 0):
+                raise ValueError("calib must be a CUDA float64 tensor [W, %d] "
+                                 "after set_calibration" % nv)
+            calib = calib.contiguous()
+            check(self._lib.gwin_loglr_batch_calib(
+                self._h, int(mode), W, params.data_ptr(), GWIN_NPARAM, 1,
+                calib.data_ptr(), nv, 1,
+                sk.data_ptr() if sk is not None else None,
+                loglr.data_ptr(), hd.data_ptr(), hh.data_ptr(), stream))
+            return loglr, hd, hh
         check(self._lib.gwin_loglr_batch(
             self._h, int(mode), W, params.data_ptr(),
             sk.data_ptr() if sk is not None else None,
             loglr.data_ptr(), hd.data_ptr(), hh.data_ptr(), stream))
         return loglr, hd, hh
 
-    def generate(self, params):
+    def generate(self, params, calib=None):
         """One detector-frame waveform set: returns (h[n_det, n_f] complex128,
-        length)."""
+        length).  ``calib``: optional [n_det * 2 * n_points] calibration values."""
         p = np.ascontiguousarray(params, dtype=np.float64).reshape(GWIN_NPARAM)
         h = np.zeros((self.n_det, self.n_f), dtype=np.complex128)
         n = C.c_int64()
-        check(self._lib.gwin_generate_host(self._h, _dptr(p),
-                                           _dptr(h.view(np.float64)),
-                                           C.byref(n)))
+        cv = None
+        if calib is not None:
+            cv = np.ascontiguousarray(calib, dtype=np.float64).reshape(
+                self.n_det * 2 * self.n_cal)
+        check(self._lib.gwin_generate_calib_host(
+            self._h, _dptr(p), cv.ctypes.data if cv is not None else None,
+            _dptr(h.view(np.float64)), C.byref(n)))
         return h, n.value
 
 

@@ -65,7 +65,9 @@ enum {
     C_A0 = 0, C_A2, C_A3, C_A4, C_A5, C_B5, C_A6, C_B6, C_A7, C_A10, C_A12,   // phase [turns]
     C_DET0                                                        // then 4 per detector
 };
-enum { D_TAUHI = 0, D_TAULO, D_ARE, D_AIM, D_ECOS, D_ESIN, D_NROW };   // E = e^{+2 pi i tau}
+enum { D_TAUHI = 0, D_TAULO, D_ARE, D_AIM, D_ECOS, D_ESIN,               // E = e^{+2 pi i tau}
+       D_CA0, D_CA1, D_CA2, D_CA3, D_CP0, D_CP1, D_CP2, D_CP3,           // calibration cubics (amplitude, phase) in z
+       D_NROW };
 #define NCOEF(nd) (C_DET0 + D_NROW * (nd))
 
 static thread_local char g_err[512] = "";
@@ -95,6 +97,11 @@ struct PlanDev {
     const double4* basis;    // [n_f] {f^(1/3), f^(-5/3), ln f^(1/3), 0}
     const double2* T;        // [n_f][n_det] norm*conj(d)*f^(-7/6)/S
     const double*  C;        // [n_det][n_f+1] prefix sums of norm*f^(-7/3)/S
+    // calibration (gwin_plan_set_calibration); n_cal = 0: none
+    int n_cal;               // spline points per detector
+    double cal_zs[GWIN_MAX_DET], cal_z0[GWIN_MAX_DET];   // z = k * zs + z0 maps the spline range to [-1, 1]
+    const double* calM;      // [n_det][4][n_cal] values -> least-squares cubic coefficients in z
+    const double* Ccal;      // [n_det][7][n_f+1] prefix sums of norm*f^(-7/3)/S * z^j
 };
 
 // Per distinct (block length, degree): node offsets and the linear map from the exact
@@ -135,6 +142,10 @@ struct gwin_plan {
     double2* d_partial;
     size_t partial_cap;
     void* d_cub; size_t cub_bytes;
+    // calibration: host copy of the per-bin <h|h> weights norm f^(-7/3)/S (for the z^j prefix tables)
+    std::vector<double> w73;
+    double *d_calM, *d_Ccal;
+    double *h_calib, *d_calib; size_t calib_cap;
     // distance marginalisation grid (1/D_j, log w_j) and the per-walker (x, opt) hand-over
     int n_marg;
     double *d_marg_u, *d_marg_logw, *d_marg_opt;
@@ -224,6 +235,31 @@ __device__ __forceinline__ double4 ld_basis(const double4* p) {
     return make_double4(a.x, a.y, b.x, b.y);
 }
 
+// Calibration factor of one detector (gwin/calibration.py:167-170):
+//   (1 + dA) (2 + i dphi) / (2 - i dphi),  dA, dphi cubic polynomials in z
+struct CalCoef { double a[4], p[4]; };
+__device__ __forceinline__ double2 calib_factor(const CalCoef& c, double z) {
+    const double A = fma(fma(fma(c.a[3], z, c.a[2]), z, c.a[1]), z, c.a[0]);
+    const double P = fma(fma(fma(c.p[3], z, c.p[2]), z, c.p[1]), z, c.p[0]);
+    const double P2 = P * P;
+    const double sc = (1.0 + A) / (4.0 + P2);
+    return make_double2(sc * (4.0 - P2), sc * (4.0 * P));
+}
+// log of the factor, split: re = log(1 + dA), im = 2 atan(dphi / 2) [rad]; amp = 1 + dA
+__device__ __forceinline__ double2 calib_log(const CalCoef& c, double z, double& amp) {
+    const double A = fma(fma(fma(c.a[3], z, c.a[2]), z, c.a[1]), z, c.a[0]);
+    const double P = fma(fma(fma(c.p[3], z, c.p[2]), z, c.p[1]), z, c.p[0]);
+    amp = 1.0 + A;
+    return make_double2(log1p(A), 2.0 * atan(0.5 * P));
+}
+__device__ __forceinline__ void load_cal_coef(CalCoef& c, const double* row /* detector's first row + walker */, int wpad) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        c.a[i] = row[(size_t)(D_CA0 + i) * wpad];
+        c.p[i] = row[(size_t)(D_CP0 + i) * wpad];
+    }
+}
+
 // TaylorF2 phase in turns at one bin, basis = {x, x^-5, ln x}
 struct PhaseCoef { double a0, a2, a3, a4, a5, b5, a6, b6, a7, a10, a12; };
 #define NPH 11                 // phase-coefficient rows
@@ -307,14 +343,17 @@ __global__ void walker_setup_kernel(PlanDev P, int W, int wpad,
                                     const int* __restrict__ perm,
                                     double* __restrict__ wc, int* __restrict__ ks_arr,
                                     int* __restrict__ ke_arr,
-                                    double* __restrict__ hh_sorted /*[n_det][wpad]*/) {
+                                    double* __restrict__ hh_sorted /*[n_det][wpad]*/,
+                                    const double* __restrict__ calib, int64_t csw, int64_t csi) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= W) return;
     const int w = perm ? perm[t] : t;
     double p[GWIN_NPARAM];
     load_params(p, params, w, sw, si);
     const int nd = P.n_det;
-    const bool ok = !(skip && skip[w]) && params_ok(p) && has_waveform(p, P.f_lower_wf);
+    bool ok = !(skip && skip[w]) && params_ok(p) && has_waveform(p, P.f_lower_wf);
+    if (calib && ok)
+        for (int v = 0; v < nd * 2 * P.n_cal; ++v) ok = ok && isfinite(calib[w * csw + v * csi]);
     if (!ok) {
         // no bins; combine() turns this into -inf via ks = -1
         ks_arr[t] = -1; ke_arr[t] = -1;
@@ -482,7 +521,36 @@ __global__ void walker_setup_kernel(PlanDev P, int W, int wpad,
         row[D_ESIN * wpad] = es;
         // <h|h> closed form: |A|^2 * sum_{ks<=k<ke} norm f^(-7/3)/S  (phase-free)
         double hh = 0.0;
-        if (ke > ks) {
+        if (calib) {
+            // least-squares cubics through the spline values (what the reference's
+            // UnivariateSpline(points, values) with its default smoothing returns)
+            const double* M = P.calM + (size_t)d * 4 * P.n_cal;
+            double b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double ca = 0.0, cp = 0.0;
+                for (int j = 0; j < P.n_cal; ++j) {
+                    const double m = M[i * P.n_cal + j];
+                    ca = fma(m, calib[w * csw + ((2 * d) * P.n_cal + j) * csi], ca);
+                    cp = fma(m, calib[w * csw + ((2 * d + 1) * P.n_cal + j) * csi], cp);
+                }
+                row[(size_t)(D_CA0 + i) * wpad] = ca;
+                row[(size_t)(D_CP0 + i) * wpad] = cp;
+                b[i] = ca;
+            }
+            if (ke > ks) {
+                // |1 + dA(z)|^2 is a sextic in z; |(2 + i dphi)/(2 - i dphi)| = 1
+                b[0] += 1.0;
+                const double q[7] = { b[0] * b[0], 2.0 * b[0] * b[1], fma(2.0 * b[0], b[2], b[1] * b[1]),
+                                      2.0 * fma(b[0], b[3], b[1] * b[2]), fma(2.0 * b[1], b[3], b[2] * b[2]),
+                                      2.0 * b[2] * b[3], b[3] * b[3] };
+                const double* C = P.Ccal + (size_t)d * 7 * (P.n_f + 1);
+                double sum = 0.0;
+#pragma unroll
+                for (int j = 0; j < 7; ++j) sum = fma(q[j], C[(size_t)j * (P.n_f + 1) + ke] - C[(size_t)j * (P.n_f + 1) + ks], sum);
+                hh = (are * are + aim * aim) * sum;
+            }
+        } else if (ke > ks) {
             const double* C = P.C + (size_t)d * (P.n_f + 1);
             hh = (are * are + aim * aim) * (C[ke] - C[ks]);
         }
@@ -496,7 +564,7 @@ __global__ void walker_setup_kernel(PlanDev P, int W, int wpad,
 // detector a delay-phasor recurrence (exact re-sync every RESYNC bins), a
 // rotation and a complex MAC against T.
 // ---------------------------------------------------------------------------
-template <int ND>
+template <int ND, bool CALIB>
 __global__ void __launch_bounds__(CTA_THREADS)
 loglr_direct_kernel(PlanDev P, int W, int wpad, int chunk_bins, int n_chunks,
                     const double* __restrict__ wc, const int* __restrict__ ks_arr,
@@ -526,6 +594,7 @@ loglr_direct_kernel(PlanDev P, int W, int wpad, int chunk_bins, int n_chunks,
         load_phase_coef(pc, wc, wpad, tt);
         double tau_hi[ND], tau_lo[ND];
         double2 step[ND], ph[ND];
+        CalCoef cal[CALIB ? ND : 1];
 #pragma unroll
         for (int d = 0; d < ND; ++d) {
             const double* row = wc + (size_t)(C_DET0 + D_NROW * d) * wpad + tt;
@@ -533,6 +602,7 @@ loglr_direct_kernel(PlanDev P, int W, int wpad, int chunk_bins, int n_chunks,
             tau_lo[d] = row[D_TAULO * wpad];
             step[d] = phasor_neg(tau_hi[d] + tau_lo[d]);
             ph[d] = make_double2(1.0, 0.0);
+            if (CALIB) load_cal_coef(cal[d], row, wpad);
         }
         const double4* __restrict__ basis = P.basis;
         const double2* __restrict__ T = P.T;
@@ -549,7 +619,8 @@ loglr_direct_kernel(PlanDev P, int W, int wpad, int chunk_bins, int n_chunks,
 #pragma unroll
             for (int d = 0; d < ND; ++d) {
                 const double2 Tk = __ldg(T + (size_t)k * ND + d);
-                const double2 wv = cmul(u, ph[d]);
+                double2 wv = cmul(u, ph[d]);
+                if (CALIB) wv = cmul(wv, calib_factor(cal[d], fma((double)k, P.cal_zs[d], P.cal_z0[d])));
                 if (on) acc[d] = cfma(Tk, wv, acc[d]);
                 ph[d] = cmul(ph[d], step[d]);
             }
@@ -580,6 +651,15 @@ loglr_direct_kernel(PlanDev P, int W, int wpad, int chunk_bins, int n_chunks,
 // sharing, hence no barrier): they are only needed in the per-block set-up, and keeping
 // them out of the register file buys a third/fourth resident CTA per SM.
 #define RC_ROWS(nd) (NPH + 4 * (nd))
+#define RC_ROWS_CAL(nd) (RC_ROWS(nd) + 8 * (nd))       // + calibration cubics: a0..a3, p0..p3 per detector
+template <int ND>
+__device__ __forceinline__ void load_block_cal(const double* sc, int d, CalCoef& c) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        c.a[i] = sc[(RC_ROWS(ND) + 8 * d + i) * CTA_THREADS];
+        c.p[i] = sc[(RC_ROWS(ND) + 8 * d + 4 + i) * CTA_THREADS];
+    }
+}
 template <int ND>
 __device__ __forceinline__ double2 load_E(const double* sc, int d) {       // e^{+2 pi i tau_d}
     return make_double2(sc[(NPH + 2 * ND + 2 * d) * CTA_THREADS], sc[(NPH + 1 + 2 * ND + 2 * d) * CTA_THREADS]);
@@ -676,8 +756,8 @@ struct TileStream {
     }
 };
 
-template <int ND>
-__device__ __forceinline__ void direct_block(const double* sc, const double4* __restrict__ basis,
+template <int ND, bool CALIB>
+__device__ __forceinline__ void direct_block(const PlanDev& P, const double* sc, const double4* __restrict__ basis,
                                              TileStream<ND>& S, int kb, int B, int lo, int hi,
                                              double2 (&acc_out)[ND]) {
     // too curved / too short for a polynomial block: evaluate these bins directly
@@ -692,10 +772,131 @@ __device__ __forceinline__ void direct_block(const double* sc, const double4* __
         const double kd = (double)k;
 #pragma unroll
         for (int d = 0; d < ND; ++d) {
-            const double2 u = phasor_neg(psi + fma(kd, tau_lo[d], frac1(kd * tau_hi[d])));
+            double2 u = phasor_neg(psi + fma(kd, tau_lo[d], frac1(kd * tau_hi[d])));
+            if (CALIB) {
+                CalCoef cc;
+                load_block_cal<ND>(sc, d, cc);
+                u = cmul(u, calib_factor(cc, fma(kd, P.cal_zs[d], P.cal_z0[d])));
+            }
             acc_out[d] = cfma(sp[d], u, acc_out[d]);
         }
     }
+}
+
+// Calibrated polynomial block.  The factor c_d(k) = exp(L_d(k)), L_d = log(1 + dA) + 2 i atan(dphi/2),
+// is smooth on the scale of a block, so L_d is sampled at the block's nodes and joins the block
+// polynomial: its imaginary part as a per-detector phase, its real part as a per-detector log
+// amplitude.  g, r, s, t become per-detector and non-unit; one bin costs 16 ND (quartic) or
+// 12 ND (cubic) FP64 issue slots.  Returns false -- having done nothing -- when some lane's
+// amplitude factor 1 + dA is not safely positive at a node (log undefined / not smooth): the
+// caller then evaluates the block bin by bin, which has no such restriction.
+template <int ND, bool MASKED, int DEG>
+__device__ __forceinline__ bool recur_block_cal(
+        const PlanDev& P, const double* sc, const double4* __restrict__ basis, TileStream<ND>& S,
+        const BlockMat* __restrict__ M, int kb, int B, int lo, int hi, double2 (&acc_out)[ND]) {
+    PhaseCoef pc;
+    double tau_hi[ND], tau_lo[ND];
+    load_block_coef<ND>(sc, pc, tau_hi, tau_lo);
+    const double f0 = phase_turns(pc, ld_basis(basis + kb));
+    double fn[DEG];
+#pragma unroll
+    for (int i = 0; i < DEG; ++i) fn[i] = phase_turns(pc, ld_basis(basis + kb + M->node[i]));
+    const double fend = fn[DEG - 1];
+    double D[4];
+#pragma unroll
+    for (int r = 0; r < DEG; ++r) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < DEG; ++i) acc = fma(M->m[4 * r + i], fn[i] - f0, acc);
+        D[r] = acc;
+    }
+    // per-detector differences of the log-calibration
+    double Dth[ND][4], Dam[ND][4], Lend_re[ND], Lend_im[ND];
+    bool bad = false;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        CalCoef cc;
+        load_block_cal<ND>(sc, d, cc);
+        double amp;
+        const double2 L0 = calib_log(cc, fma((double)kb, P.cal_zs[d], P.cal_z0[d]), amp);
+        bad = bad || !(amp > 0.25);
+        double2 Ln[DEG];
+#pragma unroll
+        for (int i = 0; i < DEG; ++i) {
+            Ln[i] = calib_log(cc, fma((double)(kb + M->node[i]), P.cal_zs[d], P.cal_z0[d]), amp);
+            bad = bad || !(amp > 0.25);
+        }
+#pragma unroll
+        for (int r = 0; r < DEG; ++r) {
+            double are = 0.0, aim = 0.0;
+#pragma unroll
+            for (int i = 0; i < DEG; ++i) {
+                are = fma(M->m[4 * r + i], Ln[i].x - L0.x, are);
+                aim = fma(M->m[4 * r + i], Ln[i].y - L0.y, aim);
+            }
+            Dam[d][r] = are;
+            Dth[d][r] = fma(aim, -1.0 / G_TWOPI, D[r]);      // theta' = theta - Im L / 2 pi  [turns]
+        }
+        Lend_re[d] = Ln[DEG - 1].x;
+        Lend_im[d] = Ln[DEG - 1].y;
+    }
+    if (__any_sync(0xffffffffu, bad)) return false;
+
+    double2 g[ND], rq[ND], sq[ND], tq[ND], acc[ND];
+    const double kend = (double)(kb + B - 1);
+    S.ensure(kb);
+    {
+        const double2* sp = S.row(kb);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            // Horner factor of bin j: exp(2 pi i dTheta'_j - dRe L_j)
+            double2 G = cmul(phasor_pos(Dth[d][0]), load_E<ND>(sc, d));
+            const double e1 = exp(-Dam[d][0]);
+            g[d] = make_double2(G.x * e1, G.y * e1);
+            double2 q = phasor_pos_small(Dth[d][1]);
+            const double e2 = exp(-Dam[d][1]);
+            rq[d] = make_double2(q.x * e2, q.y * e2);
+            q = phasor_pos_small(Dth[d][2]);
+            const double e3 = exp(-Dam[d][2]);
+            sq[d] = make_double2(q.x * e3, q.y * e3);
+            if (DEG == 4) {
+                q = phasor_pos_small(Dth[d][3]);
+                const double e4 = exp(-Dam[d][3]);
+                tq[d] = make_double2(q.x * e4, q.y * e4);
+            }
+            double2 T0 = sp[d];
+            if (MASKED && !(kb >= lo && kb < hi)) T0 = make_double2(0.0, 0.0);
+            acc[d] = T0;
+        }
+    }
+    int k = kb + 1;
+    const int kn = kb + B;
+    while (k < kn) {
+        S.ensure(k);
+        const int ke = min(kn, S.tile_end(k));
+        const double2* sp = S.row(k);
+#pragma unroll kRecurUnroll
+        for (; k < ke; ++k, sp += ND) {
+            const bool on = !MASKED || ((k >= lo) && (k < hi));
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                double2 Tk = sp[d];
+                if (MASKED && !on) Tk = make_double2(0.0, 0.0);
+                acc[d] = cfma(acc[d], g[d], Tk);
+                g[d] = cmul(g[d], rq[d]);
+                rq[d] = cmul(rq[d], sq[d]);
+                if (DEG == 4) sq[d] = cmul(sq[d], tq[d]);
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        const double anchor = fend + fma(kend, tau_lo[d], frac1(kend * tau_hi[d])) - Lend_im[d] * (1.0 / G_TWOPI);
+        const double2 a = phasor_neg(anchor);
+        const double e = exp(Lend_re[d]);
+        acc_out[d] = cfma(acc[d], make_double2(a.x * e, a.y * e), acc_out[d]);
+    }
+    return true;
 }
 
 template <int ND, bool MASKED, int DEG>
@@ -769,8 +970,8 @@ __device__ __forceinline__ void recur_block(
 #ifndef RECUR_MIN_CTAS
 #define RECUR_MIN_CTAS 3
 #endif
-template <int ND>
-__global__ void __launch_bounds__(CTA_THREADS, RECUR_MIN_CTAS)
+template <int ND, bool CALIB>
+__global__ void __launch_bounds__(CTA_THREADS, CALIB ? 2 : RECUR_MIN_CTAS)
 loglr_recur_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_blk,
                    const int* __restrict__ blk_start, const int* __restrict__ blk_mat,
                    const BlockMat* __restrict__ mats,
@@ -806,7 +1007,7 @@ loglr_recur_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_blk,
     extern __shared__ __align__(128) unsigned char s_dyn[];
     double2 (*s_tile)[2 * TILE * ND] = reinterpret_cast<double2 (*)[2 * TILE * ND]>(s_dyn);
     double* s_coef = reinterpret_cast<double*>(s_dyn + sizeof(double2) * NWARP * 2 * TILE * ND);
-    uint64_t (*s_bar)[2] = reinterpret_cast<uint64_t (*)[2]>(s_coef + RC_ROWS(ND) * CTA_THREADS);
+    uint64_t (*s_bar)[2] = reinterpret_cast<uint64_t (*)[2]>(s_coef + (CALIB ? RC_ROWS_CAL(ND) : RC_ROWS(ND)) * CTA_THREADS);
     if (wlo < whi) {
         const int tt = live ? t : 0;
         double* sc = s_coef + threadIdx.x;
@@ -819,6 +1020,11 @@ loglr_recur_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_blk,
             sc[(NPH + 1 + 2 * d) * CTA_THREADS] = row[D_TAULO * wpad];
             sc[(NPH + 2 * ND + 2 * d) * CTA_THREADS] = row[D_ECOS * wpad];
             sc[(NPH + 1 + 2 * ND + 2 * d) * CTA_THREADS] = row[D_ESIN * wpad];
+            if (CALIB) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    sc[(RC_ROWS(ND) + 8 * d + i) * CTA_THREADS] = row[(size_t)(D_CA0 + i) * wpad];
+            }
         }
         const int lane = threadIdx.x & (WARP - 1), warp = threadIdx.x / WARP;
         TileStream<ND> S;
@@ -850,14 +1056,19 @@ loglr_recur_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_blk,
             const BlockMat* M = mats + blk_mat[b];
             const int deg = M->deg;
             const bool full = kb >= ilo && kn <= ihi;       // every lane covers the whole block
-            if (deg == 4) {
+            if (CALIB) {
+                bool done = false;
+                if (deg == 4) done = recur_block_cal<ND, true, 4>(P, sc, P.basis, S, M, kb, kn - kb, lo, hi, acc);
+                else if (deg == 3) done = recur_block_cal<ND, true, 3>(P, sc, P.basis, S, M, kb, kn - kb, lo, hi, acc);
+                if (!done) direct_block<ND, true>(P, sc, P.basis, S, kb, kn - kb, lo, hi, acc);
+            } else if (deg == 4) {
                 if (full) recur_block<ND, false, 4>(sc, P.basis, S, M, kb, kn - kb, lo, hi, acc);
                 else      recur_block<ND, true, 4>(sc, P.basis, S, M, kb, kn - kb, lo, hi, acc);
             } else if (deg == 3) {
                 if (full) recur_block<ND, false, 3>(sc, P.basis, S, M, kb, kn - kb, lo, hi, acc);
                 else      recur_block<ND, true, 3>(sc, P.basis, S, M, kb, kn - kb, lo, hi, acc);
             } else {
-                direct_block<ND>(sc, P.basis, S, kb, kn - kb, lo, hi, acc);
+                direct_block<ND, false>(P, sc, P.basis, S, kb, kn - kb, lo, hi, acc);
             }
         }
         if (opened) S.close();
@@ -986,7 +1197,7 @@ marg_dist_kernel(int W, int n, const double* __restrict__ u, const double* __res
 // waveform dump (FDomainDetFrameGenerator.generate for one point)
 // ---------------------------------------------------------------------------
 __global__ void generate_kernel(PlanDev P, int wpad, const double* __restrict__ wc,
-                                const int* __restrict__ ke_arr, double2* __restrict__ out) {
+                                const int* __restrict__ ke_arr, double2* __restrict__ out, bool calibrated) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= P.n_f) return;
     PhaseCoef pc;
@@ -1005,6 +1216,11 @@ __global__ void generate_kernel(PlanDev P, int wpad, const double* __restrict__ 
             const double a = pow(f, -7.0 / 6.0);
             const double2 A = make_double2(row[D_ARE * wpad] * a, row[D_AIM * wpad] * a);
             h = cmul(A, u);
+            if (calibrated) {
+                CalCoef cc;
+                load_cal_coef(cc, row, wpad);
+                h = cmul(h, calib_factor(cc, fma(kd, P.cal_zs[d], P.cal_z0[d])));
+            }
         }
         out[(size_t)d * P.n_f + k] = h;
     }
@@ -1247,18 +1463,22 @@ extern "C" int gwin_plan_create(gwin_plan** out, int device, int n_det, int64_t 
             f76[k] = 1.0L / sqrtl(x7);          // f^(-7/6)
         }
     }
+    p->w73.assign((size_t)n_det * n_f, 0.0);
     for (int det = 0; det < n_det; ++det) {
         long double csum = 0.0L, nl = 0.0L;
         const double* dd = data + (size_t)det * n_f * 2;
         const double* S = psd ? psd + (size_t)det * n_f : nullptr;
         double* Cd = C.data() + (size_t)det * (n_f + 1);
+        double* wd = p->w73.data() + (size_t)det * n_f;
         for (int64_t k = 0; k < n_f; ++k) {
             Cd[k] = (double)csum;
+            wd[k] = 0.0;
             if (k >= kmin && k < kmax) {
                 const long double w2 = S ? (long double)norm / (long double)S[k] : (long double)norm;
                 const long double re = dd[2 * k], im = dd[2 * k + 1];
                 nl += (re * re + im * im) * w2;
                 csum += f73[k] * w2;
+                wd[k] = (double)(f73[k] * w2);
                 T[((size_t)k * n_det + det) * 2 + 0] = (double)(re * w2 * f76[k]);
                 T[((size_t)k * n_det + det) * 2 + 1] = (double)(-im * w2 * f76[k]);
             }
@@ -1299,6 +1519,7 @@ extern "C" void gwin_plan_destroy(gwin_plan* p) {
     cudaFree(p->d_key_in); cudaFree(p->d_key_out); cudaFree(p->d_perm_in); cudaFree(p->d_perm_out);
     cudaFree(p->d_partial); cudaFree(p->d_cub);
     cudaFree(p->d_marg_u); cudaFree(p->d_marg_logw); cudaFree(p->d_marg_opt);
+    cudaFree(p->d_calM); cudaFree(p->d_Ccal); cudaFree(p->d_calib); cudaFreeHost(p->h_calib);
     cudaFree(p->d_params); cudaFree(p->d_out); cudaFree(p->d_skip);
     cudaFreeHost(p->h_params); cudaFreeHost(p->h_out); cudaFreeHost(p->h_skip);
     if (p->timing) { cudaEventDestroy(p->ev0); cudaEventDestroy(p->ev1); }
@@ -1317,6 +1538,94 @@ extern "C" int gwin_plan_lognl(const gwin_plan* p, double* total, double* per_de
     if (!p) return fail(GWIN_EINVAL, "plan is NULL");
     if (total) *total = p->lognl;
     if (per_det) for (int i = 0; i < p->d.n_det; ++i) per_det[i] = p->lognl_det[i];
+    return GWIN_OK;
+}
+
+extern "C" int gwin_plan_set_calibration(gwin_plan* p, int n_points, const double* spline_freqs) {
+    if (!p) return fail(GWIN_EINVAL, "plan is NULL");
+    CK(cudaSetDevice(p->device));
+    CK(cudaDeviceSynchronize());
+    PlanDev& d = p->d;
+    cudaFree(p->d_calM); cudaFree(p->d_Ccal);
+    p->d_calM = p->d_Ccal = nullptr; d.calM = d.Ccal = nullptr; d.n_cal = 0;
+    if (n_points == 0) return GWIN_OK;
+    if (n_points < 4 || n_points > GWIN_MAX_CALIB_POINTS)
+        return fail(GWIN_EINVAL, "calibration needs 4..%d spline points, got %d", GWIN_MAX_CALIB_POINTS, n_points);
+    if (!spline_freqs) return fail(GWIN_EINVAL, "spline_freqs is NULL");
+    const int nd = d.n_det, n = n_points;
+    const int64_t n_f = d.n_f;
+    std::vector<double> M((size_t)nd * 4 * n);
+    std::vector<double> C((size_t)nd * 7 * (n_f + 1));
+    for (int det = 0; det < nd; ++det) {
+        const double* sf = spline_freqs + (size_t)det * n;
+        double fmin = sf[0], fmax = sf[0];
+        for (int j = 0; j < n; ++j) {
+            if (!std::isfinite(sf[j])) return fail(GWIN_EINVAL, "spline frequency %d of detector %d is not finite", j, det);
+            fmin = std::min(fmin, sf[j]); fmax = std::max(fmax, sf[j]);
+        }
+        if (!(fmax > fmin)) return fail(GWIN_EINVAL, "spline frequencies of detector %d span no range", det);
+        const double fm = 0.5 * (fmax + fmin), fh = 0.5 * (fmax - fmin);
+        d.cal_zs[det] = d.delta_f / fh;
+        d.cal_z0[det] = -fm / fh;
+        // least-squares cubic: Householder QR of the n x 4 Vandermonde matrix in z, M = R^-1 Q^T
+        std::vector<long double> A((size_t)n * 4), Qt((size_t)n * n, 0.0L);
+        for (int j = 0; j < n; ++j) {
+            const long double z = ((long double)sf[j] - (long double)fm) / (long double)fh;
+            A[j * 4 + 0] = 1.0L; A[j * 4 + 1] = z; A[j * 4 + 2] = z * z; A[j * 4 + 3] = z * z * z;
+            Qt[(size_t)j * n + j] = 1.0L;
+        }
+        for (int c = 0; c < 4; ++c) {
+            long double nrm = 0.0L;
+            for (int j = c; j < n; ++j) nrm += A[j * 4 + c] * A[j * 4 + c];
+            nrm = sqrtl(nrm);
+            if (!(nrm > 0.0L)) return fail(GWIN_EINVAL, "spline frequencies of detector %d are degenerate", det);
+            const long double alpha = A[c * 4 + c] > 0 ? -nrm : nrm;
+            std::vector<long double> v(n, 0.0L);
+            for (int j = c; j < n; ++j) v[j] = A[j * 4 + c];
+            v[c] -= alpha;
+            long double vv = 0.0L;
+            for (int j = c; j < n; ++j) vv += v[j] * v[j];
+            if (!(vv > 0.0L)) continue;
+            for (int cc = 0; cc < 4; ++cc) {              // A <- (I - 2 v v^T / v^T v) A
+                long double dot = 0.0L;
+                for (int j = c; j < n; ++j) dot += v[j] * A[j * 4 + cc];
+                dot = 2.0L * dot / vv;
+                for (int j = c; j < n; ++j) A[j * 4 + cc] -= dot * v[j];
+            }
+            for (int cc = 0; cc < n; ++cc) {              // Qt <- H Qt
+                long double dot = 0.0L;
+                for (int j = c; j < n; ++j) dot += v[j] * Qt[(size_t)j * n + cc];
+                dot = 2.0L * dot / vv;
+                for (int j = c; j < n; ++j) Qt[(size_t)j * n + cc] -= dot * v[j];
+            }
+        }
+        for (int col = 0; col < n; ++col) {               // back substitution per right-hand side
+            long double x[4];
+            for (int i = 3; i >= 0; --i) {
+                long double acc = Qt[(size_t)i * n + col];
+                for (int q = i + 1; q < 4; ++q) acc -= A[i * 4 + q] * x[q];
+                if (A[i * 4 + i] == 0.0L) return fail(GWIN_EINVAL, "spline frequencies of detector %d are degenerate", det);
+                x[i] = acc / A[i * 4 + i];
+            }
+            for (int i = 0; i < 4; ++i) M[((size_t)det * 4 + i) * n + col] = (double)x[i];
+        }
+        // prefix sums of the <h|h> weights times z^j
+        const double* wd = p->w73.data() + (size_t)det * n_f;
+        long double sum[7] = {0, 0, 0, 0, 0, 0, 0};
+        double* Cd = C.data() + (size_t)det * 7 * (n_f + 1);
+        for (int64_t k = 0; k <= n_f; ++k) {
+            for (int j = 0; j < 7; ++j) Cd[(size_t)j * (n_f + 1) + k] = (double)sum[j];
+            if (k == n_f || wd[k] == 0.0) continue;
+            const long double z = (long double)k * (long double)d.cal_zs[det] + (long double)d.cal_z0[det];
+            long double zj = wd[k];
+            for (int j = 0; j < 7; ++j) { sum[j] += zj; zj *= z; }
+        }
+    }
+    CK(cudaMalloc(&p->d_calM, sizeof(double) * M.size()));
+    CK(cudaMalloc(&p->d_Ccal, sizeof(double) * C.size()));
+    CK(cudaMemcpy(p->d_calM, M.data(), sizeof(double) * M.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(p->d_Ccal, C.data(), sizeof(double) * C.size(), cudaMemcpyHostToDevice));
+    d.calM = p->d_calM; d.Ccal = p->d_Ccal; d.n_cal = n;
     return GWIN_OK;
 }
 
@@ -1418,26 +1727,37 @@ static int ensure_workspace(gwin_plan* p, int64_t W, int n_chunks) {
 }
 
 template <int ND>
-static void launch_main(gwin_plan* p, bool recur, int W, int wpad, int n_chunks, int per_chunk,
+static void launch_main(gwin_plan* p, bool recur, bool calibrated, int W, int wpad, int n_chunks, int per_chunk,
                         cudaStream_t st) {
     dim3 grid((W + CTA_THREADS - 1) / CTA_THREADS, n_chunks);
     // diagnostic: GWIN_SMEM_PAD=<bytes> of unused dynamic shared memory lowers the occupancy
     static const int smem_pad = getenv("GWIN_SMEM_PAD") ? atoi(getenv("GWIN_SMEM_PAD")) : 0;
     constexpr int NWARP = CTA_THREADS / WARP;
     const int smem = (int)(sizeof(double2) * NWARP * 2 * TileStream<ND>::TILE * ND
-                           + sizeof(double) * RC_ROWS(ND) * CTA_THREADS + sizeof(uint64_t) * NWARP * 2) + smem_pad;
-    static bool attr_set = false;           // one instantiation per ND: set once
-    if (recur && !attr_set) {
-        cudaFuncSetAttribute(loglr_recur_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_set = true;
+                           + sizeof(double) * (calibrated ? RC_ROWS_CAL(ND) : RC_ROWS(ND)) * CTA_THREADS
+                           + sizeof(uint64_t) * NWARP * 2) + smem_pad;
+    static bool attr_set[2] = {false, false};           // one instantiation per (ND, CALIB): set once
+    if (recur && !attr_set[calibrated]) {
+        if (calibrated)
+            cudaFuncSetAttribute(loglr_recur_kernel<ND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        else
+            cudaFuncSetAttribute(loglr_recur_kernel<ND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set[calibrated] = true;
     }
-    if (recur)
-        loglr_recur_kernel<ND><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, per_chunk, p->n_blk, p->d_blk_start,
-                                                            p->d_blk_mat, p->d_mats,
-                                                            p->d_wc, p->d_ks, p->d_ke, p->d_partial);
+    if (recur && calibrated)
+        loglr_recur_kernel<ND, true><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, per_chunk, p->n_blk, p->d_blk_start,
+                                                                  p->d_blk_mat, p->d_mats,
+                                                                  p->d_wc, p->d_ks, p->d_ke, p->d_partial);
+    else if (recur)
+        loglr_recur_kernel<ND, false><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, per_chunk, p->n_blk, p->d_blk_start,
+                                                                   p->d_blk_mat, p->d_mats,
+                                                                   p->d_wc, p->d_ks, p->d_ke, p->d_partial);
+    else if (calibrated)
+        loglr_direct_kernel<ND, true><<<grid, CTA_THREADS, 0, st>>>(p->d, W, wpad, per_chunk, n_chunks,
+                                                                   p->d_wc, p->d_ks, p->d_ke, p->d_partial);
     else
-        loglr_direct_kernel<ND><<<grid, CTA_THREADS, 0, st>>>(p->d, W, wpad, per_chunk, n_chunks,
-                                                             p->d_wc, p->d_ks, p->d_ke, p->d_partial);
+        loglr_direct_kernel<ND, false><<<grid, CTA_THREADS, 0, st>>>(p->d, W, wpad, per_chunk, n_chunks,
+                                                                    p->d_wc, p->d_ks, p->d_ke, p->d_partial);
 }
 
 extern "C" int gwin_loglr_batch(gwin_plan* p, int mode, int64_t W64,
@@ -1446,10 +1766,36 @@ extern "C" int gwin_loglr_batch(gwin_plan* p, int mode, int64_t W64,
     return gwin_loglr_batch_strided(p, mode, W64, params, GWIN_NPARAM, 1, skip, loglr, hd, hh, stream);
 }
 
+static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
+                            const double* params, int64_t stride_walker, int64_t stride_param,
+                            const double* calib, int64_t cstride_walker, int64_t cstride_value,
+                            const uint8_t* skip,
+                            double* loglr, double* hd, double* hh, void* stream);
+
 extern "C" int gwin_loglr_batch_strided(gwin_plan* p, int mode, int64_t W64,
                                         const double* params, int64_t stride_walker, int64_t stride_param,
                                         const uint8_t* skip,
                                         double* loglr, double* hd, double* hh, void* stream) {
+    return loglr_batch_impl(p, mode, W64, params, stride_walker, stride_param, nullptr, 0, 0, skip, loglr, hd, hh, stream);
+}
+
+extern "C" int gwin_loglr_batch_calib(gwin_plan* p, int mode, int64_t W64,
+                                      const double* params, int64_t stride_walker, int64_t stride_param,
+                                      const double* calib, int64_t cstride_walker, int64_t cstride_value,
+                                      const uint8_t* skip,
+                                      double* loglr, double* hd, double* hh, void* stream) {
+    if (p && calib && p->d.n_cal == 0)
+        return fail(GWIN_EINVAL, "calibration values given but gwin_plan_set_calibration was not called");
+    if (calib && (cstride_walker < 1 || cstride_value < 1)) return fail(GWIN_EINVAL, "calibration strides must be >= 1");
+    return loglr_batch_impl(p, mode, W64, params, stride_walker, stride_param, calib, cstride_walker, cstride_value,
+                            skip, loglr, hd, hh, stream);
+}
+
+static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
+                            const double* params, int64_t stride_walker, int64_t stride_param,
+                            const double* calib, int64_t cstride_walker, int64_t cstride_value,
+                            const uint8_t* skip,
+                            double* loglr, double* hd, double* hh, void* stream) {
     if (!p) return fail(GWIN_EINVAL, "plan is NULL");
     if (stride_walker < 1 || stride_param < 1) return fail(GWIN_EINVAL, "parameter strides must be >= 1");
     if (mode < GWIN_MODE_GAUSSIAN || mode > GWIN_MODE_MARG_DIST_PHASE) return fail(GWIN_EINVAL, "bad mode %d", mode);
@@ -1499,7 +1845,8 @@ extern "C" int gwin_loglr_batch_strided(gwin_plan* p, int mode, int64_t W64,
         perm = p->d_perm_out;
         p->last_launches += 1;   // + CUB's radix-sort passes (library code, not counted)
     }
-    walker_setup_kernel<<<gb, tb, 0, st>>>(d, W, wpad, params, stride_walker, stride_param, skip, perm, p->d_wc, p->d_ks, p->d_ke, hh_rows);
+    walker_setup_kernel<<<gb, tb, 0, st>>>(d, W, wpad, params, stride_walker, stride_param, skip, perm, p->d_wc, p->d_ks, p->d_ke, hh_rows,
+                                           calib, cstride_walker, cstride_value);
     if (p->timing) {
         if (p->ev_pending) {            // harvest the previous launch (it has long finished)
             float ms = 0.f;
@@ -1510,10 +1857,10 @@ extern "C" int gwin_loglr_batch_strided(gwin_plan* p, int mode, int64_t W64,
         CK(cudaEventRecord(p->ev0, st));
     }
     switch (nd) {
-        case 1: launch_main<1>(p, recur, W, wpad, n_chunks, per_chunk, st); break;
-        case 2: launch_main<2>(p, recur, W, wpad, n_chunks, per_chunk, st); break;
-        case 3: launch_main<3>(p, recur, W, wpad, n_chunks, per_chunk, st); break;
-        default: launch_main<4>(p, recur, W, wpad, n_chunks, per_chunk, st); break;
+        case 1: launch_main<1>(p, recur, calib != nullptr, W, wpad, n_chunks, per_chunk, st); break;
+        case 2: launch_main<2>(p, recur, calib != nullptr, W, wpad, n_chunks, per_chunk, st); break;
+        case 3: launch_main<3>(p, recur, calib != nullptr, W, wpad, n_chunks, per_chunk, st); break;
+        default: launch_main<4>(p, recur, calib != nullptr, W, wpad, n_chunks, per_chunk, st); break;
     }
     if (p->timing) { CK(cudaEventRecord(p->ev1, st)); p->ev_pending = true; }
     combine_kernel<<<(W + 31) / 32, dim3(32, COMB_SEG), 0, st>>>(nd, W, wpad, n_chunks, mode, per_chunk, p->n_blk,
@@ -1556,10 +1903,49 @@ extern "C" int gwin_loglr_batch_host(gwin_plan* p, int mode, int64_t W,
 
 // params is either [W][13] (stride_walker = 13, stride_param = 1) or [13][W] (1, W); the
 // buffer is copied as one contiguous block of 13*W doubles
+static int loglr_batch_host_impl(gwin_plan* p, int mode, int64_t W,
+                                 const double* params, int64_t stride_walker, int64_t stride_param,
+                                 const double* calib, int64_t cstride_walker, int64_t cstride_value,
+                                 const uint8_t* skip, double* loglr, double* hd, double* hh);
+
 extern "C" int gwin_loglr_batch_host_strided(gwin_plan* p, int mode, int64_t W,
                                              const double* params, int64_t stride_walker, int64_t stride_param,
                                              const uint8_t* skip,
                                              double* loglr, double* hd, double* hh) {
+    return loglr_batch_host_impl(p, mode, W, params, stride_walker, stride_param, nullptr, 0, 0, skip, loglr, hd, hh);
+}
+
+extern "C" int gwin_loglr_batch_calib_host(gwin_plan* p, int mode, int64_t W,
+                                           const double* params, int64_t stride_walker, int64_t stride_param,
+                                           const double* calib, int64_t cstride_walker, int64_t cstride_value,
+                                           const uint8_t* skip,
+                                           double* loglr, double* hd, double* hh) {
+    if (p && calib) {
+        const int64_t nv = (int64_t)p->d.n_det * 2 * p->d.n_cal;
+        if (nv == 0) return fail(GWIN_EINVAL, "calibration values given but gwin_plan_set_calibration was not called");
+        if (!((cstride_walker == nv && cstride_value == 1) || (cstride_walker == 1 && cstride_value == W)))
+            return fail(GWIN_EINVAL, "host calibration values must be a dense [W][%lld] or [%lld][W] block",
+                        (long long)nv, (long long)nv);
+    }
+    return loglr_batch_host_impl(p, mode, W, params, stride_walker, stride_param, calib, cstride_walker, cstride_value,
+                                 skip, loglr, hd, hh);
+}
+
+static int ensure_calib_stage(gwin_plan* p, size_t n) {
+    if (n <= p->calib_cap) return GWIN_OK;
+    cudaFree(p->d_calib); cudaFreeHost(p->h_calib);
+    p->d_calib = p->h_calib = nullptr; p->calib_cap = 0;
+    const size_t cap = std::max<size_t>(n, 4096);
+    CK(cudaMalloc(&p->d_calib, sizeof(double) * cap));
+    CK(cudaMallocHost(&p->h_calib, sizeof(double) * cap));
+    p->calib_cap = cap;
+    return GWIN_OK;
+}
+
+static int loglr_batch_host_impl(gwin_plan* p, int mode, int64_t W,
+                                 const double* params, int64_t stride_walker, int64_t stride_param,
+                                 const double* calib, int64_t cstride_walker, int64_t cstride_value,
+                                 const uint8_t* skip, double* loglr, double* hd, double* hh) {
     if (!p) return fail(GWIN_EINVAL, "plan is NULL");
     if (!((stride_walker == GWIN_NPARAM && stride_param == 1) || (stride_walker == 1 && stride_param == W)))
         return fail(GWIN_EINVAL, "host parameters must be a dense [W][13] or [13][W] block");
@@ -1591,6 +1977,13 @@ extern "C" int gwin_loglr_batch_host_strided(gwin_plan* p, int mode, int64_t W,
         }
     }
     CK(cudaMemcpyAsync(p->d_params, p->h_params, sizeof(double) * GWIN_NPARAM * W, cudaMemcpyHostToDevice, st));
+    if (calib) {
+        const size_t nv = (size_t)nd * 2 * p->d.n_cal * (size_t)W;
+        rc = ensure_calib_stage(p, nv);
+        if (rc) return rc;
+        memcpy(p->h_calib, calib, sizeof(double) * nv);
+        CK(cudaMemcpyAsync(p->d_calib, p->h_calib, sizeof(double) * nv, cudaMemcpyHostToDevice, st));
+    }
     if (skip) {
         memcpy(p->h_skip, skip, W);
         CK(cudaMemcpyAsync(p->d_skip, p->h_skip, W, cudaMemcpyHostToDevice, st));
@@ -1598,8 +1991,9 @@ extern "C" int gwin_loglr_batch_host_strided(gwin_plan* p, int mode, int64_t W,
     double* d_lr = p->d_out;
     double* d_hd = p->d_out + p->stage_cap;
     double* d_hh = d_hd + 2 * (size_t)nd * p->stage_cap;
-    rc = gwin_loglr_batch_strided(p, mode, W, p->d_params, stride_walker, stride_param,
-                                  skip ? p->d_skip : nullptr, d_lr, d_hd, d_hh, st);
+    rc = loglr_batch_impl(p, mode, W, p->d_params, stride_walker, stride_param,
+                          calib ? p->d_calib : nullptr, cstride_walker, cstride_value,
+                          skip ? p->d_skip : nullptr, d_lr, d_hd, d_hh, st);
     if (rc) return rc;
     double* h_lr = p->h_out;
     double* h_hd = p->h_out + p->stage_cap;
@@ -1615,21 +2009,35 @@ extern "C" int gwin_loglr_batch_host_strided(gwin_plan* p, int mode, int64_t W,
 }
 
 extern "C" int gwin_generate_host(gwin_plan* p, const double* params, double* h_out, int64_t* length) {
+    return gwin_generate_calib_host(p, params, nullptr, h_out, length);
+}
+
+extern "C" int gwin_generate_calib_host(gwin_plan* p, const double* params, const double* calib,
+                                        double* h_out, int64_t* length) {
     if (!p || !params || !h_out) return fail(GWIN_EINVAL, "NULL argument");
+    if (calib && p->d.n_cal == 0)
+        return fail(GWIN_EINVAL, "calibration values given but gwin_plan_set_calibration was not called");
     CK(cudaSetDevice(p->device));
     int rc = ensure_stage(p, 1); if (rc) return rc;
+    const size_t nv = (size_t)p->d.n_det * 2 * p->d.n_cal;
+    if (calib) { rc = ensure_calib_stage(p, nv); if (rc) return rc; }
     rc = ensure_workspace(p, 2, 1); if (rc) return rc;
     const PlanDev& d = p->d;
     const int wpad = (int)p->w_cap;
     cudaStream_t st = p->stream;
     memcpy(p->h_params, params, sizeof(double) * GWIN_NPARAM);
     CK(cudaMemcpyAsync(p->d_params, p->h_params, sizeof(double) * GWIN_NPARAM, cudaMemcpyHostToDevice, st));
+    if (calib) {
+        memcpy(p->h_calib, calib, sizeof(double) * nv);
+        CK(cudaMemcpyAsync(p->d_calib, p->h_calib, sizeof(double) * nv, cudaMemcpyHostToDevice, st));
+    }
     double* hh_rows = p->d_wc + (size_t)NCOEF(d.n_det) * wpad;
-    walker_setup_kernel<<<1, 32, 0, st>>>(d, 1, wpad, p->d_params, GWIN_NPARAM, 1, nullptr, nullptr, p->d_wc, p->d_ks, p->d_ke, hh_rows);
+    walker_setup_kernel<<<1, 32, 0, st>>>(d, 1, wpad, p->d_params, GWIN_NPARAM, 1, nullptr, nullptr, p->d_wc, p->d_ks, p->d_ke, hh_rows,
+                                          calib ? p->d_calib : nullptr, (int64_t)nv, 1);
     generate_len_kernel<<<1, 1, 0, st>>>(d, p->d_params, p->d_ke);
     double2* dout = nullptr;
     CK(cudaMalloc(&dout, sizeof(double2) * (size_t)d.n_det * d.n_f));
-    generate_kernel<<<(d.n_f + 255) / 256, 256, 0, st>>>(d, wpad, p->d_wc, p->d_ke, dout);
+    generate_kernel<<<(d.n_f + 255) / 256, 256, 0, st>>>(d, wpad, p->d_wc, p->d_ke, dout, calib != nullptr);
     int n = 0;
     auto fetch = [&]() -> int {
         CK(cudaMemcpyAsync(h_out, dout, sizeof(double2) * (size_t)d.n_det * d.n_f, cudaMemcpyDeviceToHost, st));

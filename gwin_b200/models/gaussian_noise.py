@@ -14,6 +14,7 @@ from collections import OrderedDict
 import numpy
 
 from .. import _lib
+from ..calibration import spline_frequencies, values_matrix
 from ..waveform import param_rows
 from .base_data import BaseDataModel
 
@@ -71,6 +72,11 @@ class GaussianNoise(BaseDataModel):
                                        dtype=numpy.complex128)
                          for det in self._dets]),
             psd_arr, norm)
+        # calibration model held by the generator (reference base_data.py:225-230)
+        self._recalib = getattr(gen, 'recalib', None)
+        if self._recalib:
+            self._plan.set_calibration(
+                spline_frequencies(self._recalib, self._dets))
         self._kmin = self._plan.kmin
         self._kmax = self._plan.kmax
         self._f_lower = f_lower
@@ -119,9 +125,14 @@ class GaussianNoise(BaseDataModel):
         return static
 
     def _kernel_call(self, params, W, skip=None):
-        P = param_rows(params, W, static=self._static_for_kernel())
+        static = self._static_for_kernel()
+        P = param_rows(params, W, static=static)
+        calib = None
+        if self._recalib:
+            calib = values_matrix(self._recalib, self._dets, params, W,
+                                  static=static)
         return self._plan.loglr_host(P, mode=self._mode, skip=skip,
-                                     param_major=True)
+                                     param_major=True, calib=calib)
 
     def _nowaveform_loglr(self):
         for det in self._data:

@@ -113,6 +113,11 @@ class _DeviceEnsemble(BaseMCMCSampler):
         if nwalkers < 2 * ndim:
             raise ValueError("The number of walkers needs to be more than twice "
                              "the dimension of your parameter space.")
+        if getattr(model, "_recalib", None):
+            raise NotImplementedError(
+                "calibration parameters exceed the device-resident stepper's %d "
+                "sampled dimensions; use emcee / emcee_pt (host stepper, GPU "
+                "likelihood) with a calibrated model" % _lib.ENS_MAXDIM)
         self._torch = torch
         self._lib = _lib.load()
         self._spec = prior_spec_from_model(model)

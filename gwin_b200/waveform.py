@@ -16,6 +16,7 @@ from collections import OrderedDict
 import numpy
 
 from . import _lib
+from .calibration import spline_frequencies, values_matrix
 from .detector import Detector
 from .types import FrequencySeries
 
@@ -104,9 +105,9 @@ class FDomainDetFrameGenerator(object):
                  variable_args=(), recalib=None, gates=None, **frozen_params):
         if rframe_generator_class is not FDomainCBCGenerator:
             raise ValueError("only FDomainCBCGenerator is supported")
-        if recalib or gates:
-            raise NotImplementedError("recalibration / gating are outside the "
-                                      "CUDA hot path (SURVEY.md 8f-4)")
+        if gates:
+            raise NotImplementedError("gating the data is outside the CUDA "
+                                      "hot path")
         if not detectors:
             raise ValueError("at least one detector is required")
         approximant = frozen_params.pop("approximant", "TaylorF2")
@@ -125,6 +126,14 @@ class FDomainDetFrameGenerator(object):
         self.frozen_params = dict(frozen_params)
         self.current_params = dict(frozen_params)
         self._plans = {}
+        # dict detector -> calibration.Recalibrate ([UPSTREAM] pycbc generator
+        # ``recalib=``; reference models/base_data.py:225-230)
+        self.recalib = recalib if recalib else None
+        if self.recalib:
+            if sorted(self.recalib.keys()) != sorted(self.detector_names):
+                raise ValueError("recalib needs one model per detector")
+            self._spline_freqs = spline_frequencies(self.recalib,
+                                                    self.detector_names)
 
     @property
     def epoch(self):
@@ -145,6 +154,8 @@ class FDomainDetFrameGenerator(object):
                 numpy.stack([d.response for d in self.detectors.values()]),
                 numpy.stack([d.location for d in self.detectors.values()]),
                 numpy.zeros((nd, n_f), dtype=numpy.complex128), None, None)
+            if self.recalib:
+                self._plans[key].set_calibration(self._spline_freqs)
         return self._plans[key]
 
     def generate(self, device=0, **kwargs):
@@ -159,7 +170,11 @@ class FDomainDetFrameGenerator(object):
             raise NoWaveformError("f_ISCO is not above f_lower for these masses")
         n_f = max(((n + 1023) // 1024) * 1024 + 1,
                   int(self.f_lower / self.delta_f) + 9)
-        h, length = self._plan_for(n_f, device).generate(row[0])
+        calib = None
+        if self.recalib:
+            calib = values_matrix(self.recalib, self.detector_names,
+                                  self.current_params, 1)[:, 0]
+        h, length = self._plan_for(n_f, device).generate(row[0], calib=calib)
         return OrderedDict(
             (det, FrequencySeries(h[i, :length], self.delta_f, self._epoch))
             for i, det in enumerate(self.detector_names))

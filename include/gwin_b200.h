@@ -99,6 +99,22 @@ int gwin_plan_configure(gwin_plan* plan, int kernel, double phase_tol, double mc
 int gwin_plan_set_distance_marg(gwin_plan* plan, int64_t n, const double* dist, const double* weight);
 
 /*
+ * Calibration model == gwin/calibration.py:104-173 (CubicSpline) as the waveform generator
+ * applies it to every detector's template ([UPSTREAM] pycbc FDomainDetFrameGenerator
+ * ``recalib=``, handed over at base_data.py:225-230):
+ *     h_det(f) *= (1 + dA(f)) (2 + i dphi(f)) / (2 - i dphi(f))
+ * with dA, dphi = scipy UnivariateSpline(spline_points, values)(f) at its default k = 3,
+ * s = n_points -- which for calibration-sized values (sum of squares <= n_points) is the
+ * least-squares CUBIC POLYNOMIAL through the values, evaluated (and extrapolated) at every
+ * bin.  spline_freqs: HOST [n_det][n_points] = CubicSpline.spline_points per detector
+ * (plan detector order), 4 <= n_points <= GWIN_MAX_CALIB_POINTS; n_points = 0 clears.
+ * Builds the values->coefficients maps and seven prefix tables per detector for the
+ * closed-form <h|h> (|1 + dA|^2 is a sextic in f).
+ */
+#define GWIN_MAX_CALIB_POINTS 32
+int gwin_plan_set_calibration(gwin_plan* plan, int n_points, const double* spline_freqs);
+
+/*
  * One batched evaluation of GaussianNoise._loglr / MarginalizedGaussianNoise._loglr
  * for W parameter points (what pool.map(CallModel, points) computes one point at a
  * time in the reference).  All pointers are DEVICE pointers on the plan's device.
@@ -150,6 +166,28 @@ int gwin_loglr_batch_host_strided(gwin_plan* plan, int mode, int64_t W,
  */
 int gwin_generate_host(gwin_plan* plan, const double* params, double* h_out,
                        int64_t* length);
+
+/*
+ * The same calls with per-walker calibration values (what Recalibrate.map_to_adjust,
+ * calibration.py:50-76, collects from the ``recalib_*`` parameters):
+ *   calib   value v of walker w at calib[w * cstride_walker + v * cstride_value],
+ *           v = (2 * det + which) * n_points + i, which = 0 for recalib_amplitude_<ifo>_<i>,
+ *           1 for recalib_phase_<ifo>_<i>.  NULL = no calibration (the plain calls above).
+ * gwin_loglr_batch_calib takes DEVICE pointers, the _host variants HOST pointers (dense
+ * [W][n_det * 2 * n_points] or its transpose).  Non-finite values give loglr = -inf.
+ */
+int gwin_loglr_batch_calib(gwin_plan* plan, int mode, int64_t W,
+                           const double* params, int64_t stride_walker, int64_t stride_param,
+                           const double* calib, int64_t cstride_walker, int64_t cstride_value,
+                           const uint8_t* skip,
+                           double* loglr, double* hd, double* hh, void* stream);
+int gwin_loglr_batch_calib_host(gwin_plan* plan, int mode, int64_t W,
+                                const double* params, int64_t stride_walker, int64_t stride_param,
+                                const double* calib, int64_t cstride_walker, int64_t cstride_value,
+                                const uint8_t* skip,
+                                double* loglr, double* hd, double* hh);
+int gwin_generate_calib_host(gwin_plan* plan, const double* params, const double* calib,
+                             double* h_out, int64_t* length);
 
 /* Kernel launches issued by the last gwin_loglr_batch* call on this plan. */
 int gwin_plan_last_launches(const gwin_plan* plan);

@@ -408,11 +408,51 @@ def apply_fseries_time_shift(h, dt, delta_f, mode="faithful"):
 # [UPSTREAM] pycbc.waveform.generator.FDomainDetFrameGenerator, as constructed
 # by the reference at base_data.py:224-230 and test/utils/waveform.py:64-65.
 # ---------------------------------------------------------------------------
+class CubicSpline(object):
+    """gwin/calibration.py:23-78 (``Recalibrate.map_to_adjust``) and :104-173
+    (``CubicSpline``): strain * (1 + dA(f)) * (2 + i dphi(f)) / (2 - i dphi(f)) with dA, dphi
+    ``scipy.interpolate.UnivariateSpline`` fits (default k = 3 and smoothing s = n_points --
+    which for calibration-sized values returns the least-squares cubic polynomial, not an
+    interpolant) through ``n_points`` log-spaced frequencies, evaluated at every sample
+    frequency of the waveform (extrapolating below/above the spline range)."""
+    name = "cubic_spline"
+
+    def __init__(self, minimum_frequency, maximum_frequency, n_points, ifo_name):
+        self.ifo_name = ifo_name
+        self.params = dict()
+        n_points = int(n_points)
+        if n_points < 4:
+            raise ValueError("Use at least 4 spline points for calibration model")
+        self.n_points = n_points
+        self.spline_points = np.logspace(np.log10(float(minimum_frequency)),
+                                         np.log10(float(maximum_frequency)), n_points)
+
+    def map_to_adjust(self, strain, delta_f, prefix="recalib_", **params):
+        self.params.update({key[len(prefix):]: params[key] for key in params
+                            if prefix in key and self.ifo_name in key})
+        return self.apply_calibration(strain, delta_f)
+
+    def apply_calibration(self, strain, delta_f):
+        from scipy.interpolate import UnivariateSpline
+        freqs = np.arange(len(strain)) * delta_f          # strain.sample_frequencies
+        amp = [self.params["amplitude_{}_{}".format(self.ifo_name, ii)]
+               for ii in range(self.n_points)]
+        delta_amplitude = UnivariateSpline(self.spline_points, amp)(freqs)
+        pha = [self.params["phase_{}_{}".format(self.ifo_name, ii)]
+               for ii in range(self.n_points)]
+        delta_phase = UnivariateSpline(self.spline_points, pha)(freqs)
+        return strain * (1.0 + delta_amplitude) \
+            * (2.0 + 1j * delta_phase) / (2.0 - 1j * delta_phase)
+
+
 class FDomainDetFrameGenerator(object):
     location_args = ("tc", "ra", "dec", "polarization")
 
     def __init__(self, epoch, detectors, delta_f, f_lower, variable_args=(),
-                 mode="faithful", **static):
+                 mode="faithful", recalib=None, **static):
+        # [UPSTREAM] pycbc generator: ``recalib`` = dict detector -> Recalibrate instance,
+        # applied to each detector's shifted waveform (base_data.py:225-230 passes it in)
+        self.recalib = recalib
         self.epoch = float(epoch)
         self.detectors = OrderedDict((d, Detector(d)) for d in detectors)
         self.detector_names = list(detectors)
@@ -441,6 +481,9 @@ class FDomainDetFrameGenerator(object):
             dt = float(tc - self.epoch)
             h[detname] = apply_fseries_time_shift(thish, dt, self.delta_f,
                                                   mode=self.mode)
+            if self.recalib:
+                h[detname] = self.recalib[detname].map_to_adjust(
+                    h[detname], self.delta_f, **self.current_params)
         return h
 
 
@@ -473,7 +516,8 @@ class GaussianNoiseOracle(object):
 
     def __init__(self, data, delta_f, epoch, f_lower, psds=None, f_upper=None,
                  norm=None, phase_marginalization=False, mode="faithful",
-                 waveform_f_lower=None, distance_marginalization=None):
+                 waveform_f_lower=None, distance_marginalization=None,
+                 recalibration=None):
         self.mode = mode
         # marginalized_gaussian_noise.py:368-375: (dist_array, deltad * dist_prior)
         self.distance_marginalization = distance_marginalization
@@ -506,7 +550,7 @@ class GaussianNoiseOracle(object):
         self.generator = FDomainDetFrameGenerator(
             epoch, self.dets, delta_f,
             f_lower if waveform_f_lower is None else waveform_f_lower,
-            mode=mode)
+            mode=mode, recalib=recalibration)
         self.phase_marginalization = phase_marginalization
         self._lognl = None
 

@@ -67,8 +67,70 @@ class PlanModel(object):
             self.C[d, 1:] = np.cumsum(f73 * w2).astype(float)
             self.lognl_det[d] = float(-0.5 * np.sum(
                 (dd.real.astype(ld) ** 2 + dd.imag.astype(ld) ** 2) * w2))
+            if d == 0:
+                self._w73 = np.zeros((self.n_det, n_f), dtype=ld)
+            self._w73[d] = f73 * w2
         self.phase_tol, self.mchirp_min = phase_tol, mchirp_min
         self.blk_start = self.build_schedule()
+        self.cal = None
+
+    # -- gwin_plan_set_calibration ----------------------------------------------
+    def set_calibration(self, spline_freqs):
+        """spline_freqs [n_det][n_points].  Per detector: z = (f - f_mid) / f_half maps the
+        spline range to [-1, 1]; calM = the least-squares map from the n_points values to the
+        cubic's monomial coefficients in z (what UnivariateSpline's default smoothing returns);
+        Ccal[j] = prefix sums of w f^(-7/3) z^j, j = 0..6, for the closed-form <h|h>."""
+        ld = np.longdouble
+        sf = np.asarray(spline_freqs, dtype=float)
+        n_f = self.n_f
+        cal = {"zs": [], "z0": [], "M": [], "C": np.zeros((self.n_det, 7, n_f + 1))}
+        for d in range(self.n_det):
+            fm, fh = 0.5 * (sf[d].max() + sf[d].min()), 0.5 * (sf[d].max() - sf[d].min())
+            zs, z0 = self.delta_f / fh, -fm / fh
+            z = (sf[d].astype(ld) - ld(fm)) / ld(fh)
+            V = np.stack([z ** 0, z, z ** 2, z ** 3], axis=1)
+            Q, R = np.linalg.qr(V.astype(float))
+            cal["M"].append(np.linalg.solve(R, Q.T))
+            cal["zs"].append(zs)
+            cal["z0"].append(z0)
+            zk = np.arange(n_f).astype(ld) * ld(zs) + ld(z0)
+            for j in range(7):
+                cal["C"][d, j, 1:] = np.cumsum(self._w73[d] * zk ** j).astype(float)
+        self.cal = cal
+
+    def calib_coef(self, values):
+        """values [n_det][2][n_points] -> cubic coefficients [n_det][2][4] (z^0..z^3)."""
+        v = np.asarray(values, dtype=float)
+        return np.array([[self.cal["M"][d].dot(v[d, w]) for w in range(2)]
+                         for d in range(self.n_det)])
+
+    def calib_factor(self, coef, d, k):
+        """(1 + dA)(2 + i dphi)/(2 - i dphi) at bins k, as the direct kernel forms it."""
+        z = np.asarray(k, dtype=float) * self.cal["zs"][d] + self.cal["z0"][d]
+        a, ph = coef[d, 0], coef[d, 1]
+        A = ((a[3] * z + a[2]) * z + a[1]) * z + a[0]
+        P = ((ph[3] * z + ph[2]) * z + ph[1]) * z + ph[0]
+        return (1 + A) / (4 + P * P) * ((4 - P * P) + 4j * P)
+
+    def calib_log(self, coef, d, k):
+        """log of the factor, as the recurrence kernel samples it at block nodes."""
+        z = np.asarray(k, dtype=float) * self.cal["zs"][d] + self.cal["z0"][d]
+        a, ph = coef[d, 0], coef[d, 1]
+        A = ((a[3] * z + a[2]) * z + a[1]) * z + a[0]
+        P = ((ph[3] * z + ph[2]) * z + ph[1]) * z + ph[0]
+        return np.log1p(A) + 2j * np.arctan(0.5 * P)
+
+    def calib_hh(self, w, coef):
+        """closed-form <h|h> with the amplitude factor: (1 + A(z))^2 is a sextic in z."""
+        hh = []
+        for d in range(self.n_det):
+            q = np.convolve(coef[d, 0] + np.array([1., 0, 0, 0]), coef[d, 0] + np.array([1., 0, 0, 0]))
+            v = 0.0
+            if w['ke'] > w['ks']:
+                C = self.cal["C"][d]
+                v = abs(w['A'][d]) ** 2 * float(np.dot(q, C[:, w['ke']] - C[:, w['ks']]))
+            hh.append(v)
+        return hh
 
     @staticmethod
     def block_mat(B, deg):
@@ -284,27 +346,38 @@ class PlanModel(object):
         return lr, hd, hh
 
     # -- loglr_direct_kernel ------------------------------------------------------
-    def loglr_direct(self, p, marg=False):
+    def loglr_direct(self, p, marg=False, calib=None):
         w = self.walker(p)
         if not w['valid']:
             return -np.inf, None, None
         ks, ke = w['ks'], w['ke']
         S = np.zeros(self.n_det, dtype=complex)
+        coef = None
+        if calib is not None:
+            coef = self.calib_coef(calib)
+            w['hh'] = self.calib_hh(w, coef)
         if ke > ks:
             k = np.arange(ks, ke)
             psi = self.phase_turns(w, k)
             for d in range(self.n_det):
                 ph = psi + np.modf(k * w['tau'][d])[0]
                 ph = ph - np.rint(ph)
-                S[d] = np.sum(self.T[d, ks:ke] * np.exp(-2j * PI * ph))
+                u = np.exp(-2j * PI * ph)
+                if coef is not None:
+                    u = u * self.calib_factor(coef, d, k)
+                S[d] = np.sum(self.T[d, ks:ke] * u)
         return self.finish(w, S, marg)
 
     # -- loglr_recur_kernel -------------------------------------------------------
-    def loglr_recur(self, p, marg=False, return_phase_err=False):
+    def loglr_recur(self, p, marg=False, return_phase_err=False, calib=None):
         w = self.walker(p)
         if not w['valid']:
             return -np.inf, None, None
         ks, ke = w['ks'], w['ke']
+        coef = None
+        if calib is not None:
+            coef = self.calib_coef(calib)
+            w['hh'] = self.calib_hh(w, coef)
         S = np.zeros(self.n_det, dtype=complex)
         max_err = 0.0
         bs = self.blk_start
@@ -321,7 +394,10 @@ class PlanModel(object):
                 psi = self.phase_turns(w, k)
                 for d in range(self.n_det):
                     ph = psi + k * w['tau'][d]
-                    S[d] += np.sum(np.where(on, self.T[d, k], 0) * np.exp(-2j * PI * ph))
+                    u = np.exp(-2j * PI * ph)
+                    if coef is not None:
+                        u = u * self.calib_factor(coef, d, k)
+                    S[d] += np.sum(np.where(on, self.T[d, k], 0) * u)
                 continue
             deg = M["deg"]
             f0 = self.phase_turns(w, kb)
@@ -336,12 +412,22 @@ class PlanModel(object):
                 poly = f0 + np.concatenate([[0.], np.cumsum(d1)])
                 max_err = max(max_err, float(np.max(np.abs(exact - poly)[on])) * TWOPI
                               if on.any() else 0.0)
-            tq = np.exp(2j * PI * D4)
             for d in range(self.n_det):
                 Tk = np.where(on, self.T[d, k], 0)
-                g = np.exp(2j * PI * (D1 + w['tau'][d]))
-                rq = np.exp(2j * PI * D2)
-                sq = np.exp(2j * PI * D3)
+                E1, E2, E3, E4 = D1, D2, D3, D4
+                cend = 1.0
+                if coef is not None:
+                    # the per-detector log-calibration joins the block polynomial as an
+                    # imaginary phase: Theta' = Theta + i L / (2 pi)
+                    L0 = self.calib_log(coef, d, kb)
+                    Ln = self.calib_log(coef, d, kb + np.array(M["node"]))
+                    DL = M["m"][:, :deg].dot(Ln - L0) * (1j / TWOPI)
+                    E1, E2, E3, E4 = D1 + DL[0], D2 + DL[1], D3 + DL[2], D4 + DL[3]
+                    cend = np.exp(Ln[-1])
+                tq = np.exp(2j * PI * E4)
+                g = np.exp(2j * PI * (E1 + w['tau'][d]))
+                rq = np.exp(2j * PI * E2)
+                sq = np.exp(2j * PI * E3)
                 acc = Tk[0]
                 for jj in range(1, B):
                     acc = acc * g + Tk[jj]
@@ -351,7 +437,7 @@ class PlanModel(object):
                         sq = sq * tq
                 kend = kb + B - 1
                 anchor = fn[-1] + np.modf(kend * w['tau'][d])[0]
-                S[d] += acc * np.exp(-2j * PI * anchor)
+                S[d] += acc * np.exp(-2j * PI * anchor) * cend
         out = self.finish(w, S, marg)
         if return_phase_err:
             return out + (max_err,)

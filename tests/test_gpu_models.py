@@ -229,3 +229,50 @@ def test_pt_sampler_runs_on_gpu(cfg):
     assert np.all(np.isfinite(pt.lnpost))
     ms = pt.model_stats
     assert np.all(np.isfinite(ms['loglr']))
+
+
+def test_calibrated_model_and_generator(cfg):
+    """recalib= on the generator (reference base_data.py:225-230): model protocol, batch
+    protocol and generate() against the oracle's CubicSpline (calibration.py:104-173)."""
+    import gwin_oracle as O
+    from gwin_b200 import calibration
+    n = 5
+    rec = {d: calibration.CubicSpline(20., 1024., n, d.lower()) for d in cfg.dets}
+    orec = {d: O.CubicSpline(20., 1024., n, d.lower()) for d in cfg.dets}
+    names = [nm for d in cfg.dets for nm in rec[d].param_names]
+    assert names[0] == "recalib_amplitude_h1_0" and names[n] == "recalib_phase_h1_0"
+    variable = tuple(PARAM_ORDER) + tuple(names)
+    gen = FDomainDetFrameGenerator(FDomainCBCGenerator, cfg.epoch, detectors=cfg.dets,
+                                   variable_args=variable, delta_f=cfg.delta_f, f_lower=cfg.f_lower,
+                                   recalib=rec)
+    data = {d: FrequencySeries(cfg.data[d], cfg.delta_f, cfg.epoch) for d in cfg.dets}
+    model = models.GaussianNoise(variable, data, gen, cfg.f_lower, psds=cfg.psds())
+    orc = cfg.oracle(recalibration=orec)
+    rng = np.random.default_rng(12)
+    p = dict(cfg.inj)
+    p.update(zip(names, rng.normal(0, 0.05, len(names))))
+    model.update(**p)
+    lr0, hd0, hh0 = orc.loglr(**p)
+    assert abs(model.loglr - lr0) <= tol(lr0)
+    # generate(): the calibrated detector-frame waveform
+    wf = gen.generate(**p)
+    ref = orc.generator.generate(**p)
+    for det in cfg.dets:
+        a, b = wf[det].numpy(), ref[det]
+        assert len(a) == len(b)
+        assert np.max(np.abs(a - b)) <= 1e-9 * np.max(np.abs(b))
+    # batch protocol
+    W = 6
+    X = np.column_stack([util.draw_bbh(rng, W, cfg), rng.normal(0, 0.05, (W, len(names)))])
+    res = models.CallModel(model, "loglr", return_all_stats=False).batch(X)
+    ref = [orc.loglr(**dict(zip(variable, row)))[0] for row in X]
+    assert np.all(np.abs(res.values - ref) <= tol(np.array(ref)))
+    # a missing calibration parameter is a KeyError (calibration.py:151-161)
+    q = dict(cfg.inj)
+    gen2 = FDomainDetFrameGenerator(FDomainCBCGenerator, cfg.epoch, detectors=cfg.dets,
+                                    variable_args=PARAM_ORDER, delta_f=cfg.delta_f, f_lower=cfg.f_lower,
+                                    recalib=rec)
+    with pytest.raises(KeyError):
+        gen2.generate(**q)
+    with pytest.raises(ValueError):        # outside the regime the spline fit is a cubic in
+        calibration.values_matrix(rec, cfg.dets, dict(zip(names, np.full(len(names), 1.5))), 1)

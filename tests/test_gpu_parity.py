@@ -378,6 +378,89 @@ def test_reference_tc_grid_argmax_distance_marginalized():
         assert abs(call([t]) - lr0) <= tol(lr0)
 
 
+def _calib_setup(cfg, n_points, fmax, rng, W, scale=0.05):
+    import gwin_oracle as O
+    rec = {d: O.CubicSpline(cfg.f_lower, fmax, n_points, d.lower()) for d in cfg.dets}
+    vals = rng.normal(0., scale, (W, len(cfg.dets) * 2 * n_points))
+    names = []
+    for d in cfg.dets:
+        for which in ("amplitude", "phase"):
+            names += ["recalib_%s_%s_%d" % (which, d.lower(), i) for i in range(n_points)]
+    return rec, vals, names
+
+
+def _calib_oracle_batch(orc, P, vals, names):
+    nd = len(orc.dets)
+    lr = np.empty(len(P))
+    hd = np.empty((len(P), nd), complex)
+    hh = np.empty((len(P), nd))
+    for i, row in enumerate(P):
+        kw = dict(zip(PARAM_ORDER, row))
+        kw.update(zip(names, vals[i]))
+        l, d, h = orc.loglr(**kw)
+        lr[i], hd[i], hh[i] = l, [d[k] for k in orc.dets], [h[k] for k in orc.dets]
+    return lr, hd, hh
+
+
+@pytest.mark.parametrize("n_points,fmax", [(4, 1024.), (6, 512.), (10, 1024.)])
+def test_calibration_cubic_spline(cfg2, n_points, fmax):
+    """gwin/calibration.py:142-173 applied inside the kernels against the oracle's scipy
+    UnivariateSpline; spline ranges narrower than the band exercise the extrapolation."""
+    rng = np.random.default_rng(100 + n_points)
+    W = 10
+    rec, vals, names = _calib_setup(cfg2, n_points, fmax, rng, W)
+    vals[0] = 0.0                               # zero calibration == the plain likelihood
+    vals[1] *= 6.0                              # large (but still < 1) excursions
+    vals[2, :n_points] = -0.9                   # 1 + dA = 0.1: the recurrence kernel falls back to
+    vals[4, :n_points] = np.linspace(-0.99, 0.5, n_points)   # bin-by-bin evaluation where the log
+    vals[5, n_points:2 * n_points] = np.linspace(-0.99, 0.99, n_points)   # is not smooth; big phases
+    P = util.draw_bbh(rng, W, cfg2)
+    model = cfg2.cuda_model()
+    plain = model.plan.loglr_host(P)
+    model.plan.set_calibration([rec[d].spline_points for d in cfg2.dets])
+    for marg in (False, True):
+        orc = cfg2.oracle(phase_marginalization=marg, recalibration=rec)
+        lr0, hd0, hh0 = _calib_oracle_batch(orc, P, vals, names)
+        for kernel in (1, 2):
+            model.plan.configure(kernel=kernel)
+            lr, hd, hh = model.plan.loglr_host(P, mode=int(marg), calib=vals)
+            _check(lr, hd, hh, lr0, hd0, hh0, "calib n=%d marg=%d k%d" % (n_points, marg, kernel))
+            # parameter-major layout gives the same numbers
+            lr2 = model.plan.loglr_host(np.ascontiguousarray(P.T), mode=int(marg), param_major=True,
+                                        calib=np.ascontiguousarray(vals.T))[0]
+            np.testing.assert_array_equal(lr, lr2)
+    model.plan.configure(kernel=0)
+    import torch
+    lr3 = model.plan.loglr_device(torch.tensor(P, device="cuda"), calib=torch.tensor(vals, device="cuda"))[0]
+    np.testing.assert_array_equal(lr3.cpu().numpy(), model.plan.loglr_host(P, calib=vals)[0])
+    assert abs(model.plan.loglr_host(P, calib=vals)[0][0] - plain[0][0]) <= tol(plain[0][0])
+    assert np.max(np.abs(lr0[1:] - plain[0][1:])) > 0.1
+    # non-finite value -> -inf; uncalibrated call on a calibrated plan is untouched
+    bad = vals.copy()
+    bad[3, 5] = np.nan
+    assert model.plan.loglr_host(P, calib=bad)[0][3] == -np.inf
+    np.testing.assert_array_equal(model.plan.loglr_host(P)[0], plain[0])
+    model.plan.set_calibration(None)
+    with pytest.raises(ValueError):
+        model.plan.loglr_host(P, calib=vals)
+
+
+def test_calibration_bns_long_segment():
+    """Calibrated C3-like case (32 s so the oracle stays fast): both kernels."""
+    cfg = util.c3(seglen=32)
+    rng = np.random.default_rng(9)
+    W = 6
+    rec, vals, names = _calib_setup(cfg, 8, 2048., rng, W)
+    P = util.draw_bns(rng, W, cfg)
+    model = cfg.cuda_model()
+    model.plan.set_calibration([rec[d].spline_points for d in cfg.dets])
+    lr0, hd0, hh0 = _calib_oracle_batch(cfg.oracle(recalibration=rec), P, vals, names)
+    for kernel in (1, 2):
+        model.plan.configure(kernel=kernel)
+        lr, hd, hh = model.plan.loglr_host(P, calib=vals)
+        _check(lr, hd, hh, lr0, hd0, hh0, "calib bns k%d" % kernel)
+
+
 def test_four_detectors_and_large_batch():
     """n_det = 4 (the narrower TMA tile variant of the kernels) and a 100k-walker batch that
     grows the workspace: both kernels against the oracle on a sample and against each other on

@@ -270,3 +270,39 @@ def test_checkpoint_resume_is_bit_identical(tmp_path):
     fp = InferenceFile(p2, 'r')
     assert fp['samples/y'].shape == (2, 20, 5) and fp.attrs['ntemps'] == 2
     assert fp['model_stats/loglr'].shape == (2, 20, 5)
+
+
+def test_calibration_description_classes():
+    """gwin/calibration.py: constructor, spline points, parameter naming, from_config,
+    the values matrix the kernels take."""
+    from gwin_b200 import calibration as cal
+    cs = cal.CubicSpline("20", "1024", "5", "h1")
+    assert cs.n_points == 5 and np.allclose(cs.spline_points, np.logspace(np.log10(20.), np.log10(1024.), 5))
+    assert cs.param_names[:2] == ["recalib_amplitude_h1_0", "recalib_amplitude_h1_1"]
+    assert cs.param_names[5] == "recalib_phase_h1_0"
+    with pytest.raises(ValueError):
+        cal.CubicSpline(20., 1024., 3, "h1")
+    with pytest.raises(NotImplementedError):            # applied on the GPU only
+        cs.map_to_adjust(np.zeros(4, complex))
+
+    class CP(object):
+        def items(self, section):
+            assert section == "calibration"
+            return [("h1_model", "cubic_spline"), ("h1_minimum_frequency", "20"),
+                    ("h1_maximum_frequency", "512"), ("h1_n_points", "6"),
+                    ("l1_model", "cubic_spline"), ("l1_minimum_frequency", "10"),
+                    ("l1_maximum_frequency", "512"), ("l1_n_points", "6")]
+    m = cal.Recalibrate.from_config(CP(), "H1", "calibration")
+    assert isinstance(m, cal.CubicSpline) and m.ifo_name == "h1" and m.n_points == 6
+    assert np.isclose(m.spline_points[0], 20.) and np.isclose(m.spline_points[-1], 512.)
+    rec = {"H1": m, "L1": cal.Recalibrate.from_config(CP(), "L1", "calibration")}
+    sf = cal.spline_frequencies(rec, ["H1", "L1"])
+    assert sf.shape == (2, 6) and np.isclose(sf[1, 0], 10.)
+    params = {nm: np.arange(3) * 0.01 for nm in rec["H1"].param_names}
+    static = {nm: 0.02 for nm in rec["L1"].param_names}
+    V = cal.values_matrix(rec, ["H1", "L1"], params, 3, static=static)
+    assert V.shape == (24, 3) and np.all(V[:12, 2] == 0.02) and np.all(V[12:] == 0.02)
+    with pytest.raises(KeyError):
+        cal.values_matrix(rec, ["H1", "L1"], params, 3)
+    with pytest.raises(ValueError):
+        cal.spline_frequencies({"H1": m, "L1": cal.CubicSpline(20, 512, 7, "l1")}, ["H1", "L1"])

@@ -74,3 +74,29 @@ def test_tidal_terms_in_the_kernel_arithmetic():
         assert abs(pm.loglr_direct(row)[0] - lr0) <= util.tol(lr0)
         lr, hd, hh, perr = pm.loglr_recur(row, return_phase_err=True)
         assert abs(lr - lr0) <= util.tol(lr0) and perr <= pm.phase_tol
+
+
+def test_calibration_arithmetic():
+    """The kernels' calibration maths against the oracle's scipy UnivariateSpline
+    (gwin/calibration.py:142-173): least-squares cubic, closed-form <h|h> with the sextic
+    amplitude factor, and the log-calibration joining the block polynomial."""
+    cfg = util.c1()
+    rng = np.random.default_rng(1)
+    n = 6
+    rec = {d: O.CubicSpline(20., 600., n, d.lower()) for d in cfg.dets}
+    orc = cfg.oracle(recalibration=rec)
+    pm = _plan(cfg, mchirp_min=5.0)
+    pm.set_calibration([rec[d].spline_points for d in cfg.dets])
+    for row in util.draw_bbh(rng, 3, cfg):
+        vals = rng.normal(0, 0.08, (len(cfg.dets), 2, n))
+        kw = dict(zip(util.PARAM_ORDER, row))
+        for i, d in enumerate(cfg.dets):
+            for j in range(n):
+                kw['recalib_amplitude_%s_%d' % (d.lower(), j)] = vals[i, 0, j]
+                kw['recalib_phase_%s_%d' % (d.lower(), j)] = vals[i, 1, j]
+        lr0, hd0, hh0 = orc.loglr(**kw)
+        for fn in (pm.loglr_direct, pm.loglr_recur):
+            lr, hd, hh = fn(row, calib=vals)
+            assert abs(lr - lr0) <= util.tol(lr0)
+            assert np.allclose(hh, list(hh0.values()), rtol=1e-10)
+        assert abs(pm.loglr_recur(row)[0] - lr0) > 1e-3      # the calibration matters

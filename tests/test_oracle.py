@@ -269,6 +269,38 @@ def test_distance_marginalization_restatement():
     assert abs(cfg.oracle(distance_marginalization=(dist, b)).loglr(**q)[0]) < 1e-3
 
 
+def test_calibration_restatement():
+    """gwin/calibration.py:104-173.  Zero values leave the waveform untouched; the factor has
+    modulus 1 + dA; and scipy's default-smoothing UnivariateSpline through calibration-sized
+    values IS the least-squares cubic polynomial (2 knots) -- the property the CUDA path
+    relies on."""
+    from scipy.interpolate import UnivariateSpline
+    rng = np.random.default_rng(8)
+    cs = O.CubicSpline(20., 1024., 7, "h1")
+    assert np.allclose(cs.spline_points, np.logspace(np.log10(20.), np.log10(1024.), 7))
+    with pytest.raises(ValueError):
+        O.CubicSpline(20., 1024., 3, "h1")
+    h = rng.normal(size=2049) + 1j * rng.normal(size=2049)
+    zero = {"recalib_%s_h1_%d" % (w, i): 0. for w in ("amplitude", "phase") for i in range(7)}
+    assert np.allclose(cs.map_to_adjust(h, 0.5, **zero), h, rtol=0, atol=1e-15)
+    vals = dict(zero)
+    amp = rng.normal(0, 0.1, 7)
+    vals.update({"recalib_amplitude_h1_%d" % i: amp[i] for i in range(7)})
+    vals["recalib_phase_l1_0"] = 99.                       # another detector's: ignored
+    out = cs.map_to_adjust(h, 0.5, **vals)
+    f = np.arange(2049) * 0.5
+    spl = UnivariateSpline(cs.spline_points, amp)
+    assert len(spl.get_knots()) == 2
+    lsq = np.polynomial.polynomial.Polynomial.fit(cs.spline_points, amp, 3)
+    assert np.max(np.abs(spl(f) - lsq(f))) < 1e-12
+    assert np.allclose(out, h * (1 + lsq(f)), rtol=1e-12)
+    ph = dict(zero)
+    ph.update({"recalib_phase_h1_%d" % i: amp[i] for i in range(7)})
+    out = cs.map_to_adjust(h, 0.5, **ph)
+    assert np.allclose(np.abs(out), np.abs(h), rtol=1e-13)
+    assert np.allclose(np.angle(out / h), 2 * np.arctan(0.5 * lsq(f)), atol=1e-12)
+
+
 def test_spin_terms_known_limits():
     """1.5PN spin-orbit: equal masses, equal spins => 4 beta = (188/6) chi."""
     a = O.taylorf2_phasing(10., 10., 0.3, 0.3)

@@ -24,18 +24,25 @@ n = np.array([min(int(1.0 / (6 ** 1.5 * np.pi * (a + b) * 4.925491025543576e-06)
               for a, b in P[:, :2]])
 bins = n.mean()
 Pd = torch.tensor(P, device="cuda")
+# CALIB=<n_points>: time the calibrated kernels (cubic-spline model on every detector)
+ncal = int(os.environ.get("CALIB", "0"))
+Cd = None
+if ncal:
+    sf = np.tile(np.logspace(np.log10(cfg.f_lower), np.log10(2048.), ncal), (len(cfg.dets), 1))
+    model.plan.set_calibration(sf)
+    Cd = torch.tensor(rng.normal(0, 0.05, (W, len(cfg.dets) * 2 * ncal)), device="cuda")
 res = {}
 for name in kernels:
     kid = {"direct": 1, "recurrence": 2}[name]
     model.plan.configure(kernel=kid, mchirp_min=1.0, phase_tol=float(os.environ.get("PHASE_TOL", "0")))
-    out = model.plan.loglr_device(Pd)
+    out = model.plan.loglr_device(Pd, calib=Cd)
     torch.cuda.synchronize()
     res[name] = out[0].cpu().numpy()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 5
     e0.record()
     for _ in range(reps):
-        model.plan.loglr_device(Pd, out=out)
+        model.plan.loglr_device(Pd, out=out, calib=Cd)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
@@ -45,7 +52,7 @@ for name in kernels:
     for _ in range(reps):
         flush.fill_(1)
         e0.record()
-        model.plan.loglr_device(Pd, out=out)
+        model.plan.loglr_device(Pd, out=out, calib=Cd)
         e1.record()
         torch.cuda.synchronize()
         cold += e0.elapsed_time(e1) / reps
