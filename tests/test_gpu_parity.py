@@ -306,6 +306,39 @@ def test_tidal_deformabilities(cfg3):
     assert np.all(np.abs(vals - ref) <= tol(np.array(ref)))
 
 
+import glob
+import os
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                                                               "golden", "*.npz"))))
+def test_golden_fixtures(path):
+    """The CUDA path against the COMMITTED golden vectors (tests/golden/make_golden.py): no
+    oracle computation at run time.  Held to the float64-faithful numbers and to the
+    extended-precision 'truth' ones."""
+    g = np.load(path)
+    cfg = util.golden_config(os.path.basename(path))
+    model = cfg.cuda_model()
+    marg = bool(g["marg"])
+    mode = int(marg)
+    calib = None
+    if "dist_marg" in g:
+        model.plan.set_distance_marg(*util.dist_grid(*g["dist_marg"]))
+        mode = 3 if marg else 2
+    if "calib_spec" in g:
+        fmin, fmax, n = g["calib_spec"]
+        sf = np.logspace(np.log10(fmin), np.log10(fmax), int(n))
+        model.plan.set_calibration(np.tile(sf, (len(cfg.dets), 1)))
+        calib = g["calib_values"]
+    assert (model._kmin, model._kmax) == (int(g["kmin"]), int(g["kmax"]))
+    assert abs(model.lognl - float(g["lognl"])) <= 1e-9 * abs(float(g["lognl"]))
+    for kernel in (1, 2):
+        model.plan.configure(kernel=kernel)
+        lr, hd, hh = model.plan.loglr_host(g["params"], mode=mode, calib=calib)
+        _check(lr, hd, hh, g["loglr"], g["hd"], g["hh"], "%s k%d" % (os.path.basename(path), kernel))
+        assert np.all(np.abs(lr - g["loglr_truth"]) <= tol(g["loglr_truth"]))
+
+
 def _dist_grid(lo=50., hi=5000., n=10 ** 4):
     """marginalized_gaussian_noise.py:368-375 with Uniform(distance=(lo, hi)): the prior is 0
     at the closed-open upper bound, i.e. on the last grid point."""

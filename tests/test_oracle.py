@@ -377,22 +377,34 @@ def test_golden_vectors(path):
     oracle and to 1e-7 by the C restatement."""
     g = np.load(path)
     name = os.path.basename(path)
-    cfg = {"c1_gaussian_h1l1.npz": lambda: util.c1(),
-           "c2_margphase_h1l1v1.npz": lambda: util.c2(),
-           "c3_bns256_h1l1v1.npz": lambda: util.c3(),
-           "c2_gps_epoch.npz": lambda: util.c2(epoch=1126259462.0, seed=7)}[name]()
+    cfg = util.golden_config(name)
     import hashlib
     h = hashlib.sha256()
     for d in cfg.dets:
         h.update(np.ascontiguousarray(cfg.data[d]).tobytes())
     assert h.hexdigest() == str(g["data_sha256"]), "synthetic data generator changed"
     marg = bool(g["marg"])
-    orc = cfg.oracle(phase_marginalization=marg)
+    kw = {}
+    if "dist_marg" in g:
+        kw["distance_marginalization"] = util.dist_grid(*g["dist_marg"])
+    orc = cfg.oracle(phase_marginalization=marg, **kw)
     assert (orc._kmin, orc._kmax) == (int(g["kmin"]), int(g["kmax"]))
-    lr, hd, hh = O.batch_loglr(orc, g["params"])
+    if "calib_spec" in g:
+        fmin, fmax, n = g["calib_spec"]
+        rec = {d: O.CubicSpline(fmin, fmax, int(n), d.lower()) for d in cfg.dets}
+        orc = cfg.oracle(phase_marginalization=marg, recalibration=rec, **kw)
+        names = util.calib_names(cfg.dets, int(n))
+        out = [orc.loglr(**dict(list(zip(util.PARAM_ORDER, row)) + list(zip(names, v))))
+               for row, v in zip(g["params"], g["calib_values"])]
+        lr = np.array([o[0] for o in out])
+        hh = np.array([[o[2][d] for d in cfg.dets] for o in out])
+    else:
+        lr, hd, hh = O.batch_loglr(orc, g["params"])
     assert np.max(np.abs(lr - g["loglr"])) <= 1e-9
     assert np.allclose(hh, g["hh"], rtol=1e-12)
     assert np.max(np.abs(lr - g["loglr_truth"])) <= 1e-7
+    if "dist_marg" in g or "calib_spec" in g:
+        return      # the C restatement covers the plain and phase-marginalised likelihoods
     co = COracle(cfg.data, cfg.delta_f, cfg.epoch, cfg.f_lower, psds=cfg.psds())
     lc = co.batch_loglr(g["params"], mode=int(marg), nthreads=2)[0]
     assert np.max(np.abs(lc - g["loglr"])) <= 1e-7

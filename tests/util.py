@@ -145,3 +145,28 @@ def inj_row(cfg):
 def tol(loglr):
     """north_star tolerance: 1e-6 absolute, 1e-9 relative for loglr >> 1."""
     return np.maximum(1e-6, 1e-9 * np.abs(loglr))
+
+
+def dist_grid(lo=50., hi=5000., n=10 ** 4):
+    """marginalized_gaussian_noise.py:368-375 with Uniform(distance=(lo, hi)): the grid and
+    ``deltad * dist_prior`` (0 on the last point: the prior's upper bound is open)."""
+    dist = np.linspace(lo, hi, n)
+    return dist, (dist[1] - dist[0]) * np.where(dist < hi, 1. / (hi - lo), 0.)
+
+
+def calib_names(dets, n_points):
+    """``recalib_*`` parameter names in kernel order (calibration.py:151-161)."""
+    return ["recalib_%s_%s_%d" % (which, d.lower(), i) for d in dets
+            for which in ("amplitude", "phase") for i in range(n_points)]
+
+
+def golden_config(name):
+    """The synthetic-data configuration behind tests/golden/<name> (make_golden.py)."""
+    return {"c1_gaussian_h1l1.npz": lambda: c1(),
+            "c2_margphase_h1l1v1.npz": lambda: c2(),
+            "c3_bns256_h1l1v1.npz": lambda: c3(),
+            "c2_gps_epoch.npz": lambda: c2(epoch=1126259462.0, seed=7),
+            "c3s32_tidal.npz": lambda: c3(seglen=32),
+            "c2_margdist.npz": lambda: c2(),
+            "c2_margdistphase.npz": lambda: c2(),
+            "c2_calibrated.npz": lambda: c2()}[name]()

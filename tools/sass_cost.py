@@ -16,7 +16,7 @@ for i, (a, t) in enumerate(ins):
     lo = int(m.group(1), 16)
     body = [x for x in ins if lo <= x[0] <= a]
     fp = [x for x in body if re.search(r'\b(DFMA|DMUL|DADD)\b', x[1])]
-    if len(fp) < 100 or len(body) > 260: continue
+    if len(fp) < int(__import__("os").environ.get("MINFP", "100")) or len(body) > int(__import__("os").environ.get("MAXBODY", "260")): continue
     cost, prev, nre = 0, set(), 0
     for _, t2 in body:
         mm = re.match(r'(@!?P\d+\s+)?(DFMA|DMUL|DADD)\s+(\S+),\s*(.*)', t2)
