@@ -43,7 +43,7 @@ SYMBOLS = (
     "gwin_plan_last_launches",
     "gwin_plan_kernel_timing",
     "gwin_ens_propose", "gwin_ens_prior", "gwin_ens_accept", "gwin_ens_swap",
-    "gwin_ens_swap_all",
+    "gwin_ens_swap_all", "gwin_ens_record", "gwin_ens_tick",
     "gwin_fp64_peak", "gwin_fp64_probe", "gwin_last_error", "gwin_version",
 )
 
@@ -171,16 +171,22 @@ def load():
         lib.gwin_fp64_peak.argtypes = [C.c_int, dp]
         vp, u64, u32, ci, cd = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_double
         lib.gwin_ens_propose.restype = ci
-        lib.gwin_ens_propose.argtypes = [u64, u32, ci, ci, ci, ci, cd, ci, ci, vp, vp, vp, vp]
+        lib.gwin_ens_propose.argtypes = [u64, u32, vp, ci, ci, ci, ci, cd, ci, ci, vp, vp, vp, vp]
         lib.gwin_ens_prior.restype = ci
         lib.gwin_ens_prior.argtypes = [C.POINTER(PriorSpec), C.c_int64, vp, vp, vp, vp, vp]
         lib.gwin_ens_accept.restype = ci
-        lib.gwin_ens_accept.argtypes = [u64, u32, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp,
+        lib.gwin_ens_accept.argtypes = [u64, u32, vp, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp,
                                         vp, vp, vp, vp, vp]
         lib.gwin_ens_swap.restype = ci
-        lib.gwin_ens_swap.argtypes = [u64, u32, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp]
+        lib.gwin_ens_swap.argtypes = [u64, u32, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp]
         lib.gwin_ens_swap_all.restype = ci
-        lib.gwin_ens_swap_all.argtypes = [u64, u32, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp]
+        lib.gwin_ens_swap_all.argtypes = [u64, u32, vp, ci, ci, ci, vp, vp, C.c_int64,
+                                          vp, vp, vp, vp, vp]
+        lib.gwin_ens_record.restype = ci
+        lib.gwin_ens_record.argtypes = [C.c_int64, ci, C.c_int64, u32, vp,
+                                        vp, vp, vp, vp, vp, vp, vp]
+        lib.gwin_ens_tick.restype = ci
+        lib.gwin_ens_tick.argtypes = [vp, vp]
         lib.gwin_fp64_probe.restype = C.c_int
         lib.gwin_fp64_probe.argtypes = [C.c_int, C.c_int, dp]
         lib.gwin_last_error.restype = C.c_char_p

@@ -229,6 +229,16 @@ __device__ __forceinline__ double2 cfma(double2 a, double2 b, double2 c) {
     return make_double2(fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y)));
 }
 
+// One Horner step of the recurrence hot loop: acc <- acc g + T ; g <- g r.
+// (Emitting these eight instructions as inline PTX in an order where each shares a source
+// register with its predecessor does not survive ptxas, which re-schedules them; the
+// modelled operand-fetch cost stays at ~82 % of the DFMA rate either way, tools/sass_cost.py.)
+__device__ __forceinline__ void horner_step(double2& acc, double2& g, const double2 T, const double2 r) {
+    acc = cfma(acc, g, T);
+    g = cmul(g, r);
+}
+__device__ __forceinline__ void phasor_step(double2& r, const double2 s) { r = cmul(r, s); }
+
 __device__ __forceinline__ double4 ld_basis(const double4* p) {
     const double2 a = __ldg(reinterpret_cast<const double2*>(p));
     const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
@@ -953,11 +963,10 @@ __device__ __forceinline__ void recur_block(
             for (int d = 0; d < ND; ++d) {
                 double2 Tk = sp[d];
                 if (MASKED && !on) Tk = make_double2(0.0, 0.0);
-                acc[d] = cfma(acc[d], g[d], Tk);
-                g[d] = cmul(g[d], rq);
+                horner_step(acc[d], g[d], Tk, rq);
             }
-            rq = cmul(rq, sq);
-            if (DEG == 4) sq = cmul(sq, tq);
+            phasor_step(rq, sq);
+            if (DEG == 4) phasor_step(sq, tq);
         }
     }
 #pragma unroll

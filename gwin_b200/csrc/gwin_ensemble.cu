@@ -68,13 +68,15 @@ __device__ __forceinline__ int half_index(int j, int half, int nwalkers, int int
 //   move 0: emcee EnsembleSampler  z = ((a-1)u+1)^2/a,      q = c - z (c - s),  factor (ndim-1) ln z
 //   move 1: emcee PTSampler        z = exp(U(-ln a, ln a)), q = c + z (s - c),  factor  ndim    ln z
 // ---------------------------------------------------------------------------
-__global__ void ens_propose_kernel(uint64_t seed, uint32_t iter, int half, int ntemps, int nwalkers, int ndim,
+__global__ void ens_propose_kernel(uint64_t seed, uint32_t iter, const uint32_t* __restrict__ iter_dev,
+                                   int half, int ntemps, int nwalkers, int ndim,
                                    double a, int move, int interleaved,
                                    const double* __restrict__ p, double* __restrict__ q,
                                    double* __restrict__ logfac) {
     const int nh = nwalkers / 2;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ntemps * nh) return;
+    if (iter_dev) iter += *iter_dev;
     const int k = i / nh, j = i % nh;
     uint32_t r[4];
     philox4x32(seed, iter, (uint32_t)(STAGE_PROPOSE * 4 + half), (uint32_t)i, 0u, r);
@@ -172,7 +174,8 @@ __global__ void ens_prior_kernel(gwin_prior_spec_dev S, int W, const double* __r
 // ---------------------------------------------------------------------------
 // accept:  ln r < logfac + (beta*logl_q + logp_q) - lnprob_s
 // ---------------------------------------------------------------------------
-__global__ void ens_accept_kernel(uint64_t seed, uint32_t iter, int half, int ntemps, int nwalkers, int ndim,
+__global__ void ens_accept_kernel(uint64_t seed, uint32_t iter, const uint32_t* __restrict__ iter_dev,
+                                  int half, int ntemps, int nwalkers, int ndim,
                                   int interleaved, const double* __restrict__ betas,
                                   const double* __restrict__ q, const double* __restrict__ logfac,
                                   const double* __restrict__ q_logl, const double* __restrict__ q_logp,
@@ -182,6 +185,7 @@ __global__ void ens_accept_kernel(uint64_t seed, uint32_t iter, int half, int nt
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ntemps * nh) return;
     const int k = i / nh, j = i % nh;
+    if (iter_dev) iter += *iter_dev;
     uint32_t r[4];
     philox4x32(seed, iter, (uint32_t)(STAGE_ACCEPT * 4 + half), (uint32_t)i, 0u, r);
     double u0, u1;
@@ -204,13 +208,15 @@ __global__ void ens_accept_kernel(uint64_t seed, uint32_t iter, int half, int nt
 // temperature swap between chains i and i-1 (emcee PTSampler._temperature_swaps); iperm / i1perm
 // are random permutations of the walkers supplied by the caller.
 // ---------------------------------------------------------------------------
-__global__ void ens_swap_kernel(uint64_t seed, uint32_t iter, int level, int nwalkers, int ndim,
+__global__ void ens_swap_kernel(uint64_t seed, uint32_t iter, const uint32_t* __restrict__ iter_dev,
+                                int level, int nwalkers, int ndim,
                                 const double* __restrict__ betas, const int* __restrict__ iperm,
                                 const int* __restrict__ i1perm, double* __restrict__ p,
                                 double* __restrict__ logl, double* __restrict__ lnprob,
                                 int* __restrict__ nswap_accepted) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= nwalkers) return;
+    if (iter_dev) iter += *iter_dev;
     uint32_t r[4];
     philox4x32(seed, iter, (uint32_t)(STAGE_SWAP * 4), (uint32_t)(level * nwalkers + j), 0u, r);
     double u0, u1;
@@ -238,10 +244,12 @@ __global__ void ens_swap_kernel(uint64_t seed, uint32_t iter, int level, int nwa
 // l-1 as level l left it.  perms: [ntemps-1][2][nwalkers]; entry (ntemps-1-level) holds the two
 // permutations whose elements are paired.
 __global__ void __launch_bounds__(1024)
-ens_swap_all_kernel(uint64_t seed, uint32_t iter, int ntemps, int nwalkers, int ndim,
-                    const double* __restrict__ betas, const int* __restrict__ perms,
+ens_swap_all_kernel(uint64_t seed, uint32_t iter, const uint32_t* __restrict__ iter_dev,
+                    int ntemps, int nwalkers, int ndim,
+                    const double* __restrict__ betas, const int* __restrict__ perms, int64_t perm_stride,
                     double* __restrict__ p, double* __restrict__ logl, double* __restrict__ lnprob,
                     int* __restrict__ nswap_accepted) {
+    if (iter_dev) { iter += *iter_dev; perms += (size_t)(*iter_dev) * perm_stride; }
     for (int level = ntemps - 1; level >= 1; --level) {
         const int* iperm = perms + (size_t)(ntemps - 1 - level) * 2 * nwalkers;
         const int* i1perm = iperm + nwalkers;
@@ -271,6 +279,24 @@ ens_swap_all_kernel(uint64_t seed, uint32_t iter, int ntemps, int nwalkers, int 
     }
 }
 
+// History row `it (+ *it_dev)` of the chain [W][niter][ndim], lnprob [W][niter], logl [W][niter]
+__global__ void ens_record_kernel(int W, int ndim, int niter, uint32_t it, const uint32_t* __restrict__ it_dev,
+                                  const double* __restrict__ p, const double* __restrict__ lnprob,
+                                  const double* __restrict__ logl, double* __restrict__ chain,
+                                  double* __restrict__ lnp_h, double* __restrict__ lnl_h) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= W * ndim) return;
+    if (it_dev) it += *it_dev;
+    if (it >= (uint32_t)niter) return;
+    const int w = i / ndim, d = i % ndim;
+    chain[((size_t)w * niter + it) * ndim + d] = p[i];
+    if (d == 0) {
+        lnp_h[(size_t)w * niter + it] = lnprob[w];
+        lnl_h[(size_t)w * niter + it] = logl[w];
+    }
+}
+__global__ void ens_tick_kernel(uint32_t* counter) { *counter += 1u; }
+
 // ---------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------
@@ -283,14 +309,15 @@ static int check_dims(int ntemps, int nwalkers, int ndim) {
     return GWIN_OK;
 }
 
-extern "C" int gwin_ens_propose(uint64_t seed, uint32_t iter, int half, int ntemps, int nwalkers, int ndim,
+extern "C" int gwin_ens_propose(uint64_t seed, uint32_t iter, const uint32_t* iter_dev,
+                                int half, int ntemps, int nwalkers, int ndim,
                                 double a, int move, int interleaved,
                                 const double* p, double* q, double* logfac, void* stream) {
     int rc = check_dims(ntemps, nwalkers, ndim);
     if (rc) return rc;
     if (!p || !q || !logfac) return gwin_fail(GWIN_EINVAL, "NULL buffer");
     const int n = ntemps * (nwalkers / 2);
-    ens_propose_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(seed, iter, half, ntemps, nwalkers, ndim,
+    ens_propose_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(seed, iter, iter_dev, half, ntemps, nwalkers, ndim,
                                                                            a, move, interleaved, p, q, logfac);
     CKE(cudaGetLastError());
     return GWIN_OK;
@@ -313,40 +340,62 @@ extern "C" int gwin_ens_prior(const gwin_prior_spec* spec, int64_t W, const doub
     return GWIN_OK;
 }
 
-extern "C" int gwin_ens_accept(uint64_t seed, uint32_t iter, int half, int ntemps, int nwalkers, int ndim,
+extern "C" int gwin_ens_accept(uint64_t seed, uint32_t iter, const uint32_t* iter_dev,
+                               int half, int ntemps, int nwalkers, int ndim,
                                int interleaved, const double* betas, const double* q, const double* logfac,
                                const double* q_logl, const double* q_logp,
                                double* p, double* logl, double* lnprob, int* naccept, void* stream) {
     int rc = check_dims(ntemps, nwalkers, ndim);
     if (rc) return rc;
     const int n = ntemps * (nwalkers / 2);
-    ens_accept_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(seed, iter, half, ntemps, nwalkers, ndim,
+    ens_accept_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(seed, iter, iter_dev, half, ntemps, nwalkers, ndim,
                                                                           interleaved, betas, q, logfac, q_logl, q_logp,
                                                                           p, logl, lnprob, naccept);
     CKE(cudaGetLastError());
     return GWIN_OK;
 }
 
-extern "C" int gwin_ens_swap(uint64_t seed, uint32_t iter, int level, int nwalkers, int ndim,
+extern "C" int gwin_ens_swap(uint64_t seed, uint32_t iter, const uint32_t* iter_dev, int level, int nwalkers, int ndim,
                              const double* betas, const int* iperm, const int* i1perm,
                              double* p, double* logl, double* lnprob, int* nswap_accepted, void* stream) {
     if (level < 1 || nwalkers < 1 || ndim < 1) return gwin_fail(GWIN_EINVAL, "bad swap arguments");
-    ens_swap_kernel<<<(nwalkers + 127) / 128, 128, 0, (cudaStream_t)stream>>>(seed, iter, level, nwalkers, ndim, betas,
+    ens_swap_kernel<<<(nwalkers + 127) / 128, 128, 0, (cudaStream_t)stream>>>(seed, iter, iter_dev, level, nwalkers, ndim, betas,
                                                                               iperm, i1perm, p, logl, lnprob,
                                                                               nswap_accepted);
     CKE(cudaGetLastError());
     return GWIN_OK;
 }
 
-extern "C" int gwin_ens_swap_all(uint64_t seed, uint32_t iter, int ntemps, int nwalkers, int ndim,
-                                 const double* betas, const int* perms,
+extern "C" int gwin_ens_swap_all(uint64_t seed, uint32_t iter, const uint32_t* iter_dev,
+                                 int ntemps, int nwalkers, int ndim,
+                                 const double* betas, const int* perms, int64_t perm_stride,
                                  double* p, double* logl, double* lnprob, int* nswap_accepted, void* stream) {
     if (ntemps < 2) return GWIN_OK;
     if (nwalkers < 1 || ndim < 1 || !betas || !perms || !p || !logl || !lnprob || !nswap_accepted)
         return gwin_fail(GWIN_EINVAL, "bad swap arguments");
     const int threads = nwalkers >= 1024 ? 1024 : ((nwalkers + 31) / 32) * 32;
-    ens_swap_all_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(seed, iter, ntemps, nwalkers, ndim, betas, perms,
-                                                                 p, logl, lnprob, nswap_accepted);
+    ens_swap_all_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(seed, iter, iter_dev, ntemps, nwalkers, ndim, betas, perms,
+                                                                 perm_stride, p, logl, lnprob, nswap_accepted);
+    CKE(cudaGetLastError());
+    return GWIN_OK;
+}
+
+extern "C" int gwin_ens_record(int64_t W, int ndim, int64_t niter, uint32_t it, const uint32_t* it_dev,
+                               const double* p, const double* lnprob, const double* logl,
+                               double* chain, double* lnp_h, double* lnl_h, void* stream) {
+    if (W < 1 || ndim < 1 || niter < 1 || W * ndim > (1 << 30) || niter > (1u << 31) - 1)
+        return gwin_fail(GWIN_EINVAL, "bad history dimensions");
+    if (!p || !lnprob || !logl || !chain || !lnp_h || !lnl_h) return gwin_fail(GWIN_EINVAL, "NULL buffer");
+    const int n = (int)(W * ndim);
+    ens_record_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((int)W, ndim, (int)niter, it, it_dev,
+                                                                        p, lnprob, logl, chain, lnp_h, lnl_h);
+    CKE(cudaGetLastError());
+    return GWIN_OK;
+}
+
+extern "C" int gwin_ens_tick(uint32_t* counter, void* stream) {
+    if (!counter) return gwin_fail(GWIN_EINVAL, "counter is NULL");
+    ens_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter);
     CKE(cudaGetLastError());
     return GWIN_OK;
 }

@@ -15,6 +15,7 @@ UniformRadius / UniformSky without constraints, no sampling transforms, and the
 only waveform transform understood is (mchirp, q) -> (mass1, mass2).
 """
 import ctypes as C
+import os
 
 import numpy
 
@@ -233,6 +234,8 @@ class _DeviceEnsemble(BaseMCMCSampler):
         return self._p0
 
     _keep_temp_axis = True
+    # one CUDA graph per iteration (see run()); GWIN_SAMPLER_GRAPH=0 turns it off
+    use_graph = os.environ.get("GWIN_SAMPLER_GRAPH", "1") != "0"
 
     def _initialise(self, p0):
         torch = self._torch
@@ -256,20 +259,25 @@ class _DeviceEnsemble(BaseMCMCSampler):
         self._p, self._logl, self._lnprob = p, logl.contiguous(), lnprob.contiguous()
 
     def run(self, niterations, **kwargs):
+        """``niterations`` steps.  All arguments of one iteration are constant -- the
+        iteration number lives in a device counter -- so the iteration is recorded once as a
+        CUDA graph and replayed (``use_graph=False`` or ``GWIN_SAMPLER_GRAPH=0`` launches
+        every kernel from the host instead; the chains are identical)."""
         torch, lib = self._torch, self._lib
         if self._p is None:
             self._initialise(self.p0)
         nt, nw, nd = self._ntemps, self._nwalkers, self._ndim
+        W = nt * nw
         f64 = dict(dtype=torch.float64, device=self._dev)
         chain = torch.empty((nt, nw, niterations, nd), **f64)
         lnp_h = torch.empty((nt, nw, niterations), **f64)
         lnl_h = torch.empty((nt, nw, niterations), **f64)
         q_loglr = torch.empty(self._Wh, **f64)
+        g0 = self._iterations + self._iter0          # global iteration of this call's first step
         perms = None
         if nt > 1:
             # replicated host RNG for the swap pairings, keyed by (seed, global iteration):
             # identical on every rank and independent of how a run is split into run() calls
-            g0 = self._iterations + self._iter0
             perms = numpy.empty((niterations, nt - 1, 2, nw), dtype=numpy.int32)
             for it in range(niterations):
                 rs = numpy.random.RandomState((self._seed * 1000003 + g0 + it) % (2 ** 32))
@@ -277,30 +285,66 @@ class _DeviceEnsemble(BaseMCMCSampler):
                     perms[it, lv, 0] = rs.permutation(nw)
                     perms[it, lv, 1] = rs.permutation(nw)
             perms = torch.tensor(perms, device=self._dev)
-        st = torch.cuda.current_stream(self._dev).cuda_stream
-        for it in range(niterations):
-            gi = self._iterations + self._iter0
+        ctr = torch.zeros(1, dtype=torch.int32, device=self._dev)   # iteration within this call
+
+        def iteration():
+            st = torch.cuda.current_stream(self._dev).cuda_stream
             for half in (0, 1):
                 _lib.check(lib.gwin_ens_propose(
-                    self._seed, gi, half, nt, nw, nd, self._a, self._move, self._interleaved,
-                    self._p.data_ptr(), self._q.data_ptr(), self._logfac.data_ptr(), st))
+                    self._seed, g0, ctr.data_ptr(), half, nt, nw, nd, self._a, self._move,
+                    self._interleaved, self._p.data_ptr(), self._q.data_ptr(),
+                    self._logfac.data_ptr(), st))
                 self._eval_q(self._Wh, self._q, self._q_logp, self._skip, self._params, q_loglr)
                 _lib.check(lib.gwin_ens_accept(
-                    self._seed, gi, half, nt, nw, nd, self._interleaved, self._betas.data_ptr(),
-                    self._q.data_ptr(), self._logfac.data_ptr(), q_loglr.data_ptr(),
-                    self._q_logp.data_ptr(), self._p.data_ptr(), self._logl.data_ptr(),
-                    self._lnprob.data_ptr(), self._naccept.data_ptr(), st))
+                    self._seed, g0, ctr.data_ptr(), half, nt, nw, nd, self._interleaved,
+                    self._betas.data_ptr(), self._q.data_ptr(), self._logfac.data_ptr(),
+                    q_loglr.data_ptr(), self._q_logp.data_ptr(), self._p.data_ptr(),
+                    self._logl.data_ptr(), self._lnprob.data_ptr(), self._naccept.data_ptr(), st))
             if nt > 1:
                 _lib.check(lib.gwin_ens_swap_all(
-                    self._seed, gi, nt, nw, nd, self._betas.data_ptr(),
-                    perms.data_ptr() + it * (nt - 1) * 2 * nw * 4, self._p.data_ptr(),
+                    self._seed, g0, ctr.data_ptr(), nt, nw, nd, self._betas.data_ptr(),
+                    perms.data_ptr(), (nt - 1) * 2 * nw, self._p.data_ptr(),
                     self._logl.data_ptr(), self._lnprob.data_ptr(), self._nswap_acc.data_ptr(), st))
-            if nt > 1:
-                self._nswap += nw
-            chain[:, :, it, :].copy_(self._p)
-            lnp_h[:, :, it].copy_(self._lnprob)
-            lnl_h[:, :, it].copy_(self._logl)
-            self._iterations += 1
+            _lib.check(lib.gwin_ens_record(
+                W, nd, niterations, 0, ctr.data_ptr(), self._p.data_ptr(), self._lnprob.data_ptr(),
+                self._logl.data_ptr(), chain.data_ptr(), lnp_h.data_ptr(), lnl_h.data_ptr(), st))
+            _lib.check(lib.gwin_ens_tick(ctr.data_ptr(), st))
+
+        # recording costs ~50 ms: by default only runs long enough to repay it are recorded
+        if "use_graph" in kwargs:
+            use_graph = bool(kwargs["use_graph"]) and niterations >= 4
+        else:
+            use_graph = self.use_graph and niterations >= 64
+        if use_graph and self._world > 1:
+            # recording the NCCL all-gather into a graph hung on the B200 pool (torch 2.11,
+            # NCCL 2.28.9); multi-GPU runs launch kernel by kernel -- the host is an order of
+            # magnitude ahead of the device there anyway
+            use_graph = False
+        if use_graph:
+            # the first iteration runs eagerly on the capture stream (workspaces, the NCCL
+            # communicator and the block schedule come into being here), the second is
+            # recorded, the rest are replays of the record
+            cur = torch.cuda.current_stream(self._dev)
+            side = torch.cuda.Stream(self._dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                iteration()
+            cur.wait_stream(side)
+            torch.cuda.synchronize(self._dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                iteration()
+            for _ in range(niterations - 1):
+                graph.replay()
+            self._graph_keepalive = (graph, chain, lnp_h, lnl_h, perms, ctr, q_loglr)
+        else:
+            for _ in range(niterations):
+                iteration()
+        if use_graph:       # the record pass counted one replay; the others ran without Python
+            self.likelihood_evals += 2 * self._Wh * (niterations - 2)
+        if nt > 1:
+            self._nswap += nw * niterations
+        self._iterations += niterations
         # histories stay on the device until somebody reads them (chain / lnpost / model_stats)
         self._pending.append((chain, lnp_h, lnl_h))
         self._pos = None

@@ -227,7 +227,8 @@ typedef struct gwin_prior_spec {
  *   p [ntemps][nwalkers][ndim] -> q [ntemps][nwalkers/2][ndim], logfac [ntemps][nwalkers/2]
  *   move 0: EnsembleSampler (z = ((a-1)u+1)^2/a, logfac = (ndim-1) ln z), halves are contiguous
  *   move 1: PTSampler       (ln z ~ U(-ln a, ln a),  logfac = ndim ln z), halves are interleaved */
-int gwin_ens_propose(uint64_t seed, uint32_t iter, int half, int ntemps, int nwalkers, int ndim,
+int gwin_ens_propose(uint64_t seed, uint32_t iter, const uint32_t* iter_dev,
+                     int half, int ntemps, int nwalkers, int ndim,
                      double a, int move, int interleaved,
                      const double* p, double* q, double* logfac, void* stream);
 
@@ -240,22 +241,37 @@ int gwin_ens_prior(const gwin_prior_spec* spec, int64_t W, const double* q,
 
 /* Accept/reject: ln u < logfac + (beta_k q_logl + q_logp) - lnprob; updates p, logl, lnprob
  * ([ntemps][nwalkers]...) and the per-walker acceptance counters. */
-int gwin_ens_accept(uint64_t seed, uint32_t iter, int half, int ntemps, int nwalkers, int ndim,
+int gwin_ens_accept(uint64_t seed, uint32_t iter, const uint32_t* iter_dev,
+                    int half, int ntemps, int nwalkers, int ndim,
                     int interleaved, const double* betas, const double* q, const double* logfac,
                     const double* q_logl, const double* q_logp,
                     double* p, double* logl, double* lnprob, int* naccept, void* stream);
 
 /* Swap attempt between temperature `level` and `level-1` for the walker pairs
  * (iperm[j], i1perm[j]) (emcee PTSampler._temperature_swaps). */
-int gwin_ens_swap(uint64_t seed, uint32_t iter, int level, int nwalkers, int ndim,
+int gwin_ens_swap(uint64_t seed, uint32_t iter, const uint32_t* iter_dev, int level, int nwalkers, int ndim,
                   const double* betas, const int* iperm, const int* i1perm,
                   double* p, double* logl, double* lnprob, int* nswap_accepted, void* stream);
 
 /* All swap levels ntemps-1 .. 1 of one iteration in a single launch; perms is
- * [ntemps-1][2][nwalkers] (entry ntemps-1-level holds iperm, i1perm of that level). */
-int gwin_ens_swap_all(uint64_t seed, uint32_t iter, int ntemps, int nwalkers, int ndim,
-                      const double* betas, const int* perms,
+ * [ntemps-1][2][nwalkers] (entry ntemps-1-level holds iperm, i1perm of that level); with a
+ * device counter the kernel reads the block perms + *iter_dev * perm_stride. */
+int gwin_ens_swap_all(uint64_t seed, uint32_t iter, const uint32_t* iter_dev,
+                      int ntemps, int nwalkers, int ndim,
+                      const double* betas, const int* perms, int64_t perm_stride,
                       double* p, double* logl, double* lnprob, int* nswap_accepted, void* stream);
+
+/* Sampler iteration as ONE CUDA graph: every gwin_ens_* call above takes, besides the scalar
+ * iteration `iter`, an optional DEVICE counter iter_dev (NULL = 0); the Philox key uses
+ * iter + *iter_dev.  With the counter the argument lists of one iteration no longer change, so
+ * the whole iteration (proposals, priors, likelihood launches, all-gather, accept, swaps,
+ * history) can be captured once and replayed; gwin_ens_tick advances the counter at its end.
+ * gwin_ens_record writes row it + *it_dev of the histories chain [W][niter][ndim],
+ * lnp_h / lnl_h [W][niter] (what emcee's sample() appends per iteration). */
+int gwin_ens_record(int64_t W, int ndim, int64_t niter, uint32_t it, const uint32_t* it_dev,
+                    const double* p, const double* lnprob, const double* logl,
+                    double* chain, double* lnp_h, double* lnl_h, void* stream);
+int gwin_ens_tick(uint32_t* counter, void* stream);
 
 /* FP64 issue-rate micro-benchmark on the plan's device: runs a dependent-chain-free
  * DFMA loop and returns achieved FP64 FMA lane-ops per second. */

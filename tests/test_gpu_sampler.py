@@ -201,3 +201,32 @@ def test_device_sampler_checkpoint_resume(tmp_path):
     b.run(6)
     assert b.niterations == 12
     np.testing.assert_array_equal(b.chain, ref.chain[:, :, 6:, :])
+
+
+@pytest.mark.parametrize("ntemps", [1, 3])
+def test_graph_replay_equals_host_launched_iterations(ntemps):
+    """One iteration recorded as a CUDA graph and replayed gives the chains of the
+    kernel-by-kernel loop bit for bit (the iteration number is a device counter in both),
+    also when a run is split into several run() calls."""
+    cfg = util.c2()
+    names = ['tc', 'distance']
+    prior = D.JointDistribution(names, D.Uniform(tc=(cfg.inj['tc'] - 0.05, cfg.inj['tc'] + 0.05)),
+                                D.UniformRadius(distance=(50., 2000.)))
+    model = _model(cfg, names, prior)
+
+    def make():
+        np.random.seed(21)
+        s = CudaPTSampler(model, ntemps, 32, seed=5) if ntemps > 1 else CudaEnsembleSampler(model, 32, seed=5)
+        s.set_p0()
+        return s
+    eager = make()
+    eager.run(15, use_graph=False)
+    graph = make()
+    graph.run(9, use_graph=True)
+    graph.run(6, use_graph=True)
+    np.testing.assert_array_equal(graph.chain, eager.chain)
+    np.testing.assert_array_equal(graph.lnpost, eager.lnpost)
+    np.testing.assert_array_equal(graph.acceptance_fraction, eager.acceptance_fraction)
+    assert graph.likelihood_evals == eager.likelihood_evals
+    if ntemps > 1:
+        np.testing.assert_array_equal(graph.tswap_acceptance_fraction, eager.tswap_acceptance_fraction)
