@@ -201,22 +201,28 @@ class _DeviceEnsemble(BaseMCMCSampler):
         st = torch.cuda.current_stream(self._dev).cuda_stream
         _lib.check(lib.gwin_ens_prior(C.byref(self._spec), W, q.data_ptr(), q_logp.data_ptr(),
                                       skip.data_ptr(), params.data_ptr(), st))
-        wmax = -(-W // self._world)
-        a = min(self._rank * wmax, W)
-        b = min(a + wmax, W)
         if self._world == 1:
             _lib.check(lib.gwin_loglr_batch_strided(
                 self._plan._h, self.model._mode, W, params.data_ptr(), 1, W, skip.data_ptr(),
                 out_loglr.data_ptr(), None, None, st))
         else:
+            # round-robin shard: this rank evaluates points rank, rank + world, ... (hot chains
+            # propose many more points outside the prior than cold ones; contiguous slices of a
+            # temperature-ordered batch would be unbalanced).  params is [13][W]: the strided
+            # entry point walks it in place; the skip mask is compacted.
+            world, rank = self._world, self._rank
+            wmax = -(-W // world)
+            n = max(0, -(-(W - rank) // world))
             local = self._local[:wmax]
-            if b > a:
+            if n > 0:
+                skip_l = skip[rank:W:world].contiguous()
                 _lib.check(lib.gwin_loglr_batch_strided(
-                    self._plan._h, self.model._mode, b - a, params.data_ptr() + 8 * a, 1, W,
-                    skip.data_ptr() + a, local.data_ptr(), None, None, st))
-            gath = self._gath[:self._world * wmax]
+                    self._plan._h, self.model._mode, n, params.data_ptr() + 8 * rank, world, W,
+                    skip_l.data_ptr(), local.data_ptr(), None, None, st))
+            gath = self._gath[:world * wmax]
             torch.distributed.all_gather_into_tensor(gath, local, group=self._group)
-            out_loglr[:W].copy_(gath[:W])
+            # entry j of rank r is point j * world + r
+            out_loglr[:W].copy_(gath.view(world, wmax).t().reshape(-1)[:W])
         self.likelihood_evals += W
 
     def set_p0(self, samples_file=None, prior=None):

@@ -40,7 +40,8 @@ def _worker(rank, world, port, out):
     static = {k: v for k, v in cfg.inj.items() if k not in ('tc', 'distance')}
     m = OracleGaussianNoise(['tc', 'distance'], cfg, static_params=static, prior=prior, nthreads=1)
     shard = WalkerSharding()
-    assert shard.bounds(7) == [0, 4, 7] and shard.my_slice(7) == ((0, 4), (4, 7))[rank]
+    assert list(range(7))[shard.my_slice(7)] == ([0, 2, 4, 6], [1, 3, 5])[rank]
+    assert shard.count(7) == (4, 3)[rank] and shard.count(1, rank=1) == 0
     pool = BatchPool(shard=shard)
     call = models.CallModel(m, 'logplr')
     rng = np.random.RandomState(0)      # same points on every rank

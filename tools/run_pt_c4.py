@@ -80,9 +80,9 @@ else:
 if rank == 0:
     sw = pt.tswap_acceptance_fraction if resident else pt.sampler.tswap_acceptance_fraction
     print("C4 PT (%s stepper): %d GPUs, %d temps x %d walkers, %d iterations, T=%d s: %.3f s -> %.4e likelihood evals/s "
-          "(whole sampler path); chains identical on all ranks: %s; cold-chain acceptance %.2f; swap acceptance %s"
+          "(whole sampler path); chains identical on all ranks: %s (checksum %.9f); cold-chain acceptance %.2f; swap acceptance %s"
           % ("device-resident" if resident else "host", world, ntemps, nwalkers, niter, seglen, dt, evals / dt, same,
-             pt.acceptance_fraction[0].mean(), np.round(sw, 2)))
+             chk, pt.acceptance_fraction[0].mean(), np.round(sw, 2)))
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()
