@@ -29,7 +29,7 @@ MODE_GAUSSIAN = 0
 MODE_MARG_PHASE = 1
 MODE_MARG_DIST = 2
 MODE_MARG_DIST_PHASE = 3
-KERNEL_AUTO, KERNEL_DIRECT, KERNEL_RECURRENCE = 0, 1, 2
+KERNEL_AUTO, KERNEL_DIRECT, KERNEL_RECURRENCE, KERNEL_TABLE = 0, 1, 2, 3
 
 # Every symbol include/gwin_b200.h declares (checked by tests/test_abi.py).
 SYMBOLS = (

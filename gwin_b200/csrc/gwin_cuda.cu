@@ -114,6 +114,21 @@ struct BlockMat {
     int pad[3];
 };
 
+// Table kernel: sub-block moments of the data looked up by a type-2 NUFFT
+#define TAB_DEG 6            // degree of the Taylor polynomial of e^{-2 pi i R(j)}
+#define TAB_W 13             // taps of the exponential-of-semicircle interpolation kernel
+#define TAB_BETA (2.30 * TAB_W)
+#define TAB_MIN 256          // shortest / longest sub-block [bins], powers of two
+#define TAB_MAX 2048
+#define TAB_RHO 0.007        // bound on |R| at the sub-block edge [rad]: truncation error ~ rho^4/24
+struct TabMat {
+    double c[16];   // t_i = sum_j c[4 (i-1) + j] (th_{x_j} - th_centre), i = 1..4, j over nodes 0,1,3,4
+    int node[5];    // node offsets from the sub-block start; node[2] = m/2 is the centre
+    int m;
+    int hat_off;    // offset of this length's 1/phi_hat[j] in the invhat array
+    int pad;
+};
+
 struct gwin_plan {
     int device;
     PlanDev d;
@@ -146,6 +161,18 @@ struct gwin_plan {
     std::vector<double> w73;
     double *d_calM, *d_Ccal;
     double *h_calib, *d_calib; size_t calib_cap;
+    // table kernel: sub-block schedule above k_split, moment tables
+    std::vector<int> tab_start, tab_mi;
+    std::vector<int64_t> tab_off;
+    std::vector<TabMat> tabmats;
+    int n_tblk, k_split, n_blk_low;
+    bool tab_dirty;
+    int *d_tab_start, *d_tab_mi, *d_ke_low;
+    int64_t* d_tab_off;
+    TabMat* d_tabmats;
+    double* d_invhat;
+    double2* d_tab;
+    double2* d_partialT; size_t partialT_cap;
     // distance marginalisation grid (1/D_j, log w_j) and the per-walker (x, opt) hand-over
     int n_marg;
     double *d_marg_u, *d_marg_logw, *d_marg_opt;
@@ -354,7 +381,8 @@ __global__ void walker_setup_kernel(PlanDev P, int W, int wpad,
                                     double* __restrict__ wc, int* __restrict__ ks_arr,
                                     int* __restrict__ ke_arr,
                                     double* __restrict__ hh_sorted /*[n_det][wpad]*/,
-                                    const double* __restrict__ calib, int64_t csw, int64_t csi) {
+                                    const double* __restrict__ calib, int64_t csw, int64_t csi,
+                                    int* __restrict__ ke_low_arr, int k_split) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= W) return;
     const int w = perm ? perm[t] : t;
@@ -367,6 +395,7 @@ __global__ void walker_setup_kernel(PlanDev P, int W, int wpad,
     if (!ok) {
         // no bins; combine() turns this into -inf via ks = -1
         ks_arr[t] = -1; ke_arr[t] = -1;
+        if (ke_low_arr) ke_low_arr[t] = -1;
         for (int r = 0; r < NCOEF(nd); ++r) wc[r * wpad + t] = 0.0;
         for (int d = 0; d < nd; ++d) hh_sorted[d * wpad + t] = 0.0;
         return;
@@ -452,6 +481,7 @@ __global__ void walker_setup_kernel(PlanDev P, int W, int wpad,
     const int ks = max(P.kmin, P.istart);
     ks_arr[t] = ks;
     ke_arr[t] = ke;        // ke <= ks means "detectors contribute 0" (gaussian_noise.py:329-333)
+    if (ke_low_arr) ke_low_arr[t] = min(ke, k_split);      // the recurrence kernel's share of the band
 
     // --- amplitude: amp0 * sqrt(5/(32 eta)) * (pi M)^(-7/6) -------------------------
     const double r = dist * 1e6 * G_PC_SI;
@@ -1089,6 +1119,183 @@ loglr_recur_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_blk,
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// kernel 2c: table-driven <d|h> above k_split.
+//
+// A sub-block of m bins centred on kc = s + m/2: Theta_d(kc + j) = th0 + nu j + R(j) with R the
+// quadratic..quartic part of the quartic through five exact phase samples (the same bound as
+// the recurrence kernel's blocks), small enough (|R| <= TAB_RHO at the edge) that
+//     e^{-2 pi i R(j)} = sum_{n <= TAB_DEG} c_n (j/h)^n,   h = m/2
+// to ~1e-10.  Then
+//     sum_j T[kc+j] e^{-2 pi i Theta_d} = e^{-2 pi i th0} sum_n c_n M_n(nu_d),
+//     M_n(nu) = sum_j (j/h)^n T[kc+j] e^{-2 pi i nu j},
+// and M_n -- a trigonometric polynomial of nu with period 1 -- is tabulated per plan on the grid
+// nu = g/(2m) (tab_build_kernel: the DFT of the kernel-deconvolved sequence) and evaluated per
+// walker by TAB_W-tap interpolation with the "exponential of semicircle" kernel (type-2 NUFFT,
+// Barnett et al. 2019).  Cost per (walker, sub-block, detector): O(TAB_W TAB_DEG), whatever m.
+// Walkers of a batch sit within a few grid cells of each other at these frequencies, so the
+// table rows they touch stay in L1/L2.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tab_build_kernel(PlanDev P, const int* __restrict__ tab_start, const int* __restrict__ tab_mi,
+                 const int64_t* __restrict__ tab_off, const TabMat* __restrict__ mats,
+                 const double* __restrict__ invhat, double2* __restrict__ tab) {
+    const int b = blockIdx.y, d = blockIdx.z;
+    const TabMat* M = mats + tab_mi[b];
+    const int m = M->m, L = 2 * m;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= L) return;
+    const int s = tab_start[b];
+    const double* ih = invhat + M->hat_off;
+    const double ih2 = 2.0 / (double)m;
+    double2 acc[TAB_DEG + 1];
+#pragma unroll
+    for (int n = 0; n <= TAB_DEG; ++n) acc[n] = make_double2(0.0, 0.0);
+    for (int j = 0; j < m; ++j) {
+        const int k = s + j;
+        if (k >= P.n_f) break;
+        const double2 Tk = __ldg(P.T + (size_t)k * P.n_det + d);
+        if (Tk.x == 0.0 && Tk.y == 0.0) continue;
+        const int jc = j - m / 2;
+        const int idx = (jc * g) & (L - 1);                 // (jc g) mod L, L a power of two
+        double sn, cs;
+        sincospi(-2.0 * (double)idx / (double)L, &sn, &cs);
+        double2 u = cmul(Tk, make_double2(cs, sn));
+        const double w = ih[j];
+        u.x *= w; u.y *= w;
+        const double sc = (double)jc * ih2;
+#pragma unroll
+        for (int n = 0; n <= TAB_DEG; ++n) {
+            acc[n].x += u.x; acc[n].y += u.y;
+            u.x *= sc; u.y *= sc;
+        }
+    }
+    double2* out = tab + tab_off[b] + (size_t)d * (TAB_DEG + 1) * L + g;
+#pragma unroll
+    for (int n = 0; n <= TAB_DEG; ++n) out[(size_t)n * L] = acc[n];
+}
+
+template <int ND>
+__global__ void __launch_bounds__(CTA_THREADS)
+loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
+                   const int* __restrict__ tab_start, const int* __restrict__ tab_mi,
+                   const int64_t* __restrict__ tab_off, const TabMat* __restrict__ mats,
+                   const double2* __restrict__ tab,
+                   const double* __restrict__ wc, const int* __restrict__ ke_arr,
+                   double2* __restrict__ partial) {
+    const int t = blockIdx.x * CTA_THREADS + threadIdx.x;
+    const int chunk = blockIdx.y;
+    const int b0 = chunk * blocks_per_chunk;
+    const int b1 = min(b0 + blocks_per_chunk, n_tblk);
+    const bool live = t < W;
+    const int ke = live ? ke_arr[t] : 0;
+    const int k0 = tab_start[b0];
+    const bool has = k0 < ke;
+    int whi = has ? ke : 0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) whi = max(whi, __shfl_xor_sync(0xffffffffu, whi, o));
+    double2 acc[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) acc[d] = make_double2(0.0, 0.0);
+    if (k0 < whi) {
+        const int tt = live ? t : 0;
+        PhaseCoef pc;
+        load_phase_coef(pc, wc, wpad, tt);
+        double tau_hi[ND], tau_lo[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            const double* row = wc + (size_t)(C_DET0 + D_NROW * d) * wpad + tt;
+            tau_hi[d] = row[D_TAUHI * wpad];
+            tau_lo[d] = row[D_TAULO * wpad];
+        }
+        for (int b = b0; b < b1; ++b) {
+            const int s = tab_start[b];
+            if (s >= whi) break;
+            if (s >= ke) continue;
+            const TabMat* M = mats + tab_mi[b];
+            const int m = M->m, L = 2 * m;
+            if (ke >= min(s + m, P.kmax)) {
+                // ---- whole sub-block from the tables
+                const double h = 0.5 * (double)m;
+                const double thc = phase_turns(pc, ld_basis(P.basis + s + M->node[2]));
+                double v[4];
+                v[0] = phase_turns(pc, ld_basis(P.basis + s + M->node[0])) - thc;
+                v[1] = phase_turns(pc, ld_basis(P.basis + s + M->node[1])) - thc;
+                v[2] = phase_turns(pc, ld_basis(P.basis + s + M->node[3])) - thc;
+                v[3] = phase_turns(pc, ld_basis(P.basis + s + M->node[4])) - thc;
+                double tq[4];                    // t_1..t_4: Theta - th_c = sum t_i (j/h)^i [turns]
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    double a = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) a = fma(M->c[4 * i + j], v[j], a);
+                    tq[i] = a;
+                }
+                // c_n of e^{-i a R}, a = 2 pi, R = t2 s^2 + t3 s^3 + t4 s^4, through R^3, degree <= 6
+                const double a1 = G_TWOPI, t2 = tq[1], t3 = tq[2], t4 = tq[3];
+                const double a2h = 0.5 * a1 * a1;
+                double2 c[TAB_DEG + 1];
+                c[0] = make_double2(1.0, 0.0);
+                c[1] = make_double2(0.0, 0.0);
+                c[2] = make_double2(0.0, -a1 * t2);
+                c[3] = make_double2(0.0, -a1 * t3);
+                c[4] = make_double2(-a2h * t2 * t2, -a1 * t4);
+                c[5] = make_double2(-a2h * 2.0 * t2 * t3, 0.0);
+                c[6] = make_double2(-a2h * fma(2.0 * t2, t4, t3 * t3), (a1 * a1 * a1 / 6.0) * t2 * t2 * t2);
+                const double kc = (double)(s + m / 2);
+                const double2* row0 = tab + tab_off[b];
+#pragma unroll
+                for (int d = 0; d < ND; ++d) {
+                    const double tau = tau_hi[d] + tau_lo[d];
+                    const double nu = tq[0] / h + tau;                        // turns per bin
+                    const double x = (nu - floor(nu)) * (double)L;            // [0, L)
+                    const int g0 = (int)ceil(x - 0.5 * TAB_W);
+                    double2 Mn[TAB_DEG + 1];
+#pragma unroll
+                    for (int n = 0; n <= TAB_DEG; ++n) Mn[n] = make_double2(0.0, 0.0);
+                    const double2* rd = row0 + (size_t)d * (TAB_DEG + 1) * L;
+#pragma unroll 1
+                    for (int i = 0; i < TAB_W; ++i) {
+                        const int g = g0 + i;
+                        const double z = (x - (double)g) * (2.0 / TAB_W);
+                        const double arg = fmax(1.0 - z * z, 0.0);
+                        const double wt = exp(TAB_BETA * (sqrt(arg) - 1.0));
+                        const double2* e = rd + (g & (L - 1));
+#pragma unroll
+                        for (int n = 0; n <= TAB_DEG; ++n) {
+                            const double2 q = __ldg(e + (size_t)n * L);
+                            Mn[n].x = fma(wt, q.x, Mn[n].x);
+                            Mn[n].y = fma(wt, q.y, Mn[n].y);
+                        }
+                    }
+                    double2 sum = Mn[0];
+#pragma unroll
+                    for (int n = 2; n <= TAB_DEG; ++n) sum = cfma(c[n], Mn[n], sum);
+                    const double th0 = thc + fma(kc, tau_lo[d], frac1(kc * tau_hi[d]));
+                    acc[d] = cfma(sum, phasor_neg(th0), acc[d]);
+                }
+            } else {
+                // ---- the sub-block holding this walker's last bin: bin by bin
+                for (int k = s; k < ke; ++k) {
+                    const double psi = phase_turns(pc, ld_basis(P.basis + k));
+                    const double kd = (double)k;
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) {
+                        const double2 u = phasor_neg(psi + fma(kd, tau_lo[d], frac1(kd * tau_hi[d])));
+                        acc[d] = cfma(__ldg(P.T + (size_t)k * ND + d), u, acc[d]);
+                    }
+                }
+            }
+        }
+    }
+    if (live && has) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+            partial[((size_t)chunk * ND + d) * wpad + t] = acc[d];
+    }
+}
+
 // ---------------------------------------------------------------------------
 // kernel 3: combine chunk partials, scale by the walker amplitude, form loglr,
 // scatter back to the caller's walker order.
@@ -1112,7 +1319,9 @@ combine_kernel(int n_det, int W, int wpad, int n_chunks, int mode,
                const double2* __restrict__ partial,
                const double* __restrict__ hh_sorted,
                double* __restrict__ loglr, double* __restrict__ hd_out,
-               double* __restrict__ hh_out, double* __restrict__ marg_opt) {
+               double* __restrict__ hh_out, double* __restrict__ marg_opt,
+               int n_chunks2, int per_chunk2, const int* __restrict__ tab_start,
+               const double2* __restrict__ partial2, const int* __restrict__ ke2_arr) {
     __shared__ double2 s_part[COMB_SEG][GWIN_MAX_DET][32];
     const int lx = threadIdx.x, seg = threadIdx.y;
     const int t = blockIdx.x * 32 + lx;
@@ -1132,6 +1341,15 @@ combine_kernel(int n_det, int W, int wpad, int n_chunks, int mode,
                 const double2 p = partial[((size_t)c * n_det + d) * wpad + t];
                 re += p.x; im += p.y;
             }
+        // table-kernel chunks (above k_split): written where the chunk starts below the walker's end
+        if (live && n_chunks2 > 0) {
+            const int ke2 = ke2_arr[t];
+            for (int c = seg; c < n_chunks2; c += COMB_SEG) {
+                if (tab_start[c * per_chunk2] >= ke2) continue;
+                const double2 p = partial2[((size_t)c * n_det + d) * wpad + t];
+                re += p.x; im += p.y;
+            }
+        }
         s_part[seg][d][lx] = make_double2(re, im);
     }
     __syncthreads();
@@ -1396,6 +1614,141 @@ static int upload_schedule(gwin_plan* p) {
     CK(cudaMemcpy(p->d_blk_mat, p->blk_mat.data(), sizeof(int) * p->blk_mat.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(p->d_mats, p->mats.data(), sizeof(BlockMat) * p->mats.size(), cudaMemcpyHostToDevice));
     p->sched_dirty = false;
+    p->tab_dirty = true;
+    return GWIN_OK;
+}
+
+
+// ---- table kernel: schedule + moment tables -------------------------------------------------
+static int table_block_len(const gwin_plan* p, int k, double chirp) {
+    const PlanDev& d = p->d;
+    const double K2 = (5.0 / 3) * (8.0 / 3), K5 = K2 * (11.0 / 3) * (14.0 / 3) * (17.0 / 3);
+    const double f = k * d.delta_f;
+    const double d2 = chirp * K2 * d.delta_f * d.delta_f * pow(f, -11.0 / 3.0);      // rad / bin^2
+    const double d5 = chirp * K5 * pow(d.delta_f, 5.0) * pow(f, -20.0 / 3.0);        // rad / bin^5
+    const double h = sqrt(2.0 * TAB_RHO / d2);                                       // d2 h^2 / 2 <= TAB_RHO
+    const double b4 = pow(p->phase_tol * 120.0 / (0.005 * d5), 0.2) + 1.0;           // quartic through 5 nodes
+    const double m = std::min(std::min(2.0 * h, b4), (double)TAB_MAX);
+    if (m < 1.0) return 0;
+    return 1 << (int)floor(log2(m));
+}
+
+static double es_kernel_host(long double x) {
+    const long double z = 2.0L * x / TAB_W;
+    if (fabsl(z) >= 1.0L) return 0.0;
+    return (double)expl((long double)TAB_BETA * (sqrtl(1.0L - z * z) - 1.0L));
+}
+
+static TabMat make_tab_mat(int m, int hat_off) {
+    TabMat M;
+    memset(&M, 0, sizeof M);
+    M.m = m; M.hat_off = hat_off;
+    const int e = m - 1, q = (e + 4) / 8;
+    const int x[5] = {0, q, m / 2, e - q, e};
+    for (int i = 0; i < 5; ++i) M.node[i] = x[i];
+    // t_i, i = 1..4, from v_j = th(x_j) - th(centre), j over the four off-centre nodes:
+    // sum_i t_i s_j^i = v_j with s_j = (x_j - m/2) / (m/2)
+    const int col[4] = {0, 1, 3, 4};
+    long double A[4][8];
+    for (int r = 0; r < 4; ++r) {
+        const long double sj = ((long double)x[col[r]] - m / 2) / (0.5L * m);
+        long double pw = sj;
+        for (int c = 0; c < 4; ++c) { A[r][c] = pw; pw *= sj; }
+        for (int c = 0; c < 4; ++c) A[r][4 + c] = (r == c) ? 1.0L : 0.0L;
+    }
+    for (int c = 0; c < 4; ++c) {                      // Gauss-Jordan with partial pivoting
+        int piv = c;
+        for (int r = c + 1; r < 4; ++r) if (fabsl(A[r][c]) > fabsl(A[piv][c])) piv = r;
+        for (int q2 = 0; q2 < 8; ++q2) std::swap(A[c][q2], A[piv][q2]);
+        const long double inv = 1.0L / A[c][c];
+        for (int q2 = 0; q2 < 8; ++q2) A[c][q2] *= inv;
+        for (int r = 0; r < 4; ++r) {
+            if (r == c) continue;
+            const long double f = A[r][c];
+            for (int q2 = 0; q2 < 8; ++q2) A[r][q2] -= f * A[c][q2];
+        }
+    }
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) M.c[4 * i + j] = (double)A[i][4 + j];
+    return M;
+}
+
+static void free_tables(gwin_plan* p) {
+    cudaFree(p->d_tab_start); cudaFree(p->d_tab_mi); cudaFree(p->d_tab_off); cudaFree(p->d_tabmats);
+    cudaFree(p->d_invhat); cudaFree(p->d_tab);
+    p->d_tab_start = p->d_tab_mi = nullptr; p->d_tab_off = nullptr; p->d_tabmats = nullptr;
+    p->d_invhat = nullptr; p->d_tab = nullptr;
+    p->n_tblk = 0;
+}
+
+// Sub-blocks over [k_split, kmax) and their moment tables.  k_split is the first boundary of the
+// recurrence schedule from which TAB_MIN-bin sub-blocks meet both bounds; below it the
+// recurrence kernel does the work.  No tables (n_tblk = 0) when they would not fit the budget.
+static int build_tables(gwin_plan* p) {
+    PlanDev& d = p->d;
+    free_tables(p);
+    p->tab_start.clear(); p->tab_mi.clear(); p->tab_off.clear(); p->tabmats.clear();
+    p->k_split = d.kmax; p->n_blk_low = p->n_blk;
+    p->tab_dirty = false;
+    const double chirp = 2.0 * (3.0 / 128.0) * pow(G_PI * p->mchirp_min * G_MTSUN, -5.0 / 3.0);
+    const int band0 = std::max(std::max(d.kmin, d.istart), 1);
+    int raw = band0;
+    while (raw < d.kmax && table_block_len(p, raw, chirp) < TAB_MIN) raw += 64;
+    if (raw >= d.kmax) return GWIN_OK;
+    int ib = 0;
+    while (ib < p->n_blk && p->blk_start[ib] < raw) ++ib;
+    if (ib >= p->n_blk) return GWIN_OK;
+    const int k_split = p->blk_start[ib];
+    std::vector<double> invhat;
+    std::vector<int> mat_of(32, -1);
+    int64_t off = 0;
+    for (int k = k_split; k < d.kmax;) {
+        const int m = std::max(table_block_len(p, k, chirp), TAB_MIN);
+        int lg = 0;
+        while ((1 << lg) < m) ++lg;
+        if (mat_of[lg] < 0) {
+            mat_of[lg] = (int)p->tabmats.size();
+            p->tabmats.push_back(make_tab_mat(m, (int)invhat.size()));
+            // 1 / phi_hat(jc / L), phi_hat by midpoint quadrature of the kernel over its support
+            const int nq = 2048, L = 2 * m;
+            std::vector<long double> xs(nq), ph(nq);
+            for (int q = 0; q < nq; ++q) {
+                xs[q] = ((long double)q + 0.5L) / nq * TAB_W - 0.5L * TAB_W;
+                ph[q] = es_kernel_host(xs[q]);
+            }
+            for (int j = 0; j < m; ++j) {
+                const long double xi = (long double)(j - m / 2) / L;
+                long double sum = 0.0L;
+                for (int q = 0; q < nq; ++q) sum += ph[q] * cosl(2.0L * 3.14159265358979323846264338327950288L * xi * xs[q]);
+                invhat.push_back((double)(1.0L / (sum * TAB_W / nq)));
+            }
+        }
+        p->tab_start.push_back(k);
+        p->tab_mi.push_back(mat_of[lg]);
+        p->tab_off.push_back(off);
+        off += (int64_t)d.n_det * (TAB_DEG + 1) * 2 * m;
+        k += m;
+    }
+    const int n = (int)p->tab_mi.size();
+    p->tab_start.push_back(p->tab_start.back() + p->tabmats[p->tab_mi.back()].m);
+    static const double budget_gb = getenv("GWIN_TABLE_GB") ? atof(getenv("GWIN_TABLE_GB")) : 4.0;
+    if ((double)off * sizeof(double2) > budget_gb * 1073741824.0) return GWIN_OK;     // stay on the recurrence kernel
+    CK(cudaMalloc(&p->d_tab_start, sizeof(int) * (n + 1)));
+    CK(cudaMalloc(&p->d_tab_mi, sizeof(int) * n));
+    CK(cudaMalloc(&p->d_tab_off, sizeof(int64_t) * n));
+    CK(cudaMalloc(&p->d_tabmats, sizeof(TabMat) * p->tabmats.size()));
+    CK(cudaMalloc(&p->d_invhat, sizeof(double) * invhat.size()));
+    CK(cudaMalloc(&p->d_tab, sizeof(double2) * (size_t)off));
+    CK(cudaMemcpy(p->d_tab_start, p->tab_start.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(p->d_tab_mi, p->tab_mi.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(p->d_tab_off, p->tab_off.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(p->d_tabmats, p->tabmats.data(), sizeof(TabMat) * p->tabmats.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(p->d_invhat, invhat.data(), sizeof(double) * invhat.size(), cudaMemcpyHostToDevice));
+    tab_build_kernel<<<dim3(2 * TAB_MAX / 256, n, d.n_det), 256>>>(d, p->d_tab_start, p->d_tab_mi, p->d_tab_off,
+                                                               p->d_tabmats, p->d_invhat, p->d_tab);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    p->n_tblk = n; p->k_split = k_split; p->n_blk_low = ib;
     return GWIN_OK;
 }
 
@@ -1529,6 +1882,7 @@ extern "C" void gwin_plan_destroy(gwin_plan* p) {
     cudaFree(p->d_partial); cudaFree(p->d_cub);
     cudaFree(p->d_marg_u); cudaFree(p->d_marg_logw); cudaFree(p->d_marg_opt);
     cudaFree(p->d_calM); cudaFree(p->d_Ccal); cudaFree(p->d_calib); cudaFreeHost(p->h_calib);
+    free_tables(p); cudaFree(p->d_partialT); cudaFree(p->d_ke_low);
     cudaFree(p->d_params); cudaFree(p->d_out); cudaFree(p->d_skip);
     cudaFreeHost(p->h_params); cudaFreeHost(p->h_out); cudaFreeHost(p->h_skip);
     if (p->timing) { cudaEventDestroy(p->ev0); cudaEventDestroy(p->ev1); }
@@ -1664,7 +2018,7 @@ extern "C" int gwin_plan_set_distance_marg(gwin_plan* p, int64_t n, const double
 
 extern "C" int gwin_plan_configure(gwin_plan* p, int kernel, double phase_tol, double mchirp_min) {
     if (!p) return fail(GWIN_EINVAL, "plan is NULL");
-    if (kernel < GWIN_KERNEL_AUTO || kernel > GWIN_KERNEL_RECURRENCE) return fail(GWIN_EINVAL, "bad kernel id");
+    if (kernel < GWIN_KERNEL_AUTO || kernel > GWIN_KERNEL_TABLE) return fail(GWIN_EINVAL, "bad kernel id");
     p->kernel = kernel;
     if (phase_tol > 0.0 && phase_tol != p->phase_tol) { p->phase_tol = phase_tol; p->sched_dirty = true; }
     if (mchirp_min > 0.0) {
@@ -1706,8 +2060,8 @@ static int ensure_workspace(gwin_plan* p, int64_t W, int n_chunks) {
         cap = (cap + CTA_THREADS - 1) / CTA_THREADS * CTA_THREADS;
         cudaFree(p->d_wc); cudaFree(p->d_ks); cudaFree(p->d_ke);
         cudaFree(p->d_key_in); cudaFree(p->d_key_out); cudaFree(p->d_perm_in); cudaFree(p->d_perm_out);
-        cudaFree(p->d_cub); cudaFree(p->d_marg_opt);
-        p->d_marg_opt = nullptr;
+        cudaFree(p->d_cub); cudaFree(p->d_marg_opt); cudaFree(p->d_ke_low);
+        p->d_marg_opt = nullptr; p->d_ke_low = nullptr;
         p->d_wc = nullptr; p->d_ks = p->d_ke = p->d_key_in = p->d_key_out = p->d_perm_in = p->d_perm_out = nullptr;
         p->d_cub = nullptr; p->w_cap = 0;
         // coefficient rows + n_det rows of hh
@@ -1719,6 +2073,8 @@ static int ensure_workspace(gwin_plan* p, int64_t W, int n_chunks) {
         CK(cudaMalloc(&p->d_perm_in, sizeof(int) * cap));
         CK(cudaMalloc(&p->d_perm_out, sizeof(int) * cap));
         CK(cudaMalloc(&p->d_marg_opt, sizeof(double) * cap));
+        CK(cudaMalloc(&p->d_ke_low, sizeof(int) * cap));
+        p->partialT_cap = 0;
         p->cub_bytes = 0;
         CK(cub::DeviceRadixSort::SortPairs(nullptr, p->cub_bytes, p->d_key_in, p->d_key_out,
                                            p->d_perm_in, p->d_perm_out, (int)cap, 0, 23));
@@ -1737,7 +2093,7 @@ static int ensure_workspace(gwin_plan* p, int64_t W, int n_chunks) {
 
 template <int ND>
 static void launch_main(gwin_plan* p, bool recur, bool calibrated, int W, int wpad, int n_chunks, int per_chunk,
-                        cudaStream_t st) {
+                        int n_blk, const int* ke_arr, cudaStream_t st) {
     dim3 grid((W + CTA_THREADS - 1) / CTA_THREADS, n_chunks);
     // diagnostic: GWIN_SMEM_PAD=<bytes> of unused dynamic shared memory lowers the occupancy
     static const int smem_pad = getenv("GWIN_SMEM_PAD") ? atoi(getenv("GWIN_SMEM_PAD")) : 0;
@@ -1754,19 +2110,27 @@ static void launch_main(gwin_plan* p, bool recur, bool calibrated, int W, int wp
         attr_set[calibrated] = true;
     }
     if (recur && calibrated)
-        loglr_recur_kernel<ND, true><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, per_chunk, p->n_blk, p->d_blk_start,
+        loglr_recur_kernel<ND, true><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, per_chunk, n_blk, p->d_blk_start,
                                                                   p->d_blk_mat, p->d_mats,
-                                                                  p->d_wc, p->d_ks, p->d_ke, p->d_partial);
+                                                                  p->d_wc, p->d_ks, ke_arr, p->d_partial);
     else if (recur)
-        loglr_recur_kernel<ND, false><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, per_chunk, p->n_blk, p->d_blk_start,
+        loglr_recur_kernel<ND, false><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, per_chunk, n_blk, p->d_blk_start,
                                                                    p->d_blk_mat, p->d_mats,
-                                                                   p->d_wc, p->d_ks, p->d_ke, p->d_partial);
+                                                                   p->d_wc, p->d_ks, ke_arr, p->d_partial);
     else if (calibrated)
         loglr_direct_kernel<ND, true><<<grid, CTA_THREADS, 0, st>>>(p->d, W, wpad, per_chunk, n_chunks,
-                                                                   p->d_wc, p->d_ks, p->d_ke, p->d_partial);
+                                                                   p->d_wc, p->d_ks, ke_arr, p->d_partial);
     else
         loglr_direct_kernel<ND, false><<<grid, CTA_THREADS, 0, st>>>(p->d, W, wpad, per_chunk, n_chunks,
-                                                                    p->d_wc, p->d_ks, p->d_ke, p->d_partial);
+                                                                    p->d_wc, p->d_ks, ke_arr, p->d_partial);
+}
+
+template <int ND>
+static void launch_table(gwin_plan* p, int W, int wpad, int n_chunks, int per_chunk, cudaStream_t st) {
+    dim3 grid((W + CTA_THREADS - 1) / CTA_THREADS, n_chunks);
+    loglr_table_kernel<ND><<<grid, CTA_THREADS, 0, st>>>(p->d, W, wpad, per_chunk, p->n_tblk, p->d_tab_start, p->d_tab_mi,
+                                                        p->d_tab_off, p->d_tabmats, p->d_tab, p->d_wc, p->d_ke,
+                                                        p->d_partialT);
 }
 
 extern "C" int gwin_loglr_batch(gwin_plan* p, int mode, int64_t W64,
@@ -1821,6 +2185,14 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
     const int nd = d.n_det;
     const bool recur = p->kernel != GWIN_KERNEL_DIRECT;
     if (recur && p->sched_dirty) { int rc = upload_schedule(p); if (rc) return rc; }
+    // table kernel above k_split (uncalibrated batches): the recurrence kernel keeps [band0, k_split)
+    static const bool table_default = !(getenv("GWIN_TABLE") && atoi(getenv("GWIN_TABLE")) == 0);
+    bool table = !calib && (p->kernel == GWIN_KERNEL_TABLE || (p->kernel == GWIN_KERNEL_AUTO && table_default));
+    if (table) {
+        if (p->tab_dirty) { int rc = build_tables(p); if (rc) return rc; }
+        table = p->n_tblk > 0;
+    }
+    const int n_blk = table ? p->n_blk_low : p->n_blk;
 
     // frequency chunking: enough CTAs to fill 148 SMs x ~5 resident CTAs several times over
     const int band0 = std::max(d.kmin, d.istart);
@@ -1832,17 +2204,30 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
     int n_chunks, per_chunk;
     if (recur) {
         const int min_blocks = 2;
-        per_chunk = std::max(min_blocks, (p->n_blk + want_chunks - 1) / want_chunks);
-        n_chunks = (p->n_blk + per_chunk - 1) / per_chunk;
+        per_chunk = std::max(min_blocks, (n_blk + want_chunks - 1) / want_chunks);
+        n_chunks = (n_blk + per_chunk - 1) / per_chunk;
     } else {
         per_chunk = std::max(RESYNC, (nbins + want_chunks - 1) / want_chunks);
         per_chunk = (per_chunk + RESYNC - 1) / RESYNC * RESYNC;
         n_chunks = (nbins + per_chunk - 1) / per_chunk;
     }
-    int rc = ensure_workspace(p, W, n_chunks);
+    int rc = ensure_workspace(p, W, std::max(n_chunks, 1));
     if (rc) return rc;
     const int wpad = (int)p->w_cap;
     double* hh_rows = p->d_wc + (size_t)NCOEF(nd) * wpad;
+    // table chunks: a sub-block costs about as much as 100 recurrence bins
+    int n_chunksT = 0, per_chunkT = 1;
+    if (table) {
+        const int wantT = std::max(1, std::min(p->n_tblk, (148 * 12 + groups - 1) / groups));
+        per_chunkT = (p->n_tblk + wantT - 1) / wantT;
+        n_chunksT = (p->n_tblk + per_chunkT - 1) / per_chunkT;
+        const size_t need = (size_t)n_chunksT * nd * p->w_cap;
+        if (need > p->partialT_cap) {
+            cudaFree(p->d_partialT); p->d_partialT = nullptr; p->partialT_cap = 0;
+            CK(cudaMalloc(&p->d_partialT, sizeof(double2) * need));
+            p->partialT_cap = need;
+        }
+    }
 
     const int tb = 128, gb = (W + tb - 1) / tb;
     const int* perm = nullptr;
@@ -1855,7 +2240,9 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
         p->last_launches += 1;   // + CUB's radix-sort passes (library code, not counted)
     }
     walker_setup_kernel<<<gb, tb, 0, st>>>(d, W, wpad, params, stride_walker, stride_param, skip, perm, p->d_wc, p->d_ks, p->d_ke, hh_rows,
-                                           calib, cstride_walker, cstride_value);
+                                           calib, cstride_walker, cstride_value,
+                                           table ? p->d_ke_low : nullptr, p->k_split);
+    const int* ke_main = table ? p->d_ke_low : p->d_ke;
     if (p->timing) {
         if (p->ev_pending) {            // harvest the previous launch (it has long finished)
             float ms = 0.f;
@@ -1865,17 +2252,27 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
         }
         CK(cudaEventRecord(p->ev0, st));
     }
-    switch (nd) {
-        case 1: launch_main<1>(p, recur, calib != nullptr, W, wpad, n_chunks, per_chunk, st); break;
-        case 2: launch_main<2>(p, recur, calib != nullptr, W, wpad, n_chunks, per_chunk, st); break;
-        case 3: launch_main<3>(p, recur, calib != nullptr, W, wpad, n_chunks, per_chunk, st); break;
-        default: launch_main<4>(p, recur, calib != nullptr, W, wpad, n_chunks, per_chunk, st); break;
+    if (n_chunks > 0) switch (nd) {
+        case 1: launch_main<1>(p, recur, calib != nullptr, W, wpad, n_chunks, per_chunk, n_blk, ke_main, st); break;
+        case 2: launch_main<2>(p, recur, calib != nullptr, W, wpad, n_chunks, per_chunk, n_blk, ke_main, st); break;
+        case 3: launch_main<3>(p, recur, calib != nullptr, W, wpad, n_chunks, per_chunk, n_blk, ke_main, st); break;
+        default: launch_main<4>(p, recur, calib != nullptr, W, wpad, n_chunks, per_chunk, n_blk, ke_main, st); break;
+    }
+    if (table) {
+        switch (nd) {
+            case 1: launch_table<1>(p, W, wpad, n_chunksT, per_chunkT, st); break;
+            case 2: launch_table<2>(p, W, wpad, n_chunksT, per_chunkT, st); break;
+            case 3: launch_table<3>(p, W, wpad, n_chunksT, per_chunkT, st); break;
+            default: launch_table<4>(p, W, wpad, n_chunksT, per_chunkT, st); break;
+        }
+        p->last_launches += 1;
     }
     if (p->timing) { CK(cudaEventRecord(p->ev1, st)); p->ev_pending = true; }
-    combine_kernel<<<(W + 31) / 32, dim3(32, COMB_SEG), 0, st>>>(nd, W, wpad, n_chunks, mode, per_chunk, p->n_blk,
+    combine_kernel<<<(W + 31) / 32, dim3(32, COMB_SEG), 0, st>>>(nd, W, wpad, n_chunks, mode, per_chunk, n_blk,
                                                                  recur ? p->d_blk_start : nullptr, band0, d.kmax,
-                                                                 perm, p->d_wc, p->d_ks, p->d_ke,
-                                                                 p->d_partial, hh_rows, loglr, hd, hh, p->d_marg_opt);
+                                                                 perm, p->d_wc, p->d_ks, ke_main,
+                                                                 p->d_partial, hh_rows, loglr, hd, hh, p->d_marg_opt,
+                                                                 n_chunksT, per_chunkT, p->d_tab_start, p->d_partialT, p->d_ke);
     p->last_launches += 3;
     if (mode >= GWIN_MODE_MARG_DIST) {
         marg_dist_kernel<<<(W + 7) / 8, 256, 0, st>>>(W, p->n_marg, p->d_marg_u, p->d_marg_logw, p->d_marg_opt, loglr);
@@ -2042,7 +2439,7 @@ extern "C" int gwin_generate_calib_host(gwin_plan* p, const double* params, cons
     }
     double* hh_rows = p->d_wc + (size_t)NCOEF(d.n_det) * wpad;
     walker_setup_kernel<<<1, 32, 0, st>>>(d, 1, wpad, p->d_params, GWIN_NPARAM, 1, nullptr, nullptr, p->d_wc, p->d_ks, p->d_ke, hh_rows,
-                                          calib ? p->d_calib : nullptr, (int64_t)nv, 1);
+                                          calib ? p->d_calib : nullptr, (int64_t)nv, 1, nullptr, 0);
     generate_len_kernel<<<1, 1, 0, st>>>(d, p->d_params, p->d_ke);
     double2* dout = nullptr;
     CK(cudaMalloc(&dout, sizeof(double2) * (size_t)d.n_det * d.n_f));

@@ -45,6 +45,8 @@ extern "C" {
 #define GWIN_KERNEL_AUTO       0
 #define GWIN_KERNEL_DIRECT     1  /* per-bin FP64 phase + sincos                                  */
 #define GWIN_KERNEL_RECURRENCE 2  /* block-anchored chirp-phasor recurrence + Horner accumulation */
+#define GWIN_KERNEL_TABLE      3  /* recurrence below k_split, per-plan moment tables + NUFFT
+                                     interpolation above (what AUTO selects; uncalibrated only)  */
 
 typedef struct gwin_plan gwin_plan;
 

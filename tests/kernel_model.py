@@ -368,6 +368,136 @@ class PlanModel(object):
                 S[d] = np.sum(self.T[d, ks:ke] * u)
         return self.finish(w, S, marg)
 
+    # -- loglr_table_kernel -------------------------------------------------------
+    # Above k_split the band is cut into sub-blocks of m (a power of two) bins.  Per sub-block
+    # the moments M_n(nu) = sum_j (j/h)^n T[kc+j] e^{-2 pi i nu j} are tabulated on the grid
+    # nu = g/(2m) (zero-padded FFT of the kernel-deconvolved sequence); per walker the block sum
+    # is e^{-2 pi i th0} sum_n c_n M_n(nu) with the M_n interpolated by a TAB_W-tap
+    # exponential-of-semicircle kernel and c_n the Taylor coefficients of e^{-2 pi i R(j)},
+    # R = the quadratic..quartic part of the block polynomial.
+    TAB_DEG, TAB_W, TAB_MIN, TAB_MAX, TAB_RHO = 6, 13, 256, 2048, 0.007
+
+    def build_table_schedule(self):
+        band0 = max(self.kmin, self.istart)
+        K2 = (5. / 3) * (8. / 3)
+        K5 = K2 * (11. / 3) * (14. / 3) * (17. / 3)
+        chirp = 2.0 * (3. / 128.) * (PI * self.mchirp_min * MTSUN) ** (-5. / 3)
+        starts, k = [], None
+        # first bin from which TAB_MIN-bin sub-blocks meet both bounds
+        kk = max(band0, 1)
+        while kk < self.kmax:
+            if self._table_m(kk, chirp, K2, K5) >= self.TAB_MIN:
+                break
+            kk += 64
+        self.k_split = min(kk, self.kmax)
+        k = self.k_split
+        self.tab_start, self.tab_m = [], []
+        while k < self.kmax:
+            m = self._table_m(k, chirp, K2, K5)
+            self.tab_start.append(k)
+            self.tab_m.append(m)
+            k += m
+        self.tab_start.append(k)          # may run past kmax: T is zero there
+        return self.tab_start
+
+    def _table_m(self, k, chirp, K2, K5):
+        f = k * self.delta_f
+        d2 = chirp * K2 * self.delta_f ** 2 * f ** (-11. / 3)
+        d5 = chirp * K5 * self.delta_f ** 5 * f ** (-20. / 3)
+        h = math.sqrt(2.0 * self.TAB_RHO / d2)                         # d2 h^2 / 2 <= TAB_RHO
+        b4 = (self.phase_tol * 120.0 / (0.005 * d5)) ** 0.2 + 1.0      # quartic interpolation bound
+        m = min(2.0 * h, b4, self.TAB_MAX)
+        return 0 if m < 1 else 1 << int(math.floor(math.log2(m)))
+
+    @staticmethod
+    def es_kernel(x, w, beta):
+        z = 2.0 * np.asarray(x, dtype=float) / w
+        out = np.zeros_like(z)
+        ok = np.abs(z) < 1
+        out[ok] = np.exp(beta * (np.sqrt(1 - z[ok] ** 2) - 1))
+        return out
+
+    @classmethod
+    def es_hat(cls, xi, w, beta, nq=2048):
+        x = (np.arange(nq) + 0.5) / nq * w - w / 2
+        ph = cls.es_kernel(x, w, beta)
+        return (ph[None, :] * np.cos(2 * np.pi * np.asarray(xi)[:, None] * x[None, :])).sum(axis=1) * (w / nq)
+
+    def build_tables(self):
+        self.build_table_schedule()
+        w, beta, N = self.TAB_W, 2.30 * self.TAB_W, self.TAB_DEG
+        self.tab = []
+        hat = {}
+        for b, (s, m) in enumerate(zip(self.tab_start[:-1], self.tab_m)):
+            L = 2 * m
+            if m not in hat:
+                hat[m] = self.es_hat((np.arange(m) - m // 2) / float(L), w, beta)
+            jc = np.arange(m) - m // 2
+            g = np.arange(L)
+            rows = np.zeros((self.n_det, N + 1, L), dtype=complex)
+            for d in range(self.n_det):
+                seg = np.zeros(m, dtype=complex)
+                n_have = max(0, min(m, self.n_f - s))
+                seg[:n_have] = self.T[d, s:s + n_have]
+                for n in range(N + 1):
+                    a = seg * (jc / (m / 2.0)) ** n / hat[m]
+                    rows[d, n] = np.fft.fft(a, L) * np.exp(2j * np.pi * g * (m // 2) / L)
+            self.tab.append(rows)
+
+    def table_block(self, w, b, d):
+        """One full sub-block for one detector: the kernel's arithmetic."""
+        s, m = self.tab_start[b], self.tab_m[b]
+        N, W, beta = self.TAB_DEG, self.TAB_W, 2.30 * self.TAB_W
+        h = m / 2.0
+        e = m - 1
+        q = (e + 4) // 8
+        nodes = np.array([0, q, m // 2, e - q, e])
+        sn = (nodes - m // 2) / h
+        th = self.phase_turns(w, s + nodes)
+        coef = np.linalg.solve(np.vander(sn, 5, increasing=True), th - th[2])   # t_i s^i, t_0 = 0
+        th0 = th[2] + (s + m // 2) * w['tau'][d]
+        nu = coef[1] / h + w['tau'][d]
+        r = np.zeros(N + 1, dtype=complex)
+        r[2:5] = -2j * PI * coef[2:5]
+        c = np.zeros(N + 1, dtype=complex)
+        c[0] = 1.0
+        term = c.copy()
+        for kk in range(1, N // 2 + 1):
+            term = np.convolve(term, r)[:N + 1] / kk
+            c = c + term
+        x = (nu - math.floor(nu)) * (2 * m)
+        g0 = int(math.ceil(x - W / 2.0))
+        taps = g0 + np.arange(W)
+        wt = self.es_kernel(x - taps, W, beta)
+        M = (self.tab[b][d][:, taps % (2 * m)] * wt[None, :]).sum(axis=1)
+        return np.exp(-2j * PI * (th0 - math.floor(th0))) * np.dot(c, M)
+
+    def loglr_table(self, p, marg=False):
+        w = self.walker(p)
+        if not w['valid']:
+            return -np.inf, None, None
+        ks, ke = w['ks'], w['ke']
+        S = np.zeros(self.n_det, dtype=complex)
+        # low band: any exact method (the recurrence kernel on the GPU)
+        k_hi = min(ke, self.k_split)
+        if k_hi > ks:
+            k = np.arange(ks, k_hi)
+            psi = self.phase_turns(w, k)
+            for d in range(self.n_det):
+                S[d] += np.sum(self.T[d, k] * np.exp(-2j * PI * (psi + k * w['tau'][d])))
+        for b, (s, m) in enumerate(zip(self.tab_start[:-1], self.tab_m)):
+            if s >= ke:
+                break
+            if s + m <= ke or s + m >= self.kmax >= ke >= self.kmax:
+                for d in range(self.n_det):
+                    S[d] += self.table_block(w, b, d)
+            else:                       # the sub-block holding ke: bin by bin
+                k = np.arange(s, ke)
+                psi = self.phase_turns(w, k)
+                for d in range(self.n_det):
+                    S[d] += np.sum(self.T[d, k] * np.exp(-2j * PI * (psi + k * w['tau'][d])))
+        return self.finish(w, S, marg)
+
     # -- loglr_recur_kernel -------------------------------------------------------
     def loglr_recur(self, p, marg=False, return_phase_err=False, calib=None):
         w = self.walker(p)

@@ -12,7 +12,7 @@ from util import PARAM_ORDER, tol
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = {"direct": 1, "recurrence": 2}
+KERNELS = {"direct": 1, "recurrence": 2, "table": 3}
 
 
 def _oracle_batch(orc, P):

@@ -33,7 +33,7 @@ if ncal:
     Cd = torch.tensor(rng.normal(0, 0.05, (W, len(cfg.dets) * 2 * ncal)), device="cuda")
 res = {}
 for name in kernels:
-    kid = {"direct": 1, "recurrence": 2}[name]
+    kid = {"direct": 1, "recurrence": 2, "table": 3}[name]
     model.plan.configure(kernel=kid, mchirp_min=1.0, phase_tol=float(os.environ.get("PHASE_TOL", "0")))
     out = model.plan.loglr_device(Pd, calib=Cd)
     torch.cuda.synchronize()
@@ -60,6 +60,7 @@ for name in kernels:
     evs = W / (ms * 1e-3)
     print("%-10s W=%d T=%d  %.3f ms/batch  %.3e evals/s  %.3e bin-evals/s  (x68 slots = %.1f%% of 1.861e13; x32 = %.1f%%)"
           % (name, W, seglen, ms, evs, evs * bins, 100 * evs * bins * 68 / 1.861e13, 100 * evs * bins * 32 / 1.861e13))
-if len(res) == 2:
-    d = np.abs(res["direct"] - res["recurrence"])
-    print("max |direct - recurrence| = %.3e" % d.max())
+names = list(res)
+for a in range(len(names)):
+    for b in range(a + 1, len(names)):
+        print("max |%s - %s| = %.3e" % (names[a], names[b], np.abs(res[names[a]] - res[names[b]]).max()))
