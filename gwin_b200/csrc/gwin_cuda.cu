@@ -121,6 +121,7 @@ struct BlockMat {
 #define TAB_MIN 256          // shortest / longest sub-block [bins], powers of two
 #define TAB_MAX 2048
 #define TAB_RHO 0.007        // bound on |R| at the sub-block edge [rad]: truncation error ~ rho^4/24
+#define TAB_NM TAB_DEG       // moments stored per grid point: n = 0, 2, 3, .. TAB_DEG (c_1 = 0: nu carries the slope)
 struct TabMat {
     double c[16];   // t_i = sum_j c[4 (i-1) + j] (th_{x_j} - th_centre), i = 1..4, j over nodes 0,1,3,4
     int node[5];    // node offsets from the sub-block start; node[2] = m/2 is the centre
@@ -167,7 +168,7 @@ struct gwin_plan {
     std::vector<TabMat> tabmats;
     int n_tblk, k_split, n_blk_low;
     bool tab_dirty;
-    int *d_tab_start, *d_tab_mi, *d_ke_low;
+    int *d_tab_start, *d_tab_mi, *d_ke_low, *d_ks_tail;
     int64_t* d_tab_off;
     TabMat* d_tabmats;
     double* d_invhat;
@@ -382,7 +383,8 @@ __global__ void walker_setup_kernel(PlanDev P, int W, int wpad,
                                     int* __restrict__ ke_arr,
                                     double* __restrict__ hh_sorted /*[n_det][wpad]*/,
                                     const double* __restrict__ calib, int64_t csw, int64_t csi,
-                                    int* __restrict__ ke_low_arr, int k_split) {
+                                    int* __restrict__ ke_low_arr, int k_split,
+                                    int* __restrict__ ks_tail_arr, const int* __restrict__ tab_start, int n_tblk) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= W) return;
     const int w = perm ? perm[t] : t;
@@ -395,7 +397,7 @@ __global__ void walker_setup_kernel(PlanDev P, int W, int wpad,
     if (!ok) {
         // no bins; combine() turns this into -inf via ks = -1
         ks_arr[t] = -1; ke_arr[t] = -1;
-        if (ke_low_arr) ke_low_arr[t] = -1;
+        if (ke_low_arr) { ke_low_arr[t] = -1; ks_tail_arr[t] = -1; }
         for (int r = 0; r < NCOEF(nd); ++r) wc[r * wpad + t] = 0.0;
         for (int d = 0; d < nd; ++d) hh_sorted[d * wpad + t] = 0.0;
         return;
@@ -481,7 +483,18 @@ __global__ void walker_setup_kernel(PlanDev P, int W, int wpad,
     const int ks = max(P.kmin, P.istart);
     ks_arr[t] = ks;
     ke_arr[t] = ke;        // ke <= ks means "detectors contribute 0" (gaussian_noise.py:329-333)
-    if (ke_low_arr) ke_low_arr[t] = min(ke, k_split);      // the recurrence kernel's share of the band
+    if (ke_low_arr) {
+        ke_low_arr[t] = min(ke, k_split);      // the recurrence kernel's share of the band
+        // table sub-blocks are taken whole; the one holding the last bin (unless it ends there)
+        // is left to a second pass of the recurrence kernel over [ks_tail, ke)
+        int tail = ke;
+        if (ke > k_split) {
+            int lo = 0, hi = n_tblk - 1;                    // last sub-block starting below ke
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (tab_start[mid] < ke) lo = mid; else hi = mid - 1; }
+            if (ke < min(tab_start[lo + 1], P.kmax)) tail = tab_start[lo];
+        }
+        ks_tail_arr[t] = tail;
+    }
 
     // --- amplitude: amp0 * sqrt(5/(32 eta)) * (pi M)^(-7/6) -------------------------
     const double r = dist * 1e6 * G_PC_SI;
@@ -1171,13 +1184,22 @@ tab_build_kernel(PlanDev P, const int* __restrict__ tab_start, const int* __rest
             u.x *= sc; u.y *= sc;
         }
     }
-    double2* out = tab + tab_off[b] + (size_t)d * (TAB_DEG + 1) * L + g;
+    // layout [d][g][TAB_NM]: the moments of one grid point are contiguous (one or two cache lines per tap)
+    double2* out = tab + tab_off[b] + ((size_t)d * L + g) * TAB_NM;
+    out[0] = acc[0];
 #pragma unroll
-    for (int n = 0; n <= TAB_DEG; ++n) out[(size_t)n * L] = acc[n];
+    for (int n = 2; n <= TAB_DEG; ++n) out[n - 1] = acc[n];
 }
 
+#ifndef TABLE_MIN_CTAS
+#define TABLE_MIN_CTAS 4
+#endif
+#ifndef TAB_UNROLL
+#define TAB_UNROLL 2
+#endif
+static constexpr int kTabUnroll = TAB_UNROLL;
 template <int ND>
-__global__ void __launch_bounds__(CTA_THREADS)
+__global__ void __launch_bounds__(CTA_THREADS, TABLE_MIN_CTAS)
 loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
                    const int* __restrict__ tab_start, const int* __restrict__ tab_mi,
                    const int64_t* __restrict__ tab_off, const TabMat* __restrict__ mats,
@@ -1233,16 +1255,13 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
                     tq[i] = a;
                 }
                 // c_n of e^{-i a R}, a = 2 pi, R = t2 s^2 + t3 s^3 + t4 s^4, through R^3, degree <= 6
+                // (c_0 = 1, c_1 = 0, c_2 = -i a t2, c_3 = -i a t3, c_4 = -a^2 t2^2/2 - i a t4,
+                //  c_5 = -a^2 t2 t3, c_6 = -a^2 (t3^2 + 2 t2 t4)/2 + i a^3 t2^3/6)
                 const double a1 = G_TWOPI, t2 = tq[1], t3 = tq[2], t4 = tq[3];
                 const double a2h = 0.5 * a1 * a1;
-                double2 c[TAB_DEG + 1];
-                c[0] = make_double2(1.0, 0.0);
-                c[1] = make_double2(0.0, 0.0);
-                c[2] = make_double2(0.0, -a1 * t2);
-                c[3] = make_double2(0.0, -a1 * t3);
-                c[4] = make_double2(-a2h * t2 * t2, -a1 * t4);
-                c[5] = make_double2(-a2h * 2.0 * t2 * t3, 0.0);
-                c[6] = make_double2(-a2h * fma(2.0 * t2, t4, t3 * t3), (a1 * a1 * a1 / 6.0) * t2 * t2 * t2);
+                const double c2i = -a1 * t2, c3i = -a1 * t3, c4r = -a2h * t2 * t2, c4i = -a1 * t4;
+                const double c5r = -a2h * 2.0 * t2 * t3;
+                const double c6r = -a2h * fma(2.0 * t2, t4, t3 * t3), c6i = (a1 * a1 * a1 / 6.0) * t2 * t2 * t2;
                 const double kc = (double)(s + m / 2);
                 const double2* row0 = tab + tab_off[b];
 #pragma unroll
@@ -1251,40 +1270,31 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
                     const double nu = tq[0] / h + tau;                        // turns per bin
                     const double x = (nu - floor(nu)) * (double)L;            // [0, L)
                     const int g0 = (int)ceil(x - 0.5 * TAB_W);
-                    double2 Mn[TAB_DEG + 1];
+                    double2 Mn[TAB_NM];
 #pragma unroll
-                    for (int n = 0; n <= TAB_DEG; ++n) Mn[n] = make_double2(0.0, 0.0);
-                    const double2* rd = row0 + (size_t)d * (TAB_DEG + 1) * L;
-#pragma unroll 1
+                    for (int n = 0; n < TAB_NM; ++n) Mn[n] = make_double2(0.0, 0.0);
+                    const double2* rd = row0 + (size_t)d * L * TAB_NM;
+#pragma unroll kTabUnroll
                     for (int i = 0; i < TAB_W; ++i) {
-                        const int g = g0 + i;
-                        const double z = (x - (double)g) * (2.0 / TAB_W);
-                        const double arg = fmax(1.0 - z * z, 0.0);
-                        const double wt = exp(TAB_BETA * (sqrt(arg) - 1.0));
-                        const double2* e = rd + (g & (L - 1));
+                        const double z = (x - (double)(g0 + i)) * (2.0 / TAB_W);
+                        const double wt = exp(TAB_BETA * (sqrt(fmax(1.0 - z * z, 0.0)) - 1.0));
+                        const double2* e = rd + (size_t)((g0 + i) & (L - 1)) * TAB_NM;
 #pragma unroll
-                        for (int n = 0; n <= TAB_DEG; ++n) {
-                            const double2 q = __ldg(e + (size_t)n * L);
+                        for (int n = 0; n < TAB_NM; ++n) {
+                            const double2 q = __ldg(e + n);
                             Mn[n].x = fma(wt, q.x, Mn[n].x);
                             Mn[n].y = fma(wt, q.y, Mn[n].y);
                         }
                     }
+                    // sum_n c_n M_n; Mn[] holds n = 0, 2, 3, 4, 5, 6
                     double2 sum = Mn[0];
-#pragma unroll
-                    for (int n = 2; n <= TAB_DEG; ++n) sum = cfma(c[n], Mn[n], sum);
+                    sum.x = fma(-c2i, Mn[1].y, sum.x); sum.y = fma(c2i, Mn[1].x, sum.y);
+                    sum.x = fma(-c3i, Mn[2].y, sum.x); sum.y = fma(c3i, Mn[2].x, sum.y);
+                    sum = cfma(make_double2(c4r, c4i), Mn[3], sum);
+                    sum.x = fma(c5r, Mn[4].x, sum.x); sum.y = fma(c5r, Mn[4].y, sum.y);
+                    sum = cfma(make_double2(c6r, c6i), Mn[5], sum);
                     const double th0 = thc + fma(kc, tau_lo[d], frac1(kc * tau_hi[d]));
                     acc[d] = cfma(sum, phasor_neg(th0), acc[d]);
-                }
-            } else {
-                // ---- the sub-block holding this walker's last bin: bin by bin
-                for (int k = s; k < ke; ++k) {
-                    const double psi = phase_turns(pc, ld_basis(P.basis + k));
-                    const double kd = (double)k;
-#pragma unroll
-                    for (int d = 0; d < ND; ++d) {
-                        const double2 u = phasor_neg(psi + fma(kd, tau_lo[d], frac1(kd * tau_hi[d])));
-                        acc[d] = cfma(__ldg(P.T + (size_t)k * ND + d), u, acc[d]);
-                    }
                 }
             }
         }
@@ -1321,7 +1331,9 @@ combine_kernel(int n_det, int W, int wpad, int n_chunks, int mode,
                double* __restrict__ loglr, double* __restrict__ hd_out,
                double* __restrict__ hh_out, double* __restrict__ marg_opt,
                int n_chunks2, int per_chunk2, const int* __restrict__ tab_start,
-               const double2* __restrict__ partial2, const int* __restrict__ ke2_arr) {
+               const double2* __restrict__ partial2, const int* __restrict__ ke2_arr,
+               int n_chunks3, int per_chunk3, int n_blk3, const int* __restrict__ blk_start3,
+               const int* __restrict__ ks3_arr, const double2* __restrict__ partial3) {
     __shared__ double2 s_part[COMB_SEG][GWIN_MAX_DET][32];
     const int lx = threadIdx.x, seg = threadIdx.y;
     const int t = blockIdx.x * 32 + lx;
@@ -1347,6 +1359,14 @@ combine_kernel(int n_det, int W, int wpad, int n_chunks, int mode,
             for (int c = seg; c < n_chunks2; c += COMB_SEG) {
                 if (tab_start[c * per_chunk2] >= ke2) continue;
                 const double2 p = partial2[((size_t)c * n_det + d) * wpad + t];
+                re += p.x; im += p.y;
+            }
+            // tail [ks3, ke2): the sub-block holding the walker's last bin, done by the recurrence kernel
+            const int ks3 = ks3_arr[t];
+            for (int c = seg; c < n_chunks3; c += COMB_SEG) {
+                const int k0 = blk_start3[c * per_chunk3], k1 = blk_start3[min((c + 1) * per_chunk3, n_blk3)];
+                if (max(k0, ks3) >= min(k1, ke2)) continue;
+                const double2 p = partial3[((size_t)c * n_det + d) * wpad + t];
                 re += p.x; im += p.y;
             }
         }
@@ -1726,7 +1746,7 @@ static int build_tables(gwin_plan* p) {
         p->tab_start.push_back(k);
         p->tab_mi.push_back(mat_of[lg]);
         p->tab_off.push_back(off);
-        off += (int64_t)d.n_det * (TAB_DEG + 1) * 2 * m;
+        off += (int64_t)d.n_det * TAB_NM * 2 * m;
         k += m;
     }
     const int n = (int)p->tab_mi.size();
@@ -1882,7 +1902,7 @@ extern "C" void gwin_plan_destroy(gwin_plan* p) {
     cudaFree(p->d_partial); cudaFree(p->d_cub);
     cudaFree(p->d_marg_u); cudaFree(p->d_marg_logw); cudaFree(p->d_marg_opt);
     cudaFree(p->d_calM); cudaFree(p->d_Ccal); cudaFree(p->d_calib); cudaFreeHost(p->h_calib);
-    free_tables(p); cudaFree(p->d_partialT); cudaFree(p->d_ke_low);
+    free_tables(p); cudaFree(p->d_partialT); cudaFree(p->d_ke_low); cudaFree(p->d_ks_tail);
     cudaFree(p->d_params); cudaFree(p->d_out); cudaFree(p->d_skip);
     cudaFreeHost(p->h_params); cudaFreeHost(p->h_out); cudaFreeHost(p->h_skip);
     if (p->timing) { cudaEventDestroy(p->ev0); cudaEventDestroy(p->ev1); }
@@ -2060,8 +2080,8 @@ static int ensure_workspace(gwin_plan* p, int64_t W, int n_chunks) {
         cap = (cap + CTA_THREADS - 1) / CTA_THREADS * CTA_THREADS;
         cudaFree(p->d_wc); cudaFree(p->d_ks); cudaFree(p->d_ke);
         cudaFree(p->d_key_in); cudaFree(p->d_key_out); cudaFree(p->d_perm_in); cudaFree(p->d_perm_out);
-        cudaFree(p->d_cub); cudaFree(p->d_marg_opt); cudaFree(p->d_ke_low);
-        p->d_marg_opt = nullptr; p->d_ke_low = nullptr;
+        cudaFree(p->d_cub); cudaFree(p->d_marg_opt); cudaFree(p->d_ke_low); cudaFree(p->d_ks_tail);
+        p->d_marg_opt = nullptr; p->d_ke_low = p->d_ks_tail = nullptr;
         p->d_wc = nullptr; p->d_ks = p->d_ke = p->d_key_in = p->d_key_out = p->d_perm_in = p->d_perm_out = nullptr;
         p->d_cub = nullptr; p->w_cap = 0;
         // coefficient rows + n_det rows of hh
@@ -2074,6 +2094,7 @@ static int ensure_workspace(gwin_plan* p, int64_t W, int n_chunks) {
         CK(cudaMalloc(&p->d_perm_out, sizeof(int) * cap));
         CK(cudaMalloc(&p->d_marg_opt, sizeof(double) * cap));
         CK(cudaMalloc(&p->d_ke_low, sizeof(int) * cap));
+        CK(cudaMalloc(&p->d_ks_tail, sizeof(int) * cap));
         p->partialT_cap = 0;
         p->cub_bytes = 0;
         CK(cub::DeviceRadixSort::SortPairs(nullptr, p->cub_bytes, p->d_key_in, p->d_key_out,
@@ -2093,7 +2114,10 @@ static int ensure_workspace(gwin_plan* p, int64_t W, int n_chunks) {
 
 template <int ND>
 static void launch_main(gwin_plan* p, bool recur, bool calibrated, int W, int wpad, int n_chunks, int per_chunk,
-                        int n_blk, const int* ke_arr, cudaStream_t st) {
+                        int n_blk, const int* ke_arr, cudaStream_t st,
+                        int blk_off = 0, const int* ks_arr = nullptr, double2* partial = nullptr) {
+    if (!ks_arr) ks_arr = p->d_ks;
+    if (!partial) partial = p->d_partial;
     dim3 grid((W + CTA_THREADS - 1) / CTA_THREADS, n_chunks);
     // diagnostic: GWIN_SMEM_PAD=<bytes> of unused dynamic shared memory lowers the occupancy
     static const int smem_pad = getenv("GWIN_SMEM_PAD") ? atoi(getenv("GWIN_SMEM_PAD")) : 0;
@@ -2110,19 +2134,19 @@ static void launch_main(gwin_plan* p, bool recur, bool calibrated, int W, int wp
         attr_set[calibrated] = true;
     }
     if (recur && calibrated)
-        loglr_recur_kernel<ND, true><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, per_chunk, n_blk, p->d_blk_start,
-                                                                  p->d_blk_mat, p->d_mats,
-                                                                  p->d_wc, p->d_ks, ke_arr, p->d_partial);
+        loglr_recur_kernel<ND, true><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, per_chunk, n_blk, p->d_blk_start + blk_off,
+                                                                  p->d_blk_mat + blk_off, p->d_mats,
+                                                                  p->d_wc, ks_arr, ke_arr, partial);
     else if (recur)
-        loglr_recur_kernel<ND, false><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, per_chunk, n_blk, p->d_blk_start,
-                                                                   p->d_blk_mat, p->d_mats,
-                                                                   p->d_wc, p->d_ks, ke_arr, p->d_partial);
+        loglr_recur_kernel<ND, false><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, per_chunk, n_blk, p->d_blk_start + blk_off,
+                                                                   p->d_blk_mat + blk_off, p->d_mats,
+                                                                   p->d_wc, ks_arr, ke_arr, partial);
     else if (calibrated)
         loglr_direct_kernel<ND, true><<<grid, CTA_THREADS, 0, st>>>(p->d, W, wpad, per_chunk, n_chunks,
-                                                                   p->d_wc, p->d_ks, ke_arr, p->d_partial);
+                                                                   p->d_wc, ks_arr, ke_arr, partial);
     else
         loglr_direct_kernel<ND, false><<<grid, CTA_THREADS, 0, st>>>(p->d, W, wpad, per_chunk, n_chunks,
-                                                                    p->d_wc, p->d_ks, ke_arr, p->d_partial);
+                                                                    p->d_wc, ks_arr, ke_arr, partial);
 }
 
 template <int ND>
@@ -2211,14 +2235,22 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
         per_chunk = (per_chunk + RESYNC - 1) / RESYNC * RESYNC;
         n_chunks = (nbins + per_chunk - 1) / per_chunk;
     }
-    int rc = ensure_workspace(p, W, std::max(n_chunks, 1));
+    // second pass of the recurrence kernel over the blocks above k_split: every walker's tail
+    // (< one table sub-block, <= TAB_MAX bins); chunks of ~TAB_MAX bins
+    int n_chunks3 = 0, per_chunk3 = 1;
+    const int n_blk3 = table ? p->n_blk - p->n_blk_low : 0;
+    if (n_blk3 > 0) {
+        per_chunk3 = std::max(2, TAB_MAX / MAX_BLOCK);
+        n_chunks3 = (n_blk3 + per_chunk3 - 1) / per_chunk3;
+    }
+    int rc = ensure_workspace(p, W, std::max(n_chunks + n_chunks3, 1));
     if (rc) return rc;
     const int wpad = (int)p->w_cap;
     double* hh_rows = p->d_wc + (size_t)NCOEF(nd) * wpad;
     // table chunks: a sub-block costs about as much as 100 recurrence bins
     int n_chunksT = 0, per_chunkT = 1;
     if (table) {
-        const int wantT = std::max(1, std::min(p->n_tblk, (148 * 12 + groups - 1) / groups));
+        const int wantT = std::max(1, std::min(p->n_tblk, (148 * 24 + groups - 1) / groups));
         per_chunkT = (p->n_tblk + wantT - 1) / wantT;
         n_chunksT = (p->n_tblk + per_chunkT - 1) / per_chunkT;
         const size_t need = (size_t)n_chunksT * nd * p->w_cap;
@@ -2241,8 +2273,10 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
     }
     walker_setup_kernel<<<gb, tb, 0, st>>>(d, W, wpad, params, stride_walker, stride_param, skip, perm, p->d_wc, p->d_ks, p->d_ke, hh_rows,
                                            calib, cstride_walker, cstride_value,
-                                           table ? p->d_ke_low : nullptr, p->k_split);
+                                           table ? p->d_ke_low : nullptr, p->k_split,
+                                           p->d_ks_tail, p->d_tab_start, p->n_tblk);
     const int* ke_main = table ? p->d_ke_low : p->d_ke;
+    double2* partial3 = p->d_partial + (size_t)n_chunks * nd * wpad;
     if (p->timing) {
         if (p->ev_pending) {            // harvest the previous launch (it has long finished)
             float ms = 0.f;
@@ -2258,6 +2292,15 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
         case 3: launch_main<3>(p, recur, calib != nullptr, W, wpad, n_chunks, per_chunk, n_blk, ke_main, st); break;
         default: launch_main<4>(p, recur, calib != nullptr, W, wpad, n_chunks, per_chunk, n_blk, ke_main, st); break;
     }
+    if (n_chunks3 > 0) {
+        switch (nd) {
+            case 1: launch_main<1>(p, true, false, W, wpad, n_chunks3, per_chunk3, n_blk3, p->d_ke, st, p->n_blk_low, p->d_ks_tail, partial3); break;
+            case 2: launch_main<2>(p, true, false, W, wpad, n_chunks3, per_chunk3, n_blk3, p->d_ke, st, p->n_blk_low, p->d_ks_tail, partial3); break;
+            case 3: launch_main<3>(p, true, false, W, wpad, n_chunks3, per_chunk3, n_blk3, p->d_ke, st, p->n_blk_low, p->d_ks_tail, partial3); break;
+            default: launch_main<4>(p, true, false, W, wpad, n_chunks3, per_chunk3, n_blk3, p->d_ke, st, p->n_blk_low, p->d_ks_tail, partial3); break;
+        }
+        p->last_launches += 1;
+    }
     if (table) {
         switch (nd) {
             case 1: launch_table<1>(p, W, wpad, n_chunksT, per_chunkT, st); break;
@@ -2272,7 +2315,9 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
                                                                  recur ? p->d_blk_start : nullptr, band0, d.kmax,
                                                                  perm, p->d_wc, p->d_ks, ke_main,
                                                                  p->d_partial, hh_rows, loglr, hd, hh, p->d_marg_opt,
-                                                                 n_chunksT, per_chunkT, p->d_tab_start, p->d_partialT, p->d_ke);
+                                                                 n_chunksT, per_chunkT, p->d_tab_start, p->d_partialT, p->d_ke,
+                                                                 n_chunks3, per_chunk3, n_blk3, p->d_blk_start + p->n_blk_low,
+                                                                 p->d_ks_tail, partial3);
     p->last_launches += 3;
     if (mode >= GWIN_MODE_MARG_DIST) {
         marg_dist_kernel<<<(W + 7) / 8, 256, 0, st>>>(W, p->n_marg, p->d_marg_u, p->d_marg_logw, p->d_marg_opt, loglr);
@@ -2439,7 +2484,7 @@ extern "C" int gwin_generate_calib_host(gwin_plan* p, const double* params, cons
     }
     double* hh_rows = p->d_wc + (size_t)NCOEF(d.n_det) * wpad;
     walker_setup_kernel<<<1, 32, 0, st>>>(d, 1, wpad, p->d_params, GWIN_NPARAM, 1, nullptr, nullptr, p->d_wc, p->d_ks, p->d_ke, hh_rows,
-                                          calib ? p->d_calib : nullptr, (int64_t)nv, 1, nullptr, 0);
+                                          calib ? p->d_calib : nullptr, (int64_t)nv, 1, nullptr, 0, nullptr, nullptr, 0);
     generate_len_kernel<<<1, 1, 0, st>>>(d, p->d_params, p->d_ke);
     double2* dout = nullptr;
     CK(cudaMalloc(&dout, sizeof(double2) * (size_t)d.n_det * d.n_f));
