@@ -118,10 +118,14 @@ struct BlockMat {
 #define TAB_DEG 6            // degree of the Taylor polynomial of e^{-2 pi i R(j)}
 #define TAB_W 13             // taps of the exponential-of-semicircle interpolation kernel
 #define TAB_BETA (2.30 * TAB_W)
+#ifndef TAB_MIN
 #define TAB_MIN 256          // shortest / longest sub-block [bins], powers of two
+#endif
 #define TAB_MAX 2048
 #define TAB_RHO 0.007        // bound on |R| at the sub-block edge [rad]: truncation error ~ rho^4/24
 #define TAB_NM TAB_DEG       // moments stored per grid point: n = 0, 2, 3, .. TAB_DEG (c_1 = 0: nu carries the slope)
+#define TAB_PDEG 15          // degree of the per-tap polynomial of the interpolation kernel in v = 2u, u in (-1/2, 1/2]
+__constant__ double c_tab_poly[TAB_W][TAB_PDEG + 1];
 struct TabMat {
     double c[16];   // t_i = sum_j c[4 (i-1) + j] (th_{x_j} - th_centre), i = 1..4, j over nodes 0,1,3,4
     int node[5];    // node offsets from the sub-block start; node[2] = m/2 is the centre
@@ -1192,12 +1196,11 @@ tab_build_kernel(PlanDev P, const int* __restrict__ tab_start, const int* __rest
 }
 
 #ifndef TABLE_MIN_CTAS
-#define TABLE_MIN_CTAS 4
+#define TABLE_MIN_CTAS 5
 #endif
-#ifndef TAB_UNROLL
-#define TAB_UNROLL 2
+#ifndef TAB_GROUP
+#define TAB_GROUP 5          // taps whose weights are evaluated together (independent Horner chains)
 #endif
-static constexpr int kTabUnroll = TAB_UNROLL;
 template <int ND>
 __global__ void __launch_bounds__(CTA_THREADS, TABLE_MIN_CTAS)
 loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
@@ -1274,16 +1277,34 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
 #pragma unroll
                     for (int n = 0; n < TAB_NM; ++n) Mn[n] = make_double2(0.0, 0.0);
                     const double2* rd = row0 + (size_t)d * L * TAB_NM;
-#pragma unroll kTabUnroll
-                    for (int i = 0; i < TAB_W; ++i) {
-                        const double z = (x - (double)(g0 + i)) * (2.0 / TAB_W);
-                        const double wt = exp(TAB_BETA * (sqrt(fmax(1.0 - z * z, 0.0)) - 1.0));
-                        const double2* e = rd + (size_t)((g0 + i) & (L - 1)) * TAB_NM;
+                    // kernel weights: 13 independent Horner chains in v = 2 (x - g0) - (W - 1)
+                    const double v = 2.0 * (x - (double)g0) - (double)(TAB_W - 1);
+                    // (the opaque zero keeps the compiler from hoisting all 208 coefficients into
+                    //  registers across the detector / sub-block loops)
+                    int opq = 0;
+                    asm volatile("" : "+r"(opq));
+                    const double (*cp)[TAB_PDEG + 1] = c_tab_poly + opq;
+#pragma unroll 1
+                    for (int i0 = 0; i0 < TAB_W; i0 += TAB_GROUP) {
+                        double wt[TAB_GROUP];
 #pragma unroll
-                        for (int n = 0; n < TAB_NM; ++n) {
-                            const double2 q = __ldg(e + n);
-                            Mn[n].x = fma(wt, q.x, Mn[n].x);
-                            Mn[n].y = fma(wt, q.y, Mn[n].y);
+                        for (int i = 0; i < TAB_GROUP; ++i) wt[i] = cp[min(i0 + i, TAB_W - 1)][TAB_PDEG];
+#pragma unroll
+                        for (int k = TAB_PDEG - 1; k >= 0; --k) {
+#pragma unroll
+                            for (int i = 0; i < TAB_GROUP; ++i) wt[i] = fma(wt[i], v, cp[min(i0 + i, TAB_W - 1)][k]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < TAB_GROUP; ++i) {
+                            if (i0 + i < TAB_W) {
+                                const double2* e = rd + (size_t)((g0 + i0 + i) & (L - 1)) * TAB_NM;
+#pragma unroll
+                                for (int n = 0; n < TAB_NM; ++n) {
+                                    const double2 q = __ldg(e + n);
+                                    Mn[n].x = fma(wt[i], q.x, Mn[n].x);
+                                    Mn[n].y = fma(wt[i], q.y, Mn[n].y);
+                                }
+                            }
                         }
                     }
                     // sum_n c_n M_n; Mn[] holds n = 0, 2, 3, 4, 5, 6
@@ -1659,6 +1680,50 @@ static double es_kernel_host(long double x) {
     return (double)expl((long double)TAB_BETA * (sqrtl(1.0L - z * z) - 1.0L));
 }
 
+// Piecewise-polynomial form of the interpolation kernel (as in FINUFFT): with g0 = ceil(x - W/2)
+// and u = x - g0 - (W - 1)/2 in (-1/2, 1/2], tap i sits at distance u + (W - 1)/2 - i; on that unit
+// interval phi is smooth (its only singularity, at the edge of the support, has magnitude
+// e^-beta ~ 1e-13) and is replaced by its degree-TAB_PDEG Chebyshev interpolant, stored in
+// monomials of v = 2u for Horner evaluation with constant-bank operands.
+static int upload_tab_poly() {
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && done[dev]) return GWIN_OK;
+    const int n = TAB_PDEG + 1;
+    const long double pi = 3.14159265358979323846264338327950288L;
+    double out[TAB_W][TAB_PDEG + 1];
+    for (int i = 0; i < TAB_W; ++i) {
+        long double fv[TAB_PDEG + 1], cheb[TAB_PDEG + 1];
+        for (int q = 0; q < n; ++q) {
+            const long double v = cosl(pi * (q + 0.5L) / n);            // Chebyshev nodes in (-1, 1)
+            fv[q] = es_kernel_host(0.5L * v + 0.5L * (TAB_W - 1) - i);
+        }
+        for (int k = 0; k < n; ++k) {
+            long double sum = 0.0L;
+            for (int q = 0; q < n; ++q) sum += fv[q] * cosl(pi * k * (q + 0.5L) / n);
+            cheb[k] = sum * (k == 0 ? 1.0L : 2.0L) / n;
+        }
+        // Chebyshev -> monomial: T_0 = 1, T_1 = v, T_{k+1} = 2 v T_k - T_{k-1}
+        long double mono[TAB_PDEG + 1] = {0}, tkm[TAB_PDEG + 1] = {0}, tk[TAB_PDEG + 1] = {0};
+        tkm[0] = 1.0L; tk[1] = 1.0L;
+        for (int q = 0; q < n; ++q) mono[q] += cheb[0] * tkm[q];
+        if (n > 1) for (int q = 0; q < n; ++q) mono[q] += cheb[1] * tk[q];
+        for (int k = 2; k < n; ++k) {
+            long double tn[TAB_PDEG + 1] = {0};
+            for (int q = 0; q < n; ++q) {
+                if (q > 0) tn[q] += 2.0L * tk[q - 1];
+                tn[q] -= tkm[q];
+            }
+            for (int q = 0; q < n; ++q) { mono[q] += cheb[k] * tn[q]; tkm[q] = tk[q]; tk[q] = tn[q]; }
+        }
+        for (int q = 0; q < n; ++q) out[i][q] = (double)mono[q];
+    }
+    CK(cudaMemcpyToSymbol(c_tab_poly, out, sizeof out));
+    if (dev >= 0 && dev < 64) done[dev] = true;
+    return GWIN_OK;
+}
+
 static TabMat make_tab_mat(int m, int hat_off) {
     TabMat M;
     memset(&M, 0, sizeof M);
@@ -1753,6 +1818,7 @@ static int build_tables(gwin_plan* p) {
     p->tab_start.push_back(p->tab_start.back() + p->tabmats[p->tab_mi.back()].m);
     static const double budget_gb = getenv("GWIN_TABLE_GB") ? atof(getenv("GWIN_TABLE_GB")) : 4.0;
     if ((double)off * sizeof(double2) > budget_gb * 1073741824.0) return GWIN_OK;     // stay on the recurrence kernel
+    { const int rcp = upload_tab_poly(); if (rcp) return rcp; }
     CK(cudaMalloc(&p->d_tab_start, sizeof(int) * (n + 1)));
     CK(cudaMalloc(&p->d_tab_mi, sizeof(int) * n));
     CK(cudaMalloc(&p->d_tab_off, sizeof(int64_t) * n));
