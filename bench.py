@@ -345,7 +345,9 @@ def run_cuda(args):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(workload_config(W), l2="flushed between timed steps (256 MiB write)",
-                           kernel="loglr_recur_kernel: block-anchored cubic/quartic phasor recurrence (Horner), TMA-staged table tiles",
+                           kernel="loglr_recur_kernel (block-anchored phasor recurrence, TMA-staged tiles) below k_split and for "
+                                  "each walker's last sub-block; loglr_table_kernel (per-plan moment tables + 13-tap NUFFT "
+                                  "interpolation) above",
                            mean_bins_per_eval=float(bins.mean())),
             "clocks": clk,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": world * W * 13 * 8,
@@ -359,10 +361,12 @@ def run_cuda(args):
                                "nominal 148 SM x 64 lanes x 1.965 GHz = %.1f TFLOP/s" % nominal,
                 "frac_of_nominal": achieved / nominal,
                 "work_model": "W_alg = 32 + 12*n_det = %d FP64 issue slots per (walker, bin) "
-                              "(SURVEY.md 8d); the kernel itself issues 4 + 8*n_det (cubic blocks) or 8 + 8*n_det (quartic), "
-                              "so frac > 1 is expected; its practical ceiling is the register-file read bandwidth "
-                              "(DESIGN.md 4.2, profiles/r1_fp64_probe.txt)" % W_ALG_SLOTS,
-                "kernel": "loglr_recur_kernel<3>", "kernel_ms": kern_ms, "kernel_launches": kern_n,
+                              "(SURVEY.md 8d); the recurrence kernel issues 4 + 8*n_det (cubic blocks) or 8 + 8*n_det "
+                              "(quartic) per bin and the table kernel ~3500 per (walker, sub-block of 256..2048 bins), "
+                              "so frac > 1 is expected (DESIGN.md 4.2, 4.6)" % W_ALG_SLOTS,
+                "kernel": "loglr_recur_kernel<3,false> x2 + loglr_table_kernel<3> (timed as one bracket on the "
+                          "launching stream; split in profiles/)",
+                "kernel_ms": kern_ms, "kernel_launches": kern_n,
                 "kernel_share_of_step": kern_ms / (total_ms / args.steps),
                 "hbm": {"algorithmic_bytes_per_launch": alg_bytes,
                         "achieved_gbs": alg_bytes / (kern_ms * 1e-3) / 1e9,

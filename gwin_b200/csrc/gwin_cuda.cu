@@ -493,9 +493,14 @@ __global__ void walker_setup_kernel(PlanDev P, int W, int wpad,
         // is left to a second pass of the recurrence kernel over [ks_tail, ke)
         int tail = ke;
         if (ke > k_split) {
-            int lo = 0, hi = n_tblk - 1;                    // last sub-block starting below ke
-            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (tab_start[mid] < ke) lo = mid; else hi = mid - 1; }
-            if (ke < min(tab_start[lo + 1], P.kmax)) tail = tab_start[lo];
+            const int k_end = tab_start[n_tblk];            // end of the last sub-block (<= kmax)
+            if (ke > k_end) {
+                tail = k_end;
+            } else {
+                int lo = 0, hi = n_tblk - 1;                // last sub-block starting below ke
+                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (tab_start[mid] < ke) lo = mid; else hi = mid - 1; }
+                if (ke < tab_start[lo + 1]) tail = tab_start[lo];
+            }
         }
         ks_tail_arr[t] = tail;
     }
@@ -1240,7 +1245,7 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
             if (s >= ke) continue;
             const TabMat* M = mats + tab_mi[b];
             const int m = M->m, L = 2 * m;
-            if (ke >= min(s + m, P.kmax)) {
+            if (ke >= s + m) {
                 // ---- whole sub-block from the tables
                 const double h = 0.5 * (double)m;
                 const double thc = phase_turns(pc, ld_basis(P.basis + s + M->node[2]));
@@ -1788,7 +1793,11 @@ static int build_tables(gwin_plan* p) {
     std::vector<int> mat_of(32, -1);
     int64_t off = 0;
     for (int k = k_split; k < d.kmax;) {
-        const int m = std::max(table_block_len(p, k, chirp), TAB_MIN);
+        // sub-blocks lie wholly inside the band (their nodes index the basis table); what is
+        // left below kmax goes to the recurrence kernel's second pass with the walkers' tails
+        int m = std::max(table_block_len(p, k, chirp), TAB_MIN);
+        while (m > TAB_MIN && k + m > d.kmax) m >>= 1;
+        if (k + m > d.kmax) break;
         int lg = 0;
         while ((1 << lg) < m) ++lg;
         if (mat_of[lg] < 0) {
@@ -1815,6 +1824,7 @@ static int build_tables(gwin_plan* p) {
         k += m;
     }
     const int n = (int)p->tab_mi.size();
+    if (n == 0) return GWIN_OK;
     p->tab_start.push_back(p->tab_start.back() + p->tabmats[p->tab_mi.back()].m);
     static const double budget_gb = getenv("GWIN_TABLE_GB") ? atof(getenv("GWIN_TABLE_GB")) : 4.0;
     if ((double)off * sizeof(double2) > budget_gb * 1073741824.0) return GWIN_OK;     // stay on the recurrence kernel

@@ -393,11 +393,15 @@ class PlanModel(object):
         k = self.k_split
         self.tab_start, self.tab_m = [], []
         while k < self.kmax:
-            m = self._table_m(k, chirp, K2, K5)
+            m = max(self._table_m(k, chirp, K2, K5), self.TAB_MIN)
+            while m > self.TAB_MIN and k + m > self.kmax:
+                m >>= 1
+            if k + m > self.kmax:           # sub-blocks lie wholly inside the band
+                break
             self.tab_start.append(k)
             self.tab_m.append(m)
             k += m
-        self.tab_start.append(k)          # may run past kmax: T is zero there
+        self.tab_start.append(k)
         return self.tab_start
 
     def _table_m(self, k, chirp, K2, K5):
@@ -485,17 +489,18 @@ class PlanModel(object):
             psi = self.phase_turns(w, k)
             for d in range(self.n_det):
                 S[d] += np.sum(self.T[d, k] * np.exp(-2j * PI * (psi + k * w['tau'][d])))
+        done = self.k_split
         for b, (s, m) in enumerate(zip(self.tab_start[:-1], self.tab_m)):
-            if s >= ke:
+            if s + m > ke:
                 break
-            if s + m <= ke or s + m >= self.kmax >= ke >= self.kmax:
-                for d in range(self.n_det):
-                    S[d] += self.table_block(w, b, d)
-            else:                       # the sub-block holding ke: bin by bin
-                k = np.arange(s, ke)
-                psi = self.phase_turns(w, k)
-                for d in range(self.n_det):
-                    S[d] += np.sum(self.T[d, k] * np.exp(-2j * PI * (psi + k * w['tau'][d])))
+            for d in range(self.n_det):
+                S[d] += self.table_block(w, b, d)
+            done = s + m
+        if ke > done:                   # the tail: any exact method (second recurrence pass)
+            k = np.arange(done, ke)
+            psi = self.phase_turns(w, k)
+            for d in range(self.n_det):
+                S[d] += np.sum(self.T[d, k] * np.exp(-2j * PI * (psi + k * w['tau'][d])))
         return self.finish(w, S, marg)
 
     # -- loglr_recur_kernel -------------------------------------------------------

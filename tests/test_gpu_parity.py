@@ -97,19 +97,30 @@ def test_c3_kernels_agree_full_batch(cfg3):
     P = util.draw_bns(rng, 4096, cfg3)
     model.plan.configure(kernel=1)
     a = model.plan.loglr_host(P)
-    model.plan.configure(kernel=2)
-    b = model.plan.loglr_host(P)
-    assert np.all(np.abs(a[0] - b[0]) <= tol(a[0]))
-    assert np.all(np.abs(a[1] - b[1]) <= np.maximum(2e-6, 2e-9 * np.abs(a[2])))
-    np.testing.assert_array_equal(a[2], b[2])       # <h|h> is the same closed form
-    # determinism: same call, same bits
-    c = model.plan.loglr_host(P)
-    for x, y in zip(b, c):
-        np.testing.assert_array_equal(x, y)
-    # order invariance: a permuted batch gives permuted, bit-identical results
     perm = rng.permutation(len(P))
-    d = model.plan.loglr_host(P[perm])
-    np.testing.assert_array_equal(d[0], b[0][perm])
+    for kernel in (2, 3):                           # recurrence; recurrence + moment tables
+        model.plan.configure(kernel=kernel)
+        b = model.plan.loglr_host(P)
+        assert np.all(np.abs(a[0] - b[0]) <= tol(a[0])), kernel
+        assert np.all(np.abs(a[1] - b[1]) <= np.maximum(2e-6, 2e-9 * np.abs(a[2]))), kernel
+        np.testing.assert_array_equal(a[2], b[2])       # <h|h> is the same closed form
+        # determinism: same call, same bits
+        c = model.plan.loglr_host(P)
+        for x, y in zip(b, c):
+            np.testing.assert_array_equal(x, y)
+        # order invariance: a permuted batch gives permuted, bit-identical results
+        d = model.plan.loglr_host(P[perm])
+        np.testing.assert_array_equal(d[0], b[0][perm])
+    # the table kernel follows the batch's chirp-mass range: a batch of lighter systems
+    # rebuilds the schedule and the tables, and still agrees with the direct kernel
+    Q = P[:64].copy()
+    Q[:, 0] = rng.uniform(0.6, 0.8, 64)
+    Q[:, 1] = rng.uniform(0.6, 0.8, 64)
+    model.plan.configure(kernel=1)
+    a = model.plan.loglr_host(Q)
+    model.plan.configure(kernel=3)
+    b = model.plan.loglr_host(Q)
+    assert np.all(np.abs(a[0] - b[0]) <= tol(a[0]))
 
 
 def test_gps_epoch(cfg1):
@@ -241,7 +252,7 @@ def test_detector_counts_unit_psd_fupper(dets):
     assert abs(model.lognl - orc.lognl()) <= 1e-9 * abs(orc.lognl())
 
 
-@pytest.mark.parametrize("seglen", [4, 16, 64])
+@pytest.mark.parametrize("seglen", [4, 16, 64, 128])
 def test_segment_lengths_bns(seglen):
     """C5 regimes: short segments put the whole band (4 s) or its low-frequency part (16, 64 s)
     into directly-evaluated / short quartic blocks; every schedule regime must hold the
@@ -253,7 +264,7 @@ def test_segment_lengths_bns(seglen):
     P = util.draw_bns(rng, 12, cfg)
     P[0] = util.inj_row(cfg)
     lr0, hd0, hh0 = O.batch_loglr(cfg.oracle(), P)
-    for kernel in (1, 2):
+    for kernel in (1, 2, 3):
         model.plan.configure(kernel=kernel)
         lr, hd, hh = model.plan.loglr_host(P)
         _check(lr, hd, hh, lr0, hd0, hh0, "T=%d k%d" % (seglen, kernel))
@@ -273,7 +284,7 @@ def test_large_segment_two_million_bins():
     P[0] = util.inj_row(cfg)
     P[1, :2] = 1.0, 1.0            # waveform reaches 2199 Hz = bin 1.1 million
     lr0, hd0, hh0 = O.batch_loglr(cfg.oracle(), P)
-    for kernel in (1, 2):
+    for kernel in (1, 2, 3):
         model.plan.configure(kernel=kernel)
         lr, hd, hh = model.plan.loglr_host(P)
         _check(lr, hd, hh, lr0, hd0, hh0, "2M bins k%d" % kernel)

@@ -100,3 +100,22 @@ def test_calibration_arithmetic():
             assert abs(lr - lr0) <= util.tol(lr0)
             assert np.allclose(hh, list(hh0.values()), rtol=1e-10)
         assert abs(pm.loglr_recur(row)[0] - lr0) > 1e-3      # the calibration matters
+
+
+def test_table_kernel_arithmetic():
+    """The moment-table scheme above k_split (sub-block Taylor coefficients, deconvolved DFT
+    tables, 13-tap exponential-of-semicircle interpolation) against the direct sum and the
+    oracle; the schedule keeps |R| at the sub-block edge under TAB_RHO."""
+    cfg = util.c3(seglen=32)
+    pm = _plan(cfg, mchirp_min=1.0)
+    pm.build_tables()
+    assert pm.k_split < pm.kmax and min(pm.tab_m) >= pm.TAB_MIN and max(pm.tab_m) <= pm.TAB_MAX
+    assert all(m & (m - 1) == 0 for m in pm.tab_m)
+    orc = cfg.oracle()
+    rng = np.random.default_rng(3)
+    for row in util.draw_bns(rng, 2, cfg):
+        a = pm.loglr_direct(row)
+        b = pm.loglr_table(row)
+        assert abs(a[0] - b[0]) < 1e-8 and np.max(np.abs(a[1] - b[1])) < 1e-8
+        lr0 = orc.loglr(**dict(zip(util.PARAM_ORDER, row)))[0]
+        assert abs(b[0] - lr0) <= util.tol(lr0)
