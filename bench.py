@@ -224,6 +224,9 @@ def run_cuda(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION: stdout carries the one JSON line only
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     n_f = int(SEGLEN * SRATE) // 2 + 1
