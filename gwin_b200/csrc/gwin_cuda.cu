@@ -115,23 +115,24 @@ struct BlockMat {
 };
 
 // Table kernel: sub-block moments of the data looked up by a type-2 NUFFT
-#define TAB_DEG 6            // degree of the Taylor polynomial of e^{-2 pi i R(j)}
+#define TAB_DEG 8            // degree of the Taylor polynomial of e^{-2 pi i R(j)}
+#define TAB_PH 6             // degree of the phase polynomial through TAB_PH + 1 exact samples
 #define TAB_W 13             // taps of the exponential-of-semicircle interpolation kernel
 #define TAB_BETA (2.30 * TAB_W)
 #ifndef TAB_MIN
-#define TAB_MIN 256          // shortest / longest sub-block [bins], powers of two
+#define TAB_MIN 256          // shortest / longest sub-block [bins]; lengths are 2^k and 3 2^(k-1)
 #endif
-#define TAB_MAX 2048
-#define TAB_RHO 0.007        // bound on |R| at the sub-block edge [rad]: truncation error ~ rho^4/24
+#define TAB_MAX 4096
+#define TAB_RHO 0.025        // bound on |R| at the sub-block edge [rad]: truncation error ~ rho^5/120
 #define TAB_NM TAB_DEG       // moments stored per grid point: n = 0, 2, 3, .. TAB_DEG (c_1 = 0: nu carries the slope)
 #define TAB_PDEG 15          // degree of the per-tap polynomial of the interpolation kernel in v = 2u, u in (-1/2, 1/2]
 __constant__ double c_tab_poly[TAB_W][TAB_PDEG + 1];
 struct TabMat {
-    double c[16];   // t_i = sum_j c[4 (i-1) + j] (th_{x_j} - th_centre), i = 1..4, j over nodes 0,1,3,4
-    int node[5];    // node offsets from the sub-block start; node[2] = m/2 is the centre
+    double c[TAB_PH * TAB_PH];   // t_i = sum_j c[TAB_PH (i-1) + j] (th_{x_j} - th_centre), i = 1..TAB_PH, j over the off-centre nodes
+    int node[TAB_PH + 1];        // node offsets from the sub-block start; node[TAB_PH/2] = m/2 is the centre
     int m;
-    int hat_off;    // offset of this length's 1/phi_hat[j] in the invhat array
-    int pad;
+    int hat_off;                 // offset of this length's 1/phi_hat[j] in the invhat array
+    int pad[3];
 };
 
 struct gwin_plan {
@@ -1166,8 +1167,9 @@ tab_build_kernel(PlanDev P, const int* __restrict__ tab_start, const int* __rest
     const int b = blockIdx.y, d = blockIdx.z;
     const TabMat* M = mats + tab_mi[b];
     const int m = M->m, L = 2 * m;
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= L) return;
+    const int gp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gp >= L + TAB_W) return;
+    const int g = gp >= L ? gp - L : gp;         // rows carry TAB_W wrap-around points: taps never wrap
     const int s = tab_start[b];
     const double* ih = invhat + M->hat_off;
     const double ih2 = 2.0 / (double)m;
@@ -1180,7 +1182,8 @@ tab_build_kernel(PlanDev P, const int* __restrict__ tab_start, const int* __rest
         const double2 Tk = __ldg(P.T + (size_t)k * P.n_det + d);
         if (Tk.x == 0.0 && Tk.y == 0.0) continue;
         const int jc = j - m / 2;
-        const int idx = (jc * g) & (L - 1);                 // (jc g) mod L, L a power of two
+        int idx = (int)(((long long)jc * g) % L);          // (jc g) mod L
+        if (idx < 0) idx += L;
         double sn, cs;
         sincospi(-2.0 * (double)idx / (double)L, &sn, &cs);
         double2 u = cmul(Tk, make_double2(cs, sn));
@@ -1194,7 +1197,7 @@ tab_build_kernel(PlanDev P, const int* __restrict__ tab_start, const int* __rest
         }
     }
     // layout [d][g][TAB_NM]: the moments of one grid point are contiguous (one or two cache lines per tap)
-    double2* out = tab + tab_off[b] + ((size_t)d * L + g) * TAB_NM;
+    double2* out = tab + tab_off[b] + ((size_t)d * (L + TAB_W) + gp) * TAB_NM;
     out[0] = acc[0];
 #pragma unroll
     for (int n = 2; n <= TAB_DEG; ++n) out[n - 1] = acc[n];
@@ -1248,28 +1251,39 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
             if (ke >= s + m) {
                 // ---- whole sub-block from the tables
                 const double h = 0.5 * (double)m;
-                const double thc = phase_turns(pc, ld_basis(P.basis + s + M->node[2]));
-                double v[4];
-                v[0] = phase_turns(pc, ld_basis(P.basis + s + M->node[0])) - thc;
-                v[1] = phase_turns(pc, ld_basis(P.basis + s + M->node[1])) - thc;
-                v[2] = phase_turns(pc, ld_basis(P.basis + s + M->node[3])) - thc;
-                v[3] = phase_turns(pc, ld_basis(P.basis + s + M->node[4])) - thc;
-                double tq[4];                    // t_1..t_4: Theta - th_c = sum t_i (j/h)^i [turns]
+                const double thc = phase_turns(pc, ld_basis(P.basis + s + M->node[TAB_PH / 2]));
+                double v_[TAB_PH];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < TAB_PH; ++i)
+                    v_[i] = phase_turns(pc, ld_basis(P.basis + s + M->node[i < TAB_PH / 2 ? i : i + 1])) - thc;
+                double tq[TAB_PH];               // t_1..t_6: Theta - th_c = sum t_i (j/h)^i [turns]
+#pragma unroll
+                for (int i = 0; i < TAB_PH; ++i) {
                     double a = 0.0;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) a = fma(M->c[4 * i + j], v[j], a);
+                    for (int j = 0; j < TAB_PH; ++j) a = fma(M->c[TAB_PH * i + j], v_[j], a);
                     tq[i] = a;
                 }
-                // c_n of e^{-i a R}, a = 2 pi, R = t2 s^2 + t3 s^3 + t4 s^4, through R^3, degree <= 6
-                // (c_0 = 1, c_1 = 0, c_2 = -i a t2, c_3 = -i a t3, c_4 = -a^2 t2^2/2 - i a t4,
-                //  c_5 = -a^2 t2 t3, c_6 = -a^2 (t3^2 + 2 t2 t4)/2 + i a^3 t2^3/6)
-                const double a1 = G_TWOPI, t2 = tq[1], t3 = tq[2], t4 = tq[3];
-                const double a2h = 0.5 * a1 * a1;
-                const double c2i = -a1 * t2, c3i = -a1 * t3, c4r = -a2h * t2 * t2, c4i = -a1 * t4;
-                const double c5r = -a2h * 2.0 * t2 * t3;
-                const double c6r = -a2h * fma(2.0 * t2, t4, t3 * t3), c6i = (a1 * a1 * a1 / 6.0) * t2 * t2 * t2;
+                // Taylor coefficients e_n of exp(U), U = i sum_{k=2..6} w_k s^k, w_k = -2 pi t_k:
+                //   n e_n = sum_k k (i w_k) e_{n-k};  e_0 = 1, e_1 = 0 (nu carries the slope)
+                double kw[TAB_PH + 1];
+#pragma unroll
+                for (int k = 2; k <= TAB_PH; ++k) kw[k] = -G_TWOPI * (double)k * tq[k - 1];
+                double2 en[TAB_DEG + 1];
+                en[0] = make_double2(1.0, 0.0);
+                en[1] = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int n = 2; n <= TAB_DEG; ++n) {
+                    double re = 0.0, im = 0.0;
+#pragma unroll
+                    for (int k = 2; k <= TAB_PH; ++k) {
+                        if (k <= n) {
+                            re = fma(-kw[k], en[n - k].y, re);
+                            im = fma(kw[k], en[n - k].x, im);
+                        }
+                    }
+                    en[n] = make_double2(re * (1.0 / n), im * (1.0 / n));
+                }
                 const double kc = (double)(s + m / 2);
                 const double2* row0 = tab + tab_off[b];
 #pragma unroll
@@ -1277,11 +1291,12 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
                     const double tau = tau_hi[d] + tau_lo[d];
                     const double nu = tq[0] / h + tau;                        // turns per bin
                     const double x = (nu - floor(nu)) * (double)L;            // [0, L)
-                    const int g0 = (int)ceil(x - 0.5 * TAB_W);
+                    const int g0 = (int)ceil(x - 0.5 * TAB_W);                // -6 .. L - 6
                     double2 Mn[TAB_NM];
 #pragma unroll
                     for (int n = 0; n < TAB_NM; ++n) Mn[n] = make_double2(0.0, 0.0);
-                    const double2* rd = row0 + (size_t)d * L * TAB_NM;
+                    // rows are padded with TAB_W wrap-around points: the taps are contiguous
+                    const double2* rd = row0 + ((size_t)d * (L + TAB_W) + (g0 < 0 ? g0 + L : g0)) * TAB_NM;
                     // kernel weights: 13 independent Horner chains in v = 2 (x - g0) - (W - 1)
                     const double v = 2.0 * (x - (double)g0) - (double)(TAB_W - 1);
                     // (the opaque zero keeps the compiler from hoisting all 208 coefficients into
@@ -1302,7 +1317,7 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
 #pragma unroll
                         for (int i = 0; i < TAB_GROUP; ++i) {
                             if (i0 + i < TAB_W) {
-                                const double2* e = rd + (size_t)((g0 + i0 + i) & (L - 1)) * TAB_NM;
+                                const double2* e = rd + (i0 + i) * TAB_NM;
 #pragma unroll
                                 for (int n = 0; n < TAB_NM; ++n) {
                                     const double2 q = __ldg(e + n);
@@ -1312,13 +1327,10 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
                             }
                         }
                     }
-                    // sum_n c_n M_n; Mn[] holds n = 0, 2, 3, 4, 5, 6
+                    // sum_n e_n M_n; Mn[] holds n = 0, 2, 3, .. TAB_DEG
                     double2 sum = Mn[0];
-                    sum.x = fma(-c2i, Mn[1].y, sum.x); sum.y = fma(c2i, Mn[1].x, sum.y);
-                    sum.x = fma(-c3i, Mn[2].y, sum.x); sum.y = fma(c3i, Mn[2].x, sum.y);
-                    sum = cfma(make_double2(c4r, c4i), Mn[3], sum);
-                    sum.x = fma(c5r, Mn[4].x, sum.x); sum.y = fma(c5r, Mn[4].y, sum.y);
-                    sum = cfma(make_double2(c6r, c6i), Mn[5], sum);
+#pragma unroll
+                    for (int n = 2; n <= TAB_DEG; ++n) sum = cfma(en[n], Mn[n - 1], sum);
                     const double th0 = thc + fma(kc, tau_lo[d], frac1(kc * tau_hi[d]));
                     acc[d] = cfma(sum, phasor_neg(th0), acc[d]);
                 }
@@ -1666,17 +1678,51 @@ static int upload_schedule(gwin_plan* p) {
 
 
 // ---- table kernel: schedule + moment tables -------------------------------------------------
-static int table_block_len(const gwin_plan* p, int k, double chirp) {
+// Admissible sub-block lengths (2^k and 3 2^(k-1) in [TAB_MIN, TAB_MAX]), their phase-polynomial
+// nodes (rounded Chebyshev-Lobatto points, the centre moved to m/2) and the worst value of
+// |prod_i (j - x_i)| over the sub-block (the interpolation error factor).
+struct TabSize { int m; int node[TAB_PH + 1]; double omega; };
+static const std::vector<TabSize>& table_sizes() {
+    static std::vector<TabSize> sizes;
+    if (!sizes.empty()) return sizes;
+    for (int m = TAB_MIN; m <= TAB_MAX; m *= 2)
+        for (int v = 0; v < 2; ++v) {
+            TabSize S;
+            S.m = v ? m + m / 2 : m;
+            if (S.m > TAB_MAX) continue;
+            for (int i = 0; i <= TAB_PH; ++i)
+                S.node[i] = (int)lround((S.m - 1) * 0.5 * (1.0 - cos(G_PI * i / TAB_PH)));
+            S.node[TAB_PH / 2] = S.m / 2;
+            S.omega = 0.0;
+            for (int j = 0; j < S.m; ++j) {
+                double prod = 1.0;
+                for (int i = 0; i <= TAB_PH; ++i) prod *= (double)(j - S.node[i]);
+                S.omega = std::max(S.omega, std::fabs(prod));
+            }
+            sizes.push_back(S);
+        }
+    std::sort(sizes.begin(), sizes.end(), [](const TabSize& a, const TabSize& b) { return a.m < b.m; });
+    return sizes;
+}
+
+// Longest admissible sub-block starting at bin k (index into table_sizes(), -1: none): |R| <= TAB_RHO
+// at its edge and the degree-TAB_PH interpolation of the phase good to phase_tol, for the leading-order
+// chirp of the smallest chirp mass (x2 safety for the higher PN orders, as in build_schedule).
+static int table_block_size(const gwin_plan* p, int k, double chirp) {
     const PlanDev& d = p->d;
-    const double K2 = (5.0 / 3) * (8.0 / 3), K5 = K2 * (11.0 / 3) * (14.0 / 3) * (17.0 / 3);
     const double f = k * d.delta_f;
-    const double d2 = chirp * K2 * d.delta_f * d.delta_f * pow(f, -11.0 / 3.0);      // rad / bin^2
-    const double d5 = chirp * K5 * pow(d.delta_f, 5.0) * pow(f, -20.0 / 3.0);        // rad / bin^5
-    const double h = sqrt(2.0 * TAB_RHO / d2);                                       // d2 h^2 / 2 <= TAB_RHO
-    const double b4 = pow(p->phase_tol * 120.0 / (0.005 * d5), 0.2) + 1.0;           // quartic through 5 nodes
-    const double m = std::min(std::min(2.0 * h, b4), (double)TAB_MAX);
-    if (m < 1.0) return 0;
-    return 1 << (int)floor(log2(m));
+    double K2 = 1.0, Kn = 1.0, fact = 1.0;
+    for (int i = 0; i < 2; ++i) K2 *= 5.0 / 3 + i;
+    for (int i = 0; i <= TAB_PH; ++i) { Kn *= 5.0 / 3 + i; fact *= i + 1; }
+    const double d2 = chirp * K2 * d.delta_f * d.delta_f * pow(f, -5.0 / 3 - 2);                     // rad / bin^2
+    const double dn = chirp * Kn * pow(d.delta_f, TAB_PH + 1.0) * pow(f, -5.0 / 3 - (TAB_PH + 1));   // rad / bin^7
+    const std::vector<TabSize>& sizes = table_sizes();
+    int best = -1;
+    for (size_t i = 0; i < sizes.size(); ++i) {
+        const double hh = 0.5 * sizes[i].m;
+        if (0.5 * d2 * hh * hh <= TAB_RHO && dn / fact * sizes[i].omega <= p->phase_tol) best = (int)i;
+    }
+    return best;
 }
 
 static double es_kernel_host(long double x) {
@@ -1729,37 +1775,37 @@ static int upload_tab_poly() {
     return GWIN_OK;
 }
 
-static TabMat make_tab_mat(int m, int hat_off) {
+static TabMat make_tab_mat(const TabSize& S, int hat_off) {
     TabMat M;
     memset(&M, 0, sizeof M);
+    const int m = S.m;
     M.m = m; M.hat_off = hat_off;
-    const int e = m - 1, q = (e + 4) / 8;
-    const int x[5] = {0, q, m / 2, e - q, e};
-    for (int i = 0; i < 5; ++i) M.node[i] = x[i];
-    // t_i, i = 1..4, from v_j = th(x_j) - th(centre), j over the four off-centre nodes:
+    for (int i = 0; i <= TAB_PH; ++i) M.node[i] = S.node[i];
+    // t_i, i = 1..TAB_PH, from v_j = th(x_j) - th(centre), j over the off-centre nodes:
     // sum_i t_i s_j^i = v_j with s_j = (x_j - m/2) / (m/2)
-    const int col[4] = {0, 1, 3, 4};
-    long double A[4][8];
-    for (int r = 0; r < 4; ++r) {
-        const long double sj = ((long double)x[col[r]] - m / 2) / (0.5L * m);
+    const int n = TAB_PH;
+    long double A[TAB_PH][2 * TAB_PH];
+    for (int r = 0; r < n; ++r) {
+        const int xi = S.node[r < n / 2 ? r : r + 1];
+        const long double sj = ((long double)xi - m / 2) / (0.5L * m);
         long double pw = sj;
-        for (int c = 0; c < 4; ++c) { A[r][c] = pw; pw *= sj; }
-        for (int c = 0; c < 4; ++c) A[r][4 + c] = (r == c) ? 1.0L : 0.0L;
+        for (int c = 0; c < n; ++c) { A[r][c] = pw; pw *= sj; }
+        for (int c = 0; c < n; ++c) A[r][n + c] = (r == c) ? 1.0L : 0.0L;
     }
-    for (int c = 0; c < 4; ++c) {                      // Gauss-Jordan with partial pivoting
+    for (int c = 0; c < n; ++c) {                      // Gauss-Jordan with partial pivoting
         int piv = c;
-        for (int r = c + 1; r < 4; ++r) if (fabsl(A[r][c]) > fabsl(A[piv][c])) piv = r;
-        for (int q2 = 0; q2 < 8; ++q2) std::swap(A[c][q2], A[piv][q2]);
+        for (int r = c + 1; r < n; ++r) if (fabsl(A[r][c]) > fabsl(A[piv][c])) piv = r;
+        for (int q2 = 0; q2 < 2 * n; ++q2) std::swap(A[c][q2], A[piv][q2]);
         const long double inv = 1.0L / A[c][c];
-        for (int q2 = 0; q2 < 8; ++q2) A[c][q2] *= inv;
-        for (int r = 0; r < 4; ++r) {
+        for (int q2 = 0; q2 < 2 * n; ++q2) A[c][q2] *= inv;
+        for (int r = 0; r < n; ++r) {
             if (r == c) continue;
             const long double f = A[r][c];
-            for (int q2 = 0; q2 < 8; ++q2) A[r][q2] -= f * A[c][q2];
+            for (int q2 = 0; q2 < 2 * n; ++q2) A[r][q2] -= f * A[c][q2];
         }
     }
-    for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) M.c[4 * i + j] = (double)A[i][4 + j];
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) M.c[n * i + j] = (double)A[i][n + j];
     return M;
 }
 
@@ -1782,45 +1828,52 @@ static int build_tables(gwin_plan* p) {
     p->tab_dirty = false;
     const double chirp = 2.0 * (3.0 / 128.0) * pow(G_PI * p->mchirp_min * G_MTSUN, -5.0 / 3.0);
     const int band0 = std::max(std::max(d.kmin, d.istart), 1);
+    const std::vector<TabSize>& sizes = table_sizes();
     int raw = band0;
-    while (raw < d.kmax && table_block_len(p, raw, chirp) < TAB_MIN) raw += 64;
+    while (raw < d.kmax && table_block_size(p, raw, chirp) < 0) raw += 64;
     if (raw >= d.kmax) return GWIN_OK;
     int ib = 0;
     while (ib < p->n_blk && p->blk_start[ib] < raw) ++ib;
     if (ib >= p->n_blk) return GWIN_OK;
     const int k_split = p->blk_start[ib];
     std::vector<double> invhat;
-    std::vector<int> mat_of(32, -1);
+    std::vector<int> mat_of(sizes.size(), -1);
     int64_t off = 0;
     for (int k = k_split; k < d.kmax;) {
         // sub-blocks lie wholly inside the band (their nodes index the basis table); what is
         // left below kmax goes to the recurrence kernel's second pass with the walkers' tails
-        int m = std::max(table_block_len(p, k, chirp), TAB_MIN);
-        while (m > TAB_MIN && k + m > d.kmax) m >>= 1;
+        int si = std::max(table_block_size(p, k, chirp), 0);
+        while (si > 0 && k + sizes[si].m > d.kmax) --si;
+        const int m = sizes[si].m;
         if (k + m > d.kmax) break;
-        int lg = 0;
-        while ((1 << lg) < m) ++lg;
-        if (mat_of[lg] < 0) {
-            mat_of[lg] = (int)p->tabmats.size();
-            p->tabmats.push_back(make_tab_mat(m, (int)invhat.size()));
+        if (mat_of[si] < 0) {
+            mat_of[si] = (int)p->tabmats.size();
+            p->tabmats.push_back(make_tab_mat(sizes[si], (int)invhat.size()));
             // 1 / phi_hat(jc / L), phi_hat by midpoint quadrature of the kernel over its support
-            const int nq = 2048, L = 2 * m;
-            std::vector<long double> xs(nq), ph(nq);
-            for (int q = 0; q < nq; ++q) {
-                xs[q] = ((long double)q + 0.5L) / nq * TAB_W - 0.5L * TAB_W;
-                ph[q] = es_kernel_host(xs[q]);
+            // (depends on m only: computed once per process)
+            static std::vector<double> hat_cache[32];
+            std::vector<double>& hc = hat_cache[si];
+            if (hc.empty()) {
+                const int nq = 2048, L = 2 * m;
+                std::vector<long double> xs(nq), ph(nq);
+                for (int q = 0; q < nq; ++q) {
+                    xs[q] = ((long double)q + 0.5L) / nq * TAB_W - 0.5L * TAB_W;
+                    ph[q] = es_kernel_host(xs[q]);
+                }
+                hc.resize(m);
+                for (int j = 0; j < m; ++j) {
+                    const long double xi = (long double)(j - m / 2) / L;
+                    long double sum = 0.0L;
+                    for (int q = 0; q < nq; ++q) sum += ph[q] * cosl(2.0L * 3.14159265358979323846264338327950288L * xi * xs[q]);
+                    hc[j] = (double)(1.0L / (sum * TAB_W / nq));
+                }
             }
-            for (int j = 0; j < m; ++j) {
-                const long double xi = (long double)(j - m / 2) / L;
-                long double sum = 0.0L;
-                for (int q = 0; q < nq; ++q) sum += ph[q] * cosl(2.0L * 3.14159265358979323846264338327950288L * xi * xs[q]);
-                invhat.push_back((double)(1.0L / (sum * TAB_W / nq)));
-            }
+            invhat.insert(invhat.end(), hc.begin(), hc.end());
         }
         p->tab_start.push_back(k);
-        p->tab_mi.push_back(mat_of[lg]);
+        p->tab_mi.push_back(mat_of[si]);
         p->tab_off.push_back(off);
-        off += (int64_t)d.n_det * TAB_NM * 2 * m;
+        off += (int64_t)d.n_det * TAB_NM * (2 * m + TAB_W);
         k += m;
     }
     const int n = (int)p->tab_mi.size();
@@ -1840,7 +1893,7 @@ static int build_tables(gwin_plan* p) {
     CK(cudaMemcpy(p->d_tab_off, p->tab_off.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(p->d_tabmats, p->tabmats.data(), sizeof(TabMat) * p->tabmats.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(p->d_invhat, invhat.data(), sizeof(double) * invhat.size(), cudaMemcpyHostToDevice));
-    tab_build_kernel<<<dim3(2 * TAB_MAX / 256, n, d.n_det), 256>>>(d, p->d_tab_start, p->d_tab_mi, p->d_tab_off,
+    tab_build_kernel<<<dim3((2 * TAB_MAX + TAB_W + 255) / 256, n, d.n_det), 256>>>(d, p->d_tab_start, p->d_tab_mi, p->d_tab_off,
                                                                p->d_tabmats, p->d_invhat, p->d_tab);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());

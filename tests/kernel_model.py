@@ -374,28 +374,49 @@ class PlanModel(object):
     # nu = g/(2m) (zero-padded FFT of the kernel-deconvolved sequence); per walker the block sum
     # is e^{-2 pi i th0} sum_n c_n M_n(nu) with the M_n interpolated by a TAB_W-tap
     # exponential-of-semicircle kernel and c_n the Taylor coefficients of e^{-2 pi i R(j)},
-    # R = the quadratic..quartic part of the block polynomial.
-    TAB_DEG, TAB_W, TAB_MIN, TAB_MAX, TAB_RHO = 6, 13, 256, 2048, 0.007
+    # R = the quadratic..sextic part of the polynomial through TAB_PH + 1 exact phase samples.
+    TAB_DEG, TAB_W, TAB_MIN, TAB_MAX, TAB_RHO, TAB_PH = 8, 13, 256, 4096, 0.025, 6
+
+    @classmethod
+    def table_nodes(cls, m):
+        """TAB_PH + 1 nodes of the phase polynomial on [0, m-1]: rounded Chebyshev-Lobatto points
+        with the centre moved to m/2."""
+        n = cls.TAB_PH
+        x = [int(round((m - 1) * 0.5 * (1 - math.cos(math.pi * i / n)))) for i in range(n + 1)]
+        x[n // 2] = m // 2
+        return x
+
+    @classmethod
+    def table_sizes(cls):
+        """Admissible sub-block lengths: 2^k and 3 2^(k-1)."""
+        out, m = [], cls.TAB_MIN
+        while m <= cls.TAB_MAX:
+            out.append(m)
+            if m + m // 2 <= cls.TAB_MAX:
+                out.append(m + m // 2)
+            m *= 2
+        return sorted(out)
 
     def build_table_schedule(self):
         band0 = max(self.kmin, self.istart)
-        K2 = (5. / 3) * (8. / 3)
-        K5 = K2 * (11. / 3) * (14. / 3) * (17. / 3)
         chirp = 2.0 * (3. / 128.) * (PI * self.mchirp_min * MTSUN) ** (-5. / 3)
-        starts, k = [], None
-        # first bin from which TAB_MIN-bin sub-blocks meet both bounds
+        sizes = self.table_sizes()
+        # worst |prod (j - x_i)| over the sub-block, per size (interpolation error factor)
+        self._tab_omega = {}
+        for m in sizes:
+            x = np.array(self.table_nodes(m), dtype=float)
+            j = np.arange(m, dtype=float)
+            self._tab_omega[m] = float(np.max(np.abs(np.prod(j[:, None] - x[None, :], axis=1))))
         kk = max(band0, 1)
-        while kk < self.kmax:
-            if self._table_m(kk, chirp, K2, K5) >= self.TAB_MIN:
-                break
+        while kk < self.kmax and self._table_m(kk, chirp, sizes) < self.TAB_MIN:
             kk += 64
         self.k_split = min(kk, self.kmax)
         k = self.k_split
         self.tab_start, self.tab_m = [], []
         while k < self.kmax:
-            m = max(self._table_m(k, chirp, K2, K5), self.TAB_MIN)
+            m = max(self._table_m(k, chirp, sizes), self.TAB_MIN)
             while m > self.TAB_MIN and k + m > self.kmax:
-                m >>= 1
+                m = max(s for s in sizes if s < m)
             if k + m > self.kmax:           # sub-blocks lie wholly inside the band
                 break
             self.tab_start.append(k)
@@ -404,14 +425,25 @@ class PlanModel(object):
         self.tab_start.append(k)
         return self.tab_start
 
-    def _table_m(self, k, chirp, K2, K5):
+    def _table_m(self, k, chirp, sizes):
+        """Longest admissible sub-block starting at bin k: |R| <= TAB_RHO at its edge and the
+        degree-TAB_PH interpolation of the phase good to phase_tol."""
         f = k * self.delta_f
-        d2 = chirp * K2 * self.delta_f ** 2 * f ** (-11. / 3)
-        d5 = chirp * K5 * self.delta_f ** 5 * f ** (-20. / 3)
-        h = math.sqrt(2.0 * self.TAB_RHO / d2)                         # d2 h^2 / 2 <= TAB_RHO
-        b4 = (self.phase_tol * 120.0 / (0.005 * d5)) ** 0.2 + 1.0      # quartic interpolation bound
-        m = min(2.0 * h, b4, self.TAB_MAX)
-        return 0 if m < 1 else 1 << int(math.floor(math.log2(m)))
+        K = 1.0
+        for i in range(2):
+            K *= (5. / 3 + i)
+        d2 = chirp * K * self.delta_f ** 2 * f ** (-5. / 3 - 2)
+        n = self.TAB_PH + 1
+        K = 1.0
+        for i in range(n):
+            K *= (5. / 3 + i)
+        dn = chirp * K * self.delta_f ** n * f ** (-5. / 3 - n)
+        best = 0
+        for m in sizes:
+            if 0.5 * d2 * (0.5 * m) ** 2 <= self.TAB_RHO and \
+                    dn / math.factorial(n) * self._tab_omega[m] <= self.phase_tol:
+                best = m
+        return best
 
     @staticmethod
     def es_kernel(x, w, beta):
@@ -445,7 +477,7 @@ class PlanModel(object):
                 seg[:n_have] = self.T[d, s:s + n_have]
                 for n in range(N + 1):
                     a = seg * (jc / (m / 2.0)) ** n / hat[m]
-                    rows[d, n] = np.fft.fft(a, L) * np.exp(2j * np.pi * g * (m // 2) / L)
+                    rows[d, n] = np.fft.fft(a, L) * np.exp(2j * np.pi * ((g * (m // 2)) % L) / L)
             self.tab.append(rows)
 
     def table_block(self, w, b, d):
@@ -453,22 +485,24 @@ class PlanModel(object):
         s, m = self.tab_start[b], self.tab_m[b]
         N, W, beta = self.TAB_DEG, self.TAB_W, 2.30 * self.TAB_W
         h = m / 2.0
-        e = m - 1
-        q = (e + 4) // 8
-        nodes = np.array([0, q, m // 2, e - q, e])
+        nodes = np.array(self.table_nodes(m))
+        ic = self.TAB_PH // 2
         sn = (nodes - m // 2) / h
         th = self.phase_turns(w, s + nodes)
-        coef = np.linalg.solve(np.vander(sn, 5, increasing=True), th - th[2])   # t_i s^i, t_0 = 0
-        th0 = th[2] + (s + m // 2) * w['tau'][d]
-        nu = coef[1] / h + w['tau'][d]
-        r = np.zeros(N + 1, dtype=complex)
-        r[2:5] = -2j * PI * coef[2:5]
+        keep = [i for i in range(len(nodes)) if i != ic]
+        V = np.array([[sn[i] ** k for k in range(1, self.TAB_PH + 1)] for i in keep])
+        t = np.concatenate([[0.0], np.linalg.solve(V, (th - th[ic])[keep])])    # t_k s^k, t_0 = 0
+        th0 = th[ic] + (s + m // 2) * w['tau'][d]
+        nu = t[1] / h + w['tau'][d]
+        # Taylor coefficients of exp(U), U = -2 pi i sum_{k>=2} t_k s^k:  n e_n = sum_k k u_k e_{n-k}
+        u = -2j * PI * t
         c = np.zeros(N + 1, dtype=complex)
         c[0] = 1.0
-        term = c.copy()
-        for kk in range(1, N // 2 + 1):
-            term = np.convolve(term, r)[:N + 1] / kk
-            c = c + term
+        for n in range(1, N + 1):
+            acc = 0j
+            for k in range(2, min(n, self.TAB_PH) + 1):
+                acc += k * u[k] * c[n - k]
+            c[n] = acc / n
         x = (nu - math.floor(nu)) * (2 * m)
         g0 = int(math.ceil(x - W / 2.0))
         taps = g0 + np.arange(W)
