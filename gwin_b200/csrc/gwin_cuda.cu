@@ -1206,6 +1206,8 @@ tab_build_kernel(PlanDev P, const int* __restrict__ tab_start, const int* __rest
 #ifndef TABLE_MIN_CTAS
 #define TABLE_MIN_CTAS 5
 #endif
+#define TAB_SPAN 24          // table rows a warp stages per detector and sub-block (>= TAB_W + the lanes' spread)
+#define TAB_ROWB (TAB_NM * 16 + 16)
 #ifndef TAB_GROUP
 #define TAB_GROUP 5          // taps whose weights are evaluated together (independent Horner chains)
 #endif
@@ -1242,14 +1244,21 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
             tau_hi[d] = row[D_TAUHI * wpad];
             tau_lo[d] = row[D_TAULO * wpad];
         }
+        // per-warp staging buffers: [ND][TAB_SPAN] table rows of TAB_ROWB bytes (128 B of moments + 16 B
+        // of padding so that lanes reading different rows hit different banks)
+        extern __shared__ __align__(16) unsigned char s_tab[];
+        unsigned char* s_warp = s_tab + (size_t)(threadIdx.x / WARP) * ND * TAB_SPAN * TAB_ROWB;
+        const int lane = threadIdx.x & (WARP - 1);
         for (int b = b0; b < b1; ++b) {
             const int s = tab_start[b];
             if (s >= whi) break;
-            if (s >= ke) continue;
             const TabMat* M = mats + tab_mi[b];
             const int m = M->m, L = 2 * m;
-            if (ke >= s + m) {
-                // ---- whole sub-block from the tables
+            const bool act = ke >= s + m;               // this lane takes the sub-block whole
+            if (!__any_sync(0xffffffffu, act)) continue;
+            {
+                // ---- whole sub-block from the tables (lanes with act = false compute along and
+                // drop the result: the staging below is a warp-wide operation)
                 const double h = 0.5 * (double)m;
                 const double thc = phase_turns(pc, ld_basis(P.basis + s + M->node[TAB_PH / 2]));
                 double v_[TAB_PH];
@@ -1286,19 +1295,52 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
                 }
                 const double kc = (double)(s + m / 2);
                 const double2* row0 = tab + tab_off[b];
+                // Every lane's 13 taps x 128 B live within a few grid points of each other (the
+                // walkers' local times differ by less than the grid spacing times a few): the warp
+                // copies the union of the rows to shared memory with cp.async (one L2 round trip per
+                // sub-block instead of one per tap group), then each lane reads its taps from there.
+                double xs[ND];
+                int gs[ND], lo[ND];
+                bool staged[ND];
+                __syncwarp();                           // the previous sub-block's rows have been read
 #pragma unroll
                 for (int d = 0; d < ND; ++d) {
-                    const double tau = tau_hi[d] + tau_lo[d];
-                    const double nu = tq[0] / h + tau;                        // turns per bin
-                    const double x = (nu - floor(nu)) * (double)L;            // [0, L)
-                    const int g0 = (int)ceil(x - 0.5 * TAB_W);                // -6 .. L - 6
+                    const double nu = tq[0] / h + (tau_hi[d] + tau_lo[d]);    // turns per bin
+                    xs[d] = (nu - floor(nu)) * (double)L;                     // [0, L)
+                    const int g0 = (int)ceil(xs[d] - 0.5 * TAB_W);            // -6 .. L - 6
+                    gs[d] = g0 < 0 ? g0 + L : g0;
+                    xs[d] = 2.0 * (xs[d] - (double)g0) - (double)(TAB_W - 1); // v: the Horner variable
+                    int mn = act ? gs[d] : 0x7fffffff, mx = act ? gs[d] : -1;
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) {
+                        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                    }
+                    lo[d] = mn;
+                    const int span = mx - mn + TAB_W;
+                    staged[d] = span <= TAB_SPAN;
+                    if (staged[d]) {
+                        const double2* src = row0 + ((size_t)d * (L + TAB_W) + mn) * TAB_NM;
+                        const uint32_t dst = smem_u32(s_warp + (size_t)d * TAB_SPAN * TAB_ROWB);
+                        for (int pc16 = lane; pc16 < span * TAB_NM; pc16 += WARP) {
+                            const int r = pc16 / TAB_NM, c16 = pc16 % TAB_NM;
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                                         :: "r"(dst + (uint32_t)(r * TAB_ROWB + c16 * 16)), "l"(src + pc16) : "memory");
+                        }
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                bool waited = false;
+#pragma unroll
+                for (int d = 0; d < ND; ++d) {
                     double2 Mn[TAB_NM];
 #pragma unroll
                     for (int n = 0; n < TAB_NM; ++n) Mn[n] = make_double2(0.0, 0.0);
                     // rows are padded with TAB_W wrap-around points: the taps are contiguous
-                    const double2* rd = row0 + ((size_t)d * (L + TAB_W) + (g0 < 0 ? g0 + L : g0)) * TAB_NM;
+                    const double2* rd = row0 + ((size_t)d * (L + TAB_W) + gs[d]) * TAB_NM;
+                    const unsigned char* sd = s_warp + ((size_t)d * TAB_SPAN + (act ? gs[d] - lo[d] : 0)) * TAB_ROWB;
+                    const double v = xs[d];
                     // kernel weights: 13 independent Horner chains in v = 2 (x - g0) - (W - 1)
-                    const double v = 2.0 * (x - (double)g0) - (double)(TAB_W - 1);
                     // (the opaque zero keeps the compiler from hoisting all 208 coefficients into
                     //  registers across the detector / sub-block loops)
                     int opq = 0;
@@ -1314,15 +1356,35 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
 #pragma unroll
                             for (int i = 0; i < TAB_GROUP; ++i) wt[i] = fma(wt[i], v, cp[min(i0 + i, TAB_W - 1)][k]);
                         }
+                        if (!waited) {                   // the weights above overlapped the copies
+                            asm volatile("cp.async.wait_group 0;" ::: "memory");
+                            __syncwarp();
+                            waited = true;
+                        }
+                        if (staged[d]) {
 #pragma unroll
-                        for (int i = 0; i < TAB_GROUP; ++i) {
-                            if (i0 + i < TAB_W) {
-                                const double2* e = rd + (i0 + i) * TAB_NM;
+                            for (int i = 0; i < TAB_GROUP; ++i) {
+                                if (i0 + i < TAB_W) {
+                                    const double2* e = reinterpret_cast<const double2*>(sd + (i0 + i) * TAB_ROWB);
 #pragma unroll
-                                for (int n = 0; n < TAB_NM; ++n) {
-                                    const double2 q = __ldg(e + n);
-                                    Mn[n].x = fma(wt[i], q.x, Mn[n].x);
-                                    Mn[n].y = fma(wt[i], q.y, Mn[n].y);
+                                    for (int n = 0; n < TAB_NM; ++n) {
+                                        const double2 q = e[n];
+                                        Mn[n].x = fma(wt[i], q.x, Mn[n].x);
+                                        Mn[n].y = fma(wt[i], q.y, Mn[n].y);
+                                    }
+                                }
+                            }
+                        } else if (act) {                // lanes too far apart in time: straight from L2
+#pragma unroll
+                            for (int i = 0; i < TAB_GROUP; ++i) {
+                                if (i0 + i < TAB_W) {
+                                    const double2* e = rd + (i0 + i) * TAB_NM;
+#pragma unroll
+                                    for (int n = 0; n < TAB_NM; ++n) {
+                                        const double2 q = __ldg(e + n);
+                                        Mn[n].x = fma(wt[i], q.x, Mn[n].x);
+                                        Mn[n].y = fma(wt[i], q.y, Mn[n].y);
+                                    }
                                 }
                             }
                         }
@@ -1332,7 +1394,7 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
 #pragma unroll
                     for (int n = 2; n <= TAB_DEG; ++n) sum = cfma(en[n], Mn[n - 1], sum);
                     const double th0 = thc + fma(kc, tau_lo[d], frac1(kc * tau_hi[d]));
-                    acc[d] = cfma(sum, phasor_neg(th0), acc[d]);
+                    if (act) acc[d] = cfma(sum, phasor_neg(th0), acc[d]);
                 }
             }
         }
@@ -2281,7 +2343,14 @@ static void launch_main(gwin_plan* p, bool recur, bool calibrated, int W, int wp
 template <int ND>
 static void launch_table(gwin_plan* p, int W, int wpad, int n_chunks, int per_chunk, cudaStream_t st) {
     dim3 grid((W + CTA_THREADS - 1) / CTA_THREADS, n_chunks);
-    loglr_table_kernel<ND><<<grid, CTA_THREADS, 0, st>>>(p->d, W, wpad, per_chunk, p->n_tblk, p->d_tab_start, p->d_tab_mi,
+    const int smem = (CTA_THREADS / WARP) * ND * TAB_SPAN * TAB_ROWB;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(loglr_table_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(loglr_table_kernel<ND>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        attr_set = true;
+    }
+    loglr_table_kernel<ND><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, per_chunk, p->n_tblk, p->d_tab_start, p->d_tab_mi,
                                                         p->d_tab_off, p->d_tabmats, p->d_tab, p->d_wc, p->d_ke,
                                                         p->d_partialT);
 }
