@@ -120,7 +120,7 @@ struct BlockMat {
 #define TAB_W 13             // taps of the exponential-of-semicircle interpolation kernel
 #define TAB_BETA (2.30 * TAB_W)
 #ifndef TAB_MIN
-#define TAB_MIN 256          // shortest / longest sub-block [bins]; lengths are 2^k and 3 2^(k-1)
+#define TAB_MIN 128          // shortest / longest sub-block [bins]; lengths are 2^k and 3 2^(k-1)
 #endif
 #define TAB_MAX 4096
 #define TAB_RHO 0.025        // bound on |R| at the sub-block edge [rad]: truncation error ~ rho^5/120
@@ -2438,7 +2438,8 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
     int n_chunks3 = 0, per_chunk3 = 1;
     const int n_blk3 = table ? p->n_blk - p->n_blk_low : 0;
     if (n_blk3 > 0) {
-        per_chunk3 = std::max(2, TAB_MAX / MAX_BLOCK);
+        static const int tail_blocks = getenv("GWIN_TAIL_BLOCKS") ? atoi(getenv("GWIN_TAIL_BLOCKS")) : TAB_MAX / MAX_BLOCK / 2;
+        per_chunk3 = std::max(2, tail_blocks);
         n_chunks3 = (n_blk3 + per_chunk3 - 1) / per_chunk3;
     }
     int rc = ensure_workspace(p, W, std::max(n_chunks + n_chunks3, 1));

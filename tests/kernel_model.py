@@ -375,7 +375,7 @@ class PlanModel(object):
     # is e^{-2 pi i th0} sum_n c_n M_n(nu) with the M_n interpolated by a TAB_W-tap
     # exponential-of-semicircle kernel and c_n the Taylor coefficients of e^{-2 pi i R(j)},
     # R = the quadratic..sextic part of the polynomial through TAB_PH + 1 exact phase samples.
-    TAB_DEG, TAB_W, TAB_MIN, TAB_MAX, TAB_RHO, TAB_PH = 8, 13, 256, 4096, 0.025, 6
+    TAB_DEG, TAB_W, TAB_MIN, TAB_MAX, TAB_RHO, TAB_PH = 8, 13, 128, 4096, 0.025, 6
 
     @classmethod
     def table_nodes(cls, m):
