@@ -223,10 +223,13 @@ def run_cuda(args):
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    stdout_fd = None
     if world > 1:
-        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION: stdout carries the one JSON line only
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL writes its version banner to file descriptor 1 when the communicator comes up;
+        # stdout carries the one JSON line only, so fd 1 points at stderr until that line is printed
+        sys.stdout.flush()
+        stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     n_f = int(SEGLEN * SRATE) // 2 + 1
@@ -391,7 +394,11 @@ def run_cuda(args):
             lr_c = co.batch_loglr(P_host[:8], nthreads=min(8, threads))[0]
             lr_g = plan.loglr_host(P_host[:8])[0]
             line["parity_spot_max_abs_dloglr"] = float(np.max(np.abs(lr_c - lr_g)))
+        if stdout_fd is not None:
+            sys.stdout.flush()
+            os.dup2(stdout_fd, 1)
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

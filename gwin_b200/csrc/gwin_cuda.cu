@@ -173,6 +173,7 @@ struct gwin_plan {
     std::vector<TabMat> tabmats;
     int n_tblk, k_split, n_blk_low;
     bool tab_dirty;
+    bool tab_worth;          // AUTO uses the tables only where they pay (long sub-blocks, enough of them)
     int *d_tab_start, *d_tab_mi, *d_ke_low, *d_ks_tail;
     int64_t* d_tab_off;
     TabMat* d_tabmats;
@@ -1960,6 +1961,10 @@ static int build_tables(gwin_plan* p) {
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     p->n_tblk = n; p->k_split = k_split; p->n_blk_low = ib;
+    // a sub-block costs about as much as 90 bins of the recurrence kernel, and the table path adds
+    // two launches: short segments (8 s and below at 4 kHz) are better off without it
+    const int64_t tab_bins = (int64_t)p->tab_start[n] - k_split;
+    p->tab_worth = tab_bins >= 16384 && tab_bins >= (int64_t)350 * n;
     return GWIN_OK;
 }
 
@@ -2412,7 +2417,7 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
     bool table = !calib && (p->kernel == GWIN_KERNEL_TABLE || (p->kernel == GWIN_KERNEL_AUTO && table_default));
     if (table) {
         if (p->tab_dirty) { int rc = build_tables(p); if (rc) return rc; }
-        table = p->n_tblk > 0;
+        table = p->n_tblk > 0 && (p->kernel == GWIN_KERNEL_TABLE || p->tab_worth);
     }
     const int n_blk = table ? p->n_blk_low : p->n_blk;
 
