@@ -8,19 +8,24 @@
 //   <h|h> = h.inner(h).real                    gaussian_noise.py:340
 //   loglr combine                              gaussian_noise.py:341-350
 //   marginalised-phase combine                 marginalized_gaussian_noise.py:456-511
+//   distance(-phase) marginalisation           marginalized_gaussian_noise.py:431-448
+//   calibration of the template                calibration.py:142-173
 // No intermediate waveform array is ever materialised: one thread owns one
 // walker, a warp shares (broadcast) reads of the pre-weighted data table, and the
 // frequency axis is cut into chunks so that the grid fills all 148 SMs.
 //
 // Kernels per batch:  sort_key -> [CUB radix sort of walkers by their last
 // frequency bin, so that the lanes of a warp finish together] -> walker_setup ->
-// loglr_recur (production) | loglr_direct (independent second implementation) ->
-// combine.
+// loglr_recur over [band0, k_split) -> loglr_recur over every walker's last sub-block ->
+// loglr_table over the sub-blocks above k_split -> combine (-> marg_dist).
+// loglr_direct is an independent second implementation; short segments and calibrated
+// batches run loglr_recur over the whole band.
 //
-// Work is FP64-pipe bound -- more precisely bound by the register-file bandwidth that
-// feeds the FP64 pipe: there is no dense contraction here, so no
-// tensor cores; the tables are L2-resident, staged into shared memory per warp by
-// TMA bulk copies and read with warp-uniform 128-bit loads.
+// The recurrence kernel is FP64-pipe bound -- more precisely bound by the register-file
+// bandwidth that feeds the FP64 pipe: there is no dense contraction here,
+// so no tensor cores; its tables are L2-resident, staged into shared memory per warp by
+// TMA bulk copies and read with warp-uniform 128-bit loads.  The table kernel (DESIGN.md
+// 4.6) replaces the per-bin work above ~100 Hz by interpolation in per-plan moment tables.
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
 
