@@ -1955,7 +1955,13 @@ static int build_tables(gwin_plan* p) {
     CK(cudaMalloc(&p->d_tab_off, sizeof(int64_t) * n));
     CK(cudaMalloc(&p->d_tabmats, sizeof(TabMat) * p->tabmats.size()));
     CK(cudaMalloc(&p->d_invhat, sizeof(double) * invhat.size()));
-    CK(cudaMalloc(&p->d_tab, sizeof(double2) * (size_t)off));
+    if (cudaMalloc(&p->d_tab, sizeof(double2) * (size_t)off) != cudaSuccess) {
+        // not enough device memory for the tables: the recurrence kernel keeps the whole band
+        cudaGetLastError();
+        p->d_tab = nullptr;
+        free_tables(p);
+        return GWIN_OK;
+    }
     CK(cudaMemcpy(p->d_tab_start, p->tab_start.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(p->d_tab_mi, p->tab_mi.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(p->d_tab_off, p->tab_off.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice));
