@@ -534,6 +534,47 @@ def test_four_detectors_and_large_batch():
     assert np.all(np.abs(c[0] - b[0][:77]) <= 1e-9 * np.maximum(1.0, np.abs(c[0])))
 
 
+@pytest.mark.parametrize("dets", [["H1"], ["H1", "L1", "V1", "K1"]])
+def test_table_kernel_detector_counts(dets):
+    """The moment-table kernel with 1 and 4 detectors (4 needs > 48 KB of dynamic shared memory
+    per CTA for the staged rows) on a 64 s segment, against the oracle."""
+    import gwin_oracle as O
+    inj = dict(util.BNS_INJ)
+    inj["tc"] = 60.0
+    cfg = util.Config("tabdet", 64, 4096., 20., dets, inj, seed=21)
+    model = cfg.cuda_model()
+    rng = np.random.default_rng(22)
+    P = util.draw_bns(rng, 40, cfg)
+    lr0, hd0, hh0 = O.batch_loglr(cfg.oracle(), P)
+    for kernel in (2, 3, 0):
+        model.plan.configure(kernel=kernel)
+        lr, hd, hh = model.plan.loglr_host(P)
+        _check(lr, hd, hh, lr0, hd0, hh0, "%d detectors k%d" % (len(dets), kernel))
+    assert model.plan.last_launches >= 6            # AUTO took the table path here
+
+
+def test_table_kernel_coalescence_times_anywhere_in_the_segment():
+    """Walkers whose coalescence times are spread over the whole segment -- including across its
+    wrap-around -- sit far apart in the moment tables: the warp cannot stage a common set of rows
+    and every lane reads its own (and taps wrap around the table row).  Same answers."""
+    cfg = util.c3(seglen=64)
+    model = cfg.cuda_model()
+    rng = np.random.default_rng(23)
+    P = util.draw_bns(rng, 96, cfg)
+    P[:, 10] = cfg.epoch + rng.uniform(0.0, 64.0, len(P))
+    P[:8, 10] = cfg.epoch + np.array([0.0, 1e-3, 63.999, 64.0, 0.01, 63.99, 32.0, 0.5])
+    out = {}
+    for kernel in (1, 2, 3):
+        model.plan.configure(kernel=kernel)
+        out[kernel] = model.plan.loglr_host(P)
+    for kernel in (2, 3):
+        assert np.all(np.abs(out[kernel][0] - out[1][0]) <= tol(out[1][0])), kernel
+        assert np.all(np.abs(out[kernel][1] - out[1][1]) <= np.maximum(2e-6, 2e-9 * np.abs(out[1][2]))), kernel
+    import gwin_oracle as O
+    lr0 = O.batch_loglr(cfg.oracle(), P[:12])[0]
+    assert np.all(np.abs(out[3][0][:12] - lr0) <= tol(lr0))
+
+
 def test_linearity_in_data(cfg2):
     """Size-independent property: <d|h> is linear in the data, <h|h> does not
     depend on it."""
