@@ -36,6 +36,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "../../include/gwin_b200.h"
@@ -1751,25 +1752,27 @@ static int upload_schedule(gwin_plan* p) {
 // |prod_i (j - x_i)| over the sub-block (the interpolation error factor).
 struct TabSize { int m; int node[TAB_PH + 1]; double omega; };
 static const std::vector<TabSize>& table_sizes() {
-    static std::vector<TabSize> sizes;
-    if (!sizes.empty()) return sizes;
-    for (int m = TAB_MIN; m <= TAB_MAX; m *= 2)
-        for (int v = 0; v < 2; ++v) {
-            TabSize S;
-            S.m = v ? m + m / 2 : m;
-            if (S.m > TAB_MAX) continue;
-            for (int i = 0; i <= TAB_PH; ++i)
-                S.node[i] = (int)lround((S.m - 1) * 0.5 * (1.0 - cos(G_PI * i / TAB_PH)));
-            S.node[TAB_PH / 2] = S.m / 2;
-            S.omega = 0.0;
-            for (int j = 0; j < S.m; ++j) {
-                double prod = 1.0;
-                for (int i = 0; i <= TAB_PH; ++i) prod *= (double)(j - S.node[i]);
-                S.omega = std::max(S.omega, std::fabs(prod));
+    static const std::vector<TabSize> sizes = [] {        // thread-safe one-time initialisation
+        std::vector<TabSize> v;
+        for (int m = TAB_MIN; m <= TAB_MAX; m *= 2)
+            for (int half = 0; half < 2; ++half) {
+                TabSize S;
+                S.m = half ? m + m / 2 : m;
+                if (S.m > TAB_MAX) continue;
+                for (int i = 0; i <= TAB_PH; ++i)
+                    S.node[i] = (int)lround((S.m - 1) * 0.5 * (1.0 - cos(G_PI * i / TAB_PH)));
+                S.node[TAB_PH / 2] = S.m / 2;
+                S.omega = 0.0;
+                for (int j = 0; j < S.m; ++j) {
+                    double prod = 1.0;
+                    for (int i = 0; i <= TAB_PH; ++i) prod *= (double)(j - S.node[i]);
+                    S.omega = std::max(S.omega, std::fabs(prod));
+                }
+                v.push_back(S);
             }
-            sizes.push_back(S);
-        }
-    std::sort(sizes.begin(), sizes.end(), [](const TabSize& a, const TabSize& b) { return a.m < b.m; });
+        std::sort(v.begin(), v.end(), [](const TabSize& a, const TabSize& b) { return a.m < b.m; });
+        return v;
+    }();
     return sizes;
 }
 
@@ -1920,6 +1923,8 @@ static int build_tables(gwin_plan* p) {
             // 1 / phi_hat(jc / L), phi_hat by midpoint quadrature of the kernel over its support
             // (depends on m only: computed once per process)
             static std::vector<double> hat_cache[32];
+            static std::mutex hat_mutex;
+            std::lock_guard<std::mutex> hat_lock(hat_mutex);
             std::vector<double>& hc = hat_cache[si];
             if (hc.empty()) {
                 const int nq = 2048, L = 2 * m;
@@ -2332,13 +2337,15 @@ static void launch_main(gwin_plan* p, bool recur, bool calibrated, int W, int wp
     const int smem = (int)(sizeof(double2) * NWARP * 2 * TileStream<ND>::TILE * ND
                            + sizeof(double) * (calibrated ? RC_ROWS_CAL(ND) : RC_ROWS(ND)) * CTA_THREADS
                            + sizeof(uint64_t) * NWARP * 2) + smem_pad;
-    static bool attr_set[2] = {false, false};           // one instantiation per (ND, CALIB): set once
-    if (recur && !attr_set[calibrated]) {
+    // function attributes belong to the device's context: once per (ND, CALIB) and device
+    static bool attr_set_dev[64][2] = {};
+    bool& attr_flag = attr_set_dev[p->device & 63][calibrated];
+    if (recur && !attr_flag) {
         if (calibrated)
             cudaFuncSetAttribute(loglr_recur_kernel<ND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         else
             cudaFuncSetAttribute(loglr_recur_kernel<ND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_set[calibrated] = true;
+        attr_flag = true;
     }
     if (recur && calibrated)
         loglr_recur_kernel<ND, true><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, per_chunk, n_blk, p->d_blk_start + blk_off,
@@ -2360,11 +2367,11 @@ template <int ND>
 static void launch_table(gwin_plan* p, int W, int wpad, int n_chunks, int per_chunk, cudaStream_t st) {
     dim3 grid((W + CTA_THREADS - 1) / CTA_THREADS, n_chunks);
     const int smem = (CTA_THREADS / WARP) * ND * TAB_SPAN * TAB_ROWB;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set_dev[64] = {};
+    if (!attr_set_dev[p->device & 63]) {
         cudaFuncSetAttribute(loglr_table_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(loglr_table_kernel<ND>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        attr_set = true;
+        attr_set_dev[p->device & 63] = true;
     }
     loglr_table_kernel<ND><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, per_chunk, p->n_tblk, p->d_tab_start, p->d_tab_mi,
                                                         p->d_tab_off, p->d_tabmats, p->d_tab, p->d_wc, p->d_ke,
