@@ -38,32 +38,24 @@ class RefPlan(PlanModel):
                 best = m
         return best
 
-    def ref_poly(self, b):
-        s, m = self.tab_start[b], self.tab_m[b]
-        h = m / 2.0
-        nodes = np.array(self.table_nodes(m))
-        ic = self.TAB_PH // 2
-        sn = (nodes - m // 2) / h
-        th = self.phase_turns(self.ref_walker, s + nodes)
-        keep = [i for i in range(len(nodes)) if i != ic]
-        V = np.array([[sn[i] ** k for k in range(1, self.TAB_PH + 1)] for i in keep])
-        return np.concatenate([[0.0], np.linalg.solve(V, (th - th[ic])[keep])])
-
     def build_tables_ref(self, ref_row):
+        """Tables of T[k] e^{-2 pi i N_ref(j)}, N_ref the EXACT non-linear phase of the reference
+        waveform on the sub-block (its value at the centre and an endpoint slope removed)."""
         self.ref_walker = self.walker(ref_row)
         self.build_table_schedule()
         w, beta, N = self.TAB_W, 2.30 * self.TAB_W, self.TAB_DEG
-        self.tab, self.qref, hat = [], [], {}
+        self.tab, self.nref_nodes, hat = [], [], {}
         for b, (s, m) in enumerate(zip(self.tab_start[:-1], self.tab_m)):
             L = 2 * m
             if m not in hat:
                 hat[m] = self.es_hat((np.arange(m) - m // 2) / float(L), w, beta)
             jc = np.arange(m) - m // 2
             sj = jc / (m / 2.0)
-            q = self.ref_poly(b)
-            q[1] = 0.0                                  # the linear part stays with the walker (nu)
-            self.qref.append(q)
-            base = np.exp(-2j * PI * np.polynomial.polynomial.polyval(sj, q))
+            th = self.phase_turns(self.ref_walker, s + np.arange(m))
+            nu_ref = (th[-1] - th[0]) / (m - 1)
+            nref = th - th[m // 2] - nu_ref * jc
+            self.nref_nodes.append(nref[np.array(self.table_nodes(m))])
+            base = np.exp(-2j * PI * nref)
             g = np.arange(L)
             rows = np.zeros((self.n_det, N + 1, L), dtype=complex)
             for d in range(self.n_det):
@@ -80,12 +72,13 @@ class RefPlan(PlanModel):
         ic = self.TAB_PH // 2
         sn = (nodes - m // 2) / h
         th = self.phase_turns(w, s + nodes)
+        v = (th - th[ic]) - self.nref_nodes[b]          # the walker's phase relative to the reference
         keep = [i for i in range(len(nodes)) if i != ic]
         V = np.array([[sn[i] ** k for k in range(1, self.TAB_PH + 1)] for i in keep])
-        t = np.concatenate([[0.0], np.linalg.solve(V, (th - th[ic])[keep])])
+        t = np.concatenate([[0.0], np.linalg.solve(V, v[keep])])
         th0 = th[ic] + (s + m // 2) * w['tau'][d]
         nu = t[1] / h + w['tau'][d]
-        u = -2j * PI * (t - self.qref[b])               # only the residual is expanded
+        u = -2j * PI * t
         u[1] = 0.0
         c = np.zeros(N + 1, dtype=complex)
         c[0] = 1.0
