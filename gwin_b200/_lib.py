@@ -35,7 +35,8 @@ KERNEL_AUTO, KERNEL_DIRECT, KERNEL_RECURRENCE, KERNEL_TABLE = 0, 1, 2, 3
 SYMBOLS = (
     "gwin_plan_create", "gwin_plan_destroy", "gwin_plan_cutoffs",
     "gwin_plan_lognl", "gwin_plan_configure", "gwin_plan_set_distance_marg",
-    "gwin_plan_set_calibration", "gwin_loglr_batch_calib",
+    "gwin_plan_set_calibration", "gwin_plan_set_reference",
+    "gwin_plan_table_violations", "gwin_loglr_batch_calib",
     "gwin_loglr_batch_calib_host", "gwin_generate_calib_host",
     "gwin_loglr_batch",
     "gwin_loglr_batch_host", "gwin_loglr_batch_strided",
@@ -125,6 +126,10 @@ def load():
         lib.gwin_plan_set_distance_marg.restype = C.c_int
         lib.gwin_plan_set_distance_marg.argtypes = [C.c_void_p, C.c_int64,
                                                     C.c_void_p, C.c_void_p]
+        lib.gwin_plan_set_reference.restype = C.c_int
+        lib.gwin_plan_set_reference.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
+        lib.gwin_plan_table_violations.restype = C.c_int
+        lib.gwin_plan_table_violations.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         lib.gwin_plan_set_calibration.restype = C.c_int
         lib.gwin_plan_set_calibration.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         lib.gwin_loglr_batch_calib.restype = C.c_int
@@ -270,6 +275,21 @@ class Plan(object):
             raise ValueError("dist and weight must be 1-D arrays of one length")
         check(self._lib.gwin_plan_set_distance_marg(
             self._h, dist.size, dist.ctypes.data, weight.ctypes.data))
+
+    def set_reference(self, params=None, rel_width=0.0):
+        """Reference point [13] and relative width of the batches to come for the moment tables
+        (``gwin_plan_set_reference``); ``None`` clears."""
+        if params is None:
+            check(self._lib.gwin_plan_set_reference(self._h, None, 0.0))
+            return
+        row = np.ascontiguousarray(params, dtype=np.float64).reshape(GWIN_NPARAM)
+        check(self._lib.gwin_plan_set_reference(self._h, row.ctypes.data, float(rel_width)))
+
+    def table_violations(self):
+        """True if a walker since the last call fell outside the table reference range."""
+        f = C.c_int()
+        check(self._lib.gwin_plan_table_violations(self._h, C.byref(f)))
+        return bool(f.value)
 
     def set_calibration(self, spline_freqs):
         """``spline_freqs`` [n_det, n_points]: ``CubicSpline.spline_points`` of

@@ -186,6 +186,12 @@ struct gwin_plan {
     double* d_invhat;
     double2* d_tab;
     double2* d_partialT; size_t partialT_cap;
+    // optional reference waveform of the tables (gwin_plan_set_reference)
+    bool ref_on;
+    double ref_params[GWIN_NPARAM];
+    double ref_width;
+    double *d_ref_params, *d_ref_wc, *d_tab_ref;
+    int *d_ref_k, *d_violation;
     // distance marginalisation grid (1/D_j, log w_j) and the per-walker (x, opt) hand-over
     int n_marg;
     double *d_marg_u, *d_marg_logw, *d_marg_opt;
@@ -1167,10 +1173,34 @@ loglr_recur_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_blk,
 // Walkers of a batch sit within a few grid cells of each other at these frequencies, so the
 // table rows they touch stay in L1/L2.
 // ---------------------------------------------------------------------------
+// Reference waveform for the tables (gwin_plan_set_reference): per sub-block the reference's phase
+// at the centre, an end-point slope nu_ref, and its non-linear part N_ref = Theta_ref - centre - nu_ref j
+// at the phase-polynomial nodes.  The tables then hold T e^{-2 pi i N_ref(j)} and the walkers fit and
+// expand their phase RELATIVE to the reference, so sub-blocks can be as long as the batch is narrow.
+#define TAB_REFN (TAB_PH + 3)        // per sub-block: th_centre, nu_ref, N_ref at the TAB_PH + 1 nodes
+__global__ void tab_ref_kernel(PlanDev P, int n_tblk, const int* __restrict__ tab_start,
+                               const int* __restrict__ tab_mi, const TabMat* __restrict__ mats,
+                               const double* __restrict__ ref_wc, double* __restrict__ tab_ref) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_tblk) return;
+    PhaseCoef pc;
+    load_phase_coef(pc, ref_wc, 1, 0);
+    const TabMat* M = mats + tab_mi[b];
+    const int s = tab_start[b], m = M->m;
+    const double thc = phase_turns(pc, ld_basis(P.basis + s + m / 2));
+    const double nu = (phase_turns(pc, ld_basis(P.basis + s + m - 1)) - phase_turns(pc, ld_basis(P.basis + s))) / (double)(m - 1);
+    double* out = tab_ref + (size_t)b * TAB_REFN;
+    out[0] = thc;
+    out[1] = nu;
+    for (int i = 0; i <= TAB_PH; ++i)
+        out[2 + i] = phase_turns(pc, ld_basis(P.basis + s + M->node[i])) - thc - nu * (double)(M->node[i] - m / 2);
+}
+
 __global__ void __launch_bounds__(256)
 tab_build_kernel(PlanDev P, const int* __restrict__ tab_start, const int* __restrict__ tab_mi,
                  const int64_t* __restrict__ tab_off, const TabMat* __restrict__ mats,
-                 const double* __restrict__ invhat, double2* __restrict__ tab) {
+                 const double* __restrict__ invhat, double2* __restrict__ tab,
+                 const double* __restrict__ ref_wc, const double* __restrict__ tab_ref) {
     const int b = blockIdx.y, d = blockIdx.z;
     const TabMat* M = mats + tab_mi[b];
     const int m = M->m, L = 2 * m;
@@ -1180,6 +1210,13 @@ tab_build_kernel(PlanDev P, const int* __restrict__ tab_start, const int* __rest
     const int s = tab_start[b];
     const double* ih = invhat + M->hat_off;
     const double ih2 = 2.0 / (double)m;
+    PhaseCoef pcr;
+    double ref_thc = 0.0, ref_nu = 0.0;
+    if (tab_ref) {
+        load_phase_coef(pcr, ref_wc, 1, 0);
+        ref_thc = tab_ref[(size_t)b * TAB_REFN];
+        ref_nu = tab_ref[(size_t)b * TAB_REFN + 1];
+    }
     double2 acc[TAB_DEG + 1];
 #pragma unroll
     for (int n = 0; n <= TAB_DEG; ++n) acc[n] = make_double2(0.0, 0.0);
@@ -1194,6 +1231,8 @@ tab_build_kernel(PlanDev P, const int* __restrict__ tab_start, const int* __rest
         double sn, cs;
         sincospi(-2.0 * (double)idx / (double)L, &sn, &cs);
         double2 u = cmul(Tk, make_double2(cs, sn));
+        if (tab_ref)            // bake e^{-2 pi i N_ref(j)}
+            u = cmul(u, phasor_neg(phase_turns(pcr, ld_basis(P.basis + k)) - ref_thc - ref_nu * (double)jc));
         const double w = ih[j];
         u.x *= w; u.y *= w;
         const double sc = (double)jc * ih2;
@@ -1225,7 +1264,8 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
                    const int64_t* __restrict__ tab_off, const TabMat* __restrict__ mats,
                    const double2* __restrict__ tab,
                    const double* __restrict__ wc, const int* __restrict__ ke_arr,
-                   double2* __restrict__ partial) {
+                   double2* __restrict__ partial,
+                   const double* __restrict__ tab_ref, int* __restrict__ violation) {
     const int t = blockIdx.x * CTA_THREADS + threadIdx.x;
     const int chunk = blockIdx.y;
     const int b0 = chunk * blocks_per_chunk;
@@ -1272,6 +1312,11 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
 #pragma unroll
                 for (int i = 0; i < TAB_PH; ++i)
                     v_[i] = phase_turns(pc, ld_basis(P.basis + s + M->node[i < TAB_PH / 2 ? i : i + 1])) - thc;
+                if (tab_ref) {                   // phase relative to the reference waveform's non-linear part
+#pragma unroll
+                    for (int i = 0; i < TAB_PH; ++i)
+                        v_[i] -= tab_ref[(size_t)b * TAB_REFN + 2 + (i < TAB_PH / 2 ? i : i + 1)];
+                }
                 double tq[TAB_PH];               // t_1..t_6: Theta - th_c = sum t_i (j/h)^i [turns]
 #pragma unroll
                 for (int i = 0; i < TAB_PH; ++i) {
@@ -1283,8 +1328,12 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
                 // Taylor coefficients e_n of exp(U), U = i sum_{k=2..6} w_k s^k, w_k = -2 pi t_k:
                 //   n e_n = sum_k k (i w_k) e_{n-k};  e_0 = 1, e_1 = 0 (nu carries the slope)
                 double kw[TAB_PH + 1];
+                double rho = 0.0;
 #pragma unroll
-                for (int k = 2; k <= TAB_PH; ++k) kw[k] = -G_TWOPI * (double)k * tq[k - 1];
+                for (int k = 2; k <= TAB_PH; ++k) { kw[k] = -G_TWOPI * (double)k * tq[k - 1]; rho += fabs(tq[k - 1]); }
+                // a walker outside the range the schedule was built for (only possible with a
+                // reference waveform): the truncated series would be wrong -- report it
+                if (tab_ref && act && G_TWOPI * rho > 2.0 * TAB_RHO) atomicOr(violation, 1);
                 double2 en[TAB_DEG + 1];
                 en[0] = make_double2(1.0, 0.0);
                 en[1] = make_double2(0.0, 0.0);
@@ -1882,9 +1931,9 @@ static TabMat make_tab_mat(const TabSize& S, int hat_off) {
 
 static void free_tables(gwin_plan* p) {
     cudaFree(p->d_tab_start); cudaFree(p->d_tab_mi); cudaFree(p->d_tab_off); cudaFree(p->d_tabmats);
-    cudaFree(p->d_invhat); cudaFree(p->d_tab);
+    cudaFree(p->d_invhat); cudaFree(p->d_tab); cudaFree(p->d_tab_ref);
     p->d_tab_start = p->d_tab_mi = nullptr; p->d_tab_off = nullptr; p->d_tabmats = nullptr;
-    p->d_invhat = nullptr; p->d_tab = nullptr;
+    p->d_invhat = nullptr; p->d_tab = nullptr; p->d_tab_ref = nullptr;
     p->n_tblk = 0;
 }
 
@@ -1897,7 +1946,11 @@ static int build_tables(gwin_plan* p) {
     p->tab_start.clear(); p->tab_mi.clear(); p->tab_off.clear(); p->tabmats.clear();
     p->k_split = d.kmax; p->n_blk_low = p->n_blk;
     p->tab_dirty = false;
-    const double chirp = 2.0 * (3.0 / 128.0) * pow(G_PI * p->mchirp_min * G_MTSUN, -5.0 / 3.0);
+    // with a reference waveform only the batch's deviation from it has to be expanded: the bounds
+    // apply to ref_width x the chirp (+30 % and 0.02 of slack for what does not scale with the
+    // chirp mass: mass ratio, spins, tides at the higher PN orders)
+    const double wfac = p->ref_on ? std::min(1.0, 1.3 * p->ref_width + 0.02) : 1.0;
+    const double chirp = wfac * 2.0 * (3.0 / 128.0) * pow(G_PI * p->mchirp_min * G_MTSUN, -5.0 / 3.0);
     const int band0 = std::max(std::max(d.kmin, d.istart), 1);
     const std::vector<TabSize>& sizes = table_sizes();
     int raw = band0;
@@ -1972,8 +2025,32 @@ static int build_tables(gwin_plan* p) {
     CK(cudaMemcpy(p->d_tab_off, p->tab_off.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(p->d_tabmats, p->tabmats.data(), sizeof(TabMat) * p->tabmats.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(p->d_invhat, invhat.data(), sizeof(double) * invhat.size(), cudaMemcpyHostToDevice));
+    if (!p->d_violation) {
+        CK(cudaMalloc(&p->d_violation, sizeof(int)));
+        CK(cudaMemset(p->d_violation, 0, sizeof(int)));
+    }
+    if (p->ref_on) {
+        // phase coefficients of the reference point (walker_setup on a one-walker batch), then its
+        // phase at every sub-block's centre / ends / nodes
+        const int nd = d.n_det;
+        if (!p->d_ref_params) {
+            CK(cudaMalloc(&p->d_ref_params, sizeof(double) * GWIN_NPARAM));
+            CK(cudaMalloc(&p->d_ref_wc, sizeof(double) * (NCOEF(GWIN_MAX_DET) + GWIN_MAX_DET)));
+            CK(cudaMalloc(&p->d_ref_k, sizeof(int) * 4));
+        }
+        CK(cudaMemcpy(p->d_ref_params, p->ref_params, sizeof(double) * GWIN_NPARAM, cudaMemcpyHostToDevice));
+        walker_setup_kernel<<<1, 32>>>(d, 1, 1, p->d_ref_params, GWIN_NPARAM, 1, nullptr, nullptr, p->d_ref_wc,
+                                       p->d_ref_k, p->d_ref_k + 1, p->d_ref_wc + NCOEF(nd), nullptr, 0, 0,
+                                       nullptr, 0, nullptr, nullptr, 0);
+        int ks_ref = 0;
+        CK(cudaMemcpy(&ks_ref, p->d_ref_k, sizeof(int), cudaMemcpyDeviceToHost));
+        if (ks_ref < 0) { free_tables(p); return fail(GWIN_EINVAL, "the table reference point has no waveform"); }
+        CK(cudaMalloc(&p->d_tab_ref, sizeof(double) * (size_t)n * TAB_REFN));
+        tab_ref_kernel<<<(n + 127) / 128, 128>>>(d, n, p->d_tab_start, p->d_tab_mi, p->d_tabmats, p->d_ref_wc, p->d_tab_ref);
+    }
     tab_build_kernel<<<dim3((2 * TAB_MAX + TAB_W + 255) / 256, n, d.n_det), 256>>>(d, p->d_tab_start, p->d_tab_mi, p->d_tab_off,
-                                                               p->d_tabmats, p->d_invhat, p->d_tab);
+                                                               p->d_tabmats, p->d_invhat, p->d_tab,
+                                                               p->d_ref_wc, p->d_tab_ref);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     p->n_tblk = n; p->k_split = k_split; p->n_blk_low = ib;
@@ -2115,6 +2192,7 @@ extern "C" void gwin_plan_destroy(gwin_plan* p) {
     cudaFree(p->d_marg_u); cudaFree(p->d_marg_logw); cudaFree(p->d_marg_opt);
     cudaFree(p->d_calM); cudaFree(p->d_Ccal); cudaFree(p->d_calib); cudaFreeHost(p->h_calib);
     free_tables(p); cudaFree(p->d_partialT); cudaFree(p->d_ke_low); cudaFree(p->d_ks_tail);
+    cudaFree(p->d_ref_params); cudaFree(p->d_ref_wc); cudaFree(p->d_ref_k); cudaFree(p->d_violation);
     cudaFree(p->d_params); cudaFree(p->d_out); cudaFree(p->d_skip);
     cudaFreeHost(p->h_params); cudaFreeHost(p->h_out); cudaFreeHost(p->h_skip);
     if (p->timing) { cudaEventDestroy(p->ev0); cudaEventDestroy(p->ev1); }
@@ -2260,6 +2338,33 @@ extern "C" int gwin_plan_configure(gwin_plan* p, int kernel, double phase_tol, d
     return GWIN_OK;
 }
 
+extern "C" int gwin_plan_set_reference(gwin_plan* p, const double* params, double rel_width) {
+    if (!p) return fail(GWIN_EINVAL, "plan is NULL");
+    if (!params || !(rel_width > 0.0)) {                 // clear
+        if (p->ref_on) { p->ref_on = false; p->tab_dirty = true; }
+        return GWIN_OK;
+    }
+    for (int i = 0; i < GWIN_NPARAM; ++i)
+        if (!std::isfinite(params[i])) return fail(GWIN_EINVAL, "reference parameter %d is not finite", i);
+    if (!(params[0] > 0.0) || !(params[1] > 0.0) || !(params[4] > 0.0))
+        return fail(GWIN_EINVAL, "reference masses and distance must be positive");
+    memcpy(p->ref_params, params, sizeof(double) * GWIN_NPARAM);
+    p->ref_width = rel_width;
+    p->ref_on = true;
+    p->tab_dirty = true;
+    return GWIN_OK;
+}
+
+extern "C" int gwin_plan_table_violations(gwin_plan* p, int* flag) {
+    if (!p || !flag) return fail(GWIN_EINVAL, "NULL argument");
+    *flag = 0;
+    if (!p->d_violation) return GWIN_OK;
+    CK(cudaSetDevice(p->device));
+    CK(cudaMemcpy(flag, p->d_violation, sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemset(p->d_violation, 0, sizeof(int)));
+    return GWIN_OK;
+}
+
 extern "C" int gwin_plan_last_launches(const gwin_plan* p) { return p ? p->last_launches : 0; }
 
 extern "C" int gwin_plan_kernel_timing(gwin_plan* p, int enable, double* mean_ms, int* n_launches) {
@@ -2375,7 +2480,7 @@ static void launch_table(gwin_plan* p, int W, int wpad, int n_chunks, int per_ch
     }
     loglr_table_kernel<ND><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, per_chunk, p->n_tblk, p->d_tab_start, p->d_tab_mi,
                                                         p->d_tab_off, p->d_tabmats, p->d_tab, p->d_wc, p->d_ke,
-                                                        p->d_partialT);
+                                                        p->d_partialT, p->d_tab_ref, p->d_violation);
 }
 
 extern "C" int gwin_loglr_batch(gwin_plan* p, int mode, int64_t W64,

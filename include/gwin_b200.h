@@ -92,6 +92,19 @@ int gwin_plan_lognl(const gwin_plan* plan, double* lognl_total, double* lognl_de
 int gwin_plan_configure(gwin_plan* plan, int kernel, double phase_tol, double mchirp_min);
 
 /*
+ * Optional reference waveform for the moment tables of GWIN_KERNEL_TABLE (no counterpart in the
+ * reference: a property of this implementation).  params: HOST [GWIN_NPARAM], a point near the
+ * middle of the batches to come; rel_width: bound on |(Mc/Mc_ref)^(-5/3) - 1| over those batches.
+ * The tables are rebuilt relative to the reference waveform's phase, so that only a walker's
+ * deviation from it is expanded per sub-block: the narrower the ensemble, the longer the sub-blocks
+ * (DESIGN.md 4.6/9).  A walker outside the range sets a flag instead of returning a wrong number:
+ * gwin_plan_table_violations reads and clears it (non-zero: re-evaluate that batch after a wider
+ * gwin_plan_set_reference, or after clearing the reference with params = NULL).
+ */
+int gwin_plan_set_reference(gwin_plan* plan, const double* params, double rel_width);
+int gwin_plan_table_violations(gwin_plan* plan, int* flag);
+
+/*
  * Distance-marginalisation grid == MarginalizedGaussianNoise._setup_prior
  * (marginalized_gaussian_noise.py:368-375): dist[n] = numpy.linspace(min, max, 10**4),
  * weight[n] = deltad * dist_prior[j] (the ``b`` of the reference's logsumexp; entries

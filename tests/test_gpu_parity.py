@@ -575,6 +575,52 @@ def test_table_kernel_coalescence_times_anywhere_in_the_segment():
     assert np.all(np.abs(out[3][0][:12] - lr0) <= tol(lr0))
 
 
+def test_table_reference_waveform():
+    """gwin_plan_set_reference: moment tables relative to a reference waveform.  A narrow batch
+    around the reference agrees with the direct kernel; a batch wider than declared is flagged,
+    not silently wrong; clearing the reference restores the plain tables."""
+    cfg = util.c3(seglen=64)
+    model = cfg.cuda_model()
+    plan = model.plan
+    rng = np.random.default_rng(41)
+    ref = util.inj_row(cfg)
+    P = util.draw_bns(rng, 200, cfg)
+    f = 1.0 + 0.004 * rng.uniform(-1, 1, len(P))          # chirp mass within +-0.4 %
+    P[:, 0], P[:, 1] = ref[0] * f, ref[1] * f * (1.0 + 0.01 * rng.uniform(-1, 1, len(P)))
+    plan.configure(kernel=1)
+    a = plan.loglr_host(P)
+    plan.configure(kernel=3)
+    plain = plan.loglr_host(P)
+    n_plain = plan.last_launches
+    plan.set_reference(ref, 0.02)
+    b = plan.loglr_host(P)
+    assert not plan.table_violations()
+    assert np.all(np.abs(b[0] - a[0]) <= tol(a[0]))
+    assert np.all(np.abs(b[1] - a[1]) <= np.maximum(2e-6, 2e-9 * np.abs(a[2])))
+    assert np.all(np.abs(plain[0] - a[0]) <= tol(a[0])) and plan.last_launches == n_plain
+    lr0 = _oracle_batch(cfg.oracle(), P[:6])[0]
+    assert np.all(np.abs(b[0][:6] - lr0) <= tol(lr0))
+    # a batch from the whole mass box: wider than declared, but the schedule's safety margins may
+    # still cover it -- either it is flagged or it is right
+    Pw = util.draw_bns(rng, 64, cfg)
+    w = plan.loglr_host(Pw)
+    flagged = plan.table_violations()
+    plan.configure(kernel=1)
+    d = plan.loglr_host(Pw)
+    assert flagged or np.all(np.abs(w[0] - d[0]) <= tol(d[0]))
+    # 30 % lighter systems are far outside: flagged, never silently wrong
+    Pf = P[:64].copy()
+    Pf[:, :2] *= 0.7
+    plan.configure(kernel=3)
+    plan.loglr_host(Pf)
+    assert plan.table_violations()
+    assert not plan.table_violations()              # reading clears the flag
+    plan.set_reference(None)
+    c = plan.loglr_host(Pw)
+    assert not plan.table_violations()
+    assert np.all(np.abs(c[0] - d[0]) <= tol(d[0]))
+
+
 def test_linearity_in_data(cfg2):
     """Size-independent property: <d|h> is linear in the data, <h|h> does not
     depend on it."""

@@ -31,6 +31,15 @@ if ncal:
     sf = np.tile(np.logspace(np.log10(cfg.f_lower), np.log10(2048.), ncal), (len(cfg.dets), 1))
     model.plan.set_calibration(sf)
     Cd = torch.tensor(rng.normal(0, 0.05, (W, len(cfg.dets) * 2 * ncal)), device="cuda")
+# REF=<rel_width>: narrow batch around the injection + reference waveform for the moment tables
+refw = float(os.environ.get("REF", "0"))
+if refw:
+    ref = util.inj_row(cfg)
+    f = 1.0 + 0.2 * refw * rng.uniform(-1, 1, W)
+    P[:, 0], P[:, 1] = ref[0] * f, ref[1] * f
+    Pd = torch.tensor(P, device="cuda")
+    if os.environ.get("REF_ON", "1") == "1":
+        model.plan.set_reference(ref, refw)
 res = {}
 for name in kernels:
     kid = {"direct": 1, "recurrence": 2, "table": 3}[name]
@@ -60,6 +69,8 @@ for name in kernels:
     evs = W / (ms * 1e-3)
     print("%-10s W=%d T=%d  %.3f ms/batch  %.3e evals/s  %.3e bin-evals/s  (x68 slots = %.1f%% of 1.861e13; x32 = %.1f%%)"
           % (name, W, seglen, ms, evs, evs * bins, 100 * evs * bins * 68 / 1.861e13, 100 * evs * bins * 32 / 1.861e13))
+if refw:
+    print("table reference width %g, violations: %s" % (refw, model.plan.table_violations()))
 names = list(res)
 for a in range(len(names)):
     for b in range(a + 1, len(names)):
