@@ -399,7 +399,10 @@ class PlanModel(object):
 
     def build_table_schedule(self):
         band0 = max(self.kmin, self.istart)
-        chirp = 2.0 * (3. / 128.) * (PI * self.mchirp_min * MTSUN) ** (-5. / 3)
+        # with a reference waveform (set_reference) the bounds apply to the batch's deviation from it
+        ref = getattr(self, "ref", None)
+        wfac = min(1.0, 1.3 * ref[1] + 0.02) if ref else 1.0
+        chirp = wfac * 2.0 * (3. / 128.) * (PI * self.mchirp_min * MTSUN) ** (-5. / 3)
         sizes = self.table_sizes()
         # worst |prod (j - x_i)| over the sub-block, per size (interpolation error factor)
         self._tab_omega = {}
@@ -459,10 +462,18 @@ class PlanModel(object):
         ph = cls.es_kernel(x, w, beta)
         return (ph[None, :] * np.cos(2 * np.pi * np.asarray(xi)[:, None] * x[None, :])).sum(axis=1) * (w / nq)
 
+    def set_reference(self, ref_row=None, rel_width=0.0):
+        """gwin_plan_set_reference: tables relative to the waveform of ``ref_row``; ``rel_width``
+        bounds |(Mc/Mc_ref)^(-5/3) - 1| over the batches to come."""
+        self.ref = (np.asarray(ref_row, dtype=float), float(rel_width)) if ref_row is not None else None
+
     def build_tables(self):
         self.build_table_schedule()
         w, beta, N = self.TAB_W, 2.30 * self.TAB_W, self.TAB_DEG
         self.tab = []
+        self.tab_nref = []
+        ref = getattr(self, "ref", None)
+        ref_w = self.walker(ref[0]) if ref else None
         hat = {}
         for b, (s, m) in enumerate(zip(self.tab_start[:-1], self.tab_m)):
             L = 2 * m
@@ -471,10 +482,16 @@ class PlanModel(object):
             jc = np.arange(m) - m // 2
             g = np.arange(L)
             rows = np.zeros((self.n_det, N + 1, L), dtype=complex)
+            base = 1.0
+            if ref_w is not None:
+                # tab_ref_kernel: the reference's exact phase minus its centre value and an end-point
+                # slope; the tables hold T e^{-2 pi i N_ref}
+                th = self.phase_turns(ref_w, s + np.arange(m))
+                nref = th - th[m // 2] - (th[-1] - th[0]) / (m - 1) * jc
+                self.tab_nref.append(nref[np.array(self.table_nodes(m))])
+                base = np.exp(-2j * PI * nref)
             for d in range(self.n_det):
-                seg = np.zeros(m, dtype=complex)
-                n_have = max(0, min(m, self.n_f - s))
-                seg[:n_have] = self.T[d, s:s + n_have]
+                seg = self.T[d, s:s + m] * base
                 for n in range(N + 1):
                     a = seg * (jc / (m / 2.0)) ** n / hat[m]
                     rows[d, n] = np.fft.fft(a, L) * np.exp(2j * np.pi * ((g * (m // 2)) % L) / L)
@@ -491,7 +508,11 @@ class PlanModel(object):
         th = self.phase_turns(w, s + nodes)
         keep = [i for i in range(len(nodes)) if i != ic]
         V = np.array([[sn[i] ** k for k in range(1, self.TAB_PH + 1)] for i in keep])
-        t = np.concatenate([[0.0], np.linalg.solve(V, (th - th[ic])[keep])])    # t_k s^k, t_0 = 0
+        v = th - th[ic]
+        if getattr(self, "ref", None):
+            v = v - self.tab_nref[b]                    # phase relative to the reference waveform
+        t = np.concatenate([[0.0], np.linalg.solve(V, v[keep])])    # t_k s^k, t_0 = 0
+        self.last_rho = TWOPI * float(np.sum(np.abs(t[2:])))
         th0 = th[ic] + (s + m // 2) * w['tau'][d]
         nu = t[1] / h + w['tau'][d]
         # Taylor coefficients of exp(U), U = -2 pi i sum_{k>=2} t_k s^k:  n e_n = sum_k k u_k e_{n-k}

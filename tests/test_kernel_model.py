@@ -119,3 +119,34 @@ def test_table_kernel_arithmetic():
         assert abs(a[0] - b[0]) < 1e-8 and np.max(np.abs(a[1] - b[1])) < 1e-8
         lr0 = orc.loglr(**dict(zip(util.PARAM_ORDER, row)))[0]
         assert abs(b[0] - lr0) <= util.tol(lr0)
+
+
+def test_table_reference_arithmetic():
+    """Moment tables relative to a reference waveform: longer sub-blocks, same answers for a
+    narrow batch, and |2 pi R| beyond twice TAB_RHO (what the kernel flags) for a walker far
+    outside the declared width."""
+    cfg = util.c3(seglen=32)
+    ref = util.inj_row(cfg)
+    plain = _plan(cfg, mchirp_min=1.0)
+    plain.build_tables()
+    pm = _plan(cfg, mchirp_min=1.0)
+    pm.set_reference(ref, 0.02)
+    pm.build_tables()
+    assert pm.k_split < plain.k_split and len(pm.tab_m) < len(plain.tab_m)
+    rng = np.random.default_rng(9)
+    for _ in range(2):
+        row = ref.copy()
+        row[:2] *= 1.0 + 0.004 * rng.uniform(-1, 1)
+        row[10] += rng.uniform(-0.05, 0.05)
+        a, b = pm.loglr_direct(row), pm.loglr_table(row)
+        assert abs(a[0] - b[0]) < 1e-8 and np.max(np.abs(a[1] - b[1])) < 1e-8
+        assert pm.last_rho <= 2.0 * pm.TAB_RHO
+    far = ref.copy()
+    far[:2] *= 0.7
+    pm.loglr_table(far)
+    worst = 0.0
+    w = pm.walker(far)
+    for b in range(len(pm.tab_m)):
+        pm.table_block(w, b, 0)
+        worst = max(worst, pm.last_rho)
+    assert worst > 2.0 * pm.TAB_RHO
