@@ -192,6 +192,9 @@ struct gwin_plan {
     double ref_width;
     double *d_ref_params, *d_ref_wc, *d_tab_ref;
     int *d_ref_k, *d_violation;
+    // automatic choice of the reference from the batches of the host entry points (GWIN_TABLE_AUTOREF=1)
+    bool ref_auto;               // the current reference was chosen automatically
+    double ref_mc_lo, ref_mc_hi; // chirp masses the current automatic reference covers
     // distance marginalisation grid (1/D_j, log w_j) and the per-walker (x, opt) hand-over
     int n_marg;
     double *d_marg_u, *d_marg_logw, *d_marg_opt;
@@ -2351,6 +2354,7 @@ extern "C" int gwin_plan_set_reference(gwin_plan* p, const double* params, doubl
     memcpy(p->ref_params, params, sizeof(double) * GWIN_NPARAM);
     p->ref_width = rel_width;
     p->ref_on = true;
+    p->ref_auto = false;
     p->tab_dirty = true;
     return GWIN_OK;
 }
@@ -2753,6 +2757,63 @@ static int loglr_batch_host_impl(gwin_plan* p, int mode, int64_t W,
             const double q = std::exp2(std::floor(4.0 * std::log2(mc_min)) / 4.0);
             if (q != p->mchirp_min) { p->mchirp_min = q; p->sched_dirty = true; }
         }
+        // Experimental (GWIN_TABLE_AUTOREF=1): reference waveform of the moment tables from the
+        // batch itself -- the walker nearest the geometric middle of the chirp-mass range, width from
+        // the range with 25 % of margin.  Re-chosen when a batch leaves the covered range or has
+        // shrunk fourfold; dropped when the ensemble is wide (nothing to gain) or a walker is flagged.
+        static const bool autoref = getenv("GWIN_TABLE_AUTOREF") && atoi(getenv("GWIN_TABLE_AUTOREF")) != 0;
+        if (autoref && !calib && mc_min < 1e300 && (!p->ref_on || p->ref_auto)) {
+            double mc5_max = 0.0;
+            for (int64_t i = 0; i < W; ++i) {
+                if (skip && skip[i]) continue;
+                const double m1 = params[i * stride_walker], m2 = params[i * stride_walker + stride_param];
+                if (!(m1 > 0.0) || !(m2 > 0.0) || !std::isfinite(m1 + m2)) continue;
+                const double pm = m1 * m2;
+                mc5_max = std::max(mc5_max, pm * pm * pm / (m1 + m2));
+            }
+            const double mc_lo = std::pow(mc5_min, 0.2), mc_hi = std::pow(mc5_max, 0.2);
+            const double mc_ref = std::sqrt(mc_lo * mc_hi);
+            const double dev = std::max(std::pow(mc_lo / mc_ref, -5.0 / 3.0) - 1.0, 1.0 - std::pow(mc_hi / mc_ref, -5.0 / 3.0));
+            const double want = 1.25 * dev + 1e-3;
+            if (want >= 0.5) {
+                if (p->ref_on) { p->ref_on = false; p->ref_auto = false; p->tab_dirty = true; }
+            } else {
+                const bool covered = p->ref_on && mc_lo >= p->ref_mc_lo && mc_hi <= p->ref_mc_hi;
+                if (!covered || want < 0.25 * p->ref_width) {
+                    int64_t best = -1;
+                    double best_d = 1e300;
+                    const double mc5_ref = std::pow(mc_ref, 5.0);
+                    for (int64_t i = 0; i < W; ++i) {
+                        if (skip && skip[i]) continue;
+                        bool ok = true;
+                        for (int q2 = 0; q2 < GWIN_NPARAM; ++q2) ok = ok && std::isfinite(params[i * stride_walker + q2 * stride_param]);
+                        const double m1 = params[i * stride_walker], m2 = params[i * stride_walker + stride_param];
+                        if (!ok || !(m1 > 0.0) || !(m2 > 0.0) || !(params[i * stride_walker + 4 * stride_param] > 0.0)) continue;
+                        const double pm = m1 * m2;
+                        const double dd = std::fabs(pm * pm * pm / (m1 + m2) - mc5_ref);
+                        if (dd < best_d) { best_d = dd; best = i; }
+                    }
+                    if (best >= 0) {
+                        double row[GWIN_NPARAM];
+                        for (int q2 = 0; q2 < GWIN_NPARAM; ++q2) row[q2] = params[best * stride_walker + q2 * stride_param];
+                        const double m1 = row[0], m2 = row[1];
+                        const double mc_row = std::pow(m1 * m2, 0.6) / std::pow(m1 + m2, 0.2);
+                        // the row is not exactly at mc_ref: widen by its offset
+                        const double off = std::fabs(std::pow(mc_row / mc_ref, -5.0 / 3.0) - 1.0);
+                        const double width = std::exp2(std::ceil(std::log2(want + 1.25 * off)));
+                        if (width < 0.5) {
+                            gwin_plan_set_reference(p, row, width);
+                            p->ref_auto = true;
+                            const double cov = width / 1.25 - off;      // covered relative deviation in Mc^(-5/3)
+                            p->ref_mc_lo = mc_row * std::pow(1.0 + cov, -0.6);
+                            p->ref_mc_hi = cov < 1.0 ? mc_row * std::pow(1.0 - cov, -0.6) : 1e300;
+                        } else if (p->ref_on) {
+                            p->ref_on = false; p->ref_auto = false; p->tab_dirty = true;
+                        }
+                    }
+                }
+            }
+        }
     }
     CK(cudaMemcpyAsync(p->d_params, p->h_params, sizeof(double) * GWIN_NPARAM * W, cudaMemcpyHostToDevice, st));
     if (calib) {
@@ -2779,7 +2840,22 @@ static int loglr_batch_host_impl(gwin_plan* p, int mode, int64_t W,
     CK(cudaMemcpyAsync(h_lr, d_lr, sizeof(double) * W, cudaMemcpyDeviceToHost, st));
     if (hd) CK(cudaMemcpyAsync(h_hd, d_hd, sizeof(double) * 2 * nd * W, cudaMemcpyDeviceToHost, st));
     if (hh) CK(cudaMemcpyAsync(h_hh, d_hh, sizeof(double) * nd * W, cudaMemcpyDeviceToHost, st));
+    int flagged = 0;
+    if (p->ref_on && p->ref_auto && p->d_violation)
+        CK(cudaMemcpyAsync(&flagged, p->d_violation, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (flagged) {
+        // the automatic reference did not cover this batch after all: drop it and evaluate again
+        CK(cudaMemset(p->d_violation, 0, sizeof(int)));
+        p->ref_on = false; p->ref_auto = false; p->tab_dirty = true;
+        p->ref_mc_lo = 1e300; p->ref_mc_hi = 0.0;
+        const bool keep = p->auto_mchirp;
+        p->auto_mchirp = false;                  // no new automatic reference for the repeat
+        const int rc2 = loglr_batch_host_impl(p, mode, W, params, stride_walker, stride_param,
+                                              calib, cstride_walker, cstride_value, skip, loglr, hd, hh);
+        p->auto_mchirp = keep;
+        return rc2;
+    }
     memcpy(loglr, h_lr, sizeof(double) * W);
     if (hd) memcpy(hd, h_hd, sizeof(double) * 2 * nd * W);
     if (hh) memcpy(hh, h_hh, sizeof(double) * nd * W);

@@ -621,6 +621,20 @@ def test_table_reference_waveform():
     assert np.all(np.abs(c[0] - d[0]) <= tol(d[0]))
 
 
+def test_automatic_table_reference_subprocess():
+    """GWIN_TABLE_AUTOREF=1 (experimental, read once per process): the host entry point picks the
+    reference waveform from the batches; a sequence of wide / narrowing / drifting batches stays
+    within tolerance of the direct kernel (tools/check_autoref.py)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GWIN_TABLE_AUTOREF="1")
+    res = subprocess.run([sys.executable, os.path.join(root, "tools", "check_autoref.py"), "64", "512"],
+                         env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "OK" in res.stdout
+
+
 def test_linearity_in_data(cfg2):
     """Size-independent property: <d|h> is linear in the data, <h|h> does not
     depend on it."""
