@@ -19,6 +19,7 @@ Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -34,6 +35,7 @@ UNIT = "evals/s"
 SEGLEN, SRATE, F_LOWER = 256, 4096.0, 20.0
 DETS = ["H1", "L1", "V1"]
 WALKERS = 16384
+MASS_BOX = (1.2, 1.6)                   # component masses of the walkers [Msun]
 W_ALG_SLOTS = 32 + 12 * len(DETS)      # FP64 issue slots per (walker, bin): SURVEY.md 8d
 TABLE_BYTES_PER_BIN = 16 * len(DETS) + 24
 MTSUN = 4.925491025543575903411922162094833998e-6
@@ -46,8 +48,8 @@ INJ = dict(mass1=1.4, mass2=1.4, spin1z=0.0, spin2z=0.0, distance=40.0,
 
 def draw_walkers(rng, W):
     P = np.zeros((W, 13))
-    P[:, 0] = rng.uniform(1.2, 1.6, W)
-    P[:, 1] = rng.uniform(1.2, 1.6, W)
+    P[:, 0] = rng.uniform(MASS_BOX[0], MASS_BOX[1], W)
+    P[:, 1] = rng.uniform(MASS_BOX[0], MASS_BOX[1], W)
     P[:, 2] = 0.0
     P[:, 3] = 0.0
     P[:, 4] = rng.uniform(10.0, 100.0, W)
@@ -202,7 +204,7 @@ def workload_config(walkers_per_step):
     return {"workload": "C3: TaylorF2 BNS loglr (GaussianNoise), 256 s @ 4096 Hz, 524289 bins, "
                         "H1+L1+V1, coloured Gaussian noise + 1.4+1.4 Msun injection",
             "walkers_per_gpu_per_step": walkers_per_step, "f_lower_hz": F_LOWER,
-            "mass_box_msun": [1.2, 1.6]}
+            "mass_box_msun": list(MASS_BOX)}
 
 
 # ---------------------------------------------------------------------------
@@ -249,6 +251,13 @@ def run_cuda(args):
                                  device=local)
     plan = model.plan
     plan.configure(kernel=_lib.KERNEL_AUTO, mchirp_min=1.0)   # mass box [1.2,1.6] => Mc >= 1.04
+    # moment tables relative to the waveform in the middle of the mass box, declared width = the box
+    # (DESIGN.md 4.6); a walker outside it would raise the violation flag checked after the warm-up
+    mc_lo, mc_hi = MASS_BOX[0] * 2 ** -0.2, MASS_BOX[1] * 2 ** -0.2
+    mc_ref = math.sqrt(mc_lo * mc_hi)
+    ref_width = 1.1 * max((mc_lo / mc_ref) ** (-5. / 3) - 1.0, 1.0 - (mc_hi / mc_ref) ** (-5. / 3))
+    ref_row = np.array([dict(INJ, mass1=mc_ref * 2 ** 0.2, mass2=mc_ref * 2 ** 0.2)[k] for k in PARAMS])
+    plan.set_reference(ref_row, ref_width)
     call = models.CallModel(model, "loglr", return_all_stats=False)
 
     W = args.walkers
@@ -280,6 +289,12 @@ def run_cuda(args):
     for _ in range(max(args.warmup, 3)):
         step()
     sync_all()
+    if plan.table_violations():             # never observed; the plain tables are always valid
+        plan.set_reference(None)
+        ref_width = None
+        for _ in range(3):
+            step()
+        sync_all()
     fp64_peak = _lib.fp64_peak(local)       # DFMA lane-ops/s, measured live on this GPU
     plan.kernel_timing(True)
 
@@ -354,6 +369,7 @@ def run_cuda(args):
                            kernel="loglr_recur_kernel (block-anchored phasor recurrence, TMA-staged tiles) below k_split and for "
                                   "each walker's last sub-block; loglr_table_kernel (per-plan moment tables + 13-tap NUFFT "
                                   "interpolation) above",
+                           table_reference_width=ref_width,
                            mean_bins_per_eval=float(bins.mean())),
             "clocks": clk,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": world * W * 13 * 8,
