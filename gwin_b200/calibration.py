@@ -44,14 +44,15 @@ class Recalibrate(object):
 
     @classmethod
     def from_config(cls, cp, ifo, section):
-        """Reference :78-101: ``<ifo>_model``, ``<ifo>_minimum_frequency`` ... in
-        ``section`` of a config parser."""
-        all_params = dict(cp.items(section))
-        params = {key[len(ifo) + 1:]: all_params[key]
-                  for key in all_params if ifo.lower() in key}
-        model = params.pop('model')
-        params['ifo_name'] = ifo.lower()
-        return all_models[model](**params)
+        """Reference :78-101.  ``section`` holds ``<ifo>_model = cubic_spline`` and the model's
+        constructor arguments as ``<ifo>_<argument>``; the model is built for that detector."""
+        tag = ifo.lower()
+        kwargs = {}
+        for key, value in cp.items(section):
+            if tag in key:
+                kwargs[key[len(ifo) + 1:]] = value
+        kind = kwargs.pop('model')
+        return all_models[kind](ifo_name=tag, **kwargs)
 
 
 class CubicSpline(Recalibrate):
@@ -61,16 +62,13 @@ class CubicSpline(Recalibrate):
     def __init__(self, minimum_frequency, maximum_frequency, n_points,
                  ifo_name):
         Recalibrate.__init__(self, ifo_name=ifo_name)
-        minimum_frequency = float(minimum_frequency)
-        maximum_frequency = float(maximum_frequency)
-        n_points = int(n_points)
-        if n_points < 4:
+        self.n_points = int(n_points)
+        if self.n_points < 4:
             raise ValueError(
                 'Use at least 4 spline points for calibration model')
-        self.n_points = n_points
-        self.spline_points = numpy.logspace(numpy.log10(minimum_frequency),
-                                            numpy.log10(maximum_frequency),
-                                            n_points)
+        # log-spaced nodes between the two frequencies (config values arrive as strings)
+        lo, hi = numpy.log10(float(minimum_frequency)), numpy.log10(float(maximum_frequency))
+        self.spline_points = numpy.logspace(lo, hi, self.n_points)
 
     def apply_calibration(self, strain):
         return self.map_to_adjust(strain)
