@@ -249,15 +249,7 @@ def run_cuda(args):
         data[d] = FrequencySeries(x, delta_f, 0.0)
     model = models.GaussianNoise(PARAMS, data, gen, F_LOWER, psds={d: psd for d in DETS},
                                  device=local)
-    plan = model.plan
-    plan.configure(kernel=_lib.KERNEL_AUTO, mchirp_min=1.0)   # mass box [1.2,1.6] => Mc >= 1.04
-    # moment tables relative to the waveform in the middle of the mass box, declared width = the box
-    # (DESIGN.md 4.6); a walker outside it would raise the violation flag checked after the warm-up
-    mc_lo, mc_hi = MASS_BOX[0] * 2 ** -0.2, MASS_BOX[1] * 2 ** -0.2
-    mc_ref = math.sqrt(mc_lo * mc_hi)
-    ref_width = 1.1 * max((mc_lo / mc_ref) ** (-5. / 3) - 1.0, 1.0 - (mc_hi / mc_ref) ** (-5. / 3))
-    ref_row = np.array([dict(INJ, mass1=mc_ref * 2 ** 0.2, mass2=mc_ref * 2 ** 0.2)[k] for k in PARAMS])
-    plan.set_reference(ref_row, ref_width)
+    plan = model.plan          # plain constructor, kernel AUTO: nothing about the workload is told to the plan
     call = models.CallModel(model, "loglr", return_all_stats=False)
 
     W = args.walkers
@@ -289,12 +281,7 @@ def run_cuda(args):
     for _ in range(max(args.warmup, 3)):
         step()
     sync_all()
-    if plan.table_violations():             # never observed; the plain tables are always valid
-        plan.set_reference(None)
-        ref_width = None
-        for _ in range(3):
-            step()
-        sync_all()
+    plan.slow_path_walkers()                # reset the count: the timed steps must not use the slow path
     fp64_peak = _lib.fp64_peak(local)       # DFMA lane-ops/s, measured live on this GPU
     plan.kernel_timing(True)
 
@@ -312,6 +299,8 @@ def run_cuda(args):
     total_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
     kern_ms, kern_n = plan.kernel_timing(False)
     launches = plan.last_launches * args.steps
+    n_slow = plan.slow_path_walkers()
+    tab_info = plan.table_info()
 
     # end to end through the plugin call with HOST buffers (CallModel.batch -> C ABI host
     # entry: pinned staging, H2D of the parameter rows, kernels, D2H of loglr/hd/hh)
@@ -369,7 +358,7 @@ def run_cuda(args):
                            kernel="loglr_recur_kernel (block-anchored phasor recurrence, TMA-staged tiles) below k_split and for "
                                   "each walker's last sub-block; loglr_table_kernel (per-plan moment tables + 13-tap NUFFT "
                                   "interpolation) above",
-                           table_reference_width=ref_width,
+                           moment_tables=tab_info, slow_path_walkers=n_slow,
                            mean_bins_per_eval=float(bins.mean())),
             "clocks": clk,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": world * W * 13 * 8,
@@ -406,10 +395,14 @@ def run_cuda(args):
                 "sample": "%d of the %d walkers of one step in %.1f s on %d host threads; "
                           "C port of the reference path (oracle/loglr_ref.c), not pycbc/lalsimulation"
                           % (n, W, dt, threads)}
-            # spot parity on the bench data itself
-            lr_c = co.batch_loglr(P_host[:8], nthreads=min(8, threads))[0]
-            lr_g = plan.loglr_host(P_host[:8])[0]
-            line["parity_spot_max_abs_dloglr"] = float(np.max(np.abs(lr_c - lr_g)))
+            # spot parity on the bench data itself: 256 walkers spanning the range of last bins
+            sel = np.argsort(bins)[np.linspace(0, W - 1, 256).astype(int)]
+            lr_c = co.batch_loglr(P_host[sel], nthreads=threads)[0]
+            lr_g = res.values[sel]
+            err = np.abs(lr_c - lr_g)
+            line["parity_spot"] = {"walkers": len(sel), "max_abs_dloglr": float(err.max()),
+                                   "max_over_tolerance": float(np.max(err / np.maximum(1e-6, 1e-9 * np.abs(lr_c)))),
+                                   "against": "C port of the reference path (float64)"}
         if stdout_fd is not None:
             sys.stdout.flush()
             os.dup2(stdout_fd, 1)

@@ -35,8 +35,8 @@ KERNEL_AUTO, KERNEL_DIRECT, KERNEL_RECURRENCE, KERNEL_TABLE = 0, 1, 2, 3
 SYMBOLS = (
     "gwin_plan_create", "gwin_plan_destroy", "gwin_plan_cutoffs",
     "gwin_plan_lognl", "gwin_plan_configure", "gwin_plan_set_distance_marg",
-    "gwin_plan_set_calibration", "gwin_plan_set_reference",
-    "gwin_plan_table_violations", "gwin_loglr_batch_calib",
+    "gwin_plan_set_calibration", "gwin_plan_cover_host", "gwin_plan_cover_device",
+    "gwin_plan_table_info", "gwin_plan_slow_path", "gwin_loglr_batch_calib",
     "gwin_loglr_batch_calib_host", "gwin_generate_calib_host",
     "gwin_loglr_batch",
     "gwin_loglr_batch_host", "gwin_loglr_batch_strided",
@@ -126,10 +126,16 @@ def load():
         lib.gwin_plan_set_distance_marg.restype = C.c_int
         lib.gwin_plan_set_distance_marg.argtypes = [C.c_void_p, C.c_int64,
                                                     C.c_void_p, C.c_void_p]
-        lib.gwin_plan_set_reference.restype = C.c_int
-        lib.gwin_plan_set_reference.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
-        lib.gwin_plan_table_violations.restype = C.c_int
-        lib.gwin_plan_table_violations.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        lib.gwin_plan_cover_host.restype = C.c_int
+        lib.gwin_plan_cover_host.argtypes = [C.c_void_p, C.c_int64, C.c_void_p,
+                                             C.c_int64, C.c_int64]
+        lib.gwin_plan_cover_device.restype = C.c_int
+        lib.gwin_plan_cover_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p,
+                                               C.c_int64, C.c_int64, C.c_void_p]
+        lib.gwin_plan_table_info.restype = C.c_int
+        lib.gwin_plan_table_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int64)] * 4
+        lib.gwin_plan_slow_path.restype = C.c_int
+        lib.gwin_plan_slow_path.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         lib.gwin_plan_set_calibration.restype = C.c_int
         lib.gwin_plan_set_calibration.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         lib.gwin_loglr_batch_calib.restype = C.c_int
@@ -276,20 +282,46 @@ class Plan(object):
         check(self._lib.gwin_plan_set_distance_marg(
             self._h, dist.size, dist.ctypes.data, weight.ctypes.data))
 
-    def set_reference(self, params=None, rel_width=0.0):
-        """Reference point [13] and relative width of the batches to come for the moment tables
-        (``gwin_plan_set_reference``); ``None`` clears."""
+    def cover(self, params=None, param_major=False, stream=None):
+        """Declare what the moment tables must cover (``gwin_plan_cover_host`` /
+        ``_device``): ``params`` is a [W, 13] host array or CUDA float64 tensor of
+        points spanning the batches to come (e.g. prior draws), [13, W] with
+        ``param_major``; ``None`` returns to automatic coverage."""
         if params is None:
-            check(self._lib.gwin_plan_set_reference(self._h, None, 0.0))
+            check(self._lib.gwin_plan_cover_host(self._h, 0, None, 0, 0))
             return
-        row = np.ascontiguousarray(params, dtype=np.float64).reshape(GWIN_NPARAM)
-        check(self._lib.gwin_plan_set_reference(self._h, row.ctypes.data, float(rel_width)))
+        if hasattr(params, "is_cuda"):
+            import torch
+            if not params.is_cuda or params.dtype != torch.float64:
+                raise ValueError("params must be a CUDA float64 tensor")
+            params = params.contiguous()
+            W = params.shape[1] if param_major else params.shape[0]
+            sw, si = (1, W) if param_major else (GWIN_NPARAM, 1)
+            if stream is None:
+                stream = torch.cuda.current_stream(params.device).cuda_stream
+            check(self._lib.gwin_plan_cover_device(self._h, W, params.data_ptr(),
+                                                   sw, si, stream))
+            return
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        if params.ndim != 2 or params.shape[1 - int(param_major)] != GWIN_NPARAM:
+            raise ValueError("params must be [W, %d]" % GWIN_NPARAM)
+        W = params.shape[1] if param_major else params.shape[0]
+        sw, si = (1, W) if param_major else (GWIN_NPARAM, 1)
+        check(self._lib.gwin_plan_cover_host(self._h, W, params.ctypes.data, sw, si))
 
-    def table_violations(self):
-        """True if a walker since the last call fell outside the table reference range."""
-        f = C.c_int()
-        check(self._lib.gwin_plan_table_violations(self._h, C.byref(f)))
-        return bool(f.value)
+    def table_info(self):
+        """dict(subblocks, references, bytes, k_split) of the current moment tables."""
+        v = [C.c_int64() for _ in range(4)]
+        check(self._lib.gwin_plan_table_info(self._h, *[C.byref(x) for x in v]))
+        return dict(zip(("subblocks", "references", "bytes", "k_split"),
+                        (x.value for x in v)))
+
+    def slow_path_walkers(self):
+        """Walkers evaluated by the slow path (outside the block schedule's or the
+        tables' coverage: right, but ~20x slower) since the last call."""
+        n = C.c_int64()
+        check(self._lib.gwin_plan_slow_path(self._h, C.byref(n)))
+        return n.value
 
     def set_calibration(self, spline_freqs):
         """``spline_freqs`` [n_det, n_points]: ``CubicSpline.spline_points`` of

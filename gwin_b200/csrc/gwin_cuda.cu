@@ -122,23 +122,47 @@ struct BlockMat {
 
 // Table kernel: sub-block moments of the data looked up by a type-2 NUFFT
 #define TAB_DEG 8            // degree of the Taylor polynomial of e^{-2 pi i R(j)}
-#define TAB_PH 6             // degree of the phase polynomial through TAB_PH + 1 exact samples
+#define TAB_NT 9             // Taylor orders of the phase kept per sub-block: s^0 .. s^8, s = j / (m/2)
+#define TAB_NTP 10           // ... padded to an even count (128-bit shared-memory reads)
+#define TAB_NTH 13           // orders the host-side bound of the schedule looks at
 #define TAB_W 13             // taps of the exponential-of-semicircle interpolation kernel
 #define TAB_BETA (2.30 * TAB_W)
 #ifndef TAB_MIN
 #define TAB_MIN 128          // shortest / longest sub-block [bins]; lengths are 2^k and 3 2^(k-1)
 #endif
+#ifndef TAB_MAX
 #define TAB_MAX 4096
-#define TAB_RHO 0.025        // bound on |R| at the sub-block edge [rad]: truncation error ~ rho^5/120
-#define TAB_NM TAB_DEG       // moments stored per grid point: n = 0, 2, 3, .. TAB_DEG (c_1 = 0: nu carries the slope)
-#define TAB_PDEG 15          // degree of the per-tap polynomial of the interpolation kernel in v = 2u, u in (-1/2, 1/2]
-__constant__ double c_tab_poly[TAB_W][TAB_PDEG + 1];
-struct TabMat {
-    double c[TAB_PH * TAB_PH];   // t_i = sum_j c[TAB_PH (i-1) + j] (th_{x_j} - th_centre), i = 1..TAB_PH, j over the off-centre nodes
-    int node[TAB_PH + 1];        // node offsets from the sub-block start; node[TAB_PH/2] = m/2 is the centre
-    int m;
-    int hat_off;                 // offset of this length's 1/phi_hat[j] in the invhat array
-    int pad[3];
+#endif
+#define TAB_NM TAB_DEG       // moments stored per grid point: n = 0, 2, 3, .. TAB_DEG (e_1 = 0: nu carries the slope)
+// truncation of e^{-2 pi i R}: the schedule is built so that the majorant of the dropped terms stays
+// below TAB_EST_DESIGN for every covered walker; a walker whose own estimate exceeds TAB_EST_MAX (or
+// whose |2 pi R| exceeds TAB_RHO_MAX) leaves the table path for the slow path (direct kernel)
+#define TAB_EST_DESIGN 2.0e-9
+#define TAB_EST_MAX 1.6e-8
+#define TAB_RHO_DESIGN 0.05
+#define TAB_RHO_MAX 0.10
+#define TAB_KEY_BITS 20      // walkers are ordered by their Newtonian chirp coefficient, quantised over the covered range
+#include "tab_poly.inc"      // TAB_TAP_i(v): the interpolation kernel's per-tap polynomials, literal coefficients
+
+// One sub-block of the table schedule.  Its K reference chirps sit at a_lo + (r + 1/2) da in the
+// Newtonian coefficient a0 (turns Hz^(5/3)); tables of reference r and detector d start at
+// off + ((r n_det + d) (2 m + TAB_W)) TAB_NM double2.
+struct TabBlk {
+    int start, m;
+    int K, pair0;            // pair0: index of (this sub-block, reference 0) in the per-pair arrays
+    double a_lo, da, inv_da;
+    double eps;              // (m/2) / centre bin
+    long long off;
+    long long pad;
+};
+
+// What the tables are built for (gwin_plan_cover_*): the range of the Newtonian coefficient and, for
+// every other phase coefficient, the largest deviation of a walker from the equal-mass, non-spinning,
+// point-particle reference chirp of the same a0.
+struct Cover {
+    bool valid;
+    double a_lo, a_hi;
+    double dev[16];
 };
 
 struct gwin_plan {
@@ -173,28 +197,29 @@ struct gwin_plan {
     std::vector<double> w73;
     double *d_calM, *d_Ccal;
     double *h_calib, *d_calib; size_t calib_cap;
-    // table kernel: sub-block schedule above k_split, moment tables
-    std::vector<int> tab_start, tab_mi;
-    std::vector<int64_t> tab_off;
-    std::vector<TabMat> tabmats;
-    int n_tblk, k_split, n_blk_low;
+    // table kernel: sub-block schedule above k_split, reference chirps, moment tables
+    Cover cover;             // what the current tables cover
+    Cover want;              // what the next build should cover (gwin_plan_cover_*, automatic re-planning)
+    bool cover_manual;       // coverage was declared by the caller: no automatic re-planning
+    std::vector<TabBlk> tblk;
+    int n_tblk, n_pairs, k_split, n_blk_low, k_tab_end;
+    size_t tab_bytes;
     bool tab_dirty;
     bool tab_worth;          // AUTO uses the tables only where they pay (long sub-blocks, enough of them)
-    int *d_tab_start, *d_tab_mi, *d_ke_low, *d_ks_tail;
-    int64_t* d_tab_off;
-    TabMat* d_tabmats;
-    double* d_invhat;
+    TabBlk* d_tblk;
+    double *d_cmat, *d_tref, *d_invhat;
     double2* d_tab;
     double2* d_partialT; size_t partialT_cap;
-    // optional reference waveform of the tables (gwin_plan_set_reference)
-    bool ref_on;
-    double ref_params[GWIN_NPARAM];
-    double ref_width;
-    double *d_ref_params, *d_ref_wc, *d_tab_ref;
-    int *d_ref_k, *d_violation;
-    // automatic choice of the reference from the batches of the host entry points (GWIN_TABLE_AUTOREF=1)
-    bool ref_auto;               // the current reference was chosen automatically
-    double ref_mc_lo, ref_mc_hi; // chirp masses the current automatic reference covers
+    // walker order bookkeeping of the table path
+    int *d_ke_fast, *d_ke_low, *d_ks_tail, *d_key2_in, *d_key2_out, *d_idx2_in, *d_perm_e, *d_grp_b;
+    // slow path: walkers the fast kernels cannot take (outside the schedule / the tables' coverage)
+    unsigned char* d_slow;
+    int *d_slow_list, *d_slow_n;         // d_slow_n[0]: this batch, [1]: since the last query
+    double2* d_partialS; size_t partialS_cap;
+    unsigned long long* d_stats;         // cover_stats_kernel output
+    bool replan;                         // re-measure the coverage on the next batch
+    // ordering of calls that arrive on different streams (they share the workspace)
+    cudaEvent_t ev_done; bool ev_done_set; cudaStream_t last_stream;
     // distance marginalisation grid (1/D_j, log w_j) and the per-walker (x, opt) hand-over
     int n_marg;
     double *d_marg_u, *d_marg_logw, *d_marg_opt;
@@ -334,6 +359,99 @@ __device__ __forceinline__ double phase_turns(const PhaseCoef& c, double4 b) {
     return lo + hi;
 }
 
+// TaylorF2 phase coefficients of one walker (lalsimulation XLALSimInspiralPNPhasing_F2, 3.5PN with
+// aligned spins, plus the 5PN/6PN tidal terms), folded with powers of (pi M)^(1/3) so that
+//   Psi(f) [turns] = a0 x^-5 + a2 x^-3 + a3 x^-2 + a4 x^-1 + a5 + b5 ln x + a6 x + b6 x ln x + a7 x^2
+//                    + a10 x^5 + a12 x^7,   x = f^(1/3)
+// out[] in the order of the C_A* rows.  Returns (pi M)^(1/3).
+__host__ __device__ inline double pn_phase_coefs(double m1, double m2, double chi1, double chi2, double phic,
+                                                 double lam1, double lam2, double* out) {
+    const double mtot = m1 + m2;
+    const double dm = (m1 - m2) / (m1 + m2);
+    const double eta = m1 * m2 / mtot / mtot;
+    const double m1M = m1 / mtot, m2M = m2 / mtot;
+    const double pfaN = 3.0 / (128.0 * eta);
+    double v2 = 5.0 * (743.0 / 84.0 + 11.0 * eta) / 9.0;
+    double v3 = -16.0 * G_PI;
+    double v4 = 5.0 * (3058.673 / 7.056 + 5429.0 / 7.0 * eta + 617.0 * eta * eta) / 72.0;
+    double v5 = 5.0 / 9.0 * (7729.0 / 84.0 - 13.0 * eta) * G_PI;
+    double vl5 = 5.0 / 3.0 * (7729.0 / 84.0 - 13.0 * eta) * G_PI;
+    double v6 = (11583.231236531 / 4.694215680 - 640.0 / 3.0 * G_PI * G_PI - 6848.0 / 21.0 * G_GAMMA)
+              + eta * (-15737.765635 / 3.048192 + 2255.0 / 12.0 * G_PI * G_PI)
+              + eta * eta * 76055.0 / 1728.0 - eta * eta * eta * 127825.0 / 1296.0;
+    v6 += (-6848.0 / 21.0) * 1.3862943611198906188;   // log(4)
+    const double vl6 = -6848.0 / 21.0;
+    double v7 = G_PI * (77096675.0 / 254016.0 + 378515.0 / 1512.0 * eta - 74045.0 / 756.0 * eta * eta);
+    {
+        const double chi1sq = chi1 * chi1, chi2sq = chi2 * chi2;
+        const double SL = m1M * m1M * chi1 + m2M * m2M * chi2;
+        const double dSigmaL = dm * (m2M * chi2 - m1M * chi1);
+        double pn_sigma = eta * (721.0 / 48.0 * chi1 * chi2 - 247.0 / 48.0 * chi1 * chi2);
+        pn_sigma += (720.0 - 1.0) / 96.0 * m1M * m1M * chi1 * chi1;
+        pn_sigma += (720.0 - 1.0) / 96.0 * m2M * m2M * chi2 * chi2;
+        pn_sigma -= (240.0 - 7.0) / 96.0 * m1M * m1M * chi1sq;
+        pn_sigma -= (240.0 - 7.0) / 96.0 * m2M * m2M * chi2sq;
+        double pn_ss3 = (326.75 / 1.12 + 557.5 / 1.8 * eta) * eta * chi1 * chi2;
+        pn_ss3 += ((4703.5 / 8.4 + 2935.0 / 6.0 * m1M - 120.0 * m1M * m1M)
+                   + (-4108.25 / 6.72 - 108.5 / 1.2 * m1M + 125.5 / 3.6 * m1M * m1M)) * m1M * m1M * chi1sq;
+        pn_ss3 += ((4703.5 / 8.4 + 2935.0 / 6.0 * m2M - 120.0 * m2M * m2M)
+                   + (-4108.25 / 6.72 - 108.5 / 1.2 * m2M + 125.5 / 3.6 * m2M * m2M)) * m2M * m2M * chi2sq;
+        const double pn_gamma = (554345.0 / 1134.0 + 110.0 * eta / 9.0) * SL
+                              + (13915.0 / 84.0 - 10.0 * eta / 3.0) * dSigmaL;
+        v7 += (-8980424995.0 / 762048.0 + 6586595.0 * eta / 756.0 - 305.0 * eta * eta / 36.0) * SL
+            - (170978035.0 / 48384.0 - 2876425.0 * eta / 672.0 - 4735.0 * eta * eta / 144.0) * dSigmaL;
+        v6 += G_PI * (3760.0 * SL + 1490.0 * dSigmaL) / 3.0 + pn_ss3;
+        v5 += -1.0 * pn_gamma;
+        vl5 += -3.0 * pn_gamma;
+        v4 += -10.0 * pn_sigma;
+        v3 += 188.0 * SL / 3.0 + 25.0 * dSigmaL;
+    }
+    // fold v = (pi M f)^(1/3) = m3 * x,  x = f^(1/3), into coefficients [turns]
+    const double m_sec = mtot * G_MTSUN;
+    const double piM = G_PI * m_sec;
+    const double m3 = cbrt(piM);
+    const double lm3 = log(m3);
+    const double s = pfaN / G_TWOPI;
+    const double im3 = 1.0 / m3;
+    const double im3_2 = im3 * im3, im3_3 = im3_2 * im3, im3_5 = im3_3 * im3_2;
+    out[C_A0] = s * im3_5;
+    out[C_A2] = s * v2 * im3_3;
+    out[C_A3] = s * v3 * im3_2;
+    out[C_A4] = s * v4 * im3;
+    // constant term also absorbs -2 phi_c - pi/4
+    out[C_A5] = s * (v5 + vl5 * lm3) - (2.0 * phic + 0.25 * G_PI) / G_TWOPI;
+    out[C_B5] = s * vl5;
+    out[C_A6] = s * (v6 + vl6 * lm3) * m3;
+    out[C_B6] = s * vl6 * m3;
+    out[C_A7] = s * v7 * m3 * m3;
+    {   // tidal terms (lalsimulation TaylorF2Phasing_10PN/12PNTidalCoeff): pfaN (pft10 v^10 + pft12 v^12) / v^5
+        const double m1M4 = m1M * m1M * m1M * m1M, m2M4 = m2M * m2M * m2M * m2M;
+        const double pft10 = lam1 * (-288.0 + 264.0 * m1M) * m1M4 + lam2 * (-288.0 + 264.0 * m2M) * m2M4;
+        const double pft12 = lam1 * (-15895.0 / 28.0 + 4595.0 / 28.0 * m1M + 5715.0 / 14.0 * m1M * m1M
+                                     - 325.0 / 7.0 * m1M * m1M * m1M) * m1M4
+                           + lam2 * (-15895.0 / 28.0 + 4595.0 / 28.0 * m2M + 5715.0 / 14.0 * m2M * m2M
+                                     - 325.0 / 7.0 * m2M * m2M * m2M) * m2M4;
+        const double m3_2 = m3 * m3, m3_5 = m3_2 * m3_2 * m3;
+        out[C_A10] = s * pft10 * m3_5;
+        out[C_A12] = s * pft12 * m3_5 * m3_2;
+    }
+    return m3;
+}
+// The reference chirp of Newtonian coefficient a0: equal masses, no spins, no tides.
+__host__ __device__ inline void ref_phase_coefs(double a0, double* out) {
+    // a0 = 3 / (128 eta 2 pi) (pi M)^(-5/3) with eta = 1/4
+    const double piM = pow(a0 * (64.0 * G_PI / 3.0), -0.6);
+    const double m = 0.5 * piM / (G_PI * G_MTSUN);
+    pn_phase_coefs(m, m, 0.0, 0.0, 0.0, 0.0, 0.0, out);
+}
+// a0 from the masses alone (one cbrt): (3 / 256 pi) (pi Mc)^(-5/3), Mc^5 = (m1 m2)^3 / (m1 + m2)
+__host__ __device__ inline double newtonian_coef(double m1, double m2) {
+    const double pm = m1 * m2;
+    const double mc5 = pm * pm * pm / (m1 + m2);
+    const double pim = G_PI * G_MTSUN;
+    return 3.0 / (256.0 * G_PI) / (cbrt(mc5) * pim * cbrt(pim * pim));
+}
+
 __device__ __forceinline__ void load_phase_coef(PhaseCoef& c, const double* wc, int wpad, int w) {
     c.a0 = wc[C_A0 * wpad + w]; c.a2 = wc[C_A2 * wpad + w]; c.a3 = wc[C_A3 * wpad + w];
     c.a4 = wc[C_A4 * wpad + w]; c.a5 = wc[C_A5 * wpad + w]; c.b5 = wc[C_B5 * wpad + w];
@@ -375,22 +493,41 @@ __device__ __forceinline__ int waveform_len(double mtot, double delta_f) {
     return n > 2.0e9 ? 2000000000 : (int)n;
 }
 
+// key_a0 = false: the walker's last bin (lanes of a warp finish together); true (table path): its
+// Newtonian chirp coefficient quantised over the covered range (lanes of a warp share a reference
+// chirp and sit in neighbouring table rows).  Walkers without a waveform sort to one end.
 __global__ void sort_key_kernel(PlanDev P, int W, const double* __restrict__ params,
                                 int64_t sw, int64_t si,
                                 const uint8_t* __restrict__ skip, int* __restrict__ key,
-                                int* __restrict__ idx) {
+                                int* __restrict__ idx, bool key_a0, double a_lo, double a_scale) {
     int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= W) return;
     double p[GWIN_NPARAM];
     load_params(p, params, w, sw, si);
-    int ke = 0;
-    if (!(skip && skip[w]) && params_ok(p) && has_waveform(p, P.f_lower_wf)) {
-        int n = waveform_len(p[0] + p[1], P.delta_f);
-        ke = min(n, P.kmax);
+    const bool ok = !(skip && skip[w]) && params_ok(p) && has_waveform(p, P.f_lower_wf);
+    int k = key_a0 ? (1 << TAB_KEY_BITS) - 1 : 0;
+    if (ok) {
+        if (key_a0) {
+            const double q = (newtonian_coef(p[0], p[1]) - a_lo) * a_scale;
+            k = (int)fmin(fmax(q, 0.0), (double)((1 << TAB_KEY_BITS) - 2));
+        } else {
+            k = min(waveform_len(p[0] + p[1], P.delta_f), P.kmax);
+        }
     }
-    key[w] = ke;
+    key[w] = k;
     idx[w] = w;
 }
+
+// What walker_setup needs to split a walker's band between the kernels.
+struct FastArgs {
+    double a_sched_max;      // largest Newtonian coefficient (smallest chirp mass) the recurrence schedule covers
+    double cov_lo, cov_hi;   // Newtonian coefficients the moment tables cover (table path)
+    int table;               // table path: recurrence below k_split, tables above, tails by a second recurrence pass
+    int k_split, k_tab_end, n_tblk;
+    const TabBlk* blks;
+    int *ke_fast, *ke_low, *ks_tail, *key2, *idx2;
+    unsigned char* slow;
+};
 
 // ---------------------------------------------------------------------------
 // kernel 1: per-walker coefficients.  Thread t handles walker perm[t] and writes
@@ -404,8 +541,7 @@ __global__ void walker_setup_kernel(PlanDev P, int W, int wpad,
                                     int* __restrict__ ke_arr,
                                     double* __restrict__ hh_sorted /*[n_det][wpad]*/,
                                     const double* __restrict__ calib, int64_t csw, int64_t csi,
-                                    int* __restrict__ ke_low_arr, int k_split,
-                                    int* __restrict__ ks_tail_arr, const int* __restrict__ tab_start, int n_tblk) {
+                                    FastArgs F) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= W) return;
     const int w = perm ? perm[t] : t;
@@ -418,7 +554,8 @@ __global__ void walker_setup_kernel(PlanDev P, int W, int wpad,
     if (!ok) {
         // no bins; combine() turns this into -inf via ks = -1
         ks_arr[t] = -1; ke_arr[t] = -1;
-        if (ke_low_arr) { ke_low_arr[t] = -1; ks_tail_arr[t] = -1; }
+        if (F.ke_fast) { F.ke_fast[t] = -1; F.slow[t] = 0; }
+        if (F.table) { F.ke_low[t] = -1; F.ks_tail[t] = -1; F.key2[t] = 0; F.idx2[t] = t; }
         for (int r = 0; r < NCOEF(nd); ++r) wc[r * wpad + t] = 0.0;
         for (int d = 0; d < nd; ++d) hh_sorted[d * wpad + t] = 0.0;
         return;
@@ -426,77 +563,18 @@ __global__ void walker_setup_kernel(PlanDev P, int W, int wpad,
     const double m1 = p[0], m2 = p[1], chi1 = p[2], chi2 = p[3], dist = p[4];
     const double incl = p[5], phic = p[6], ra = p[7], dec = p[8], psi = p[9], tc = p[10];
 
-    // --- XLALSimInspiralPNPhasing_F2 (3.5PN, aligned spins) ---------------------
+    // --- XLALSimInspiralPNPhasing_F2 folded into 11 phase coefficients [turns] ---------
     const double mtot = m1 + m2;
-    const double dm = (m1 - m2) / (m1 + m2);
     const double eta = m1 * m2 / mtot / mtot;
-    const double m1M = m1 / mtot, m2M = m2 / mtot;
-    const double pfaN = 3.0 / (128.0 * eta);
-    double v2 = 5.0 * (743.0 / 84.0 + 11.0 * eta) / 9.0;
-    double v3 = -16.0 * G_PI;
-    double v4 = 5.0 * (3058.673 / 7.056 + 5429.0 / 7.0 * eta + 617.0 * eta * eta) / 72.0;
-    double v5 = 5.0 / 9.0 * (7729.0 / 84.0 - 13.0 * eta) * G_PI;
-    double vl5 = 5.0 / 3.0 * (7729.0 / 84.0 - 13.0 * eta) * G_PI;
-    double v6 = (11583.231236531 / 4.694215680 - 640.0 / 3.0 * G_PI * G_PI - 6848.0 / 21.0 * G_GAMMA)
-              + eta * (-15737.765635 / 3.048192 + 2255.0 / 12.0 * G_PI * G_PI)
-              + eta * eta * 76055.0 / 1728.0 - eta * eta * eta * 127825.0 / 1296.0;
-    v6 += (-6848.0 / 21.0) * 1.3862943611198906188;   // log(4)
-    const double vl6 = -6848.0 / 21.0;
-    double v7 = G_PI * (77096675.0 / 254016.0 + 378515.0 / 1512.0 * eta - 74045.0 / 756.0 * eta * eta);
+    double m3;
     {
-        const double chi1sq = chi1 * chi1, chi2sq = chi2 * chi2;
-        const double SL = m1M * m1M * chi1 + m2M * m2M * chi2;
-        const double dSigmaL = dm * (m2M * chi2 - m1M * chi1);
-        double pn_sigma = eta * (721.0 / 48.0 * chi1 * chi2 - 247.0 / 48.0 * chi1 * chi2);
-        pn_sigma += (720.0 - 1.0) / 96.0 * m1M * m1M * chi1 * chi1;
-        pn_sigma += (720.0 - 1.0) / 96.0 * m2M * m2M * chi2 * chi2;
-        pn_sigma -= (240.0 - 7.0) / 96.0 * m1M * m1M * chi1sq;
-        pn_sigma -= (240.0 - 7.0) / 96.0 * m2M * m2M * chi2sq;
-        double pn_ss3 = (326.75 / 1.12 + 557.5 / 1.8 * eta) * eta * chi1 * chi2;
-        pn_ss3 += ((4703.5 / 8.4 + 2935.0 / 6.0 * m1M - 120.0 * m1M * m1M)
-                   + (-4108.25 / 6.72 - 108.5 / 1.2 * m1M + 125.5 / 3.6 * m1M * m1M)) * m1M * m1M * chi1sq;
-        pn_ss3 += ((4703.5 / 8.4 + 2935.0 / 6.0 * m2M - 120.0 * m2M * m2M)
-                   + (-4108.25 / 6.72 - 108.5 / 1.2 * m2M + 125.5 / 3.6 * m2M * m2M)) * m2M * m2M * chi2sq;
-        const double pn_gamma = (554345.0 / 1134.0 + 110.0 * eta / 9.0) * SL
-                              + (13915.0 / 84.0 - 10.0 * eta / 3.0) * dSigmaL;
-        v7 += (-8980424995.0 / 762048.0 + 6586595.0 * eta / 756.0 - 305.0 * eta * eta / 36.0) * SL
-            - (170978035.0 / 48384.0 - 2876425.0 * eta / 672.0 - 4735.0 * eta * eta / 144.0) * dSigmaL;
-        v6 += G_PI * (3760.0 * SL + 1490.0 * dSigmaL) / 3.0 + pn_ss3;
-        v5 += -1.0 * pn_gamma;
-        vl5 += -3.0 * pn_gamma;
-        v4 += -10.0 * pn_sigma;
-        v3 += 188.0 * SL / 3.0 + 25.0 * dSigmaL;
+        double pcf[NPH];
+        m3 = pn_phase_coefs(m1, m2, chi1, chi2, phic, p[11], p[12], pcf);
+#pragma unroll
+        for (int i = 0; i < NPH; ++i) wc[(size_t)i * wpad + t] = pcf[i];
     }
-    // --- fold v = (pi M f)^(1/3) = m3 * x,  x = f^(1/3), into coefficients [turns] --
-    const double m_sec = mtot * G_MTSUN;
-    const double piM = G_PI * m_sec;
-    const double m3 = cbrt(piM);
-    const double lm3 = log(m3);
-    const double s = pfaN / G_TWOPI;
     const double im3 = 1.0 / m3;
-    const double im3_2 = im3 * im3, im3_3 = im3_2 * im3, im3_5 = im3_3 * im3_2;
-    wc[C_A0 * wpad + t] = s * im3_5;
-    wc[C_A2 * wpad + t] = s * v2 * im3_3;
-    wc[C_A3 * wpad + t] = s * v3 * im3_2;
-    wc[C_A4 * wpad + t] = s * v4 * im3;
-    // constant term also absorbs -2 phi_c - pi/4
-    wc[C_A5 * wpad + t] = s * (v5 + vl5 * lm3) - (2.0 * phic + 0.25 * G_PI) / G_TWOPI;
-    wc[C_B5 * wpad + t] = s * vl5;
-    wc[C_A6 * wpad + t] = s * (v6 + vl6 * lm3) * m3;
-    wc[C_B6 * wpad + t] = s * vl6 * m3;
-    wc[C_A7 * wpad + t] = s * v7 * m3 * m3;
-    {   // tidal terms (lalsimulation TaylorF2Phasing_10PN/12PNTidalCoeff): pfaN (pft10 v^10 + pft12 v^12) / v^5
-        const double lam1 = p[11], lam2 = p[12];
-        const double m1M4 = m1M * m1M * m1M * m1M, m2M4 = m2M * m2M * m2M * m2M;
-        const double pft10 = lam1 * (-288.0 + 264.0 * m1M) * m1M4 + lam2 * (-288.0 + 264.0 * m2M) * m2M4;
-        const double pft12 = lam1 * (-15895.0 / 28.0 + 4595.0 / 28.0 * m1M + 5715.0 / 14.0 * m1M * m1M
-                                     - 325.0 / 7.0 * m1M * m1M * m1M) * m1M4
-                           + lam2 * (-15895.0 / 28.0 + 4595.0 / 28.0 * m2M + 5715.0 / 14.0 * m2M * m2M
-                                     - 325.0 / 7.0 * m2M * m2M * m2M) * m2M4;
-        const double m3_2 = m3 * m3, m3_5 = m3_2 * m3_2 * m3;
-        wc[C_A10 * wpad + t] = s * pft10 * m3_5;
-        wc[C_A12 * wpad + t] = s * pft12 * m3_5 * m3_2;
-    }
+    const double im3_3 = im3 * im3 * im3;
 
     // --- band ------------------------------------------------------------------
     const int n = waveform_len(mtot, P.delta_f);
@@ -504,22 +582,33 @@ __global__ void walker_setup_kernel(PlanDev P, int W, int wpad,
     const int ks = max(P.kmin, P.istart);
     ks_arr[t] = ks;
     ke_arr[t] = ke;        // ke <= ks means "detectors contribute 0" (gaussian_noise.py:329-333)
-    if (ke_low_arr) {
-        ke_low_arr[t] = min(ke, k_split);      // the recurrence kernel's share of the band
-        // table sub-blocks are taken whole; the one holding the last bin (unless it ends there)
-        // is left to a second pass of the recurrence kernel over [ks_tail, ke)
-        int tail = ke;
-        if (ke > k_split) {
-            const int k_end = tab_start[n_tblk];            // end of the last sub-block (<= kmax)
-            if (ke > k_end) {
-                tail = k_end;
-            } else {
-                int lo = 0, hi = n_tblk - 1;                // last sub-block starting below ke
-                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (tab_start[mid] < ke) lo = mid; else hi = mid - 1; }
-                if (ke < tab_start[lo + 1]) tail = tab_start[lo];
+    if (F.ke_fast) {
+        // A walker the fast kernels are not built for -- lighter than the recurrence schedule's smallest
+        // chirp mass, or outside the range the moment tables cover -- keeps an empty band there and is
+        // evaluated by the direct kernel afterwards (slow path: always right, counted).
+        const double a0 = wc[(size_t)C_A0 * wpad + t];
+        const bool slow = a0 > F.a_sched_max || (F.table && (a0 < F.cov_lo || a0 > F.cov_hi));
+        F.slow[t] = slow ? 1 : 0;
+        const int kef = slow ? ks : ke;
+        F.ke_fast[t] = kef;
+        if (F.table) {
+            F.ke_low[t] = min(kef, F.k_split);      // the recurrence kernel's share of the band
+            // table sub-blocks are taken whole; what lies between the last whole one and the walker's
+            // last bin is left to a second pass of the recurrence kernel over [ks_tail, ke)
+            int tail = kef;
+            if (kef > F.k_split) {
+                if (kef >= F.k_tab_end) {
+                    tail = F.k_tab_end;
+                } else {
+                    int lo = 0, hi = F.n_tblk - 1;          // the sub-block holding bin kef
+                    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (F.blks[mid].start <= kef) lo = mid; else hi = mid - 1; }
+                    tail = F.blks[lo].start;
+                }
             }
+            F.ks_tail[t] = tail;
+            F.key2[t] = tail < kef ? kef : 0;
+            F.idx2[t] = t;
         }
-        ks_tail_arr[t] = tail;
     }
 
     // --- amplitude: amp0 * sqrt(5/(32 eta)) * (pi M)^(-7/6) -------------------------
@@ -647,14 +736,21 @@ template <int ND, bool CALIB>
 __global__ void __launch_bounds__(CTA_THREADS)
 loglr_direct_kernel(PlanDev P, int W, int wpad, int chunk_bins, int n_chunks,
                     const double* __restrict__ wc, const int* __restrict__ ks_arr,
-                    const int* __restrict__ ke_arr, double2* __restrict__ partial) {
-    const int t = blockIdx.x * CTA_THREADS + threadIdx.x;
+                    const int* __restrict__ ke_arr, double2* __restrict__ partial,
+                    const int* __restrict__ list, const int* __restrict__ n_list) {
+    // list != NULL (slow path): the walkers to evaluate are columns list[0 .. *n_list) of the
+    // coefficient rows; their partial sums go to slots 0 .. *n_list.  The grid's x extent is fixed
+    // and strides over the list, so an empty list costs one wave of CTAs that exit at once.
+    const int n = list ? *n_list : W;
     const int chunk = blockIdx.y;
     const int band0 = max(P.kmin, P.istart);
     const int k0 = band0 + chunk * chunk_bins;
     const int k1 = min(k0 + chunk_bins, P.kmax);
-    const bool live = t < W;
-    const int ks = live ? ks_arr[t] : 0, ke = live ? ke_arr[t] : 0;
+    for (int grp = blockIdx.x; grp * CTA_THREADS < n; grp += gridDim.x) {
+    const int t = grp * CTA_THREADS + threadIdx.x;
+    const bool live = t < n;
+    const int col = live ? (list ? list[t] : t) : 0;
+    const int ks = live ? ks_arr[col] : 0, ke = live ? ke_arr[col] : 0;
     const int lo = max(k0, ks), hi = min(k1, ke);
     const bool has = lo < hi;
     int wlo = has ? lo : 0x7fffffff, whi = has ? hi : 0;
@@ -668,7 +764,7 @@ loglr_direct_kernel(PlanDev P, int W, int wpad, int chunk_bins, int n_chunks,
     for (int d = 0; d < ND; ++d) acc[d] = make_double2(0.0, 0.0);
 
     if (wlo < whi) {
-        const int tt = live ? t : 0;
+        const int tt = col;
         PhaseCoef pc;
         load_phase_coef(pc, wc, wpad, tt);
         double tau_hi[ND], tau_lo[ND];
@@ -709,6 +805,7 @@ loglr_direct_kernel(PlanDev P, int W, int wpad, int chunk_bins, int n_chunks,
 #pragma unroll
         for (int d = 0; d < ND; ++d)
             partial[((size_t)chunk * ND + d) * wpad + t] = acc[d];
+    }
     }
 }
 
@@ -804,6 +901,7 @@ struct TileStream {
     }
     __device__ __forceinline__ void open(double2* buf_, uint64_t* bars, const double2* T_, int ka_, int kz_, int lane_) {
         buf = buf_; bar = smem_u32(bars); T = T_; ka = ka_; kz = kz_; cur = -1; lane = lane_;
+        __syncwarp();                              // a previous stream of this warp is fully closed
         if (lane == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar + 8u) : "memory");
@@ -1054,13 +1152,35 @@ loglr_recur_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_blk,
                    const int* __restrict__ blk_start, const int* __restrict__ blk_mat,
                    const BlockMat* __restrict__ mats,
                    const double* __restrict__ wc, const int* __restrict__ ks_arr,
-                   const int* __restrict__ ke_arr, double2* __restrict__ partial) {
+                   const int* __restrict__ ke_arr, double2* __restrict__ partial,
+                   const int* __restrict__ col_arr, const int* __restrict__ grp_b) {
+    // Thread t works on column col_arr[t] of the per-walker arrays (NULL: t itself).
+    // grp_b == NULL: the CTA takes chunk blockIdx.y of the schedule.  grp_b != NULL (the tails of the
+    // table path, walkers ordered by their last bin): the 128 walkers of this CTA only need blocks
+    // [grp_b[x], grp_b[gridDim.x + x]); the CTA takes chunks y, y + gridDim.y, ... of that range and
+    // writes one partial sum per walker into slot y.
     const int t = blockIdx.x * CTA_THREADS + threadIdx.x;
-    const int chunk = blockIdx.y;
-    const int b0 = chunk * blocks_per_chunk;
-    const int b1 = min(b0 + blocks_per_chunk, n_blk);
     const bool live = t < W;
-    const int ks = live ? ks_arr[t] : 0, ke = live ? ke_arr[t] : 0;
+    const int col = live ? (col_arr ? col_arr[t] : t) : 0;
+    const int ks = live ? ks_arr[col] : 0, ke = live ? ke_arr[col] : 0;
+    const int cb0 = grp_b ? grp_b[blockIdx.x] : 0;
+    const int cb1 = grp_b ? grp_b[gridDim.x + blockIdx.x] : n_blk;
+    double2 acc[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) acc[d] = make_double2(0.0, 0.0);
+
+    // dynamic shared memory: [per-warp tile buffers][per-thread coefficient columns][mbarriers]
+    constexpr int TILE = TileStream<ND>::TILE;
+    constexpr int NWARP = CTA_THREADS / WARP;
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    double2 (*s_tile)[2 * TILE * ND] = reinterpret_cast<double2 (*)[2 * TILE * ND]>(s_dyn);
+    double* s_coef = reinterpret_cast<double*>(s_dyn + sizeof(double2) * NWARP * 2 * TILE * ND);
+    uint64_t (*s_bar)[2] = reinterpret_cast<uint64_t (*)[2]>(s_coef + (CALIB ? RC_ROWS_CAL(ND) : RC_ROWS(ND)) * CTA_THREADS);
+    bool coef_staged = false;
+    for (int chunk = blockIdx.y;; chunk += gridDim.y) {
+    const int b0 = cb0 + chunk * blocks_per_chunk;
+    if (b0 >= cb1) break;
+    const int b1 = min(b0 + blocks_per_chunk, cb1);
     const int k0 = blk_start[b0], k1 = blk_start[b1];
     const int lo = max(k0, ks), hi = min(k1, ke);
     const bool has = lo < hi;
@@ -1075,33 +1195,24 @@ loglr_recur_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_blk,
         ihi = min(ihi, __shfl_xor_sync(0xffffffffu, ihi, o));
     }
     if (any_idle) { ilo = 0x7fffffff; ihi = 0; }
-    double2 acc[ND];
-#pragma unroll
-    for (int d = 0; d < ND; ++d) acc[d] = make_double2(0.0, 0.0);
-
-    // dynamic shared memory: [per-warp tile buffers][per-thread coefficient columns][mbarriers]
-    constexpr int TILE = TileStream<ND>::TILE;
-    constexpr int NWARP = CTA_THREADS / WARP;
-    extern __shared__ __align__(128) unsigned char s_dyn[];
-    double2 (*s_tile)[2 * TILE * ND] = reinterpret_cast<double2 (*)[2 * TILE * ND]>(s_dyn);
-    double* s_coef = reinterpret_cast<double*>(s_dyn + sizeof(double2) * NWARP * 2 * TILE * ND);
-    uint64_t (*s_bar)[2] = reinterpret_cast<uint64_t (*)[2]>(s_coef + (CALIB ? RC_ROWS_CAL(ND) : RC_ROWS(ND)) * CTA_THREADS);
     if (wlo < whi) {
-        const int tt = live ? t : 0;
         double* sc = s_coef + threadIdx.x;
+        if (!coef_staged) {
+            coef_staged = true;
 #pragma unroll
-        for (int r = 0; r < NPH; ++r) sc[r * CTA_THREADS] = wc[(size_t)r * wpad + tt];
+            for (int r = 0; r < NPH; ++r) sc[r * CTA_THREADS] = wc[(size_t)r * wpad + col];
 #pragma unroll
-        for (int d = 0; d < ND; ++d) {
-            const double* row = wc + (size_t)(C_DET0 + D_NROW * d) * wpad + tt;
-            sc[(NPH + 2 * d) * CTA_THREADS] = row[D_TAUHI * wpad];
-            sc[(NPH + 1 + 2 * d) * CTA_THREADS] = row[D_TAULO * wpad];
-            sc[(NPH + 2 * ND + 2 * d) * CTA_THREADS] = row[D_ECOS * wpad];
-            sc[(NPH + 1 + 2 * ND + 2 * d) * CTA_THREADS] = row[D_ESIN * wpad];
-            if (CALIB) {
+            for (int d = 0; d < ND; ++d) {
+                const double* row = wc + (size_t)(C_DET0 + D_NROW * d) * wpad + col;
+                sc[(NPH + 2 * d) * CTA_THREADS] = row[D_TAUHI * wpad];
+                sc[(NPH + 1 + 2 * d) * CTA_THREADS] = row[D_TAULO * wpad];
+                sc[(NPH + 2 * ND + 2 * d) * CTA_THREADS] = row[D_ECOS * wpad];
+                sc[(NPH + 1 + 2 * ND + 2 * d) * CTA_THREADS] = row[D_ESIN * wpad];
+                if (CALIB) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    sc[(RC_ROWS(ND) + 8 * d + i) * CTA_THREADS] = row[(size_t)(D_CA0 + i) * wpad];
+                    for (int i = 0; i < 8; ++i)
+                        sc[(RC_ROWS(ND) + 8 * d + i) * CTA_THREADS] = row[(size_t)(D_CA0 + i) * wpad];
+                }
             }
         }
         const int lane = threadIdx.x & (WARP - 1), warp = threadIdx.x / WARP;
@@ -1151,10 +1262,19 @@ loglr_recur_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_blk,
         }
         if (opened) S.close();
     }
-    if (live && has) {          // chunks a walker does not reach are neither written nor read back
+    if (!grp_b) {
+        if (live && has) {      // chunks a walker does not reach are neither written nor read back
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+                partial[((size_t)chunk * ND + d) * wpad + col] = acc[d];
+        }
+        break;
+    }
+    }
+    if (grp_b && live) {
 #pragma unroll
         for (int d = 0; d < ND; ++d)
-            partial[((size_t)chunk * ND + d) * wpad + t] = acc[d];
+            partial[((size_t)blockIdx.y * ND + d) * wpad + col] = acc[d];
     }
 }
 
@@ -1162,120 +1282,195 @@ loglr_recur_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_blk,
 // ---------------------------------------------------------------------------
 // kernel 2c: table-driven <d|h> above k_split.
 //
-// A sub-block of m bins centred on kc = s + m/2: Theta_d(kc + j) = th0 + nu j + R(j) with R the
-// quadratic..quartic part of the quartic through five exact phase samples (the same bound as
-// the recurrence kernel's blocks), small enough (|R| <= TAB_RHO at the edge) that
-//     e^{-2 pi i R(j)} = sum_{n <= TAB_DEG} c_n (j/h)^n,   h = m/2
-// to ~1e-10.  Then
-//     sum_j T[kc+j] e^{-2 pi i Theta_d} = e^{-2 pi i th0} sum_n c_n M_n(nu_d),
-//     M_n(nu) = sum_j (j/h)^n T[kc+j] e^{-2 pi i nu j},
-// and M_n -- a trigonometric polynomial of nu with period 1 -- is tabulated per plan on the grid
-// nu = g/(2m) (tab_build_kernel: the DFT of the kernel-deconvolved sequence) and evaluated per
-// walker by TAB_W-tap interpolation with the "exponential of semicircle" kernel (type-2 NUFFT,
-// Barnett et al. 2019).  Cost per (walker, sub-block, detector): O(TAB_W TAB_DEG), whatever m.
-// Walkers of a batch sit within a few grid cells of each other at these frequencies, so the
-// table rows they touch stay in L1/L2.
+// A sub-block of m bins centred on kc = s + m/2, s_j = j / h, h = m/2.  The TaylorF2 phase is a
+// combination of 11 fixed functions of f (powers of f^(1/3) and two logarithms), so its Taylor
+// coefficients about kc are a per-sub-block 11 x TAB_NT matrix (host, long double) applied to the
+// walker's phase coefficients:  Theta_d(kc + j) = sum_n t_n s_j^n  (+ the detector's linear term).
+// Per sub-block there are K reference chirps (equal masses, no spin, a0 on a uniform grid over the
+// covered range); the tables of reference r hold T e^{-2 pi i N_r(j)}, N_r the reference's exact phase
+// minus its own constant and linear Taylor terms.  Relative to its nearest reference a walker has
+//     Theta_d(kc + j) - N_r(j) = th0 + nu_d j + R(j),  R = sum_{n=2..8} (t_n - t_n^ref) s^n,
+// |2 pi R| <= a few 1e-2, and
+//     sum_j T[kc+j] e^{-2 pi i Theta_d} = e^{-2 pi i th0} sum_{n <= TAB_DEG} e_n M_n(nu_d),
+//     M_n(nu) = sum_j s_j^n T[kc+j] e^{-2 pi i N_r(j)} e^{-2 pi i nu j},
+// e_n the Taylor coefficients of e^{-2 pi i R} (recurrence n e_n = sum_k k u_k e_{n-k}).  M_n -- a
+// trigonometric polynomial of nu with period 1 -- is tabulated on the grid nu = g/(2m) (tab_dft_kernel:
+// the DFT of the kernel-deconvolved sequence) and evaluated per walker by TAB_W-tap interpolation
+// with the "exponential of semicircle" kernel (type-2 NUFFT, Barnett et al. 2019).  Cost per
+// (walker, sub-block, detector): O(TAB_W TAB_DEG), whatever m.  The dropped terms e_9, e_10 are
+// formed as well: a walker whose truncation estimate is too large (it lies outside what the
+// schedule was built for) is handed to the slow path instead of getting a wrong number.
+// Walkers are ordered by a0, so the lanes of a warp share the reference and sit within a few grid
+// points of each other: the warp stages the union of their table rows in shared memory.
 // ---------------------------------------------------------------------------
-// Reference waveform for the tables (gwin_plan_set_reference): per sub-block the reference's phase
-// at the centre, an end-point slope nu_ref, and its non-linear part N_ref = Theta_ref - centre - nu_ref j
-// at the phase-polynomial nodes.  The tables then hold T e^{-2 pi i N_ref(j)} and the walkers fit and
-// expand their phase RELATIVE to the reference, so sub-blocks can be as long as the batch is narrow.
-#define TAB_REFN (TAB_PH + 3)        // per sub-block: th_centre, nu_ref, N_ref at the TAB_PH + 1 nodes
-__global__ void tab_ref_kernel(PlanDev P, int n_tblk, const int* __restrict__ tab_start,
-                               const int* __restrict__ tab_mi, const TabMat* __restrict__ mats,
-                               const double* __restrict__ ref_wc, double* __restrict__ tab_ref) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n_tblk) return;
-    PhaseCoef pc;
-    load_phase_coef(pc, ref_wc, 1, 0);
-    const TabMat* M = mats + tab_mi[b];
-    const int s = tab_start[b], m = M->m;
-    const double thc = phase_turns(pc, ld_basis(P.basis + s + m / 2));
-    const double nu = (phase_turns(pc, ld_basis(P.basis + s + m - 1)) - phase_turns(pc, ld_basis(P.basis + s))) / (double)(m - 1);
-    double* out = tab_ref + (size_t)b * TAB_REFN;
-    out[0] = thc;
-    out[1] = nu;
-    for (int i = 0; i <= TAB_PH; ++i)
-        out[2 + i] = phase_turns(pc, ld_basis(P.basis + s + M->node[i])) - thc - nu * (double)(M->node[i] - m / 2);
+__global__ void tab_tref_kernel(int n_pairs, const int* __restrict__ pair_blk, const TabBlk* __restrict__ blks,
+                                const double* __restrict__ cmat, double* __restrict__ tref,
+                                double* __restrict__ refcoef) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= n_pairs) return;
+    const int b = pair_blk[pair];
+    const TabBlk B = blks[b];
+    const int r = pair - B.pair0;
+    double c[NPH];
+    ref_phase_coefs(B.a_lo + ((double)r + 0.5) * B.da, c);
+    const double* cm = cmat + (size_t)b * NPH * TAB_NTP;
+    for (int n = 0; n < TAB_NTP; ++n) {
+        double acc = 0.0;
+        for (int i = 0; i < NPH; ++i) acc = fma(c[i], cm[i * TAB_NTP + n], acc);
+        tref[(size_t)pair * TAB_NTP + n] = acc;
+    }
+    for (int i = 0; i < NPH; ++i) refcoef[(size_t)pair * NPH + i] = c[i];
 }
 
+// seg[j] = T[s + j] e^{-2 pi i N_r(j)} / phi_hat(j): the sequence whose moments' DFT is the table
 __global__ void __launch_bounds__(256)
-tab_build_kernel(PlanDev P, const int* __restrict__ tab_start, const int* __restrict__ tab_mi,
-                 const int64_t* __restrict__ tab_off, const TabMat* __restrict__ mats,
-                 const double* __restrict__ invhat, double2* __restrict__ tab,
-                 const double* __restrict__ ref_wc, const double* __restrict__ tab_ref) {
-    const int b = blockIdx.y, d = blockIdx.z;
-    const TabMat* M = mats + tab_mi[b];
-    const int m = M->m, L = 2 * m;
+tab_seg_kernel(PlanDev P, const int* __restrict__ pair_blk, const TabBlk* __restrict__ blks,
+               const long long* __restrict__ pair_seg, const int* __restrict__ blk_hat,
+               const double* __restrict__ invhat, const double* __restrict__ tref,
+               const double* __restrict__ refcoef, double2* __restrict__ seg, int pair_base) {
+    const int pair = pair_base + blockIdx.y, d = blockIdx.z;
+    const int b = pair_blk[pair];
+    const int s = blks[b].start, m = blks[b].m;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    PhaseCoef pc;
+    load_phase_coef(pc, refcoef + (size_t)pair * NPH, 1, 0);
+    const int k = s + j, jc = j - m / 2;
+    const double th = phase_turns(pc, ld_basis(P.basis + k));
+    const double nref = (th - tref[(size_t)pair * TAB_NTP]) - tref[(size_t)pair * TAB_NTP + 1] * ((double)jc / (0.5 * (double)m));
+    const double2 Tk = __ldg(P.T + (size_t)k * P.n_det + d);
+    double2 u = cmul(Tk, phasor_neg(nref));
+    const double w = invhat[blk_hat[b] + j];
+    u.x *= w; u.y *= w;
+    seg[pair_seg[pair] + (size_t)d * m + j] = u;
+}
+
+// tab[g][n] = sum_j seg[j] s_j^n e^{-2 pi i j_c g / L}, j_c = j - m/2, L = 2m; rows carry TAB_W
+// wrap-around points so that taps never wrap.  One thread per grid point; the sequence goes through
+// shared memory in tiles; the twiddle factor advances by rotation, re-anchored every 32 terms.
+__global__ void __launch_bounds__(256)
+tab_dft_kernel(const int* __restrict__ pair_blk, const TabBlk* __restrict__ blks,
+               const long long* __restrict__ pair_seg, const double2* __restrict__ seg,
+               double2* __restrict__ tab, int n_det, int pair_base) {
+    const int pair = pair_base + blockIdx.y, d = blockIdx.z;
+    const int b = pair_blk[pair];
+    const TabBlk B = blks[b];
+    const int m = B.m, L = 2 * m;
+    if ((int)(blockIdx.x * blockDim.x) >= L + TAB_W) return;          // uniform per CTA
     const int gp = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gp >= L + TAB_W) return;
-    const int g = gp >= L ? gp - L : gp;         // rows carry TAB_W wrap-around points: taps never wrap
-    const int s = tab_start[b];
-    const double* ih = invhat + M->hat_off;
-    const double ih2 = 2.0 / (double)m;
-    PhaseCoef pcr;
-    double ref_thc = 0.0, ref_nu = 0.0;
-    if (tab_ref) {
-        load_phase_coef(pcr, ref_wc, 1, 0);
-        ref_thc = tab_ref[(size_t)b * TAB_REFN];
-        ref_nu = tab_ref[(size_t)b * TAB_REFN + 1];
-    }
+    const bool live = gp < L + TAB_W;
+    const int g = gp >= L ? gp - L : gp;
+    const double2* sq = seg + pair_seg[pair] + (size_t)d * m;
+    const double ih2 = 2.0 / (double)m, invL = 1.0 / (double)L;
+    __shared__ double2 s_seg[256];
     double2 acc[TAB_DEG + 1];
 #pragma unroll
     for (int n = 0; n <= TAB_DEG; ++n) acc[n] = make_double2(0.0, 0.0);
-    for (int j = 0; j < m; ++j) {
-        const int k = s + j;
-        if (k >= P.n_f) break;
-        const double2 Tk = __ldg(P.T + (size_t)k * P.n_det + d);
-        if (Tk.x == 0.0 && Tk.y == 0.0) continue;
-        const int jc = j - m / 2;
-        int idx = (int)(((long long)jc * g) % L);          // (jc g) mod L
-        if (idx < 0) idx += L;
-        double sn, cs;
-        sincospi(-2.0 * (double)idx / (double)L, &sn, &cs);
-        double2 u = cmul(Tk, make_double2(cs, sn));
-        if (tab_ref)            // bake e^{-2 pi i N_ref(j)}
-            u = cmul(u, phasor_neg(phase_turns(pcr, ld_basis(P.basis + k)) - ref_thc - ref_nu * (double)jc));
-        const double w = ih[j];
-        u.x *= w; u.y *= w;
-        const double sc = (double)jc * ih2;
+    double sn, cs;
+    sincospi(-2.0 * (double)g * invL, &sn, &cs);
+    const double2 rot = make_double2(cs, sn);                   // e^{-2 pi i g / L}
+    for (int j0 = 0; j0 < m; j0 += 256) {
+        __syncthreads();
+        s_seg[threadIdx.x] = j0 + (int)threadIdx.x < m ? sq[j0 + threadIdx.x] : make_double2(0.0, 0.0);
+        __syncthreads();
+        if (!live) continue;
+        const int nj = min(256, m - j0);
+        double2 w = make_double2(1.0, 0.0);
+        for (int jj = 0; jj < nj; ++jj) {
+            const int jc = j0 + jj - m / 2;
+            if ((jj & 31) == 0) {
+                int idx = (int)(((long long)jc * g) % L);      // (jc g) mod L
+                if (idx < 0) idx += L;
+                sincospi(-2.0 * (double)idx * invL, &sn, &cs);
+                w = make_double2(cs, sn);
+            }
+            double2 u = cmul(s_seg[jj], w);
+            w = cmul(w, rot);
+            const double sc = (double)jc * ih2;
 #pragma unroll
-        for (int n = 0; n <= TAB_DEG; ++n) {
-            acc[n].x += u.x; acc[n].y += u.y;
-            u.x *= sc; u.y *= sc;
+            for (int n = 0; n <= TAB_DEG; ++n) {
+                acc[n].x += u.x; acc[n].y += u.y;
+                u.x *= sc; u.y *= sc;
+            }
         }
     }
-    // layout [d][g][TAB_NM]: the moments of one grid point are contiguous (one or two cache lines per tap)
-    double2* out = tab + tab_off[b] + ((size_t)d * (L + TAB_W) + gp) * TAB_NM;
+    if (!live) return;
+    // layout [r][d][g][TAB_NM]: the moments of one grid point are contiguous (one cache line per tap)
+    double2* out = tab + B.off + (((size_t)(pair - B.pair0) * n_det + d) * (L + TAB_W) + gp) * TAB_NM;
     out[0] = acc[0];
 #pragma unroll
     for (int n = 2; n <= TAB_DEG; ++n) out[n - 1] = acc[n];
 }
 
+// What a batch needs the tables to cover: range of the Newtonian coefficient a0 and, per other phase
+// coefficient, the largest deviation from the reference chirp of the same a0.
+// out[0] = min a0, [1] = max a0, [2 + i] = max |a_i - a_i^ref| (bit patterns of non-negative doubles
+// order like the numbers), [2 + NPH] = number of walkers with a waveform.
+__global__ void cover_stats_kernel(PlanDev P, int W, const double* __restrict__ params, int64_t sw, int64_t si,
+                                   const uint8_t* __restrict__ skip, unsigned long long* __restrict__ out) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    double v[2 + NPH];
+    v[0] = INFINITY; v[1] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NPH; ++i) v[2 + i] = 0.0;
+    bool ok = false;
+    if (w < W) {
+        double p[GWIN_NPARAM];
+        load_params(p, params, w, sw, si);
+        ok = !(skip && skip[w]) && params_ok(p) && has_waveform(p, P.f_lower_wf);
+        if (ok) {
+            double a[NPH], ar[NPH];
+            pn_phase_coefs(p[0], p[1], p[2], p[3], 0.0, p[11], p[12], a);
+            ref_phase_coefs(a[0], ar);
+            v[0] = v[1] = a[0];
+#pragma unroll
+            for (int i = 1; i < NPH; ++i) v[2 + i] = fabs(a[i] - ar[i]);
+            v[2 + C_A5] = 0.0;                  // the constant term carries no curvature
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        v[0] = fmin(v[0], __shfl_xor_sync(0xffffffffu, v[0], o));
+#pragma unroll
+        for (int i = 1; i < 2 + NPH; ++i) v[i] = fmax(v[i], __shfl_xor_sync(0xffffffffu, v[i], o));
+    }
+    const unsigned cnt = __popc(__ballot_sync(0xffffffffu, ok));
+    if ((threadIdx.x & 31) == 0 && cnt) {
+        atomicMin(out, (unsigned long long)__double_as_longlong(v[0]));
+        for (int i = 1; i < 2 + NPH; ++i) atomicMax(out + i, (unsigned long long)__double_as_longlong(v[i]));
+        atomicAdd(out + 2 + NPH, (unsigned long long)cnt);
+    }
+}
+
 #ifndef TABLE_MIN_CTAS
-#define TABLE_MIN_CTAS 5
+#define TABLE_MIN_CTAS 4
 #endif
 #define TAB_SPAN 24          // table rows a warp stages per detector and sub-block (>= TAB_W + the lanes' spread)
 #define TAB_ROWB (TAB_NM * 16 + 16)
-#ifndef TAB_GROUP
-#define TAB_GROUP 5          // taps whose weights are evaluated together (independent Horner chains)
-#endif
+#define TAB_CHUNK_MAX 16     // sub-blocks per CTA at most (their Taylor matrices are staged in shared memory)
 template <int ND>
 __global__ void __launch_bounds__(CTA_THREADS, TABLE_MIN_CTAS)
 loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
-                   const int* __restrict__ tab_start, const int* __restrict__ tab_mi,
-                   const int64_t* __restrict__ tab_off, const TabMat* __restrict__ mats,
-                   const double2* __restrict__ tab,
+                   const TabBlk* __restrict__ blks, const double* __restrict__ cmat,
+                   const double* __restrict__ tref, const double2* __restrict__ tab,
                    const double* __restrict__ wc, const int* __restrict__ ke_arr,
-                   double2* __restrict__ partial,
-                   const double* __restrict__ tab_ref, int* __restrict__ violation) {
+                   double2* __restrict__ partial, unsigned char* __restrict__ slow) {
     const int t = blockIdx.x * CTA_THREADS + threadIdx.x;
     const int chunk = blockIdx.y;
     const int b0 = chunk * blocks_per_chunk;
     const int b1 = min(b0 + blocks_per_chunk, n_tblk);
     const bool live = t < W;
     const int ke = live ? ke_arr[t] : 0;
-    const int k0 = tab_start[b0];
+    // shared memory: [chunk's Taylor matrices][per-warp staging buffers: ND x TAB_SPAN table rows of
+    // TAB_ROWB bytes (128 B of moments + 16 B of padding against bank conflicts)]
+    extern __shared__ __align__(16) unsigned char s_tab[];
+    double* s_c = reinterpret_cast<double*>(s_tab);
+    unsigned char* s_warp = s_tab + (size_t)blocks_per_chunk * NPH * TAB_NTP * sizeof(double)
+                          + (size_t)(threadIdx.x / WARP) * ND * TAB_SPAN * TAB_ROWB;
+    for (int i = threadIdx.x; i < (b1 - b0) * NPH * TAB_NTP; i += CTA_THREADS)
+        s_c[i] = cmat[(size_t)b0 * NPH * TAB_NTP + i];
+    __syncthreads();
+    const int k0 = blks[b0].start;
     const bool has = k0 < ke;
     int whi = has ? ke : 0;
 #pragma unroll
@@ -1285,8 +1480,9 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
     for (int d = 0; d < ND; ++d) acc[d] = make_double2(0.0, 0.0);
     if (k0 < whi) {
         const int tt = live ? t : 0;
-        PhaseCoef pc;
-        load_phase_coef(pc, wc, wpad, tt);
+        double a[NPH];
+#pragma unroll
+        for (int i = 0; i < NPH; ++i) a[i] = wc[(size_t)i * wpad + tt];
         double tau_hi[ND], tau_lo[ND];
 #pragma unroll
         for (int d = 0; d < ND; ++d) {
@@ -1294,167 +1490,164 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
             tau_hi[d] = row[D_TAUHI * wpad];
             tau_lo[d] = row[D_TAULO * wpad];
         }
-        // per-warp staging buffers: [ND][TAB_SPAN] table rows of TAB_ROWB bytes (128 B of moments + 16 B
-        // of padding so that lanes reading different rows hit different banks)
-        extern __shared__ __align__(16) unsigned char s_tab[];
-        unsigned char* s_warp = s_tab + (size_t)(threadIdx.x / WARP) * ND * TAB_SPAN * TAB_ROWB;
         const int lane = threadIdx.x & (WARP - 1);
+        bool dead = false;                              // this walker left the table path
         for (int b = b0; b < b1; ++b) {
-            const int s = tab_start[b];
+            const TabBlk B = blks[b];
+            const int s = B.start, m = B.m, L = 2 * m;
             if (s >= whi) break;
-            const TabMat* M = mats + tab_mi[b];
-            const int m = M->m, L = 2 * m;
-            const bool act = ke >= s + m;               // this lane takes the sub-block whole
-            if (!__any_sync(0xffffffffu, act)) continue;
+            bool act = !dead && ke >= s + m;            // this lane takes the sub-block whole
+            const unsigned amask = __ballot_sync(0xffffffffu, act);
+            if (!amask) continue;
+            // ---- reference chirp: the lanes of a warp are neighbours in a0; when they all lie within
+            // 3/4 of the reference spacing of the middle lane's reference they share it (and the staged
+            // table rows), else every lane takes its own nearest one
+            int r = (int)((a[0] - B.a_lo) * B.inv_da);
+            r = max(0, min(r, B.K - 1));
+            const int mid = __fns(amask, 0, (__popc(amask) + 1) / 2);
+            const int rL = __shfl_sync(0xffffffffu, r, mid);
+            const double aL = B.a_lo + ((double)rL + 0.5) * B.da;
+            const bool uni = __all_sync(0xffffffffu, !act || fabs(a[0] - aL) <= 0.75 * B.da);
+            if (uni) r = rL;
+            // ---- Taylor coefficients of the phase about the centre: t_n = sum_i a_i c[i][n]
+            const double* sc = s_c + (size_t)(b - b0) * NPH * TAB_NTP;
+            double tq[TAB_NT];
+#pragma unroll
+            for (int n = 0; n < TAB_NT; ++n) tq[n] = 0.0;
+#pragma unroll
+            for (int i = 0; i < NPH; ++i) {
+#pragma unroll
+                for (int n = 0; n < TAB_NT; ++n) tq[n] = fma(a[i], sc[i * TAB_NTP + n], tq[n]);
+            }
+            // ---- e_n: Taylor coefficients of exp(U), U = i sum_{k=2..8} w_k s^k, w_k = -2 pi (t_k - t_k^ref):
+            //   n e_n = sum_k k (i w_k) e_{n-k};  e_0 = 1, e_1 = 0 (nu carries the slope)
+            const double* tr = tref + ((size_t)B.pair0 + r) * TAB_NTP;
+            double kw[TAB_DEG + 1];
+            double rho = 0.0;
+#pragma unroll
+            for (int k = 2; k <= TAB_DEG; ++k) {
+                const double dt = tq[k] - __ldg(tr + k);
+                kw[k] = -G_TWOPI * (double)k * dt;
+                rho += fabs(dt);
+            }
+            double2 en[TAB_DEG + 3];
+            en[0] = make_double2(1.0, 0.0);
+            en[1] = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int n = 2; n <= TAB_DEG + 2; ++n) {
+                double re = 0.0, im = 0.0;
+#pragma unroll
+                for (int k = 2; k <= TAB_DEG; ++k) {
+                    if (k <= n) {
+                        re = fma(-kw[k], en[n - k].y, re);
+                        im = fma(kw[k], en[n - k].x, im);
+                    }
+                }
+                en[n] = make_double2(re * (1.0 / n), im * (1.0 / n));
+            }
             {
-                // ---- whole sub-block from the tables (lanes with act = false compute along and
-                // drop the result: the staging below is a warp-wide operation)
-                const double h = 0.5 * (double)m;
-                const double thc = phase_turns(pc, ld_basis(P.basis + s + M->node[TAB_PH / 2]));
-                double v_[TAB_PH];
-#pragma unroll
-                for (int i = 0; i < TAB_PH; ++i)
-                    v_[i] = phase_turns(pc, ld_basis(P.basis + s + M->node[i < TAB_PH / 2 ? i : i + 1])) - thc;
-                if (tab_ref) {                   // phase relative to the reference waveform's non-linear part
-#pragma unroll
-                    for (int i = 0; i < TAB_PH; ++i)
-                        v_[i] -= tab_ref[(size_t)b * TAB_REFN + 2 + (i < TAB_PH / 2 ? i : i + 1)];
+                // what the degree-TAB_DEG polynomial leaves out at the sub-block's edge: e_9, e_10, and
+                // the phase's own ninth/tenth-order terms (a power law's Taylor coefficients fall off by
+                // less than 1.2 eps per order)
+                const double u8 = fabs(kw[TAB_DEG]) * (1.0 / TAB_DEG);
+                const double est = fabs(en[TAB_DEG + 1].x) + fabs(en[TAB_DEG + 1].y)
+                                 + fabs(en[TAB_DEG + 2].x) + fabs(en[TAB_DEG + 2].y)
+                                 + 1.2 * B.eps * u8 * (1.0 + 1.2 * B.eps);
+                if (act && (est > TAB_EST_MAX || G_TWOPI * rho > TAB_RHO_MAX)) {
+                    slow[t] = 1;                        // outside what the tables were built for: slow path
+                    dead = true;
+                    act = false;
                 }
-                double tq[TAB_PH];               // t_1..t_6: Theta - th_c = sum t_i (j/h)^i [turns]
+            }
+            const double h = 0.5 * (double)m;
+            const double kc = (double)(s + m / 2);
+            const double2* row0 = tab + B.off;
+            // Every lane's 13 taps x 128 B live within a few grid points of each other (the
+            // walkers' local times differ by less than the grid spacing times a few): the warp
+            // copies the union of the rows to shared memory with cp.async (one L2 round trip per
+            // sub-block instead of one per tap group), then each lane reads its taps from there.
+            double xs[ND];
+            int gs[ND], lo[ND];
+            bool staged[ND];
+            __syncwarp();                           // the previous sub-block's rows have been read
 #pragma unroll
-                for (int i = 0; i < TAB_PH; ++i) {
-                    double a = 0.0;
+            for (int d = 0; d < ND; ++d) {
+                const double nu = tq[1] / h + (tau_hi[d] + tau_lo[d]);    // turns per bin
+                xs[d] = (nu - floor(nu)) * (double)L;                     // [0, L)
+                const int g0 = (int)ceil(xs[d] - 0.5 * TAB_W);            // -6 .. L - 6
+                gs[d] = g0 < 0 ? g0 + L : g0;
+                xs[d] = 2.0 * (xs[d] - (double)g0) - (double)(TAB_W - 1); // v: the Horner variable
+                int mn = act ? gs[d] : 0x7fffffff, mx = act ? gs[d] : -1;
 #pragma unroll
-                    for (int j = 0; j < TAB_PH; ++j) a = fma(M->c[TAB_PH * i + j], v_[j], a);
-                    tq[i] = a;
+                for (int o = 16; o; o >>= 1) {
+                    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
                 }
-                // Taylor coefficients e_n of exp(U), U = i sum_{k=2..6} w_k s^k, w_k = -2 pi t_k:
-                //   n e_n = sum_k k (i w_k) e_{n-k};  e_0 = 1, e_1 = 0 (nu carries the slope)
-                double kw[TAB_PH + 1];
-                double rho = 0.0;
-#pragma unroll
-                for (int k = 2; k <= TAB_PH; ++k) { kw[k] = -G_TWOPI * (double)k * tq[k - 1]; rho += fabs(tq[k - 1]); }
-                // a walker outside the range the schedule was built for (only possible with a
-                // reference waveform): the truncated series would be wrong -- report it
-                if (tab_ref && act && G_TWOPI * rho > 2.0 * TAB_RHO) atomicOr(violation, 1);
-                double2 en[TAB_DEG + 1];
-                en[0] = make_double2(1.0, 0.0);
-                en[1] = make_double2(0.0, 0.0);
-#pragma unroll
-                for (int n = 2; n <= TAB_DEG; ++n) {
-                    double re = 0.0, im = 0.0;
-#pragma unroll
-                    for (int k = 2; k <= TAB_PH; ++k) {
-                        if (k <= n) {
-                            re = fma(-kw[k], en[n - k].y, re);
-                            im = fma(kw[k], en[n - k].x, im);
-                        }
-                    }
-                    en[n] = make_double2(re * (1.0 / n), im * (1.0 / n));
-                }
-                const double kc = (double)(s + m / 2);
-                const double2* row0 = tab + tab_off[b];
-                // Every lane's 13 taps x 128 B live within a few grid points of each other (the
-                // walkers' local times differ by less than the grid spacing times a few): the warp
-                // copies the union of the rows to shared memory with cp.async (one L2 round trip per
-                // sub-block instead of one per tap group), then each lane reads its taps from there.
-                double xs[ND];
-                int gs[ND], lo[ND];
-                bool staged[ND];
-                __syncwarp();                           // the previous sub-block's rows have been read
-#pragma unroll
-                for (int d = 0; d < ND; ++d) {
-                    const double nu = tq[0] / h + (tau_hi[d] + tau_lo[d]);    // turns per bin
-                    xs[d] = (nu - floor(nu)) * (double)L;                     // [0, L)
-                    const int g0 = (int)ceil(xs[d] - 0.5 * TAB_W);            // -6 .. L - 6
-                    gs[d] = g0 < 0 ? g0 + L : g0;
-                    xs[d] = 2.0 * (xs[d] - (double)g0) - (double)(TAB_W - 1); // v: the Horner variable
-                    int mn = act ? gs[d] : 0x7fffffff, mx = act ? gs[d] : -1;
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) {
-                        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-                        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                    }
-                    lo[d] = mn;
-                    const int span = mx - mn + TAB_W;
-                    staged[d] = span <= TAB_SPAN;
-                    if (staged[d]) {
-                        const double2* src = row0 + ((size_t)d * (L + TAB_W) + mn) * TAB_NM;
-                        const uint32_t dst = smem_u32(s_warp + (size_t)d * TAB_SPAN * TAB_ROWB);
-                        for (int pc16 = lane; pc16 < span * TAB_NM; pc16 += WARP) {
-                            const int r = pc16 / TAB_NM, c16 = pc16 % TAB_NM;
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
-                                         :: "r"(dst + (uint32_t)(r * TAB_ROWB + c16 * 16)), "l"(src + pc16) : "memory");
-                        }
+                lo[d] = mn;
+                const int span = mx - mn + TAB_W;
+                staged[d] = uni && mx >= 0 && span <= TAB_SPAN;
+                if (staged[d]) {
+                    const double2* src = row0 + (((size_t)rL * ND + d) * (L + TAB_W) + mn) * TAB_NM;
+                    const uint32_t dst = smem_u32(s_warp + (size_t)d * TAB_SPAN * TAB_ROWB);
+                    for (int pc16 = lane; pc16 < span * TAB_NM; pc16 += WARP) {
+                        const int rr = pc16 / TAB_NM, c16 = pc16 % TAB_NM;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                                     :: "r"(dst + (uint32_t)(rr * TAB_ROWB + c16 * 16)), "l"(src + pc16) : "memory");
                     }
                 }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                bool waited = false;
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            bool waited = false;
 #pragma unroll
-                for (int d = 0; d < ND; ++d) {
-                    double2 Mn[TAB_NM];
+            for (int d = 0; d < ND; ++d) {
+                double2 Mn[TAB_NM];
 #pragma unroll
-                    for (int n = 0; n < TAB_NM; ++n) Mn[n] = make_double2(0.0, 0.0);
-                    // rows are padded with TAB_W wrap-around points: the taps are contiguous
-                    const double2* rd = row0 + ((size_t)d * (L + TAB_W) + gs[d]) * TAB_NM;
-                    const unsigned char* sd = s_warp + ((size_t)d * TAB_SPAN + (act ? gs[d] - lo[d] : 0)) * TAB_ROWB;
-                    const double v = xs[d];
-                    // kernel weights: 13 independent Horner chains in v = 2 (x - g0) - (W - 1)
-                    // (the opaque zero keeps the compiler from hoisting all 208 coefficients into
-                    //  registers across the detector / sub-block loops)
-                    int opq = 0;
-                    asm volatile("" : "+r"(opq));
-                    const double (*cp)[TAB_PDEG + 1] = c_tab_poly + opq;
-#pragma unroll 1
-                    for (int i0 = 0; i0 < TAB_W; i0 += TAB_GROUP) {
-                        double wt[TAB_GROUP];
+                for (int n = 0; n < TAB_NM; ++n) Mn[n] = make_double2(0.0, 0.0);
+                // rows are padded with TAB_W wrap-around points: the taps are contiguous
+                const double2* rd = row0 + (((size_t)r * ND + d) * (L + TAB_W) + gs[d]) * TAB_NM;
+                const unsigned char* sd = s_warp + ((size_t)d * TAB_SPAN + (act ? gs[d] - lo[d] : 0)) * TAB_ROWB;
+                const double v = xs[d];
+                // kernel weights: 13 independent Horner chains in v = 2 (x - g0) - (W - 1), coefficients
+                // as literal constants (constant-bank operands, no loads)
+                double wt[TAB_W];
+                wt[0] = TAB_TAP_0(v); wt[1] = TAB_TAP_1(v); wt[2] = TAB_TAP_2(v); wt[3] = TAB_TAP_3(v);
+                wt[4] = TAB_TAP_4(v); wt[5] = TAB_TAP_5(v); wt[6] = TAB_TAP_6(v); wt[7] = TAB_TAP_7(v);
+                wt[8] = TAB_TAP_8(v); wt[9] = TAB_TAP_9(v); wt[10] = TAB_TAP_10(v); wt[11] = TAB_TAP_11(v);
+                wt[12] = TAB_TAP_12(v);
+                if (!waited) {                       // the weights above overlapped the copies
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncwarp();
+                    waited = true;
+                }
+                if (staged[d]) {
 #pragma unroll
-                        for (int i = 0; i < TAB_GROUP; ++i) wt[i] = cp[min(i0 + i, TAB_W - 1)][TAB_PDEG];
+                    for (int i = 0; i < TAB_W; ++i) {
+                        const double2* e = reinterpret_cast<const double2*>(sd + i * TAB_ROWB);
 #pragma unroll
-                        for (int k = TAB_PDEG - 1; k >= 0; --k) {
-#pragma unroll
-                            for (int i = 0; i < TAB_GROUP; ++i) wt[i] = fma(wt[i], v, cp[min(i0 + i, TAB_W - 1)][k]);
-                        }
-                        if (!waited) {                   // the weights above overlapped the copies
-                            asm volatile("cp.async.wait_group 0;" ::: "memory");
-                            __syncwarp();
-                            waited = true;
-                        }
-                        if (staged[d]) {
-#pragma unroll
-                            for (int i = 0; i < TAB_GROUP; ++i) {
-                                if (i0 + i < TAB_W) {
-                                    const double2* e = reinterpret_cast<const double2*>(sd + (i0 + i) * TAB_ROWB);
-#pragma unroll
-                                    for (int n = 0; n < TAB_NM; ++n) {
-                                        const double2 q = e[n];
-                                        Mn[n].x = fma(wt[i], q.x, Mn[n].x);
-                                        Mn[n].y = fma(wt[i], q.y, Mn[n].y);
-                                    }
-                                }
-                            }
-                        } else if (act) {                // lanes too far apart in time: straight from L2
-#pragma unroll
-                            for (int i = 0; i < TAB_GROUP; ++i) {
-                                if (i0 + i < TAB_W) {
-                                    const double2* e = rd + (i0 + i) * TAB_NM;
-#pragma unroll
-                                    for (int n = 0; n < TAB_NM; ++n) {
-                                        const double2 q = __ldg(e + n);
-                                        Mn[n].x = fma(wt[i], q.x, Mn[n].x);
-                                        Mn[n].y = fma(wt[i], q.y, Mn[n].y);
-                                    }
-                                }
-                            }
+                        for (int n = 0; n < TAB_NM; ++n) {
+                            const double2 q = e[n];
+                            Mn[n].x = fma(wt[i], q.x, Mn[n].x);
+                            Mn[n].y = fma(wt[i], q.y, Mn[n].y);
                         }
                     }
-                    // sum_n e_n M_n; Mn[] holds n = 0, 2, 3, .. TAB_DEG
-                    double2 sum = Mn[0];
+                } else if (act) {                    // lanes too far apart (in time or in a0): straight from L2
 #pragma unroll
-                    for (int n = 2; n <= TAB_DEG; ++n) sum = cfma(en[n], Mn[n - 1], sum);
-                    const double th0 = thc + fma(kc, tau_lo[d], frac1(kc * tau_hi[d]));
-                    if (act) acc[d] = cfma(sum, phasor_neg(th0), acc[d]);
+                    for (int i = 0; i < TAB_W; ++i) {
+                        const double2* e = rd + i * TAB_NM;
+#pragma unroll
+                        for (int n = 0; n < TAB_NM; ++n) {
+                            const double2 q = __ldg(e + n);
+                            Mn[n].x = fma(wt[i], q.x, Mn[n].x);
+                            Mn[n].y = fma(wt[i], q.y, Mn[n].y);
+                        }
+                    }
                 }
+                // sum_n e_n M_n; Mn[] holds n = 0, 2, 3, .. TAB_DEG
+                double2 sum = Mn[0];
+#pragma unroll
+                for (int n = 2; n <= TAB_DEG; ++n) sum = cfma(en[n], Mn[n - 1], sum);
+                const double th0 = tq[0] + fma(kc, tau_lo[d], frac1(kc * tau_hi[d]));
+                if (act) acc[d] = cfma(sum, phasor_neg(th0), acc[d]);
             }
         }
     }
@@ -1463,6 +1656,50 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
         for (int d = 0; d < ND; ++d)
             partial[((size_t)chunk * ND + d) * wpad + t] = acc[d];
     }
+}
+
+// Tails of the table path.  Walkers are taken in the order of their last bin (col = perm_e[t]); the
+// 128 walkers of a CTA then need only a short run of recurrence blocks: grp_b[g] .. grp_b[groups + g].
+__global__ void __launch_bounds__(CTA_THREADS)
+tail_plan_kernel(int W, int n_blk, const int* __restrict__ blk_start, const int* __restrict__ perm_e,
+                 const int* __restrict__ ks_tail, const int* __restrict__ ke_fast, int* __restrict__ grp_b) {
+    __shared__ int s_lo[CTA_THREADS / WARP], s_hi[CTA_THREADS / WARP];
+    const int t = blockIdx.x * CTA_THREADS + threadIdx.x;
+    int lo = 0x7fffffff, hi = 0;
+    if (t < W) {
+        const int col = perm_e[t];
+        const int a = ks_tail[col], e = ke_fast[col];
+        if (a >= 0 && a < e) { lo = a; hi = e; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x / WARP] = lo; s_hi[threadIdx.x / WARP] = hi; }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    for (int i = 1; i < CTA_THREADS / WARP; ++i) { lo = min(lo, s_lo[i]); hi = max(hi, s_hi[i]); }
+    int b_lo = 0, b_hi = 0;
+    if (lo < hi) {
+        int x = 0, y = n_blk - 1;                       // last block starting at or below lo
+        while (x < y) { const int mid = (x + y + 1) >> 1; if (blk_start[mid] <= lo) x = mid; else y = mid - 1; }
+        b_lo = x;
+        x = b_lo; y = n_blk;                            // first boundary at or above hi
+        while (x < y) { const int mid = (x + y) >> 1; if (blk_start[mid] >= hi) y = mid; else x = mid + 1; }
+        b_hi = x;
+    }
+    grp_b[blockIdx.x] = b_lo;
+    grp_b[gridDim.x + blockIdx.x] = b_hi;
+}
+
+// Slow path: the list of walkers (columns) the fast kernels did not take.
+__global__ void slow_compact_kernel(int W, const unsigned char* __restrict__ slow, int* __restrict__ list,
+                                    int* __restrict__ n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= W || !slow[t]) return;
+    list[atomicAdd(n, 1)] = t;
+    atomicAdd(n + 1, 1);
 }
 
 // ---------------------------------------------------------------------------
@@ -1479,6 +1716,40 @@ __device__ __forceinline__ double log_i0(double x) {
     return x - 0.5 * log(G_TWOPI * x) + log(ser);
 }
 
+// One walker's result from its per-detector sums: scale by the walker amplitude, form loglr, scatter
+// to the caller's walker order.
+__device__ __forceinline__ void finish_walker(int n_det, int wpad, int mode, int t, int w, bool invalid,
+                                              const double2* __restrict__ sums, const double* __restrict__ wc,
+                                              const double* __restrict__ hh_sorted,
+                                              double* __restrict__ loglr, double* __restrict__ hd_out,
+                                              double* __restrict__ hh_out, double* __restrict__ marg_opt) {
+    double lr = 0.0, sre = 0.0, sim = 0.0, shh = 0.0;
+    for (int d = 0; d < n_det; ++d) {
+        const double re = sums[d].x, im = sums[d].y;
+        const double* row = wc + (size_t)(C_DET0 + D_NROW * d) * wpad + t;
+        const double are = row[D_ARE * wpad], aim = row[D_AIM * wpad];
+        const double hre = are * re - aim * im;
+        const double him = are * im + aim * re;
+        const double hh = hh_sorted[d * wpad + t];
+        if (hd_out) {
+            hd_out[((size_t)w * n_det + d) * 2 + 0] = invalid ? 0.0 : hre;
+            hd_out[((size_t)w * n_det + d) * 2 + 1] = invalid ? 0.0 : him;
+        }
+        if (hh_out) hh_out[(size_t)w * n_det + d] = invalid ? 0.0 : hh;
+        lr += hre - 0.5 * hh;
+        sre += hre; sim += him; shh += hh;
+    }
+    if (mode == GWIN_MODE_MARG_PHASE) lr = log_i0(hypot(sre, sim)) - 0.5 * shh;
+    if (mode >= GWIN_MODE_MARG_DIST) {
+        // hand (x, opt) to marg_dist_kernel: x travels in loglr[w]
+        const double mf = hypot(sre, sim);
+        lr = mode == GWIN_MODE_MARG_DIST ? mf : log_i0(mf);
+        marg_opt[w] = shh;
+    }
+    if (invalid || isnan(lr)) lr = -INFINITY;
+    loglr[w] = lr;
+}
+
 #define COMB_SEG 16     // chunk segments summed in parallel per walker (fixed order: deterministic)
 __global__ void __launch_bounds__(32 * COMB_SEG)
 combine_kernel(int n_det, int W, int wpad, int n_chunks, int mode,
@@ -1489,10 +1760,9 @@ combine_kernel(int n_det, int W, int wpad, int n_chunks, int mode,
                const double* __restrict__ hh_sorted,
                double* __restrict__ loglr, double* __restrict__ hd_out,
                double* __restrict__ hh_out, double* __restrict__ marg_opt,
-               int n_chunks2, int per_chunk2, const int* __restrict__ tab_start,
+               int n_chunks2, int per_chunk2, const TabBlk* __restrict__ tblk,
                const double2* __restrict__ partial2, const int* __restrict__ ke2_arr,
-               int n_chunks3, int per_chunk3, int n_blk3, const int* __restrict__ blk_start3,
-               const int* __restrict__ ks3_arr, const double2* __restrict__ partial3) {
+               int n_chunks3, const double2* __restrict__ partial3) {
     __shared__ double2 s_part[COMB_SEG][GWIN_MAX_DET][32];
     const int lx = threadIdx.x, seg = threadIdx.y;
     const int t = blockIdx.x * 32 + lx;
@@ -1516,15 +1786,13 @@ combine_kernel(int n_det, int W, int wpad, int n_chunks, int mode,
         if (live && n_chunks2 > 0) {
             const int ke2 = ke2_arr[t];
             for (int c = seg; c < n_chunks2; c += COMB_SEG) {
-                if (tab_start[c * per_chunk2] >= ke2) continue;
+                if (tblk[c * per_chunk2].start >= ke2) continue;
                 const double2 p = partial2[((size_t)c * n_det + d) * wpad + t];
                 re += p.x; im += p.y;
             }
-            // tail [ks3, ke2): the sub-block holding the walker's last bin, done by the recurrence kernel
-            const int ks3 = ks3_arr[t];
+            // the tail between the last whole sub-block and the walker's last bin, done by the second
+            // pass of the recurrence kernel: every slot is written
             for (int c = seg; c < n_chunks3; c += COMB_SEG) {
-                const int k0 = blk_start3[c * per_chunk3], k1 = blk_start3[min((c + 1) * per_chunk3, n_blk3)];
-                if (max(k0, ks3) >= min(k1, ke2)) continue;
                 const double2 p = partial3[((size_t)c * n_det + d) * wpad + t];
                 re += p.x; im += p.y;
             }
@@ -1534,35 +1802,44 @@ combine_kernel(int n_det, int W, int wpad, int n_chunks, int mode,
     __syncthreads();
     if (seg != 0 || !live) return;
     // stage 2: one thread per walker finishes
-    const int w = perm ? perm[t] : t;
-    const bool invalid = ks_arr[t] < 0;
-    double lr = 0.0, sre = 0.0, sim = 0.0, shh = 0.0;
+    double2 sums[GWIN_MAX_DET];
     for (int d = 0; d < n_det; ++d) {
         double re = 0.0, im = 0.0;
 #pragma unroll
         for (int q = 0; q < COMB_SEG; ++q) { re += s_part[q][d][lx].x; im += s_part[q][d][lx].y; }
-        const double* row = wc + (size_t)(C_DET0 + D_NROW * d) * wpad + t;
-        const double are = row[D_ARE * wpad], aim = row[D_AIM * wpad];
-        const double hre = are * re - aim * im;
-        const double him = are * im + aim * re;
-        const double hh = hh_sorted[d * wpad + t];
-        if (hd_out) {
-            hd_out[((size_t)w * n_det + d) * 2 + 0] = invalid ? 0.0 : hre;
-            hd_out[((size_t)w * n_det + d) * 2 + 1] = invalid ? 0.0 : him;
+        sums[d] = make_double2(re, im);
+    }
+    finish_walker(n_det, wpad, mode, t, perm ? perm[t] : t, ks_arr[t] < 0, sums, wc, hh_sorted,
+                  loglr, hd_out, hh_out, marg_opt);
+}
+
+// Slow path: the direct kernel's chunk sums of the listed walkers, in chunk order; overwrites what
+// combine_kernel wrote for them.
+__global__ void slow_finish_kernel(int n_det, int wpad, int n_chunks, int mode, int per_chunk, int band0, int kmax,
+                                   const int* __restrict__ perm, const double* __restrict__ wc,
+                                   const int* __restrict__ ks_arr, const int* __restrict__ ke_arr,
+                                   const double2* __restrict__ partial, const double* __restrict__ hh_sorted,
+                                   const int* __restrict__ list, const int* __restrict__ n_list,
+                                   double* __restrict__ loglr, double* __restrict__ hd_out,
+                                   double* __restrict__ hh_out, double* __restrict__ marg_opt) {
+    const int n = *n_list;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int t = list[i];
+        const int ks = ks_arr[t], ke = ke_arr[t];
+        double2 sums[GWIN_MAX_DET];
+        for (int d = 0; d < n_det; ++d) {
+            double re = 0.0, im = 0.0;
+            for (int c = 0; c < n_chunks; ++c) {
+                const int k0 = band0 + c * per_chunk, k1 = min(k0 + per_chunk, kmax);
+                if (max(k0, ks) >= min(k1, ke)) continue;
+                const double2 p = partial[((size_t)c * n_det + d) * wpad + i];
+                re += p.x; im += p.y;
+            }
+            sums[d] = make_double2(re, im);
         }
-        if (hh_out) hh_out[(size_t)w * n_det + d] = invalid ? 0.0 : hh;
-        lr += hre - 0.5 * hh;
-        sre += hre; sim += him; shh += hh;
+        finish_walker(n_det, wpad, mode, t, perm ? perm[t] : t, false, sums, wc, hh_sorted,
+                      loglr, hd_out, hh_out, marg_opt);
     }
-    if (mode == GWIN_MODE_MARG_PHASE) lr = log_i0(hypot(sre, sim)) - 0.5 * shh;
-    if (mode >= GWIN_MODE_MARG_DIST) {
-        // hand (x, opt) to marg_dist_kernel: x travels in loglr[w]
-        const double mf = hypot(sre, sim);
-        lr = mode == GWIN_MODE_MARG_DIST ? mf : log_i0(mf);
-        marg_opt[w] = shh;
-    }
-    if (invalid || isnan(lr)) lr = -INFINITY;
-    loglr[w] = lr;
 }
 
 // ---------------------------------------------------------------------------
@@ -1798,54 +2075,18 @@ static int upload_schedule(gwin_plan* p) {
 }
 
 
-// ---- table kernel: schedule + moment tables -------------------------------------------------
-// Admissible sub-block lengths (2^k and 3 2^(k-1) in [TAB_MIN, TAB_MAX]), their phase-polynomial
-// nodes (rounded Chebyshev-Lobatto points, the centre moved to m/2) and the worst value of
-// |prod_i (j - x_i)| over the sub-block (the interpolation error factor).
-struct TabSize { int m; int node[TAB_PH + 1]; double omega; };
-static const std::vector<TabSize>& table_sizes() {
-    static const std::vector<TabSize> sizes = [] {        // thread-safe one-time initialisation
-        std::vector<TabSize> v;
-        for (int m = TAB_MIN; m <= TAB_MAX; m *= 2)
-            for (int half = 0; half < 2; ++half) {
-                TabSize S;
-                S.m = half ? m + m / 2 : m;
-                if (S.m > TAB_MAX) continue;
-                for (int i = 0; i <= TAB_PH; ++i)
-                    S.node[i] = (int)lround((S.m - 1) * 0.5 * (1.0 - cos(G_PI * i / TAB_PH)));
-                S.node[TAB_PH / 2] = S.m / 2;
-                S.omega = 0.0;
-                for (int j = 0; j < S.m; ++j) {
-                    double prod = 1.0;
-                    for (int i = 0; i <= TAB_PH; ++i) prod *= (double)(j - S.node[i]);
-                    S.omega = std::max(S.omega, std::fabs(prod));
-                }
-                v.push_back(S);
-            }
-        std::sort(v.begin(), v.end(), [](const TabSize& a, const TabSize& b) { return a.m < b.m; });
+// ---- table kernel: coverage, schedule, moment tables ------------------------------------------
+static const std::vector<int>& table_sizes() {            // 2^k and 3 2^(k-1) in [TAB_MIN, TAB_MAX]
+    static const std::vector<int> sizes = [] {
+        std::vector<int> v;
+        for (int m = TAB_MIN; m <= TAB_MAX; m *= 2) {
+            v.push_back(m);
+            if (m + m / 2 <= TAB_MAX) v.push_back(m + m / 2);
+        }
+        std::sort(v.begin(), v.end());
         return v;
     }();
     return sizes;
-}
-
-// Longest admissible sub-block starting at bin k (index into table_sizes(), -1: none): |R| <= TAB_RHO
-// at its edge and the degree-TAB_PH interpolation of the phase good to phase_tol, for the leading-order
-// chirp of the smallest chirp mass (x2 safety for the higher PN orders, as in build_schedule).
-static int table_block_size(const gwin_plan* p, int k, double chirp) {
-    const PlanDev& d = p->d;
-    const double f = k * d.delta_f;
-    double K2 = 1.0, Kn = 1.0, fact = 1.0;
-    for (int i = 0; i < 2; ++i) K2 *= 5.0 / 3 + i;
-    for (int i = 0; i <= TAB_PH; ++i) { Kn *= 5.0 / 3 + i; fact *= i + 1; }
-    const double d2 = chirp * K2 * d.delta_f * d.delta_f * pow(f, -5.0 / 3 - 2);                     // rad / bin^2
-    const double dn = chirp * Kn * pow(d.delta_f, TAB_PH + 1.0) * pow(f, -5.0 / 3 - (TAB_PH + 1));   // rad / bin^7
-    const std::vector<TabSize>& sizes = table_sizes();
-    int best = -1;
-    for (size_t i = 0; i < sizes.size(); ++i) {
-        const double hh = 0.5 * sizes[i].m;
-        if (0.5 * d2 * hh * hh <= TAB_RHO && dn / fact * sizes[i].omega <= p->phase_tol) best = (int)i;
-    }
-    return best;
 }
 
 static double es_kernel_host(long double x) {
@@ -1854,214 +2095,321 @@ static double es_kernel_host(long double x) {
     return (double)expl((long double)TAB_BETA * (sqrtl(1.0L - z * z) - 1.0L));
 }
 
-// Piecewise-polynomial form of the interpolation kernel (as in FINUFFT): with g0 = ceil(x - W/2)
-// and u = x - g0 - (W - 1)/2 in (-1/2, 1/2], tap i sits at distance u + (W - 1)/2 - i; on that unit
-// interval phi is smooth (its only singularity, at the edge of the support, has magnitude
-// e^-beta ~ 1e-13) and is replaced by its degree-TAB_PDEG Chebyshev interpolant, stored in
-// monomials of v = 2u for Horner evaluation with constant-bank operands.
-static int upload_tab_poly() {
-    static bool done[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && done[dev]) return GWIN_OK;
-    const int n = TAB_PDEG + 1;
-    const long double pi = 3.14159265358979323846264338327950288L;
-    double out[TAB_W][TAB_PDEG + 1];
-    for (int i = 0; i < TAB_W; ++i) {
-        long double fv[TAB_PDEG + 1], cheb[TAB_PDEG + 1];
-        for (int q = 0; q < n; ++q) {
-            const long double v = cosl(pi * (q + 0.5L) / n);            // Chebyshev nodes in (-1, 1)
-            fv[q] = es_kernel_host(0.5L * v + 0.5L * (TAB_W - 1) - i);
+// 1 / phi_hat(j_c / L), j_c = j - m/2, phi_hat by midpoint quadrature of the interpolation kernel over
+// its support (depends on m only: computed once per process)
+static const std::vector<double>& inv_hat(int m) {
+    static std::vector<double> cache[64];
+    static std::mutex mtx;
+    std::lock_guard<std::mutex> lock(mtx);
+    const std::vector<int>& sizes = table_sizes();
+    const size_t si = std::find(sizes.begin(), sizes.end(), m) - sizes.begin();
+    std::vector<double>& hc = cache[si];
+    if (hc.empty()) {
+        const int nq = 2048, L = 2 * m;
+        std::vector<long double> xs(nq), ph(nq);
+        for (int q = 0; q < nq; ++q) {
+            xs[q] = ((long double)q + 0.5L) / nq * TAB_W - 0.5L * TAB_W;
+            ph[q] = es_kernel_host(xs[q]);
         }
-        for (int k = 0; k < n; ++k) {
+        hc.resize(m);
+        for (int j = 0; j < m; ++j) {
+            const long double xi = (long double)(j - m / 2) / L;
             long double sum = 0.0L;
-            for (int q = 0; q < n; ++q) sum += fv[q] * cosl(pi * k * (q + 0.5L) / n);
-            cheb[k] = sum * (k == 0 ? 1.0L : 2.0L) / n;
+            for (int q = 0; q < nq; ++q) sum += ph[q] * cosl(2.0L * 3.14159265358979323846264338327950288L * xi * xs[q]);
+            hc[j] = (double)(1.0L / (sum * TAB_W / nq));
         }
-        // Chebyshev -> monomial: T_0 = 1, T_1 = v, T_{k+1} = 2 v T_k - T_{k-1}
-        long double mono[TAB_PDEG + 1] = {0}, tkm[TAB_PDEG + 1] = {0}, tk[TAB_PDEG + 1] = {0};
-        tkm[0] = 1.0L; tk[1] = 1.0L;
-        for (int q = 0; q < n; ++q) mono[q] += cheb[0] * tkm[q];
-        if (n > 1) for (int q = 0; q < n; ++q) mono[q] += cheb[1] * tk[q];
-        for (int k = 2; k < n; ++k) {
-            long double tn[TAB_PDEG + 1] = {0};
-            for (int q = 0; q < n; ++q) {
-                if (q > 0) tn[q] += 2.0L * tk[q - 1];
-                tn[q] -= tkm[q];
-            }
-            for (int q = 0; q < n; ++q) { mono[q] += cheb[k] * tn[q]; tkm[q] = tk[q]; tk[q] = tn[q]; }
-        }
-        for (int q = 0; q < n; ++q) out[i][q] = (double)mono[q];
     }
-    CK(cudaMemcpyToSymbol(c_tab_poly, out, sizeof out));
-    if (dev >= 0 && dev < 64) done[dev] = true;
-    return GWIN_OK;
+    return hc;
 }
 
-static TabMat make_tab_mat(const TabSize& S, int hat_off) {
-    TabMat M;
-    memset(&M, 0, sizeof M);
-    const int m = S.m;
-    M.m = m; M.hat_off = hat_off;
-    for (int i = 0; i <= TAB_PH; ++i) M.node[i] = S.node[i];
-    // t_i, i = 1..TAB_PH, from v_j = th(x_j) - th(centre), j over the off-centre nodes:
-    // sum_i t_i s_j^i = v_j with s_j = (x_j - m/2) / (m/2)
-    const int n = TAB_PH;
-    long double A[TAB_PH][2 * TAB_PH];
-    for (int r = 0; r < n; ++r) {
-        const int xi = S.node[r < n / 2 ? r : r + 1];
-        const long double sj = ((long double)xi - m / 2) / (0.5L * m);
-        long double pw = sj;
-        for (int c = 0; c < n; ++c) { A[r][c] = pw; pw *= sj; }
-        for (int c = 0; c < n; ++c) A[r][n + c] = (r == c) ? 1.0L : 0.0L;
-    }
-    for (int c = 0; c < n; ++c) {                      // Gauss-Jordan with partial pivoting
-        int piv = c;
-        for (int r = c + 1; r < n; ++r) if (fabsl(A[r][c]) > fabsl(A[piv][c])) piv = r;
-        for (int q2 = 0; q2 < 2 * n; ++q2) std::swap(A[c][q2], A[piv][q2]);
-        const long double inv = 1.0L / A[c][c];
-        for (int q2 = 0; q2 < 2 * n; ++q2) A[c][q2] *= inv;
-        for (int r = 0; r < n; ++r) {
-            if (r == c) continue;
-            const long double f = A[r][c];
-            for (int q2 = 0; q2 < 2 * n; ++q2) A[r][q2] -= f * A[c][q2];
+// Taylor coefficients, in s = (k - kc) / h, of the 11 functions of f the TaylorF2 phase is made of
+// (the order of the C_A* rows): x^p for p = -5, -3, -2, -1, 0, (ln x), 1, (x ln x), 2, 5, 7, x = f^(1/3).
+static void taylor_matrix(double kc, double h, double delta_f, long double c[NPH][TAB_NTH]) {
+    static const int pw[NPH] = {-5, -3, -2, -1, 0, 0, 1, 1, 2, 5, 7};
+    static const int lg[NPH] = {0, 0, 0, 0, 0, 1, 0, 1, 0, 0, 0};
+    const long double fc = (long double)kc * (long double)delta_f, eps = (long double)h / (long double)kc;
+    long double ls[TAB_NTH];                               // ln x = ln(fc)/3 + ln(1 + eps s)/3
+    ls[0] = logl(fc) / 3.0L;
+    long double en = 1.0L;
+    for (int n = 1; n < TAB_NTH; ++n) { en *= eps; ls[n] = ((n & 1) ? en : -en) / n / 3.0L; }
+    for (int i = 0; i < NPH; ++i) {
+        const long double q = (long double)pw[i] / 3.0L;
+        long double bs[TAB_NTH];                           // fc^q (1 + eps s)^q
+        bs[0] = powl(fc, q);
+        for (int n = 0; n + 1 < TAB_NTH; ++n) bs[n + 1] = bs[n] * (q - n) / (n + 1) * eps;
+        for (int n = 0; n < TAB_NTH; ++n) {
+            if (!lg[i]) { c[i][n] = bs[n]; continue; }
+            long double acc = 0.0L;
+            for (int k = 0; k <= n; ++k) acc += bs[k] * ls[n - k];
+            c[i][n] = acc;
         }
     }
-    for (int i = 0; i < n; ++i)
-        for (int j = 0; j < n; ++j) M.c[n * i + j] = (double)A[i][n + j];
-    return M;
+}
+
+// Majorant of what the degree-TAB_DEG polynomial of e^{-2 pi i R} drops, for a walker da_half away (in
+// a0) from its reference chirp and dev[i] away in the other phase coefficients.
+static bool table_admissible(const long double c[NPH][TAB_NTH], const double* dev, double da_half) {
+    long double u[TAB_NTH], e[TAB_NTH];
+    long double rho = 0.0L;
+    for (int k = 2; k < TAB_NTH; ++k) {
+        long double acc = (long double)da_half * fabsl(c[0][k]);
+        for (int i = 1; i < NPH; ++i) acc += (long double)dev[i] * fabsl(c[i][k]);
+        u[k] = 2.0L * 3.14159265358979323846264338327950288L * acc;
+        if (k <= TAB_DEG) rho += u[k];
+    }
+    e[0] = 1.0L; e[1] = 0.0L;
+    long double est = 0.0L;
+    for (int n = 2; n < TAB_NTH; ++n) {
+        long double acc = 0.0L;
+        for (int k = 2; k <= n; ++k) acc += k * u[k] * e[n - k];
+        e[n] = acc / n;
+        if (n > TAB_DEG) est += e[n];
+    }
+    return est <= TAB_EST_DESIGN && rho <= TAB_RHO_DESIGN;
+}
+
+// References needed by a sub-block [k, k + m) for the coverage C (0: not admissible at any spacing)
+static int table_refs_needed(const gwin_plan* p, const Cover& C, int k, int m, int kmax_refs) {
+    long double c[NPH][TAB_NTH];
+    taylor_matrix((double)(k + m / 2), 0.5 * m, p->d.delta_f, c);
+    const double half = 0.5 * (C.a_hi - C.a_lo);
+    if (table_admissible(c, C.dev, half)) return 1;
+    if (!table_admissible(c, C.dev, half / kmax_refs)) return 0;
+    double lo = half / kmax_refs, hi = half;            // lo admissible, hi not
+    for (int it = 0; it < 14; ++it) {
+        const double mid = std::sqrt(lo * hi);
+        if (table_admissible(c, C.dev, mid)) lo = mid; else hi = mid;
+    }
+    return std::min(kmax_refs, (int)std::ceil(half / lo));
 }
 
 static void free_tables(gwin_plan* p) {
-    cudaFree(p->d_tab_start); cudaFree(p->d_tab_mi); cudaFree(p->d_tab_off); cudaFree(p->d_tabmats);
-    cudaFree(p->d_invhat); cudaFree(p->d_tab); cudaFree(p->d_tab_ref);
-    p->d_tab_start = p->d_tab_mi = nullptr; p->d_tab_off = nullptr; p->d_tabmats = nullptr;
-    p->d_invhat = nullptr; p->d_tab = nullptr; p->d_tab_ref = nullptr;
-    p->n_tblk = 0;
+    cudaFree(p->d_tblk); cudaFree(p->d_cmat); cudaFree(p->d_tref); cudaFree(p->d_tab);
+    p->d_tblk = nullptr; p->d_cmat = p->d_tref = nullptr; p->d_tab = nullptr;
+    p->n_tblk = 0; p->n_pairs = 0; p->tab_bytes = 0;
+    p->tblk.clear();
 }
 
-// Sub-blocks over [k_split, kmax) and their moment tables.  k_split is the first boundary of the
-// recurrence schedule from which TAB_MIN-bin sub-blocks meet both bounds; below it the
-// recurrence kernel does the work.  No tables (n_tblk = 0) when they would not fit the budget.
-static int build_tables(gwin_plan* p) {
-    PlanDev& d = p->d;
-    free_tables(p);
-    p->tab_start.clear(); p->tab_mi.clear(); p->tab_off.clear(); p->tabmats.clear();
-    p->k_split = d.kmax; p->n_blk_low = p->n_blk;
-    p->tab_dirty = false;
-    // with a reference waveform only the batch's deviation from it has to be expanded: the bounds
-    // apply to ref_width x the chirp (+30 % and 0.02 of slack for what does not scale with the
-    // chirp mass: mass ratio, spins, tides at the higher PN orders)
-    const double wfac = p->ref_on ? std::min(1.0, 1.3 * p->ref_width + 0.02) : 1.0;
-    const double chirp = wfac * 2.0 * (3.0 / 128.0) * pow(G_PI * p->mchirp_min * G_MTSUN, -5.0 / 3.0);
+// Sub-blocks over [k_split, kmax) for the coverage `C`, longest first, with at most K0 (f/f0)^(-11/9)
+// reference chirps per sub-block (the split of a memory budget that minimises the number of
+// sub-blocks when the reference count grows like m^2 f^(-11/3)).  Returns the table bytes.
+static double table_schedule(const gwin_plan* p, const Cover& C, double K0, std::vector<TabBlk>& out, int* ib_split) {
+    const PlanDev& d = p->d;
+    const std::vector<int>& sizes = table_sizes();
     const int band0 = std::max(std::max(d.kmin, d.istart), 1);
-    const std::vector<TabSize>& sizes = table_sizes();
-    int raw = band0;
-    while (raw < d.kmax && table_block_size(p, raw, chirp) < 0) raw += 64;
-    if (raw >= d.kmax) return GWIN_OK;
-    int ib = 0;
-    while (ib < p->n_blk && p->blk_start[ib] < raw) ++ib;
-    if (ib >= p->n_blk) return GWIN_OK;
-    const int k_split = p->blk_start[ib];
-    std::vector<double> invhat;
-    std::vector<int> mat_of(sizes.size(), -1);
-    int64_t off = 0;
-    for (int k = k_split; k < d.kmax;) {
-        // sub-blocks lie wholly inside the band (their nodes index the basis table); what is
-        // left below kmax goes to the recurrence kernel's second pass with the walkers' tails
-        int si = std::max(table_block_size(p, k, chirp), 0);
-        while (si > 0 && k + sizes[si].m > d.kmax) --si;
-        const int m = sizes[si].m;
-        if (k + m > d.kmax) break;
-        if (mat_of[si] < 0) {
-            mat_of[si] = (int)p->tabmats.size();
-            p->tabmats.push_back(make_tab_mat(sizes[si], (int)invhat.size()));
-            // 1 / phi_hat(jc / L), phi_hat by midpoint quadrature of the kernel over its support
-            // (depends on m only: computed once per process)
-            static std::vector<double> hat_cache[32];
-            static std::mutex hat_mutex;
-            std::lock_guard<std::mutex> hat_lock(hat_mutex);
-            std::vector<double>& hc = hat_cache[si];
-            if (hc.empty()) {
-                const int nq = 2048, L = 2 * m;
-                std::vector<long double> xs(nq), ph(nq);
-                for (int q = 0; q < nq; ++q) {
-                    xs[q] = ((long double)q + 0.5L) / nq * TAB_W - 0.5L * TAB_W;
-                    ph[q] = es_kernel_host(xs[q]);
-                }
-                hc.resize(m);
-                for (int j = 0; j < m; ++j) {
-                    const long double xi = (long double)(j - m / 2) / L;
-                    long double sum = 0.0L;
-                    for (int q = 0; q < nq; ++q) sum += ph[q] * cosl(2.0L * 3.14159265358979323846264338327950288L * xi * xs[q]);
-                    hc[j] = (double)(1.0L / (sum * TAB_W / nq));
-                }
-            }
-            invhat.insert(invhat.end(), hc.begin(), hc.end());
+    const double f0 = band0 * d.delta_f;
+    out.clear();
+    static const int kmax_refs = 4096;
+    auto pick = [&](int k, int* K_out) -> int {          // longest admissible size at bin k within the cap
+        const double cap = std::max(1.0, K0 * std::pow(k * d.delta_f / f0, -11.0 / 9.0));
+        for (int si = (int)sizes.size() - 1; si >= 0; --si) {
+            const int m = sizes[si];
+            if (k + m > d.kmax) continue;
+            const int K = table_refs_needed(p, C, k, m, kmax_refs);
+            if (K > 0 && K <= cap) { *K_out = K; return m; }
         }
-        p->tab_start.push_back(k);
-        p->tab_mi.push_back(mat_of[si]);
-        p->tab_off.push_back(off);
-        off += (int64_t)d.n_det * TAB_NM * (2 * m + TAB_W);
+        return 0;
+    };
+    // k_split: the first boundary of the recurrence schedule from which sub-blocks qualify
+    int ib = 0, K = 0, m = 0;
+    while (ib < p->n_blk && (m = pick(p->blk_start[ib], &K)) == 0) {
+        // skip ahead by at least 64 bins
+        const int k_next = p->blk_start[ib] + 64;
+        while (ib < p->n_blk && p->blk_start[ib] < k_next) ++ib;
+    }
+    *ib_split = ib;
+    if (ib >= p->n_blk) return 0.0;
+    double bytes = 0.0;
+    int pair0 = 0;
+    long long off = 0;
+    for (int k = p->blk_start[ib]; k < d.kmax;) {
+        m = pick(k, &K);
+        if (m == 0) break;                                // what is left below kmax goes to the tails
+        TabBlk B;
+        memset(&B, 0, sizeof B);
+        B.start = k; B.m = m; B.K = K; B.pair0 = pair0;
+        B.da = (C.a_hi - C.a_lo) / K;
+        B.a_lo = C.a_lo;
+        B.inv_da = 1.0 / B.da;
+        B.eps = 0.5 * m / (double)(k + m / 2);
+        B.off = off;
+        out.push_back(B);
+        pair0 += K;
+        off += (long long)K * d.n_det * (2 * m + TAB_W) * TAB_NM;
         k += m;
     }
-    const int n = (int)p->tab_mi.size();
-    if (n == 0) return GWIN_OK;
-    p->tab_start.push_back(p->tab_start.back() + p->tabmats[p->tab_mi.back()].m);
-    static const double budget_gb = getenv("GWIN_TABLE_GB") ? atof(getenv("GWIN_TABLE_GB")) : 4.0;
-    if ((double)off * sizeof(double2) > budget_gb * 1073741824.0) return GWIN_OK;     // stay on the recurrence kernel
-    { const int rcp = upload_tab_poly(); if (rcp) return rcp; }
-    CK(cudaMalloc(&p->d_tab_start, sizeof(int) * (n + 1)));
-    CK(cudaMalloc(&p->d_tab_mi, sizeof(int) * n));
-    CK(cudaMalloc(&p->d_tab_off, sizeof(int64_t) * n));
-    CK(cudaMalloc(&p->d_tabmats, sizeof(TabMat) * p->tabmats.size()));
-    CK(cudaMalloc(&p->d_invhat, sizeof(double) * invhat.size()));
-    if (cudaMalloc(&p->d_tab, sizeof(double2) * (size_t)off) != cudaSuccess) {
-        // not enough device memory for the tables: the recurrence kernel keeps the whole band
-        cudaGetLastError();
-        p->d_tab = nullptr;
-        free_tables(p);
-        return GWIN_OK;
-    }
-    CK(cudaMemcpy(p->d_tab_start, p->tab_start.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(p->d_tab_mi, p->tab_mi.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(p->d_tab_off, p->tab_off.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(p->d_tabmats, p->tabmats.data(), sizeof(TabMat) * p->tabmats.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(p->d_invhat, invhat.data(), sizeof(double) * invhat.size(), cudaMemcpyHostToDevice));
-    if (!p->d_violation) {
-        CK(cudaMalloc(&p->d_violation, sizeof(int)));
-        CK(cudaMemset(p->d_violation, 0, sizeof(int)));
-    }
-    if (p->ref_on) {
-        // phase coefficients of the reference point (walker_setup on a one-walker batch), then its
-        // phase at every sub-block's centre / ends / nodes
-        const int nd = d.n_det;
-        if (!p->d_ref_params) {
-            CK(cudaMalloc(&p->d_ref_params, sizeof(double) * GWIN_NPARAM));
-            CK(cudaMalloc(&p->d_ref_wc, sizeof(double) * (NCOEF(GWIN_MAX_DET) + GWIN_MAX_DET)));
-            CK(cudaMalloc(&p->d_ref_k, sizeof(int) * 4));
+    bytes = (double)off * sizeof(double2);
+    return bytes;
+}
+
+static int build_tables(gwin_plan* p) {
+    PlanDev& d = p->d;
+    CK(cudaDeviceSynchronize());                          // nothing in flight reads the old tables
+    free_tables(p);
+    p->k_split = d.kmax; p->n_blk_low = p->n_blk; p->k_tab_end = d.kmax;
+    p->tab_dirty = false;
+    p->tab_worth = false;
+    p->cover = p->want;
+    if (!p->cover.valid || !(p->cover.a_hi > p->cover.a_lo)) { p->cover.valid = false; return GWIN_OK; }
+    static const double budget_gb = getenv("GWIN_TABLE_GB") ? atof(getenv("GWIN_TABLE_GB")) : 2.0;
+    const double budget = budget_gb * 1073741824.0;
+    // the largest reference-count scale that fits the budget
+    std::vector<TabBlk> blks;
+    int ib = 0;
+    double K0 = 2048.0;
+    double bytes = table_schedule(p, p->cover, K0, blks, &ib);
+    if (bytes > budget) {
+        double lo = 0.5, hi = K0;
+        for (int it = 0; it < 10; ++it) {
+            const double mid = std::sqrt(lo * hi);
+            if (table_schedule(p, p->cover, mid, blks, &ib) > budget) hi = mid; else lo = mid;
         }
-        CK(cudaMemcpy(p->d_ref_params, p->ref_params, sizeof(double) * GWIN_NPARAM, cudaMemcpyHostToDevice));
-        walker_setup_kernel<<<1, 32>>>(d, 1, 1, p->d_ref_params, GWIN_NPARAM, 1, nullptr, nullptr, p->d_ref_wc,
-                                       p->d_ref_k, p->d_ref_k + 1, p->d_ref_wc + NCOEF(nd), nullptr, 0, 0,
-                                       nullptr, 0, nullptr, nullptr, 0);
-        int ks_ref = 0;
-        CK(cudaMemcpy(&ks_ref, p->d_ref_k, sizeof(int), cudaMemcpyDeviceToHost));
-        if (ks_ref < 0) { free_tables(p); return fail(GWIN_EINVAL, "the table reference point has no waveform"); }
-        CK(cudaMalloc(&p->d_tab_ref, sizeof(double) * (size_t)n * TAB_REFN));
-        tab_ref_kernel<<<(n + 127) / 128, 128>>>(d, n, p->d_tab_start, p->d_tab_mi, p->d_tabmats, p->d_ref_wc, p->d_tab_ref);
+        K0 = lo;
+        bytes = table_schedule(p, p->cover, K0, blks, &ib);
+        if (bytes > budget) return GWIN_OK;               // stay on the recurrence kernel
     }
-    tab_build_kernel<<<dim3((2 * TAB_MAX + TAB_W + 255) / 256, n, d.n_det), 256>>>(d, p->d_tab_start, p->d_tab_mi, p->d_tab_off,
-                                                               p->d_tabmats, p->d_invhat, p->d_tab,
-                                                               p->d_ref_wc, p->d_tab_ref);
-    CK(cudaGetLastError());
-    CK(cudaDeviceSynchronize());
-    p->n_tblk = n; p->k_split = k_split; p->n_blk_low = ib;
-    // a sub-block costs about as much as 90 bins of the recurrence kernel, and the table path adds
-    // two launches: short segments (8 s and below at 4 kHz) are better off without it
-    const int64_t tab_bins = (int64_t)p->tab_start[n] - k_split;
+    const int n = (int)blks.size();
+    if (n == 0) return GWIN_OK;
+    int n_pairs = 0;
+    for (const TabBlk& B : blks) n_pairs += B.K;
+    // per-sub-block Taylor matrices, per-pair bookkeeping of the build
+    std::vector<double> cmat((size_t)n * NPH * TAB_NTP, 0.0);
+    std::vector<int> pair_blk(n_pairs), blk_hat(n);
+    std::vector<long long> pair_seg(n_pairs);
+    std::vector<double> invhat;
+    std::vector<int> hat_of(TAB_MAX + 1, -1);
+    long long seg_total = 0;
+    int m_max = 0;
+    for (int b = 0; b < n; ++b) {
+        const TabBlk& B = blks[b];
+        long double c[NPH][TAB_NTH];
+        taylor_matrix((double)(B.start + B.m / 2), 0.5 * B.m, d.delta_f, c);
+        for (int i = 0; i < NPH; ++i)
+            for (int q = 0; q < TAB_NT; ++q) cmat[((size_t)b * NPH + i) * TAB_NTP + q] = (double)c[i][q];
+        if (hat_of[B.m] < 0) {
+            hat_of[B.m] = (int)invhat.size();
+            const std::vector<double>& hc = inv_hat(B.m);
+            invhat.insert(invhat.end(), hc.begin(), hc.end());
+        }
+        blk_hat[b] = hat_of[B.m];
+        for (int r = 0; r < B.K; ++r) {
+            pair_blk[B.pair0 + r] = b;
+            pair_seg[B.pair0 + r] = seg_total;
+            seg_total += (long long)d.n_det * B.m;
+        }
+        m_max = std::max(m_max, B.m);
+    }
+    int *d_pair_blk = nullptr, *d_blk_hat = nullptr;
+    long long* d_pair_seg = nullptr;
+    double *d_invhat = nullptr, *d_refcoef = nullptr;
+    double2* d_seg = nullptr;
+    auto build = [&]() -> int {
+        CK(cudaMalloc(&p->d_tblk, sizeof(TabBlk) * n));
+        CK(cudaMalloc(&p->d_cmat, sizeof(double) * cmat.size()));
+        CK(cudaMalloc(&p->d_tref, sizeof(double) * (size_t)n_pairs * TAB_NTP));
+        CK(cudaMalloc(&d_pair_blk, sizeof(int) * n_pairs));
+        CK(cudaMalloc(&d_blk_hat, sizeof(int) * n));
+        CK(cudaMalloc(&d_pair_seg, sizeof(long long) * n_pairs));
+        CK(cudaMalloc(&d_invhat, sizeof(double) * invhat.size()));
+        CK(cudaMalloc(&d_refcoef, sizeof(double) * (size_t)n_pairs * NPH));
+        if (cudaMalloc(&p->d_tab, (size_t)bytes) != cudaSuccess ||
+            cudaMalloc(&d_seg, sizeof(double2) * (size_t)seg_total) != cudaSuccess) {
+            cudaGetLastError();                           // not enough device memory: no tables
+            return 1;
+        }
+        CK(cudaMemcpy(p->d_tblk, blks.data(), sizeof(TabBlk) * n, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(p->d_cmat, cmat.data(), sizeof(double) * cmat.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_pair_blk, pair_blk.data(), sizeof(int) * n_pairs, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_blk_hat, blk_hat.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_pair_seg, pair_seg.data(), sizeof(long long) * n_pairs, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_invhat, invhat.data(), sizeof(double) * invhat.size(), cudaMemcpyHostToDevice));
+        tab_tref_kernel<<<(n_pairs + 127) / 128, 128>>>(n_pairs, d_pair_blk, p->d_tblk, p->d_cmat, p->d_tref, d_refcoef);
+        for (int base = 0; base < n_pairs; base += 32768) {
+            const int np = std::min(32768, n_pairs - base);
+            tab_seg_kernel<<<dim3((m_max + 255) / 256, np, d.n_det), 256>>>(d, d_pair_blk, p->d_tblk, d_pair_seg, d_blk_hat,
+                                                                           d_invhat, p->d_tref, d_refcoef, d_seg, base);
+            tab_dft_kernel<<<dim3((2 * m_max + TAB_W + 255) / 256, np, d.n_det), 256>>>(d_pair_blk, p->d_tblk, d_pair_seg,
+                                                                                       d_seg, p->d_tab, d.n_det, base);
+        }
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        return GWIN_OK;
+    };
+    const int rc = build();
+    cudaFree(d_pair_blk); cudaFree(d_blk_hat); cudaFree(d_pair_seg); cudaFree(d_invhat); cudaFree(d_refcoef); cudaFree(d_seg);
+    if (rc != GWIN_OK) {
+        free_tables(p);
+        return rc > 0 ? GWIN_OK : rc;                     // no memory for the tables: the recurrence kernel keeps the band
+    }
+    p->tblk = blks;
+    p->n_tblk = n; p->n_pairs = n_pairs; p->tab_bytes = (size_t)bytes;
+    p->k_split = blks[0].start; p->n_blk_low = ib;
+    p->k_tab_end = blks[n - 1].start + blks[n - 1].m;
+    // a sub-block costs about as much as 70 bins of the recurrence kernel, and the table path adds
+    // launches: short segments (8 s and below at 4 kHz) are better off without it
+    const int64_t tab_bins = (int64_t)p->k_tab_end - p->k_split;
     p->tab_worth = tab_bins >= 16384 && tab_bins >= (int64_t)350 * n;
     return GWIN_OK;
+}
+
+// ---- coverage ---------------------------------------------------------------------------------
+static void cover_merge(Cover& dst, const Cover& src) {
+    if (!src.valid) return;
+    if (!dst.valid) { dst = src; return; }
+    dst.a_lo = std::min(dst.a_lo, src.a_lo);
+    dst.a_hi = std::max(dst.a_hi, src.a_hi);
+    for (int i = 0; i < NPH; ++i) dst.dev[i] = std::max(dst.dev[i], src.dev[i]);
+}
+static bool cover_contains(const Cover& big, const Cover& small) {
+    if (!small.valid) return true;
+    if (!big.valid) return false;
+    if (small.a_lo < big.a_lo || small.a_hi > big.a_hi) return false;
+    for (int i = 0; i < NPH; ++i) if (small.dev[i] > big.dev[i]) return false;
+    return true;
+}
+// margins around what a batch was seen to need: the next batches of a sampler wander
+static void cover_widen(Cover& c) {
+    const double pad = 0.05 * (c.a_hi - c.a_lo) + 2e-3 * c.a_hi;
+    c.a_lo = std::max(c.a_lo - pad, 0.25 * c.a_lo);
+    c.a_hi += pad;
+    for (int i = 0; i < NPH; ++i) c.dev[i] *= 1.5;
+}
+
+// Statistics of a batch of DEVICE parameter rows (synchronises `st`)
+static int cover_from_device(gwin_plan* p, int64_t W, const double* params, int64_t sw, int64_t si,
+                             const uint8_t* skip, cudaStream_t st, Cover* out) {
+    out->valid = false;
+    if (W <= 0) return GWIN_OK;
+    if (!p->d_stats) CK(cudaMalloc(&p->d_stats, sizeof(unsigned long long) * 16));
+    unsigned long long init[16];
+    memset(init, 0, sizeof init);
+    const double inf = INFINITY;
+    memcpy(&init[0], &inf, sizeof(double));
+    CK(cudaMemcpyAsync(p->d_stats, init, sizeof init, cudaMemcpyHostToDevice, st));
+    cover_stats_kernel<<<(int)((W + 127) / 128), 128, 0, st>>>(p->d, (int)W, params, sw, si, skip, p->d_stats);
+    unsigned long long res[16];
+    CK(cudaMemcpyAsync(res, p->d_stats, sizeof res, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (res[2 + NPH] == 0) return GWIN_OK;
+    memcpy(&out->a_lo, &res[0], sizeof(double));
+    memcpy(&out->a_hi, &res[1], sizeof(double));
+    for (int i = 0; i < NPH; ++i) memcpy(&out->dev[i], &res[2 + i], sizeof(double));
+    out->dev[0] = 0.0;
+    out->valid = true;
+    return GWIN_OK;
+}
+
+// the coverage changed: the recurrence schedule must reach the lightest covered system, the tables
+// are rebuilt on the next call that uses them
+static void cover_apply(gwin_plan* p) {
+    if (!p->want.valid) return;
+    if (!cover_contains(p->cover, p->want)) p->tab_dirty = true;
+    if (p->auto_mchirp) {
+        // a0 = 3 / (256 pi) (pi Mc)^(-5/3)  ->  the smallest chirp mass covered, a quarter octave down
+        const double mc = std::pow(p->want.a_hi * (256.0 * G_PI / 3.0), -0.6) / (G_PI * G_MTSUN);
+        const double q = std::exp2(std::floor(4.0 * std::log2(std::min(std::max(mc, 0.02), 1e4))) / 4.0);
+        if (q < p->mchirp_min || q > 2.0 * p->mchirp_min) { p->mchirp_min = q; p->sched_dirty = true; }
+    }
 }
 
 extern "C" const char* gwin_last_error(void) { return g_err; }
@@ -2194,8 +2542,11 @@ extern "C" void gwin_plan_destroy(gwin_plan* p) {
     cudaFree(p->d_partial); cudaFree(p->d_cub);
     cudaFree(p->d_marg_u); cudaFree(p->d_marg_logw); cudaFree(p->d_marg_opt);
     cudaFree(p->d_calM); cudaFree(p->d_Ccal); cudaFree(p->d_calib); cudaFreeHost(p->h_calib);
-    free_tables(p); cudaFree(p->d_partialT); cudaFree(p->d_ke_low); cudaFree(p->d_ks_tail);
-    cudaFree(p->d_ref_params); cudaFree(p->d_ref_wc); cudaFree(p->d_ref_k); cudaFree(p->d_violation);
+    free_tables(p); cudaFree(p->d_partialT); cudaFree(p->d_partialS);
+    cudaFree(p->d_ke_fast); cudaFree(p->d_ke_low); cudaFree(p->d_ks_tail);
+    cudaFree(p->d_key2_in); cudaFree(p->d_key2_out); cudaFree(p->d_idx2_in); cudaFree(p->d_perm_e); cudaFree(p->d_grp_b);
+    cudaFree(p->d_slow); cudaFree(p->d_slow_list); cudaFree(p->d_slow_n); cudaFree(p->d_stats);
+    if (p->ev_done_set) cudaEventDestroy(p->ev_done);
     cudaFree(p->d_params); cudaFree(p->d_out); cudaFree(p->d_skip);
     cudaFreeHost(p->h_params); cudaFreeHost(p->h_out); cudaFreeHost(p->h_skip);
     if (p->timing) { cudaEventDestroy(p->ev0); cudaEventDestroy(p->ev1); }
@@ -2341,31 +2692,69 @@ extern "C" int gwin_plan_configure(gwin_plan* p, int kernel, double phase_tol, d
     return GWIN_OK;
 }
 
-extern "C" int gwin_plan_set_reference(gwin_plan* p, const double* params, double rel_width) {
-    if (!p) return fail(GWIN_EINVAL, "plan is NULL");
-    if (!params || !(rel_width > 0.0)) {                 // clear
-        if (p->ref_on) { p->ref_on = false; p->tab_dirty = true; }
-        return GWIN_OK;
-    }
-    for (int i = 0; i < GWIN_NPARAM; ++i)
-        if (!std::isfinite(params[i])) return fail(GWIN_EINVAL, "reference parameter %d is not finite", i);
-    if (!(params[0] > 0.0) || !(params[1] > 0.0) || !(params[4] > 0.0))
-        return fail(GWIN_EINVAL, "reference masses and distance must be positive");
-    memcpy(p->ref_params, params, sizeof(double) * GWIN_NPARAM);
-    p->ref_width = rel_width;
-    p->ref_on = true;
-    p->ref_auto = false;
-    p->tab_dirty = true;
+static int cover_declare(gwin_plan* p, const Cover& seen) {
+    if (!seen.valid) return fail(GWIN_EINVAL, "none of the points has a waveform");
+    Cover c = seen;
+    cover_widen(c);
+    cover_merge(p->want, c);
+    p->cover_manual = true;
+    cover_apply(p);
     return GWIN_OK;
 }
 
-extern "C" int gwin_plan_table_violations(gwin_plan* p, int* flag) {
-    if (!p || !flag) return fail(GWIN_EINVAL, "NULL argument");
-    *flag = 0;
-    if (!p->d_violation) return GWIN_OK;
+extern "C" int gwin_plan_cover_device(gwin_plan* p, int64_t W, const double* params,
+                                      int64_t stride_walker, int64_t stride_param, void* stream) {
+    if (!p) return fail(GWIN_EINVAL, "plan is NULL");
     CK(cudaSetDevice(p->device));
-    CK(cudaMemcpy(flag, p->d_violation, sizeof(int), cudaMemcpyDeviceToHost));
-    CK(cudaMemset(p->d_violation, 0, sizeof(int)));
+    if (W <= 0 || !params) {                              // back to automatic coverage
+        p->want.valid = false; p->cover_manual = false; p->tab_dirty = true;
+        return GWIN_OK;
+    }
+    if (stride_walker < 1 || stride_param < 1) return fail(GWIN_EINVAL, "parameter strides must be >= 1");
+    Cover seen;
+    memset(&seen, 0, sizeof seen);
+    int rc = cover_from_device(p, W, params, stride_walker, stride_param, nullptr, (cudaStream_t)stream, &seen);
+    if (rc) return rc;
+    return cover_declare(p, seen);
+}
+
+extern "C" int gwin_plan_cover_host(gwin_plan* p, int64_t W, const double* params,
+                                    int64_t stride_walker, int64_t stride_param) {
+    if (!p) return fail(GWIN_EINVAL, "plan is NULL");
+    if (W <= 0 || !params) return gwin_plan_cover_device(p, 0, nullptr, 0, 0, nullptr);
+    if (!((stride_walker == GWIN_NPARAM && stride_param == 1) || (stride_walker == 1 && stride_param == W)))
+        return fail(GWIN_EINVAL, "host parameters must be a dense [W][13] or [13][W] block");
+    CK(cudaSetDevice(p->device));
+    double* d = nullptr;
+    CK(cudaMalloc(&d, sizeof(double) * GWIN_NPARAM * W));
+    int rc = GWIN_OK;
+    if (cudaMemcpy(d, params, sizeof(double) * GWIN_NPARAM * W, cudaMemcpyHostToDevice) != cudaSuccess)
+        rc = fail(GWIN_ECUDA, "copy of the coverage points failed");
+    if (!rc) rc = gwin_plan_cover_device(p, W, d, stride_walker, stride_param, p->stream);
+    cudaFree(d);
+    return rc;
+}
+
+extern "C" int gwin_plan_table_info(gwin_plan* p, int64_t* n_subblocks, int64_t* n_references,
+                                    int64_t* bytes, int64_t* k_split) {
+    if (!p) return fail(GWIN_EINVAL, "plan is NULL");
+    if (n_subblocks) *n_subblocks = p->n_tblk;
+    if (n_references) *n_references = p->n_pairs;
+    if (bytes) *bytes = (int64_t)p->tab_bytes;
+    if (k_split) *k_split = p->n_tblk ? p->k_split : p->d.kmax;
+    return GWIN_OK;
+}
+
+extern "C" int gwin_plan_slow_path(gwin_plan* p, int64_t* n_walkers) {
+    if (!p || !n_walkers) return fail(GWIN_EINVAL, "NULL argument");
+    *n_walkers = 0;
+    if (!p->d_slow_n) return GWIN_OK;
+    CK(cudaSetDevice(p->device));
+    CK(cudaDeviceSynchronize());
+    int n = 0;
+    CK(cudaMemcpy(&n, p->d_slow_n + 1, sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemset(p->d_slow_n + 1, 0, sizeof(int)));
+    *n_walkers = n;
     return GWIN_OK;
 }
 
@@ -2399,24 +2788,26 @@ static int ensure_workspace(gwin_plan* p, int64_t W, int n_chunks) {
     if (W > p->w_cap) {
         int64_t cap = std::max<int64_t>(W, 1024);
         cap = (cap + CTA_THREADS - 1) / CTA_THREADS * CTA_THREADS;
-        cudaFree(p->d_wc); cudaFree(p->d_ks); cudaFree(p->d_ke);
-        cudaFree(p->d_key_in); cudaFree(p->d_key_out); cudaFree(p->d_perm_in); cudaFree(p->d_perm_out);
-        cudaFree(p->d_cub); cudaFree(p->d_marg_opt); cudaFree(p->d_ke_low); cudaFree(p->d_ks_tail);
-        p->d_marg_opt = nullptr; p->d_ke_low = p->d_ks_tail = nullptr;
-        p->d_wc = nullptr; p->d_ks = p->d_ke = p->d_key_in = p->d_key_out = p->d_perm_in = p->d_perm_out = nullptr;
-        p->d_cub = nullptr; p->w_cap = 0;
+        CK(cudaDeviceSynchronize());
+        int** ints[] = { &p->d_ks, &p->d_ke, &p->d_key_in, &p->d_key_out, &p->d_perm_in, &p->d_perm_out,
+                         &p->d_ke_fast, &p->d_ke_low, &p->d_ks_tail, &p->d_key2_in, &p->d_key2_out,
+                         &p->d_idx2_in, &p->d_perm_e, &p->d_slow_list };
+        for (int** q : ints) { cudaFree(*q); *q = nullptr; }
+        cudaFree(p->d_wc); cudaFree(p->d_cub); cudaFree(p->d_marg_opt); cudaFree(p->d_slow); cudaFree(p->d_grp_b);
+        p->d_wc = nullptr; p->d_cub = nullptr; p->d_marg_opt = nullptr; p->d_slow = nullptr; p->d_grp_b = nullptr;
+        p->w_cap = 0;
         // coefficient rows + n_det rows of hh
         CK(cudaMalloc(&p->d_wc, sizeof(double) * (NCOEF(nd) + nd) * cap));
-        CK(cudaMalloc(&p->d_ks, sizeof(int) * cap));
-        CK(cudaMalloc(&p->d_ke, sizeof(int) * cap));
-        CK(cudaMalloc(&p->d_key_in, sizeof(int) * cap));
-        CK(cudaMalloc(&p->d_key_out, sizeof(int) * cap));
-        CK(cudaMalloc(&p->d_perm_in, sizeof(int) * cap));
-        CK(cudaMalloc(&p->d_perm_out, sizeof(int) * cap));
+        for (int** q : ints) CK(cudaMalloc(q, sizeof(int) * cap));
         CK(cudaMalloc(&p->d_marg_opt, sizeof(double) * cap));
-        CK(cudaMalloc(&p->d_ke_low, sizeof(int) * cap));
-        CK(cudaMalloc(&p->d_ks_tail, sizeof(int) * cap));
+        CK(cudaMalloc(&p->d_slow, cap));
+        CK(cudaMalloc(&p->d_grp_b, sizeof(int) * 2 * (cap / CTA_THREADS + 1)));
+        if (!p->d_slow_n) {
+            CK(cudaMalloc(&p->d_slow_n, sizeof(int) * 2));
+            CK(cudaMemset(p->d_slow_n, 0, sizeof(int) * 2));
+        }
         p->partialT_cap = 0;
+        p->partialS_cap = 0;
         p->cub_bytes = 0;
         CK(cub::DeviceRadixSort::SortPairs(nullptr, p->cub_bytes, p->d_key_in, p->d_key_out,
                                            p->d_perm_in, p->d_perm_out, (int)cap, 0, 23));
@@ -2426,6 +2817,7 @@ static int ensure_workspace(gwin_plan* p, int64_t W, int n_chunks) {
     }
     const size_t need = (size_t)n_chunks * nd * p->w_cap;
     if (need > p->partial_cap) {
+        CK(cudaDeviceSynchronize());
         cudaFree(p->d_partial); p->d_partial = nullptr; p->partial_cap = 0;
         CK(cudaMalloc(&p->d_partial, sizeof(double2) * need));
         p->partial_cap = need;
@@ -2433,58 +2825,77 @@ static int ensure_workspace(gwin_plan* p, int64_t W, int n_chunks) {
     return GWIN_OK;
 }
 
+// One launch of the recurrence kernel (or, recur = false, of the direct kernel).
+//   blk_off, n_blk   the part of the block schedule the launch covers
+//   ks_arr, ke_arr   per-walker band
+//   col, grp_b       tails of the table path (see loglr_recur_kernel), grid.y = n_chunks slots
+//   list, n_list     slow path of the direct kernel (see loglr_direct_kernel), grid.x = grid_x CTAs
+struct MainLaunch {
+    bool recur, calibrated;
+    int W, wpad, n_chunks, per_chunk, n_blk, blk_off;
+    const int *ks_arr, *ke_arr;
+    double2* partial;
+    const int *col, *grp_b;
+    const int *list, *n_list;
+    int grid_x;
+};
 template <int ND>
-static void launch_main(gwin_plan* p, bool recur, bool calibrated, int W, int wpad, int n_chunks, int per_chunk,
-                        int n_blk, const int* ke_arr, cudaStream_t st,
-                        int blk_off = 0, const int* ks_arr = nullptr, double2* partial = nullptr) {
-    if (!ks_arr) ks_arr = p->d_ks;
-    if (!partial) partial = p->d_partial;
-    dim3 grid((W + CTA_THREADS - 1) / CTA_THREADS, n_chunks);
+static void launch_main(gwin_plan* p, const MainLaunch& a, cudaStream_t st) {
+    dim3 grid(a.grid_x > 0 ? a.grid_x : (a.W + CTA_THREADS - 1) / CTA_THREADS, a.n_chunks);
     // diagnostic: GWIN_SMEM_PAD=<bytes> of unused dynamic shared memory lowers the occupancy
     static const int smem_pad = getenv("GWIN_SMEM_PAD") ? atoi(getenv("GWIN_SMEM_PAD")) : 0;
     constexpr int NWARP = CTA_THREADS / WARP;
     const int smem = (int)(sizeof(double2) * NWARP * 2 * TileStream<ND>::TILE * ND
-                           + sizeof(double) * (calibrated ? RC_ROWS_CAL(ND) : RC_ROWS(ND)) * CTA_THREADS
+                           + sizeof(double) * (a.calibrated ? RC_ROWS_CAL(ND) : RC_ROWS(ND)) * CTA_THREADS
                            + sizeof(uint64_t) * NWARP * 2) + smem_pad;
     // function attributes belong to the device's context: once per (ND, CALIB) and device
     static bool attr_set_dev[64][2] = {};
-    bool& attr_flag = attr_set_dev[p->device & 63][calibrated];
-    if (recur && !attr_flag) {
-        if (calibrated)
+    bool& attr_flag = attr_set_dev[p->device & 63][a.calibrated];
+    if (a.recur && !attr_flag) {
+        if (a.calibrated)
             cudaFuncSetAttribute(loglr_recur_kernel<ND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         else
             cudaFuncSetAttribute(loglr_recur_kernel<ND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr_flag = true;
     }
-    if (recur && calibrated)
-        loglr_recur_kernel<ND, true><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, per_chunk, n_blk, p->d_blk_start + blk_off,
-                                                                  p->d_blk_mat + blk_off, p->d_mats,
-                                                                  p->d_wc, ks_arr, ke_arr, partial);
-    else if (recur)
-        loglr_recur_kernel<ND, false><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, per_chunk, n_blk, p->d_blk_start + blk_off,
-                                                                   p->d_blk_mat + blk_off, p->d_mats,
-                                                                   p->d_wc, ks_arr, ke_arr, partial);
-    else if (calibrated)
-        loglr_direct_kernel<ND, true><<<grid, CTA_THREADS, 0, st>>>(p->d, W, wpad, per_chunk, n_chunks,
-                                                                   p->d_wc, ks_arr, ke_arr, partial);
+    if (a.recur && a.calibrated)
+        loglr_recur_kernel<ND, true><<<grid, CTA_THREADS, smem, st>>>(p->d, a.W, a.wpad, a.per_chunk, a.n_blk, p->d_blk_start + a.blk_off,
+                                                                  p->d_blk_mat + a.blk_off, p->d_mats,
+                                                                  p->d_wc, a.ks_arr, a.ke_arr, a.partial, a.col, a.grp_b);
+    else if (a.recur)
+        loglr_recur_kernel<ND, false><<<grid, CTA_THREADS, smem, st>>>(p->d, a.W, a.wpad, a.per_chunk, a.n_blk, p->d_blk_start + a.blk_off,
+                                                                   p->d_blk_mat + a.blk_off, p->d_mats,
+                                                                   p->d_wc, a.ks_arr, a.ke_arr, a.partial, a.col, a.grp_b);
+    else if (a.calibrated)
+        loglr_direct_kernel<ND, true><<<grid, CTA_THREADS, 0, st>>>(p->d, a.W, a.wpad, a.per_chunk, a.n_chunks,
+                                                                   p->d_wc, a.ks_arr, a.ke_arr, a.partial, a.list, a.n_list);
     else
-        loglr_direct_kernel<ND, false><<<grid, CTA_THREADS, 0, st>>>(p->d, W, wpad, per_chunk, n_chunks,
-                                                                    p->d_wc, ks_arr, ke_arr, partial);
+        loglr_direct_kernel<ND, false><<<grid, CTA_THREADS, 0, st>>>(p->d, a.W, a.wpad, a.per_chunk, a.n_chunks,
+                                                                    p->d_wc, a.ks_arr, a.ke_arr, a.partial, a.list, a.n_list);
+}
+static void launch_main_nd(gwin_plan* p, const MainLaunch& a, cudaStream_t st) {
+    switch (p->d.n_det) {
+        case 1: launch_main<1>(p, a, st); break;
+        case 2: launch_main<2>(p, a, st); break;
+        case 3: launch_main<3>(p, a, st); break;
+        default: launch_main<4>(p, a, st); break;
+    }
 }
 
 template <int ND>
 static void launch_table(gwin_plan* p, int W, int wpad, int n_chunks, int per_chunk, cudaStream_t st) {
     dim3 grid((W + CTA_THREADS - 1) / CTA_THREADS, n_chunks);
-    const int smem = (CTA_THREADS / WARP) * ND * TAB_SPAN * TAB_ROWB;
+    const int smem = per_chunk * NPH * TAB_NTP * (int)sizeof(double) + (CTA_THREADS / WARP) * ND * TAB_SPAN * TAB_ROWB;
     static bool attr_set_dev[64] = {};
     if (!attr_set_dev[p->device & 63]) {
-        cudaFuncSetAttribute(loglr_table_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(loglr_table_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             TAB_CHUNK_MAX * NPH * TAB_NTP * (int)sizeof(double) + (CTA_THREADS / WARP) * ND * TAB_SPAN * TAB_ROWB);
         cudaFuncSetAttribute(loglr_table_kernel<ND>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         attr_set_dev[p->device & 63] = true;
     }
-    loglr_table_kernel<ND><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, per_chunk, p->n_tblk, p->d_tab_start, p->d_tab_mi,
-                                                        p->d_tab_off, p->d_tabmats, p->d_tab, p->d_wc, p->d_ke,
-                                                        p->d_partialT, p->d_tab_ref, p->d_violation);
+    loglr_table_kernel<ND><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, per_chunk, p->n_tblk, p->d_tblk, p->d_cmat,
+                                                        p->d_tref, p->d_tab, p->d_wc, p->d_ke_fast,
+                                                        p->d_partialT, p->d_slow);
 }
 
 extern "C" int gwin_loglr_batch(gwin_plan* p, int mode, int64_t W64,
@@ -2518,6 +2929,21 @@ extern "C" int gwin_loglr_batch_calib(gwin_plan* p, int mode, int64_t W64,
                             skip, loglr, hd, hh, stream);
 }
 
+// Would this batch go through the moment tables (once they cover it)?
+static bool table_wanted(const gwin_plan* p, int64_t W, bool calibrated) {
+    static const bool table_default = !(getenv("GWIN_TABLE") && atoi(getenv("GWIN_TABLE")) == 0);
+    if (calibrated) return false;
+    if (p->kernel == GWIN_KERNEL_TABLE) return true;
+    if (p->kernel != GWIN_KERNEL_AUTO || !table_default) return false;
+    // AUTO: tables that exist are used where they pay; they are built for batches worth the build.
+    // A segment too short for the tables to pay at all is recognised from the band alone.
+    const PlanDev& d = p->d;
+    const int band0 = std::max(d.kmin, d.istart);
+    if (d.kmax - band0 < 32768) return false;
+    if (p->n_tblk > 0 && !p->tab_dirty) return p->tab_worth;
+    return W >= 256;
+}
+
 static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
                             const double* params, int64_t stride_walker, int64_t stride_param,
                             const double* calib, int64_t cstride_walker, int64_t cstride_value,
@@ -2538,12 +2964,39 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
     const PlanDev& d = p->d;
     const int nd = d.n_det;
     const bool recur = p->kernel != GWIN_KERNEL_DIRECT;
-    if (recur && p->sched_dirty) { int rc = upload_schedule(p); if (rc) return rc; }
-    // table kernel above k_split (uncalibrated batches): the recurrence kernel keeps [band0, k_split)
-    static const bool table_default = !(getenv("GWIN_TABLE") && atoi(getenv("GWIN_TABLE")) == 0);
-    bool table = !calib && (p->kernel == GWIN_KERNEL_TABLE || (p->kernel == GWIN_KERNEL_AUTO && table_default));
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    const bool capturing = cap != cudaStreamCaptureStatusNone;
+    // Calls on one plan share its workspace: a call on another stream than the previous one waits
+    // for it on the device (nothing to order inside a graph capture: the graph's own edges do)
+    if (!capturing && p->ev_done_set && p->last_stream != st) CK(cudaStreamWaitEvent(st, p->ev_done, 0));
+
+    // ---- moment tables above k_split (uncalibrated batches); the recurrence kernel keeps [band0, k_split)
+    bool table = recur && table_wanted(p, W, calib != nullptr);
+    if (table && (!p->want.valid || p->replan) && !p->cover_manual) {
+        // what the tables have to cover is read off this batch (first use, or after a batch that sent
+        // many walkers down the slow path): one small kernel, one synchronisation
+        if (capturing) {
+            if (!p->want.valid) return fail(GWIN_EINVAL, "the moment tables' coverage is not known yet and cannot be measured inside a "
+                                                         "stream capture: call gwin_plan_cover_device first");
+        } else {
+            Cover seen;
+            memset(&seen, 0, sizeof seen);
+            int rc = cover_from_device(p, W, params, stride_walker, stride_param, skip, st, &seen);
+            if (rc) return rc;
+            if (seen.valid) { cover_widen(seen); cover_merge(p->want, seen); cover_apply(p); }
+            p->replan = false;
+        }
+    }
+    if (recur && p->sched_dirty) {
+        if (capturing) return fail(GWIN_EINVAL, "the block schedule has to be rebuilt: not inside a stream capture");
+        int rc = upload_schedule(p); if (rc) return rc;
+    }
     if (table) {
-        if (p->tab_dirty) { int rc = build_tables(p); if (rc) return rc; }
+        if (p->tab_dirty) {
+            if (capturing) return fail(GWIN_EINVAL, "the moment tables have to be rebuilt: not inside a stream capture");
+            int rc = build_tables(p); if (rc) return rc;
+        }
         table = p->n_tblk > 0 && (p->kernel == GWIN_KERNEL_TABLE || p->tab_worth);
     }
     const int n_blk = table ? p->n_blk_low : p->n_blk;
@@ -2554,7 +3007,8 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
     const int groups = (W + CTA_THREADS - 1) / CTA_THREADS;
     static const int chunk_mult = getenv("GWIN_CHUNK_MULT") ? atoi(getenv("GWIN_CHUNK_MULT")) : 192;
     // at most 512 chunks: every chunk costs one partial per walker and detector in the combine pass
-    const int want_chunks = std::min(512, std::max(1, (148 * chunk_mult + groups - 1) / groups));
+    int want_chunks = std::min(512, std::max(1, (148 * chunk_mult + groups - 1) / groups));
+    if (table) want_chunks = std::min(want_chunks, std::max(1, (148 * 16 + groups - 1) / groups));     // the short low band
     int n_chunks, per_chunk;
     if (recur) {
         const int min_blocks = 2;
@@ -2565,49 +3019,79 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
         per_chunk = (per_chunk + RESYNC - 1) / RESYNC * RESYNC;
         n_chunks = (nbins + per_chunk - 1) / per_chunk;
     }
-    // second pass of the recurrence kernel over the blocks above k_split: every walker's tail
-    // (< one table sub-block, <= TAB_MAX bins); chunks of ~TAB_MAX bins
-    int n_chunks3 = 0, per_chunk3 = 1;
-    const int n_blk3 = table ? p->n_blk - p->n_blk_low : 0;
-    if (n_blk3 > 0) {
-        static const int tail_blocks = getenv("GWIN_TAIL_BLOCKS") ? atoi(getenv("GWIN_TAIL_BLOCKS")) : TAB_MAX / MAX_BLOCK / 2;
-        per_chunk3 = std::max(2, tail_blocks);
-        n_chunks3 = (n_blk3 + per_chunk3 - 1) / per_chunk3;
-    }
+    // tails of the table path: second pass of the recurrence kernel, walkers in the order of their last
+    // bin, every CTA over its own walkers' blocks in chunks of tail_blocks, TAIL_SLOTS partial sums
+    static const int tail_blocks = std::max(1, getenv("GWIN_TAIL_BLOCKS") ? atoi(getenv("GWIN_TAIL_BLOCKS")) : 2);
+    static const int tail_slots = std::max(1, getenv("GWIN_TAIL_SLOTS") ? atoi(getenv("GWIN_TAIL_SLOTS")) : 8);
+    const int n_chunks3 = table ? tail_slots : 0;
     int rc = ensure_workspace(p, W, std::max(n_chunks + n_chunks3, 1));
     if (rc) return rc;
     const int wpad = (int)p->w_cap;
     double* hh_rows = p->d_wc + (size_t)NCOEF(nd) * wpad;
-    // table chunks: a sub-block costs about as much as 100 recurrence bins
+    // table chunks: a sub-block costs about as much as 70 recurrence bins
     int n_chunksT = 0, per_chunkT = 1;
     if (table) {
         const int wantT = std::max(1, std::min(p->n_tblk, (148 * 24 + groups - 1) / groups));
-        per_chunkT = (p->n_tblk + wantT - 1) / wantT;
+        per_chunkT = std::min(TAB_CHUNK_MAX, (p->n_tblk + wantT - 1) / wantT);
         n_chunksT = (p->n_tblk + per_chunkT - 1) / per_chunkT;
         const size_t need = (size_t)n_chunksT * nd * p->w_cap;
         if (need > p->partialT_cap) {
+            CK(cudaDeviceSynchronize());
             cudaFree(p->d_partialT); p->d_partialT = nullptr; p->partialT_cap = 0;
             CK(cudaMalloc(&p->d_partialT, sizeof(double2) * need));
             p->partialT_cap = need;
+        }
+    }
+    // slow path (direct kernel over a list of walkers): its own chunking and partial sums
+    const int slow_gx = std::min(groups, 8);
+    int per_chunkS = std::max(RESYNC, (nbins + 255) / 256);
+    per_chunkS = (per_chunkS + RESYNC - 1) / RESYNC * RESYNC;
+    const int n_chunksS = (nbins + per_chunkS - 1) / per_chunkS;
+    if (recur) {
+        const size_t need = (size_t)n_chunksS * nd * p->w_cap;
+        if (need > p->partialS_cap) {
+            CK(cudaDeviceSynchronize());
+            cudaFree(p->d_partialS); p->d_partialS = nullptr; p->partialS_cap = 0;
+            CK(cudaMalloc(&p->d_partialS, sizeof(double2) * need));
+            p->partialS_cap = need;
         }
     }
 
     const int tb = 128, gb = (W + tb - 1) / tb;
     const int* perm = nullptr;
     if (W > WARP) {
-        sort_key_kernel<<<gb, tb, 0, st>>>(d, W, params, stride_walker, stride_param, skip, p->d_key_in, p->d_perm_in);
+        const double a_lo = p->cover.a_lo;
+        const double a_scale = table ? (double)(1 << TAB_KEY_BITS) / (p->cover.a_hi - p->cover.a_lo) : 0.0;
+        sort_key_kernel<<<gb, tb, 0, st>>>(d, W, params, stride_walker, stride_param, skip, p->d_key_in, p->d_perm_in,
+                                           table, a_lo, a_scale);
         size_t bytes = p->cub_bytes;
         CK(cub::DeviceRadixSort::SortPairs(p->d_cub, bytes, p->d_key_in, p->d_key_out,
-                                           p->d_perm_in, p->d_perm_out, W, 0, 23, st));
+                                           p->d_perm_in, p->d_perm_out, W, 0, table ? TAB_KEY_BITS : 23, st));
         perm = p->d_perm_out;
         p->last_launches += 1;   // + CUB's radix-sort passes (library code, not counted)
     }
+    FastArgs F;
+    memset(&F, 0, sizeof F);
+    // the recurrence schedule holds for chirp masses >= mchirp_min, i.e. a0 <= a0(mchirp_min)
+    F.a_sched_max = recur ? 3.0 / (256.0 * G_PI) * std::pow(G_PI * p->mchirp_min * G_MTSUN, -5.0 / 3.0) * (1.0 + 1e-12) : INFINITY;
+    F.table = table;
+    F.cov_lo = p->cover.a_lo; F.cov_hi = p->cover.a_hi;
+    F.k_split = p->k_split; F.k_tab_end = p->k_tab_end; F.n_tblk = p->n_tblk; F.blks = p->d_tblk;
+    F.ke_fast = p->d_ke_fast; F.ke_low = p->d_ke_low; F.ks_tail = p->d_ks_tail;
+    F.key2 = p->d_key2_in; F.idx2 = p->d_idx2_in; F.slow = p->d_slow;
+    if (recur) CK(cudaMemsetAsync(p->d_slow_n, 0, sizeof(int), st));
     walker_setup_kernel<<<gb, tb, 0, st>>>(d, W, wpad, params, stride_walker, stride_param, skip, perm, p->d_wc, p->d_ks, p->d_ke, hh_rows,
-                                           calib, cstride_walker, cstride_value,
-                                           table ? p->d_ke_low : nullptr, p->k_split,
-                                           p->d_ks_tail, p->d_tab_start, p->n_tblk);
-    const int* ke_main = table ? p->d_ke_low : p->d_ke;
+                                           calib, cstride_walker, cstride_value, F);
+    const int* ke_main = table ? p->d_ke_low : p->d_ke_fast;
     double2* partial3 = p->d_partial + (size_t)n_chunks * nd * wpad;
+    if (table) {
+        // second ordering, by last bin, for the tails
+        size_t bytes = p->cub_bytes;
+        CK(cub::DeviceRadixSort::SortPairs(p->d_cub, bytes, p->d_key2_in, p->d_key2_out,
+                                           p->d_idx2_in, p->d_perm_e, W, 0, 23, st));
+        tail_plan_kernel<<<groups, CTA_THREADS, 0, st>>>(W, p->n_blk, p->d_blk_start, p->d_perm_e, p->d_ks_tail, p->d_ke_fast, p->d_grp_b);
+        p->last_launches += 1;
+    }
     if (p->timing) {
         if (p->ev_pending) {            // harvest the previous launch (it has long finished)
             float ms = 0.f;
@@ -2617,19 +3101,13 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
         }
         CK(cudaEventRecord(p->ev0, st));
     }
-    if (n_chunks > 0) switch (nd) {
-        case 1: launch_main<1>(p, recur, calib != nullptr, W, wpad, n_chunks, per_chunk, n_blk, ke_main, st); break;
-        case 2: launch_main<2>(p, recur, calib != nullptr, W, wpad, n_chunks, per_chunk, n_blk, ke_main, st); break;
-        case 3: launch_main<3>(p, recur, calib != nullptr, W, wpad, n_chunks, per_chunk, n_blk, ke_main, st); break;
-        default: launch_main<4>(p, recur, calib != nullptr, W, wpad, n_chunks, per_chunk, n_blk, ke_main, st); break;
-    }
-    if (n_chunks3 > 0) {
-        switch (nd) {
-            case 1: launch_main<1>(p, true, false, W, wpad, n_chunks3, per_chunk3, n_blk3, p->d_ke, st, p->n_blk_low, p->d_ks_tail, partial3); break;
-            case 2: launch_main<2>(p, true, false, W, wpad, n_chunks3, per_chunk3, n_blk3, p->d_ke, st, p->n_blk_low, p->d_ks_tail, partial3); break;
-            case 3: launch_main<3>(p, true, false, W, wpad, n_chunks3, per_chunk3, n_blk3, p->d_ke, st, p->n_blk_low, p->d_ks_tail, partial3); break;
-            default: launch_main<4>(p, true, false, W, wpad, n_chunks3, per_chunk3, n_blk3, p->d_ke, st, p->n_blk_low, p->d_ks_tail, partial3); break;
-        }
+    MainLaunch M;
+    memset(&M, 0, sizeof M);
+    M.recur = recur; M.calibrated = calib != nullptr; M.W = W; M.wpad = wpad;
+    if (n_chunks > 0 && (!recur || n_blk > 0)) {
+        M.n_chunks = n_chunks; M.per_chunk = per_chunk; M.n_blk = n_blk; M.blk_off = 0;
+        M.ks_arr = p->d_ks; M.ke_arr = ke_main; M.partial = p->d_partial;
+        launch_main_nd(p, M, st);
         p->last_launches += 1;
     }
     if (table) {
@@ -2639,22 +3117,46 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
             case 3: launch_table<3>(p, W, wpad, n_chunksT, per_chunkT, st); break;
             default: launch_table<4>(p, W, wpad, n_chunksT, per_chunkT, st); break;
         }
-        p->last_launches += 1;
+        MainLaunch T = M;
+        T.recur = true; T.calibrated = false;
+        T.n_chunks = n_chunks3; T.per_chunk = tail_blocks; T.n_blk = p->n_blk; T.blk_off = 0;
+        T.ks_arr = p->d_ks_tail; T.ke_arr = p->d_ke_fast; T.partial = partial3;
+        T.col = p->d_perm_e; T.grp_b = p->d_grp_b;
+        launch_main_nd(p, T, st);
+        p->last_launches += 2;
     }
     if (p->timing) { CK(cudaEventRecord(p->ev1, st)); p->ev_pending = true; }
-    combine_kernel<<<(W + 31) / 32, dim3(32, COMB_SEG), 0, st>>>(nd, W, wpad, n_chunks, mode, per_chunk, n_blk,
+    combine_kernel<<<(W + 31) / 32, dim3(32, COMB_SEG), 0, st>>>(nd, W, wpad, (n_blk > 0 || !recur) ? n_chunks : 0, mode, per_chunk, n_blk,
                                                                  recur ? p->d_blk_start : nullptr, band0, d.kmax,
                                                                  perm, p->d_wc, p->d_ks, ke_main,
                                                                  p->d_partial, hh_rows, loglr, hd, hh, p->d_marg_opt,
-                                                                 n_chunksT, per_chunkT, p->d_tab_start, p->d_partialT, p->d_ke,
-                                                                 n_chunks3, per_chunk3, n_blk3, p->d_blk_start + p->n_blk_low,
-                                                                 p->d_ks_tail, partial3);
-    p->last_launches += 3;
+                                                                 n_chunksT, per_chunkT, p->d_tblk, p->d_partialT, p->d_ke_fast,
+                                                                 n_chunks3, partial3);
+    p->last_launches += 2;
+    if (recur) {
+        // slow path: whoever the fast kernels could not take goes through the direct kernel (no one, normally:
+        // the CTAs of the three launches then exit at once)
+        slow_compact_kernel<<<gb, tb, 0, st>>>(W, p->d_slow, p->d_slow_list, p->d_slow_n);
+        MainLaunch S = M;
+        S.recur = false;
+        S.n_chunks = n_chunksS; S.per_chunk = per_chunkS; S.ks_arr = p->d_ks; S.ke_arr = p->d_ke; S.partial = p->d_partialS;
+        S.list = p->d_slow_list; S.n_list = p->d_slow_n; S.grid_x = slow_gx;
+        launch_main_nd(p, S, st);
+        slow_finish_kernel<<<slow_gx, CTA_THREADS, 0, st>>>(nd, wpad, n_chunksS, mode, per_chunkS, band0, d.kmax, perm, p->d_wc,
+                                                            p->d_ks, p->d_ke, p->d_partialS, hh_rows, p->d_slow_list,
+                                                            p->d_slow_n, loglr, hd, hh, p->d_marg_opt);
+        p->last_launches += 3;
+    }
     if (mode >= GWIN_MODE_MARG_DIST) {
         marg_dist_kernel<<<(W + 7) / 8, 256, 0, st>>>(W, p->n_marg, p->d_marg_u, p->d_marg_logw, p->d_marg_opt, loglr);
         p->last_launches += 1;
     }
     CK(cudaGetLastError());
+    if (!capturing) {
+        if (!p->ev_done_set) { CK(cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming)); p->ev_done_set = true; }
+        CK(cudaEventRecord(p->ev_done, st));
+        p->last_stream = st;
+    }
     return GWIN_OK;
 }
 
@@ -2662,6 +3164,7 @@ static int ensure_stage(gwin_plan* p, int64_t W) {
     if (W <= p->stage_cap) return GWIN_OK;
     const int nd = p->d.n_det;
     int64_t cap = std::max<int64_t>(W, 1024);
+    CK(cudaDeviceSynchronize());
     cudaFree(p->d_params); cudaFree(p->d_out); cudaFree(p->d_skip);
     cudaFreeHost(p->h_params); cudaFreeHost(p->h_out); cudaFreeHost(p->h_skip);
     p->d_params = p->d_out = nullptr; p->d_skip = nullptr;
@@ -2671,7 +3174,7 @@ static int ensure_stage(gwin_plan* p, int64_t W) {
     CK(cudaMalloc(&p->d_out, sizeof(double) * out_row * cap));
     CK(cudaMalloc(&p->d_skip, cap));
     CK(cudaMallocHost(&p->h_params, sizeof(double) * GWIN_NPARAM * cap));
-    CK(cudaMallocHost(&p->h_out, sizeof(double) * out_row * cap));
+    CK(cudaMallocHost(&p->h_out, sizeof(double) * (out_row * cap + 2)));
     CK(cudaMallocHost(&p->h_skip, cap));
     p->stage_cap = cap;
     return GWIN_OK;
@@ -2715,6 +3218,7 @@ extern "C" int gwin_loglr_batch_calib_host(gwin_plan* p, int mode, int64_t W,
 
 static int ensure_calib_stage(gwin_plan* p, size_t n) {
     if (n <= p->calib_cap) return GWIN_OK;
+    CK(cudaDeviceSynchronize());
     cudaFree(p->d_calib); cudaFreeHost(p->h_calib);
     p->d_calib = p->h_calib = nullptr; p->calib_cap = 0;
     const size_t cap = std::max<size_t>(n, 4096);
@@ -2740,9 +3244,11 @@ static int loglr_batch_host_impl(gwin_plan* p, int mode, int64_t W,
     const int nd = p->d.n_det;
     cudaStream_t st = p->stream;
     memcpy(p->h_params, params, sizeof(double) * GWIN_NPARAM * W);
-    if (p->auto_mchirp && p->kernel != GWIN_KERNEL_DIRECT) {
+    const bool table = p->kernel != GWIN_KERNEL_DIRECT && table_wanted(p, W, calib != nullptr);
+    if (p->auto_mchirp && p->kernel != GWIN_KERNEL_DIRECT && !table) {
         // the block schedule must cover the smallest chirp mass of the batch: quantise it
-        // down to a quarter octave so the (cheap) schedule rebuild is rare
+        // down to a quarter octave so the (cheap) schedule rebuild is rare.  (On the table path the
+        // coverage measured on the device sets it.)
         double mc5_min = 1e300;                   // chirp mass^5 = (m1 m2)^3 / (m1 + m2): no pow per walker
         for (int64_t i = 0; i < W; ++i) {
             if (skip && skip[i]) continue;
@@ -2756,63 +3262,6 @@ static int loglr_batch_host_impl(gwin_plan* p, int mode, int64_t W,
             mc_min = std::min(std::max(mc_min, 0.02), 1e4);
             const double q = std::exp2(std::floor(4.0 * std::log2(mc_min)) / 4.0);
             if (q != p->mchirp_min) { p->mchirp_min = q; p->sched_dirty = true; }
-        }
-        // Experimental (GWIN_TABLE_AUTOREF=1): reference waveform of the moment tables from the
-        // batch itself -- the walker nearest the geometric middle of the chirp-mass range, width from
-        // the range with 25 % of margin.  Re-chosen when a batch leaves the covered range or has
-        // shrunk fourfold; dropped when the ensemble is wide (nothing to gain) or a walker is flagged.
-        static const bool autoref = getenv("GWIN_TABLE_AUTOREF") && atoi(getenv("GWIN_TABLE_AUTOREF")) != 0;
-        if (autoref && !calib && mc_min < 1e300 && (!p->ref_on || p->ref_auto)) {
-            double mc5_max = 0.0;
-            for (int64_t i = 0; i < W; ++i) {
-                if (skip && skip[i]) continue;
-                const double m1 = params[i * stride_walker], m2 = params[i * stride_walker + stride_param];
-                if (!(m1 > 0.0) || !(m2 > 0.0) || !std::isfinite(m1 + m2)) continue;
-                const double pm = m1 * m2;
-                mc5_max = std::max(mc5_max, pm * pm * pm / (m1 + m2));
-            }
-            const double mc_lo = std::pow(mc5_min, 0.2), mc_hi = std::pow(mc5_max, 0.2);
-            const double mc_ref = std::sqrt(mc_lo * mc_hi);
-            const double dev = std::max(std::pow(mc_lo / mc_ref, -5.0 / 3.0) - 1.0, 1.0 - std::pow(mc_hi / mc_ref, -5.0 / 3.0));
-            const double want = 1.25 * dev + 1e-3;
-            if (want >= 0.5) {
-                if (p->ref_on) { p->ref_on = false; p->ref_auto = false; p->tab_dirty = true; }
-            } else {
-                const bool covered = p->ref_on && mc_lo >= p->ref_mc_lo && mc_hi <= p->ref_mc_hi;
-                if (!covered || want < 0.25 * p->ref_width) {
-                    int64_t best = -1;
-                    double best_d = 1e300;
-                    const double mc5_ref = std::pow(mc_ref, 5.0);
-                    for (int64_t i = 0; i < W; ++i) {
-                        if (skip && skip[i]) continue;
-                        bool ok = true;
-                        for (int q2 = 0; q2 < GWIN_NPARAM; ++q2) ok = ok && std::isfinite(params[i * stride_walker + q2 * stride_param]);
-                        const double m1 = params[i * stride_walker], m2 = params[i * stride_walker + stride_param];
-                        if (!ok || !(m1 > 0.0) || !(m2 > 0.0) || !(params[i * stride_walker + 4 * stride_param] > 0.0)) continue;
-                        const double pm = m1 * m2;
-                        const double dd = std::fabs(pm * pm * pm / (m1 + m2) - mc5_ref);
-                        if (dd < best_d) { best_d = dd; best = i; }
-                    }
-                    if (best >= 0) {
-                        double row[GWIN_NPARAM];
-                        for (int q2 = 0; q2 < GWIN_NPARAM; ++q2) row[q2] = params[best * stride_walker + q2 * stride_param];
-                        const double m1 = row[0], m2 = row[1];
-                        const double mc_row = std::pow(m1 * m2, 0.6) / std::pow(m1 + m2, 0.2);
-                        // the row is not exactly at mc_ref: widen by its offset
-                        const double off = std::fabs(std::pow(mc_row / mc_ref, -5.0 / 3.0) - 1.0);
-                        const double width = std::exp2(std::ceil(std::log2(want + 1.25 * off)));
-                        if (width < 0.5) {
-                            gwin_plan_set_reference(p, row, width);
-                            p->ref_auto = true;
-                            const double cov = width / 1.25 - off;      // covered relative deviation in Mc^(-5/3)
-                            p->ref_mc_lo = mc_row * std::pow(1.0 + cov, -0.6);
-                            p->ref_mc_hi = cov < 1.0 ? mc_row * std::pow(1.0 - cov, -0.6) : 1e300;
-                        } else if (p->ref_on) {
-                            p->ref_on = false; p->ref_auto = false; p->tab_dirty = true;
-                        }
-                    }
-                }
-            }
         }
     }
     CK(cudaMemcpyAsync(p->d_params, p->h_params, sizeof(double) * GWIN_NPARAM * W, cudaMemcpyHostToDevice, st));
@@ -2832,29 +3281,22 @@ static int loglr_batch_host_impl(gwin_plan* p, int mode, int64_t W,
     double* d_hh = d_hd + 2 * (size_t)nd * p->stage_cap;
     rc = loglr_batch_impl(p, mode, W, p->d_params, stride_walker, stride_param,
                           calib ? p->d_calib : nullptr, cstride_walker, cstride_value,
-                          skip ? p->d_skip : nullptr, d_lr, d_hd, d_hh, st);
+                          skip ? p->d_skip : nullptr, d_lr, hd ? d_hd : nullptr, hh ? d_hh : nullptr, st);
     if (rc) return rc;
     double* h_lr = p->h_out;
     double* h_hd = p->h_out + p->stage_cap;
     double* h_hh = h_hd + 2 * (size_t)nd * p->stage_cap;
+    int* h_slow = reinterpret_cast<int*>(p->h_out + (1 + 3 * (size_t)nd) * p->stage_cap);
+    *h_slow = 0;
     CK(cudaMemcpyAsync(h_lr, d_lr, sizeof(double) * W, cudaMemcpyDeviceToHost, st));
     if (hd) CK(cudaMemcpyAsync(h_hd, d_hd, sizeof(double) * 2 * nd * W, cudaMemcpyDeviceToHost, st));
     if (hh) CK(cudaMemcpyAsync(h_hh, d_hh, sizeof(double) * nd * W, cudaMemcpyDeviceToHost, st));
-    int flagged = 0;
-    if (p->ref_on && p->ref_auto && p->d_violation)
-        CK(cudaMemcpyAsync(&flagged, p->d_violation, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (p->kernel != GWIN_KERNEL_DIRECT) CK(cudaMemcpyAsync(h_slow, p->d_slow_n, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (flagged) {
-        // the automatic reference did not cover this batch after all: drop it and evaluate again
-        CK(cudaMemset(p->d_violation, 0, sizeof(int)));
-        p->ref_on = false; p->ref_auto = false; p->tab_dirty = true;
-        p->ref_mc_lo = 1e300; p->ref_mc_hi = 0.0;
-        const bool keep = p->auto_mchirp;
-        p->auto_mchirp = false;                  // no new automatic reference for the repeat
-        const int rc2 = loglr_batch_host_impl(p, mode, W, params, stride_walker, stride_param,
-                                              calib, cstride_walker, cstride_value, skip, loglr, hd, hh);
-        p->auto_mchirp = keep;
-        return rc2;
+    // a batch that sent more than a few walkers down the slow path: re-measure what the schedule and
+    // the tables have to cover before the next batch (this batch's results are right as they are)
+    if (*h_slow > 4 + W / 64 && !p->cover_manual) {
+        if (table) p->replan = true;
     }
     memcpy(loglr, h_lr, sizeof(double) * W);
     if (hd) memcpy(hd, h_hd, sizeof(double) * 2 * nd * W);
@@ -2886,8 +3328,10 @@ extern "C" int gwin_generate_calib_host(gwin_plan* p, const double* params, cons
         CK(cudaMemcpyAsync(p->d_calib, p->h_calib, sizeof(double) * nv, cudaMemcpyHostToDevice, st));
     }
     double* hh_rows = p->d_wc + (size_t)NCOEF(d.n_det) * wpad;
+    FastArgs F;
+    memset(&F, 0, sizeof F);
     walker_setup_kernel<<<1, 32, 0, st>>>(d, 1, wpad, p->d_params, GWIN_NPARAM, 1, nullptr, nullptr, p->d_wc, p->d_ks, p->d_ke, hh_rows,
-                                          calib ? p->d_calib : nullptr, (int64_t)nv, 1, nullptr, 0, nullptr, nullptr, 0);
+                                          calib ? p->d_calib : nullptr, (int64_t)nv, 1, F);
     generate_len_kernel<<<1, 1, 0, st>>>(d, p->d_params, p->d_ke);
     double2* dout = nullptr;
     CK(cudaMalloc(&dout, sizeof(double2) * (size_t)d.n_det * d.n_f));

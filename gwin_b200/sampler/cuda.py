@@ -257,12 +257,33 @@ class _DeviceEnsemble(BaseMCMCSampler):
         if self._world > 1 and self._gath.numel() < self._world * (-(-W // self._world)):
             self._gath = torch.empty(self._world * (-(-W // self._world)), **f64)
             self._local = torch.zeros(-(-W // self._world), **f64)
+        self._declare_coverage()
         self._eval_q(W, p.view(W, nd), logp, skip, params, loglr)
         logl = torch.where(torch.isneginf(logp), torch.zeros_like(loglr), loglr).view(nt, nw)
         lnprob = logl * self._betas.view(-1, 1) + logp.view(nt, nw)
         if bool(torch.isposinf(lnprob).any()) or bool(torch.isnan(lnprob).any()):
             raise ValueError("The initial lnprob was NaN or +inf.")
         self._p, self._logl, self._lnprob = p, logl.contiguous(), lnprob.contiguous()
+
+    def _declare_coverage(self, n=4096):
+        """The moment tables of the likelihood must cover what the sampler can propose: points
+        spread over the prior box go through the device prior kernel (boundary conditions,
+        mchirp/q -> masses) and are declared to the plan (``gwin_plan_cover_device``).  Inside
+        a recorded CUDA graph the library could not measure a batch itself."""
+        torch, lib = self._torch, self._lib
+        spec = self._spec
+        nd = self._ndim
+        lo = numpy.array([spec.lo[i] for i in range(nd)])
+        hi = numpy.array([spec.hi[i] for i in range(nd)])
+        rs = numpy.random.RandomState(12345)
+        q = torch.tensor(lo + (hi - lo) * rs.uniform(size=(n, nd)), dtype=torch.float64, device=self._dev)
+        logp = torch.empty(n, dtype=torch.float64, device=self._dev)
+        skip = torch.empty(n, dtype=torch.uint8, device=self._dev)
+        params = torch.empty((_lib.GWIN_NPARAM, n), dtype=torch.float64, device=self._dev)
+        st = torch.cuda.current_stream(self._dev).cuda_stream
+        _lib.check(lib.gwin_ens_prior(C.byref(spec), n, q.data_ptr(), logp.data_ptr(),
+                                      skip.data_ptr(), params.data_ptr(), st))
+        self._plan.cover(params, param_major=True)
 
     def run(self, niterations, **kwargs):
         """``niterations`` steps.  All arguments of one iteration are constant -- the

@@ -45,8 +45,9 @@ extern "C" {
 #define GWIN_KERNEL_AUTO       0
 #define GWIN_KERNEL_DIRECT     1  /* per-bin FP64 phase + sincos                                  */
 #define GWIN_KERNEL_RECURRENCE 2  /* block-anchored chirp-phasor recurrence + Horner accumulation */
-#define GWIN_KERNEL_TABLE      3  /* recurrence below k_split, per-plan moment tables + NUFFT
-                                     interpolation above (what AUTO selects; uncalibrated only)  */
+#define GWIN_KERNEL_TABLE      3  /* per-plan moment tables + NUFFT interpolation wherever sub-blocks of
+                                     >= 128 bins qualify, recurrence below and for the walkers' last
+                                     bins (what AUTO selects on long segments; uncalibrated only) */
 
 typedef struct gwin_plan gwin_plan;
 
@@ -87,22 +88,43 @@ int gwin_plan_cutoffs(const gwin_plan* plan, int64_t* kmin, int64_t* kmax);
 int gwin_plan_lognl(const gwin_plan* plan, double* lognl_total, double* lognl_det);
 
 /* Tuning knobs: kernel = GWIN_KERNEL_*, phase_tol = max block-polynomial phase
- * error [rad] of the recurrence kernel (default 1e-11), mchirp_min [Msun] =
- * smallest chirp mass the block schedule must cover (default 0.5). */
+ * error [rad] of the recurrence kernel (default 1e-10), mchirp_min [Msun] =
+ * smallest chirp mass the block schedule must cover (default 0.5; the host entry points and the
+ * table path derive it from the batches unless it is set here).  0 leaves a value unchanged. */
 int gwin_plan_configure(gwin_plan* plan, int kernel, double phase_tol, double mchirp_min);
 
 /*
- * Optional reference waveform for the moment tables of GWIN_KERNEL_TABLE (no counterpart in the
- * reference: a property of this implementation).  params: HOST [GWIN_NPARAM], a point near the
- * middle of the batches to come; rel_width: bound on |(Mc/Mc_ref)^(-5/3) - 1| over those batches.
- * The tables are rebuilt relative to the reference waveform's phase, so that only a walker's
- * deviation from it is expanded per sub-block: the narrower the ensemble, the longer the sub-blocks
- * (DESIGN.md 4.6/9).  A walker outside the range sets a flag instead of returning a wrong number:
- * gwin_plan_table_violations reads and clears it (non-zero: re-evaluate that batch after a wider
- * gwin_plan_set_reference, or after clearing the reference with params = NULL).
+ * Coverage of the moment tables of GWIN_KERNEL_TABLE / AUTO (no counterpart in the reference: a
+ * property of this implementation).  The tables are built for a range of the
+ * Newtonian chirp coefficient (i.e. of the chirp mass) and a bound on how far the other phase
+ * coefficients (mass ratio, spins, tides) lie from those of an equal-mass, non-spinning chirp.
+ * By default the library measures both on the first batch that uses the tables (one small kernel
+ * and one synchronisation; the host entry points measure again after a batch that sent many walkers
+ * down the slow path).  A caller that knows its prior declares it instead:
+ * gwin_plan_cover_host / _device take W parameter points (layout as gwin_loglr_batch_strided; e.g.
+ * a few thousand prior draws), widen their range by a margin, and add it to what is covered;
+ * W = 0 returns to automatic coverage.  gwin_plan_cover_device synchronises `stream`.
+ * Walkers outside the coverage are never wrong, only slow: see gwin_plan_slow_path.
  */
-int gwin_plan_set_reference(gwin_plan* plan, const double* params, double rel_width);
-int gwin_plan_table_violations(gwin_plan* plan, int* flag);
+int gwin_plan_cover_host(gwin_plan* plan, int64_t W, const double* params,
+                         int64_t stride_walker, int64_t stride_param);
+int gwin_plan_cover_device(gwin_plan* plan, int64_t W, const double* params,
+                           int64_t stride_walker, int64_t stride_param, void* stream);
+
+/* Sub-blocks, reference chirps and bytes of the current moment tables (0 if none), and the first
+ * bin they take (kmax if none). */
+int gwin_plan_table_info(gwin_plan* plan, int64_t* n_subblocks, int64_t* n_references,
+                         int64_t* bytes, int64_t* k_split);
+
+/*
+ * Slow path.  The recurrence schedule holds for chirp masses >= mchirp_min and the moment tables for
+ * their coverage; a walker outside either (seen when its coefficients are set up, or -- for the
+ * tables -- when its own truncation estimate of a sub-block is too large) is evaluated by the
+ * direct kernel instead (per-bin phase + sincos: ~20x slower, same tolerance).  Returns the number of
+ * such walkers since the previous call and resets it (synchronises the device).  A count that
+ * keeps growing means the coverage should be re-declared.
+ */
+int gwin_plan_slow_path(gwin_plan* plan, int64_t* n_walkers);
 
 /*
  * Distance-marginalisation grid == MarginalizedGaussianNoise._setup_prior
@@ -146,7 +168,8 @@ int gwin_plan_set_calibration(gwin_plan* plan, int n_points, const double* splin
  *   hh      [W][n_det] <h|h> per detector ({det}_optimal_snrsq); may be NULL
  *   stream  cudaStream_t (0 = legacy default stream).  Asynchronous.
  *
- * Calls on one plan share its workspace and must be issued on one stream at a time.
+ * Calls on one plan share its workspace; a call on another stream than the previous call waits for
+ * it on the device (cudaStreamWaitEvent), so callers need no ordering of their own.
  * Points with non-finite / non-physical parameters return loglr = -inf, never NaN.
  */
 int gwin_loglr_batch(gwin_plan* plan, int mode, int64_t W,

@@ -369,22 +369,20 @@ class PlanModel(object):
         return self.finish(w, S, marg)
 
     # -- loglr_table_kernel -------------------------------------------------------
-    # Above k_split the band is cut into sub-blocks of m (a power of two) bins.  Per sub-block
-    # the moments M_n(nu) = sum_j (j/h)^n T[kc+j] e^{-2 pi i nu j} are tabulated on the grid
-    # nu = g/(2m) (zero-padded FFT of the kernel-deconvolved sequence); per walker the block sum
-    # is e^{-2 pi i th0} sum_n c_n M_n(nu) with the M_n interpolated by a TAB_W-tap
-    # exponential-of-semicircle kernel and c_n the Taylor coefficients of e^{-2 pi i R(j)},
-    # R = the quadratic..sextic part of the polynomial through TAB_PH + 1 exact phase samples.
-    TAB_DEG, TAB_W, TAB_MIN, TAB_MAX, TAB_RHO, TAB_PH = 8, 13, 128, 4096, 0.025, 6
-
-    @classmethod
-    def table_nodes(cls, m):
-        """TAB_PH + 1 nodes of the phase polynomial on [0, m-1]: rounded Chebyshev-Lobatto points
-        with the centre moved to m/2."""
-        n = cls.TAB_PH
-        x = [int(round((m - 1) * 0.5 * (1 - math.cos(math.pi * i / n)))) for i in range(n + 1)]
-        x[n // 2] = m // 2
-        return x
+    # Above k_split the band is cut into sub-blocks of m bins (2^k or 3 2^(k-1)).  The TaylorF2
+    # phase is a combination of 11 fixed functions of f, so its Taylor coefficients about a
+    # sub-block's centre are a matrix (taylor_matrix) applied to the walker's phase coefficients.
+    # Per sub-block there are K reference chirps (equal masses, no spin, a0 on a uniform grid over
+    # the covered range) whose exact non-linear phase is baked into the tabulated moments
+    #   M_n(nu) = sum_j (j/h)^n T[kc+j] e^{-2 pi i N_ref(j)} e^{-2 pi i nu j}      (grid nu = g/(2m))
+    # and the block sum is e^{-2 pi i th0} sum_n e_n M_n(nu), the M_n interpolated by a TAB_W-tap
+    # exponential-of-semicircle kernel, e_n the Taylor coefficients of e^{-2 pi i R},
+    # R = sum_{n=2..8} (t_n - t_n^ref) s^n.  The dropped e_9, e_10 give the run-time estimate
+    # that sends a walker outside the coverage to the slow path.
+    TAB_DEG, TAB_NT, TAB_NTH, TAB_W, TAB_MIN, TAB_MAX = 8, 9, 13, 13, 128, 4096
+    TAB_EST_DESIGN, TAB_EST_MAX, TAB_RHO_DESIGN, TAB_RHO_MAX = 2.0e-9, 1.6e-8, 0.05, 0.10
+    BASIS = (("a0", -5, 0), ("a2", -3, 0), ("a3", -2, 0), ("a4", -1, 0), ("a5", 0, 0), ("b5", 0, 1),
+             ("a6", 1, 0), ("b6", 1, 1), ("a7", 2, 0), ("a10", 5, 0), ("a12", 7, 0))
 
     @classmethod
     def table_sizes(cls):
@@ -397,56 +395,137 @@ class PlanModel(object):
             m *= 2
         return sorted(out)
 
-    def build_table_schedule(self):
-        band0 = max(self.kmin, self.istart)
-        # with a reference waveform (set_reference) the bounds apply to the batch's deviation from it
-        ref = getattr(self, "ref", None)
-        wfac = min(1.0, 1.3 * ref[1] + 0.02) if ref else 1.0
-        chirp = wfac * 2.0 * (3. / 128.) * (PI * self.mchirp_min * MTSUN) ** (-5. / 3)
-        sizes = self.table_sizes()
-        # worst |prod (j - x_i)| over the sub-block, per size (interpolation error factor)
-        self._tab_omega = {}
-        for m in sizes:
-            x = np.array(self.table_nodes(m), dtype=float)
-            j = np.arange(m, dtype=float)
-            self._tab_omega[m] = float(np.max(np.abs(np.prod(j[:, None] - x[None, :], axis=1))))
-        kk = max(band0, 1)
-        while kk < self.kmax and self._table_m(kk, chirp, sizes) < self.TAB_MIN:
-            kk += 64
-        self.k_split = min(kk, self.kmax)
-        k = self.k_split
-        self.tab_start, self.tab_m = [], []
-        while k < self.kmax:
-            m = max(self._table_m(k, chirp, sizes), self.TAB_MIN)
-            while m > self.TAB_MIN and k + m > self.kmax:
-                m = max(s for s in sizes if s < m)
-            if k + m > self.kmax:           # sub-blocks lie wholly inside the band
-                break
-            self.tab_start.append(k)
-            self.tab_m.append(m)
-            k += m
-        self.tab_start.append(k)
-        return self.tab_start
+    def taylor_matrix(self, kc, h):
+        """c[i][n]: basis function i at f = (kc + h s) delta_f as a series in s (long double)."""
+        ld = np.longdouble
+        n = self.TAB_NTH
+        fc = ld(kc) * ld(self.delta_f)
+        eps = ld(h) / ld(kc)
+        ls = np.zeros(n, dtype=ld)
+        ls[0] = np.log(fc) / 3
+        for k in range(1, n):
+            ls[k] = ld(-1) ** (k + 1) * eps ** k / k / 3
+        out = np.zeros((len(self.BASIS), n), dtype=ld)
+        for i, (_, pw, lg) in enumerate(self.BASIS):
+            q = ld(pw) / 3
+            bs = np.zeros(n, dtype=ld)
+            bs[0] = fc ** q
+            for k in range(n - 1):
+                bs[k + 1] = bs[k] * (q - k) / (k + 1) * eps
+            out[i] = np.convolve(bs, ls)[:n] if lg else bs
+        return out
 
-    def _table_m(self, k, chirp, sizes):
-        """Longest admissible sub-block starting at bin k: |R| <= TAB_RHO at its edge and the
-        degree-TAB_PH interpolation of the phase good to phase_tol."""
-        f = k * self.delta_f
-        K = 1.0
-        for i in range(2):
-            K *= (5. / 3 + i)
-        d2 = chirp * K * self.delta_f ** 2 * f ** (-5. / 3 - 2)
-        n = self.TAB_PH + 1
-        K = 1.0
-        for i in range(n):
-            K *= (5. / 3 + i)
-        dn = chirp * K * self.delta_f ** n * f ** (-5. / 3 - n)
-        best = 0
-        for m in sizes:
-            if 0.5 * d2 * (0.5 * m) ** 2 <= self.TAB_RHO and \
-                    dn / math.factorial(n) * self._tab_omega[m] <= self.phase_tol:
-                best = m
-        return best
+    def coef_vector(self, w):
+        return np.array([w[name] for name, _, _ in self.BASIS])
+
+    def ref_walker(self, a0):
+        """The reference chirp of Newtonian coefficient a0: equal masses, no spins, no tides."""
+        piM = (a0 * (64.0 * PI / 3.0)) ** -0.6
+        m = 0.5 * piM / (PI * MTSUN)
+        return self.walker([m, m, 0, 0, 1.0, 0, 0, 0, 0, 0, self.epoch, 0, 0])
+
+    def cover_stats(self, rows):
+        """cover_stats_kernel + cover_widen: (a_lo, a_hi, dev[11]) of a set of parameter rows."""
+        a0, dev = [], np.zeros(len(self.BASIS))
+        for p in rows:
+            q = list(p)
+            q[6] = 0.0
+            w = self.walker(q)
+            if not w['valid']:
+                continue
+            a = self.coef_vector(w)
+            ar = self.coef_vector(self.ref_walker(a[0]))
+            d = np.abs(a - ar)
+            d[0] = d[4] = 0.0
+            dev = np.maximum(dev, d)
+            a0.append(a[0])
+        lo, hi = min(a0), max(a0)
+        pad = 0.05 * (hi - lo) + 2e-3 * hi
+        return max(lo - pad, 0.25 * lo), hi + pad, 1.5 * dev
+
+    def table_admissible(self, c, dev, da_half):
+        n = self.TAB_NTH
+        u = np.zeros(n)
+        for k in range(2, n):
+            u[k] = TWOPI * float(da_half * abs(c[0][k]) + np.dot(dev[1:], np.abs(c[1:, k]).astype(float)))
+        e = np.zeros(n)
+        e[0] = 1.0
+        for m in range(2, n):
+            e[m] = sum(k * u[k] * e[m - k] for k in range(2, m + 1)) / m
+        return e[self.TAB_DEG + 1:].sum() <= self.TAB_EST_DESIGN and u[2:self.TAB_DEG + 1].sum() <= self.TAB_RHO_DESIGN
+
+    def table_refs_needed(self, cover, k, m, kmax_refs=4096):
+        a_lo, a_hi, dev = cover
+        c = self.taylor_matrix(k + m // 2, 0.5 * m)
+        half = 0.5 * (a_hi - a_lo)
+        if self.table_admissible(c, dev, half):
+            return 1
+        if not self.table_admissible(c, dev, half / kmax_refs):
+            return 0
+        lo, hi = half / kmax_refs, half
+        for _ in range(14):
+            mid = math.sqrt(lo * hi)
+            if self.table_admissible(c, dev, mid):
+                lo = mid
+            else:
+                hi = mid
+        return min(kmax_refs, int(math.ceil(half / lo)))
+
+    def build_tables(self, cover, K0=64.0):
+        """table_schedule + the lazily filled tables for the coverage (a_lo, a_hi, dev)."""
+        self.cover = cover
+        band0 = max(max(self.kmin, self.istart), 1)
+        f0 = band0 * self.delta_f
+        sizes = self.table_sizes()
+
+        def pick(k):
+            cap = max(1.0, K0 * (k * self.delta_f / f0) ** (-11.0 / 9.0))
+            for m in reversed(sizes):
+                if k + m > self.kmax:
+                    continue
+                K = self.table_refs_needed(cover, k, m)
+                if 0 < K <= cap:
+                    return m, K
+            return 0, 0
+        bs = list(self.blk_start)
+        ib = 0
+        while ib < len(bs) - 1 and pick(bs[ib])[0] == 0:
+            k_next = bs[ib] + 64
+            while ib < len(bs) - 1 and bs[ib] < k_next:
+                ib += 1
+        self.tblk = []
+        self.k_split = self.k_tab_end = self.kmax
+        if ib >= len(bs) - 1:
+            return
+        k = bs[ib]
+        self.k_split = k
+        while k < self.kmax:
+            m, K = pick(k)
+            if m == 0:
+                break
+            self.tblk.append(dict(start=k, m=m, K=K, da=(cover[1] - cover[0]) / K, c=self.taylor_matrix(k + m // 2, 0.5 * m).astype(float),
+                                  tabs={}, tref={}))
+            k += m
+        self.k_tab_end = k
+        self._hat = {}
+
+    def _table(self, B, r, d):
+        if (r, d) not in B['tabs']:
+            m, L, s = B['m'], 2 * B['m'], B['start']
+            if m not in self._hat:
+                self._hat[m] = self.es_hat((np.arange(m) - m // 2) / float(L), self.TAB_W, 2.30 * self.TAB_W)
+            wr = self.ref_walker(self.cover[0] + (r + 0.5) * B['da'])
+            tr = self.coef_vector(wr).dot(B['c'])
+            B['tref'][r] = tr
+            jc = np.arange(m) - m // 2
+            nref = (self.phase_turns(wr, s + m // 2 + jc) - tr[0]) - tr[1] * (jc / (m / 2.0))
+            seg = self.T[d, s:s + m] * np.exp(-2j * PI * nref) / self._hat[m]
+            g = np.arange(L)
+            rows = np.zeros((self.TAB_DEG + 1, L), dtype=complex)
+            for n in range(self.TAB_DEG + 1):
+                rows[n] = np.fft.fft(seg * (jc / (m / 2.0)) ** n, L) * np.exp(2j * np.pi * ((g * (m // 2)) % L) / L)
+            B['tabs'][(r, d)] = rows
+        return B['tabs'][(r, d)]
 
     @staticmethod
     def es_kernel(x, w, beta):
@@ -462,100 +541,65 @@ class PlanModel(object):
         ph = cls.es_kernel(x, w, beta)
         return (ph[None, :] * np.cos(2 * np.pi * np.asarray(xi)[:, None] * x[None, :])).sum(axis=1) * (w / nq)
 
-    def set_reference(self, ref_row=None, rel_width=0.0):
-        """gwin_plan_set_reference: tables relative to the waveform of ``ref_row``; ``rel_width``
-        bounds |(Mc/Mc_ref)^(-5/3) - 1| over the batches to come."""
-        self.ref = (np.asarray(ref_row, dtype=float), float(rel_width)) if ref_row is not None else None
-
-    def build_tables(self):
-        self.build_table_schedule()
-        w, beta, N = self.TAB_W, 2.30 * self.TAB_W, self.TAB_DEG
-        self.tab = []
-        self.tab_nref = []
-        ref = getattr(self, "ref", None)
-        ref_w = self.walker(ref[0]) if ref else None
-        hat = {}
-        for b, (s, m) in enumerate(zip(self.tab_start[:-1], self.tab_m)):
-            L = 2 * m
-            if m not in hat:
-                hat[m] = self.es_hat((np.arange(m) - m // 2) / float(L), w, beta)
-            jc = np.arange(m) - m // 2
-            g = np.arange(L)
-            rows = np.zeros((self.n_det, N + 1, L), dtype=complex)
-            base = 1.0
-            if ref_w is not None:
-                # tab_ref_kernel: the reference's exact phase minus its centre value and an end-point
-                # slope; the tables hold T e^{-2 pi i N_ref}
-                th = self.phase_turns(ref_w, s + np.arange(m))
-                nref = th - th[m // 2] - (th[-1] - th[0]) / (m - 1) * jc
-                self.tab_nref.append(nref[np.array(self.table_nodes(m))])
-                base = np.exp(-2j * PI * nref)
-            for d in range(self.n_det):
-                seg = self.T[d, s:s + m] * base
-                for n in range(N + 1):
-                    a = seg * (jc / (m / 2.0)) ** n / hat[m]
-                    rows[d, n] = np.fft.fft(a, L) * np.exp(2j * np.pi * ((g * (m // 2)) % L) / L)
-            self.tab.append(rows)
-
     def table_block(self, w, b, d):
-        """One full sub-block for one detector: the kernel's arithmetic."""
-        s, m = self.tab_start[b], self.tab_m[b]
+        """One full sub-block for one detector: the kernel's arithmetic.  Sets ``last_est`` /
+        ``last_rho`` (what the kernel compares with TAB_EST_MAX / TAB_RHO_MAX)."""
+        B = self.tblk[b]
+        s, m = B['start'], B['m']
         N, W, beta = self.TAB_DEG, self.TAB_W, 2.30 * self.TAB_W
-        h = m / 2.0
-        nodes = np.array(self.table_nodes(m))
-        ic = self.TAB_PH // 2
-        sn = (nodes - m // 2) / h
-        th = self.phase_turns(w, s + nodes)
-        keep = [i for i in range(len(nodes)) if i != ic]
-        V = np.array([[sn[i] ** k for k in range(1, self.TAB_PH + 1)] for i in keep])
-        v = th - th[ic]
-        if getattr(self, "ref", None):
-            v = v - self.tab_nref[b]                    # phase relative to the reference waveform
-        t = np.concatenate([[0.0], np.linalg.solve(V, v[keep])])    # t_k s^k, t_0 = 0
-        self.last_rho = TWOPI * float(np.sum(np.abs(t[2:])))
-        th0 = th[ic] + (s + m // 2) * w['tau'][d]
+        h, L, kc = m / 2.0, 2 * m, s + m // 2
+        t = self.coef_vector(w).dot(B['c'])[:self.TAB_NT]
+        r = min(max(int((w['a0'] - self.cover[0]) / B['da']), 0), B['K'] - 1)
+        rows = self._table(B, r, d)
+        dt = t - B['tref'][r][:self.TAB_NT]
+        th0 = t[0] + kc * w['tau'][d]
         nu = t[1] / h + w['tau'][d]
-        # Taylor coefficients of exp(U), U = -2 pi i sum_{k>=2} t_k s^k:  n e_n = sum_k k u_k e_{n-k}
-        u = -2j * PI * t
-        c = np.zeros(N + 1, dtype=complex)
-        c[0] = 1.0
-        for n in range(1, N + 1):
-            acc = 0j
-            for k in range(2, min(n, self.TAB_PH) + 1):
-                acc += k * u[k] * c[n - k]
-            c[n] = acc / n
-        x = (nu - math.floor(nu)) * (2 * m)
+        u = -2j * PI * dt
+        e = np.zeros(N + 3, dtype=complex)
+        e[0] = 1.0
+        for n in range(2, N + 3):
+            e[n] = sum(k * u[k] * e[n - k] for k in range(2, min(n, N) + 1)) / n
+        eps = h / kc
+        self.last_est = float(np.abs(e[N + 1:].real).sum() + np.abs(e[N + 1:].imag).sum()
+                              + 1.2 * eps * abs(u[N]) * (1 + 1.2 * eps))
+        self.last_rho = TWOPI * float(np.sum(np.abs(dt[2:])))
+        x = (nu - math.floor(nu)) * L
         g0 = int(math.ceil(x - W / 2.0))
         taps = g0 + np.arange(W)
         wt = self.es_kernel(x - taps, W, beta)
-        M = (self.tab[b][d][:, taps % (2 * m)] * wt[None, :]).sum(axis=1)
-        return np.exp(-2j * PI * (th0 - math.floor(th0))) * np.dot(c, M)
+        M = (rows[:, taps % L] * wt[None, :]).sum(axis=1)
+        return np.exp(-2j * PI * (th0 - math.floor(th0))) * np.dot(e[:N + 1], M)
 
     def loglr_table(self, p, marg=False):
+        """Returns (loglr, hd, hh) and sets ``slow`` when the walker would leave the table path."""
         w = self.walker(p)
         if not w['valid']:
             return -np.inf, None, None
         ks, ke = w['ks'], w['ke']
         S = np.zeros(self.n_det, dtype=complex)
-        # low band: any exact method (the recurrence kernel on the GPU)
-        k_hi = min(ke, self.k_split)
-        if k_hi > ks:
-            k = np.arange(ks, k_hi)
+        self.slow = not (self.cover[0] <= w['a0'] <= self.cover[1])
+        self.worst_est = 0.0
+
+        def exact(k_lo, k_hi):
+            k = np.arange(k_lo, k_hi)
             psi = self.phase_turns(w, k)
             for d in range(self.n_det):
                 S[d] += np.sum(self.T[d, k] * np.exp(-2j * PI * (psi + k * w['tau'][d])))
+        # low band: any exact method (the recurrence kernel on the GPU)
+        if min(ke, self.k_split) > ks:
+            exact(ks, min(ke, self.k_split))
         done = self.k_split
-        for b, (s, m) in enumerate(zip(self.tab_start[:-1], self.tab_m)):
-            if s + m > ke:
+        for b, B in enumerate(self.tblk):
+            if B['start'] + B['m'] > ke:
                 break
             for d in range(self.n_det):
                 S[d] += self.table_block(w, b, d)
-            done = s + m
+                self.worst_est = max(self.worst_est, self.last_est)
+                if self.last_est > self.TAB_EST_MAX or self.last_rho > self.TAB_RHO_MAX:
+                    self.slow = True
+            done = B['start'] + B['m']
         if ke > done:                   # the tail: any exact method (second recurrence pass)
-            k = np.arange(done, ke)
-            psi = self.phase_turns(w, k)
-            for d in range(self.n_det):
-                S[d] += np.sum(self.T[d, k] * np.exp(-2j * PI * (psi + k * w['tau'][d])))
+            exact(done, ke)
         return self.finish(w, S, marg)
 
     # -- loglr_recur_kernel -------------------------------------------------------

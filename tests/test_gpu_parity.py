@@ -130,7 +130,7 @@ def test_gps_epoch(cfg1):
     model = cfg.cuda_model()
     rng = np.random.default_rng(5)
     P = util.draw_bbh(rng, 64, cfg)
-    for kernel in (1, 2):
+    for kernel in (1, 2, 3, 0):
         model.plan.configure(kernel=kernel)
         lr, hd, hh = model.plan.loglr_host(P)
         lr0, hd0, hh0 = _oracle_batch(cfg.oracle(), P)
@@ -183,7 +183,7 @@ def test_edge_cases(cfg2):
     P[7, 0], P[7, 1] = 1.0, 1.0  # BNS-like in an 8 s segment: clipped at kmax
     skip = np.zeros(12, dtype=np.uint8)
     skip[8] = 1
-    for kernel in (1, 2):
+    for kernel in (1, 2, 3, 0):
         model.plan.configure(kernel=kernel)
         lr, hd, hh = model.plan.loglr_host(P, skip=skip)
         assert not np.any(np.isnan(lr))
@@ -244,7 +244,7 @@ def test_detector_counts_unit_psd_fupper(dets):
     assert (model._kmin, model._kmax) == (orc._kmin, orc._kmax)
     rng = np.random.default_rng(11)
     P = util.draw_bbh(rng, 40, cfg)
-    for kernel in (1, 2):
+    for kernel in (1, 2, 3, 0):
         model.plan.configure(kernel=kernel)
         lr, hd, hh = model.plan.loglr_host(P)
         lr0, hd0, hh0 = O.batch_loglr(orc, P)
@@ -301,7 +301,7 @@ def test_tidal_deformabilities(cfg3):
     P2[:, 11] = rng.uniform(0., 3000., len(P))
     P2[:, 12] = rng.uniform(0., 3000., len(P))
     lr0, hd0, hh0 = _oracle_batch(cfg3.oracle(), P2)
-    for kernel in (1, 2):
+    for kernel in (1, 2, 3, 0):
         model.plan.configure(kernel=kernel)
         lr, hd, hh = model.plan.loglr_host(P2)
         _check(lr, hd, hh, lr0, hd0, hh0, "tidal k%d" % kernel)
@@ -343,7 +343,7 @@ def test_golden_fixtures(path):
         calib = g["calib_values"]
     assert (model._kmin, model._kmax) == (int(g["kmin"]), int(g["kmax"]))
     assert abs(model.lognl - float(g["lognl"])) <= 1e-9 * abs(float(g["lognl"]))
-    for kernel in (1, 2):
+    for kernel in (1, 2, 3, 0):
         model.plan.configure(kernel=kernel)
         lr, hd, hh = model.plan.loglr_host(g["params"], mode=mode, calib=calib)
         _check(lr, hd, hh, g["loglr"], g["hd"], g["hh"], "%s k%d" % (os.path.basename(path), kernel))
@@ -375,7 +375,7 @@ def test_distance_marginalization(cfg2, phase):
     mode = 3 if phase else 2
     for what, Q in (("drawn", P), ("1 Mpc", P1)):
         lr0, hd0, hh0 = _oracle_batch(orc, Q)
-        for kernel in (1, 2):
+        for kernel in (1, 2, 3, 0):
             model.plan.configure(kernel=kernel)
             lr, hd, hh = model.plan.loglr_host(Q, mode=mode)
             _check(lr, hd, hh, lr0, hd0, hh0, "margdist %s k%d" % (what, kernel))
@@ -465,7 +465,7 @@ def test_calibration_cubic_spline(cfg2, n_points, fmax):
     for marg in (False, True):
         orc = cfg2.oracle(phase_marginalization=marg, recalibration=rec)
         lr0, hd0, hh0 = _calib_oracle_batch(orc, P, vals, names)
-        for kernel in (1, 2):
+        for kernel in (1, 2, 3, 0):
             model.plan.configure(kernel=kernel)
             lr, hd, hh = model.plan.loglr_host(P, mode=int(marg), calib=vals)
             _check(lr, hd, hh, lr0, hd0, hh0, "calib n=%d marg=%d k%d" % (n_points, marg, kernel))
@@ -499,7 +499,7 @@ def test_calibration_bns_long_segment():
     model = cfg.cuda_model()
     model.plan.set_calibration([rec[d].spline_points for d in cfg.dets])
     lr0, hd0, hh0 = _calib_oracle_batch(cfg.oracle(recalibration=rec), P, vals, names)
-    for kernel in (1, 2):
+    for kernel in (1, 2, 3, 0):
         model.plan.configure(kernel=kernel)
         lr, hd, hh = model.plan.loglr_host(P, calib=vals)
         _check(lr, hd, hh, lr0, hd0, hh0, "calib bns k%d" % kernel)
@@ -520,6 +520,11 @@ def test_four_detectors_and_large_batch():
     b = model.plan.loglr_host(P)
     assert a[1].shape == (100003, 4)
     assert np.all(np.abs(a[0] - b[0]) <= tol(a[0]))
+    for kernel in (3, 0):
+        model.plan.configure(kernel=kernel)
+        c = model.plan.loglr_host(P)
+        assert np.all(np.abs(a[0] - c[0]) <= tol(a[0])), kernel
+    model.plan.configure(kernel=2)
     sel = rng.choice(len(P), 48, replace=False)
     lr0, hd0, hh0 = O.batch_loglr(cfg.oracle(), P[sel])
     _check(b[0][sel], b[1][sel], b[2][sel], lr0, hd0, hh0, "4 detectors")
@@ -575,64 +580,56 @@ def test_table_kernel_coalescence_times_anywhere_in_the_segment():
     assert np.all(np.abs(out[3][0][:12] - lr0) <= tol(lr0))
 
 
-def test_table_reference_waveform():
-    """gwin_plan_set_reference: moment tables relative to a reference waveform.  A narrow batch
-    around the reference agrees with the direct kernel; a batch wider than declared is flagged,
-    not silently wrong; clearing the reference restores the plain tables."""
+def test_table_coverage_declared_and_automatic():
+    """Coverage of the moment tables.  Declared from prior draws (``plan.cover``): a batch inside
+    it runs wholly on the table path; a batch outside it is still right -- through the slow path,
+    counted.  Automatic: the host entry point measures the first batch and, after a batch that
+    sent many walkers down the slow path, measures again."""
     cfg = util.c3(seglen=64)
     model = cfg.cuda_model()
     plan = model.plan
     rng = np.random.default_rng(41)
     ref = util.inj_row(cfg)
-    P = util.draw_bns(rng, 200, cfg)
+    P = util.draw_bns(rng, 400, cfg)
     f = 1.0 + 0.004 * rng.uniform(-1, 1, len(P))          # chirp mass within +-0.4 %
     P[:, 0], P[:, 1] = ref[0] * f, ref[1] * f * (1.0 + 0.01 * rng.uniform(-1, 1, len(P)))
-    plan.configure(kernel=1)
-    a = plan.loglr_host(P)
+    a = _direct(plan, P)
     plan.configure(kernel=3)
-    plain = plan.loglr_host(P)
-    n_plain = plan.last_launches
-    plan.set_reference(ref, 0.02)
+    plan.cover(P[:200])
+    narrow = plan.table_info()
+    assert narrow["subblocks"] > 0 and narrow["references"] >= narrow["subblocks"]
     b = plan.loglr_host(P)
-    assert not plan.table_violations()
-    assert np.all(np.abs(b[0] - a[0]) <= tol(a[0]))
-    assert np.all(np.abs(b[1] - a[1]) <= np.maximum(2e-6, 2e-9 * np.abs(a[2])))
-    assert np.all(np.abs(plain[0] - a[0]) <= tol(a[0])) and plan.last_launches == n_plain
+    assert plan.slow_path_walkers() == 0
+    _agree(b, a, "declared narrow coverage")
     lr0 = _oracle_batch(cfg.oracle(), P[:6])[0]
     assert np.all(np.abs(b[0][:6] - lr0) <= tol(lr0))
-    # a batch from the whole mass box: wider than declared, but the schedule's safety margins may
-    # still cover it -- either it is flagged or it is right
-    Pw = util.draw_bns(rng, 64, cfg)
+    # the whole mass box is far outside the declared coverage: slow path, same answers
+    Pw = util.draw_bns(rng, 96, cfg)
     w = plan.loglr_host(Pw)
-    flagged = plan.table_violations()
-    plan.configure(kernel=1)
-    d = plan.loglr_host(Pw)
-    assert flagged or np.all(np.abs(w[0] - d[0]) <= tol(d[0]))
-    # 30 % lighter systems are far outside: flagged, never silently wrong
-    Pf = P[:64].copy()
-    Pf[:, :2] *= 0.7
+    n_slow = plan.slow_path_walkers()
+    assert n_slow > 48 and plan.slow_path_walkers() == 0   # reading resets the count
+    d = _direct(plan, Pw)
     plan.configure(kernel=3)
-    plan.loglr_host(Pf)
-    assert plan.table_violations()
-    assert not plan.table_violations()              # reading clears the flag
-    plan.set_reference(None)
-    c = plan.loglr_host(Pw)
-    assert not plan.table_violations()
-    assert np.all(np.abs(c[0] - d[0]) <= tol(d[0]))
-
-
-def test_automatic_table_reference_subprocess():
-    """GWIN_TABLE_AUTOREF=1 (experimental, read once per process): the host entry point picks the
-    reference waveform from the batches; a sequence of wide / narrowing / drifting batches stays
-    within tolerance of the direct kernel (tools/check_autoref.py)."""
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, GWIN_TABLE_AUTOREF="1")
-    res = subprocess.run([sys.executable, os.path.join(root, "tools", "check_autoref.py"), "64", "512"],
-                         env=env, capture_output=True, text=True, timeout=600)
-    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
-    assert "OK" in res.stdout
+    _agree(w, d, "outside the declared coverage")
+    # a declared coverage is not re-planned behind the caller's back ...
+    assert plan.table_info() == narrow
+    # ... adding the box to it is the caller's move: more references, nobody on the slow path
+    plan.cover(Pw)
+    w2 = plan.loglr_host(Pw)
+    wide = plan.table_info()
+    assert plan.slow_path_walkers() == 0 and wide["references"] > narrow["references"]
+    _agree(w2, d, "coverage extended to the box")
+    _agree(plan.loglr_host(P), a, "narrow batch on the wide tables")
+    # automatic coverage: first batch measured; a batch that leaves it is right (slow path) and
+    # triggers a new measurement, so the batch after it is fast again
+    plan.cover(None)
+    _agree(plan.loglr_host(P), a, "automatic, narrow batch")
+    assert plan.slow_path_walkers() == 0
+    auto_narrow = plan.table_info()
+    _agree(plan.loglr_host(Pw), d, "automatic, first wide batch")
+    assert plan.slow_path_walkers() > 48
+    _agree(plan.loglr_host(Pw), d, "automatic, second wide batch")
+    assert plan.slow_path_walkers() == 0 and plan.table_info()["references"] > auto_narrow["references"]
 
 
 def test_linearity_in_data(cfg2):
@@ -650,3 +647,139 @@ def test_linearity_in_data(cfg2):
     scale = np.abs(a[1]) + np.abs(b[1]) + 1.0
     assert np.all(np.abs(s[1] - (a[1] + b[1])) <= 1e-12 * scale)
     np.testing.assert_allclose(s[2], a[2], rtol=1e-14)
+
+
+# ---------------------------------------------------------------------------
+# round 2: the configuration users and bench.py actually run (kernel AUTO at C3), wide
+# parameter ranges through the moment tables, and the slow-path accounting
+# ---------------------------------------------------------------------------
+def _direct(plan, P, **kw):
+    plan.configure(kernel=1)
+    out = plan.loglr_host(P, **kw)
+    plan.configure(kernel=0)
+    return out
+
+
+def _agree(a, b, what=""):
+    err = np.abs(a[0] - b[0])
+    assert np.all(err <= tol(b[0])), "%s: max |dloglr| %.3e at %d" % (what, err.max(), err.argmax())
+    assert np.all(np.abs(a[1] - b[1]) <= np.maximum(2e-6, 2e-9 * np.abs(b[2]))), what
+    assert np.all(np.abs(a[2] - b[2]) <= np.maximum(1e-6, 1e-9 * np.abs(b[2]))), what
+
+
+def test_bench_configuration_c3_auto(cfg3):
+    """The headline configuration exactly as bench.py builds it: C3, plain model constructor,
+    kernel AUTO, 4096 walkers from the bench's mass box -- held to the direct kernel (all), the
+    oracle (24) and the extended-precision oracle (6); no walker may have left the fast path."""
+    import bench
+    model = cfg3.cuda_model()
+    plan = model.plan
+    rng = np.random.default_rng(20182)
+    P = bench.draw_walkers(rng, 4096)
+    P[:, 10] += cfg3.inj["tc"] - bench.INJ["tc"]
+    auto = plan.loglr_host(P)
+    assert plan.slow_path_walkers() == 0
+    assert plan.last_launches >= 5                  # AUTO took the table path
+    _agree(auto, _direct(plan, P), "bench config, AUTO vs direct")
+    sel = np.argsort(P[:, 0] + P[:, 1])[np.linspace(0, len(P) - 1, 24).astype(int)]   # spans the sorted ke range
+    lr0, hd0, hh0 = _oracle_batch(cfg3.oracle(), P[sel])
+    _check(auto[0][sel], auto[1][sel], auto[2][sel], lr0, hd0, hh0, "bench config vs oracle")
+    lrT = _oracle_batch(cfg3.oracle(mode="truth"), P[sel[:6]])[0]
+    assert np.all(np.abs(auto[0][sel[:6]] - lrT) <= tol(lrT))
+    # the device entry point gives the same bits as the host entry point
+    import torch
+    dev = plan.loglr_device(torch.tensor(P, device="cuda"))
+    np.testing.assert_array_equal(dev[0].cpu().numpy(), auto[0])
+
+
+def _draw_wide(rng, W, cfg, spin=0.9, qmax=3.0, lam=5000.0, mc=(1.0, 1.6)):
+    """Spinning, unequal-mass, tidally deformed systems: chirp mass in ``mc``, mass ratio up to
+    ``qmax``, aligned spins up to ``spin``, tidal deformabilities up to ``lam``."""
+    P = util.draw_bns(rng, W, cfg)
+    mchirp = rng.uniform(mc[0], mc[1], W)
+    q = rng.uniform(1.0, qmax, W)
+    eta = q / (1.0 + q) ** 2
+    mtot = mchirp * eta ** -0.6
+    P[:, 0] = mtot * q / (1.0 + q)
+    P[:, 1] = mtot / (1.0 + q)
+    P[:, 2] = rng.uniform(-spin, spin, W)
+    P[:, 3] = rng.uniform(-spin, spin, W)
+    P[:, 11] = rng.uniform(0.0, lam, W)
+    P[:, 12] = rng.uniform(0.0, lam, W)
+    return P
+
+
+@pytest.mark.parametrize("seglen", [64, 256])
+def test_table_kernel_spins_mass_ratio_tides(seglen):
+    """Long segments, kernel AUTO and TABLE over spins +-0.9, q <= 3, lambda <= 5000 (the tidal
+    phase at 1 kHz is comparable to the point-particle phase): every walker within tolerance
+    of the direct kernel, a sample within tolerance of the oracle.  Walkers the tables cannot
+    take go through the slow path -- counted, never wrong."""
+    cfg = util.c3(seglen=seglen)
+    model = cfg.cuda_model()
+    plan = model.plan
+    rng = np.random.default_rng(900 + seglen)
+    W = 1024 if seglen == 64 else 512
+    for what, P in (("wide", _draw_wide(rng, W, cfg)),
+                    ("extreme corners", _draw_wide(rng, 64, cfg, mc=(1.55, 1.6), qmax=1.02))):
+        if what == "extreme corners":               # all spins / tides at their bounds, both signs
+            P[:, 2] = np.where(np.arange(len(P)) & 1, 0.9, -0.9)
+            P[:, 3] = np.where(np.arange(len(P)) & 2, 0.9, -0.9)
+            P[:, 11] = np.where(np.arange(len(P)) & 4, 5000.0, 0.0)
+            P[:, 12] = np.where(np.arange(len(P)) & 8, 5000.0, 0.0)
+        ref = _direct(plan, P)
+        for kernel in (0, 3, 2):
+            plan.configure(kernel=kernel)
+            _agree(plan.loglr_host(P), ref, "%s T=%d k%d" % (what, seglen, kernel))
+        plan.configure(kernel=0)
+        n = 12 if seglen == 64 else 6
+        lr0, hd0, hh0 = _oracle_batch(cfg.oracle(), P[:n])
+        out = plan.loglr_host(P[:n])
+        _check(out[0], out[1], out[2], lr0, hd0, hh0, "%s T=%d vs oracle" % (what, seglen))
+
+
+def test_device_entry_walkers_below_schedule_mchirp_min(cfg3):
+    """The device entry points do not see the batch before launching: a walker lighter than the
+    schedule's smallest chirp mass (or outside the range the moment tables cover) must come out
+    right anyway -- through the slow path -- and be counted."""
+    import torch
+    model = cfg3.cuda_model()
+    plan = model.plan
+    rng = np.random.default_rng(77)
+    P = util.draw_bns(rng, 256, cfg3)
+    plan.loglr_host(P)                              # schedule + tables now follow this batch
+    plan.slow_path_walkers()
+    Q = P.copy()
+    Q[::16, 0] = 0.5                                # 16 much lighter systems
+    Q[::16, 1] = 0.45
+    dev = plan.loglr_device(torch.tensor(Q, device="cuda"))
+    torch.cuda.synchronize()
+    assert plan.slow_path_walkers() >= 16
+    ref = _direct(plan, Q)
+    got = (dev[0].cpu().numpy(), dev[1].cpu().numpy().view(np.complex128)[..., 0], dev[2].cpu().numpy())
+    _agree(got, ref, "device entry, light walkers")
+    # the host entry point re-plans for the batch instead: nothing on the slow path
+    _agree(plan.loglr_host(Q), ref, "host entry, light walkers")
+    assert plan.slow_path_walkers() == 0
+
+
+def test_interleaved_host_and_device_calls_on_different_streams(cfg2):
+    """Calls on one plan from different streams share its workspace; the library orders them."""
+    import torch
+    model = cfg2.cuda_model()
+    plan = model.plan
+    rng = np.random.default_rng(5)
+    P = util.draw_bbh(rng, 4096, cfg2)
+    ref = plan.loglr_host(P)
+    Pd = torch.tensor(P, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for i in range(6):
+        st = (s1, s2)[i & 1]
+        st.wait_stream(torch.cuda.current_stream())
+        outs.append(plan.loglr_device(Pd, stream=st.cuda_stream))
+        if i == 3:
+            np.testing.assert_array_equal(plan.loglr_host(P)[0], ref[0])
+    torch.cuda.synchronize()
+    for o in outs:
+        np.testing.assert_array_equal(o[0].cpu().numpy(), ref[0])

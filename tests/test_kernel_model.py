@@ -103,50 +103,49 @@ def test_calibration_arithmetic():
 
 
 def test_table_kernel_arithmetic():
-    """The moment-table scheme above k_split (sub-block Taylor coefficients, deconvolved DFT
-    tables, 13-tap exponential-of-semicircle interpolation) against the direct sum and the
-    oracle; the schedule keeps |R| at the sub-block edge under TAB_RHO."""
+    """The moment-table scheme (analytic Taylor coefficients per sub-block, reference chirps,
+    deconvolved DFT tables, 13-tap exponential-of-semicircle interpolation) against the direct
+    sum and the oracle, for a coverage measured on the walkers themselves."""
     cfg = util.c3(seglen=32)
     pm = _plan(cfg, mchirp_min=1.0)
-    pm.build_tables()
-    assert pm.k_split < pm.kmax and min(pm.tab_m) >= pm.TAB_MIN and max(pm.tab_m) <= pm.TAB_MAX
-    assert set(pm.tab_m) <= set(pm.table_sizes())
-    orc = cfg.oracle()
     rng = np.random.default_rng(3)
-    for row in util.draw_bns(rng, 2, cfg):
+    rows = util.draw_bns(rng, 3, cfg)
+    rows[2, 2:4] = 0.04, -0.03                      # small spins
+    rows[2, 11:13] = 300.0, 500.0                   # and tides
+    pm.build_tables(pm.cover_stats(rows))
+    ms = [B['m'] for B in pm.tblk]
+    assert pm.k_split < pm.kmax and min(ms) >= pm.TAB_MIN and max(ms) <= pm.TAB_MAX
+    assert set(ms) <= set(pm.table_sizes()) and max(B['K'] for B in pm.tblk) > 1
+    orc = cfg.oracle()
+    for row in rows:
         a = pm.loglr_direct(row)
         b = pm.loglr_table(row)
+        assert not pm.slow and pm.worst_est <= pm.TAB_EST_MAX
         assert abs(a[0] - b[0]) < 1e-8 and np.max(np.abs(a[1] - b[1])) < 1e-8
         lr0 = orc.loglr(**dict(zip(util.PARAM_ORDER, row)))[0]
         assert abs(b[0] - lr0) <= util.tol(lr0)
 
 
-def test_table_reference_arithmetic():
-    """Moment tables relative to a reference waveform: longer sub-blocks, same answers for a
-    narrow batch, and |2 pi R| beyond twice TAB_RHO (what the kernel flags) for a walker far
-    outside the declared width."""
+def test_table_truncation_estimate_flags_uncovered_walkers():
+    """A walker outside what the tables were built for -- far in chirp mass, or with spins the
+    coverage did not see -- is recognised from its own truncation estimate (the kernel then takes
+    the slow path); the majorant the schedule is built with bounds the estimate of covered ones."""
     cfg = util.c3(seglen=32)
     ref = util.inj_row(cfg)
-    plain = _plan(cfg, mchirp_min=1.0)
-    plain.build_tables()
     pm = _plan(cfg, mchirp_min=1.0)
-    pm.set_reference(ref, 0.02)
-    pm.build_tables()
-    assert pm.k_split < plain.k_split and len(pm.tab_m) < len(plain.tab_m)
     rng = np.random.default_rng(9)
-    for _ in range(2):
-        row = ref.copy()
-        row[:2] *= 1.0 + 0.004 * rng.uniform(-1, 1)
-        row[10] += rng.uniform(-0.05, 0.05)
+    rows = np.tile(ref, (4, 1))
+    rows[:, :2] *= 1.0 + 0.004 * rng.uniform(-1, 1, (4, 1))
+    pm.build_tables(pm.cover_stats(rows))
+    for row in rows:
         a, b = pm.loglr_direct(row), pm.loglr_table(row)
-        assert abs(a[0] - b[0]) < 1e-8 and np.max(np.abs(a[1] - b[1])) < 1e-8
-        assert pm.last_rho <= 2.0 * pm.TAB_RHO
+        assert not pm.slow and pm.worst_est <= 4 * pm.TAB_EST_DESIGN
+        assert abs(a[0] - b[0]) < 1e-8
     far = ref.copy()
     far[:2] *= 0.7
     pm.loglr_table(far)
-    worst = 0.0
-    w = pm.walker(far)
-    for b in range(len(pm.tab_m)):
-        pm.table_block(w, b, 0)
-        worst = max(worst, pm.last_rho)
-    assert worst > 2.0 * pm.TAB_RHO
+    assert pm.slow
+    spinning = ref.copy()
+    spinning[2:4] = 0.8, -0.6
+    pm.loglr_table(spinning)
+    assert pm.slow and pm.worst_est > pm.TAB_EST_MAX
