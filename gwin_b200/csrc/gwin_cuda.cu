@@ -86,6 +86,9 @@ int gwin_fail(int code, const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
     return code;
 }
+// GWIN_DEBUG=1: progress of the (rare, slow) plan-level steps on stderr
+static bool dbg_on() { static const bool on = getenv("GWIN_DEBUG") && atoi(getenv("GWIN_DEBUG")) != 0; return on; }
+#define DBG(...) do { if (dbg_on()) { fprintf(stderr, "[gwin] " __VA_ARGS__); fputc('\n', stderr); fflush(stderr); } } while (0)
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
     return fail(GWIN_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
 
@@ -926,10 +929,17 @@ struct TileStream {
     __device__ __forceinline__ int tile_end(int k) const {         // first bin of the next tile
         return ka + ((k - ka) / TILE + 1) * TILE;
     }
-    // no bulk copy may be in flight when the CTA retires
+    // no bulk copy may be in flight when the CTA retires; the barriers are invalidated so that the
+    // warp may open another stream on them (mbarrier.init on a live barrier is undefined)
     __device__ __forceinline__ void close() {
         const int t = cur + 1;
         if (ka + t * TILE < kz) mbar_wait(bar + 8u * (uint32_t)(t & 1), (uint32_t)((t >> 1) & 1));
+        __syncwarp();
+        if (lane == 0) {
+            asm volatile("mbarrier.inval.shared::cta.b64 [%0];" :: "r"(bar) : "memory");
+            asm volatile("mbarrier.inval.shared::cta.b64 [%0];" :: "r"(bar + 8u) : "memory");
+        }
+        __syncwarp();
     }
 };
 
@@ -2272,6 +2282,8 @@ static int build_tables(gwin_plan* p) {
     if (n == 0) return GWIN_OK;
     int n_pairs = 0;
     for (const TabBlk& B : blks) n_pairs += B.K;
+    DBG("tables: a0 in [%.6g, %.6g], %d sub-blocks from bin %d (m %d .. %d), %d references, %.1f MB, K0 %.1f",
+        p->cover.a_lo, p->cover.a_hi, n, blks[0].start, blks[0].m, blks[n - 1].m, n_pairs, bytes / 1048576.0, K0);
     // per-sub-block Taylor matrices, per-pair bookkeeping of the build
     std::vector<double> cmat((size_t)n * NPH * TAB_NTP, 0.0);
     std::vector<int> pair_blk(n_pairs), blk_hat(n);
@@ -2333,6 +2345,7 @@ static int build_tables(gwin_plan* p) {
         }
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
+        DBG("tables: built");
         return GWIN_OK;
     };
     const int rc = build();
@@ -3000,6 +3013,8 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
         table = p->n_tblk > 0 && (p->kernel == GWIN_KERNEL_TABLE || p->tab_worth);
     }
     const int n_blk = table ? p->n_blk_low : p->n_blk;
+    DBG("batch W=%d kernel=%d table=%d n_blk=%d/%d n_tblk=%d k_split=%d mchirp_min=%g", W, p->kernel, (int)table, n_blk, p->n_blk,
+        p->n_tblk, p->k_split, p->mchirp_min);
 
     // frequency chunking: enough CTAs to fill 148 SMs x ~5 resident CTAs several times over
     const int band0 = std::max(d.kmin, d.istart);

@@ -15,7 +15,7 @@ import numpy
 
 from .. import _lib
 from ..calibration import spline_frequencies, values_matrix
-from ..waveform import param_rows
+from ..waveform import check_waveform_params, param_rows
 from .base_data import BaseDataModel
 
 
@@ -49,6 +49,14 @@ class GaussianNoise(BaseDataModel):
         dlens = numpy.array([len(d) for d in data.values()])
         if not all(dlens == dlens[0]):
             raise ValueError("all data must be of the same length")
+        # everything that reaches the generator must be something the kernel evaluates
+        recalib = getattr(waveform_generator, 'recalib', None)
+        recalib_names = []
+        if recalib:
+            for rec in recalib.values():
+                recalib_names += rec.param_names
+        check_waveform_params(self.variable_params, self.static_params,
+                              self._waveform_transforms, recalib_names)
         self._dets = list(self._data.keys())
         d = self._data[self._dets[0]]
         N = len(d)

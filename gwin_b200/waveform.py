@@ -32,6 +32,51 @@ WAVEFORM_PARAMS = OrderedDict([
 
 SUPPORTED_APPROXIMANTS = ("TaylorF2",)
 
+#: ``get_fd_waveform`` arguments that this path does not implement and that change a TaylorF2
+#: waveform when they are not at the listed neutral value (pycbc's defaults): accepted as static
+#: parameters at that value only, never as sampled ones
+NEUTRAL_ONLY = {
+    "f_ref": 0.0, "f_final": 0.0, "f_final_func": "", "phase_order": -1, "spin_order": -1,
+    "tidal_order": -1, "amplitude_order": 0, "eccentricity": 0.0, "long_asc_nodes": 0.0,
+    "mean_per_ano": 0.0, "spin1x": 0.0, "spin1y": 0.0, "spin2x": 0.0, "spin2y": 0.0,
+    "dquad_mon1": 0.0, "dquad_mon2": 0.0, "lambda_octu1": None, "lambda_octu2": None,
+    "quadfmode1": None, "quadfmode2": None, "octufmode1": None, "octufmode2": None,
+    "frame_axis": 0, "modes_choice": 0, "side_bands": 0, "numrel_data": ""}
+#: arguments that do not enter a frequency-domain TaylorF2 waveform at all
+IGNORED = ("approximant", "delta_f", "delta_t", "f_lower", "taper", "fft_type", "t_gate_start",
+           "t_gate_end")
+
+
+def check_waveform_params(variable, static, transforms=None, recalib_names=()):
+    """Every parameter that reaches the waveform generator must be one the kernel evaluates.
+
+    In the reference any ``get_fd_waveform`` argument may be sampled or frozen
+    (``models/base_data.py:84-161``; the generator forwards all of them).  Here the kernel reads
+    the 13 TaylorF2 parameters of ``WAVEFORM_PARAMS`` (plus the ``recalib_*`` values); anything
+    else would be ignored silently -- a flat marginal for a sampled parameter, a different
+    likelihood than the reference's for a static one.  Raises ``ValueError`` instead."""
+    consumed, produced = set(), set()
+    for t in (transforms or ()):
+        consumed.update(t.inputs)
+        produced.update(t.outputs)
+    known = set(WAVEFORM_PARAMS) | set(recalib_names)
+    for name in (set(variable) - consumed) | produced:
+        if name not in known:
+            raise ValueError("variable parameter %r does not enter the TaylorF2 waveform of this "
+                             "implementation (known: %s, recalib_*, or the inputs of a waveform "
+                             "transform)" % (name, ", ".join(WAVEFORM_PARAMS)))
+    for name, value in dict(static).items():
+        if name in known or name in consumed or name in IGNORED:
+            continue
+        if name in NEUTRAL_ONLY:
+            neutral = NEUTRAL_ONLY[name]
+            if value is None or value == neutral or (neutral is None and not value):
+                continue
+            raise ValueError("static parameter %s=%r is not implemented by this TaylorF2 path "
+                             "(only its neutral value %r is accepted)" % (name, value, neutral))
+        raise ValueError("static parameter %r is not understood by the TaylorF2 waveform of this "
+                         "implementation" % name)
+
 
 class NoWaveformError(Exception):
     """No waveform could be generated for the given parameters
@@ -118,6 +163,7 @@ class FDomainDetFrameGenerator(object):
         except KeyError as e:
             raise ValueError("%s must be provided" % e)
         frozen_params.pop("delta_t", None)
+        check_waveform_params((), frozen_params)
         self.approximant = approximant
         self._epoch = float(epoch)
         self.detectors = OrderedDict((d, Detector(d)) for d in detectors)
@@ -163,11 +209,11 @@ class FDomainDetFrameGenerator(object):
         (CUDA ``generate_kernel``)."""
         self.current_params.update(kwargs)
         row = param_matrix(self.current_params, 1)
-        n = taylorf2_length(row[0, 0], row[0, 1], self.delta_f)
         if not (row[0, 0] > 0 and row[0, 1] > 0) or \
                 taylorf2_fisco(row[0, 0], row[0, 1]) <= self.f_lower:
-            # lalsimulation: "f_max <= fStart" is a domain error
+            # lalsimulation: non-positive masses and "f_max <= fStart" are domain errors
             raise NoWaveformError("f_ISCO is not above f_lower for these masses")
+        n = taylorf2_length(row[0, 0], row[0, 1], self.delta_f)
         n_f = max(((n + 1023) // 1024) * 1024 + 1,
                   int(self.f_lower / self.delta_f) + 9)
         calib = None

@@ -306,3 +306,30 @@ def test_calibration_description_classes():
         cal.values_matrix(rec, ["H1", "L1"], params, 3)
     with pytest.raises(ValueError):
         cal.spline_frequencies({"H1": m, "L1": cal.CubicSpline(20, 512, 7, "l1")}, ["H1", "L1"])
+
+
+def test_parameters_the_kernel_does_not_evaluate_are_refused():
+    """The reference forwards every sampled / static parameter to ``get_fd_waveform``
+    (models/base_data.py:84-161); the kernel evaluates the 13 TaylorF2 parameters.  Anything
+    else must raise instead of being ignored (a flat marginal, or a likelihood that differs from
+    the reference's without a word)."""
+    from gwin_b200 import transforms as T
+    from gwin_b200.waveform import (FDomainCBCGenerator, FDomainDetFrameGenerator,
+                                    NoWaveformError, check_waveform_params)
+    check_waveform_params(("mass1", "tc"), {"mass2": 1.4, "f_ref": 0.0, "phase_order": -1,
+                                             "approximant": "TaylorF2", "f_lower": 20.})
+    check_waveform_params(("mchirp", "q", "tc"), {}, [T.MchirpQToMass1Mass2()])
+    check_waveform_params(("tc", "recalib_amplitude_h1_0"), {}, None, ["recalib_amplitude_h1_0"])
+    for variable, static in ((("spin1x",), {}), (("eccentricity",), {}), (("mchirp",), {}),
+                             ((), {"phase_order": 4}), ((), {"f_final": 512.}), ((), {"f_ref": 20.}),
+                             ((), {"spin1_a": 0.3}), ((), {"spin2y": 0.1})):
+        with pytest.raises(ValueError):
+            check_waveform_params(variable, static)
+    with pytest.raises(ValueError):
+        FDomainDetFrameGenerator(FDomainCBCGenerator, 0., detectors=["H1"], variable_args=("tc",),
+                                 delta_f=0.25, f_lower=20., approximant="TaylorF2", f_final=300.)
+    gen = FDomainDetFrameGenerator(FDomainCBCGenerator, 0., detectors=["H1"], variable_args=("tc",),
+                                   delta_f=0.25, f_lower=20., approximant="TaylorF2", f_ref=0.)
+    # zero total mass is "no waveform", not a ZeroDivisionError
+    with pytest.raises(NoWaveformError):
+        gen.generate(mass1=0., mass2=0., ra=0., dec=0., polarization=0., tc=1.)
