@@ -27,6 +27,7 @@
 // TMA bulk copies and read with warp-uniform 128-bit loads.  The table kernel (DESIGN.md
 // 4.6) replaces the per-bin work above ~100 Hz by interpolation in per-plan moment tables.
 #include <cuda_runtime.h>
+#include <cub/block/block_radix_sort.cuh>
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
@@ -496,29 +497,62 @@ __device__ __forceinline__ int waveform_len(double mtot, double delta_f) {
     return n > 2.0e9 ? 2000000000 : (int)n;
 }
 
-// key_a0 = false: the walker's last bin (lanes of a warp finish together); true (table path): its
-// Newtonian chirp coefficient quantised over the covered range (lanes of a warp share a reference
-// chirp and sit in neighbouring table rows).  Walkers without a waveform sort to one end.
+// Sort keys.  key: the order the walkers are processed in -- key_a0 = false: their last bin (lanes of a
+// warp finish together); true (table path): their Newtonian chirp coefficient quantised over the
+// covered range (lanes of a warp share a reference chirp and sit in neighbouring table rows).
+// key_e (table path): the last bin again, the order in which the tails are taken.  Walkers without
+// a waveform sort to one end.
 __global__ void sort_key_kernel(PlanDev P, int W, const double* __restrict__ params,
                                 int64_t sw, int64_t si,
                                 const uint8_t* __restrict__ skip, int* __restrict__ key,
-                                int* __restrict__ idx, bool key_a0, double a_lo, double a_scale) {
+                                int* __restrict__ idx, bool key_a0, double a_lo, double a_scale,
+                                int* __restrict__ key_e) {
     int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= W) return;
     double p[GWIN_NPARAM];
     load_params(p, params, w, sw, si);
     const bool ok = !(skip && skip[w]) && params_ok(p) && has_waveform(p, P.f_lower_wf);
-    int k = key_a0 ? (1 << TAB_KEY_BITS) - 1 : 0;
+    int k = key_a0 ? (1 << TAB_KEY_BITS) - 1 : 0, ke = 0;
     if (ok) {
+        ke = min(waveform_len(p[0] + p[1], P.delta_f), P.kmax);
         if (key_a0) {
             const double q = (newtonian_coef(p[0], p[1]) - a_lo) * a_scale;
             k = (int)fmin(fmax(q, 0.0), (double)((1 << TAB_KEY_BITS) - 2));
         } else {
-            k = min(waveform_len(p[0] + p[1], P.delta_f), P.kmax);
+            k = ke;
         }
     }
     key[w] = k;
     idx[w] = w;
+    if (key_e) key_e[w] = ke;
+}
+
+// Batches of up to 16384 walkers: one CTA sorts (key, index) pairs in shared memory (stable LSD radix
+// sort, cub::BlockRadixSort); CTA y sorts key set y -- the table path's two orders in one launch
+// instead of two device-wide sorts of five launches each.
+template <int ITEMS>
+__global__ void __launch_bounds__(1024)
+block_sort_kernel(int W, const int* __restrict__ key0, int bits0, int* __restrict__ out0,
+                  const int* __restrict__ key1, int bits1, int* __restrict__ out1) {
+    using Sort = cub::BlockRadixSort<int, 1024, ITEMS, int>;
+    extern __shared__ __align__(16) unsigned char s_sort[];
+    typename Sort::TempStorage& temp = *reinterpret_cast<typename Sort::TempStorage*>(s_sort);
+    const int* key = blockIdx.x ? key1 : key0;
+    int* out = blockIdx.x ? out1 : out0;
+    const int bits = blockIdx.x ? bits1 : bits0;
+    int k[ITEMS], v[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const int w = threadIdx.x * ITEMS + i;
+        k[i] = w < W ? key[w] : 0x7fffffff;
+        v[i] = w;
+    }
+    Sort(temp).Sort(k, v, 0, bits + 1);                 // + 1: the padding keys sort last
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const int w = threadIdx.x * ITEMS + i;
+        if (w < W) out[w] = v[i];
+    }
 }
 
 // What walker_setup needs to split a walker's band between the kernels.
@@ -528,7 +562,7 @@ struct FastArgs {
     int table;               // table path: recurrence below k_split, tables above, tails by a second recurrence pass
     int k_split, k_tab_end, n_tblk;
     const TabBlk* blks;
-    int *ke_fast, *ke_low, *ks_tail, *key2, *idx2;
+    int *ke_fast, *ke_low, *ks_tail, *inv;      // inv[w]: position of walker w in the processing order
     unsigned char* slow;
 };
 
@@ -558,7 +592,7 @@ __global__ void walker_setup_kernel(PlanDev P, int W, int wpad,
         // no bins; combine() turns this into -inf via ks = -1
         ks_arr[t] = -1; ke_arr[t] = -1;
         if (F.ke_fast) { F.ke_fast[t] = -1; F.slow[t] = 0; }
-        if (F.table) { F.ke_low[t] = -1; F.ks_tail[t] = -1; F.key2[t] = 0; F.idx2[t] = t; }
+        if (F.table) { F.ke_low[t] = -1; F.ks_tail[t] = -1; F.inv[w] = t; }
         for (int r = 0; r < NCOEF(nd); ++r) wc[r * wpad + t] = 0.0;
         for (int d = 0; d < nd; ++d) hh_sorted[d * wpad + t] = 0.0;
         return;
@@ -609,8 +643,7 @@ __global__ void walker_setup_kernel(PlanDev P, int W, int wpad,
                 }
             }
             F.ks_tail[t] = tail;
-            F.key2[t] = tail < kef ? kef : 0;
-            F.idx2[t] = t;
+            F.inv[w] = t;
         }
     }
 
@@ -1187,10 +1220,17 @@ loglr_recur_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_blk,
     double* s_coef = reinterpret_cast<double*>(s_dyn + sizeof(double2) * NWARP * 2 * TILE * ND);
     uint64_t (*s_bar)[2] = reinterpret_cast<uint64_t (*)[2]>(s_coef + (CALIB ? RC_ROWS_CAL(ND) : RC_ROWS(ND)) * CTA_THREADS);
     bool coef_staged = false;
-    for (int chunk = blockIdx.y;; chunk += gridDim.y) {
-    const int b0 = cb0 + chunk * blocks_per_chunk;
+    // tails: chunks are cut on the absolute block grid (chunk c = blocks [c per, (c+1) per), slot c mod
+    // gridDim.y), so a walker's tail is summed in the same order whoever its neighbours are
+    int chunk = blockIdx.y;
+    if (grp_b) {
+        const int c0 = cb0 / blocks_per_chunk;
+        chunk = c0 + ((int)blockIdx.y - c0 % (int)gridDim.y + (int)gridDim.y) % (int)gridDim.y;
+    }
+    for (;; chunk += gridDim.y) {
+    const int b0 = chunk * blocks_per_chunk;
     if (b0 >= cb1) break;
-    const int b1 = min(b0 + blocks_per_chunk, cb1);
+    const int b1 = min(b0 + blocks_per_chunk, n_blk);
     const int k0 = blk_start[b0], k1 = blk_start[b1];
     const int lo = max(k0, ks), hi = min(k1, ke);
     const bool has = lo < hi;
@@ -1509,16 +1549,9 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
             bool act = !dead && ke >= s + m;            // this lane takes the sub-block whole
             const unsigned amask = __ballot_sync(0xffffffffu, act);
             if (!amask) continue;
-            // ---- reference chirp: the lanes of a warp are neighbours in a0; when they all lie within
-            // 3/4 of the reference spacing of the middle lane's reference they share it (and the staged
-            // table rows), else every lane takes its own nearest one
+            // ---- reference chirp: the nearest one on the sub-block's grid (a function of the walker alone)
             int r = (int)((a[0] - B.a_lo) * B.inv_da);
             r = max(0, min(r, B.K - 1));
-            const int mid = __fns(amask, 0, (__popc(amask) + 1) / 2);
-            const int rL = __shfl_sync(0xffffffffu, r, mid);
-            const double aL = B.a_lo + ((double)rL + 0.5) * B.da;
-            const bool uni = __all_sync(0xffffffffu, !act || fabs(a[0] - aL) <= 0.75 * B.da);
-            if (uni) r = rL;
             // ---- Taylor coefficients of the phase about the centre: t_n = sum_i a_i c[i][n]
             const double* sc = s_c + (size_t)(b - b0) * NPH * TAB_NTP;
             double tq[TAB_NT];
@@ -1572,14 +1605,14 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
             const double h = 0.5 * (double)m;
             const double kc = (double)(s + m / 2);
             const double2* row0 = tab + B.off;
-            // Every lane's 13 taps x 128 B live within a few grid points of each other (the
-            // walkers' local times differ by less than the grid spacing times a few): the warp
-            // copies the union of the rows to shared memory with cp.async (one L2 round trip per
-            // sub-block instead of one per tap group), then each lane reads its taps from there.
+            // The lanes of a warp are neighbours in a0: nearly always they share the reference, and their
+            // 13 taps x 128 B live within a few grid points of each other (the walkers' local times differ
+            // by less than the grid spacing times a few).  The lanes of one reference are taken together:
+            // the warp copies the union of their rows to shared memory with cp.async (one L2 round trip per
+            // sub-block instead of one per tap group), then each lane reads its taps from there.  A warp
+            // that straddles a boundary of the reference grid makes a second pass for the other reference.
             double xs[ND];
-            int gs[ND], lo[ND];
-            bool staged[ND];
-            __syncwarp();                           // the previous sub-block's rows have been read
+            int gs[ND];
 #pragma unroll
             for (int d = 0; d < ND; ++d) {
                 const double nu = tq[1] / h + (tau_hi[d] + tau_lo[d]);    // turns per bin
@@ -1587,77 +1620,89 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
                 const int g0 = (int)ceil(xs[d] - 0.5 * TAB_W);            // -6 .. L - 6
                 gs[d] = g0 < 0 ? g0 + L : g0;
                 xs[d] = 2.0 * (xs[d] - (double)g0) - (double)(TAB_W - 1); // v: the Horner variable
-                int mn = act ? gs[d] : 0x7fffffff, mx = act ? gs[d] : -1;
-#pragma unroll
-                for (int o = 16; o; o >>= 1) {
-                    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-                    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                }
-                lo[d] = mn;
-                const int span = mx - mn + TAB_W;
-                staged[d] = uni && mx >= 0 && span <= TAB_SPAN;
-                if (staged[d]) {
-                    const double2* src = row0 + (((size_t)rL * ND + d) * (L + TAB_W) + mn) * TAB_NM;
-                    const uint32_t dst = smem_u32(s_warp + (size_t)d * TAB_SPAN * TAB_ROWB);
-                    for (int pc16 = lane; pc16 < span * TAB_NM; pc16 += WARP) {
-                        const int rr = pc16 / TAB_NM, c16 = pc16 % TAB_NM;
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
-                                     :: "r"(dst + (uint32_t)(rr * TAB_ROWB + c16 * 16)), "l"(src + pc16) : "memory");
-                    }
-                }
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            bool waited = false;
+            unsigned todo = __ballot_sync(0xffffffffu, act);
+            while (todo) {
+                const int rL = __shfl_sync(0xffffffffu, r, __ffs(todo) - 1);
+                const bool mine = act && r == rL;
+                todo &= ~__ballot_sync(0xffffffffu, mine);
+                int lo[ND];
+                bool staged[ND];
+                __syncwarp();                           // the previous pass's rows have been read
 #pragma unroll
-            for (int d = 0; d < ND; ++d) {
-                double2 Mn[TAB_NM];
+                for (int d = 0; d < ND; ++d) {
+                    int mn = mine ? gs[d] : 0x7fffffff, mx = mine ? gs[d] : -1;
 #pragma unroll
-                for (int n = 0; n < TAB_NM; ++n) Mn[n] = make_double2(0.0, 0.0);
-                // rows are padded with TAB_W wrap-around points: the taps are contiguous
-                const double2* rd = row0 + (((size_t)r * ND + d) * (L + TAB_W) + gs[d]) * TAB_NM;
-                const unsigned char* sd = s_warp + ((size_t)d * TAB_SPAN + (act ? gs[d] - lo[d] : 0)) * TAB_ROWB;
-                const double v = xs[d];
-                // kernel weights: 13 independent Horner chains in v = 2 (x - g0) - (W - 1), coefficients
-                // as literal constants (constant-bank operands, no loads)
-                double wt[TAB_W];
-                wt[0] = TAB_TAP_0(v); wt[1] = TAB_TAP_1(v); wt[2] = TAB_TAP_2(v); wt[3] = TAB_TAP_3(v);
-                wt[4] = TAB_TAP_4(v); wt[5] = TAB_TAP_5(v); wt[6] = TAB_TAP_6(v); wt[7] = TAB_TAP_7(v);
-                wt[8] = TAB_TAP_8(v); wt[9] = TAB_TAP_9(v); wt[10] = TAB_TAP_10(v); wt[11] = TAB_TAP_11(v);
-                wt[12] = TAB_TAP_12(v);
-                if (!waited) {                       // the weights above overlapped the copies
-                    asm volatile("cp.async.wait_group 0;" ::: "memory");
-                    __syncwarp();
-                    waited = true;
-                }
-                if (staged[d]) {
-#pragma unroll
-                    for (int i = 0; i < TAB_W; ++i) {
-                        const double2* e = reinterpret_cast<const double2*>(sd + i * TAB_ROWB);
-#pragma unroll
-                        for (int n = 0; n < TAB_NM; ++n) {
-                            const double2 q = e[n];
-                            Mn[n].x = fma(wt[i], q.x, Mn[n].x);
-                            Mn[n].y = fma(wt[i], q.y, Mn[n].y);
-                        }
+                    for (int o = 16; o; o >>= 1) {
+                        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
                     }
-                } else if (act) {                    // lanes too far apart (in time or in a0): straight from L2
-#pragma unroll
-                    for (int i = 0; i < TAB_W; ++i) {
-                        const double2* e = rd + i * TAB_NM;
-#pragma unroll
-                        for (int n = 0; n < TAB_NM; ++n) {
-                            const double2 q = __ldg(e + n);
-                            Mn[n].x = fma(wt[i], q.x, Mn[n].x);
-                            Mn[n].y = fma(wt[i], q.y, Mn[n].y);
+                    lo[d] = mn;
+                    const int span = mx - mn + TAB_W;
+                    staged[d] = span <= TAB_SPAN;
+                    if (staged[d]) {
+                        const double2* src = row0 + (((size_t)rL * ND + d) * (L + TAB_W) + mn) * TAB_NM;
+                        const uint32_t dst = smem_u32(s_warp + (size_t)d * TAB_SPAN * TAB_ROWB);
+                        for (int pc16 = lane; pc16 < span * TAB_NM; pc16 += WARP) {
+                            const int rr = pc16 / TAB_NM, c16 = pc16 % TAB_NM;
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                                         :: "r"(dst + (uint32_t)(rr * TAB_ROWB + c16 * 16)), "l"(src + pc16) : "memory");
                         }
                     }
                 }
-                // sum_n e_n M_n; Mn[] holds n = 0, 2, 3, .. TAB_DEG
-                double2 sum = Mn[0];
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                bool waited = false;
 #pragma unroll
-                for (int n = 2; n <= TAB_DEG; ++n) sum = cfma(en[n], Mn[n - 1], sum);
-                const double th0 = tq[0] + fma(kc, tau_lo[d], frac1(kc * tau_hi[d]));
-                if (act) acc[d] = cfma(sum, phasor_neg(th0), acc[d]);
+                for (int d = 0; d < ND; ++d) {
+                    double2 Mn[TAB_NM];
+#pragma unroll
+                    for (int n = 0; n < TAB_NM; ++n) Mn[n] = make_double2(0.0, 0.0);
+                    // rows are padded with TAB_W wrap-around points: the taps are contiguous
+                    const double2* rd = row0 + (((size_t)rL * ND + d) * (L + TAB_W) + gs[d]) * TAB_NM;
+                    const unsigned char* sd = s_warp + ((size_t)d * TAB_SPAN + (mine ? gs[d] - lo[d] : 0)) * TAB_ROWB;
+                    const double v = xs[d];
+                    // kernel weights: 13 independent Horner chains in v = 2 (x - g0) - (W - 1), coefficients
+                    // as literal constants (constant-bank operands, no loads)
+                    double wt[TAB_W];
+                    wt[0] = TAB_TAP_0(v); wt[1] = TAB_TAP_1(v); wt[2] = TAB_TAP_2(v); wt[3] = TAB_TAP_3(v);
+                    wt[4] = TAB_TAP_4(v); wt[5] = TAB_TAP_5(v); wt[6] = TAB_TAP_6(v); wt[7] = TAB_TAP_7(v);
+                    wt[8] = TAB_TAP_8(v); wt[9] = TAB_TAP_9(v); wt[10] = TAB_TAP_10(v); wt[11] = TAB_TAP_11(v);
+                    wt[12] = TAB_TAP_12(v);
+                    if (!waited) {                       // the weights above overlapped the copies
+                        asm volatile("cp.async.wait_group 0;" ::: "memory");
+                        __syncwarp();
+                        waited = true;
+                    }
+                    if (staged[d]) {
+#pragma unroll
+                        for (int i = 0; i < TAB_W; ++i) {
+                            const double2* e = reinterpret_cast<const double2*>(sd + i * TAB_ROWB);
+#pragma unroll
+                            for (int n = 0; n < TAB_NM; ++n) {
+                                const double2 q = e[n];
+                                Mn[n].x = fma(wt[i], q.x, Mn[n].x);
+                                Mn[n].y = fma(wt[i], q.y, Mn[n].y);
+                            }
+                        }
+                    } else if (mine) {                   // lanes too far apart in time: straight from L2
+#pragma unroll
+                        for (int i = 0; i < TAB_W; ++i) {
+                            const double2* e = rd + i * TAB_NM;
+#pragma unroll
+                            for (int n = 0; n < TAB_NM; ++n) {
+                                const double2 q = __ldg(e + n);
+                                Mn[n].x = fma(wt[i], q.x, Mn[n].x);
+                                Mn[n].y = fma(wt[i], q.y, Mn[n].y);
+                            }
+                        }
+                    }
+                    // sum_n e_n M_n; Mn[] holds n = 0, 2, 3, .. TAB_DEG
+                    double2 sum = Mn[0];
+#pragma unroll
+                    for (int n = 2; n <= TAB_DEG; ++n) sum = cfma(en[n], Mn[n - 1], sum);
+                    const double th0 = tq[0] + fma(kc, tau_lo[d], frac1(kc * tau_hi[d]));
+                    if (mine) acc[d] = cfma(sum, phasor_neg(th0), acc[d]);
+                }
             }
         }
     }
@@ -1668,16 +1713,19 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
     }
 }
 
-// Tails of the table path.  Walkers are taken in the order of their last bin (col = perm_e[t]); the
+// Tails of the table path.  Walkers are taken in the order of their last bin: perm_e[t] is the t-th
+// walker in that order, inv[] its column in the processing order; col_e[t] keeps the composition.  The
 // 128 walkers of a CTA then need only a short run of recurrence blocks: grp_b[g] .. grp_b[groups + g].
 __global__ void __launch_bounds__(CTA_THREADS)
 tail_plan_kernel(int W, int n_blk, const int* __restrict__ blk_start, const int* __restrict__ perm_e,
+                 const int* __restrict__ inv, int* __restrict__ col_e,
                  const int* __restrict__ ks_tail, const int* __restrict__ ke_fast, int* __restrict__ grp_b) {
     __shared__ int s_lo[CTA_THREADS / WARP], s_hi[CTA_THREADS / WARP];
     const int t = blockIdx.x * CTA_THREADS + threadIdx.x;
     int lo = 0x7fffffff, hi = 0;
     if (t < W) {
-        const int col = perm_e[t];
+        const int col = inv[perm_e[t]];
+        col_e[t] = col;
         const int a = ks_tail[col], e = ke_fast[col];
         if (a >= 0 && a < e) { lo = a; hi = e; }
     }
@@ -3074,16 +3122,42 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
 
     const int tb = 128, gb = (W + tb - 1) / tb;
     const int* perm = nullptr;
-    if (W > WARP) {
+    if (W > WARP || table) {
         const double a_lo = p->cover.a_lo;
         const double a_scale = table ? (double)(1 << TAB_KEY_BITS) / (p->cover.a_hi - p->cover.a_lo) : 0.0;
         sort_key_kernel<<<gb, tb, 0, st>>>(d, W, params, stride_walker, stride_param, skip, p->d_key_in, p->d_perm_in,
-                                           table, a_lo, a_scale);
-        size_t bytes = p->cub_bytes;
-        CK(cub::DeviceRadixSort::SortPairs(p->d_cub, bytes, p->d_key_in, p->d_key_out,
-                                           p->d_perm_in, p->d_perm_out, W, 0, table ? TAB_KEY_BITS : 23, st));
+                                           table, a_lo, a_scale, table ? p->d_key2_in : nullptr);
+        const int bits = table ? TAB_KEY_BITS : 23;
+        static const bool block_sort = !(getenv("GWIN_BLOCK_SORT") && atoi(getenv("GWIN_BLOCK_SORT")) == 0);
+        if (W <= 16384 && block_sort) {
+            // one launch: CTA 0 sorts the processing order, CTA 1 (table path) the tails' order
+            const int items = W <= 4096 ? 4 : 16;
+            const size_t smem = items == 4 ? sizeof(cub::BlockRadixSort<int, 1024, 4, int>::TempStorage)
+                                           : sizeof(cub::BlockRadixSort<int, 1024, 16, int>::TempStorage);
+            static bool attr_set_dev[64] = {};
+            if (!attr_set_dev[p->device & 63]) {
+                cudaFuncSetAttribute(block_sort_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(cub::BlockRadixSort<int, 1024, 4, int>::TempStorage));
+                cudaFuncSetAttribute(block_sort_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(cub::BlockRadixSort<int, 1024, 16, int>::TempStorage));
+                attr_set_dev[p->device & 63] = true;
+            }
+            if (items == 4)
+                block_sort_kernel<4><<<table ? 2 : 1, 1024, smem, st>>>(W, p->d_key_in, bits, p->d_perm_out, p->d_key2_in, 23, p->d_perm_e);
+            else
+                block_sort_kernel<16><<<table ? 2 : 1, 1024, smem, st>>>(W, p->d_key_in, bits, p->d_perm_out, p->d_key2_in, 23, p->d_perm_e);
+        } else {
+            size_t bytes = p->cub_bytes;
+            CK(cub::DeviceRadixSort::SortPairs(p->d_cub, bytes, p->d_key_in, p->d_key_out,
+                                               p->d_perm_in, p->d_perm_out, W, 0, bits, st));
+            if (table) {
+                bytes = p->cub_bytes;
+                CK(cub::DeviceRadixSort::SortPairs(p->d_cub, bytes, p->d_key2_in, p->d_key2_out,
+                                                   p->d_perm_in, p->d_perm_e, W, 0, 23, st));
+            }
+        }
         perm = p->d_perm_out;
-        p->last_launches += 1;   // + CUB's radix-sort passes (library code, not counted)
+        p->last_launches += 2;   // (CUB's device-wide radix-sort passes are library code, not counted)
     }
     FastArgs F;
     memset(&F, 0, sizeof F);
@@ -3093,18 +3167,16 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
     F.cov_lo = p->cover.a_lo; F.cov_hi = p->cover.a_hi;
     F.k_split = p->k_split; F.k_tab_end = p->k_tab_end; F.n_tblk = p->n_tblk; F.blks = p->d_tblk;
     F.ke_fast = p->d_ke_fast; F.ke_low = p->d_ke_low; F.ks_tail = p->d_ks_tail;
-    F.key2 = p->d_key2_in; F.idx2 = p->d_idx2_in; F.slow = p->d_slow;
+    F.inv = p->d_idx2_in; F.slow = p->d_slow;
     if (recur) CK(cudaMemsetAsync(p->d_slow_n, 0, sizeof(int), st));
     walker_setup_kernel<<<gb, tb, 0, st>>>(d, W, wpad, params, stride_walker, stride_param, skip, perm, p->d_wc, p->d_ks, p->d_ke, hh_rows,
                                            calib, cstride_walker, cstride_value, F);
     const int* ke_main = table ? p->d_ke_low : p->d_ke_fast;
     double2* partial3 = p->d_partial + (size_t)n_chunks * nd * wpad;
     if (table) {
-        // second ordering, by last bin, for the tails
-        size_t bytes = p->cub_bytes;
-        CK(cub::DeviceRadixSort::SortPairs(p->d_cub, bytes, p->d_key2_in, p->d_key2_out,
-                                           p->d_idx2_in, p->d_perm_e, W, 0, 23, st));
-        tail_plan_kernel<<<groups, CTA_THREADS, 0, st>>>(W, p->n_blk, p->d_blk_start, p->d_perm_e, p->d_ks_tail, p->d_ke_fast, p->d_grp_b);
+        // the tails are taken in the order of the walkers' last bins
+        tail_plan_kernel<<<groups, CTA_THREADS, 0, st>>>(W, p->n_blk, p->d_blk_start, p->d_perm_e, p->d_idx2_in, p->d_key2_out,
+                                                        p->d_ks_tail, p->d_ke_fast, p->d_grp_b);
         p->last_launches += 1;
     }
     if (p->timing) {
@@ -3136,7 +3208,7 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
         T.recur = true; T.calibrated = false;
         T.n_chunks = n_chunks3; T.per_chunk = tail_blocks; T.n_blk = p->n_blk; T.blk_off = 0;
         T.ks_arr = p->d_ks_tail; T.ke_arr = p->d_ke_fast; T.partial = partial3;
-        T.col = p->d_perm_e; T.grp_b = p->d_grp_b;
+        T.col = p->d_key2_out; T.grp_b = p->d_grp_b;
         launch_main_nd(p, T, st);
         p->last_launches += 2;
     }
