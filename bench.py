@@ -254,7 +254,9 @@ def run_cuda(args):
 
     W = args.walkers
     rng = np.random.default_rng(20182 + rank)
-    P_host = draw_walkers(rng, W)
+    import gwin_b200
+    P_host = gwin_b200.pinned_empty((W, len(PARAMS)))      # the sampler's points live in page-locked host memory
+    P_host[:] = draw_walkers(rng, W)
     bins = bins_used(P_host, plan.kmin, plan.kmax, delta_f)
     P_dev = torch.tensor(P_host, device=dev)
     nd = len(DETS)
@@ -362,8 +364,9 @@ def run_cuda(args):
                            mean_bins_per_eval=float(bins.mean())),
             "clocks": clk,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": world * W * 13 * 8,
-                    "d2h_bytes_per_step": world * W * (1 + 3 * nd) * 8,
-                    "path": "CallModel.batch(points) -> gwin_loglr_batch_host"},
+                    "d2h_bytes_per_step": world * W * 8,
+                    "path": "CallModel.batch(points) -> gwin_loglr_batch_points_host (points in page-locked host memory; "
+                            "H2D of the points, kernels, D2H of loglr inside the timed call)"},
             "gpu_launches": launches,
             "roofline": {
                 "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",

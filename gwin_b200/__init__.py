@@ -5,6 +5,6 @@ The package holds only what that path needs: the CUDA library and its C ABI
 ``CallModel`` / pool protocols, and the ensemble stepper that calls them.
 """
 from . import _lib  # noqa: F401
-from ._lib import GwinCudaError, build  # noqa: F401
+from ._lib import GwinCudaError, build, pinned_empty  # noqa: F401
 
 __version__ = "0.1.0"

@@ -41,6 +41,7 @@ SYMBOLS = (
     "gwin_loglr_batch",
     "gwin_loglr_batch_host", "gwin_loglr_batch_strided",
     "gwin_loglr_batch_host_strided", "gwin_generate_host",
+    "gwin_loglr_batch_points_host", "gwin_host_alloc", "gwin_host_free",
     "gwin_plan_last_launches",
     "gwin_plan_kernel_timing",
     "gwin_ens_propose", "gwin_ens_prior", "gwin_ens_accept", "gwin_ens_swap",
@@ -170,6 +171,14 @@ def load():
         lib.gwin_loglr_batch_host_strided.argtypes = [
             C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.gwin_loglr_batch_points_host.restype = C.c_int
+        lib.gwin_loglr_batch_points_host.argtypes = [
+            C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_int64,
+            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.gwin_host_alloc.restype = C.c_int
+        lib.gwin_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+        lib.gwin_host_free.restype = None
+        lib.gwin_host_free.argtypes = [C.c_void_p]
         lib.gwin_generate_host.restype = C.c_int
         lib.gwin_generate_host.argtypes = [C.c_void_p, dp, dp,
                                            C.POINTER(C.c_int64)]
@@ -216,6 +225,22 @@ def check(rc):
 
 def _dptr(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array in page-locked host memory (``gwin_host_alloc``): the host entry points copy
+    from / into such buffers directly instead of through their staging buffers."""
+    import weakref
+    lib = load()
+    shape = tuple(int(x) for x in np.atleast_1d(shape))
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    ptr = C.c_void_p()
+    check(lib.gwin_host_alloc(C.byref(ptr), nbytes))
+    buf = (C.c_char * max(nbytes, 1)).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, lib.gwin_host_free, ptr.value)
+    return arr
 
 
 class Plan(object):
@@ -392,6 +417,37 @@ class Plan(object):
             self._h, int(mode), W, params.ctypes.data, sw, si,
             sk.ctypes.data if sk is not None else None,
             loglr.ctypes.data, hd.ctypes.data, hh.ctypes.data))
+        return loglr, hd, hh
+
+    def loglr_points_host(self, points, colmap, fixed, mode=MODE_GAUSSIAN, skip=None,
+                          stats=True, col_major=False):
+        """``gwin_loglr_batch_points_host``: ``points`` is the [W, ndim] array of SAMPLED values
+        (``[ndim, W]`` with ``col_major``), ``colmap[i]`` the column holding kernel parameter i
+        (-1: ``fixed[i]``).  Page-locked ``points`` (``pinned_empty``) are copied from directly.
+        ``stats=False`` leaves hd / hh on the device: returns (loglr, None, None)."""
+        points = np.ascontiguousarray(points, dtype=np.float64)
+        if points.ndim != 2:
+            raise ValueError("points must be 2-D")
+        ndim, W = points.shape if col_major else points.shape[::-1]
+        sw, si = (1, W) if col_major else (ndim, 1)
+        cm = np.ascontiguousarray(colmap, dtype=np.int32)
+        fx = np.ascontiguousarray(fixed, dtype=np.float64)
+        if cm.shape != (GWIN_NPARAM,) or fx.shape != (GWIN_NPARAM,):
+            raise ValueError("colmap and fixed must have %d entries" % GWIN_NPARAM)
+        loglr = np.empty(W)
+        hd = hh = None
+        if stats:
+            hd = np.empty((W, self.n_det), dtype=np.complex128)
+            hh = np.empty((W, self.n_det))
+        sk = None
+        if skip is not None:
+            sk = np.ascontiguousarray(skip, dtype=np.uint8)
+            if sk.shape != (W,):
+                raise ValueError("skip must be [W]")
+        check(self._lib.gwin_loglr_batch_points_host(
+            self._h, int(mode), W, points.ctypes.data, ndim, sw, si, cm.ctypes.data,
+            fx.ctypes.data, sk.ctypes.data if sk is not None else None, loglr.ctypes.data,
+            hd.ctypes.data if stats else None, hh.ctypes.data if stats else None))
         return loglr, hd, hh
 
     def loglr_device(self, params, mode=MODE_GAUSSIAN, skip=None, out=None,

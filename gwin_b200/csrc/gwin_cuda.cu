@@ -229,7 +229,7 @@ struct gwin_plan {
     double *d_marg_u, *d_marg_logw, *d_marg_opt;
     // staging for the host API
     double *h_params, *h_out; uint8_t* h_skip;
-    double *d_params, *d_out; uint8_t* d_skip;
+    double *d_params, *d_out, *d_points; uint8_t* d_skip;
     int64_t stage_cap;
     cudaStream_t stream;
     int last_launches;
@@ -495,6 +495,19 @@ __device__ __forceinline__ int waveform_len(double mtot, double delta_f) {
     const double fISCO = vISCO * vISCO * vISCO / piM;
     const double n = fISCO / delta_f + 1.0;
     return n > 2.0e9 ? 2000000000 : (int)n;
+}
+
+// Host entry with a column map: the caller's points[w * sw + c * si] (ndim columns: the sampled
+// parameters, in the caller's order) become the kernels' parameter-major rows; parameters that are
+// not sampled take their fixed value.
+struct PointMap { int col[GWIN_NPARAM]; double fixed[GWIN_NPARAM]; };
+__global__ void expand_points_kernel(int W, const double* __restrict__ pts, int64_t sw, int64_t si, PointMap M,
+                                     double* __restrict__ params) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+#pragma unroll
+    for (int i = 0; i < GWIN_NPARAM; ++i)
+        params[(size_t)i * W + w] = M.col[i] >= 0 ? pts[w * sw + M.col[i] * si] : M.fixed[i];
 }
 
 // Sort keys.  key: the order the walkers are processed in -- key_a0 = false: their last bin (lanes of a
@@ -2608,7 +2621,7 @@ extern "C" void gwin_plan_destroy(gwin_plan* p) {
     cudaFree(p->d_key2_in); cudaFree(p->d_key2_out); cudaFree(p->d_idx2_in); cudaFree(p->d_perm_e); cudaFree(p->d_grp_b);
     cudaFree(p->d_slow); cudaFree(p->d_slow_list); cudaFree(p->d_slow_n); cudaFree(p->d_stats);
     if (p->ev_done_set) cudaEventDestroy(p->ev_done);
-    cudaFree(p->d_params); cudaFree(p->d_out); cudaFree(p->d_skip);
+    cudaFree(p->d_params); cudaFree(p->d_out); cudaFree(p->d_skip); cudaFree(p->d_points);
     cudaFreeHost(p->h_params); cudaFreeHost(p->h_out); cudaFreeHost(p->h_skip);
     if (p->timing) { cudaEventDestroy(p->ev0); cudaEventDestroy(p->ev1); }
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -3252,12 +3265,13 @@ static int ensure_stage(gwin_plan* p, int64_t W) {
     const int nd = p->d.n_det;
     int64_t cap = std::max<int64_t>(W, 1024);
     CK(cudaDeviceSynchronize());
-    cudaFree(p->d_params); cudaFree(p->d_out); cudaFree(p->d_skip);
+    cudaFree(p->d_params); cudaFree(p->d_out); cudaFree(p->d_skip); cudaFree(p->d_points);
     cudaFreeHost(p->h_params); cudaFreeHost(p->h_out); cudaFreeHost(p->h_skip);
     p->d_params = p->d_out = nullptr; p->d_skip = nullptr;
     p->h_params = p->h_out = nullptr; p->h_skip = nullptr; p->stage_cap = 0;
     const size_t out_row = 1 + 3 * (size_t)nd;
     CK(cudaMalloc(&p->d_params, sizeof(double) * GWIN_NPARAM * cap));
+    CK(cudaMalloc(&p->d_points, sizeof(double) * GWIN_NPARAM * cap));
     CK(cudaMalloc(&p->d_out, sizeof(double) * out_row * cap));
     CK(cudaMalloc(&p->d_skip, cap));
     CK(cudaMallocHost(&p->h_params, sizeof(double) * GWIN_NPARAM * cap));
@@ -3386,6 +3400,102 @@ static int loglr_batch_host_impl(gwin_plan* p, int mode, int64_t W,
         if (table) p->replan = true;
     }
     memcpy(loglr, h_lr, sizeof(double) * W);
+    if (hd) memcpy(hd, h_hd, sizeof(double) * 2 * nd * W);
+    if (hh) memcpy(hh, h_hh, sizeof(double) * nd * W);
+    return GWIN_OK;
+}
+
+static bool host_pinned(const void* ptr) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+extern "C" int gwin_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return fail(GWIN_EINVAL, "NULL argument");
+    *ptr = nullptr;
+    CK(cudaMallocHost(ptr, bytes ? bytes : 1));
+    return GWIN_OK;
+}
+extern "C" void gwin_host_free(void* ptr) { if (ptr) cudaFreeHost(ptr); }
+
+extern "C" int gwin_loglr_batch_points_host(gwin_plan* p, int mode, int64_t W,
+                                            const double* points, int ndim, int64_t stride_walker, int64_t stride_col,
+                                            const int* map, const double* fixed, const uint8_t* skip,
+                                            double* loglr, double* hd, double* hh) {
+    if (!p) return fail(GWIN_EINVAL, "plan is NULL");
+    if (W < 0) return fail(GWIN_EINVAL, "W < 0");
+    if (W == 0) { p->last_launches = 0; return GWIN_OK; }
+    if (!map || !fixed || !loglr) return fail(GWIN_EINVAL, "map/fixed/loglr is NULL");
+    if (ndim < 0 || ndim > GWIN_NPARAM) return fail(GWIN_EINVAL, "ndim must be 0..%d", GWIN_NPARAM);
+    if (ndim > 0 && !points) return fail(GWIN_EINVAL, "points is NULL");
+    if (ndim > 0 && !((stride_walker == ndim && stride_col == 1) || (stride_walker == 1 && stride_col == W)))
+        return fail(GWIN_EINVAL, "host points must be a dense [W][ndim] or [ndim][W] block");
+    PointMap M;
+    for (int i = 0; i < GWIN_NPARAM; ++i) {
+        if (map[i] >= ndim) return fail(GWIN_EINVAL, "map[%d] = %d is not a column of the points", i, map[i]);
+        M.col[i] = map[i] < 0 ? -1 : map[i];
+        M.fixed[i] = fixed[i];
+    }
+    CK(cudaSetDevice(p->device));
+    int rc = ensure_stage(p, W);
+    if (rc) return rc;
+    const int nd = p->d.n_det;
+    cudaStream_t st = p->stream;
+    // parameters: straight from the caller's buffer when it is page-locked, else through the staging buffer
+    if (ndim > 0) {
+        const double* src = points;
+        if (!host_pinned(points)) {
+            memcpy(p->h_params, points, sizeof(double) * (size_t)ndim * W);
+            src = p->h_params;
+        }
+        CK(cudaMemcpyAsync(p->d_points, src, sizeof(double) * (size_t)ndim * W, cudaMemcpyHostToDevice, st));
+    }
+    if (skip) {
+        memcpy(p->h_skip, skip, W);
+        CK(cudaMemcpyAsync(p->d_skip, p->h_skip, W, cudaMemcpyHostToDevice, st));
+    }
+    expand_points_kernel<<<(int)((W + 127) / 128), 128, 0, st>>>((int)W, p->d_points, stride_walker, stride_col, M, p->d_params);
+    const bool table = p->kernel != GWIN_KERNEL_DIRECT && table_wanted(p, W, false);
+    if (p->auto_mchirp && p->kernel != GWIN_KERNEL_DIRECT && !table) {
+        // (as in the plain host entry point: the schedule follows the lightest system of the batch)
+        const int c1 = M.col[0], c2 = M.col[1];
+        double mc5_min = 1e300;
+        for (int64_t i = 0; i < W; ++i) {
+            if (skip && skip[i]) continue;
+            const double m1 = c1 >= 0 ? points[i * stride_walker + c1 * stride_col] : M.fixed[0];
+            const double m2 = c2 >= 0 ? points[i * stride_walker + c2 * stride_col] : M.fixed[1];
+            if (!(m1 > 0.0) || !(m2 > 0.0) || !std::isfinite(m1 + m2)) continue;
+            const double pm = m1 * m2;
+            mc5_min = std::min(mc5_min, pm * pm * pm / (m1 + m2));
+            if (c1 < 0 && c2 < 0) break;
+        }
+        if (mc5_min < 1e300) {
+            const double mc_min = std::min(std::max(std::pow(mc5_min, 0.2), 0.02), 1e4);
+            const double q = std::exp2(std::floor(4.0 * std::log2(mc_min)) / 4.0);
+            if (q != p->mchirp_min) { p->mchirp_min = q; p->sched_dirty = true; }
+        }
+    }
+    double* d_lr = p->d_out;
+    double* d_hd = p->d_out + p->stage_cap;
+    double* d_hh = d_hd + 2 * (size_t)nd * p->stage_cap;
+    rc = loglr_batch_impl(p, mode, W, p->d_params, 1, W, nullptr, 0, 0, skip ? p->d_skip : nullptr,
+                          d_lr, hd ? d_hd : nullptr, hh ? d_hh : nullptr, st);
+    if (rc) return rc;
+    p->last_launches += 1;
+    double* h_lr = p->h_out;
+    double* h_hd = p->h_out + p->stage_cap;
+    double* h_hh = h_hd + 2 * (size_t)nd * p->stage_cap;
+    int* h_slow = reinterpret_cast<int*>(p->h_out + (1 + 3 * (size_t)nd) * p->stage_cap);
+    *h_slow = 0;
+    const bool direct_out = host_pinned(loglr);
+    CK(cudaMemcpyAsync(direct_out ? loglr : h_lr, d_lr, sizeof(double) * W, cudaMemcpyDeviceToHost, st));
+    if (hd) CK(cudaMemcpyAsync(h_hd, d_hd, sizeof(double) * 2 * nd * W, cudaMemcpyDeviceToHost, st));
+    if (hh) CK(cudaMemcpyAsync(h_hh, d_hh, sizeof(double) * nd * W, cudaMemcpyDeviceToHost, st));
+    if (p->kernel != GWIN_KERNEL_DIRECT) CK(cudaMemcpyAsync(h_slow, p->d_slow_n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (*h_slow > 4 + W / 64 && !p->cover_manual && table) p->replan = true;
+    if (!direct_out) memcpy(loglr, h_lr, sizeof(double) * W);
     if (hd) memcpy(hd, h_hd, sizeof(double) * 2 * nd * W);
     if (hh) memcpy(hh, h_hh, sizeof(double) * nd * W);
     return GWIN_OK;

@@ -48,7 +48,8 @@ class CallModel(object):
 
     def batch(self, points, callstat=None):
         """All points at once: returns a ``BatchResult``."""
-        return self.model.evaluate_batch(points, callstat=callstat or self.callstat)
+        return self.model.evaluate_batch(points, callstat=callstat or self.callstat,
+                                         with_stats=self.return_all_stats)
 
 
 models = {_cls.name: _cls for _cls in (

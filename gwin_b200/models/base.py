@@ -282,7 +282,7 @@ class BaseModel(object, metaclass=ABCMeta):
             out[i] = self.loglikelihood
         return out, OrderedDict()
 
-    def evaluate_batch(self, points, callstat='logposterior'):
+    def evaluate_batch(self, points, callstat='logposterior', with_stats=True):
         """Evaluate ``callstat`` for W points given in ``sampling_params`` order.
 
         Returns a ``BatchResult`` whose ``stats`` are materialised on first use.
@@ -290,6 +290,9 @@ class BaseModel(object, metaclass=ABCMeta):
         ``models/__init__.py:101-137``) including the ``logprior == -inf``
         short-circuit of ``logposterior``/``logplr``; stats that the scalar
         path would not have computed for a point are NaN for that point.
+        ``with_stats=False`` tells the model that only ``values`` will be read (the
+        per-detector statistics are then not brought back from the device; asking
+        for them anyway evaluates the batch again).
         """
         points = numpy.asarray(points, dtype=numpy.float64)
         if points.ndim == 1:
@@ -317,7 +320,12 @@ class BaseModel(object, metaclass=ABCMeta):
         skip = None
         if callstat in ('logposterior', 'logplr'):
             skip = numpy.isneginf(logp)
-        values, more = self._batch_callstat(callstat, params, W, skip, logp, stats)
+        # hints for models that can hand the sampled columns to a kernel as they are
+        self._batch_hint = (points, samples, bool(with_stats))
+        try:
+            values, more = self._batch_callstat(callstat, params, W, skip, logp, stats)
+        finally:
+            self._batch_hint = None
         if callable(more):
             base = stats
 

@@ -15,7 +15,7 @@ import numpy
 
 from .. import _lib
 from ..calibration import spline_frequencies, values_matrix
-from ..waveform import check_waveform_params, param_rows
+from ..waveform import WAVEFORM_PARAMS, check_waveform_params, param_rows
 from .base_data import BaseDataModel
 
 
@@ -132,15 +132,47 @@ class GaussianNoise(BaseDataModel):
         static.update(self._static_params)
         return static
 
-    def _kernel_call(self, params, W, skip=None):
+    def _kernel_call(self, params, W, skip=None, stats=True):
+        """One launch for W points.  The kernel's 13-parameter rows are assembled on the device
+        (``gwin_loglr_batch_points_host``): when the sampled columns reach the waveform unchanged
+        -- no transforms, no boundary condition touched them -- the sampler's own ``points`` array
+        is handed over as it is; otherwise the parameters that vary go through a page-locked
+        block, one row each.  Parameters that do not vary travel as 13 scalars."""
         static = self._static_for_kernel()
-        P = param_rows(params, W, static=static)
-        calib = None
         if self._recalib:
-            calib = values_matrix(self._recalib, self._dets, params, W,
-                                  static=static)
-        return self._plan.loglr_host(P, mode=self._mode, skip=skip,
-                                     param_major=True, calib=calib)
+            P = param_rows(params, W, static=static)
+            calib = values_matrix(self._recalib, self._dets, params, W, static=static)
+            return self._plan.loglr_host(P, mode=self._mode, skip=skip,
+                                         param_major=True, calib=calib)
+        hint = getattr(self, '_batch_hint', None)
+        points, samples = (hint[0], hint[1]) if hint is not None else (None, {})
+        colmap = numpy.full(len(WAVEFORM_PARAMS), -1, dtype=numpy.int32)
+        fixed = numpy.zeros(len(WAVEFORM_PARAMS))
+        varying = []
+        direct = points is not None
+        for i, (name, default) in enumerate(WAVEFORM_PARAMS.items()):
+            if name in params and numpy.ndim(params[name]) > 0:
+                varying.append((i, name))
+                direct = direct and params[name] is samples.get(name)
+                continue
+            v = params.get(name, static.get(name, default))
+            if v is None:
+                raise ValueError("waveform parameter %r was not provided" % name)
+            fixed[i] = v
+        if direct:
+            order = {name: j for j, name in enumerate(self.sampling_params)}
+            for i, name in varying:
+                colmap[i] = order[name]
+            return self._plan.loglr_points_host(points, colmap, fixed, mode=self._mode,
+                                                skip=skip, stats=stats)
+        key = (len(varying), W)
+        if getattr(self, '_rows_key', None) != key:
+            self._rows_key, self._rows = key, _lib.pinned_empty(key)
+        for j, (i, name) in enumerate(varying):
+            self._rows[j] = params[name]
+            colmap[i] = j
+        return self._plan.loglr_points_host(self._rows, colmap, fixed, mode=self._mode,
+                                            skip=skip, stats=stats, col_major=True)
 
     def _nowaveform_loglr(self):
         for det in self._data:
@@ -192,13 +224,19 @@ class GaussianNoise(BaseDataModel):
     def _batch_callstat(self, callstat, params, W, skip, logp, stats):
         if callstat not in ('logposterior', 'loglikelihood', 'loglr', 'logplr'):
             raise ValueError("unsupported callstat %r" % callstat)
-        lr, hd, hh = self._kernel_call(params, W, skip=skip)
+        hint = getattr(self, '_batch_hint', None)
+        want = hint[2] if hint is not None else True
+        lr, hd, hh = self._kernel_call(params, W, skip=skip, stats=want)
         lognl = self.lognl
         logl = lr + lognl
+        held = {'hd': hd, 'hh': hh}
 
         def extra():
+            if held['hd'] is None:
+                # the caller said it would not read the statistics, and does: evaluate again
+                _, held['hd'], held['hh'] = self._kernel_call(params, W, skip=skip, stats=True)
             dead = numpy.isneginf(lr)
-            out = self._det_stats(hd, hh, dead)
+            out = self._det_stats(held['hd'], held['hh'], dead)
             out['loglr'] = lr
             out['loglikelihood'] = logl
             if skip is not None and skip.any():

@@ -15,6 +15,7 @@
 #ifndef GWIN_B200_H
 #define GWIN_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -195,6 +196,24 @@ int gwin_loglr_batch_host_strided(gwin_plan* plan, int mode, int64_t W,
                                   const double* params, int64_t stride_walker, int64_t stride_param,
                                   const uint8_t* skip,
                                   double* loglr, double* hd, double* hh);
+
+/*
+ * Host entry with a column map, for callers that hold the SAMPLED parameters only (what a sampler hands
+ * to pool.map: one row of model.sampling_params values per walker, models/__init__.py:101-110).
+ *   points  HOST, dense [W][ndim] (stride_walker = ndim, stride_col = 1) or [ndim][W] (1, W)
+ *   map     [GWIN_NPARAM]: for every kernel parameter the column of `points` that holds it, or -1
+ *   fixed   [GWIN_NPARAM]: the value of every parameter whose map entry is -1 (static parameters)
+ * The rows of gwin_loglr_batch are assembled on the device.  Buffers that are page-locked
+ * (gwin_host_alloc, cudaHostAlloc, a pinned torch tensor) are copied from / into directly; pageable
+ * ones go through the plan's staging buffers.  hd / hh may be NULL (then they are not copied back).
+ */
+int gwin_loglr_batch_points_host(gwin_plan* plan, int mode, int64_t W,
+                                 const double* points, int ndim, int64_t stride_walker, int64_t stride_col,
+                                 const int* map, const double* fixed, const uint8_t* skip,
+                                 double* loglr, double* hd, double* hh);
+/* Page-locked host memory for the buffers of the host entry points. */
+int gwin_host_alloc(void** ptr, size_t bytes);
+void gwin_host_free(void* ptr);
 
 /*
  * FDomainDetFrameGenerator.generate (the call at gaussian_noise.py:322) for ONE
