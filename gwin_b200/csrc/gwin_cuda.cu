@@ -216,6 +216,8 @@ struct gwin_plan {
     double2* d_partialT; size_t partialT_cap;
     // walker order bookkeeping of the table path
     int *d_ke_fast, *d_ke_low, *d_ks_tail, *d_key2_in, *d_key2_out, *d_idx2_in, *d_perm_e, *d_grp_b;
+    int *d_key3_in, *d_perm_t, *d_col_t;
+    int tab_split;           // sub-blocks from here on have at most two reference chirps: taken in time order
     // slow path: walkers the fast kernels cannot take (outside the schedule / the tables' coverage)
     unsigned char* d_slow;
     int *d_slow_list, *d_slow_n;         // d_slow_n[0]: this batch, [1]: since the last query
@@ -513,24 +515,30 @@ __global__ void expand_points_kernel(int W, const double* __restrict__ pts, int6
 // Sort keys.  key: the order the walkers are processed in -- key_a0 = false: their last bin (lanes of a
 // warp finish together); true (table path): their Newtonian chirp coefficient quantised over the
 // covered range (lanes of a warp share a reference chirp and sit in neighbouring table rows).
-// key_e (table path): the last bin again, the order in which the tails are taken.  Walkers without
-// a waveform sort to one end.
+// key_e (table path): the last bin again, the order in which the tails are taken.  key_t (table path):
+// the chirp's local time, the order in which the long sub-blocks at high frequency are taken (lanes
+// of a warp read the same table rows).  Walkers without a waveform sort to one end.
 __global__ void sort_key_kernel(PlanDev P, int W, const double* __restrict__ params,
                                 int64_t sw, int64_t si,
                                 const uint8_t* __restrict__ skip, int* __restrict__ key,
                                 int* __restrict__ idx, bool key_a0, double a_lo, double a_scale,
-                                int* __restrict__ key_e) {
+                                int* __restrict__ key_e, int* __restrict__ key_t, double tfac) {
     int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= W) return;
     double p[GWIN_NPARAM];
     load_params(p, params, w, sw, si);
     const bool ok = !(skip && skip[w]) && params_ok(p) && has_waveform(p, P.f_lower_wf);
-    int k = key_a0 ? (1 << TAB_KEY_BITS) - 1 : 0, ke = 0;
+    int k = key_a0 ? (1 << TAB_KEY_BITS) - 1 : 0, ke = 0, kt = (1 << 22) - 1;
     if (ok) {
         ke = min(waveform_len(p[0] + p[1], P.delta_f), P.kmax);
         if (key_a0) {
-            const double q = (newtonian_coef(p[0], p[1]) - a_lo) * a_scale;
+            const double a0 = newtonian_coef(p[0], p[1]);
+            const double q = (a0 - a_lo) * a_scale;
             k = (int)fmin(fmax(q, 0.0), (double)((1 << TAB_KEY_BITS) - 2));
+            // local time of the chirp at the frequency where the time-ordered sub-blocks begin, as a
+            // fraction of the segment: t_c - (5/3) a0 f^(-8/3)   (Theta = a0 f^(-5/3) turns to leading order)
+            const double tl = (p[10] - P.epoch - a0 * tfac) * P.delta_f;
+            kt = (int)((tl - floor(tl)) * (double)((1 << 22) - 2));
         } else {
             k = ke;
         }
@@ -538,21 +546,23 @@ __global__ void sort_key_kernel(PlanDev P, int W, const double* __restrict__ par
     key[w] = k;
     idx[w] = w;
     if (key_e) key_e[w] = ke;
+    if (key_t) key_t[w] = kt;
 }
 
 // Batches of up to 16384 walkers: one CTA sorts (key, index) pairs in shared memory (stable LSD radix
-// sort, cub::BlockRadixSort); CTA y sorts key set y -- the table path's two orders in one launch
-// instead of two device-wide sorts of five launches each.
+// sort, cub::BlockRadixSort); CTA x sorts key set x -- the table path's three orders in one launch
+// instead of three device-wide sorts of five launches each.
+struct SortJob { const int* key; int bits; int* out; };
+struct SortJobs { SortJob j[3]; };
 template <int ITEMS>
 __global__ void __launch_bounds__(1024)
-block_sort_kernel(int W, const int* __restrict__ key0, int bits0, int* __restrict__ out0,
-                  const int* __restrict__ key1, int bits1, int* __restrict__ out1) {
+block_sort_kernel(int W, SortJobs jobs) {
     using Sort = cub::BlockRadixSort<int, 1024, ITEMS, int>;
     extern __shared__ __align__(16) unsigned char s_sort[];
     typename Sort::TempStorage& temp = *reinterpret_cast<typename Sort::TempStorage*>(s_sort);
-    const int* key = blockIdx.x ? key1 : key0;
-    int* out = blockIdx.x ? out1 : out0;
-    const int bits = blockIdx.x ? bits1 : bits0;
+    const int* key = jobs.j[blockIdx.x].key;
+    int* out = jobs.j[blockIdx.x].out;
+    const int bits = jobs.j[blockIdx.x].bits;
     int k[ITEMS], v[ITEMS];
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
@@ -1506,32 +1516,63 @@ __global__ void cover_stats_kernel(PlanDev P, int W, const double* __restrict__ 
 }
 
 #ifndef TABLE_MIN_CTAS
-#define TABLE_MIN_CTAS 4
+#define TABLE_MIN_CTAS 2
 #endif
 #define TAB_SPAN 24          // table rows a warp stages per detector and sub-block (>= TAB_W + the lanes' spread)
 #define TAB_ROWB (TAB_NM * 16 + 16)
-#define TAB_CHUNK_MAX 16     // sub-blocks per CTA at most (their Taylor matrices are staged in shared memory)
+#define TAB_CHUNK_MAX 8      // sub-blocks per CTA at most (their Taylor matrices are staged in shared memory)
+#ifndef TAB_COEF_SMEM
+#define TAB_COEF_SMEM 1      // per-thread coefficients in shared memory (1) or in registers (0)
+#endif
+#define TAB_CROWS(nd) (NPH + 2 * (nd))      // per-thread coefficient column: phase coefficients, tau_hi/lo per detector
+#define TAB_WPITCH TAB_SPAN                 // window weights per lane [doubles], stored [window row][lane]
+// Thread t works on column col_arr[t] of the per-walker arrays (NULL: t itself): the sub-blocks with
+// several reference chirps are taken with the walkers ordered by a0 (lanes share a reference), the
+// long sub-blocks above them with the walkers ordered by their local time (lanes share table rows:
+// one shared-memory wavefront per load instead of one per distinct row).  The launch covers sub-blocks
+// [blk_lo, blk_hi); CTA y takes blocks_per_chunk of them and writes partial-sum slot blk_lo / blocks_per_chunk + y.
 template <int ND>
 __global__ void __launch_bounds__(CTA_THREADS, TABLE_MIN_CTAS)
-loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
+loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo, int blk_hi,
                    const TabBlk* __restrict__ blks, const double* __restrict__ cmat,
                    const double* __restrict__ tref, const double2* __restrict__ tab,
                    const double* __restrict__ wc, const int* __restrict__ ke_arr,
-                   double2* __restrict__ partial, unsigned char* __restrict__ slow) {
+                   double2* __restrict__ partial, unsigned char* __restrict__ slow,
+                   const int* __restrict__ col_arr) {
     const int t = blockIdx.x * CTA_THREADS + threadIdx.x;
-    const int chunk = blockIdx.y;
-    const int b0 = chunk * blocks_per_chunk;
-    const int b1 = min(b0 + blocks_per_chunk, n_tblk);
+    const int b0 = blk_lo + blockIdx.y * blocks_per_chunk;
+    const int b1 = min(b0 + blocks_per_chunk, blk_hi);
+    const int chunk = b0 / blocks_per_chunk;
     const bool live = t < W;
-    const int ke = live ? ke_arr[t] : 0;
-    // shared memory: [chunk's Taylor matrices][per-warp staging buffers: ND x TAB_SPAN table rows of
-    // TAB_ROWB bytes (128 B of moments + 16 B of padding against bank conflicts)]
+    const int col = live ? (col_arr ? col_arr[t] : t) : 0;
+    const int ke = live ? ke_arr[col] : 0;
+    // shared memory: [chunk's Taylor matrices][per-thread coefficient columns][per-warp staging buffers:
+    // ND x TAB_SPAN table rows of TAB_ROWB bytes (128 B of moments + 16 B of padding against bank conflicts)]
     extern __shared__ __align__(16) unsigned char s_tab[];
     double* s_c = reinterpret_cast<double*>(s_tab);
-    unsigned char* s_warp = s_tab + (size_t)blocks_per_chunk * NPH * TAB_NTP * sizeof(double)
+    double* s_coef = s_c + (size_t)blocks_per_chunk * NPH * TAB_NTP;
+    double* s_wt = s_coef + (TAB_COEF_SMEM ? TAB_CROWS(ND) : 0) * CTA_THREADS + (size_t)(threadIdx.x / WARP) * WARP * TAB_WPITCH;
+    unsigned char* s_warp = reinterpret_cast<unsigned char*>(s_coef + ((TAB_COEF_SMEM ? TAB_CROWS(ND) : 0) + TAB_WPITCH) * CTA_THREADS)
                           + (size_t)(threadIdx.x / WARP) * ND * TAB_SPAN * TAB_ROWB;
     for (int i = threadIdx.x; i < (b1 - b0) * NPH * TAB_NTP; i += CTA_THREADS)
         s_c[i] = cmat[(size_t)b0 * NPH * TAB_NTP + i];
+    // per-thread coefficients live in shared memory (one column per thread, no sharing): they are needed
+    // once per sub-block, and keeping them out of the register file keeps the tap loop from spilling
+#if TAB_COEF_SMEM
+    double* sa = s_coef + threadIdx.x;
+#define TCOEF(i) sa[(i) * CTA_THREADS]
+#else
+    double sa[TAB_CROWS(ND)];
+#define TCOEF(i) sa[i]
+#endif
+#pragma unroll
+    for (int i = 0; i < NPH; ++i) TCOEF(i) = wc[(size_t)i * wpad + col];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        const double* row = wc + (size_t)(C_DET0 + D_NROW * d) * wpad + col;
+        TCOEF(NPH + 2 * d) = row[D_TAUHI * wpad];
+        TCOEF(NPH + 2 * d + 1) = row[D_TAULO * wpad];
+    }
     __syncthreads();
     const int k0 = blks[b0].start;
     const bool has = k0 < ke;
@@ -1542,17 +1583,6 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
 #pragma unroll
     for (int d = 0; d < ND; ++d) acc[d] = make_double2(0.0, 0.0);
     if (k0 < whi) {
-        const int tt = live ? t : 0;
-        double a[NPH];
-#pragma unroll
-        for (int i = 0; i < NPH; ++i) a[i] = wc[(size_t)i * wpad + tt];
-        double tau_hi[ND], tau_lo[ND];
-#pragma unroll
-        for (int d = 0; d < ND; ++d) {
-            const double* row = wc + (size_t)(C_DET0 + D_NROW * d) * wpad + tt;
-            tau_hi[d] = row[D_TAUHI * wpad];
-            tau_lo[d] = row[D_TAULO * wpad];
-        }
         const int lane = threadIdx.x & (WARP - 1);
         bool dead = false;                              // this walker left the table path
         for (int b = b0; b < b1; ++b) {
@@ -1563,7 +1593,10 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
             const unsigned amask = __ballot_sync(0xffffffffu, act);
             if (!amask) continue;
             // ---- reference chirp: the nearest one on the sub-block's grid (a function of the walker alone)
-            int r = (int)((a[0] - B.a_lo) * B.inv_da);
+#if TAB_COEF_SMEM
+            asm volatile("" ::: "memory");               // re-read the coefficient column per sub-block: do not hoist
+#endif
+            int r = (int)((TCOEF(0) - B.a_lo) * B.inv_da);
             r = max(0, min(r, B.K - 1));
             // ---- Taylor coefficients of the phase about the centre: t_n = sum_i a_i c[i][n]
             const double* sc = s_c + (size_t)(b - b0) * NPH * TAB_NTP;
@@ -1572,8 +1605,9 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
             for (int n = 0; n < TAB_NT; ++n) tq[n] = 0.0;
 #pragma unroll
             for (int i = 0; i < NPH; ++i) {
+                const double ai = TCOEF(i);
 #pragma unroll
-                for (int n = 0; n < TAB_NT; ++n) tq[n] = fma(a[i], sc[i * TAB_NTP + n], tq[n]);
+                for (int n = 0; n < TAB_NT; ++n) tq[n] = fma(ai, sc[i * TAB_NTP + n], tq[n]);
             }
             // ---- e_n: Taylor coefficients of exp(U), U = i sum_{k=2..8} w_k s^k, w_k = -2 pi (t_k - t_k^ref):
             //   n e_n = sum_k k (i w_k) e_{n-k};  e_0 = 1, e_1 = 0 (nu carries the slope)
@@ -1610,7 +1644,7 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
                                  + fabs(en[TAB_DEG + 2].x) + fabs(en[TAB_DEG + 2].y)
                                  + 1.2 * B.eps * u8 * (1.0 + 1.2 * B.eps);
                 if (act && (est > TAB_EST_MAX || G_TWOPI * rho > TAB_RHO_MAX)) {
-                    slow[t] = 1;                        // outside what the tables were built for: slow path
+                    slow[col] = 1;                      // outside what the tables were built for: slow path
                     dead = true;
                     act = false;
                 }
@@ -1628,7 +1662,7 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
             int gs[ND];
 #pragma unroll
             for (int d = 0; d < ND; ++d) {
-                const double nu = tq[1] / h + (tau_hi[d] + tau_lo[d]);    // turns per bin
+                const double nu = tq[1] / h + (TCOEF(NPH + 2 * d) + TCOEF(NPH + 2 * d + 1));    // turns per bin
                 xs[d] = (nu - floor(nu)) * (double)L;                     // [0, L)
                 const int g0 = (int)ceil(xs[d] - 0.5 * TAB_W);            // -6 .. L - 6
                 gs[d] = g0 < 0 ? g0 + L : g0;
@@ -1639,7 +1673,7 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
                 const int rL = __shfl_sync(0xffffffffu, r, __ffs(todo) - 1);
                 const bool mine = act && r == rL;
                 todo &= ~__ballot_sync(0xffffffffu, mine);
-                int lo[ND];
+                int lo[ND], span_d[ND];
                 bool staged[ND];
                 __syncwarp();                           // the previous pass's rows have been read
 #pragma unroll
@@ -1652,6 +1686,7 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
                     }
                     lo[d] = mn;
                     const int span = mx - mn + TAB_W;
+                    span_d[d] = span;
                     staged[d] = span <= TAB_SPAN;
                     if (staged[d]) {
                         const double2* src = row0 + (((size_t)rL * ND + d) * (L + TAB_W) + mn) * TAB_NM;
@@ -1670,34 +1705,50 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
                     double2 Mn[TAB_NM];
 #pragma unroll
                     for (int n = 0; n < TAB_NM; ++n) Mn[n] = make_double2(0.0, 0.0);
-                    // rows are padded with TAB_W wrap-around points: the taps are contiguous
-                    const double2* rd = row0 + (((size_t)rL * ND + d) * (L + TAB_W) + gs[d]) * TAB_NM;
-                    const unsigned char* sd = s_warp + ((size_t)d * TAB_SPAN + (mine ? gs[d] - lo[d] : 0)) * TAB_ROWB;
                     const double v = xs[d];
-                    // kernel weights: 13 independent Horner chains in v = 2 (x - g0) - (W - 1), coefficients
-                    // as literal constants (constant-bank operands, no loads)
+                    // kernel weights: 13 independent Horner chains in v = 2 (x - g0) - (W - 1), coefficients as
+                    // literal constants (constant-bank operands, no loads)
                     double wt[TAB_W];
                     wt[0] = TAB_TAP_0(v); wt[1] = TAB_TAP_1(v); wt[2] = TAB_TAP_2(v); wt[3] = TAB_TAP_3(v);
                     wt[4] = TAB_TAP_4(v); wt[5] = TAB_TAP_5(v); wt[6] = TAB_TAP_6(v); wt[7] = TAB_TAP_7(v);
                     wt[8] = TAB_TAP_8(v); wt[9] = TAB_TAP_9(v); wt[10] = TAB_TAP_10(v); wt[11] = TAB_TAP_11(v);
                     wt[12] = TAB_TAP_12(v);
-                    if (!waited) {                       // the weights above overlapped the copies
-                        asm volatile("cp.async.wait_group 0;" ::: "memory");
-                        __syncwarp();
-                        waited = true;
-                    }
                     if (staged[d]) {
+                        // The staged rows are a window of span = 13 + (spread of the lanes' first rows) rows.
+                        // Each lane lays its 13 weights into a zeroed row of that length at its own offset;
+                        // then the warp walks the window row by row: the table row is read with warp-uniform
+                        // 128-bit loads (one shared-memory wavefront each, whatever the spread) and every
+                        // lane multiplies by its own weight for that row.
+                        const int span = span_d[d];
+                        double* sw = s_wt + lane;        // [window row][lane]: conflict-free whatever the lanes' offsets
+                        __syncwarp();                    // the previous detector's weights have been read
 #pragma unroll
-                        for (int i = 0; i < TAB_W; ++i) {
-                            const double2* e = reinterpret_cast<const double2*>(sd + i * TAB_ROWB);
+                        for (int j = 0; j < TAB_SPAN; ++j) sw[j * WARP] = 0.0;
+                        if (mine) {
+                            double* so = sw + (gs[d] - lo[d]) * WARP;
+#pragma unroll
+                            for (int i = 0; i < TAB_W; ++i) so[i * WARP] = wt[i];
+                        }
+                        if (!waited) {                   // the weights above overlapped the copies
+                            asm volatile("cp.async.wait_group 0;" ::: "memory");
+                            waited = true;
+                        }
+                        __syncwarp();
+                        const unsigned char* sr = s_warp + (size_t)d * TAB_SPAN * TAB_ROWB;
+#pragma unroll 2
+                        for (int j = 0; j < span; ++j) {
+                            const double w = sw[j * WARP];
+                            const double2* e = reinterpret_cast<const double2*>(sr + j * TAB_ROWB);
 #pragma unroll
                             for (int n = 0; n < TAB_NM; ++n) {
                                 const double2 q = e[n];
-                                Mn[n].x = fma(wt[i], q.x, Mn[n].x);
-                                Mn[n].y = fma(wt[i], q.y, Mn[n].y);
+                                Mn[n].x = fma(w, q.x, Mn[n].x);
+                                Mn[n].y = fma(w, q.y, Mn[n].y);
                             }
                         }
-                    } else if (mine) {                   // lanes too far apart in time: straight from L2
+                    } else if (mine) {                   // lanes too far apart in time: every lane its own rows, from L2
+                        // rows are padded with TAB_W wrap-around points: the taps are contiguous
+                        const double2* rd = row0 + (((size_t)rL * ND + d) * (L + TAB_W) + gs[d]) * TAB_NM;
 #pragma unroll
                         for (int i = 0; i < TAB_W; ++i) {
                             const double2* e = rd + i * TAB_NM;
@@ -1713,7 +1764,7 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
                     double2 sum = Mn[0];
 #pragma unroll
                     for (int n = 2; n <= TAB_DEG; ++n) sum = cfma(en[n], Mn[n - 1], sum);
-                    const double th0 = tq[0] + fma(kc, tau_lo[d], frac1(kc * tau_hi[d]));
+                    const double th0 = tq[0] + fma(kc, TCOEF(NPH + 2 * d + 1), frac1(kc * TCOEF(NPH + 2 * d)));
                     if (mine) acc[d] = cfma(sum, phasor_neg(th0), acc[d]);
                 }
             }
@@ -1722,8 +1773,9 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
     if (live && has) {
 #pragma unroll
         for (int d = 0; d < ND; ++d)
-            partial[((size_t)chunk * ND + d) * wpad + t] = acc[d];
+            partial[((size_t)chunk * ND + d) * wpad + col] = acc[d];
     }
+#undef TCOEF
 }
 
 // Tails of the table path.  Walkers are taken in the order of their last bin: perm_e[t] is the t-th
@@ -1732,13 +1784,15 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int n_tblk,
 __global__ void __launch_bounds__(CTA_THREADS)
 tail_plan_kernel(int W, int n_blk, const int* __restrict__ blk_start, const int* __restrict__ perm_e,
                  const int* __restrict__ inv, int* __restrict__ col_e,
-                 const int* __restrict__ ks_tail, const int* __restrict__ ke_fast, int* __restrict__ grp_b) {
+                 const int* __restrict__ ks_tail, const int* __restrict__ ke_fast, int* __restrict__ grp_b,
+                 const int* __restrict__ perm_t, int* __restrict__ col_t) {
     __shared__ int s_lo[CTA_THREADS / WARP], s_hi[CTA_THREADS / WARP];
     const int t = blockIdx.x * CTA_THREADS + threadIdx.x;
     int lo = 0x7fffffff, hi = 0;
     if (t < W) {
         const int col = inv[perm_e[t]];
         col_e[t] = col;
+        if (perm_t) col_t[t] = inv[perm_t[t]];
         const int a = ks_tail[col], e = ke_fast[col];
         if (a >= 0 && a < e) { lo = a; hi = e; }
     }
@@ -1988,9 +2042,33 @@ __global__ void generate_len_kernel(PlanDev P, const double* __restrict__ params
 // reads three registers no neighbouring instruction reads (no reuse-cache help); variant 2:
 // the hot loop's own pattern, 4 independent unit-phasor complex multiplications per step
 // (2 DMUL + 2 DFMA each).
+__device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
 template <int VARIANT>
 __global__ void dfma_probe_kernel(double* out, int iters) {
     const double t0 = threadIdx.x * 1e-9;
+    if (VARIANT == 3 || VARIANT == 4) {
+        // 3: eight independent FP64 tensor-core MMAs (m8n8k4) per iteration; 4: the same interleaved with
+        // eight independent DFMAs (do the two pipes overlap?)
+        double d[8][2], f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { d[i][0] = t0 + i; d[i][1] = t0 - i; f[i] = t0 + 0.5 * i; }
+        const double a = 0.999999 + t0, b = 1e-9 + t0, m = 0.999999999, c = 1e-12;
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                dmma884(d[q], a, b);
+                if (VARIANT == 4) f[q] = fma(f[q], m, c);
+            }
+        }
+        double r = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r += d[i][0] + d[i][1] + f[i];
+        out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+        return;
+    }
     if (VARIANT == 0) {
         double a0 = t0, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
         const double m = 0.999999999, c = 1e-12;
@@ -2417,6 +2495,8 @@ static int build_tables(gwin_plan* p) {
     }
     p->tblk = blks;
     p->n_tblk = n; p->n_pairs = n_pairs; p->tab_bytes = (size_t)bytes;
+    p->tab_split = n;
+    while (p->tab_split > 0 && blks[p->tab_split - 1].K <= 2) --p->tab_split;
     p->k_split = blks[0].start; p->n_blk_low = ib;
     p->k_tab_end = blks[n - 1].start + blks[n - 1].m;
     // a sub-block costs about as much as 70 bins of the recurrence kernel, and the table path adds
@@ -2619,6 +2699,7 @@ extern "C" void gwin_plan_destroy(gwin_plan* p) {
     free_tables(p); cudaFree(p->d_partialT); cudaFree(p->d_partialS);
     cudaFree(p->d_ke_fast); cudaFree(p->d_ke_low); cudaFree(p->d_ks_tail);
     cudaFree(p->d_key2_in); cudaFree(p->d_key2_out); cudaFree(p->d_idx2_in); cudaFree(p->d_perm_e); cudaFree(p->d_grp_b);
+    cudaFree(p->d_key3_in); cudaFree(p->d_perm_t); cudaFree(p->d_col_t);
     cudaFree(p->d_slow); cudaFree(p->d_slow_list); cudaFree(p->d_slow_n); cudaFree(p->d_stats);
     if (p->ev_done_set) cudaEventDestroy(p->ev_done);
     cudaFree(p->d_params); cudaFree(p->d_out); cudaFree(p->d_skip); cudaFree(p->d_points);
@@ -2865,7 +2946,7 @@ static int ensure_workspace(gwin_plan* p, int64_t W, int n_chunks) {
         CK(cudaDeviceSynchronize());
         int** ints[] = { &p->d_ks, &p->d_ke, &p->d_key_in, &p->d_key_out, &p->d_perm_in, &p->d_perm_out,
                          &p->d_ke_fast, &p->d_ke_low, &p->d_ks_tail, &p->d_key2_in, &p->d_key2_out,
-                         &p->d_idx2_in, &p->d_perm_e, &p->d_slow_list };
+                         &p->d_idx2_in, &p->d_perm_e, &p->d_slow_list, &p->d_key3_in, &p->d_perm_t, &p->d_col_t };
         for (int** q : ints) { cudaFree(*q); *q = nullptr; }
         cudaFree(p->d_wc); cudaFree(p->d_cub); cudaFree(p->d_marg_opt); cudaFree(p->d_slow); cudaFree(p->d_grp_b);
         p->d_wc = nullptr; p->d_cub = nullptr; p->d_marg_opt = nullptr; p->d_slow = nullptr; p->d_grp_b = nullptr;
@@ -2957,19 +3038,29 @@ static void launch_main_nd(gwin_plan* p, const MainLaunch& a, cudaStream_t st) {
 }
 
 template <int ND>
-static void launch_table(gwin_plan* p, int W, int wpad, int n_chunks, int per_chunk, cudaStream_t st) {
-    dim3 grid((W + CTA_THREADS - 1) / CTA_THREADS, n_chunks);
-    const int smem = per_chunk * NPH * TAB_NTP * (int)sizeof(double) + (CTA_THREADS / WARP) * ND * TAB_SPAN * TAB_ROWB;
+static void launch_table(gwin_plan* p, int W, int wpad, int per_chunk, int blk_lo, int blk_hi, const int* col, cudaStream_t st) {
+    if (blk_hi <= blk_lo) return;
+    dim3 grid((W + CTA_THREADS - 1) / CTA_THREADS, (blk_hi - blk_lo + per_chunk - 1) / per_chunk);
+    const int fixed = ((TAB_COEF_SMEM ? TAB_CROWS(ND) : 0) + TAB_WPITCH) * CTA_THREADS * (int)sizeof(double) + (CTA_THREADS / WARP) * ND * TAB_SPAN * TAB_ROWB;
+    const int smem = per_chunk * NPH * TAB_NTP * (int)sizeof(double) + fixed;
     static bool attr_set_dev[64] = {};
     if (!attr_set_dev[p->device & 63]) {
         cudaFuncSetAttribute(loglr_table_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             TAB_CHUNK_MAX * NPH * TAB_NTP * (int)sizeof(double) + (CTA_THREADS / WARP) * ND * TAB_SPAN * TAB_ROWB);
+                             TAB_CHUNK_MAX * NPH * TAB_NTP * (int)sizeof(double) + fixed);
         cudaFuncSetAttribute(loglr_table_kernel<ND>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         attr_set_dev[p->device & 63] = true;
     }
-    loglr_table_kernel<ND><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, per_chunk, p->n_tblk, p->d_tblk, p->d_cmat,
+    loglr_table_kernel<ND><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, per_chunk, blk_lo, blk_hi, p->d_tblk, p->d_cmat,
                                                         p->d_tref, p->d_tab, p->d_wc, p->d_ke_fast,
-                                                        p->d_partialT, p->d_slow);
+                                                        p->d_partialT, p->d_slow, col);
+}
+static void launch_table_nd(gwin_plan* p, int W, int wpad, int per_chunk, int blk_lo, int blk_hi, const int* col, cudaStream_t st) {
+    switch (p->d.n_det) {
+        case 1: launch_table<1>(p, W, wpad, per_chunk, blk_lo, blk_hi, col, st); break;
+        case 2: launch_table<2>(p, W, wpad, per_chunk, blk_lo, blk_hi, col, st); break;
+        case 3: launch_table<3>(p, W, wpad, per_chunk, blk_lo, blk_hi, col, st); break;
+        default: launch_table<4>(p, W, wpad, per_chunk, blk_lo, blk_hi, col, st); break;
+    }
 }
 
 extern "C" int gwin_loglr_batch(gwin_plan* p, int mode, int64_t W64,
@@ -3135,15 +3226,23 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
 
     const int tb = 128, gb = (W + tb - 1) / tb;
     const int* perm = nullptr;
+    bool time_order = false;
     if (W > WARP || table) {
         const double a_lo = p->cover.a_lo;
         const double a_scale = table ? (double)(1 << TAB_KEY_BITS) / (p->cover.a_hi - p->cover.a_lo) : 0.0;
+        // the long sub-blocks with one or two reference chirps are taken with the walkers in time order
+        // (off by default: with the window walk of the table kernel the lanes' row spread no longer costs
+        //  shared-memory wavefronts, and in time order the lanes of a warp end at different sub-blocks)
+        static const bool time_order_on = getenv("GWIN_TIME_ORDER") && atoi(getenv("GWIN_TIME_ORDER")) != 0;
+        time_order = table && time_order_on && p->tab_split < p->n_tblk;
+        const double f_split = time_order ? p->tblk[p->tab_split].start * d.delta_f : 1.0;
         sort_key_kernel<<<gb, tb, 0, st>>>(d, W, params, stride_walker, stride_param, skip, p->d_key_in, p->d_perm_in,
-                                           table, a_lo, a_scale, table ? p->d_key2_in : nullptr);
+                                           table, a_lo, a_scale, table ? p->d_key2_in : nullptr,
+                                           time_order ? p->d_key3_in : nullptr, 5.0 / 3.0 * std::pow(f_split, -8.0 / 3.0));
         const int bits = table ? TAB_KEY_BITS : 23;
         static const bool block_sort = !(getenv("GWIN_BLOCK_SORT") && atoi(getenv("GWIN_BLOCK_SORT")) == 0);
         if (W <= 16384 && block_sort) {
-            // one launch: CTA 0 sorts the processing order, CTA 1 (table path) the tails' order
+            // one launch: CTA 0 sorts the processing order, CTAs 1, 2 (table path) the tails' and the time order
             const int items = W <= 4096 ? 4 : 16;
             const size_t smem = items == 4 ? sizeof(cub::BlockRadixSort<int, 1024, 4, int>::TempStorage)
                                            : sizeof(cub::BlockRadixSort<int, 1024, 16, int>::TempStorage);
@@ -3155,10 +3254,13 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
                                      (int)sizeof(cub::BlockRadixSort<int, 1024, 16, int>::TempStorage));
                 attr_set_dev[p->device & 63] = true;
             }
-            if (items == 4)
-                block_sort_kernel<4><<<table ? 2 : 1, 1024, smem, st>>>(W, p->d_key_in, bits, p->d_perm_out, p->d_key2_in, 23, p->d_perm_e);
-            else
-                block_sort_kernel<16><<<table ? 2 : 1, 1024, smem, st>>>(W, p->d_key_in, bits, p->d_perm_out, p->d_key2_in, 23, p->d_perm_e);
+            SortJobs J;
+            J.j[0] = SortJob{p->d_key_in, bits, p->d_perm_out};
+            J.j[1] = SortJob{p->d_key2_in, 23, p->d_perm_e};
+            J.j[2] = SortJob{p->d_key3_in, 22, p->d_perm_t};
+            const int njobs = table ? (time_order ? 3 : 2) : 1;
+            if (items == 4) block_sort_kernel<4><<<njobs, 1024, smem, st>>>(W, J);
+            else block_sort_kernel<16><<<njobs, 1024, smem, st>>>(W, J);
         } else {
             size_t bytes = p->cub_bytes;
             CK(cub::DeviceRadixSort::SortPairs(p->d_cub, bytes, p->d_key_in, p->d_key_out,
@@ -3167,6 +3269,11 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
                 bytes = p->cub_bytes;
                 CK(cub::DeviceRadixSort::SortPairs(p->d_cub, bytes, p->d_key2_in, p->d_key2_out,
                                                    p->d_perm_in, p->d_perm_e, W, 0, 23, st));
+            }
+            if (time_order) {
+                bytes = p->cub_bytes;
+                CK(cub::DeviceRadixSort::SortPairs(p->d_cub, bytes, p->d_key3_in, p->d_key2_out,
+                                                   p->d_perm_in, p->d_perm_t, W, 0, 22, st));
             }
         }
         perm = p->d_perm_out;
@@ -3189,7 +3296,8 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
     if (table) {
         // the tails are taken in the order of the walkers' last bins
         tail_plan_kernel<<<groups, CTA_THREADS, 0, st>>>(W, p->n_blk, p->d_blk_start, p->d_perm_e, p->d_idx2_in, p->d_key2_out,
-                                                        p->d_ks_tail, p->d_ke_fast, p->d_grp_b);
+                                                        p->d_ks_tail, p->d_ke_fast, p->d_grp_b,
+                                                        time_order ? p->d_perm_t : nullptr, p->d_col_t);
         p->last_launches += 1;
     }
     if (p->timing) {
@@ -3211,12 +3319,11 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
         p->last_launches += 1;
     }
     if (table) {
-        switch (nd) {
-            case 1: launch_table<1>(p, W, wpad, n_chunksT, per_chunkT, st); break;
-            case 2: launch_table<2>(p, W, wpad, n_chunksT, per_chunkT, st); break;
-            case 3: launch_table<3>(p, W, wpad, n_chunksT, per_chunkT, st); break;
-            default: launch_table<4>(p, W, wpad, n_chunksT, per_chunkT, st); break;
-        }
+        // sub-blocks with several reference chirps: walkers in a0 order; the long ones above: in time order
+        int split = time_order ? std::min(p->n_tblk, (p->tab_split + per_chunkT - 1) / per_chunkT * per_chunkT) : p->n_tblk;
+        launch_table_nd(p, W, wpad, per_chunkT, 0, split, nullptr, st);
+        launch_table_nd(p, W, wpad, per_chunkT, split, p->n_tblk, p->d_col_t, st);
+        p->last_launches += split > 0 && split < p->n_tblk ? 1 : 0;
         MainLaunch T = M;
         T.recur = true; T.calibrated = false;
         T.n_chunks = n_chunks3; T.per_chunk = tail_blocks; T.n_blk = p->n_blk; T.blk_off = 0;
@@ -3554,7 +3661,7 @@ static int run_probe(int device, double* rate) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 1 << 15;
-    const double per_iter = V == 2 ? 16.0 : 8.0;      // FP64 instructions per thread per iteration
+    const double per_iter = V == 2 ? 16.0 : 8.0;      // FP64 instructions (3, 4: MMAs) per thread per iteration
     double* out = nullptr;
     CK(cudaMalloc(&out, sizeof(double) * threads * blocks));
     cudaEvent_t e0, e1;
@@ -3586,6 +3693,8 @@ extern "C" int gwin_fp64_probe(int device, int variant, double* ops_per_sec) {
         case 0: return run_probe<0>(device, ops_per_sec);
         case 1: return run_probe<1>(device, ops_per_sec);
         case 2: return run_probe<2>(device, ops_per_sec);
-        default: return fail(GWIN_EINVAL, "variant must be 0..2");
+        case 3: return run_probe<3>(device, ops_per_sec);
+        case 4: return run_probe<4>(device, ops_per_sec);
+        default: return fail(GWIN_EINVAL, "variant must be 0..4");
     }
 }

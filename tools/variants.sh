@@ -3,11 +3,8 @@
 cd "$(dirname "$0")/.."
 T=${T:-200}
 run() { echo "=== $*"; timeout "$T" env "$@" 2>&1 | grep -E "cold-L2|evals/s|max \||first call|Error|error"; }
-run GWIN_B200_LIB=$PWD/gwin_b200/libgwin_b200.so python tools/quick_time.py 16384 256 table
+run GWIN_B200_LIB=$PWD/gwin_b200/libgwin_b200.so python tools/quick_time.py 16384 256 table,direct
 for v in "$@"; do
   run GWIN_B200_LIB=$PWD/gwin_b200/libgwin_$v.so python tools/quick_time.py 16384 256 table
 done
-run GWIN_TAIL_BLOCKS=1 GWIN_TAIL_SLOTS=16 python tools/quick_time.py 16384 256 table
-run GWIN_TAIL_BLOCKS=4 GWIN_TAIL_SLOTS=8 python tools/quick_time.py 16384 256 table
-run GWIN_TABLE_GB=6 python tools/quick_time.py 16384 256 table
-run GWIN_BLOCK_SORT=0 python tools/quick_time.py 16384 256 table
+run GWIN_TIME_ORDER=1 python tools/quick_time.py 16384 256 table
