@@ -146,7 +146,7 @@ struct BlockMat {
 #define TAB_RHO_DESIGN 0.05
 #define TAB_RHO_MAX 0.10
 #define TAB_KEY_BITS 20      // walkers are ordered by their Newtonian chirp coefficient, quantised over the covered range
-#include "tab_poly.inc"      // TAB_TAP_i(v): the interpolation kernel's per-tap polynomials, literal coefficients
+#include "tab_poly.inc"      // TAB_WEIGHTS(v, w): the interpolation kernel's per-tap polynomials, literal coefficients
 
 // One sub-block of the table schedule.  Its K reference chirps sit at a_lo + (r + 1/2) da in the
 // Newtonian coefficient a0 (turns Hz^(5/3)); tables of reference r and detector d start at
@@ -1706,13 +1706,10 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
 #pragma unroll
                     for (int n = 0; n < TAB_NM; ++n) Mn[n] = make_double2(0.0, 0.0);
                     const double v = xs[d];
-                    // kernel weights: 13 independent Horner chains in v = 2 (x - g0) - (W - 1), coefficients as
-                    // literal constants (constant-bank operands, no loads)
+                    // kernel weights: per pair of mirror taps an even and an odd Horner chain in v^2,
+                    // v = 2 (x - g0) - (W - 1); coefficients as literal constants (no loads)
                     double wt[TAB_W];
-                    wt[0] = TAB_TAP_0(v); wt[1] = TAB_TAP_1(v); wt[2] = TAB_TAP_2(v); wt[3] = TAB_TAP_3(v);
-                    wt[4] = TAB_TAP_4(v); wt[5] = TAB_TAP_5(v); wt[6] = TAB_TAP_6(v); wt[7] = TAB_TAP_7(v);
-                    wt[8] = TAB_TAP_8(v); wt[9] = TAB_TAP_9(v); wt[10] = TAB_TAP_10(v); wt[11] = TAB_TAP_11(v);
-                    wt[12] = TAB_TAP_12(v);
+                    TAB_WEIGHTS(v, wt);
                     if (staged[d]) {
                         // The staged rows are a window of span = 13 + (spread of the lanes' first rows) rows.
                         // Each lane lays its 13 weights into a zeroed row of that length at its own offset;
@@ -1723,7 +1720,7 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
                         double* sw = s_wt + lane;        // [window row][lane]: conflict-free whatever the lanes' offsets
                         __syncwarp();                    // the previous detector's weights have been read
 #pragma unroll
-                        for (int j = 0; j < TAB_SPAN; ++j) sw[j * WARP] = 0.0;
+                        for (int j = 0; j < TAB_SPAN; ++j) if (j < span) sw[j * WARP] = 0.0;
                         if (mine) {
                             double* so = sw + (gs[d] - lo[d]) * WARP;
 #pragma unroll
