@@ -28,6 +28,7 @@
 // 4.6) replaces the per-bin work above ~100 Hz by interpolation in per-plan moment tables.
 #include <cuda_runtime.h>
 #include <cub/block/block_radix_sort.cuh>
+#include <cub/block/block_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
@@ -135,7 +136,7 @@ struct BlockMat {
 #define TAB_MIN 128          // shortest / longest sub-block [bins]; lengths are 2^k and 3 2^(k-1)
 #endif
 #ifndef TAB_MAX
-#define TAB_MAX 4096
+#define TAB_MAX 8192
 #endif
 #define TAB_NM TAB_DEG       // moments stored per grid point: n = 0, 2, 3, .. TAB_DEG (e_1 = 0: nu carries the slope)
 // truncation of e^{-2 pi i R}: the schedule is built so that the majorant of the dropped terms stays
@@ -157,7 +158,11 @@ struct TabBlk {
     double a_lo, da, inv_da;
     double eps;              // (m/2) / centre bin
     long long off;
-    long long pad;
+    // tails: a sub-block in which walkers may end carries a tree of fine sub-blocks (its halves, their
+    // halves, ... down to fine_min bins), entries [fine_first, fine_first + fine_n) of the block array;
+    // a fine sub-block knows its parent's start
+    int fine_first, fine_n;
+    int fine_min, parent_start;
 };
 
 // What the tables are built for (gwin_plan_cover_*): the range of the Newtonian coefficient and, for
@@ -167,6 +172,7 @@ struct Cover {
     bool valid;
     double a_lo, a_hi;
     double dev[16];
+    double ke_lo, ke_hi;     // range of the walkers' last bins: where the fine sub-blocks of the tails are built
 };
 
 struct gwin_plan {
@@ -206,7 +212,7 @@ struct gwin_plan {
     Cover want;              // what the next build should cover (gwin_plan_cover_*, automatic re-planning)
     bool cover_manual;       // coverage was declared by the caller: no automatic re-planning
     std::vector<TabBlk> tblk;
-    int n_tblk, n_pairs, k_split, n_blk_low, k_tab_end;
+    int n_tblk, n_fine, n_pairs, k_split, n_blk_low, k_tab_end;      // n_tblk sub-blocks of the schedule, then n_fine fine ones
     size_t tab_bytes;
     bool tab_dirty;
     bool tab_worth;          // AUTO uses the tables only where they pay (long sub-blocks, enough of them)
@@ -216,7 +222,8 @@ struct gwin_plan {
     double2* d_partialT; size_t partialT_cap;
     // walker order bookkeeping of the table path
     int *d_ke_fast, *d_ke_low, *d_ks_tail, *d_key2_in, *d_key2_out, *d_idx2_in, *d_perm_e, *d_grp_b;
-    int *d_key3_in, *d_perm_t, *d_col_t;
+    int *d_key3_in, *d_perm_t, *d_col_t, *d_ks_fine, *d_ks_rec, *d_tail_parent, *d_grp_p;
+    double2* d_partialF; size_t partialF_cap;
     int tab_split;           // sub-blocks from here on have at most two reference chirps: taken in time order
     // slow path: walkers the fast kernels cannot take (outside the schedule / the tables' coverage)
     unsigned char* d_slow;
@@ -522,7 +529,8 @@ __global__ void sort_key_kernel(PlanDev P, int W, const double* __restrict__ par
                                 int64_t sw, int64_t si,
                                 const uint8_t* __restrict__ skip, int* __restrict__ key,
                                 int* __restrict__ idx, bool key_a0, double a_lo, double a_scale,
-                                int* __restrict__ key_e, int* __restrict__ key_t, double tfac) {
+                                int* __restrict__ key_e, int* __restrict__ key_t, double tfac,
+                                double e_lo, double e_scale) {
     int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= W) return;
     double p[GWIN_NPARAM];
@@ -530,7 +538,9 @@ __global__ void sort_key_kernel(PlanDev P, int W, const double* __restrict__ par
     const bool ok = !(skip && skip[w]) && params_ok(p) && has_waveform(p, P.f_lower_wf);
     int k = key_a0 ? (1 << TAB_KEY_BITS) - 1 : 0, ke = 0, kt = (1 << 22) - 1;
     if (ok) {
+        // last bin, quantised to 12 bits over the range it can take (bucket order, see bucket_order_kernel)
         ke = min(waveform_len(p[0] + p[1], P.delta_f), P.kmax);
+        ke = 1 + (int)fmin(fmax(((double)ke - e_lo) * e_scale, 0.0), 4094.0);
         if (key_a0) {
             const double a0 = newtonian_coef(p[0], p[1]);
             const double q = (a0 - a_lo) * a_scale;
@@ -578,6 +588,45 @@ block_sort_kernel(int W, SortJobs jobs) {
     }
 }
 
+// Cheaper than a sort, and all the kernels need: walkers ordered by the top 12 bits of their key (4096
+// buckets; within a bucket in whatever order the atomics fall -- no result depends on a walker's
+// neighbours).  One CTA per order: shared-memory histogram, scan, scatter.
+#define ORDER_BUCKETS 4096
+template <int ITEMS>
+__global__ void __launch_bounds__(1024)
+bucket_order_kernel(int W, SortJobs jobs) {
+    using Scan = cub::BlockScan<int, 1024>;
+    __shared__ int s_hist[ORDER_BUCKETS];
+    __shared__ typename Scan::TempStorage s_scan;
+    const int* key = jobs.j[blockIdx.x].key;
+    int* out = jobs.j[blockIdx.x].out;
+    const int shift = max(jobs.j[blockIdx.x].bits - 12, 0);
+    for (int i = threadIdx.x; i < ORDER_BUCKETS; i += 1024) s_hist[i] = 0;
+    __syncthreads();
+    int bkt[ITEMS], pos[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const int w = threadIdx.x + i * 1024;
+        if (w < W) {
+            bkt[i] = min(key[w] >> shift, ORDER_BUCKETS - 1);
+            pos[i] = atomicAdd(&s_hist[bkt[i]], 1);
+        }
+    }
+    __syncthreads();
+    int cnt[ORDER_BUCKETS / 1024], off[ORDER_BUCKETS / 1024];
+#pragma unroll
+    for (int i = 0; i < ORDER_BUCKETS / 1024; ++i) cnt[i] = s_hist[threadIdx.x * (ORDER_BUCKETS / 1024) + i];
+    Scan(s_scan).ExclusiveSum(cnt, off);
+#pragma unroll
+    for (int i = 0; i < ORDER_BUCKETS / 1024; ++i) s_hist[threadIdx.x * (ORDER_BUCKETS / 1024) + i] = off[i];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const int w = threadIdx.x + i * 1024;
+        if (w < W) out[s_hist[bkt[i]] + pos[i]] = w;
+    }
+}
+
 // What walker_setup needs to split a walker's band between the kernels.
 struct FastArgs {
     double a_sched_max;      // largest Newtonian coefficient (smallest chirp mass) the recurrence schedule covers
@@ -586,6 +635,8 @@ struct FastArgs {
     int k_split, k_tab_end, n_tblk;
     const TabBlk* blks;
     int *ke_fast, *ke_low, *ks_tail, *inv;      // inv[w]: position of walker w in the processing order
+    int *ks_rec;                                // tails: start of what is left to the recurrence kernel
+    int *ks_fine, *tail_parent;                 // tails: end of the stretch taken by fine sub-blocks; the sub-block the walker ends in (-1: no fine sub-blocks)
     unsigned char* slow;
 };
 
@@ -615,7 +666,7 @@ __global__ void walker_setup_kernel(PlanDev P, int W, int wpad,
         // no bins; combine() turns this into -inf via ks = -1
         ks_arr[t] = -1; ke_arr[t] = -1;
         if (F.ke_fast) { F.ke_fast[t] = -1; F.slow[t] = 0; }
-        if (F.table) { F.ke_low[t] = -1; F.ks_tail[t] = -1; F.inv[w] = t; }
+        if (F.table) { F.ke_low[t] = -1; F.ks_tail[t] = -1; F.ks_fine[t] = -1; F.ks_rec[t] = -1; F.tail_parent[t] = -1; F.inv[w] = t; }
         for (int r = 0; r < NCOEF(nd); ++r) wc[r * wpad + t] = 0.0;
         for (int d = 0; d < nd; ++d) hh_sorted[d * wpad + t] = 0.0;
         return;
@@ -655,17 +706,27 @@ __global__ void walker_setup_kernel(PlanDev P, int W, int wpad,
             F.ke_low[t] = min(kef, F.k_split);      // the recurrence kernel's share of the band
             // table sub-blocks are taken whole; what lies between the last whole one and the walker's
             // last bin is left to a second pass of the recurrence kernel over [ks_tail, ke)
-            int tail = kef;
+            // Where the sub-block the walker ends in carries fine sub-blocks, they take the stretch up to
+            // the last multiple of the finest length; the recurrence pass keeps [ks_fine, ke).
+            int tail = kef, fine = kef, parent = -1;
             if (kef > F.k_split) {
                 if (kef >= F.k_tab_end) {
-                    tail = F.k_tab_end;
+                    tail = fine = F.k_tab_end;
                 } else {
                     int lo = 0, hi = F.n_tblk - 1;          // the sub-block holding bin kef
                     while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (F.blks[mid].start <= kef) lo = mid; else hi = mid - 1; }
-                    tail = F.blks[lo].start;
+                    tail = fine = F.blks[lo].start;
+                    const int fmin = F.blks[lo].fine_min;
+                    if (F.blks[lo].fine_n > 0) {
+                        fine = tail + (kef - tail) / fmin * fmin;
+                        parent = lo;
+                    }
                 }
             }
             F.ks_tail[t] = tail;
+            F.ks_fine[t] = fine;
+            F.ks_rec[t] = parent >= 0 ? kef : tail;    // with fine sub-blocks the bins after them are done there too
+            F.tail_parent[t] = parent;
             F.inv[w] = t;
         }
     }
@@ -1478,7 +1539,7 @@ tab_dft_kernel(const int* __restrict__ pair_blk, const TabBlk* __restrict__ blks
 // What a batch needs the tables to cover: range of the Newtonian coefficient a0 and, per other phase
 // coefficient, the largest deviation from the reference chirp of the same a0.
 // out[0] = min a0, [1] = max a0, [2 + i] = max |a_i - a_i^ref| (bit patterns of non-negative doubles
-// order like the numbers), [2 + NPH] = number of walkers with a waveform.
+// order like the numbers), [2 + NPH] = number of walkers with a waveform, [14] / [15] = min / max last bin.
 __global__ void cover_stats_kernel(PlanDev P, int W, const double* __restrict__ params, int64_t sw, int64_t si,
                                    const uint8_t* __restrict__ skip, unsigned long long* __restrict__ out) {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1487,11 +1548,13 @@ __global__ void cover_stats_kernel(PlanDev P, int W, const double* __restrict__ 
 #pragma unroll
     for (int i = 0; i < NPH; ++i) v[2 + i] = 0.0;
     bool ok = false;
+    double ke_lo = INFINITY, ke_hi = 0.0;
     if (w < W) {
         double p[GWIN_NPARAM];
         load_params(p, params, w, sw, si);
         ok = !(skip && skip[w]) && params_ok(p) && has_waveform(p, P.f_lower_wf);
         if (ok) {
+            ke_lo = ke_hi = (double)min(waveform_len(p[0] + p[1], P.delta_f), P.kmax);
             double a[NPH], ar[NPH];
             pn_phase_coefs(p[0], p[1], p[2], p[3], 0.0, p[11], p[12], a);
             ref_phase_coefs(a[0], ar);
@@ -1504,6 +1567,8 @@ __global__ void cover_stats_kernel(PlanDev P, int W, const double* __restrict__ 
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
         v[0] = fmin(v[0], __shfl_xor_sync(0xffffffffu, v[0], o));
+        ke_lo = fmin(ke_lo, __shfl_xor_sync(0xffffffffu, ke_lo, o));
+        ke_hi = fmax(ke_hi, __shfl_xor_sync(0xffffffffu, ke_hi, o));
 #pragma unroll
         for (int i = 1; i < 2 + NPH; ++i) v[i] = fmax(v[i], __shfl_xor_sync(0xffffffffu, v[i], o));
     }
@@ -1512,6 +1577,8 @@ __global__ void cover_stats_kernel(PlanDev P, int W, const double* __restrict__ 
         atomicMin(out, (unsigned long long)__double_as_longlong(v[0]));
         for (int i = 1; i < 2 + NPH; ++i) atomicMax(out + i, (unsigned long long)__double_as_longlong(v[i]));
         atomicAdd(out + 2 + NPH, (unsigned long long)cnt);
+        atomicMin(out + 14, (unsigned long long)__double_as_longlong(ke_lo));
+        atomicMax(out + 15, (unsigned long long)__double_as_longlong(ke_hi));
     }
 }
 
@@ -1531,21 +1598,31 @@ __global__ void cover_stats_kernel(PlanDev P, int W, const double* __restrict__ 
 // long sub-blocks above them with the walkers ordered by their local time (lanes share table rows:
 // one shared-memory wavefront per load instead of one per distinct row).  The launch covers sub-blocks
 // [blk_lo, blk_hi); CTA y takes blocks_per_chunk of them and writes partial-sum slot blk_lo / blocks_per_chunk + y.
-template <int ND>
+// FINE: the tails.  Thread t is the t-th walker in the order of the last bins; between the last whole
+// sub-block and its last bin a walker takes the fine sub-blocks (halves, quarters, ... of the sub-block
+// parent_arr[col] it ends in) of the binary decomposition of that stretch -- at most one per level, found
+// in closed form -- and evaluates the few bins left after the finest one directly.  CTA y takes levels
+// y, y + gridDim.y, ... and writes partial-sum slot y.
+template <int ND, bool FINE>
 __global__ void __launch_bounds__(CTA_THREADS, TABLE_MIN_CTAS)
 loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo, int blk_hi,
                    const TabBlk* __restrict__ blks, const double* __restrict__ cmat,
                    const double* __restrict__ tref, const double2* __restrict__ tab,
                    const double* __restrict__ wc, const int* __restrict__ ke_arr,
                    double2* __restrict__ partial, unsigned char* __restrict__ slow,
-                   const int* __restrict__ col_arr) {
+                   const int* __restrict__ col_arr,
+                   const int* __restrict__ ks_tail_arr, const int* __restrict__ ks_fine_arr,
+                   const int* __restrict__ parent_arr) {
     const int t = blockIdx.x * CTA_THREADS + threadIdx.x;
-    const int b0 = blk_lo + blockIdx.y * blocks_per_chunk;
-    const int b1 = min(b0 + blocks_per_chunk, blk_hi);
-    const int chunk = b0 / blocks_per_chunk;
+    const int b0 = FINE ? 0 : blk_lo + blockIdx.y * blocks_per_chunk;
+    const int b1 = FINE ? 0 : min(b0 + blocks_per_chunk, blk_hi);
+    const int chunk = FINE ? (int)blockIdx.y : b0 / blocks_per_chunk;
     const bool live = t < W;
     const int col = live ? (col_arr ? col_arr[t] : t) : 0;
     const int ke = live ? ke_arr[col] : 0;
+    // FINE: the stretch [tail_s, tail_s + tail_len) goes to fine sub-blocks
+    const int tail_s = (FINE && live) ? ks_tail_arr[col] : 0;
+    const int tail_len = (FINE && live) ? ks_fine_arr[col] - tail_s : 0;
     // shared memory: [chunk's Taylor matrices][per-thread coefficient columns][per-warp staging buffers:
     // ND x TAB_SPAN table rows of TAB_ROWB bytes (128 B of moments + 16 B of padding against bank conflicts)]
     extern __shared__ __align__(16) unsigned char s_tab[];
@@ -1554,8 +1631,9 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
     double* s_wt = s_coef + (TAB_COEF_SMEM ? TAB_CROWS(ND) : 0) * CTA_THREADS + (size_t)(threadIdx.x / WARP) * WARP * TAB_WPITCH;
     unsigned char* s_warp = reinterpret_cast<unsigned char*>(s_coef + ((TAB_COEF_SMEM ? TAB_CROWS(ND) : 0) + TAB_WPITCH) * CTA_THREADS)
                           + (size_t)(threadIdx.x / WARP) * ND * TAB_SPAN * TAB_ROWB;
-    for (int i = threadIdx.x; i < (b1 - b0) * NPH * TAB_NTP; i += CTA_THREADS)
-        s_c[i] = cmat[(size_t)b0 * NPH * TAB_NTP + i];
+    if (!FINE)
+        for (int i = threadIdx.x; i < (b1 - b0) * NPH * TAB_NTP; i += CTA_THREADS)
+            s_c[i] = cmat[(size_t)b0 * NPH * TAB_NTP + i];
     // per-thread coefficients live in shared memory (one column per thread, no sharing): they are needed
     // once per sub-block, and keeping them out of the register file keeps the tap loop from spilling
 #if TAB_COEF_SMEM
@@ -1574,24 +1652,21 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
         TCOEF(NPH + 2 * d + 1) = row[D_TAULO * wpad];
     }
     __syncthreads();
-    const int k0 = blks[b0].start;
-    const bool has = k0 < ke;
+    const int k0 = (FINE || b0 >= b1) ? 0 : blks[b0].start;
+    const bool has = FINE ? live : (b0 < b1 && k0 < ke);
     int whi = has ? ke : 0;
 #pragma unroll
     for (int o = 16; o; o >>= 1) whi = max(whi, __shfl_xor_sync(0xffffffffu, whi, o));
     double2 acc[ND];
 #pragma unroll
     for (int d = 0; d < ND; ++d) acc[d] = make_double2(0.0, 0.0);
-    if (k0 < whi) {
-        const int lane = threadIdx.x & (WARP - 1);
-        bool dead = false;                              // this walker left the table path
-        for (int b = b0; b < b1; ++b) {
-            const TabBlk B = blks[b];
+    const int lane = threadIdx.x & (WARP - 1);
+    bool dead = false;                                  // this walker left the table path
+    // one sub-block for the lanes with `act` set (a warp-wide operation: every lane calls it)
+    auto do_block = [&](const int b, const TabBlk& B, bool act) {
             const int s = B.start, m = B.m, L = 2 * m;
-            if (s >= whi) break;
-            bool act = !dead && ke >= s + m;            // this lane takes the sub-block whole
             const unsigned amask = __ballot_sync(0xffffffffu, act);
-            if (!amask) continue;
+            if (!amask) return;
             // ---- reference chirp: the nearest one on the sub-block's grid (a function of the walker alone)
 #if TAB_COEF_SMEM
             asm volatile("" ::: "memory");               // re-read the coefficient column per sub-block: do not hoist
@@ -1599,7 +1674,7 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
             int r = (int)((TCOEF(0) - B.a_lo) * B.inv_da);
             r = max(0, min(r, B.K - 1));
             // ---- Taylor coefficients of the phase about the centre: t_n = sum_i a_i c[i][n]
-            const double* sc = s_c + (size_t)(b - b0) * NPH * TAB_NTP;
+            const double* sc = FINE ? cmat + (size_t)b * NPH * TAB_NTP : s_c + (size_t)(b - b0) * NPH * TAB_NTP;
             double tq[TAB_NT];
 #pragma unroll
             for (int n = 0; n < TAB_NT; ++n) tq[n] = 0.0;
@@ -1765,9 +1840,65 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
                     if (mine) acc[d] = cfma(sum, phasor_neg(th0), acc[d]);
                 }
             }
+    };
+    if (!FINE) {
+        if (b0 < b1 && k0 < whi) {
+            for (int b = b0; b < b1; ++b) {
+                const TabBlk B = blks[b];
+                if (B.start >= whi) break;
+                do_block(b, B, !dead && ke >= B.start + B.m);       // a lane takes the sub-block whole
+            }
+        }
+    } else {
+        // binary decomposition of the stretch: at the level of sub-blocks of ml bins the walker takes the
+        // one at offset (q - 1) ml when q = len / ml is odd
+        const int par = live ? parent_arr[col] : -1;
+        int pf = 0, pm = 0, pmin = 0x7fffffff;
+        if (par >= 0) { pf = blks[par].fine_first; pm = blks[par].m; pmin = blks[par].fine_min; }
+        for (int lev = blockIdx.y; lev < 20; lev += gridDim.y) {
+            const int ml = pm >> (lev + 1);
+            const bool deep = par >= 0 && ml >= pmin;
+            if (!__any_sync(0xffffffffu, deep)) break;
+            int myb = -1;
+            if (deep) { const int q = tail_len / ml; if (q & 1) myb = pf + (2 << lev) - 2 + (q - 1); }
+            unsigned todo = __ballot_sync(0xffffffffu, myb >= 0);
+            while (todo) {
+                const int b = __shfl_sync(0xffffffffu, myb, __ffs(todo) - 1);
+                const bool same = myb == b;
+                todo &= ~__ballot_sync(0xffffffffu, same);
+                const TabBlk B = blks[b];
+                do_block(b, B, same && !dead);
+            }
+        }
+        if (blockIdx.y == 0) {
+            // the bins after the finest sub-block (fewer than its length): per-bin phase and sincos, every
+            // lane its own bins
+            const int r0 = tail_s + tail_len;
+            const int nres = par >= 0 ? ke - r0 : 0;
+            int nmax = nres;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+            if (nmax > 0) {
+                PhaseCoef pc;
+                pc.a0 = TCOEF(C_A0); pc.a2 = TCOEF(C_A2); pc.a3 = TCOEF(C_A3); pc.a4 = TCOEF(C_A4); pc.a5 = TCOEF(C_A5);
+                pc.b5 = TCOEF(C_B5); pc.a6 = TCOEF(C_A6); pc.b6 = TCOEF(C_B6); pc.a7 = TCOEF(C_A7);
+                pc.a10 = TCOEF(C_A10); pc.a12 = TCOEF(C_A12);
+                for (int i = 0; i < nmax; ++i) {
+                    if (i < nres && !dead) {
+                        const int k = r0 + i;
+                        const double kd = (double)k;
+                        const double psi = phase_turns(pc, ld_basis(P.basis + k));
+#pragma unroll
+                        for (int d = 0; d < ND; ++d) {
+                            const double2 u = phasor_neg(psi + fma(kd, TCOEF(NPH + 2 * d + 1), frac1(kd * TCOEF(NPH + 2 * d))));
+                            acc[d] = cfma(__ldg(P.T + (size_t)k * ND + d), u, acc[d]);
+                        }
+                    }
+                }
+            }
         }
     }
-    if (live && has) {
+    if (live && has) {          // (FINE: every slot is written)
 #pragma unroll
         for (int d = 0; d < ND; ++d)
             partial[((size_t)chunk * ND + d) * wpad + col] = acc[d];
@@ -1781,27 +1912,40 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
 __global__ void __launch_bounds__(CTA_THREADS)
 tail_plan_kernel(int W, int n_blk, const int* __restrict__ blk_start, const int* __restrict__ perm_e,
                  const int* __restrict__ inv, int* __restrict__ col_e,
-                 const int* __restrict__ ks_tail, const int* __restrict__ ke_fast, int* __restrict__ grp_b,
-                 const int* __restrict__ perm_t, int* __restrict__ col_t) {
-    __shared__ int s_lo[CTA_THREADS / WARP], s_hi[CTA_THREADS / WARP];
+                 const int* __restrict__ ks_fine, const int* __restrict__ ke_fast, int* __restrict__ grp_b,
+                 const int* __restrict__ perm_t, int* __restrict__ col_t,
+                 const int* __restrict__ tail_parent, int* __restrict__ grp_p) {
+    __shared__ int s_lo[CTA_THREADS / WARP], s_hi[CTA_THREADS / WARP], s_pl[CTA_THREADS / WARP], s_ph[CTA_THREADS / WARP];
     const int t = blockIdx.x * CTA_THREADS + threadIdx.x;
-    int lo = 0x7fffffff, hi = 0;
+    int lo = 0x7fffffff, hi = 0, pl = 0x7fffffff, ph = -1;
     if (t < W) {
         const int col = inv[perm_e[t]];
         col_e[t] = col;
         if (perm_t) col_t[t] = inv[perm_t[t]];
-        const int a = ks_tail[col], e = ke_fast[col];
+        const int a = ks_fine[col], e = ke_fast[col];
         if (a >= 0 && a < e) { lo = a; hi = e; }
+        const int par = tail_parent[col];
+        if (par >= 0) { pl = par; ph = par; }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
         lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
         hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        pl = min(pl, __shfl_xor_sync(0xffffffffu, pl, o));
+        ph = max(ph, __shfl_xor_sync(0xffffffffu, ph, o));
     }
-    if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x / WARP] = lo; s_hi[threadIdx.x / WARP] = hi; }
+    if ((threadIdx.x & 31) == 0) {
+        s_lo[threadIdx.x / WARP] = lo; s_hi[threadIdx.x / WARP] = hi;
+        s_pl[threadIdx.x / WARP] = pl; s_ph[threadIdx.x / WARP] = ph;
+    }
     __syncthreads();
     if (threadIdx.x != 0) return;
-    for (int i = 1; i < CTA_THREADS / WARP; ++i) { lo = min(lo, s_lo[i]); hi = max(hi, s_hi[i]); }
+    for (int i = 1; i < CTA_THREADS / WARP; ++i) {
+        lo = min(lo, s_lo[i]); hi = max(hi, s_hi[i]);
+        pl = min(pl, s_pl[i]); ph = max(ph, s_ph[i]);
+    }
+    grp_p[blockIdx.x] = pl;                             // pl > ph: nobody in this group has fine sub-blocks
+    grp_p[gridDim.x + blockIdx.x] = ph;
     int b_lo = 0, b_hi = 0;
     if (lo < hi) {
         int x = 0, y = n_blk - 1;                       // last block starting at or below lo
@@ -1884,7 +2028,8 @@ combine_kernel(int n_det, int W, int wpad, int n_chunks, int mode,
                double* __restrict__ hh_out, double* __restrict__ marg_opt,
                int n_chunks2, int per_chunk2, const TabBlk* __restrict__ tblk,
                const double2* __restrict__ partial2, const int* __restrict__ ke2_arr,
-               int n_chunks3, const double2* __restrict__ partial3) {
+               int n_chunks3, const double2* __restrict__ partial3,
+               int n_chunks4, const double2* __restrict__ partial4) {
     __shared__ double2 s_part[COMB_SEG][GWIN_MAX_DET][32];
     const int lx = threadIdx.x, seg = threadIdx.y;
     const int t = blockIdx.x * 32 + lx;
@@ -1916,6 +2061,11 @@ combine_kernel(int n_det, int W, int wpad, int n_chunks, int mode,
             // pass of the recurrence kernel: every slot is written
             for (int c = seg; c < n_chunks3; c += COMB_SEG) {
                 const double2 p = partial3[((size_t)c * n_det + d) * wpad + t];
+                re += p.x; im += p.y;
+            }
+            // ... and of the fine sub-blocks before it
+            for (int c = seg; c < n_chunks4; c += COMB_SEG) {
+                const double2 p = partial4[((size_t)c * n_det + d) * wpad + t];
                 re += p.x; im += p.y;
             }
         }
@@ -2332,7 +2482,7 @@ static int table_refs_needed(const gwin_plan* p, const Cover& C, int k, int m, i
 static void free_tables(gwin_plan* p) {
     cudaFree(p->d_tblk); cudaFree(p->d_cmat); cudaFree(p->d_tref); cudaFree(p->d_tab);
     p->d_tblk = nullptr; p->d_cmat = p->d_tref = nullptr; p->d_tab = nullptr;
-    p->n_tblk = 0; p->n_pairs = 0; p->tab_bytes = 0;
+    p->n_tblk = 0; p->n_fine = 0; p->n_pairs = 0; p->tab_bytes = 0;
     p->tblk.clear();
 }
 
@@ -2414,12 +2564,51 @@ static int build_tables(gwin_plan* p) {
         bytes = table_schedule(p, p->cover, K0, blks, &ib);
         if (bytes > budget) return GWIN_OK;               // stay on the recurrence kernel
     }
+    const int n_main = (int)blks.size();
+    if (n_main == 0) return GWIN_OK;
+    {
+        // Fine sub-blocks for the tails: every sub-block a covered walker may end in gets its halves,
+        // their halves, ... down to >= TAB_MIN bins, appended parent after parent (so that the fine
+        // sub-blocks of neighbouring parents are contiguous).
+        static const bool fine_on = !(getenv("GWIN_TABLE_FINE") && atoi(getenv("GWIN_TABLE_FINE")) == 0);
+        int pair0 = blks[n_main - 1].pair0 + blks[n_main - 1].K;
+        long long off = blks[n_main - 1].off + (long long)blks[n_main - 1].K * d.n_det * (2 * blks[n_main - 1].m + TAB_W) * TAB_NM;
+        for (int b = 0; fine_on && b < n_main; ++b) {
+            const int ps = blks[b].start, pm = blks[b].m;
+            if (ps + pm <= p->cover.ke_lo || ps > p->cover.ke_hi || pm / 2 < TAB_MIN) continue;
+            if ((double)off * sizeof(double2) > 1.5 * budget) break;
+            blks[b].fine_first = (int)blks.size();
+            int m = pm / 2;
+            for (; m >= TAB_MIN; m /= 2) {
+                for (int k = ps; k + m <= ps + pm; k += m) {
+                    TabBlk B;
+                    memset(&B, 0, sizeof B);
+                    B.start = k; B.m = m;
+                    B.K = std::max(1, table_refs_needed(p, p->cover, k, m, 4096));
+                    B.pair0 = pair0;
+                    B.da = (p->cover.a_hi - p->cover.a_lo) / B.K;
+                    B.a_lo = p->cover.a_lo;
+                    B.inv_da = 1.0 / B.da;
+                    B.eps = 0.5 * m / (double)(k + m / 2);
+                    B.off = off;
+                    B.parent_start = ps;
+                    blks.push_back(B);
+                    pair0 += B.K;
+                    off += (long long)B.K * d.n_det * (2 * m + TAB_W) * TAB_NM;
+                }
+                blks[b].fine_min = m;
+                if (m % 2 || m / 2 < TAB_MIN) break;
+            }
+            blks[b].fine_n = (int)blks.size() - blks[b].fine_first;
+        }
+        bytes = (double)off * sizeof(double2);
+    }
     const int n = (int)blks.size();
-    if (n == 0) return GWIN_OK;
     int n_pairs = 0;
     for (const TabBlk& B : blks) n_pairs += B.K;
-    DBG("tables: a0 in [%.6g, %.6g], %d sub-blocks from bin %d (m %d .. %d), %d references, %.1f MB, K0 %.1f",
-        p->cover.a_lo, p->cover.a_hi, n, blks[0].start, blks[0].m, blks[n - 1].m, n_pairs, bytes / 1048576.0, K0);
+    DBG("tables: a0 in [%.6g, %.6g], last bins in [%.0f, %.0f], %d sub-blocks from bin %d (m %d .. %d) + %d fine ones, "
+        "%d references, %.1f MB, K0 %.1f", p->cover.a_lo, p->cover.a_hi, p->cover.ke_lo, p->cover.ke_hi, n_main, blks[0].start,
+        blks[0].m, blks[n_main - 1].m, n - n_main, n_pairs, bytes / 1048576.0, K0);
     // per-sub-block Taylor matrices, per-pair bookkeeping of the build
     std::vector<double> cmat((size_t)n * NPH * TAB_NTP, 0.0);
     std::vector<int> pair_blk(n_pairs), blk_hat(n);
@@ -2491,15 +2680,15 @@ static int build_tables(gwin_plan* p) {
         return rc > 0 ? GWIN_OK : rc;                     // no memory for the tables: the recurrence kernel keeps the band
     }
     p->tblk = blks;
-    p->n_tblk = n; p->n_pairs = n_pairs; p->tab_bytes = (size_t)bytes;
-    p->tab_split = n;
+    p->n_tblk = n_main; p->n_fine = n - n_main; p->n_pairs = n_pairs; p->tab_bytes = (size_t)bytes;
+    p->tab_split = n_main;
     while (p->tab_split > 0 && blks[p->tab_split - 1].K <= 2) --p->tab_split;
     p->k_split = blks[0].start; p->n_blk_low = ib;
-    p->k_tab_end = blks[n - 1].start + blks[n - 1].m;
+    p->k_tab_end = blks[n_main - 1].start + blks[n_main - 1].m;
     // a sub-block costs about as much as 70 bins of the recurrence kernel, and the table path adds
     // launches: short segments (8 s and below at 4 kHz) are better off without it
     const int64_t tab_bins = (int64_t)p->k_tab_end - p->k_split;
-    p->tab_worth = tab_bins >= 16384 && tab_bins >= (int64_t)350 * n;
+    p->tab_worth = tab_bins >= 16384 && tab_bins >= (int64_t)350 * n_main;
     return GWIN_OK;
 }
 
@@ -2509,12 +2698,15 @@ static void cover_merge(Cover& dst, const Cover& src) {
     if (!dst.valid) { dst = src; return; }
     dst.a_lo = std::min(dst.a_lo, src.a_lo);
     dst.a_hi = std::max(dst.a_hi, src.a_hi);
+    dst.ke_lo = std::min(dst.ke_lo, src.ke_lo);
+    dst.ke_hi = std::max(dst.ke_hi, src.ke_hi);
     for (int i = 0; i < NPH; ++i) dst.dev[i] = std::max(dst.dev[i], src.dev[i]);
 }
 static bool cover_contains(const Cover& big, const Cover& small) {
     if (!small.valid) return true;
     if (!big.valid) return false;
     if (small.a_lo < big.a_lo || small.a_hi > big.a_hi) return false;
+    if (small.ke_lo < big.ke_lo || small.ke_hi > big.ke_hi) return false;
     for (int i = 0; i < NPH; ++i) if (small.dev[i] > big.dev[i]) return false;
     return true;
 }
@@ -2523,6 +2715,8 @@ static void cover_widen(Cover& c) {
     const double pad = 0.05 * (c.a_hi - c.a_lo) + 2e-3 * c.a_hi;
     c.a_lo = std::max(c.a_lo - pad, 0.25 * c.a_lo);
     c.a_hi += pad;
+    c.ke_lo = std::floor(0.97 * c.ke_lo) - 64.0;
+    c.ke_hi = std::ceil(1.03 * c.ke_hi) + 64.0;
     for (int i = 0; i < NPH; ++i) c.dev[i] *= 1.5;
 }
 
@@ -2536,6 +2730,7 @@ static int cover_from_device(gwin_plan* p, int64_t W, const double* params, int6
     memset(init, 0, sizeof init);
     const double inf = INFINITY;
     memcpy(&init[0], &inf, sizeof(double));
+    memcpy(&init[14], &inf, sizeof(double));
     CK(cudaMemcpyAsync(p->d_stats, init, sizeof init, cudaMemcpyHostToDevice, st));
     cover_stats_kernel<<<(int)((W + 127) / 128), 128, 0, st>>>(p->d, (int)W, params, sw, si, skip, p->d_stats);
     unsigned long long res[16];
@@ -2545,6 +2740,8 @@ static int cover_from_device(gwin_plan* p, int64_t W, const double* params, int6
     memcpy(&out->a_lo, &res[0], sizeof(double));
     memcpy(&out->a_hi, &res[1], sizeof(double));
     for (int i = 0; i < NPH; ++i) memcpy(&out->dev[i], &res[2 + i], sizeof(double));
+    memcpy(&out->ke_lo, &res[14], sizeof(double));
+    memcpy(&out->ke_hi, &res[15], sizeof(double));
     out->dev[0] = 0.0;
     out->valid = true;
     return GWIN_OK;
@@ -2697,6 +2894,7 @@ extern "C" void gwin_plan_destroy(gwin_plan* p) {
     cudaFree(p->d_ke_fast); cudaFree(p->d_ke_low); cudaFree(p->d_ks_tail);
     cudaFree(p->d_key2_in); cudaFree(p->d_key2_out); cudaFree(p->d_idx2_in); cudaFree(p->d_perm_e); cudaFree(p->d_grp_b);
     cudaFree(p->d_key3_in); cudaFree(p->d_perm_t); cudaFree(p->d_col_t);
+    cudaFree(p->d_ks_fine); cudaFree(p->d_ks_rec); cudaFree(p->d_tail_parent); cudaFree(p->d_grp_p); cudaFree(p->d_partialF);
     cudaFree(p->d_slow); cudaFree(p->d_slow_list); cudaFree(p->d_slow_n); cudaFree(p->d_stats);
     if (p->ev_done_set) cudaEventDestroy(p->ev_done);
     cudaFree(p->d_params); cudaFree(p->d_out); cudaFree(p->d_skip); cudaFree(p->d_points);
@@ -2943,10 +3141,11 @@ static int ensure_workspace(gwin_plan* p, int64_t W, int n_chunks) {
         CK(cudaDeviceSynchronize());
         int** ints[] = { &p->d_ks, &p->d_ke, &p->d_key_in, &p->d_key_out, &p->d_perm_in, &p->d_perm_out,
                          &p->d_ke_fast, &p->d_ke_low, &p->d_ks_tail, &p->d_key2_in, &p->d_key2_out,
-                         &p->d_idx2_in, &p->d_perm_e, &p->d_slow_list, &p->d_key3_in, &p->d_perm_t, &p->d_col_t };
+                         &p->d_idx2_in, &p->d_perm_e, &p->d_slow_list, &p->d_key3_in, &p->d_perm_t, &p->d_col_t,
+                         &p->d_ks_fine, &p->d_ks_rec, &p->d_tail_parent };
         for (int** q : ints) { cudaFree(*q); *q = nullptr; }
-        cudaFree(p->d_wc); cudaFree(p->d_cub); cudaFree(p->d_marg_opt); cudaFree(p->d_slow); cudaFree(p->d_grp_b);
-        p->d_wc = nullptr; p->d_cub = nullptr; p->d_marg_opt = nullptr; p->d_slow = nullptr; p->d_grp_b = nullptr;
+        cudaFree(p->d_wc); cudaFree(p->d_cub); cudaFree(p->d_marg_opt); cudaFree(p->d_slow); cudaFree(p->d_grp_b); cudaFree(p->d_grp_p);
+        p->d_wc = nullptr; p->d_cub = nullptr; p->d_marg_opt = nullptr; p->d_slow = nullptr; p->d_grp_b = p->d_grp_p = nullptr;
         p->w_cap = 0;
         // coefficient rows + n_det rows of hh
         CK(cudaMalloc(&p->d_wc, sizeof(double) * (NCOEF(nd) + nd) * cap));
@@ -2954,12 +3153,14 @@ static int ensure_workspace(gwin_plan* p, int64_t W, int n_chunks) {
         CK(cudaMalloc(&p->d_marg_opt, sizeof(double) * cap));
         CK(cudaMalloc(&p->d_slow, cap));
         CK(cudaMalloc(&p->d_grp_b, sizeof(int) * 2 * (cap / CTA_THREADS + 1)));
+        CK(cudaMalloc(&p->d_grp_p, sizeof(int) * 2 * (cap / CTA_THREADS + 1)));
         if (!p->d_slow_n) {
             CK(cudaMalloc(&p->d_slow_n, sizeof(int) * 2));
             CK(cudaMemset(p->d_slow_n, 0, sizeof(int) * 2));
         }
         p->partialT_cap = 0;
         p->partialS_cap = 0;
+        p->partialF_cap = 0;
         p->cub_bytes = 0;
         CK(cub::DeviceRadixSort::SortPairs(nullptr, p->cub_bytes, p->d_key_in, p->d_key_out,
                                            p->d_perm_in, p->d_perm_out, (int)cap, 0, 23));
@@ -3034,29 +3235,42 @@ static void launch_main_nd(gwin_plan* p, const MainLaunch& a, cudaStream_t st) {
     }
 }
 
+// fine = false: sub-blocks [blk_lo, blk_hi) of the schedule, per_chunk of them per CTA.
+// fine = true: the tails' fine sub-blocks, walkers in the order of their last bins, `slots` CTAs per group.
 template <int ND>
-static void launch_table(gwin_plan* p, int W, int wpad, int per_chunk, int blk_lo, int blk_hi, const int* col, cudaStream_t st) {
-    if (blk_hi <= blk_lo) return;
-    dim3 grid((W + CTA_THREADS - 1) / CTA_THREADS, (blk_hi - blk_lo + per_chunk - 1) / per_chunk);
-    const int fixed = ((TAB_COEF_SMEM ? TAB_CROWS(ND) : 0) + TAB_WPITCH) * CTA_THREADS * (int)sizeof(double) + (CTA_THREADS / WARP) * ND * TAB_SPAN * TAB_ROWB;
-    const int smem = per_chunk * NPH * TAB_NTP * (int)sizeof(double) + fixed;
+static void launch_table(gwin_plan* p, int W, int wpad, int per_chunk, int blk_lo, int blk_hi, const int* col,
+                         bool fine, int slots, cudaStream_t st) {
+    if (!fine && blk_hi <= blk_lo) return;
+    dim3 grid((W + CTA_THREADS - 1) / CTA_THREADS, fine ? slots : (blk_hi - blk_lo + per_chunk - 1) / per_chunk);
+    const int fixed = ((TAB_COEF_SMEM ? TAB_CROWS(ND) : 0) + TAB_WPITCH) * CTA_THREADS * (int)sizeof(double)
+                    + (CTA_THREADS / WARP) * ND * TAB_SPAN * TAB_ROWB;
+    const int smem = (fine ? 0 : per_chunk) * NPH * TAB_NTP * (int)sizeof(double) + fixed;
     static bool attr_set_dev[64] = {};
     if (!attr_set_dev[p->device & 63]) {
-        cudaFuncSetAttribute(loglr_table_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(loglr_table_kernel<ND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              TAB_CHUNK_MAX * NPH * TAB_NTP * (int)sizeof(double) + fixed);
-        cudaFuncSetAttribute(loglr_table_kernel<ND>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(loglr_table_kernel<ND, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(loglr_table_kernel<ND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fixed);
+        cudaFuncSetAttribute(loglr_table_kernel<ND, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         attr_set_dev[p->device & 63] = true;
     }
-    loglr_table_kernel<ND><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, per_chunk, blk_lo, blk_hi, p->d_tblk, p->d_cmat,
-                                                        p->d_tref, p->d_tab, p->d_wc, p->d_ke_fast,
-                                                        p->d_partialT, p->d_slow, col);
+    if (fine)
+        loglr_table_kernel<ND, true><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, 0, 0, 0, p->d_tblk, p->d_cmat,
+                                                                  p->d_tref, p->d_tab, p->d_wc, p->d_ke_fast,
+                                                                  p->d_partialF, p->d_slow, col,
+                                                                  p->d_ks_tail, p->d_ks_fine, p->d_tail_parent);
+    else
+        loglr_table_kernel<ND, false><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, per_chunk, blk_lo, blk_hi, p->d_tblk, p->d_cmat,
+                                                                   p->d_tref, p->d_tab, p->d_wc, p->d_ke_fast,
+                                                                   p->d_partialT, p->d_slow, col, nullptr, nullptr, nullptr);
 }
-static void launch_table_nd(gwin_plan* p, int W, int wpad, int per_chunk, int blk_lo, int blk_hi, const int* col, cudaStream_t st) {
+static void launch_table_nd(gwin_plan* p, int W, int wpad, int per_chunk, int blk_lo, int blk_hi, const int* col,
+                            bool fine, int slots, cudaStream_t st) {
     switch (p->d.n_det) {
-        case 1: launch_table<1>(p, W, wpad, per_chunk, blk_lo, blk_hi, col, st); break;
-        case 2: launch_table<2>(p, W, wpad, per_chunk, blk_lo, blk_hi, col, st); break;
-        case 3: launch_table<3>(p, W, wpad, per_chunk, blk_lo, blk_hi, col, st); break;
-        default: launch_table<4>(p, W, wpad, per_chunk, blk_lo, blk_hi, col, st); break;
+        case 1: launch_table<1>(p, W, wpad, per_chunk, blk_lo, blk_hi, col, fine, slots, st); break;
+        case 2: launch_table<2>(p, W, wpad, per_chunk, blk_lo, blk_hi, col, fine, slots, st); break;
+        case 3: launch_table<3>(p, W, wpad, per_chunk, blk_lo, blk_hi, col, fine, slots, st); break;
+        default: launch_table<4>(p, W, wpad, per_chunk, blk_lo, blk_hi, col, fine, slots, st); break;
     }
 }
 
@@ -3206,6 +3420,17 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
             p->partialT_cap = need;
         }
     }
+    static const int fine_slots = std::max(1, getenv("GWIN_FINE_SLOTS") ? atoi(getenv("GWIN_FINE_SLOTS")) : 6);
+    const int n_chunksF = (table && p->n_fine > 0) ? fine_slots : 0;
+    if (n_chunksF > 0) {
+        const size_t need = (size_t)n_chunksF * nd * p->w_cap;
+        if (need > p->partialF_cap) {
+            CK(cudaDeviceSynchronize());
+            cudaFree(p->d_partialF); p->d_partialF = nullptr; p->partialF_cap = 0;
+            CK(cudaMalloc(&p->d_partialF, sizeof(double2) * need));
+            p->partialF_cap = need;
+        }
+    }
     // slow path (direct kernel over a list of walkers): its own chunking and partial sums
     const int slow_gx = std::min(groups, 8);
     int per_chunkS = std::max(RESYNC, (nbins + 255) / 256);
@@ -3227,6 +3452,9 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
     if (W > WARP || table) {
         const double a_lo = p->cover.a_lo;
         const double a_scale = table ? (double)(1 << TAB_KEY_BITS) / (p->cover.a_hi - p->cover.a_lo) : 0.0;
+        // the walkers' last bins lie in the covered range (table path) or anywhere in the band
+        const double e_lo = table ? std::max(p->cover.ke_lo, (double)band0) : (double)band0;
+        const double e_hi = table ? std::min(p->cover.ke_hi, (double)d.kmax) : (double)d.kmax;
         // the long sub-blocks with one or two reference chirps are taken with the walkers in time order
         // (off by default: with the window walk of the table kernel the lanes' row spread no longer costs
         //  shared-memory wavefronts, and in time order the lanes of a warp end at different sub-blocks)
@@ -3235,8 +3463,9 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
         const double f_split = time_order ? p->tblk[p->tab_split].start * d.delta_f : 1.0;
         sort_key_kernel<<<gb, tb, 0, st>>>(d, W, params, stride_walker, stride_param, skip, p->d_key_in, p->d_perm_in,
                                            table, a_lo, a_scale, table ? p->d_key2_in : nullptr,
-                                           time_order ? p->d_key3_in : nullptr, 5.0 / 3.0 * std::pow(f_split, -8.0 / 3.0));
-        const int bits = table ? TAB_KEY_BITS : 23;
+                                           time_order ? p->d_key3_in : nullptr, 5.0 / 3.0 * std::pow(f_split, -8.0 / 3.0),
+                                           e_lo, 4095.0 / std::max(e_hi - e_lo, 1.0));
+        const int bits = table ? TAB_KEY_BITS : 12;
         static const bool block_sort = !(getenv("GWIN_BLOCK_SORT") && atoi(getenv("GWIN_BLOCK_SORT")) == 0);
         if (W <= 16384 && block_sort) {
             // one launch: CTA 0 sorts the processing order, CTAs 1, 2 (table path) the tails' and the time order
@@ -3253,10 +3482,14 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
             }
             SortJobs J;
             J.j[0] = SortJob{p->d_key_in, bits, p->d_perm_out};
-            J.j[1] = SortJob{p->d_key2_in, 23, p->d_perm_e};
+            J.j[1] = SortJob{p->d_key2_in, 12, p->d_perm_e};
             J.j[2] = SortJob{p->d_key3_in, 22, p->d_perm_t};
             const int njobs = table ? (time_order ? 3 : 2) : 1;
-            if (items == 4) block_sort_kernel<4><<<njobs, 1024, smem, st>>>(W, J);
+            static const bool exact_sort = getenv("GWIN_EXACT_SORT") && atoi(getenv("GWIN_EXACT_SORT")) != 0;
+            if (!exact_sort) {
+                if (items == 4) bucket_order_kernel<4><<<njobs, 1024, 0, st>>>(W, J);
+                else bucket_order_kernel<16><<<njobs, 1024, 0, st>>>(W, J);
+            } else if (items == 4) block_sort_kernel<4><<<njobs, 1024, smem, st>>>(W, J);
             else block_sort_kernel<16><<<njobs, 1024, smem, st>>>(W, J);
         } else {
             size_t bytes = p->cub_bytes;
@@ -3265,7 +3498,7 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
             if (table) {
                 bytes = p->cub_bytes;
                 CK(cub::DeviceRadixSort::SortPairs(p->d_cub, bytes, p->d_key2_in, p->d_key2_out,
-                                                   p->d_perm_in, p->d_perm_e, W, 0, 23, st));
+                                                   p->d_perm_in, p->d_perm_e, W, 0, 12, st));
             }
             if (time_order) {
                 bytes = p->cub_bytes;
@@ -3285,6 +3518,7 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
     F.k_split = p->k_split; F.k_tab_end = p->k_tab_end; F.n_tblk = p->n_tblk; F.blks = p->d_tblk;
     F.ke_fast = p->d_ke_fast; F.ke_low = p->d_ke_low; F.ks_tail = p->d_ks_tail;
     F.inv = p->d_idx2_in; F.slow = p->d_slow;
+    F.ks_fine = p->d_ks_fine; F.ks_rec = p->d_ks_rec; F.tail_parent = p->d_tail_parent;
     if (recur) CK(cudaMemsetAsync(p->d_slow_n, 0, sizeof(int), st));
     walker_setup_kernel<<<gb, tb, 0, st>>>(d, W, wpad, params, stride_walker, stride_param, skip, perm, p->d_wc, p->d_ks, p->d_ke, hh_rows,
                                            calib, cstride_walker, cstride_value, F);
@@ -3293,8 +3527,9 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
     if (table) {
         // the tails are taken in the order of the walkers' last bins
         tail_plan_kernel<<<groups, CTA_THREADS, 0, st>>>(W, p->n_blk, p->d_blk_start, p->d_perm_e, p->d_idx2_in, p->d_key2_out,
-                                                        p->d_ks_tail, p->d_ke_fast, p->d_grp_b,
-                                                        time_order ? p->d_perm_t : nullptr, p->d_col_t);
+                                                        p->d_ks_rec, p->d_ke_fast, p->d_grp_b,
+                                                        time_order ? p->d_perm_t : nullptr, p->d_col_t,
+                                                        p->d_tail_parent, p->d_grp_p);
         p->last_launches += 1;
     }
     if (p->timing) {
@@ -3318,13 +3553,19 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
     if (table) {
         // sub-blocks with several reference chirps: walkers in a0 order; the long ones above: in time order
         int split = time_order ? std::min(p->n_tblk, (p->tab_split + per_chunkT - 1) / per_chunkT * per_chunkT) : p->n_tblk;
-        launch_table_nd(p, W, wpad, per_chunkT, 0, split, nullptr, st);
-        launch_table_nd(p, W, wpad, per_chunkT, split, p->n_tblk, p->d_col_t, st);
+        launch_table_nd(p, W, wpad, per_chunkT, 0, split, nullptr, false, 0, st);
+        launch_table_nd(p, W, wpad, per_chunkT, split, p->n_tblk, p->d_col_t, false, 0, st);
         p->last_launches += split > 0 && split < p->n_tblk ? 1 : 0;
+        // tails: fine sub-blocks (walkers in the order of their last bins), then the recurrence kernel
+        // over what is left (less than the finest sub-block)
+        if (n_chunksF > 0) {
+            launch_table_nd(p, W, wpad, 0, 0, 0, p->d_key2_out, true, n_chunksF, st);
+            p->last_launches += 1;
+        }
         MainLaunch T = M;
         T.recur = true; T.calibrated = false;
         T.n_chunks = n_chunks3; T.per_chunk = tail_blocks; T.n_blk = p->n_blk; T.blk_off = 0;
-        T.ks_arr = p->d_ks_tail; T.ke_arr = p->d_ke_fast; T.partial = partial3;
+        T.ks_arr = p->d_ks_rec; T.ke_arr = p->d_ke_fast; T.partial = partial3;
         T.col = p->d_key2_out; T.grp_b = p->d_grp_b;
         launch_main_nd(p, T, st);
         p->last_launches += 2;
@@ -3335,7 +3576,7 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
                                                                  perm, p->d_wc, p->d_ks, ke_main,
                                                                  p->d_partial, hh_rows, loglr, hd, hh, p->d_marg_opt,
                                                                  n_chunksT, per_chunkT, p->d_tblk, p->d_partialT, p->d_ke_fast,
-                                                                 n_chunks3, partial3);
+                                                                 n_chunks3, partial3, n_chunksF, p->d_partialF);
     p->last_launches += 2;
     if (recur) {
         // slow path: whoever the fast kernels could not take goes through the direct kernel (no one, normally:
