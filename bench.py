@@ -69,6 +69,41 @@ def bins_used(P, kmin, kmax, delta_f):
     return np.clip(np.minimum(n, kmax) - kmin, 0, None)
 
 
+# FP64 lane-operations the kernels execute per unit of work, counted in the source and
+# checked against ncu's smsp__inst_executed_pipe_fp64 (profiles/r2_fp64_counts.txt):
+#   one (walker, sub-block) of the table kernel: Taylor coefficients 99, relative coefficients 21, the
+#   series e_2..e_10 102, truncation estimate 12; per detector: grid position 10, weights 78, 13 taps x 8
+#   complex moments 208, sum e_n M_n 28, anchor phase + sincos + accumulate 31
+C_SUB_SETUP, C_SUB_DET = 234, 355
+C_RES_BIN = 14 + 33 * len(DETS)          # fine kernel: the bins after the finest sub-block, per-bin phase + sincos
+C_REC_BIN = 6 + 8 * len(DETS) + 2        # recurrence kernel: 4 (cubic) / 8 (quartic) + 8 per detector, + block set-up
+
+
+def executed_work(plan, ke, band0):
+    """FP64 lane-operations of one batch per launch: dict(recurrence, table, table_fine, recurrence_tail),
+    from the moment tables' schedule and the walkers' last bins."""
+    start, m, _, fmin = plan.table_blocks()
+    c_sub = C_SUB_SETUP + len(DETS) * C_SUB_DET
+    out = dict(recurrence=0.0, table=0.0, table_fine=0.0, recurrence_tail=0.0)
+    if len(start) == 0:
+        out["recurrence"] = float(np.clip(ke - band0, 0, None).sum()) * C_REC_BIN
+        return out
+    k_split, end = int(start[0]), start + m
+    out["recurrence"] = float(np.clip(np.minimum(ke, k_split) - band0, 0, None).sum()) * C_REC_BIN
+    whole = np.searchsorted(end, ke, side="right")            # sub-blocks wholly below the last bin
+    out["table"] = float(whole.sum()) * c_sub
+    tail_s = np.where(whole < len(start), start[np.minimum(whole, len(start) - 1)], end[-1])
+    tail_s = np.where(ke > k_split, tail_s, ke)
+    left = np.clip(ke - tail_s, 0, None)
+    fm = np.where(whole < len(start), fmin[np.minimum(whole, len(start) - 1)], 0)
+    has_fine = (fm > 0) & (left > 0)
+    units = np.where(has_fine, left // np.maximum(fm, 1), 0)
+    out["table_fine"] = float(sum(bin(int(u)).count("1") for u in units)) * c_sub \
+        + float(np.where(has_fine, left % np.maximum(fm, 1), 0).sum()) * C_RES_BIN
+    out["recurrence_tail"] = float(np.where(has_fine, 0, left).sum()) * C_REC_BIN
+    return out
+
+
 def synthetic_noise(n_f, delta_f, seed=20181):
     from gwin_b200.psd import aLIGOZeroDetHighPower, colored_noise
     psd = aLIGOZeroDetHighPower(n_f, delta_f, F_LOWER)
@@ -300,6 +335,7 @@ def run_cuda(args):
     clk = clocks.stop() if clocks else None
     total_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
     kern_ms, kern_n = plan.kernel_timing(False)
+    kern_detail = plan.kernel_timing_detail()
     launches = plan.last_launches * args.steps
     n_slow = plan.slow_path_walkers()
     tab_info = plan.table_info()
@@ -330,9 +366,23 @@ def run_cuda(args):
         evals = world * W * args.steps
         value = evals / (total_ms * 1e-3)
         e2e = evals / e2e_s
-        # roofline of the dominant kernel (this rank): algorithmic FP64 work / its own duration
-        slots = float(bins.sum()) * W_ALG_SLOTS                 # per launch
-        achieved = 2.0 * slots / (kern_ms * 1e-3) / 1e12          # TFLOP/s (1 slot = 2 flop)
+        # roofline (this rank): FP64 lane-operations the loglr launches execute / their own duration
+        band0 = plan.kmin
+        ke = np.minimum((1.0 / (6.0 ** 1.5 * np.pi * (P_host[:, 0] + P_host[:, 1]) * MTSUN) / delta_f + 1).astype(np.int64),
+                        plan.kmax)
+        work = executed_work(plan, ke, band0)
+        names = {"recurrence": "loglr_recur_kernel<3,false> (band below the tables)",
+                 "table": "loglr_table_kernel<3,false> (sub-blocks of the schedule)",
+                 "table_fine": "loglr_table_kernel<3,true> (tails: fine sub-blocks + last bins)",
+                 "recurrence_tail": "loglr_recur_kernel<3,false> (tails without fine sub-blocks)"}
+        per_launch = []
+        for k in ("recurrence", "table", "table_fine", "recurrence_tail"):
+            if work[k] > 0 or kern_detail[k] > 2e-3:
+                per_launch.append({"kernel": names[k], "ms": kern_detail[k], "fp64_lane_ops": work[k],
+                                   "frac": work[k] / max(kern_detail[k], 1e-9) / 1e-3 / fp64_peak})
+        lane_ops = sum(work.values())
+        achieved = 2.0 * lane_ops / (kern_ms * 1e-3) / 1e12       # TFLOP/s (1 lane-op = 2 flop)
+        slots = float(bins.sum()) * W_ALG_SLOTS                   # the survey's work model, per launch
         peak = 2.0 * fp64_peak / 1e12
         nominal = 2.0 * 148 * 64 * 1.965e9 / 1e12
         peaks = {}
@@ -357,9 +407,9 @@ def run_cuda(args):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(workload_config(W), l2="flushed between timed steps (256 MiB write)",
-                           kernel="loglr_recur_kernel (block-anchored phasor recurrence, TMA-staged tiles) below k_split and for "
-                                  "each walker's last sub-block; loglr_table_kernel (per-plan moment tables + 13-tap NUFFT "
-                                  "interpolation) above",
+                           kernel="AUTO: loglr_table_kernel (per-plan moment tables with reference chirps + 13-tap NUFFT "
+                                  "interpolation) over the schedule's sub-blocks and the tails' fine sub-blocks; "
+                                  "loglr_recur_kernel (block-anchored phasor recurrence) for whatever band the tables do not take",
                            moment_tables=tab_info, slow_path_walkers=n_slow,
                            mean_bins_per_eval=float(bins.mean())),
             "clocks": clk,
@@ -374,12 +424,17 @@ def run_cuda(args):
                 "peak_source": "live DFMA probe on this GPU (MEASURED_PEAKS.json has no FP64 entry); "
                                "nominal 148 SM x 64 lanes x 1.965 GHz = %.1f TFLOP/s" % nominal,
                 "frac_of_nominal": achieved / nominal,
-                "work_model": "W_alg = 32 + 12*n_det = %d FP64 issue slots per (walker, bin) "
-                              "(SURVEY.md 8d); the recurrence kernel issues 4 + 8*n_det (cubic blocks) or 8 + 8*n_det "
-                              "(quartic) per bin and the table kernel ~3500 per (walker, sub-block of 256..2048 bins), "
-                              "so frac > 1 is expected (DESIGN.md 4.2, 4.6)" % W_ALG_SLOTS,
-                "kernel": "loglr_recur_kernel<3,false> x2 + loglr_table_kernel<3> (timed as one bracket on the "
-                          "launching stream; split in profiles/)",
+                "work_model": "executed FP64 lane-operations, counted in the source and checked against ncu "
+                              "smsp__inst_executed_pipe_fp64 (profiles/r2_fp64_counts.txt): %d per (walker, sub-block) of the "
+                              "table kernel (%d + %d per detector), %d per bin evaluated directly after the finest tail "
+                              "sub-block, %d per bin of the recurrence kernel; units from the tables' schedule and the "
+                              "walkers' last bins" % (C_SUB_SETUP + nd * C_SUB_DET, C_SUB_SETUP, C_SUB_DET, C_RES_BIN, C_REC_BIN),
+                "launches": per_launch,
+                "speedup_vs_work_model": 2.0 * slots / (kern_ms * 1e-3) / 1e12 / peak,
+                "speedup_vs_work_model_note": "SURVEY.md 8d allots W_alg = 32 + 12*n_det = %d FP64 slots to every (walker, "
+                                              "bin); this many times the live DFMA peak would be needed to do that work in "
+                                              "the measured time" % W_ALG_SLOTS,
+                "kernel": "the loglr launches of one step, timed as one bracket on the launching stream and launch by launch",
                 "kernel_ms": kern_ms, "kernel_launches": kern_n,
                 "kernel_share_of_step": kern_ms / (total_ms / args.steps),
                 "hbm": {"algorithmic_bytes_per_launch": alg_bytes,

@@ -43,7 +43,7 @@ SYMBOLS = (
     "gwin_loglr_batch_host_strided", "gwin_generate_host",
     "gwin_loglr_batch_points_host", "gwin_host_alloc", "gwin_host_free",
     "gwin_plan_last_launches",
-    "gwin_plan_kernel_timing",
+    "gwin_plan_kernel_timing", "gwin_plan_kernel_timing_detail", "gwin_plan_table_blocks",
     "gwin_ens_propose", "gwin_ens_prior", "gwin_ens_accept", "gwin_ens_swap",
     "gwin_ens_swap_all", "gwin_ens_record", "gwin_ens_tick",
     "gwin_fp64_peak", "gwin_fp64_probe", "gwin_last_error", "gwin_version",
@@ -187,6 +187,11 @@ def load():
         lib.gwin_plan_kernel_timing.restype = C.c_int
         lib.gwin_plan_kernel_timing.argtypes = [C.c_void_p, C.c_int, dp,
                                                 C.POINTER(C.c_int)]
+        lib.gwin_plan_kernel_timing_detail.restype = C.c_int
+        lib.gwin_plan_kernel_timing_detail.argtypes = [C.c_void_p, dp]
+        lib.gwin_plan_table_blocks.restype = C.c_int
+        lib.gwin_plan_table_blocks.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
         lib.gwin_fp64_peak.restype = C.c_int
         lib.gwin_fp64_peak.argtypes = [C.c_int, dp]
         vp, u64, u32, ci, cd = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_double
@@ -374,6 +379,21 @@ class Plan(object):
         check(self._lib.gwin_plan_kernel_timing(self._h, int(bool(enable)),
                                                 C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def kernel_timing_detail(self):
+        """Mean ms of the launches inside the bracket ``kernel_timing`` last reported:
+        dict(recurrence, table, table_fine, recurrence_tail)."""
+        ms = np.zeros(4)
+        check(self._lib.gwin_plan_kernel_timing_detail(self._h, _dptr(ms)))
+        return dict(zip(("recurrence", "table", "table_fine", "recurrence_tail"), ms.tolist()))
+
+    def table_blocks(self):
+        """The moment tables' schedule: int32 arrays (start, m, references, fine_min)."""
+        n = C.c_int64()
+        check(self._lib.gwin_plan_table_blocks(self._h, 0, None, None, None, None, C.byref(n)))
+        out = [np.zeros(n.value, dtype=np.int32) for _ in range(4)]
+        check(self._lib.gwin_plan_table_blocks(self._h, n.value, *[a.ctypes.data for a in out], C.byref(n)))
+        return tuple(out)
 
     def loglr_host(self, params, mode=MODE_GAUSSIAN, skip=None,
                    param_major=False, calib=None):

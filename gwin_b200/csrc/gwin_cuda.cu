@@ -245,6 +245,8 @@ struct gwin_plan {
     // optional timing of the dominant kernel on the launching stream
     bool timing;
     cudaEvent_t ev0, ev1;
+    cudaEvent_t evd[3];          // between the launches of the bracket: after the main recurrence / direct launch, the table launches, the fine tails
+    double detail_ms_sum[4], detail_last[4];
     double kernel_ms_sum;
     int kernel_ms_n;
     bool ev_pending;
@@ -1583,16 +1585,22 @@ __global__ void cover_stats_kernel(PlanDev P, int W, const double* __restrict__ 
 }
 
 #ifndef TABLE_MIN_CTAS
-#define TABLE_MIN_CTAS 2
+#define TABLE_MIN_CTAS 2     // 255 registers: a third resident CTA (168) spills in the tap loop and loses 60 %
 #endif
-#define TAB_SPAN 24          // table rows a warp stages per detector and sub-block (>= TAB_W + the lanes' spread)
+#ifndef TAB_SPAN
+#define TAB_SPAN 24
+#endif
+// TAB_SPAN: table rows a warp stages per detector and sub-block (>= TAB_W + the lanes' spread)
 #define TAB_ROWB (TAB_NM * 16 + 16)
-#define TAB_CHUNK_MAX 8      // sub-blocks per CTA at most (their Taylor matrices are staged in shared memory)
+#ifndef TAB_CHUNK_MAX
+#define TAB_CHUNK_MAX 8
+#endif
+// TAB_CHUNK_MAX: sub-blocks per CTA at most (their Taylor matrices are staged in shared memory)
 #ifndef TAB_COEF_SMEM
 #define TAB_COEF_SMEM 1      // per-thread coefficients in shared memory (1) or in registers (0)
 #endif
 #define TAB_CROWS(nd) (NPH + 2 * (nd))      // per-thread coefficient column: phase coefficients, tau_hi/lo per detector
-#define TAB_WPITCH TAB_SPAN                 // window weights per lane [doubles], stored [window row][lane]
+#define TAB_WPITCH TAB_W                    // tap weights per lane [doubles], stored [tap][lane]
 // Thread t works on column col_arr[t] of the per-walker arrays (NULL: t itself): the sub-blocks with
 // several reference chirps are taken with the walkers ordered by a0 (lanes share a reference), the
 // long sub-blocks above them with the walkers ordered by their local time (lanes share table rows:
@@ -1787,20 +1795,16 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
                     TAB_WEIGHTS(v, wt);
                     if (staged[d]) {
                         // The staged rows are a window of span = 13 + (spread of the lanes' first rows) rows.
-                        // Each lane lays its 13 weights into a zeroed row of that length at its own offset;
-                        // then the warp walks the window row by row: the table row is read with warp-uniform
+                        // The warp walks the window row by row: the table row is read with warp-uniform
                         // 128-bit loads (one shared-memory wavefront each, whatever the spread) and every
-                        // lane multiplies by its own weight for that row.
+                        // lane multiplies by its own weight for that row -- tap (row - its offset), fetched
+                        // from its column of the weights it parked in shared memory, or 0.
                         const int span = span_d[d];
-                        double* sw = s_wt + lane;        // [window row][lane]: conflict-free whatever the lanes' offsets
+                        double* sw = s_wt + lane;        // [tap][lane]: conflict-free whatever the lanes' offsets
+                        const int off = mine ? gs[d] - lo[d] : -TAB_W;       // this lane's first row in the window
                         __syncwarp();                    // the previous detector's weights have been read
 #pragma unroll
-                        for (int j = 0; j < TAB_SPAN; ++j) if (j < span) sw[j * WARP] = 0.0;
-                        if (mine) {
-                            double* so = sw + (gs[d] - lo[d]) * WARP;
-#pragma unroll
-                            for (int i = 0; i < TAB_W; ++i) so[i * WARP] = wt[i];
-                        }
+                        for (int i = 0; i < TAB_W; ++i) sw[i * WARP] = wt[i];
                         if (!waited) {                   // the weights above overlapped the copies
                             asm volatile("cp.async.wait_group 0;" ::: "memory");
                             waited = true;
@@ -1809,7 +1813,8 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
                         const unsigned char* sr = s_warp + (size_t)d * TAB_SPAN * TAB_ROWB;
 #pragma unroll 2
                         for (int j = 0; j < span; ++j) {
-                            const double w = sw[j * WARP];
+                            const int i = j - off;       // this lane's tap on window row j (none: weight 0)
+                            const double w = (unsigned)i < (unsigned)TAB_W ? sw[i * WARP] : 0.0;
                             const double2* e = reinterpret_cast<const double2*>(sr + j * TAB_ROWB);
 #pragma unroll
                             for (int n = 0; n < TAB_NM; ++n) {
@@ -2899,7 +2904,7 @@ extern "C" void gwin_plan_destroy(gwin_plan* p) {
     if (p->ev_done_set) cudaEventDestroy(p->ev_done);
     cudaFree(p->d_params); cudaFree(p->d_out); cudaFree(p->d_skip); cudaFree(p->d_points);
     cudaFreeHost(p->h_params); cudaFreeHost(p->h_out); cudaFreeHost(p->h_skip);
-    if (p->timing) { cudaEventDestroy(p->ev0); cudaEventDestroy(p->ev1); }
+    if (p->timing) { cudaEventDestroy(p->ev0); cudaEventDestroy(p->ev1); for (cudaEvent_t e : p->evd) cudaEventDestroy(e); }
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
 }
@@ -3110,26 +3115,56 @@ extern "C" int gwin_plan_slow_path(gwin_plan* p, int64_t* n_walkers) {
 
 extern "C" int gwin_plan_last_launches(const gwin_plan* p) { return p ? p->last_launches : 0; }
 
+static void timing_harvest(gwin_plan* p) {
+    if (!p->timing || !p->ev_pending) return;
+    float ms = 0.f;
+    if (cudaEventSynchronize(p->ev1) == cudaSuccess && cudaEventElapsedTime(&ms, p->ev0, p->ev1) == cudaSuccess) {
+        p->kernel_ms_sum += ms; p->kernel_ms_n++;
+        cudaEvent_t seq[5] = { p->ev0, p->evd[0], p->evd[1], p->evd[2], p->ev1 };
+        for (int i = 0; i < 4; ++i)
+            if (cudaEventElapsedTime(&ms, seq[i], seq[i + 1]) == cudaSuccess) p->detail_ms_sum[i] += ms;
+    }
+    p->ev_pending = false;
+}
+
 extern "C" int gwin_plan_kernel_timing(gwin_plan* p, int enable, double* mean_ms, int* n_launches) {
     if (!p) return fail(GWIN_EINVAL, "plan is NULL");
     CK(cudaSetDevice(p->device));
-    if (p->timing && p->ev_pending) {
-        float ms = 0.f;
-        CK(cudaEventSynchronize(p->ev1));
-        CK(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
-        p->kernel_ms_sum += ms; p->kernel_ms_n++;
-        p->ev_pending = false;
-    }
+    timing_harvest(p);
     if (mean_ms) *mean_ms = p->kernel_ms_n ? p->kernel_ms_sum / p->kernel_ms_n : 0.0;
     if (n_launches) *n_launches = p->kernel_ms_n;
+    for (int i = 0; i < 4; ++i) p->detail_last[i] = p->kernel_ms_n ? p->detail_ms_sum[i] / p->kernel_ms_n : 0.0;
     if (enable && !p->timing) {
         CK(cudaEventCreate(&p->ev0)); CK(cudaEventCreate(&p->ev1));
+        for (cudaEvent_t& e : p->evd) CK(cudaEventCreate(&e));
         p->timing = true;
     } else if (!enable && p->timing) {
         cudaEventDestroy(p->ev0); cudaEventDestroy(p->ev1);
+        for (cudaEvent_t e : p->evd) cudaEventDestroy(e);
         p->timing = false;
     }
     p->kernel_ms_sum = 0.0; p->kernel_ms_n = 0;
+    for (double& x : p->detail_ms_sum) x = 0.0;
+    return GWIN_OK;
+}
+
+extern "C" int gwin_plan_kernel_timing_detail(const gwin_plan* p, double* mean_ms4) {
+    if (!p || !mean_ms4) return fail(GWIN_EINVAL, "NULL argument");
+    for (int i = 0; i < 4; ++i) mean_ms4[i] = p->detail_last[i];
+    return GWIN_OK;
+}
+
+extern "C" int gwin_plan_table_blocks(const gwin_plan* p, int64_t cap, int32_t* start, int32_t* m, int32_t* n_refs,
+                                      int32_t* fine_min, int64_t* n) {
+    if (!p || !n) return fail(GWIN_EINVAL, "NULL argument");
+    *n = p->n_tblk;
+    for (int64_t i = 0; i < std::min<int64_t>(cap, p->n_tblk); ++i) {
+        const TabBlk& B = p->tblk[i];
+        if (start) start[i] = B.start;
+        if (m) m[i] = B.m;
+        if (n_refs) n_refs[i] = B.K;
+        if (fine_min) fine_min[i] = B.fine_n > 0 ? B.fine_min : 0;
+    }
     return GWIN_OK;
 }
 
@@ -3533,12 +3568,7 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
         p->last_launches += 1;
     }
     if (p->timing) {
-        if (p->ev_pending) {            // harvest the previous launch (it has long finished)
-            float ms = 0.f;
-            if (cudaEventSynchronize(p->ev1) == cudaSuccess &&
-                cudaEventElapsedTime(&ms, p->ev0, p->ev1) == cudaSuccess) { p->kernel_ms_sum += ms; p->kernel_ms_n++; }
-            p->ev_pending = false;
-        }
+        timing_harvest(p);              // the previous bracket (it has long finished)
         CK(cudaEventRecord(p->ev0, st));
     }
     MainLaunch M;
@@ -3550,18 +3580,21 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
         launch_main_nd(p, M, st);
         p->last_launches += 1;
     }
+    if (p->timing) CK(cudaEventRecord(p->evd[0], st));
     if (table) {
         // sub-blocks with several reference chirps: walkers in a0 order; the long ones above: in time order
         int split = time_order ? std::min(p->n_tblk, (p->tab_split + per_chunkT - 1) / per_chunkT * per_chunkT) : p->n_tblk;
         launch_table_nd(p, W, wpad, per_chunkT, 0, split, nullptr, false, 0, st);
         launch_table_nd(p, W, wpad, per_chunkT, split, p->n_tblk, p->d_col_t, false, 0, st);
         p->last_launches += split > 0 && split < p->n_tblk ? 1 : 0;
+        if (p->timing) CK(cudaEventRecord(p->evd[1], st));
         // tails: fine sub-blocks (walkers in the order of their last bins), then the recurrence kernel
         // over what is left (less than the finest sub-block)
         if (n_chunksF > 0) {
             launch_table_nd(p, W, wpad, 0, 0, 0, p->d_key2_out, true, n_chunksF, st);
             p->last_launches += 1;
         }
+        if (p->timing) CK(cudaEventRecord(p->evd[2], st));
         MainLaunch T = M;
         T.recur = true; T.calibrated = false;
         T.n_chunks = n_chunks3; T.per_chunk = tail_blocks; T.n_blk = p->n_blk; T.blk_off = 0;
@@ -3570,7 +3603,11 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
         launch_main_nd(p, T, st);
         p->last_launches += 2;
     }
-    if (p->timing) { CK(cudaEventRecord(p->ev1, st)); p->ev_pending = true; }
+    if (p->timing) {
+        if (!table) { CK(cudaEventRecord(p->evd[1], st)); CK(cudaEventRecord(p->evd[2], st)); }
+        CK(cudaEventRecord(p->ev1, st));
+        p->ev_pending = true;
+    }
     combine_kernel<<<(W + 31) / 32, dim3(32, COMB_SEG), 0, st>>>(nd, W, wpad, (n_blk > 0 || !recur) ? n_chunks : 0, mode, per_chunk, n_blk,
                                                                  recur ? p->d_blk_start : nullptr, band0, d.kmax,
                                                                  perm, p->d_wc, p->d_ks, ke_main,

@@ -253,6 +253,14 @@ int gwin_plan_last_launches(const gwin_plan* plan);
  * launching stream.  enable != 0 switches it on; every call returns the mean duration
  * [ms] and count of the loglr-kernel launches since the previous call, then resets. */
 int gwin_plan_kernel_timing(gwin_plan* plan, int enable, double* mean_ms, int* n_launches);
+/* The same bracket split by launch (means over the launches the last gwin_plan_kernel_timing call reported):
+ * [0] recurrence (or direct) kernel over its share of the band, [1] table kernel over the schedule's
+ * sub-blocks, [2] table kernel over the tails' fine sub-blocks, [3] recurrence kernel over what is left. */
+int gwin_plan_kernel_timing_detail(const gwin_plan* plan, double* mean_ms4);
+/* The schedule of the moment tables: start bin, length, reference chirps and finest tail sub-block (0: none)
+ * of up to `cap` sub-blocks; *n receives their number. */
+int gwin_plan_table_blocks(const gwin_plan* plan, int64_t cap, int32_t* start, int32_t* m, int32_t* n_refs,
+                           int32_t* fine_min, int64_t* n);
 
 /* ------------------------------------------------------------------------------------------
  * Device-resident ensemble step (replaces, on the device, what emcee does on the host between

@@ -570,6 +570,22 @@ class PlanModel(object):
         M = (rows[:, taps % L] * wt[None, :]).sum(axis=1)
         return np.exp(-2j * PI * (th0 - math.floor(th0))) * np.dot(e[:N + 1], M)
 
+    @staticmethod
+    def fine_decomposition(length, pm, fmin):
+        """loglr_table_kernel<FINE>: the fine sub-blocks (offset, size) a walker takes between the start
+        of the sub-block of ``pm`` bins it ends in and its last bin, ``length`` bins further on: at the
+        level of sub-blocks of ml = pm / 2, pm / 4, ... >= fmin bins, the one at offset (q - 1) ml when
+        q = (length // fmin * fmin) // ml is odd; and the number of bins left after the last one."""
+        taken = []
+        stretch = length // fmin * fmin
+        ml = pm // 2
+        while ml >= fmin:
+            q = stretch // ml
+            if q & 1:
+                taken.append(((q - 1) * ml, ml))
+            ml //= 2
+        return taken, length - stretch
+
     def loglr_table(self, p, marg=False):
         """Returns (loglr, hd, hh) and sets ``slow`` when the walker would leave the table path."""
         w = self.walker(p)

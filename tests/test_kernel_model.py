@@ -149,3 +149,18 @@ def test_table_truncation_estimate_flags_uncovered_walkers():
     spinning[2:4] = 0.8, -0.6
     pm.loglr_table(spinning)
     assert pm.slow and pm.worst_est > pm.TAB_EST_MAX
+
+
+def test_fine_decomposition_of_the_tails():
+    """The closed-form choice of fine sub-blocks tiles the stretch between the last whole sub-block
+    and the walker's last bin exactly, left to right, with at most one sub-block per level."""
+    from kernel_model import PlanModel
+    for pm, fmin in ((8192, 128), (4096, 128), (3072, 192), (6144, 192), (256, 128)):
+        for length in list(range(0, min(pm, 700))) + [pm - 1, pm - fmin, pm // 2, pm // 2 - 1, pm // 2 + 1]:
+            taken, left = PlanModel.fine_decomposition(length, pm, fmin)
+            pos = 0
+            for off, size in taken:
+                assert off == pos and off % size == 0 and size >= fmin and off + size <= pm
+                pos += size
+            assert pos + left == length and 0 <= left < fmin
+            assert len(set(size for _, size in taken)) == len(taken)
