@@ -1611,8 +1611,11 @@ __global__ void cover_stats_kernel(PlanDev P, int W, const double* __restrict__ 
 // parent_arr[col] it ends in) of the binary decomposition of that stretch -- at most one per level, found
 // in closed form -- and evaluates the few bins left after the finest one directly.  CTA y takes levels
 // y, y + gridDim.y, ... and writes partial-sum slot y.
+#ifndef TABLE_FINE_CTAS
+#define TABLE_FINE_CTAS TABLE_MIN_CTAS
+#endif
 template <int ND, bool FINE>
-__global__ void __launch_bounds__(CTA_THREADS, TABLE_MIN_CTAS)
+__global__ void __launch_bounds__(CTA_THREADS, FINE ? TABLE_FINE_CTAS : TABLE_MIN_CTAS)
 loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo, int blk_hi,
                    const TabBlk* __restrict__ blks, const double* __restrict__ cmat,
                    const double* __restrict__ tref, const double2* __restrict__ tab,
@@ -1860,7 +1863,9 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
         const int par = live ? parent_arr[col] : -1;
         int pf = 0, pm = 0, pmin = 0x7fffffff;
         if (par >= 0) { pf = blks[par].fine_first; pm = blks[par].m; pmin = blks[par].fine_min; }
-        for (int lev = blockIdx.y; lev < 20; lev += gridDim.y) {
+        // (the last slot keeps the bins after the finest sub-block; the others share the levels)
+        const int lev_slots = max((int)gridDim.y - 1, 1);
+        for (int lev = blockIdx.y; lev < 20 && (int)blockIdx.y < lev_slots; lev += lev_slots) {
             const int ml = pm >> (lev + 1);
             const bool deep = par >= 0 && ml >= pmin;
             if (!__any_sync(0xffffffffu, deep)) break;
@@ -1875,7 +1880,7 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
                 do_block(b, B, same && !dead);
             }
         }
-        if (blockIdx.y == 0) {
+        if (blockIdx.y == gridDim.y - 1) {
             // the bins after the finest sub-block (fewer than its length): per-bin phase and sincos, every
             // lane its own bins
             const int r0 = tail_s + tail_len;
@@ -1888,16 +1893,21 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
                 pc.a0 = TCOEF(C_A0); pc.a2 = TCOEF(C_A2); pc.a3 = TCOEF(C_A3); pc.a4 = TCOEF(C_A4); pc.a5 = TCOEF(C_A5);
                 pc.b5 = TCOEF(C_B5); pc.a6 = TCOEF(C_A6); pc.b6 = TCOEF(C_B6); pc.a7 = TCOEF(C_A7);
                 pc.a10 = TCOEF(C_A10); pc.a12 = TCOEF(C_A12);
+                // (branch-free, so that the loads of several bins are in flight at once: every lane walks its
+                //  own bins, nothing is coalesced, and the loop would otherwise wait out one L2 latency per bin)
+                const int kpark = max(P.kmin, 1);
+#pragma unroll 4
                 for (int i = 0; i < nmax; ++i) {
-                    if (i < nres && !dead) {
-                        const int k = r0 + i;
-                        const double kd = (double)k;
-                        const double psi = phase_turns(pc, ld_basis(P.basis + k));
+                    const bool on = i < nres && !dead;
+                    const int k = on ? r0 + i : kpark;
+                    const double kd = (double)k;
+                    const double psi = phase_turns(pc, ld_basis(P.basis + k));
 #pragma unroll
-                        for (int d = 0; d < ND; ++d) {
-                            const double2 u = phasor_neg(psi + fma(kd, TCOEF(NPH + 2 * d + 1), frac1(kd * TCOEF(NPH + 2 * d))));
-                            acc[d] = cfma(__ldg(P.T + (size_t)k * ND + d), u, acc[d]);
-                        }
+                    for (int d = 0; d < ND; ++d) {
+                        const double2 u = phasor_neg(psi + fma(kd, TCOEF(NPH + 2 * d + 1), frac1(kd * TCOEF(NPH + 2 * d))));
+                        double2 Tk = __ldg(P.T + (size_t)k * ND + d);
+                        if (!on) Tk = make_double2(0.0, 0.0);
+                        acc[d] = cfma(Tk, u, acc[d]);
                     }
                 }
             }
@@ -3455,7 +3465,7 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
             p->partialT_cap = need;
         }
     }
-    static const int fine_slots = std::max(1, getenv("GWIN_FINE_SLOTS") ? atoi(getenv("GWIN_FINE_SLOTS")) : 6);
+    static const int fine_slots = std::max(1, getenv("GWIN_FINE_SLOTS") ? atoi(getenv("GWIN_FINE_SLOTS")) : 7);
     const int n_chunksF = (table && p->n_fine > 0) ? fine_slots : 0;
     if (n_chunksF > 0) {
         const size_t need = (size_t)n_chunksF * nd * p->w_cap;

@@ -1,9 +1,10 @@
 #!/bin/bash
-# development aid: time build variants / run-time knobs of the table path on the C3 batch
+# development aid: time build variants / run-time knobs of the table path on the C3 batch (bench.py's own split)
 cd "$(dirname "$0")/.."
-T=${T:-200}
-run() { echo "=== $*"; timeout "$T" env "$@" 2>&1 | grep -E "cold-L2|evals/s|max \||first call|Error|error|tables:"; }
-run GWIN_B200_LIB=$PWD/gwin_b200/libgwin_b200.so python tools/quick_time.py 16384 256 table,direct
+T=${T:-300}
+run() { echo "=== $*"; timeout "$T" env "$@" python bench.py --steps 10 --warmup 3 --no-cpu 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], [(l['kernel'][:22], round(l['ms'],4)) for l in d['roofline']['launches']])"; }
+run GWIN_B200_LIB=$PWD/gwin_b200/libgwin_b200.so
 for v in "$@"; do
-  run GWIN_B200_LIB=$PWD/gwin_b200/libgwin_$v.so python tools/quick_time.py 16384 256 table
+  run GWIN_B200_LIB=$PWD/gwin_b200/libgwin_$v.so
 done
