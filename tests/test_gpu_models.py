@@ -214,6 +214,56 @@ def test_posterior_consistency_ks_vs_oracle():
     assert abs(np.median(chains[0][:, 0]) - cfg.inj['tc']) < 2e-3
 
 
+@pytest.mark.slow
+def test_posterior_consistency_ks_independent_runs():
+    """The north-star criterion as SURVEY.md 8d states it: C1, emcee semantics, 200 walkers,
+    >= 2000 iterations after burn-in, thinned by the measured autocorrelation length; the run
+    with the CUDA likelihood and the run driven by the CPU oracle use DIFFERENT seeds (independent
+    chains); two-sample KS p > 0.01 per parameter.  The device-resident stepper
+    (CudaEnsembleSampler, its own Philox stream) is held to the oracle-driven run the same way."""
+    from gwin_b200.sampler import CudaEnsembleSampler
+    cfg = util.c1()
+    names = ['tc', 'distance', 'inclination', 'coa_phase']
+    prior = D.JointDistribution(
+        names, D.Uniform(tc=(cfg.inj['tc'] - 0.02, cfg.inj['tc'] + 0.02)),
+        D.UniformRadius(distance=(100., 1500.)), D.SinAngle(inclination=None),
+        D.UniformAngle(coa_phase=None))
+    static = {k: v for k, v in cfg.inj.items() if k not in names}
+    cuda = cfg.cuda_model(variable_params=tuple(names), static_params=static, prior=prior)
+    orc = OracleGaussianNoise(names, cfg, static_params=static, prior=prior, nthreads=8)
+    nwalkers, burn, keep = 200, 600, 2000
+
+    def host_run(model, seed):
+        np.random.seed(seed)
+        s = EmceeEnsembleSampler(model, nwalkers, model_call=models.CallModel(model, 'logplr'))
+        s.set_p0()
+        s.run(burn + keep)
+        return s.chain[:, burn:, :]
+
+    def device_run(seed):
+        np.random.seed(seed)
+        s = CudaEnsembleSampler(cuda, nwalkers, seed=seed)
+        s.set_p0()
+        s.run(burn + keep)
+        return s.chain[:, burn:, :]
+
+    chains = {"oracle": host_run(orc, 101), "cuda, host stepper": host_run(cuda, 202),
+              "cuda, device stepper": device_run(303)}
+    thinned = {}
+    for what, c in chains.items():
+        acl = int(np.ceil(max(util.autocorrelation_length(c[:, :, i]) for i in range(len(names)))))
+        assert acl < keep // 10, (what, acl)
+        thinned[what] = c[:, ::acl, :].reshape(-1, len(names))
+        assert len(thinned[what]) >= 1000
+    for what in ("cuda, host stepper", "cuda, device stepper"):
+        for i, n in enumerate(names):
+            p = stats.ks_2samp(thinned[what][:, i], thinned["oracle"][:, i]).pvalue
+            assert p > 0.01, (what, n, p)
+        # independent runs: no sample in common
+        assert not np.any(np.isin(thinned[what][:50, 0], thinned["oracle"][:, 0]))
+    assert abs(np.median(thinned["cuda, host stepper"][:, 0]) - cfg.inj['tc']) < 2e-3
+
+
 def test_pt_sampler_runs_on_gpu(cfg):
     prior = D.JointDistribution(['tc', 'distance'],
                                 D.Uniform(tc=(cfg.inj['tc'] - 0.05, cfg.inj['tc'] + 0.05)),

@@ -794,3 +794,22 @@ def test_interleaved_host_and_device_calls_on_different_streams(cfg2):
     torch.cuda.synchronize()
     for o in outs:
         np.testing.assert_array_equal(o[0].cpu().numpy(), ref[0])
+
+
+def _upstream_files():
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    return sorted(glob.glob(os.path.join(here, "*_upstream.npz")))
+
+
+@pytest.mark.skipif(not _upstream_files(), reason="no tests/golden/*_upstream.npz (see make_upstream_golden.py)")
+@pytest.mark.parametrize("path", _upstream_files())
+def test_upstream_golden_vectors_cuda(path):
+    """The CUDA path against vectors computed by the reference's own classes over pycbc /
+    lalsimulation, every kernel."""
+    u = np.load(path)
+    cfg = util.golden_config(os.path.basename(path).replace("_upstream", ""))
+    model = cfg.cuda_model()
+    for kernel in (1, 2, 3, 0):
+        model.plan.configure(kernel=kernel)
+        lr = model.plan.loglr_host(u["params"], mode=int(bool(u["marg"])))[0]
+        assert np.all(np.abs(lr - u["loglr"]) <= tol(u["loglr"])), kernel

@@ -408,3 +408,26 @@ def test_golden_vectors(path):
     co = COracle(cfg.data, cfg.delta_f, cfg.epoch, cfg.f_lower, psds=cfg.psds())
     lc = co.batch_loglr(g["params"], mode=int(marg), nthreads=2)[0]
     assert np.max(np.abs(lc - g["loglr"])) <= 1e-7
+
+
+def _upstream_files():
+    import glob
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    return sorted(glob.glob(os.path.join(here, "*_upstream.npz")))
+
+
+@pytest.mark.skipif(not _upstream_files(), reason="no tests/golden/*_upstream.npz: make_upstream_golden.py has not "
+                    "been run where pycbc + lalsuite are installed (numeric parity with upstream stays unpinned)")
+@pytest.mark.parametrize("path", _upstream_files())
+def test_upstream_golden_vectors(path):
+    """Vectors computed by the reference's own model classes over pycbc / lalsimulation
+    (tests/golden/make_upstream_golden.py): the oracle is held to them at the north-star tolerance."""
+    u = np.load(path)
+    name = os.path.basename(path).replace("_upstream", "")
+    cfg = util.golden_config(name)
+    orc = cfg.oracle(phase_marginalization=bool(u["marg"]))
+    lr, hd, hh = O.batch_loglr(orc, u["params"])
+    assert np.all(np.abs(lr - u["loglr"]) <= util.tol(u["loglr"]))
+    ok = np.isfinite(u["hh"])
+    assert np.all(np.abs(hh[ok] - u["hh"][ok]) <= np.maximum(1e-6, 1e-9 * np.abs(u["hh"][ok])))
+    assert abs(orc.lognl() - float(u["lognl"])) <= 1e-9 * abs(float(u["lognl"]))

@@ -170,3 +170,24 @@ def golden_config(name):
             "c2_margdist.npz": lambda: c2(),
             "c2_margdistphase.npz": lambda: c2(),
             "c2_calibrated.npz": lambda: c2()}[name]()
+
+
+def autocorrelation_length(chain):
+    """Integrated autocorrelation time [iterations] of an ensemble chain [nwalkers, niter]: the
+    walker-averaged autocorrelation function summed up to Sokal's window M = 5 tau (what
+    pycbc.filter.autocorrelation.calculate_acl, used by gwin/burn_in.py and the samplers' ACL
+    thinning, estimates)."""
+    x = np.asarray(chain, dtype=float)
+    x = x - x.mean(axis=1, keepdims=True)
+    n = x.shape[1]
+    f = np.fft.rfft(x, 2 * n, axis=1)
+    acf = np.fft.irfft(f * np.conj(f), axis=1)[:, :n].mean(axis=0)
+    if acf[0] <= 0:
+        return 1.0
+    rho = acf / acf[0]
+    tau = 1.0
+    for m in range(1, n):
+        tau += 2.0 * rho[m]
+        if m >= 5.0 * tau:
+            break
+    return max(tau, 1.0)
