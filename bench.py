@@ -226,7 +226,7 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(per_step),
+        "config": workload_config(),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -235,11 +235,17 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def workload_config(walkers_per_step):
+def workload_config():
+    """The same dict on both arms (the driver compares them): the workload is one step of 16 384 walkers per
+    GPU; how much of it a CPU step samples is said in that line's ``cpu_baseline.sample``."""
     return {"workload": "C3: TaylorF2 BNS loglr (GaussianNoise), 256 s @ 4096 Hz, 524289 bins, "
                         "H1+L1+V1, coloured Gaussian noise + 1.4+1.4 Msun injection",
-            "walkers_per_gpu_per_step": walkers_per_step, "f_lower_hz": F_LOWER,
-            "mass_box_msun": list(MASS_BOX)}
+            "walkers_per_gpu_per_step": WALKERS, "f_lower_hz": F_LOWER,
+            "mass_box_msun": list(MASS_BOX),
+            "l2": "CUDA arm: flushed between timed steps (256 MiB write); CPU arm: tables far larger than the host caches",
+            "kernel": "CUDA arm: plain model constructor, kernel AUTO (loglr_table_kernel over per-plan moment tables, "
+                      "loglr_recur_kernel for whatever band the tables do not take); CPU arm: C port of the reference "
+                      "path (oracle/loglr_ref.c) on all host threads, rank 0 only whatever N"}
 
 
 # ---------------------------------------------------------------------------
@@ -406,12 +412,9 @@ def run_cuda(args):
             "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(W), l2="flushed between timed steps (256 MiB write)",
-                           kernel="AUTO: loglr_table_kernel (per-plan moment tables with reference chirps + 13-tap NUFFT "
-                                  "interpolation) over the schedule's sub-blocks and the tails' fine sub-blocks; "
-                                  "loglr_recur_kernel (block-anchored phasor recurrence) for whatever band the tables do not take",
-                           moment_tables=tab_info, slow_path_walkers=n_slow,
-                           mean_bins_per_eval=float(bins.mean())),
+            "config": workload_config(),
+            "detail": {"moment_tables": tab_info, "slow_path_walkers": n_slow, "mean_bins_per_eval": float(bins.mean()),
+                       "walkers_this_run": W, "timed_region_ms": total_ms},
             "clocks": clk,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": world * W * 13 * 8,
                     "d2h_bytes_per_step": world * W * 8,
@@ -481,7 +484,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.steps is None:
-        args.steps = 30 if args.impl == "cuda" else 3
+        args.steps = 1000 if args.impl == "cuda" else 3
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -10,6 +10,12 @@ each half-step's proposals to ONE batched likelihood call.
 
 ``lnpostfn(points[W, ndim]) -> (lnprob[W], blobs)`` where ``blobs`` is a list of W
 stat tuples or None; the PT variant takes ``logl_logp(points) -> (logl, logp)``.
+
+Attribution: the step order, the use of the random stream and the swap rule follow
+emcee 2.x (``emcee/ensemble.py``, ``emcee/ptsampler.py``; Copyright 2010-2013 Daniel
+Foreman-Mackey & contributors, MIT licence) so that chains drawn here are
+RNG-stream-identical to chains drawn by the reference through emcee; emcee is a
+third-party dependency of the reference (``setup.py``), not part of /root/reference.
 """
 import numpy
 
