@@ -220,41 +220,50 @@ def test_posterior_consistency_ks_independent_runs():
     >= 2000 iterations after burn-in, thinned by the measured autocorrelation length; the run
     with the CUDA likelihood and the run driven by the CPU oracle use DIFFERENT seeds (independent
     chains); two-sample KS p > 0.01 per parameter.  The device-resident stepper
-    (CudaEnsembleSampler, its own Philox stream) is held to the oracle-driven run the same way."""
+    (CudaEnsembleSampler, its own Philox stream) is held to the oracle-driven run the same way.
+
+    Walkers start in a small ball around the injection (the reference's ``[initial]`` distribution,
+    ``set_p0(prior=...)``) and sample tc, distance and coa_phase: started from prior draws, or with
+    the inclination sampled, this posterior keeps walkers in side lobes of tc / in the face-off mode
+    for good, and two independent oracle-driven runs already differ by more than KS allows
+    (ACL > 600 iterations, p = 0).  Thinning is by twice the ACL: the walkers of one ensemble are
+    not independent of each other at equal iteration."""
     from gwin_b200.sampler import CudaEnsembleSampler
     cfg = util.c1()
-    names = ['tc', 'distance', 'inclination', 'coa_phase']
+    names = ['tc', 'distance', 'coa_phase']
     prior = D.JointDistribution(
         names, D.Uniform(tc=(cfg.inj['tc'] - 0.02, cfg.inj['tc'] + 0.02)),
-        D.UniformRadius(distance=(100., 1500.)), D.SinAngle(inclination=None),
-        D.UniformAngle(coa_phase=None))
+        D.UniformRadius(distance=(100., 1500.)), D.UniformAngle(coa_phase=None))
+    init = D.JointDistribution(
+        names, D.Uniform(tc=(cfg.inj['tc'] - 2e-4, cfg.inj['tc'] + 2e-4)),
+        D.Uniform(distance=(250., 350.)), D.Uniform(coa_phase=(1.0, 1.2)))
     static = {k: v for k, v in cfg.inj.items() if k not in names}
     cuda = cfg.cuda_model(variable_params=tuple(names), static_params=static, prior=prior)
     orc = OracleGaussianNoise(names, cfg, static_params=static, prior=prior, nthreads=8)
-    nwalkers, burn, keep = 200, 600, 2000
+    nwalkers, burn, keep = 200, 500, 2500
 
     def host_run(model, seed):
         np.random.seed(seed)
         s = EmceeEnsembleSampler(model, nwalkers, model_call=models.CallModel(model, 'logplr'))
-        s.set_p0()
+        s.set_p0(prior=init)
         s.run(burn + keep)
         return s.chain[:, burn:, :]
 
     def device_run(seed):
         np.random.seed(seed)
         s = CudaEnsembleSampler(cuda, nwalkers, seed=seed)
-        s.set_p0()
+        s.set_p0(prior=init)
         s.run(burn + keep)
         return s.chain[:, burn:, :]
 
-    chains = {"oracle": host_run(orc, 101), "cuda, host stepper": host_run(cuda, 202),
-              "cuda, device stepper": device_run(303)}
+    chains = {"oracle": host_run(orc, 202), "cuda, host stepper": host_run(cuda, 303),
+              "cuda, device stepper": device_run(404)}
     thinned = {}
     for what, c in chains.items():
         acl = int(np.ceil(max(util.autocorrelation_length(c[:, :, i]) for i in range(len(names)))))
-        assert acl < keep // 10, (what, acl)
-        thinned[what] = c[:, ::acl, :].reshape(-1, len(names))
-        assert len(thinned[what]) >= 1000
+        assert acl <= keep // 25, (what, acl)          # >= 25 autocorrelation lengths per walker
+        thinned[what] = c[:, ::2 * acl, :].reshape(-1, len(names))
+        assert len(thinned[what]) >= 3000
     for what in ("cuda, host stepper", "cuda, device stepper"):
         for i, n in enumerate(names):
             p = stats.ks_2samp(thinned[what][:, i], thinned["oracle"][:, i]).pvalue

@@ -333,3 +333,85 @@ def test_parameters_the_kernel_does_not_evaluate_are_refused():
     # zero total mass is "no waveform", not a ZeroDivisionError
     with pytest.raises(NoWaveformError):
         gen.generate(mass1=0., mass2=0., ra=0., dec=0., polarization=0., tc=1.)
+
+
+class _KombineShapedSampler(object):
+    """The call pattern of ``kombine.Sampler`` as the reference drives it
+    (``gwin/sampler/kombine.py:81-84, 142-147``): it is given ``pool`` and ``processes = pool.count``,
+    the wrapper first computes ``blob0 = [model(p0[wi, :])[1] for wi in range(nwalkers)]`` with
+    scalar calls, and every iteration maps the log-posterior callable over ALL walkers' proposals,
+    each call returning ``(lnpost, blob)``."""
+
+    def __init__(self, nwalkers, ndim, lnpostfn, pool=None, processes=1):
+        self.nwalkers, self.ndim, self.lnpostfn = nwalkers, ndim, lnpostfn
+        self.pool, self.processes = pool, processes
+        self.blobs = []
+
+    def run_mcmc(self, niter, p0, blob0, rng):
+        p, blob = np.array(p0), list(blob0)
+        lnpost = np.array([self.lnpostfn(x)[0] for x in p])
+        for _ in range(niter):
+            prop = p + 0.3 * rng.standard_normal(p.shape)      # (kombine draws from its KDE; any proposal does here)
+            results = list(self.pool.map(self.lnpostfn, prop))
+            lnq = np.array([r[0] for r in results])
+            acc = np.log(rng.uniform(size=self.nwalkers)) < lnq - lnpost
+            p[acc], lnpost[acc] = prop[acc], lnq[acc]
+            blob = [results[i][1] if acc[i] else blob[i] for i in range(self.nwalkers)]
+            self.blobs.append(list(blob))
+        return p, lnpost
+
+
+def test_kombine_call_pattern_through_the_pool():
+    prior = D.JointDistribution(['x', 'y'], D.Uniform(x=(-5, 5), y=(-5, 5)))
+    m = models.TestNormal(['x', 'y'], prior=prior)
+    call = models.CallModel(m, 'logposterior')            # return_all_stats: (value, blob) per point
+    pool = BatchPool()
+    pool.count = 4                                        # what sampler_from_cli sets from opts.nprocesses
+    nwalkers = 16
+    s = _KombineShapedSampler(nwalkers, 2, call, pool=pool, processes=pool.count)
+    assert s.processes == 4
+    rng = np.random.default_rng(5)
+    p0 = rng.uniform(-1, 1, (nwalkers, 2))
+    blob0 = [call(p0[wi, :])[1] for wi in range(nwalkers)]           # kombine.py:145-147
+    assert all(len(b) == len(m.default_stats) for b in blob0)
+    p, lnpost = s.run_mcmc(5, p0, blob0, rng)
+    assert pool.ncalls == 5 and pool.npoints == 5 * nwalkers          # one batched evaluation per iteration
+    # the blobs carried with the accepted positions are the scalar calls' blobs
+    for wi in range(nwalkers):
+        v, b = call(p[wi])
+        assert v == lnpost[wi]
+        assert all(x == y or (np.isnan(x) and np.isnan(y)) for x, y in zip(b, s.blobs[-1][wi]))
+
+
+def test_sampler_from_cli_selects_pool_and_global_instance():
+    """option_utils.sampler_from_cli (reference gwin/option_utils.py:150-185)."""
+    from types import SimpleNamespace
+    from gwin_b200 import option_utils
+    prior = D.JointDistribution(['x'], D.Uniform(x=(-5, 5)))
+    m = models.TestNormal(['x'], prior=prior)
+    try:
+        opts = SimpleNamespace(sampler="emcee", logpost_function="logposterior", nprocesses=1,
+                               use_mpi=False, nwalkers=8)
+        models._global_instance = None
+        s = option_utils.sampler_from_cli(opts, m)
+        assert isinstance(s, EmceeEnsembleSampler)
+        assert models._global_instance is None                     # one process: the model is called directly
+        assert isinstance(s.model, models.CallModel) and s.model.callstat == "logposterior"
+        assert isinstance(s._pool, BatchPool) and s._pool.count == 1
+        opts.nprocesses = 6
+        s = option_utils.sampler_from_cli(opts, m)
+        assert isinstance(models._global_instance, models.CallModel)
+        assert s._model_call is models._call_global_model           # workers would call it by name
+        assert s._pool.count == 6
+        np.random.seed(2)
+        s.set_p0()
+        s.run(20)
+        assert s.chain.shape == (8, 20, 1)
+        opts.sampler, opts.ntemps = "emcee_pt", 2
+        s = option_utils.sampler_from_cli(opts, m)
+        assert isinstance(s, EmceePTSampler)
+        with pytest.raises(KeyError):
+            opts.sampler = "no_such_sampler"
+            option_utils.sampler_from_cli(opts, m)
+    finally:
+        models._global_instance = None
