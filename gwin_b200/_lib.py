@@ -41,7 +41,8 @@ SYMBOLS = (
     "gwin_loglr_batch",
     "gwin_loglr_batch_host", "gwin_loglr_batch_strided",
     "gwin_loglr_batch_host_strided", "gwin_generate_host",
-    "gwin_loglr_batch_points_host", "gwin_host_alloc", "gwin_host_free",
+    "gwin_loglr_batch_points_host", "gwin_loglr_batch_points_submit", "gwin_loglr_batch_points_wait",
+    "gwin_host_alloc", "gwin_host_free",
     "gwin_plan_last_launches",
     "gwin_plan_kernel_timing", "gwin_plan_kernel_timing_detail", "gwin_plan_table_blocks",
     "gwin_ens_propose", "gwin_ens_prior", "gwin_ens_accept", "gwin_ens_swap",
@@ -175,6 +176,12 @@ def load():
         lib.gwin_loglr_batch_points_host.argtypes = [
             C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_int64,
             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.gwin_loglr_batch_points_submit.restype = C.c_int
+        lib.gwin_loglr_batch_points_submit.argtypes = [
+            C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_int64,
+            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        lib.gwin_loglr_batch_points_wait.restype = C.c_int
+        lib.gwin_loglr_batch_points_wait.argtypes = [C.c_void_p, C.c_int]
         lib.gwin_host_alloc.restype = C.c_int
         lib.gwin_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
         lib.gwin_host_free.restype = None
@@ -246,6 +253,29 @@ def pinned_empty(shape, dtype=np.float64):
     arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
     weakref.finalize(buf, lib.gwin_host_free, ptr.value)
     return arr
+
+
+class PendingCall(object):
+    """A queued ``gwin_loglr_batch_points_submit``: ``wait()`` blocks until the results are in
+    host memory (``gwin_loglr_batch_points_wait``) and returns them.  The input buffers are kept
+    alive until then."""
+
+    def __init__(self, plan, ticket, out, keep=()):
+        self._plan, self._ticket, self._out, self._keep = plan, ticket, out, keep
+
+    def wait(self):
+        if self._ticket is not None:
+            check(self._plan._lib.gwin_loglr_batch_points_wait(self._plan._h, self._ticket))
+            self._ticket, self._keep = None, ()
+        return self._out
+
+    def __del__(self):
+        # never leave a slot busy (and the device writing into freed host memory)
+        try:
+            if self._ticket is not None and self._plan._h:
+                self._plan._lib.gwin_loglr_batch_points_wait(self._plan._h, self._ticket)
+        except Exception:        # noqa: BLE001 -- interpreter shutdown
+            pass
 
 
 class Plan(object):
@@ -440,11 +470,13 @@ class Plan(object):
         return loglr, hd, hh
 
     def loglr_points_host(self, points, colmap, fixed, mode=MODE_GAUSSIAN, skip=None,
-                          stats=True, col_major=False):
+                          stats=True, col_major=False, defer=False):
         """``gwin_loglr_batch_points_host``: ``points`` is the [W, ndim] array of SAMPLED values
         (``[ndim, W]`` with ``col_major``), ``colmap[i]`` the column holding kernel parameter i
         (-1: ``fixed[i]``).  Page-locked ``points`` (``pinned_empty``) are copied from directly.
-        ``stats=False`` leaves hd / hh on the device: returns (loglr, None, None)."""
+        ``stats=False`` leaves hd / hh on the device: returns (loglr, None, None).
+        ``defer=True`` only queues the call (``gwin_loglr_batch_points_submit``) and returns a
+        ``PendingCall``; its ``wait()`` gives the same tuple.  Two calls may be pending per plan."""
         points = np.ascontiguousarray(points, dtype=np.float64)
         if points.ndim != 2:
             raise ValueError("points must be 2-D")
@@ -464,10 +496,14 @@ class Plan(object):
             sk = np.ascontiguousarray(skip, dtype=np.uint8)
             if sk.shape != (W,):
                 raise ValueError("skip must be [W]")
-        check(self._lib.gwin_loglr_batch_points_host(
-            self._h, int(mode), W, points.ctypes.data, ndim, sw, si, cm.ctypes.data,
-            fx.ctypes.data, sk.ctypes.data if sk is not None else None, loglr.ctypes.data,
-            hd.ctypes.data if stats else None, hh.ctypes.data if stats else None))
+        args = (self._h, int(mode), W, points.ctypes.data, ndim, sw, si, cm.ctypes.data,
+                fx.ctypes.data, sk.ctypes.data if sk is not None else None, loglr.ctypes.data,
+                hd.ctypes.data if stats else None, hh.ctypes.data if stats else None)
+        if defer:
+            ticket = C.c_int(-1)
+            check(self._lib.gwin_loglr_batch_points_submit(*(args + (C.byref(ticket),))))
+            return PendingCall(self, ticket.value, (loglr, hd, hh), keep=(points, cm, fx, sk))
+        check(self._lib.gwin_loglr_batch_points_host(*args))
         return loglr, hd, hh
 
     def loglr_device(self, params, mode=MODE_GAUSSIAN, skip=None, out=None,

@@ -241,6 +241,17 @@ struct gwin_plan {
     double *d_params, *d_out, *d_points; uint8_t* d_skip;
     int64_t stage_cap;
     cudaStream_t stream;
+    // asynchronous host entry (gwin_loglr_batch_points_submit / _wait): two calls in flight, each with its own
+    // staging; copies in and out run on their own streams so that they overlap the other call's kernels
+    struct AsyncSlot {
+        double *d_points, *d_params, *d_out, *h_points, *h_out; uint8_t *d_skip, *h_skip;
+        int64_t cap;
+        bool busy, table;
+        int64_t W; double *loglr, *hd, *hh; bool direct_out;
+        cudaEvent_t ev_in, ev_k, ev_out;
+    } aslot[2];
+    cudaStream_t stream_in, stream_out;
+    bool async_ready;
     int last_launches;
     // optional timing of the dominant kernel on the launching stream
     bool timing;
@@ -322,6 +333,13 @@ __device__ __forceinline__ double2 cfma(double2 a, double2 b, double2 c) {
 // (Emitting these eight instructions as inline PTX in an order where each shares a source
 // register with its predecessor does not survive ptxas, which re-schedules them; the
 // modelled operand-fetch cost stays at ~82 % of the DFMA rate either way, tools/sass_cost.py.)
+// FP64 tensor-core MMA, D (8x8) += A (8x4, row-major) B (4x8, column-major): lane l holds A[l/4][l%4], B[l%4][l/4],
+// D[l/4][2 (l%4)] and D[l/4][2 (l%4) + 1].  Same pipe and peak rate as DFMA on B200 (tools/fp64_probe.py) at one
+// instruction and four operand registers per 8 multiply-adds per lane.
+__device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
 __device__ __forceinline__ void horner_step(double2& acc, double2& g, const double2 T, const double2 r) {
     acc = cfma(acc, g, T);
     g = cmul(g, r);
@@ -1591,7 +1609,20 @@ __global__ void cover_stats_kernel(PlanDev P, int W, const double* __restrict__ 
 #define TAB_SPAN 24
 #endif
 // TAB_SPAN: table rows a warp stages per detector and sub-block (>= TAB_W + the lanes' spread)
+#ifndef TAB_DMMA
+#define TAB_DMMA 1           // taps x moments on the FP64 tensor cores (mma.m8n8k4.f64) instead of DFMA + broadcast loads
+#endif
+#if TAB_DMMA
+#define TAB_ROWB (TAB_NM * 16 + 32)         // 20 doubles: the B fragments' loads (4 rows x 8 columns per half-warp) hit 16 distinct banks
+#else
 #define TAB_ROWB (TAB_NM * 16 + 16)
+#endif
+#ifndef TAB_BGLOBAL
+#define TAB_BGLOBAL 1        // B fragments (table rows) straight from global memory / L1 instead of a staged copy in shared memory
+#endif
+#define TAB_MD_ALIAS 0        // (1: the moments' hand-over buffer would share the weight matrix' memory)
+#define TAB_STAGE_BYTES(nd) ((TAB_DMMA && TAB_BGLOBAL) ? 0 : (nd) * TAB_SPAN * TAB_ROWB)      // per warp
+#define TAB_WDP 36           // pitch [doubles] of the dense weight matrix [window row][lane]: conflict-free A fragments
 #ifndef TAB_CHUNK_MAX
 #define TAB_CHUNK_MAX 8
 #endif
@@ -1600,7 +1631,13 @@ __global__ void cover_stats_kernel(PlanDev P, int W, const double* __restrict__ 
 #define TAB_COEF_SMEM 1      // per-thread coefficients in shared memory (1) or in registers (0)
 #endif
 #define TAB_CROWS(nd) (NPH + 2 * (nd))      // per-thread coefficient column: phase coefficients, tau_hi/lo per detector
+#if TAB_DMMA
+// per lane (i.e. x 32 per warp) [doubles]: its column of the dense weight matrix [TAB_SPAN][TAB_WDP] and its row of
+// the moments handed back by the tensor cores [32][2 TAB_NM]
+#define TAB_WPITCH ((TAB_SPAN * TAB_WDP + WARP - 1) / WARP + (TAB_MD_ALIAS ? 0 : 2 * TAB_NM))
+#else
 #define TAB_WPITCH TAB_W                    // tap weights per lane [doubles], stored [tap][lane]
+#endif
 // Thread t works on column col_arr[t] of the per-walker arrays (NULL: t itself): the sub-blocks with
 // several reference chirps are taken with the walkers ordered by a0 (lanes share a reference), the
 // long sub-blocks above them with the walkers ordered by their local time (lanes share table rows:
@@ -1641,10 +1678,20 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
     double* s_coef = s_c + (size_t)blocks_per_chunk * NPH * TAB_NTP;
     double* s_wt = s_coef + (TAB_COEF_SMEM ? TAB_CROWS(ND) : 0) * CTA_THREADS + (size_t)(threadIdx.x / WARP) * WARP * TAB_WPITCH;
     unsigned char* s_warp = reinterpret_cast<unsigned char*>(s_coef + ((TAB_COEF_SMEM ? TAB_CROWS(ND) : 0) + TAB_WPITCH) * CTA_THREADS)
-                          + (size_t)(threadIdx.x / WARP) * ND * TAB_SPAN * TAB_ROWB;
+                          + (size_t)(threadIdx.x / WARP) * TAB_STAGE_BYTES(ND);
     if (!FINE)
         for (int i = threadIdx.x; i < (b1 - b0) * NPH * TAB_NTP; i += CTA_THREADS)
             s_c[i] = cmat[(size_t)b0 * NPH * TAB_NTP + i];
+#if TAB_DMMA
+    // dense weight matrix [window row][lane] of the tensor-core product: zero outside the lanes' windows
+    for (int j = 0; j < TAB_SPAN; ++j) s_wt[j * TAB_WDP + (threadIdx.x & (WARP - 1))] = 0.0;
+    int off_prev = -1;
+#endif
+#if TAB_DMMA && !TAB_BGLOBAL
+    // staged rows past a window's end meet zero weights in the tensor-core product: they must hold numbers
+    for (int i = threadIdx.x & (WARP - 1); i < ND * TAB_SPAN * TAB_ROWB / 16; i += WARP)
+        reinterpret_cast<double2*>(s_warp)[i] = make_double2(0.0, 0.0);
+#endif
     // per-thread coefficients live in shared memory (one column per thread, no sharing): they are needed
     // once per sub-block, and keeping them out of the register file keeps the tap loop from spilling
 #if TAB_COEF_SMEM
@@ -1764,17 +1811,13 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
                 __syncwarp();                           // the previous pass's rows have been read
 #pragma unroll
                 for (int d = 0; d < ND; ++d) {
-                    int mn = mine ? gs[d] : 0x7fffffff, mx = mine ? gs[d] : -1;
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) {
-                        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-                        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                    }
+                    const int mn = __reduce_min_sync(0xffffffffu, mine ? gs[d] : 0x7fffffff);
+                    const int mx = __reduce_max_sync(0xffffffffu, mine ? gs[d] : -1);
                     lo[d] = mn;
                     const int span = mx - mn + TAB_W;
                     span_d[d] = span;
                     staged[d] = span <= TAB_SPAN;
-                    if (staged[d]) {
+                    if (staged[d] && !(TAB_DMMA && TAB_BGLOBAL)) {
                         const double2* src = row0 + (((size_t)rL * ND + d) * (L + TAB_W) + mn) * TAB_NM;
                         const uint32_t dst = smem_u32(s_warp + (size_t)d * TAB_SPAN * TAB_ROWB);
                         for (int pc16 = lane; pc16 < span * TAB_NM; pc16 += WARP) {
@@ -1785,7 +1828,7 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
                     }
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
-                bool waited = false;
+                [[maybe_unused]] bool waited = false;
 #pragma unroll
                 for (int d = 0; d < ND; ++d) {
                     double2 Mn[TAB_NM];
@@ -1794,9 +1837,122 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
                     const double v = xs[d];
                     // kernel weights: per pair of mirror taps an even and an odd Horner chain in v^2,
                     // v = 2 (x - g0) - (W - 1); coefficients as literal constants (no loads)
+#if TAB_DMMA && TAB_BGLOBAL
+                    // B fragments of all steps, straight from the table (rows shared by the warp's lanes and by
+                    // the neighbouring warps: L1 / L2 hits): in flight while the weights are evaluated.  Rows past
+                    // the window's end are table rows too (the allocation is padded) and meet zero weights.
+                    double bf[TAB_SPAN / 4][2];
+                    if (staged[d]) {
+                        const double* pbg = reinterpret_cast<const double*>(row0 + (((size_t)rL * ND + d) * (L + TAB_W) + lo[d]) * TAB_NM)
+                                          + (lane & 3) * (2 * TAB_NM) + (lane >> 2);
+                        const int nks_ = (span_d[d] + 3) >> 2;
+#pragma unroll
+                        for (int ks = 0; ks < TAB_SPAN / 4; ++ks) {
+                            const int kr = min(ks, nks_ - 1) * 4 * (2 * TAB_NM);
+                            bf[ks][0] = __ldg(pbg + kr); bf[ks][1] = __ldg(pbg + kr + 8);
+                        }
+                    }
+#endif
                     double wt[TAB_W];
                     TAB_WEIGHTS(v, wt);
                     if (staged[d]) {
+#if TAB_DMMA
+                        // M[lane][c] = sum_j Wd[j][lane] R[j][c] over the window rows j (span = 13 + the spread of
+                        // the lanes' first rows, padded to a multiple of 4; Wd holds a lane's 13 weights at its
+                        // own rows and zeros elsewhere; R = the staged rows, 16 reals each): a 32 x K x 16 product
+                        // on the FP64 tensor cores -- 4 x 2 accumulator tiles of mma.m8n8k4, K / 4 steps.  The
+                        // pipe does the same multiply-adds as the DFMA form at its full rate, from 6 shared-memory
+                        // loads per step instead of 9 per row, and 8 instructions per step instead of 16 per row.
+                        const int nks = (span_d[d] + 3) >> 2;
+                        double* wd = s_wt;                               // [TAB_SPAN][TAB_WDP]
+                        double* md = s_wt + (TAB_MD_ALIAS ? 0 : TAB_SPAN * TAB_WDP);     // [32][2 TAB_NM], 16-byte units swizzled
+                        // A lane's column holds its 13 weights at the rows of its window and zeros everywhere else:
+                        // only the rows of the previous window that the new one does not cover are cleared.
+                        // (The previous detector's A fragments were all loaded before its lanes passed the
+                        //  __syncwarp ahead of their moment reads.)
+                        const int off = mine ? gs[d] - lo[d] : -2 * TAB_W;
+                        if (off_prev >= 0) {
+                            const int nz = min(abs(off - off_prev), TAB_W);
+                            const int z0 = off > off_prev ? off_prev : off_prev + TAB_W - nz;
+                            for (int z = 0; z < nz; ++z) wd[(z0 + z) * TAB_WDP + lane] = 0.0;
+                        }
+                        if (mine) {
+#pragma unroll
+                            for (int i = 0; i < TAB_W; ++i) wd[(off + i) * TAB_WDP + lane] = wt[i];
+                        }
+                        off_prev = mine ? off : -1;
+#if !TAB_BGLOBAL
+                        if (!waited) {                   // the weights above overlapped the copies
+                            asm volatile("cp.async.wait_group 0;" ::: "memory");
+                            waited = true;
+                        }
+#endif
+                        __syncwarp();
+                        const int l4 = lane & 3, g8 = lane >> 2;
+                        const double* pa = wd + l4 * TAB_WDP + g8;
+                        double cf[4][2][2];
+#pragma unroll
+                        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                            for (int nt = 0; nt < 2; ++nt) cf[mt][nt][0] = cf[mt][nt][1] = 0.0;
+#if TAB_BGLOBAL
+#pragma unroll
+                        for (int ks = 0; ks < TAB_SPAN / 4; ++ks) {
+                            if (ks < nks) {
+                                double fa[4];
+#pragma unroll
+                                for (int mt = 0; mt < 4; ++mt) fa[mt] = pa[ks * 4 * TAB_WDP + 8 * mt];
+#pragma unroll
+                                for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                                    for (int nt = 0; nt < 2; ++nt) dmma884(cf[mt][nt], fa[mt], bf[ks][nt]);
+                            }
+                        }
+#else
+                        const double* pb = reinterpret_cast<const double*>(s_warp + (size_t)d * TAB_SPAN * TAB_ROWB)
+                                         + l4 * (TAB_ROWB / 8) + g8;
+                        double fa[4], fb[2];
+#pragma unroll
+                        for (int mt = 0; mt < 4; ++mt) fa[mt] = pa[8 * mt];
+                        fb[0] = pb[0]; fb[1] = pb[8];
+                        for (int ks = 0; ks < nks; ++ks) {
+                            // next step's fragments (the last step re-reads its own)
+                            const int kn = min(ks + 1, nks - 1) * 4;
+                            double na[4], nb[2];
+#pragma unroll
+                            for (int mt = 0; mt < 4; ++mt) na[mt] = pa[kn * TAB_WDP + 8 * mt];
+                            nb[0] = pb[kn * (TAB_ROWB / 8)]; nb[1] = pb[kn * (TAB_ROWB / 8) + 8];
+#pragma unroll
+                            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                                for (int nt = 0; nt < 2; ++nt) dmma884(cf[mt][nt], fa[mt], fb[nt]);
+#pragma unroll
+                            for (int mt = 0; mt < 4; ++mt) fa[mt] = na[mt];
+                            fb[0] = nb[0]; fb[1] = nb[1];
+                        }
+#endif
+                        // accumulator tile (mt, nt): walker 8 mt + lane / 4, complex moment 4 nt + lane % 4.  Through
+                        // shared memory to the walker's own lane; unit (n + f(walker)) mod 8 of the walker's 128-byte
+                        // row, f = 4 (w & 1) + ((w >> 1) & 3): conflict-free 128-bit stores and loads.
+                        if (TAB_MD_ALIAS) __syncwarp();
+#pragma unroll
+                        for (int mt = 0; mt < 4; ++mt) {
+                            const int wk = 8 * mt + g8;
+                            const int fw = 4 * (wk & 1) + ((wk >> 1) & 3);
+#pragma unroll
+                            for (int nt = 0; nt < 2; ++nt)
+                                *reinterpret_cast<double2*>(md + wk * (2 * TAB_NM) + 2 * ((4 * nt + l4 + fw) & 7)) =
+                                    make_double2(cf[mt][nt][0], cf[mt][nt][1]);
+                        }
+                        __syncwarp();
+                        {
+                            const int fw = 4 * (lane & 1) + ((lane >> 1) & 3);
+#pragma unroll
+                            for (int n = 0; n < TAB_NM; ++n)
+                                Mn[n] = *reinterpret_cast<const double2*>(md + lane * (2 * TAB_NM) + 2 * ((n + fw) & 7));
+                        }
+                        if (TAB_MD_ALIAS) __syncwarp();
+#else
                         // The staged rows are a window of span = 13 + (spread of the lanes' first rows) rows.
                         // The warp walks the window row by row: the table row is read with warp-uniform
                         // 128-bit loads (one shared-memory wavefront each, whatever the spread) and every
@@ -1826,6 +1982,7 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
                                 Mn[n].y = fma(w, q.y, Mn[n].y);
                             }
                         }
+#endif
                     } else if (mine) {                   // lanes too far apart in time: every lane its own rows, from L2
                         // rows are padded with TAB_W wrap-around points: the taps are contiguous
                         const double2* rd = row0 + (((size_t)rL * ND + d) * (L + TAB_W) + gs[d]) * TAB_NM;
@@ -2204,10 +2361,6 @@ __global__ void generate_len_kernel(PlanDev P, const double* __restrict__ params
 // reads three registers no neighbouring instruction reads (no reuse-cache help); variant 2:
 // the hot loop's own pattern, 4 independent unit-phasor complex multiplications per step
 // (2 DMUL + 2 DFMA each).
-__device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-                 : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
-}
 template <int VARIANT>
 __global__ void dfma_probe_kernel(double* out, int iters) {
     const double t0 = threadIdx.x * 1e-9;
@@ -2664,7 +2817,7 @@ static int build_tables(gwin_plan* p) {
         CK(cudaMalloc(&d_pair_seg, sizeof(long long) * n_pairs));
         CK(cudaMalloc(&d_invhat, sizeof(double) * invhat.size()));
         CK(cudaMalloc(&d_refcoef, sizeof(double) * (size_t)n_pairs * NPH));
-        if (cudaMalloc(&p->d_tab, (size_t)bytes) != cudaSuccess ||
+        if (cudaMalloc(&p->d_tab, (size_t)bytes + 1024) != cudaSuccess ||       // (+ the rows a padded window may touch)
             cudaMalloc(&d_seg, sizeof(double2) * (size_t)seg_total) != cudaSuccess) {
             cudaGetLastError();                           // not enough device memory: no tables
             return 1;
@@ -2915,6 +3068,15 @@ extern "C" void gwin_plan_destroy(gwin_plan* p) {
     cudaFree(p->d_params); cudaFree(p->d_out); cudaFree(p->d_skip); cudaFree(p->d_points);
     cudaFreeHost(p->h_params); cudaFreeHost(p->h_out); cudaFreeHost(p->h_skip);
     if (p->timing) { cudaEventDestroy(p->ev0); cudaEventDestroy(p->ev1); for (cudaEvent_t e : p->evd) cudaEventDestroy(e); }
+    if (p->async_ready) {
+        for (int i = 0; i < 2; ++i) {
+            gwin_plan::AsyncSlot& a = p->aslot[i];
+            cudaFree(a.d_points); cudaFree(a.d_params); cudaFree(a.d_out); cudaFree(a.d_skip);
+            cudaFreeHost(a.h_points); cudaFreeHost(a.h_out); cudaFreeHost(a.h_skip);
+            cudaEventDestroy(a.ev_in); cudaEventDestroy(a.ev_k); cudaEventDestroy(a.ev_out);
+        }
+        cudaStreamDestroy(p->stream_in); cudaStreamDestroy(p->stream_out);
+    }
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
 }
@@ -3288,7 +3450,7 @@ static void launch_table(gwin_plan* p, int W, int wpad, int per_chunk, int blk_l
     if (!fine && blk_hi <= blk_lo) return;
     dim3 grid((W + CTA_THREADS - 1) / CTA_THREADS, fine ? slots : (blk_hi - blk_lo + per_chunk - 1) / per_chunk);
     const int fixed = ((TAB_COEF_SMEM ? TAB_CROWS(ND) : 0) + TAB_WPITCH) * CTA_THREADS * (int)sizeof(double)
-                    + (CTA_THREADS / WARP) * ND * TAB_SPAN * TAB_ROWB;
+                    + (CTA_THREADS / WARP) * TAB_STAGE_BYTES(ND);
     const int smem = (fine ? 0 : per_chunk) * NPH * TAB_NTP * (int)sizeof(double) + fixed;
     static bool attr_set_dev[64] = {};
     if (!attr_set_dev[p->device & 63]) {
@@ -3890,6 +4052,152 @@ extern "C" int gwin_loglr_batch_points_host(gwin_plan* p, int mode, int64_t W,
     if (!direct_out) memcpy(loglr, h_lr, sizeof(double) * W);
     if (hd) memcpy(hd, h_hd, sizeof(double) * 2 * nd * W);
     if (hh) memcpy(hh, h_hh, sizeof(double) * nd * W);
+    return GWIN_OK;
+}
+
+// ---- asynchronous host entry -------------------------------------------------------------------
+static int async_setup(gwin_plan* p) {
+    if (p->async_ready) return GWIN_OK;
+    memset(p->aslot, 0, sizeof p->aslot);
+    CK(cudaStreamCreateWithFlags(&p->stream_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&p->stream_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaEventCreateWithFlags(&p->aslot[i].ev_in, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&p->aslot[i].ev_k, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&p->aslot[i].ev_out, cudaEventDisableTiming));
+    }
+    p->async_ready = true;
+    return GWIN_OK;
+}
+
+static int async_stage(gwin_plan* p, gwin_plan::AsyncSlot& a, int64_t W) {
+    if (W <= a.cap) return GWIN_OK;
+    const int nd = p->d.n_det;
+    const int64_t cap = std::max<int64_t>(W, 1024);
+    const size_t out_row = 1 + 3 * (size_t)nd;
+    // (the slot is idle: its previous call has been waited for; cudaFree orders itself after queued work)
+    cudaFree(a.d_points); cudaFree(a.d_params); cudaFree(a.d_out); cudaFree(a.d_skip);
+    cudaFreeHost(a.h_points); cudaFreeHost(a.h_out); cudaFreeHost(a.h_skip);
+    a.d_points = a.d_params = a.d_out = a.h_points = a.h_out = nullptr; a.d_skip = a.h_skip = nullptr; a.cap = 0;
+    CK(cudaMalloc(&a.d_points, sizeof(double) * GWIN_NPARAM * cap));
+    CK(cudaMalloc(&a.d_params, sizeof(double) * GWIN_NPARAM * cap));
+    CK(cudaMalloc(&a.d_out, sizeof(double) * out_row * cap));
+    CK(cudaMalloc(&a.d_skip, cap));
+    CK(cudaMallocHost(&a.h_points, sizeof(double) * GWIN_NPARAM * cap));
+    CK(cudaMallocHost(&a.h_out, sizeof(double) * (out_row * cap + 2)));
+    CK(cudaMallocHost(&a.h_skip, cap));
+    a.cap = cap;
+    return GWIN_OK;
+}
+
+extern "C" int gwin_loglr_batch_points_submit(gwin_plan* p, int mode, int64_t W,
+                                              const double* points, int ndim, int64_t stride_walker, int64_t stride_col,
+                                              const int* map, const double* fixed, const uint8_t* skip,
+                                              double* loglr, double* hd, double* hh, int* ticket) {
+    if (!p) return fail(GWIN_EINVAL, "plan is NULL");
+    if (!ticket) return fail(GWIN_EINVAL, "ticket is NULL");
+    *ticket = -1;
+    if (W <= 0) return fail(GWIN_EINVAL, "W must be positive");
+    if (!map || !fixed || !loglr) return fail(GWIN_EINVAL, "map/fixed/loglr is NULL");
+    if (ndim < 0 || ndim > GWIN_NPARAM) return fail(GWIN_EINVAL, "ndim must be 0..%d", GWIN_NPARAM);
+    if (ndim > 0 && !points) return fail(GWIN_EINVAL, "points is NULL");
+    if (ndim > 0 && !((stride_walker == ndim && stride_col == 1) || (stride_walker == 1 && stride_col == W)))
+        return fail(GWIN_EINVAL, "host points must be a dense [W][ndim] or [ndim][W] block");
+    PointMap M;
+    for (int i = 0; i < GWIN_NPARAM; ++i) {
+        if (map[i] >= ndim) return fail(GWIN_EINVAL, "map[%d] = %d is not a column of the points", i, map[i]);
+        M.col[i] = map[i] < 0 ? -1 : map[i];
+        M.fixed[i] = fixed[i];
+    }
+    CK(cudaSetDevice(p->device));
+    int rc = async_setup(p);
+    if (rc) return rc;
+    const int s = !p->aslot[0].busy ? 0 : (!p->aslot[1].busy ? 1 : -1);
+    if (s < 0) return fail(GWIN_EINVAL, "two calls are already in flight: gwin_loglr_batch_points_wait for one of them first");
+    gwin_plan::AsyncSlot& a = p->aslot[s];
+    rc = async_stage(p, a, W);
+    if (rc) return rc;
+    const int nd = p->d.n_det;
+    if (ndim > 0) {
+        const double* src = points;
+        if (!host_pinned(points)) {
+            memcpy(a.h_points, points, sizeof(double) * (size_t)ndim * W);
+            src = a.h_points;
+        }
+        CK(cudaMemcpyAsync(a.d_points, src, sizeof(double) * (size_t)ndim * W, cudaMemcpyHostToDevice, p->stream_in));
+    }
+    if (skip) {
+        memcpy(a.h_skip, skip, W);
+        CK(cudaMemcpyAsync(a.d_skip, a.h_skip, W, cudaMemcpyHostToDevice, p->stream_in));
+    }
+    CK(cudaEventRecord(a.ev_in, p->stream_in));
+    cudaStream_t st = p->stream;
+    CK(cudaStreamWaitEvent(st, a.ev_in, 0));
+    expand_points_kernel<<<(int)((W + 127) / 128), 128, 0, st>>>((int)W, a.d_points, stride_walker, stride_col, M, a.d_params);
+    const bool table = p->kernel != GWIN_KERNEL_DIRECT && table_wanted(p, W, false);
+    if (p->auto_mchirp && p->kernel != GWIN_KERNEL_DIRECT && !table) {
+        const int c1 = M.col[0], c2 = M.col[1];
+        double mc5_min = 1e300;
+        for (int64_t i = 0; i < W; ++i) {
+            if (skip && skip[i]) continue;
+            const double m1 = c1 >= 0 ? points[i * stride_walker + c1 * stride_col] : M.fixed[0];
+            const double m2 = c2 >= 0 ? points[i * stride_walker + c2 * stride_col] : M.fixed[1];
+            if (!(m1 > 0.0) || !(m2 > 0.0) || !std::isfinite(m1 + m2)) continue;
+            const double pm = m1 * m2;
+            mc5_min = std::min(mc5_min, pm * pm * pm / (m1 + m2));
+            if (c1 < 0 && c2 < 0) break;
+        }
+        if (mc5_min < 1e300) {
+            const double mc_min = std::min(std::max(std::pow(mc5_min, 0.2), 0.02), 1e4);
+            const double q = std::exp2(std::floor(4.0 * std::log2(mc_min)) / 4.0);
+            if (q != p->mchirp_min) { p->mchirp_min = q; p->sched_dirty = true; }
+        }
+    }
+    double* d_lr = a.d_out;
+    double* d_hd = a.d_out + a.cap;
+    double* d_hh = d_hd + 2 * (size_t)nd * a.cap;
+    rc = loglr_batch_impl(p, mode, W, a.d_params, 1, W, nullptr, 0, 0, skip ? a.d_skip : nullptr,
+                          d_lr, hd ? d_hd : nullptr, hh ? d_hh : nullptr, st);
+    if (rc) return rc;
+    p->last_launches += 1;
+    int* h_slow = reinterpret_cast<int*>(a.h_out + (1 + 3 * (size_t)nd) * a.cap);
+    *h_slow = 0;
+    // (this batch's slow-path count: read on the compute stream, before the next batch's kernels reset it)
+    if (p->kernel != GWIN_KERNEL_DIRECT) CK(cudaMemcpyAsync(h_slow, p->d_slow_n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(a.ev_k, st));
+    cudaStream_t so = p->stream_out;
+    CK(cudaStreamWaitEvent(so, a.ev_k, 0));
+    double* h_lr = a.h_out;
+    double* h_hd = a.h_out + a.cap;
+    double* h_hh = h_hd + 2 * (size_t)nd * a.cap;
+    a.direct_out = host_pinned(loglr);
+    CK(cudaMemcpyAsync(a.direct_out ? loglr : h_lr, d_lr, sizeof(double) * W, cudaMemcpyDeviceToHost, so));
+    if (hd) CK(cudaMemcpyAsync(h_hd, d_hd, sizeof(double) * 2 * nd * W, cudaMemcpyDeviceToHost, so));
+    if (hh) CK(cudaMemcpyAsync(h_hh, d_hh, sizeof(double) * nd * W, cudaMemcpyDeviceToHost, so));
+    CK(cudaEventRecord(a.ev_out, so));
+    a.busy = true; a.table = table; a.W = W; a.loglr = loglr; a.hd = hd; a.hh = hh;
+    *ticket = s;
+    return GWIN_OK;
+}
+
+extern "C" int gwin_loglr_batch_points_wait(gwin_plan* p, int ticket) {
+    if (!p) return fail(GWIN_EINVAL, "plan is NULL");
+    if (ticket < 0 || ticket > 1 || !p->async_ready || !p->aslot[ticket].busy)
+        return fail(GWIN_EINVAL, "no call in flight with ticket %d", ticket);
+    gwin_plan::AsyncSlot& a = p->aslot[ticket];
+    CK(cudaSetDevice(p->device));
+    CK(cudaEventSynchronize(a.ev_out));
+    a.busy = false;
+    const int nd = p->d.n_det;
+    const int64_t W = a.W;
+    const double* h_lr = a.h_out;
+    const double* h_hd = a.h_out + a.cap;
+    const double* h_hh = h_hd + 2 * (size_t)nd * a.cap;
+    const int* h_slow = reinterpret_cast<const int*>(a.h_out + (1 + 3 * (size_t)nd) * a.cap);
+    if (*h_slow > 4 + W / 64 && !p->cover_manual && a.table) p->replan = true;
+    if (!a.direct_out) memcpy(a.loglr, h_lr, sizeof(double) * W);
+    if (a.hd) memcpy(a.hd, h_hd, sizeof(double) * 2 * nd * W);
+    if (a.hh) memcpy(a.hh, h_hh, sizeof(double) * nd * W);
     return GWIN_OK;
 }
 

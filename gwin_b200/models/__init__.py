@@ -51,6 +51,12 @@ class CallModel(object):
         return self.model.evaluate_batch(points, callstat=callstat or self.callstat,
                                          with_stats=self.return_all_stats)
 
+    def batch_async(self, points, callstat=None):
+        """``batch`` that only queues the evaluation: returns a handle whose ``result()`` is the
+        ``BatchResult``.  Up to two may be pending per model (``gwin_loglr_batch_points_submit``)."""
+        return self.model.evaluate_batch(points, callstat=callstat or self.callstat,
+                                         with_stats=self.return_all_stats, defer=True)
+
 
 models = {_cls.name: _cls for _cls in (
     TestNormal,

@@ -116,6 +116,26 @@ class BatchResult(object):
         return list(zip(vals, blobs))
 
 
+class Deferred(object):
+    """What ``_batch_callstat`` returns for a queued evaluation: ``finish()`` waits for it and
+    returns the ``(values, stats)`` pair the synchronous form returns."""
+
+    def __init__(self, finish):
+        self.finish = finish
+
+
+class PendingBatch(object):
+    """Handle of ``evaluate_batch(..., defer=True)`` / ``CallModel.batch_async``."""
+
+    def __init__(self, finish):
+        self._finish, self._res = finish, None
+
+    def result(self):
+        if self._finish is not None:
+            self._res, self._finish = self._finish(), None
+        return self._res
+
+
 class BaseModel(object, metaclass=ABCMeta):
     name = None
 
@@ -282,7 +302,7 @@ class BaseModel(object, metaclass=ABCMeta):
             out[i] = self.loglikelihood
         return out, OrderedDict()
 
-    def evaluate_batch(self, points, callstat='logposterior', with_stats=True):
+    def evaluate_batch(self, points, callstat='logposterior', with_stats=True, defer=False):
         """Evaluate ``callstat`` for W points given in ``sampling_params`` order.
 
         Returns a ``BatchResult`` whose ``stats`` are materialised on first use.
@@ -293,6 +313,9 @@ class BaseModel(object, metaclass=ABCMeta):
         ``with_stats=False`` tells the model that only ``values`` will be read (the
         per-detector statistics are then not brought back from the device; asking
         for them anyway evaluates the batch again).
+        ``defer=True`` returns a ``PendingBatch`` at once -- a model with a device behind it has only
+        queued the work (copies in, kernels, copies out) -- whose ``result()`` is the ``BatchResult``;
+        a caller with several batches keeps two in flight so that one's copies overlap the other's kernels.
         """
         points = numpy.asarray(points, dtype=numpy.float64)
         if points.ndim == 1:
@@ -313,19 +336,26 @@ class BaseModel(object, metaclass=ABCMeta):
             stats['logjacobian'] = logj
             stats['logprior'] = logp
         all_names = list(self.default_stats)
-        if callstat == 'logprior':
-            return BatchResult(logp, stats, all_names)
-        if callstat == 'logjacobian':
-            return BatchResult(stats['logjacobian'], stats, all_names)
+        if callstat in ('logprior', 'logjacobian'):
+            res = BatchResult(logp if callstat == 'logprior' else stats['logjacobian'], stats, all_names)
+            return PendingBatch(lambda: res) if defer else res
         skip = None
         if callstat in ('logposterior', 'logplr'):
             skip = numpy.isneginf(logp)
         # hints for models that can hand the sampled columns to a kernel as they are
-        self._batch_hint = (points, samples, bool(with_stats))
+        self._batch_hint = (points, samples, bool(with_stats), bool(defer))
         try:
-            values, more = self._batch_callstat(callstat, params, W, skip, logp, stats)
+            out = self._batch_callstat(callstat, params, W, skip, logp, stats)
         finally:
             self._batch_hint = None
+        if isinstance(out, Deferred):
+            return PendingBatch(lambda: self._wrap_batch(out.finish(), stats, all_names))
+        res = self._wrap_batch(out, stats, all_names)
+        return PendingBatch(lambda: res) if defer else res
+
+    @staticmethod
+    def _wrap_batch(out, stats, all_names):
+        values, more = out
         if callable(more):
             base = stats
 

@@ -16,6 +16,7 @@ import numpy
 from .. import _lib
 from ..calibration import spline_frequencies, values_matrix
 from ..waveform import WAVEFORM_PARAMS, check_waveform_params, param_rows
+from .base import Deferred
 from .base_data import BaseDataModel
 
 
@@ -132,7 +133,7 @@ class GaussianNoise(BaseDataModel):
         static.update(self._static_params)
         return static
 
-    def _kernel_call(self, params, W, skip=None, stats=True):
+    def _kernel_call(self, params, W, skip=None, stats=True, defer=False):
         """One launch for W points.  The kernel's 13-parameter rows are assembled on the device
         (``gwin_loglr_batch_points_host``): when the sampled columns reach the waveform unchanged
         -- no transforms, no boundary condition touched them -- the sampler's own ``points`` array
@@ -146,6 +147,7 @@ class GaussianNoise(BaseDataModel):
                                          param_major=True, calib=calib)
         hint = getattr(self, '_batch_hint', None)
         points, samples = (hint[0], hint[1]) if hint is not None else (None, {})
+        defer = bool(defer and hint is not None)
         colmap = numpy.full(len(WAVEFORM_PARAMS), -1, dtype=numpy.int32)
         fixed = numpy.zeros(len(WAVEFORM_PARAMS))
         varying = []
@@ -164,7 +166,15 @@ class GaussianNoise(BaseDataModel):
             for i, name in varying:
                 colmap[i] = order[name]
             return self._plan.loglr_points_host(points, colmap, fixed, mode=self._mode,
-                                                skip=skip, stats=stats)
+                                                skip=skip, stats=stats, defer=defer)
+        if defer:
+            # a deferred call keeps its (page-locked) rows until it has been waited for
+            rows = _lib.pinned_empty((len(varying), W))
+            for j, (i, name) in enumerate(varying):
+                rows[j] = params[name]
+                colmap[i] = j
+            return self._plan.loglr_points_host(rows, colmap, fixed, mode=self._mode,
+                                                skip=skip, stats=stats, col_major=True, defer=True)
         key = (len(varying), W)
         if getattr(self, '_rows_key', None) != key:
             self._rows_key, self._rows = key, _lib.pinned_empty(key)
@@ -226,7 +236,15 @@ class GaussianNoise(BaseDataModel):
             raise ValueError("unsupported callstat %r" % callstat)
         hint = getattr(self, '_batch_hint', None)
         want = hint[2] if hint is not None else True
-        lr, hd, hh = self._kernel_call(params, W, skip=skip, stats=want)
+        defer = bool(hint[3]) if hint is not None and len(hint) > 3 else False
+        res = self._kernel_call(params, W, skip=skip, stats=want, defer=defer)
+        if defer and not isinstance(res, tuple):
+            # queued: the rest runs when the caller asks for the result
+            return Deferred(lambda: self._finish_callstat(callstat, params, W, skip, logp, res.wait()))
+        return self._finish_callstat(callstat, params, W, skip, logp, res)
+
+    def _finish_callstat(self, callstat, params, W, skip, logp, res):
+        lr, hd, hh = res
         lognl = self.lognl
         logl = lr + lognl
         held = {'hd': hd, 'hh': hh}

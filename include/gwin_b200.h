@@ -211,6 +211,20 @@ int gwin_loglr_batch_points_host(gwin_plan* plan, int mode, int64_t W,
                                  const double* points, int ndim, int64_t stride_walker, int64_t stride_col,
                                  const int* map, const double* fixed, const uint8_t* skip,
                                  double* loglr, double* hd, double* hh);
+/*
+ * The same call in two halves, for callers with more than one batch to evaluate (the halves of a
+ * parallel-tempered ensemble, several independent ensembles, pool.map over chunks): _submit queues the
+ * host-to-device copy, the kernels and the copy back and returns at once with a ticket; _wait blocks until
+ * that call's results are in loglr / hd / hh.  Two calls may be in flight per plan: the copies of one
+ * overlap the kernels of the other (separate copy streams, separate staging).  points / skip may be reused
+ * as soon as _submit returns unless points is page-locked (then it is read until the copy has run: keep it
+ * unchanged until _wait); loglr / hd / hh must stay valid until _wait.  Tickets are 0 and 1.
+ */
+int gwin_loglr_batch_points_submit(gwin_plan* plan, int mode, int64_t W,
+                                   const double* points, int ndim, int64_t stride_walker, int64_t stride_col,
+                                   const int* map, const double* fixed, const uint8_t* skip,
+                                   double* loglr, double* hd, double* hh, int* ticket);
+int gwin_loglr_batch_points_wait(gwin_plan* plan, int ticket);
 /* Page-locked host memory for the buffers of the host entry points. */
 int gwin_host_alloc(void** ptr, size_t bytes);
 void gwin_host_free(void* ptr);

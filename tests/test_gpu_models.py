@@ -335,3 +335,54 @@ def test_calibrated_model_and_generator(cfg):
         gen2.generate(**q)
     with pytest.raises(ValueError):        # outside the regime the spline fit is a cubic in
         calibration.values_matrix(rec, cfg.dets, dict(zip(names, np.full(len(names), 1.5))), 1)
+
+
+def test_batch_async_two_calls_in_flight(cfg):
+    """CallModel.batch_async (gwin_loglr_batch_points_submit / _wait): queued evaluations give
+    the numbers of the synchronous call bit for bit, two may be pending, a third is refused."""
+    import gwin_b200
+    names = ['tc', 'distance', 'inclination', 'mass1']
+    prior = D.JointDistribution(
+        names, D.Uniform(tc=(cfg.inj['tc'] - 0.05, cfg.inj['tc'] + 0.05)),
+        D.UniformRadius(distance=(100., 1000.)), D.SinAngle(inclination=None), D.Uniform(mass1=(20., 40.)))
+    static = {k: v for k, v in cfg.inj.items() if k not in names}
+    model = cfg.cuda_model(variable_params=tuple(names), static_params=static, prior=prior)
+    rng = np.random.default_rng(11)
+    A = np.column_stack([cfg.inj['tc'] + rng.uniform(-0.06, 0.06, 300), rng.uniform(100., 1000., 300),
+                         np.arccos(rng.uniform(-1, 1, 300)), rng.uniform(20., 40., 300)])
+    B = A[::-1][:200].copy()
+    Ap = gwin_b200.pinned_empty(A.shape)
+    Ap[:] = A
+    for stat, all_stats in (('logposterior', True), ('loglr', False), ('logplr', True)):
+        call = models.CallModel(model, stat, return_all_stats=all_stats)
+        ra, rb = call.batch(A), call.batch(B)
+        pa = call.batch_async(Ap)                 # page-locked points: copied from directly
+        pb = call.batch_async(B)                  # pageable: through the slot's staging buffer
+        with pytest.raises(ValueError):
+            call.batch_async(A)                   # both slots busy (GWIN_EINVAL)
+        qb, qa = pb.result(), pa.result()         # any order
+        np.testing.assert_array_equal(qa.values, ra.values)
+        np.testing.assert_array_equal(qb.values, rb.values)
+        if all_stats:
+            for k in ra.stats:
+                np.testing.assert_array_equal(qa.stats[k], ra.stats[k])
+        assert np.isneginf(ra.values).any() or stat == 'loglr'      # some points outside the prior (skipped)
+    # a longer pipeline: results stay matched to their submissions
+    call = models.CallModel(model, 'loglr', return_all_stats=False)
+    batches = [A[i:i + 64] for i in range(0, 256, 64)]
+    ref = [call.batch(b).values for b in batches]
+    pend, got = None, []
+    for b in batches:
+        nxt = call.batch_async(b)
+        if pend is not None:
+            got.append(pend.result().values)
+        pend = nxt
+    got.append(pend.result().values)
+    for g, r in zip(got, ref):
+        np.testing.assert_array_equal(g, r)
+    # a handle dropped without result(): its slot is released
+    call.batch_async(A)
+    call.batch_async(B)
+    import gc
+    gc.collect()
+    np.testing.assert_array_equal(call.batch_async(A).result().values, call.batch(A).values)
