@@ -1651,7 +1651,7 @@ __global__ void cover_stats_kernel(PlanDev P, int W, const double* __restrict__ 
 #ifndef TABLE_FINE_CTAS
 #define TABLE_FINE_CTAS TABLE_MIN_CTAS
 #endif
-template <int ND, bool FINE>
+template <int ND, bool FINE, bool CALIB>
 __global__ void __launch_bounds__(CTA_THREADS, FINE ? TABLE_FINE_CTAS : TABLE_MIN_CTAS)
 loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo, int blk_hi,
                    const TabBlk* __restrict__ blks, const double* __restrict__ cmat,
@@ -1756,19 +1756,24 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
             double2 en[TAB_DEG + 3];
             en[0] = make_double2(1.0, 0.0);
             en[1] = make_double2(0.0, 0.0);
+            if (!CALIB) {
 #pragma unroll
-            for (int n = 2; n <= TAB_DEG + 2; ++n) {
-                double re = 0.0, im = 0.0;
+                for (int n = 2; n <= TAB_DEG + 2; ++n) {
+                    double re = 0.0, im = 0.0;
 #pragma unroll
-                for (int k = 2; k <= TAB_DEG; ++k) {
-                    if (k <= n) {
-                        re = fma(-kw[k], en[n - k].y, re);
-                        im = fma(kw[k], en[n - k].x, im);
+                    for (int k = 2; k <= TAB_DEG; ++k) {
+                        if (k <= n) {
+                            re = fma(-kw[k], en[n - k].y, re);
+                            im = fma(kw[k], en[n - k].x, im);
+                        }
                     }
+                    en[n] = make_double2(re * (1.0 / n), im * (1.0 / n));
                 }
-                en[n] = make_double2(re * (1.0 / n), im * (1.0 / n));
             }
-            {
+            if (CALIB) {
+                // (the series is per detector: see the detector loop; here only the phase's own bound)
+                if (act && G_TWOPI * rho > TAB_RHO_MAX) { slow[col] = 1; dead = true; act = false; }
+            } else {
                 // what the degree-TAB_DEG polynomial leaves out at the sub-block's edge: e_9, e_10, and
                 // the phase's own ninth/tenth-order terms (a power law's Taylor coefficients fall off by
                 // less than 1.2 eps per order)
@@ -1853,6 +1858,77 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
                         }
                     }
 #endif
+                    double2 cfac = make_double2(1.0, 0.0);
+                    if (CALIB) {
+                        // Calibrated template (gwin/calibration.py:142-173): h_d is multiplied by c_d(f) = exp(L_d),
+                        // L_d = log(1 + dA_d) + 2 i atan(dphi_d / 2), dA_d and dphi_d cubics in z (walker_setup).  On the
+                        // sub-block z = z_c + eps s: c_d = c_d(z_c) exp(sum_{n>=1} L_n s^n); the L_n (Taylor series of
+                        // log(1 + r) and of atan about the centre, by their differential equations -- no transcendental
+                        // function) join the phase's u_n = -2 pi i (t_n - t_n^ref), now with a first-order term, and the
+                        // series e_n of exp(sum u_n s^n) becomes this detector's own.
+                        CalCoef cc;
+                        load_cal_coef(cc, wc + (size_t)(C_DET0 + D_NROW * d) * wpad + col, wpad);
+                        const double zc = fma(kc, P.cal_zs[d], P.cal_z0[d]);
+                        const double ez = h * P.cal_zs[d];
+                        const double A0 = fma(fma(fma(cc.a[3], zc, cc.a[2]), zc, cc.a[1]), zc, cc.a[0]);
+                        const double P0 = fma(fma(fma(cc.p[3], zc, cc.p[2]), zc, cc.p[1]), zc, cc.p[0]);
+                        const double ia = 1.0 / (1.0 + A0);
+                        // r = (dA(z) - dA(z_c)) / (1 + dA(z_c)) and x = dphi(z) / 2, as cubics in s
+                        double rr[4], xx[4];
+                        rr[1] = ez * fma(fma(3.0 * cc.a[3], zc, 2.0 * cc.a[2]), zc, cc.a[1]) * ia;
+                        rr[2] = ez * ez * fma(3.0 * cc.a[3], zc, cc.a[2]) * ia;
+                        rr[3] = ez * ez * ez * cc.a[3] * ia;
+                        xx[0] = 0.5 * P0;
+                        xx[1] = 0.5 * ez * fma(fma(3.0 * cc.p[3], zc, 2.0 * cc.p[2]), zc, cc.p[1]);
+                        xx[2] = 0.5 * ez * ez * fma(3.0 * cc.p[3], zc, cc.p[2]);
+                        xx[3] = 0.5 * ez * ez * ez * cc.p[3];
+                        // f = log(1 + r): (1 + r) f' = r'  ->  n f_n = n r_n - sum_{k<n} (n - k) r_k f_{n-k}
+                        // g = atan(x):    q g' = x', q = 1 + x^2  ->  n q_0 g_n = n x_n - sum_{0<k<n} (n - k) q_k g_{n-k}
+                        double qq[6];
+                        qq[0] = fma(xx[0], xx[0], 1.0);
+                        qq[1] = 2.0 * xx[0] * xx[1];
+                        qq[2] = fma(xx[1], xx[1], 2.0 * xx[0] * xx[2]);
+                        qq[3] = 2.0 * fma(xx[0], xx[3], xx[1] * xx[2]);
+                        qq[4] = fma(xx[2], xx[2], 2.0 * xx[1] * xx[3]);
+                        qq[5] = 2.0 * xx[2] * xx[3];
+                        const double iq = 1.0 / qq[0];
+                        double ff[7], gg[7];
+#pragma unroll
+                        for (int n = 1; n <= 6; ++n) {
+                            double sf = 0.0, sg = 0.0;
+#pragma unroll
+                            for (int k = 1; k < n; ++k) {
+                                if (k <= 3) sf = fma((double)(n - k) * rr[k], ff[n - k], sf);
+                                if (k <= 5) sg = fma((double)(n - k) * qq[k], gg[n - k], sg);
+                            }
+                            ff[n] = (n <= 3 ? rr[n] : 0.0) - sf * (1.0 / n);
+                            gg[n] = ((n <= 3 ? xx[n] : 0.0) - sg * (1.0 / n)) * iq;
+                        }
+                        // k u_k, k = 1 .. 8 (orders past 5 of L_d: below the truncation bound checked here)
+                        double2 ku[TAB_DEG + 1];
+#pragma unroll
+                        for (int k = 1; k <= TAB_DEG; ++k)
+                            ku[k] = make_double2(k <= 5 ? (double)k * ff[k] : 0.0,
+                                                 (k <= 5 ? 2.0 * (double)k * gg[k] : 0.0) + (k >= 2 ? kw[k] : 0.0));
+#pragma unroll
+                        for (int n = 1; n <= TAB_DEG + 2; ++n) {
+                            double2 a2 = make_double2(0.0, 0.0);
+#pragma unroll
+                            for (int k = 1; k <= TAB_DEG; ++k)
+                                if (k <= n) a2 = cfma(ku[k], en[n - k], a2);
+                            en[n] = make_double2(a2.x * (1.0 / n), a2.y * (1.0 / n));
+                        }
+                        const double u8 = fabs(kw[TAB_DEG]) * (1.0 / TAB_DEG);
+                        const double est = fabs(en[TAB_DEG + 1].x) + fabs(en[TAB_DEG + 1].y)
+                                         + fabs(en[TAB_DEG + 2].x) + fabs(en[TAB_DEG + 2].y)
+                                         + 1.2 * B.eps * u8 * (1.0 + 1.2 * B.eps)
+                                         + fabs(ff[6]) + 2.0 * fabs(gg[6]);
+                        // (a detector whose amplitude factor comes near zero, or whose series does not settle: the
+                        //  walker goes down the slow path -- the direct kernel takes any values)
+                        if (mine && (!(1.0 + A0 > 0.25) || !(est <= TAB_EST_MAX))) { slow[col] = 1; dead = true; }
+                        const double P2 = P0 * P0, scf = (1.0 + A0) / (4.0 + P2);
+                        cfac = make_double2(scf * (4.0 - P2), scf * (4.0 * P0));
+                    }
                     double wt[TAB_W];
                     TAB_WEIGHTS(v, wt);
                     if (staged[d]) {
@@ -2001,6 +2077,25 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
                     double2 sum = Mn[0];
 #pragma unroll
                     for (int n = 2; n <= TAB_DEG; ++n) sum = cfma(en[n], Mn[n - 1], sum);
+                    if (CALIB) {
+                        // the first moment is not tabulated: M_1 = (i / 2 pi h) dM_0/dnu = (2 i / pi) sum_i w_i' tab_0[g0 + i],
+                        // w' the derivative of the interpolation weights with respect to the grid coordinate
+                        double dw[TAB_W];
+                        TAB_DWEIGHTS(v, dw);
+                        double2 m1 = make_double2(0.0, 0.0);
+                        if (mine) {
+                            const double2* rd = row0 + (((size_t)rL * ND + d) * (L + TAB_W) + gs[d]) * TAB_NM;
+#pragma unroll
+                            for (int i = 0; i < TAB_W; ++i) {
+                                const double2 q = __ldg(rd + i * TAB_NM);
+                                m1.x = fma(dw[i], q.x, m1.x);
+                                m1.y = fma(dw[i], q.y, m1.y);
+                            }
+                        }
+                        const double c1 = 2.0 / G_PI;
+                        sum = cfma(en[1], make_double2(-c1 * m1.y, c1 * m1.x), sum);
+                        sum = cmul(sum, cfac);
+                    }
                     const double th0 = tq[0] + fma(kc, TCOEF(NPH + 2 * d + 1), frac1(kc * TCOEF(NPH + 2 * d)));
                     if (mine) acc[d] = cfma(sum, phasor_neg(th0), acc[d]);
                 }
@@ -2053,6 +2148,11 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
                 // (branch-free, so that the loads of several bins are in flight at once: every lane walks its
                 //  own bins, nothing is coalesced, and the loop would otherwise wait out one L2 latency per bin)
                 const int kpark = max(P.kmin, 1);
+                CalCoef ccd[ND];
+                if (CALIB) {
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) load_cal_coef(ccd[d], wc + (size_t)(C_DET0 + D_NROW * d) * wpad + col, wpad);
+                }
 #pragma unroll 4
                 for (int i = 0; i < nmax; ++i) {
                     const bool on = i < nres && !dead;
@@ -2061,7 +2161,8 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
                     const double psi = phase_turns(pc, ld_basis(P.basis + k));
 #pragma unroll
                     for (int d = 0; d < ND; ++d) {
-                        const double2 u = phasor_neg(psi + fma(kd, TCOEF(NPH + 2 * d + 1), frac1(kd * TCOEF(NPH + 2 * d))));
+                        double2 u = phasor_neg(psi + fma(kd, TCOEF(NPH + 2 * d + 1), frac1(kd * TCOEF(NPH + 2 * d))));
+                        if (CALIB) u = cmul(u, calib_factor(ccd[d], fma(kd, P.cal_zs[d], P.cal_z0[d])));
                         double2 Tk = __ldg(P.T + (size_t)k * ND + d);
                         if (!on) Tk = make_double2(0.0, 0.0);
                         acc[d] = cfma(Tk, u, acc[d]);
@@ -3444,7 +3545,7 @@ static void launch_main_nd(gwin_plan* p, const MainLaunch& a, cudaStream_t st) {
 
 // fine = false: sub-blocks [blk_lo, blk_hi) of the schedule, per_chunk of them per CTA.
 // fine = true: the tails' fine sub-blocks, walkers in the order of their last bins, `slots` CTAs per group.
-template <int ND>
+template <int ND, bool CALIB>
 static void launch_table(gwin_plan* p, int W, int wpad, int per_chunk, int blk_lo, int blk_hi, const int* col,
                          bool fine, int slots, cudaStream_t st) {
     if (!fine && blk_hi <= blk_lo) return;
@@ -3454,31 +3555,34 @@ static void launch_table(gwin_plan* p, int W, int wpad, int per_chunk, int blk_l
     const int smem = (fine ? 0 : per_chunk) * NPH * TAB_NTP * (int)sizeof(double) + fixed;
     static bool attr_set_dev[64] = {};
     if (!attr_set_dev[p->device & 63]) {
-        cudaFuncSetAttribute(loglr_table_kernel<ND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaFuncSetAttribute(loglr_table_kernel<ND, false, CALIB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              TAB_CHUNK_MAX * NPH * TAB_NTP * (int)sizeof(double) + fixed);
-        cudaFuncSetAttribute(loglr_table_kernel<ND, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        cudaFuncSetAttribute(loglr_table_kernel<ND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fixed);
-        cudaFuncSetAttribute(loglr_table_kernel<ND, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(loglr_table_kernel<ND, false, CALIB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(loglr_table_kernel<ND, true, CALIB>, cudaFuncAttributeMaxDynamicSharedMemorySize, fixed);
+        cudaFuncSetAttribute(loglr_table_kernel<ND, true, CALIB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         attr_set_dev[p->device & 63] = true;
     }
     if (fine)
-        loglr_table_kernel<ND, true><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, 0, 0, 0, p->d_tblk, p->d_cmat,
-                                                                  p->d_tref, p->d_tab, p->d_wc, p->d_ke_fast,
-                                                                  p->d_partialF, p->d_slow, col,
-                                                                  p->d_ks_tail, p->d_ks_fine, p->d_tail_parent);
+        loglr_table_kernel<ND, true, CALIB><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, 0, 0, 0, p->d_tblk, p->d_cmat,
+                                                                         p->d_tref, p->d_tab, p->d_wc, p->d_ke_fast,
+                                                                         p->d_partialF, p->d_slow, col,
+                                                                         p->d_ks_tail, p->d_ks_fine, p->d_tail_parent);
     else
-        loglr_table_kernel<ND, false><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, per_chunk, blk_lo, blk_hi, p->d_tblk, p->d_cmat,
-                                                                   p->d_tref, p->d_tab, p->d_wc, p->d_ke_fast,
-                                                                   p->d_partialT, p->d_slow, col, nullptr, nullptr, nullptr);
+        loglr_table_kernel<ND, false, CALIB><<<grid, CTA_THREADS, smem, st>>>(p->d, W, wpad, per_chunk, blk_lo, blk_hi, p->d_tblk, p->d_cmat,
+                                                                          p->d_tref, p->d_tab, p->d_wc, p->d_ke_fast,
+                                                                          p->d_partialT, p->d_slow, col, nullptr, nullptr, nullptr);
 }
 static void launch_table_nd(gwin_plan* p, int W, int wpad, int per_chunk, int blk_lo, int blk_hi, const int* col,
-                            bool fine, int slots, cudaStream_t st) {
+                            bool fine, int slots, bool calib, cudaStream_t st) {
+#define GWIN_LT(ND) do { if (calib) launch_table<ND, true>(p, W, wpad, per_chunk, blk_lo, blk_hi, col, fine, slots, st); \
+                         else launch_table<ND, false>(p, W, wpad, per_chunk, blk_lo, blk_hi, col, fine, slots, st); } while (0)
     switch (p->d.n_det) {
-        case 1: launch_table<1>(p, W, wpad, per_chunk, blk_lo, blk_hi, col, fine, slots, st); break;
-        case 2: launch_table<2>(p, W, wpad, per_chunk, blk_lo, blk_hi, col, fine, slots, st); break;
-        case 3: launch_table<3>(p, W, wpad, per_chunk, blk_lo, blk_hi, col, fine, slots, st); break;
-        default: launch_table<4>(p, W, wpad, per_chunk, blk_lo, blk_hi, col, fine, slots, st); break;
+        case 1: GWIN_LT(1); break;
+        case 2: GWIN_LT(2); break;
+        case 3: GWIN_LT(3); break;
+        default: GWIN_LT(4); break;
     }
+#undef GWIN_LT
 }
 
 extern "C" int gwin_loglr_batch(gwin_plan* p, int mode, int64_t W64,
@@ -3515,7 +3619,8 @@ extern "C" int gwin_loglr_batch_calib(gwin_plan* p, int mode, int64_t W64,
 // Would this batch go through the moment tables (once they cover it)?
 static bool table_wanted(const gwin_plan* p, int64_t W, bool calibrated) {
     static const bool table_default = !(getenv("GWIN_TABLE") && atoi(getenv("GWIN_TABLE")) == 0);
-    if (calibrated) return false;
+    static const bool table_calib = !(getenv("GWIN_TABLE_CALIB") && atoi(getenv("GWIN_TABLE_CALIB")) == 0);
+    if (calibrated && !table_calib) return false;
     if (p->kernel == GWIN_KERNEL_TABLE) return true;
     if (p->kernel != GWIN_KERNEL_AUTO || !table_default) return false;
     // AUTO: tables that exist are used where they pay; they are built for batches worth the build.
@@ -3756,19 +3861,19 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
     if (table) {
         // sub-blocks with several reference chirps: walkers in a0 order; the long ones above: in time order
         int split = time_order ? std::min(p->n_tblk, (p->tab_split + per_chunkT - 1) / per_chunkT * per_chunkT) : p->n_tblk;
-        launch_table_nd(p, W, wpad, per_chunkT, 0, split, nullptr, false, 0, st);
-        launch_table_nd(p, W, wpad, per_chunkT, split, p->n_tblk, p->d_col_t, false, 0, st);
+        launch_table_nd(p, W, wpad, per_chunkT, 0, split, nullptr, false, 0, calib != nullptr, st);
+        launch_table_nd(p, W, wpad, per_chunkT, split, p->n_tblk, p->d_col_t, false, 0, calib != nullptr, st);
         p->last_launches += split > 0 && split < p->n_tblk ? 1 : 0;
         if (p->timing) CK(cudaEventRecord(p->evd[1], st));
         // tails: fine sub-blocks (walkers in the order of their last bins), then the recurrence kernel
         // over what is left (less than the finest sub-block)
         if (n_chunksF > 0) {
-            launch_table_nd(p, W, wpad, 0, 0, 0, p->d_key2_out, true, n_chunksF, st);
+            launch_table_nd(p, W, wpad, 0, 0, 0, p->d_key2_out, true, n_chunksF, calib != nullptr, st);
             p->last_launches += 1;
         }
         if (p->timing) CK(cudaEventRecord(p->evd[2], st));
         MainLaunch T = M;
-        T.recur = true; T.calibrated = false;
+        T.recur = true; T.calibrated = calib != nullptr;
         T.n_chunks = n_chunks3; T.per_chunk = tail_blocks; T.n_blk = p->n_blk; T.blk_off = 0;
         T.ks_arr = p->d_ks_rec; T.ke_arr = p->d_ke_fast; T.partial = partial3;
         T.col = p->d_key2_out; T.grp_b = p->d_grp_b;

@@ -700,6 +700,41 @@ def test_bench_configuration_c3_auto(cfg3):
     np.testing.assert_array_equal(dev[0].cpu().numpy(), auto[0])
 
 
+def test_calibrated_batches_take_the_table_path_c3(cfg3):
+    """Calibrated likelihood (gwin/calibration.py:142-173) through the moment tables at the headline
+    size: the log-calibration's Taylor coefficients join the per-detector series, the first moment comes
+    from the derivative of the interpolation weights.  2048 walkers with 8-point splines on three
+    detectors -- values of the size the reference's priors give (a few per cent) and ten times that --
+    against the calibrated direct kernel; a sample against the oracle's scipy splines."""
+    import bench
+    rng = np.random.default_rng(77)
+    W = 2048
+    P = bench.draw_walkers(rng, W)
+    P[:, 10] += cfg3.inj["tc"] - bench.INJ["tc"]
+    model = cfg3.cuda_model()
+    plan = model.plan
+    for scale in (0.03, 0.3):
+        rec, vals, names = _calib_setup(cfg3, 8, 2048., rng, W, scale=scale)
+        plan.set_calibration([rec[d].spline_points for d in cfg3.dets])
+        plan.configure(kernel=0)
+        auto = plan.loglr_host(P, calib=vals)
+        n_slow = plan.slow_path_walkers()
+        assert plan.last_launches >= 5                  # AUTO took the table path
+        assert n_slow <= (0 if scale < 0.1 else W // 4), n_slow      # (large values: some walkers fall back to the direct kernel)
+        _agree(auto, _direct(plan, P, calib=vals), "calibrated, AUTO vs direct, scale %g" % scale)
+        plan.configure(kernel=3)
+        _agree(plan.loglr_host(P, calib=vals), auto, "calibrated, TABLE vs AUTO")
+        plan.configure(kernel=0)
+        if scale < 0.1:
+            sel = np.argsort(P[:, 0] + P[:, 1])[np.linspace(0, W - 1, 3).astype(int)]
+            lr0, hd0, hh0 = _calib_oracle_batch(cfg3.oracle(recalibration=rec), P[sel], vals[sel], names)
+            _check(auto[0][sel], auto[1][sel], auto[2][sel], lr0, hd0, hh0, "calibrated table path vs oracle")
+            # and the calibration matters at this size
+            plain = plan.loglr_host(P)
+            assert np.max(np.abs(plain[0] - auto[0])) > 1.0
+    plan.set_calibration(None)
+
+
 def _draw_wide(rng, W, cfg, spin=0.9, qmax=3.0, lam=5000.0, mc=(1.0, 1.6)):
     """Spinning, unequal-mass, tidally deformed systems: chirp mass in ``mc``, mass ratio up to
     ``qmax``, aligned spins up to ``spin``, tidal deformabilities up to ``lam``."""
