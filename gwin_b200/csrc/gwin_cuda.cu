@@ -1606,8 +1606,9 @@ __global__ void cover_stats_kernel(PlanDev P, int W, const double* __restrict__ 
 #define TABLE_MIN_CTAS 2     // 255 registers: a third resident CTA (168) spills in the tap loop and loses 60 %
 #endif
 #ifndef TAB_SPAN
-#define TAB_SPAN 24
+#define TAB_SPAN 48
 #endif
+#define TAB_KPRE 6           // steps (of 4 window rows) whose B fragments are fetched ahead of the weights
 // TAB_SPAN: table rows a warp stages per detector and sub-block (>= TAB_W + the lanes' spread)
 #ifndef TAB_DMMA
 #define TAB_DMMA 1           // taps x moments on the FP64 tensor cores (mma.m8n8k4.f64) instead of DFMA + broadcast loads
@@ -1816,8 +1817,14 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
                 __syncwarp();                           // the previous pass's rows have been read
 #pragma unroll
                 for (int d = 0; d < ND; ++d) {
-                    const int mn = __reduce_min_sync(0xffffffffu, mine ? gs[d] : 0x7fffffff);
+                    int mn = __reduce_min_sync(0xffffffffu, mine ? gs[d] : 0x7fffffff);
                     const int mx = __reduce_max_sync(0xffffffffu, mine ? gs[d] : -1);
+#if TAB_DMMA
+                    // the window starts on a multiple of 4 grid points: which of a lane's 13 taps share a step of
+                    // the tensor-core product then depends on the lane alone (its first row mod 4), not on its
+                    // neighbours -- a walker's result does not depend on the batch it is evaluated in
+                    mn &= ~3;
+#endif
                     lo[d] = mn;
                     const int span = mx - mn + TAB_W;
                     span_d[d] = span;
@@ -1846,13 +1853,13 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
                     // B fragments of all steps, straight from the table (rows shared by the warp's lanes and by
                     // the neighbouring warps: L1 / L2 hits): in flight while the weights are evaluated.  Rows past
                     // the window's end are table rows too (the allocation is padded) and meet zero weights.
-                    double bf[TAB_SPAN / 4][2];
+                    double bf[TAB_KPRE][2];
+                    const double* pbg = reinterpret_cast<const double*>(row0 + (((size_t)rL * ND + d) * (L + TAB_W) + (staged[d] ? lo[d] : 0)) * TAB_NM)
+                                      + (lane & 3) * (2 * TAB_NM) + (lane >> 2);
                     if (staged[d]) {
-                        const double* pbg = reinterpret_cast<const double*>(row0 + (((size_t)rL * ND + d) * (L + TAB_W) + lo[d]) * TAB_NM)
-                                          + (lane & 3) * (2 * TAB_NM) + (lane >> 2);
                         const int nks_ = (span_d[d] + 3) >> 2;
 #pragma unroll
-                        for (int ks = 0; ks < TAB_SPAN / 4; ++ks) {
+                        for (int ks = 0; ks < TAB_KPRE; ++ks) {
                             const int kr = min(ks, nks_ - 1) * 4 * (2 * TAB_NM);
                             bf[ks][0] = __ldg(pbg + kr); bf[ks][1] = __ldg(pbg + kr + 8);
                         }
@@ -1973,7 +1980,7 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
                             for (int nt = 0; nt < 2; ++nt) cf[mt][nt][0] = cf[mt][nt][1] = 0.0;
 #if TAB_BGLOBAL
 #pragma unroll
-                        for (int ks = 0; ks < TAB_SPAN / 4; ++ks) {
+                        for (int ks = 0; ks < TAB_KPRE; ++ks) {
                             if (ks < nks) {
                                 double fa[4];
 #pragma unroll
@@ -1983,6 +1990,18 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
 #pragma unroll
                                     for (int nt = 0; nt < 2; ++nt) dmma884(cf[mt][nt], fa[mt], bf[ks][nt]);
                             }
+                        }
+                        // a window wider than 24 rows (lanes further apart in time): the steps beyond, fetched as they come
+#pragma unroll 1
+                        for (int ks = TAB_KPRE; ks < nks; ++ks) {
+                            double fa[4], fb[2];
+                            fb[0] = __ldg(pbg + ks * 4 * (2 * TAB_NM)); fb[1] = __ldg(pbg + ks * 4 * (2 * TAB_NM) + 8);
+#pragma unroll
+                            for (int mt = 0; mt < 4; ++mt) fa[mt] = pa[ks * 4 * TAB_WDP + 8 * mt];
+#pragma unroll
+                            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                                for (int nt = 0; nt < 2; ++nt) dmma884(cf[mt][nt], fa[mt], fb[nt]);
                         }
 #else
                         const double* pb = reinterpret_cast<const double*>(s_warp + (size_t)d * TAB_SPAN * TAB_ROWB)
