@@ -69,18 +69,45 @@ def bins_used(P, kmin, kmax, delta_f):
     return np.clip(np.minimum(n, kmax) - kmin, 0, None)
 
 
-# FP64 lane-operations the kernels execute per unit of work, counted in the source and
-# checked against ncu's smsp__inst_executed_pipe_fp64 (profiles/r2_fp64_counts.txt):
+# FP64 lane-operations per unit of work, counted in the source:
 #   one (walker, sub-block) of the table kernel: Taylor coefficients 99, relative coefficients 21, the
 #   series e_2..e_10 102, truncation estimate 12; per detector: grid position 10, weights 78, 13 taps x 8
 #   complex moments 208, sum e_n M_n 28, anchor phase + sincos + accumulate 31
+# This is the USEFUL work (what a walker's result needs).  What the launches EXECUTE is more: every lane of a
+# warp runs a sub-block any of its lanes takes, and the taps x moments product runs on the FP64 tensor cores
+# over the whole window of rows a warp's lanes touch (13 + their spread, zero weights elsewhere).  The executed
+# count per launch comes from the committed ncu capture of this same command (profiles/r2_ncu_counts.json:
+# FP64 warp instructions by opcode, a DMMA.884 = 8 multiply-adds per lane) as a ratio to the useful count.
 C_SUB_SETUP, C_SUB_DET = 234, 355
 C_RES_BIN = 14 + 33 * len(DETS)          # fine kernel: the bins after the finest sub-block, per-bin phase + sincos
 C_REC_BIN = 6 + 8 * len(DETS) + 2        # recurrence kernel: 4 (cubic) / 8 (quartic) + 8 per detector, + block set-up
 
 
-def executed_work(plan, ke, band0):
-    """FP64 lane-operations of one batch per launch: dict(recurrence, table, table_fine, recurrence_tail),
+def ncu_counts():
+    """Per launch of one step, from the committed capture: dict(kind -> kernel record) or {}."""
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_counts.json")))
+    except (OSError, ValueError):
+        return {}, None
+    out, rec = {}, []
+    for k in tj.get("kernels", []):
+        nm = k["name"]
+        if "loglr_table_kernel" in nm:
+            out["table_fine" if "<3, 1" in nm else "table"] = k
+        elif "loglr_recur_kernel" in nm:
+            rec.append(k)
+    # (with tables from kmin on there is no low-band launch: the one recurrence launch is the tails')
+    if len(rec) == 1 and "table" in out:
+        out["recurrence_tail"] = rec[0]
+    elif rec:
+        out["recurrence"] = rec[0]
+        if len(rec) > 1:
+            out["recurrence_tail"] = rec[1]
+    return out, tj
+
+
+def useful_work(plan, ke, band0):
+    """Useful FP64 lane-operations of one batch per launch: dict(recurrence, table, table_fine, recurrence_tail),
     from the moment tables' schedule and the walkers' last bins."""
     start, m, _, fmin = plan.table_blocks()
     c_sub = C_SUB_SETUP + len(DETS) * C_SUB_DET
@@ -397,18 +424,28 @@ def run_cuda(args):
         band0 = plan.kmin
         ke = np.minimum((1.0 / (6.0 ** 1.5 * np.pi * (P_host[:, 0] + P_host[:, 1]) * MTSUN) / delta_f + 1).astype(np.int64),
                         plan.kmax)
-        work = executed_work(plan, ke, band0)
+        work = useful_work(plan, ke, band0)
         names = {"recurrence": "loglr_recur_kernel<3,false> (band below the tables)",
                  "table": "loglr_table_kernel<3,false> (sub-blocks of the schedule)",
                  "table_fine": "loglr_table_kernel<3,true> (tails: fine sub-blocks + last bins)",
                  "recurrence_tail": "loglr_recur_kernel<3,false> (tails without fine sub-blocks)"}
+        counts, counts_file = ncu_counts()
+        executed = {}
+        for k in work:
+            c = counts.get(k)
+            # executed / useful of this launch in the committed capture of the same (seeded) workload
+            ratio = c["fp64_lane_ops_executed"] / c["useful_lane_ops"] if c and c.get("useful_lane_ops") else 1.0
+            executed[k] = work[k] * ratio
         per_launch = []
         for k in ("recurrence", "table", "table_fine", "recurrence_tail"):
             if work[k] > 0 or kern_detail[k] > 2e-3:
-                per_launch.append({"kernel": names[k], "ms": kern_detail[k], "fp64_lane_ops": work[k],
-                                   "frac": work[k] / max(kern_detail[k], 1e-9) / 1e-3 / fp64_peak})
-        lane_ops = sum(work.values())
+                per_launch.append({"kernel": names[k], "ms": kern_detail[k], "fp64_lane_ops_executed": executed[k],
+                                   "fp64_lane_ops_useful": work[k],
+                                   "frac": executed[k] / max(kern_detail[k], 1e-9) / 1e-3 / fp64_peak,
+                                   "useful_frac": work[k] / max(kern_detail[k], 1e-9) / 1e-3 / fp64_peak})
+        lane_ops = sum(executed.values())
         achieved = 2.0 * lane_ops / (kern_ms * 1e-3) / 1e12       # TFLOP/s (1 lane-op = 2 flop)
+        useful = 2.0 * sum(work.values()) / (kern_ms * 1e-3) / 1e12
         slots = float(bins.sum()) * W_ALG_SLOTS                   # the survey's work model, per launch
         peak = 2.0 * fp64_peak / 1e12
         nominal = 2.0 * 148 * 64 * 1.965e9 / 1e12
@@ -419,12 +456,12 @@ def run_cuda(args):
             pass
         hbm = peaks.get("hbm_gbs", 6650.0)
         traffic, traffic_src = None, None
-        try:        # dram bytes per launch of this kernel from the committed ncu --set full capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            traffic = float(tj["dram_bytes_read"] + tj["dram_bytes_write"])
-            traffic_src = tj["source"] + " -- " + tj.get("note", "")
-        except (OSError, ValueError, KeyError):
-            pass
+        if counts:       # dram bytes of the loglr launches of one step from the committed ncu --set full capture
+            traffic = float(sum(c["dram_bytes_read"] + c["dram_bytes_write"] for c in counts.values()))
+            traffic_src = ("profiles/r2_ncu_counts.json (%s; ncu --set full of the loglr launches of one timed step of `%s`) -- "
+                           "reads = moment-table rows near the walkers' local times that are not in L2 after the flush (the "
+                           "2.9 GB of tables are never streamed) plus the walkers' coefficient rows; writes = per-chunk partial "
+                           "sums stay in L2 until the combine kernel reads them" % (counts_file["report"], counts_file["command"]))
         # every table byte has to come from HBM once per launch (L2 was flushed); the
         # 128 walker tiles that re-read it are served by the 126 MB L2
         alg_bytes = float(plan.kmax - plan.kmin) * TABLE_BYTES_PER_BIN + W * (13 + 1 + 3 * nd) * 8.0
@@ -451,11 +488,14 @@ def run_cuda(args):
                 "peak_source": "live DFMA probe on this GPU (MEASURED_PEAKS.json has no FP64 entry); "
                                "nominal 148 SM x 64 lanes x 1.965 GHz = %.1f TFLOP/s" % nominal,
                 "frac_of_nominal": achieved / nominal,
-                "work_model": "executed FP64 lane-operations, counted in the source and checked against ncu "
-                              "smsp__inst_executed_pipe_fp64 (profiles/r2_fp64_counts.txt): %d per (walker, sub-block) of the "
-                              "table kernel (%d + %d per detector), %d per bin evaluated directly after the finest tail "
-                              "sub-block, %d per bin of the recurrence kernel; units from the tables' schedule and the "
-                              "walkers' last bins" % (C_SUB_SETUP + nd * C_SUB_DET, C_SUB_SETUP, C_SUB_DET, C_RES_BIN, C_REC_BIN),
+                "useful_achieved": useful, "useful_frac": useful / peak,
+                "work_model": "frac: FP64 lane-operations the launches EXECUTE (warp instructions x 32 lanes, DMMA.884 = 8 "
+                              "per lane; per launch = useful count x the executed/useful ratio of the committed ncu capture of "
+                              "this command, profiles/r2_ncu_counts.json) / CUDA-event time / live DFMA peak.  useful_frac: only "
+                              "what the walkers' results need, counted in the source: %d per (walker, sub-block) of the table "
+                              "kernel (%d + %d per detector), %d per bin evaluated directly after the finest tail sub-block, %d "
+                              "per bin of the recurrence kernel; units from the tables' schedule and the walkers' last bins"
+                              % (C_SUB_SETUP + nd * C_SUB_DET, C_SUB_SETUP, C_SUB_DET, C_RES_BIN, C_REC_BIN),
                 "launches": per_launch,
                 "speedup_vs_work_model": 2.0 * slots / (kern_ms * 1e-3) / 1e12 / peak,
                 "speedup_vs_work_model_note": "SURVEY.md 8d allots W_alg = 32 + 12*n_det = %d FP64 slots to every (walker, "
