@@ -1608,6 +1608,9 @@ __global__ void cover_stats_kernel(PlanDev P, int W, const double* __restrict__ 
 #ifndef TAB_SPAN
 #define TAB_SPAN 48
 #endif
+#ifndef TAB_PREFETCH
+#define TAB_PREFETCH 0
+#endif
 #define TAB_KPRE 6           // steps (of 4 window rows) whose B fragments are fetched ahead of the weights
 // TAB_SPAN: table rows a warp stages per detector and sub-block (>= TAB_W + the lanes' spread)
 #ifndef TAB_DMMA
@@ -1829,6 +1832,15 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
                     const int span = mx - mn + TAB_W;
                     span_d[d] = span;
                     staged[d] = span <= TAB_SPAN;
+#if TAB_DMMA && TAB_BGLOBAL && TAB_PREFETCH
+                    // the window's rows towards L1 while the series and the weights are being evaluated (one 128-byte
+                    // row per lane and instruction)
+                    if (staged[d]) {
+                        const double2* prow = row0 + (((size_t)rL * ND + d) * (L + TAB_W) + mn) * TAB_NM;
+                        for (int j = lane; j < ((span + 3) & ~3); j += WARP)
+                            asm volatile("prefetch.global.L1 [%0];" :: "l"(prow + (size_t)j * TAB_NM));
+                    }
+#endif
                     if (staged[d] && !(TAB_DMMA && TAB_BGLOBAL)) {
                         const double2* src = row0 + (((size_t)rL * ND + d) * (L + TAB_W) + mn) * TAB_NM;
                         const uint32_t dst = smem_u32(s_warp + (size_t)d * TAB_SPAN * TAB_ROWB);
@@ -3740,7 +3752,8 @@ static int loglr_batch_impl(gwin_plan* p, int mode, int64_t W64,
     // table chunks: a sub-block costs about as much as 70 recurrence bins
     int n_chunksT = 0, per_chunkT = 1;
     if (table) {
-        const int wantT = std::max(1, std::min(p->n_tblk, (148 * 24 + groups - 1) / groups));
+        static const int tab_ctas = getenv("GWIN_TAB_CTAS") ? atoi(getenv("GWIN_TAB_CTAS")) : 24;      // CTAs per SM aimed at
+        const int wantT = std::max(1, std::min(p->n_tblk, (148 * tab_ctas + groups - 1) / groups));
         per_chunkT = std::min(TAB_CHUNK_MAX, (p->n_tblk + wantT - 1) / wantT);
         n_chunksT = (p->n_tblk + per_chunkT - 1) / per_chunkT;
         const size_t need = (size_t)n_chunksT * nd * p->w_cap;
