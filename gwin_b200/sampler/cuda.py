@@ -150,6 +150,7 @@ class _DeviceEnsemble(BaseMCMCSampler):
         self._wmax = -(-self._Wh // self._world)
         self._gath = torch.empty(self._world * self._wmax, **f64)
         self._local = torch.zeros(self._wmax, **f64)
+        self._skip_l = torch.zeros(self._wmax, dtype=torch.uint8, device=self._dev)
         self._p = None
         self._iterations = 0
         self._iter0 = 0              # RNG counter offset (resume / cleared chains)
@@ -195,8 +196,9 @@ class _DeviceEnsemble(BaseMCMCSampler):
         return numpy.empty((self._ntemps, self._nwalkers, 0) + ((self._ndim,) if t else ())) \
             if self._chain is None else None
 
-    def _eval_q(self, W, q, q_logp, skip, params, out_loglr):
-        """prior + sharded likelihood for W points in q; result in out_loglr[:W]."""
+    def _eval_local(self, W, q, q_logp, skip, params, out_loglr):
+        """prior for W points in q and the likelihood of this rank's share of them: all W into
+        out_loglr on one GPU, else points rank, rank + world, ... into ``self._local``."""
         torch, lib = self._torch, self._lib
         st = torch.cuda.current_stream(self._dev).cuda_stream
         _lib.check(lib.gwin_ens_prior(C.byref(self._spec), W, q.data_ptr(), q_logp.data_ptr(),
@@ -215,15 +217,30 @@ class _DeviceEnsemble(BaseMCMCSampler):
             n = max(0, -(-(W - rank) // world))
             local = self._local[:wmax]
             if n > 0:
-                skip_l = skip[rank:W:world].contiguous()
+                self._skip_l[:n].copy_(skip[rank:W:world])
                 _lib.check(lib.gwin_loglr_batch_strided(
                     self._plan._h, self.model._mode, n, params.data_ptr() + 8 * rank, world, W,
-                    skip_l.data_ptr(), local.data_ptr(), None, None, st))
-            gath = self._gath[:world * wmax]
-            torch.distributed.all_gather_into_tensor(gath, local, group=self._group)
-            # entry j of rank r is point j * world + r
-            out_loglr[:W].copy_(gath.view(world, wmax).t().reshape(-1)[:W])
+                    self._skip_l.data_ptr(), local.data_ptr(), None, None, st))
         self.likelihood_evals += W
+
+    def _gather(self, W):
+        """The one collective of a half-step: every rank's share of the log-likelihoods."""
+        wmax = -(-W // self._world)
+        self._torch.distributed.all_gather_into_tensor(self._gath[:self._world * wmax], self._local[:wmax],
+                                                       group=self._group)
+
+    def _scatter_back(self, W, out_loglr):
+        # entry j of rank r is point j * world + r
+        world = self._world
+        wmax = -(-W // world)
+        out_loglr[:W].copy_(self._gath[:world * wmax].view(world, wmax).t().reshape(-1)[:W])
+
+    def _eval_q(self, W, q, q_logp, skip, params, out_loglr):
+        """prior + sharded likelihood for W points in q; result in out_loglr[:W]."""
+        self._eval_local(W, q, q_logp, skip, params, out_loglr)
+        if self._world > 1:
+            self._gather(W)
+            self._scatter_back(W, out_loglr)
 
     def set_p0(self, samples_file=None, prior=None):
         nt, nw = self._ntemps, self._nwalkers
@@ -257,6 +274,7 @@ class _DeviceEnsemble(BaseMCMCSampler):
         if self._world > 1 and self._gath.numel() < self._world * (-(-W // self._world)):
             self._gath = torch.empty(self._world * (-(-W // self._world)), **f64)
             self._local = torch.zeros(-(-W // self._world), **f64)
+            self._skip_l = torch.zeros(-(-W // self._world), dtype=torch.uint8, device=self._dev)
         self._declare_coverage()
         self._eval_q(W, p.view(W, nd), logp, skip, params, loglr)
         logl = torch.where(torch.isneginf(logp), torch.zeros_like(loglr), loglr).view(nt, nw)
@@ -314,19 +332,25 @@ class _DeviceEnsemble(BaseMCMCSampler):
             perms = torch.tensor(perms, device=self._dev)
         ctr = torch.zeros(1, dtype=torch.int32, device=self._dev)   # iteration within this call
 
-        def iteration():
+        def pre(half):
             st = torch.cuda.current_stream(self._dev).cuda_stream
-            for half in (0, 1):
-                _lib.check(lib.gwin_ens_propose(
-                    self._seed, g0, ctr.data_ptr(), half, nt, nw, nd, self._a, self._move,
-                    self._interleaved, self._p.data_ptr(), self._q.data_ptr(),
-                    self._logfac.data_ptr(), st))
-                self._eval_q(self._Wh, self._q, self._q_logp, self._skip, self._params, q_loglr)
-                _lib.check(lib.gwin_ens_accept(
-                    self._seed, g0, ctr.data_ptr(), half, nt, nw, nd, self._interleaved,
-                    self._betas.data_ptr(), self._q.data_ptr(), self._logfac.data_ptr(),
-                    q_loglr.data_ptr(), self._q_logp.data_ptr(), self._p.data_ptr(),
-                    self._logl.data_ptr(), self._lnprob.data_ptr(), self._naccept.data_ptr(), st))
+            _lib.check(lib.gwin_ens_propose(
+                self._seed, g0, ctr.data_ptr(), half, nt, nw, nd, self._a, self._move,
+                self._interleaved, self._p.data_ptr(), self._q.data_ptr(),
+                self._logfac.data_ptr(), st))
+            self._eval_local(self._Wh, self._q, self._q_logp, self._skip, self._params, q_loglr)
+
+        def post(half):
+            st = torch.cuda.current_stream(self._dev).cuda_stream
+            if self._world > 1:
+                self._scatter_back(self._Wh, q_loglr)
+            _lib.check(lib.gwin_ens_accept(
+                self._seed, g0, ctr.data_ptr(), half, nt, nw, nd, self._interleaved,
+                self._betas.data_ptr(), self._q.data_ptr(), self._logfac.data_ptr(),
+                q_loglr.data_ptr(), self._q_logp.data_ptr(), self._p.data_ptr(),
+                self._logl.data_ptr(), self._lnprob.data_ptr(), self._naccept.data_ptr(), st))
+            if half == 0:
+                return
             if nt > 1:
                 _lib.check(lib.gwin_ens_swap_all(
                     self._seed, g0, ctr.data_ptr(), nt, nw, nd, self._betas.data_ptr(),
@@ -337,16 +361,18 @@ class _DeviceEnsemble(BaseMCMCSampler):
                 self._logl.data_ptr(), chain.data_ptr(), lnp_h.data_ptr(), lnl_h.data_ptr(), st))
             _lib.check(lib.gwin_ens_tick(ctr.data_ptr(), st))
 
+        def iteration():
+            for half in (0, 1):
+                pre(half)
+                if self._world > 1:
+                    self._gather(self._Wh)
+                post(half)
+
         # recording costs ~50 ms: by default only runs long enough to repay it are recorded
         if "use_graph" in kwargs:
             use_graph = bool(kwargs["use_graph"]) and niterations >= 4
         else:
             use_graph = self.use_graph and niterations >= 64
-        if use_graph and self._world > 1:
-            # recording the NCCL all-gather into a graph hung on the B200 pool (torch 2.11,
-            # NCCL 2.28.9); multi-GPU runs launch kernel by kernel -- the host is an order of
-            # magnitude ahead of the device there anyway
-            use_graph = False
         if use_graph:
             # the first iteration runs eagerly on the capture stream (workspaces, the NCCL
             # communicator and the block schedule come into being here), the second is
@@ -358,12 +384,30 @@ class _DeviceEnsemble(BaseMCMCSampler):
                 iteration()
             cur.wait_stream(side)
             torch.cuda.synchronize(self._dev)
+        if use_graph and self._world == 1:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=side):
                 iteration()
             for _ in range(niterations - 1):
                 graph.replay()
             self._graph_keepalive = (graph, chain, lnp_h, lnl_h, perms, ctr, q_loglr)
+        elif use_graph:
+            # several GPUs: the all-gather stays outside (recording the NCCL call into a graph hung on
+            # this pool: torch 2.11, NCCL 2.28.9), everything between two all-gathers is one graph --
+            # per iteration four graph launches and two collectives instead of ~60 launches
+            graphs = []
+            for half in (0, 1):
+                for part in (pre, post):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=side):
+                        part(half)
+                    graphs.append(g)
+            for _ in range(niterations - 1):
+                for half in (0, 1):
+                    graphs[2 * half].replay()
+                    self._gather(self._Wh)
+                    graphs[2 * half + 1].replay()
+            self._graph_keepalive = (graphs, chain, lnp_h, lnl_h, perms, ctr, q_loglr)
         else:
             for _ in range(niterations):
                 iteration()
