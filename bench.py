@@ -328,19 +328,16 @@ def run_cuda(args):
     bins = bins_used(P_host, plan.kmin, plan.kmax, delta_f)
     P_dev = torch.tensor(P_host, device=dev)
     nd = len(DETS)
-    out = (torch.empty(W, dtype=torch.float64, device=dev),
-           torch.empty((W, nd, 2), dtype=torch.float64, device=dev),
-           torch.empty((W, nd), dtype=torch.float64, device=dev))
-    packed = torch.empty((W, 1 + 3 * nd), dtype=torch.float64, device=dev)
-    gathered = torch.empty((world * W, 1 + 3 * nd), dtype=torch.float64, device=dev) if world > 1 else None
+    # one flat result buffer per rank, [loglr (W) | <d|h> (W x n_det x 2) | <h|h> (W x n_det)]: the kernels write
+    # into its three segments and the all-gather sends it as it is (no packing copies)
+    packed = torch.empty(W * (1 + 3 * nd), dtype=torch.float64, device=dev)
+    out = (packed[:W], packed[W:W + 2 * nd * W].view(W, nd, 2), packed[W + 2 * nd * W:].view(W, nd))
+    gathered = torch.empty((world, W * (1 + 3 * nd)), dtype=torch.float64, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def step():
         plan.loglr_device(P_dev, out=out)
         if world > 1:
-            packed[:, 0] = out[0]
-            packed[:, 1:1 + 2 * nd] = out[1].reshape(W, 2 * nd)
-            packed[:, 1 + 2 * nd:] = out[2]
             dist.all_gather_into_tensor(gathered, packed)
 
     def sync_all():

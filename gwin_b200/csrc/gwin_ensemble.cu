@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "../../include/gwin_b200.h"
 
@@ -279,6 +280,101 @@ ens_swap_all_kernel(uint64_t seed, uint32_t iter, const uint32_t* __restrict__ i
     }
 }
 
+// The same, for ensembles whose log-likelihoods fit in shared memory (ntemps x nwalkers x 8 bytes) with at
+// most two walkers per thread: the random numbers, their logarithms and the pairings of every level are
+// prepared before the level loop (they do not depend on the chains), the log-likelihoods -- all a decision
+// reads -- live in shared memory, and only accepted swaps touch global memory (positions, lnprob).  Same
+// Philox counters, same decisions, same arithmetic: the chains are bit-identical to the kernel above.
+#define SWAP_MAXLV 8
+__global__ void __launch_bounds__(1024)
+ens_swap_all_fast_kernel(uint64_t seed, uint32_t iter, const uint32_t* __restrict__ iter_dev,
+                         int ntemps, int nwalkers, int ndim,
+                         const double* __restrict__ betas, const int* __restrict__ perms, int64_t perm_stride,
+                         double* __restrict__ p, double* __restrict__ logl, double* __restrict__ lnprob,
+                         int* __restrict__ nswap_accepted) {
+    extern __shared__ double s_logl[];                       // [ntemps][nwalkers]
+    __shared__ int s_acc[SWAP_MAXLV + 1];
+    if (iter_dev) { iter += *iter_dev; perms += (size_t)(*iter_dev) * perm_stride; }
+    for (int i = threadIdx.x; i < ntemps * nwalkers; i += blockDim.x) s_logl[i] = logl[i];
+    if (threadIdx.x <= SWAP_MAXLV) s_acc[threadIdx.x] = 0;
+    const int j0 = threadIdx.x, j1 = threadIdx.x + blockDim.x;
+    double lu[SWAP_MAXLV][2];
+#pragma unroll
+    for (int q = 0; q < SWAP_MAXLV; ++q) {
+        const int level = ntemps - 1 - q;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = h ? j1 : j0;
+            lu[q][h] = 0.0;
+            if (level >= 1 && j < nwalkers) {
+                uint32_t r[4];
+                philox4x32(seed, iter, (uint32_t)(STAGE_SWAP * 4), (uint32_t)(level * nwalkers + j), 0u, r);
+                double u0, u1;
+                uniform2(r, u0, u1);
+                lu[q][h] = log(u0);
+            }
+        }
+    }
+    // pairings of the first level; those of the next level are fetched while a level is being decided
+    int na[2], nb[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int j = h ? j1 : j0;
+        na[h] = j < nwalkers ? perms[j] : 0;
+        nb[h] = j < nwalkers ? perms[nwalkers + j] : 0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < SWAP_MAXLV; ++q) {
+        const int level = ntemps - 1 - q;
+        if (level >= 1) {                                      // (uniform)
+            const double dbeta = betas[level - 1] - betas[level];
+            const int ca[2] = {na[0], na[1]}, cb[2] = {nb[0], nb[1]};
+            if (level >= 2) {
+                const int* nxt = perms + (size_t)(q + 1) * 2 * nwalkers;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int j = h ? j1 : j0;
+                    na[h] = j < nwalkers ? nxt[j] : 0;
+                    nb[h] = j < nwalkers ? nxt[nwalkers + j] : 0;
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = h ? j1 : j0;
+                if (j < nwalkers) {
+                    const int a = level * nwalkers + ca[h], b = (level - 1) * nwalkers + cb[h];
+                    const double la = s_logl[a], lb = s_logl[b];
+                    if (dbeta * (la - lb) > lu[q][h]) {
+                        // both rows are read before either is written: one round trip to global memory per 8
+                        // coordinates instead of one per coordinate
+                        double* ra = p + (size_t)a * ndim;
+                        double* rb = p + (size_t)b * ndim;
+                        for (int d0 = 0; d0 < ndim; d0 += 8) {
+                            double ta[8], tb[8];
+#pragma unroll
+                            for (int d = 0; d < 8; ++d)
+                                if (d0 + d < ndim) { ta[d] = ra[d0 + d]; tb[d] = rb[d0 + d]; }
+#pragma unroll
+                            for (int d = 0; d < 8; ++d)
+                                if (d0 + d < ndim) { ra[d0 + d] = tb[d]; rb[d0 + d] = ta[d]; }
+                        }
+                        const double qa = lnprob[a], qb = lnprob[b];
+                        s_logl[a] = lb; s_logl[b] = la;
+                        lnprob[a] = qb - dbeta * lb;
+                        lnprob[b] = qa + dbeta * la;
+                        atomicAdd(s_acc + level, 1);
+                        atomicAdd(s_acc + level - 1, 1);
+                    }
+                }
+            }
+            __syncthreads();            // level l-1 reads what level l wrote to chain l-1
+        }
+    }
+    for (int i = threadIdx.x; i < ntemps * nwalkers; i += blockDim.x) logl[i] = s_logl[i];
+    if (threadIdx.x < ntemps && s_acc[threadIdx.x]) atomicAdd(nswap_accepted + threadIdx.x, s_acc[threadIdx.x]);
+}
+
 // History row `it (+ *it_dev)` of the chain [W][niter][ndim], lnprob [W][niter], logl [W][niter]
 __global__ void ens_record_kernel(int W, int ndim, int niter, uint32_t it, const uint32_t* __restrict__ it_dev,
                                   const double* __restrict__ p, const double* __restrict__ lnprob,
@@ -374,8 +470,22 @@ extern "C" int gwin_ens_swap_all(uint64_t seed, uint32_t iter, const uint32_t* i
     if (nwalkers < 1 || ndim < 1 || !betas || !perms || !p || !logl || !lnprob || !nswap_accepted)
         return gwin_fail(GWIN_EINVAL, "bad swap arguments");
     const int threads = nwalkers >= 1024 ? 1024 : ((nwalkers + 31) / 32) * 32;
-    ens_swap_all_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(seed, iter, iter_dev, ntemps, nwalkers, ndim, betas, perms,
-                                                                 perm_stride, p, logl, lnprob, nswap_accepted);
+    const size_t smem = sizeof(double) * (size_t)ntemps * nwalkers;
+    static const bool fast_on = !(getenv("GWIN_SWAP_FAST") && atoi(getenv("GWIN_SWAP_FAST")) == 0);
+    if (fast_on && ntemps - 1 <= SWAP_MAXLV && nwalkers <= 2 * threads && smem <= 200 * 1024) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        static bool attr_set_dev[64] = {};
+        if (!attr_set_dev[dev & 63]) {
+            cudaFuncSetAttribute(ens_swap_all_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr_set_dev[dev & 63] = true;
+        }
+        ens_swap_all_fast_kernel<<<1, threads, smem, (cudaStream_t)stream>>>(seed, iter, iter_dev, ntemps, nwalkers, ndim, betas, perms,
+                                                                             perm_stride, p, logl, lnprob, nswap_accepted);
+    } else {
+        ens_swap_all_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(seed, iter, iter_dev, ntemps, nwalkers, ndim, betas, perms,
+                                                                     perm_stride, p, logl, lnprob, nswap_accepted);
+    }
     CKE(cudaGetLastError());
     return GWIN_OK;
 }
