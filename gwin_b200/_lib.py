@@ -45,15 +45,15 @@ SYMBOLS = (
     "gwin_host_alloc", "gwin_host_free",
     "gwin_plan_last_launches",
     "gwin_plan_kernel_timing", "gwin_plan_kernel_timing_detail", "gwin_plan_table_blocks",
-    "gwin_ens_propose", "gwin_ens_prior", "gwin_ens_accept", "gwin_ens_swap",
+    "gwin_ens_propose", "gwin_ens_prior", "gwin_ens_prior_calib", "gwin_ens_accept", "gwin_ens_swap",
     "gwin_ens_swap_all", "gwin_ens_record", "gwin_ens_tick",
     "gwin_fp64_peak", "gwin_fp64_probe", "gwin_last_error", "gwin_version",
 )
 
-ENS_MAXDIM = 16
+ENS_MAXDIM = 64
 PRIOR_UNIFORM, PRIOR_UNIFORM_ANGLE, PRIOR_SIN_ANGLE, PRIOR_COS_ANGLE, \
-    PRIOR_UNIFORM_RADIUS = range(5)
-TARGET_MCHIRP, TARGET_Q = 100, 101
+    PRIOR_UNIFORM_RADIUS, PRIOR_GAUSSIAN = range(6)
+TARGET_MCHIRP, TARGET_Q, TARGET_CALIB0 = 100, 101, 200
 
 
 class PriorSpec(C.Structure):
@@ -63,6 +63,8 @@ class PriorSpec(C.Structure):
                 ("target", C.c_int32 * ENS_MAXDIM),
                 ("lo", C.c_double * ENS_MAXDIM),
                 ("hi", C.c_double * ENS_MAXDIM),
+                ("mu", C.c_double * ENS_MAXDIM),
+                ("sigma", C.c_double * ENS_MAXDIM),
                 ("fixed", C.c_double * GWIN_NPARAM)]
 
 
@@ -206,6 +208,8 @@ def load():
         lib.gwin_ens_propose.argtypes = [u64, u32, vp, ci, ci, ci, ci, cd, ci, ci, vp, vp, vp, vp]
         lib.gwin_ens_prior.restype = ci
         lib.gwin_ens_prior.argtypes = [C.POINTER(PriorSpec), C.c_int64, vp, vp, vp, vp, vp]
+        lib.gwin_ens_prior_calib.restype = ci
+        lib.gwin_ens_prior_calib.argtypes = [C.POINTER(PriorSpec), C.c_int64, vp, vp, vp, vp, vp, ci, vp]
         lib.gwin_ens_accept.restype = ci
         lib.gwin_ens_accept.argtypes = [u64, u32, vp, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp,
                                         vp, vp, vp, vp, vp]

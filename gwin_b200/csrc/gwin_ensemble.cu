@@ -102,6 +102,7 @@ struct gwin_prior_spec_dev {
     int type[GWIN_ENS_MAXDIM];
     int target[GWIN_ENS_MAXDIM];
     double lo[GWIN_ENS_MAXDIM], hi[GWIN_ENS_MAXDIM];
+    double mu[GWIN_ENS_MAXDIM], sigma[GWIN_ENS_MAXDIM];
     double fixed[GWIN_NPARAM];
 };
 
@@ -120,9 +121,9 @@ __device__ __forceinline__ double wrap_reflect(double x, double lo, double hi) {
 }
 
 // q [W][ndim] (sampling parameters, untouched) -> logp [W], skip [W], params [13][W]
-__global__ void ens_prior_kernel(gwin_prior_spec_dev S, int W, const double* __restrict__ q,
+__global__ void ens_prior_kernel(const __grid_constant__ gwin_prior_spec_dev S, int W, const double* __restrict__ q,
                                  double* __restrict__ logp, uint8_t* __restrict__ skip,
-                                 double* __restrict__ params) {
+                                 double* __restrict__ params, double* __restrict__ calib) {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= W) return;
     double row[GWIN_NPARAM];
@@ -152,6 +153,12 @@ __global__ void ens_prior_kernel(gwin_prior_spec_dev S, int W, const double* __r
             case GWIN_PRIOR_UNIFORM_RADIUS:         // p ~ x^2
                 lp += (x >= lo && x <= hi) ? log(3.0 * x * x / (hi * hi * hi - lo * lo * lo)) : -INFINITY;
                 break;
+            case GWIN_PRIOR_GAUSSIAN: {             // normal (mu, sigma) truncated to [lo, hi]
+                const double sg = S.sigma[d], z = (x - S.mu[d]) / sg;
+                const double nrm = 0.5 * (erf((hi - S.mu[d]) / (sg * 1.4142135623730951)) - erf((lo - S.mu[d]) / (sg * 1.4142135623730951)));
+                lp += (x >= lo && x <= hi) ? -0.5 * z * z - log(sg * 2.5066282746310002 * nrm) : -INFINITY;
+                break;
+            }
             default:
                 lp = -INFINITY;
         }
@@ -159,6 +166,7 @@ __global__ void ens_prior_kernel(gwin_prior_spec_dev S, int W, const double* __r
         if (tg >= 0 && tg < GWIN_NPARAM) row[tg] = x;
         else if (tg == GWIN_TARGET_MCHIRP) mchirp = x;
         else if (tg == GWIN_TARGET_Q) qratio = x;
+        else if (tg >= GWIN_TARGET_CALIB0 && calib) calib[(size_t)(tg - GWIN_TARGET_CALIB0) * W + w] = x;
     }
     if (mchirp > 0.0 && qratio > 0.0) {             // waveform transform (mchirp, q = m1/m2) -> (m1, m2)
         const double m2 = mchirp * pow(1.0 + qratio, 0.2) / pow(qratio, 0.6);
@@ -421,17 +429,32 @@ extern "C" int gwin_ens_propose(uint64_t seed, uint32_t iter, const uint32_t* it
 
 extern "C" int gwin_ens_prior(const gwin_prior_spec* spec, int64_t W, const double* q,
                               double* logp, uint8_t* skip, double* params, void* stream) {
+    return gwin_ens_prior_calib(spec, W, q, logp, skip, params, nullptr, 0, stream);
+}
+
+extern "C" int gwin_ens_prior_calib(const gwin_prior_spec* spec, int64_t W, const double* q,
+                                    double* logp, uint8_t* skip, double* params,
+                                    double* calib, int n_calib, void* stream) {
     if (!spec || !q || !logp || !skip || !params) return gwin_fail(GWIN_EINVAL, "NULL argument");
     if (spec->ndim < 1 || spec->ndim > GWIN_ENS_MAXDIM) return gwin_fail(GWIN_EINVAL, "bad ndim");
     if (W <= 0) return GWIN_OK;
+    if (n_calib < 0 || (n_calib > 0 && !calib)) return gwin_fail(GWIN_EINVAL, "bad calibration buffer");
     gwin_prior_spec_dev S;
     S.ndim = spec->ndim;
     for (int d = 0; d < GWIN_ENS_MAXDIM; ++d) {
         S.type[d] = spec->type[d]; S.target[d] = spec->target[d];
         S.lo[d] = spec->lo[d]; S.hi[d] = spec->hi[d];
+        S.mu[d] = spec->mu[d]; S.sigma[d] = spec->sigma[d];
+        if (d < spec->ndim && spec->target[d] >= GWIN_TARGET_CALIB0 && n_calib > 0) {
+            const int v = spec->target[d] - GWIN_TARGET_CALIB0;
+            if (v >= n_calib) return gwin_fail(GWIN_EINVAL, "dimension %d targets calibration value %d of %d", d, v, n_calib);
+        }
+        if (d < spec->ndim && spec->type[d] == GWIN_PRIOR_GAUSSIAN && !(spec->sigma[d] > 0.0))
+            return gwin_fail(GWIN_EINVAL, "dimension %d: sigma must be positive", d);
     }
     for (int i = 0; i < GWIN_NPARAM; ++i) S.fixed[i] = spec->fixed[i];
-    ens_prior_kernel<<<(unsigned)((W + 127) / 128), 128, 0, (cudaStream_t)stream>>>(S, (int)W, q, logp, skip, params);
+    ens_prior_kernel<<<(unsigned)((W + 127) / 128), 128, 0, (cudaStream_t)stream>>>(S, (int)W, q, logp, skip, params,
+                                                                                    n_calib > 0 ? calib : nullptr);
     CKE(cudaGetLastError());
     return GWIN_OK;
 }

@@ -11,8 +11,13 @@ RNG regenerates identical proposals and decisions on every rank.
 torch is used for what the task allows it: owning device memory, the stream and
 ``torch.distributed``.  Restrictions (use the host steppers otherwise): priors
 must be a ``JointDistribution`` of Uniform / UniformAngle / SinAngle / CosAngle /
-UniformRadius / UniformSky without constraints, no sampling transforms, and the
-only waveform transform understood is (mchirp, q) -> (mass1, mass2).
+UniformRadius / UniformSky / Gaussian without constraints, at most 64 sampled
+dimensions, no sampling transforms, and the only waveform transform understood is
+(mchirp, q) -> (mass1, mass2).  ``recalib_*`` parameters of a calibrated model
+(``gwin/calibration.py``) are sampled like any other: the prior kernel fills the
+kernels' calibration matrix (values are not checked against the regime in which the
+least-squares cubic equals scipy's smoothing spline -- keep their priors inside
+sum(values^2) <= n_points per detector and quantity, as ``calibration.values_matrix`` demands on the host path).
 """
 import ctypes as C
 import os
@@ -29,7 +34,7 @@ from .ensemble import default_beta_ladder
 
 _TYPES = {D.Uniform: _lib.PRIOR_UNIFORM, D.UniformAngle: _lib.PRIOR_UNIFORM_ANGLE,
           D.SinAngle: _lib.PRIOR_SIN_ANGLE, D.CosAngle: _lib.PRIOR_COS_ANGLE,
-          D.UniformRadius: _lib.PRIOR_UNIFORM_RADIUS}
+          D.UniformRadius: _lib.PRIOR_UNIFORM_RADIUS, D.Gaussian: _lib.PRIOR_GAUSSIAN}
 
 
 def prior_spec_from_model(model):
@@ -57,16 +62,29 @@ def prior_spec_from_model(model):
                                           % type(part).__name__)
             for name, b in part.bounds.items():
                 per_param[name] = (_TYPES[type(part)], b.min, b.max)
+                if isinstance(part, D.Gaussian):
+                    per_param[name] += (part._mean[name], float(numpy.sqrt(part._var[name])))
     names = list(model.sampling_params)
     if len(names) > _lib.ENS_MAXDIM:
         raise NotImplementedError("more than %d sampling dimensions" % _lib.ENS_MAXDIM)
     wf_names = list(WAVEFORM_PARAMS.keys())
+    # recalib_* parameters: value v = (2 det + which) n_points + i of the kernels' calibration matrix
+    calib_names = []
+    recalib = getattr(model, "_recalib", None)
+    if recalib:
+        for det in model.detectors:
+            calib_names += list(recalib[det].param_names)
     spec = _lib.PriorSpec()
     spec.ndim = len(names)
     for d, name in enumerate(names):
-        kind, lo, hi = per_param[name]
+        kind, lo, hi = per_param[name][:3]
         spec.type[d], spec.lo[d], spec.hi[d] = kind, lo, hi
-        if name in wf_names:
+        spec.sigma[d] = 1.0
+        if kind == _lib.PRIOR_GAUSSIAN:
+            spec.mu[d], spec.sigma[d] = per_param[name][3:5]
+        if name in calib_names:
+            spec.target[d] = _lib.TARGET_CALIB0 + calib_names.index(name)
+        elif name in wf_names:
             spec.target[d] = wf_names.index(name)
         elif mchirp_q and name == "mchirp":
             spec.target[d] = _lib.TARGET_MCHIRP
@@ -114,11 +132,6 @@ class _DeviceEnsemble(BaseMCMCSampler):
         if nwalkers < 2 * ndim:
             raise ValueError("The number of walkers needs to be more than twice "
                              "the dimension of your parameter space.")
-        if getattr(model, "_recalib", None):
-            raise NotImplementedError(
-                "calibration parameters exceed the device-resident stepper's %d "
-                "sampled dimensions; use emcee / emcee_pt (host stepper, GPU "
-                "likelihood) with a calibrated model" % _lib.ENS_MAXDIM)
         self._torch = torch
         self._lib = _lib.load()
         self._spec = prior_spec_from_model(model)
@@ -138,6 +151,16 @@ class _DeviceEnsemble(BaseMCMCSampler):
         self._q_logp = torch.empty(self._Wh, **f64)
         self._skip = torch.empty(self._Wh, dtype=torch.uint8, device=self._dev)
         self._params = torch.empty((_lib.GWIN_NPARAM, self._Wh), **f64)
+        # calibrated model: the recalib_* values of the proposals, value-major [n_values][W]; values that
+        # are static keep what is written here once
+        self._calib_names = []
+        recalib = getattr(model, "_recalib", None)
+        if recalib:
+            for det in model.detectors:
+                self._calib_names += list(recalib[det].param_names)
+        self._calib = None
+        if self._calib_names:
+            self._calib = self._calib_buffer(self._Wh)
         self._naccept = torch.zeros((ntemps, nwalkers), dtype=torch.int32, device=self._dev)
         self._nswap_acc = torch.zeros(ntemps, dtype=torch.int32, device=self._dev)
         self._nswap = 0
@@ -201,9 +224,18 @@ class _DeviceEnsemble(BaseMCMCSampler):
         out_loglr on one GPU, else points rank, rank + world, ... into ``self._local``."""
         torch, lib = self._torch, self._lib
         st = torch.cuda.current_stream(self._dev).cuda_stream
-        _lib.check(lib.gwin_ens_prior(C.byref(self._spec), W, q.data_ptr(), q_logp.data_ptr(),
-                                      skip.data_ptr(), params.data_ptr(), st))
-        if self._world == 1:
+        calib = None
+        if self._calib_names:
+            calib = self._calib if W == self._calib.shape[1] else self._calib_buffer(W)
+        _lib.check(lib.gwin_ens_prior_calib(C.byref(self._spec), W, q.data_ptr(), q_logp.data_ptr(),
+                                            skip.data_ptr(), params.data_ptr(),
+                                            calib.data_ptr() if calib is not None else None,
+                                            len(self._calib_names), st))
+        if self._world == 1 and calib is not None:
+            _lib.check(lib.gwin_loglr_batch_calib(
+                self._plan._h, self.model._mode, W, params.data_ptr(), 1, W, calib.data_ptr(), 1, W,
+                skip.data_ptr(), out_loglr.data_ptr(), None, None, st))
+        elif self._world == 1:
             _lib.check(lib.gwin_loglr_batch_strided(
                 self._plan._h, self.model._mode, W, params.data_ptr(), 1, W, skip.data_ptr(),
                 out_loglr.data_ptr(), None, None, st))
@@ -218,10 +250,32 @@ class _DeviceEnsemble(BaseMCMCSampler):
             local = self._local[:wmax]
             if n > 0:
                 self._skip_l[:n].copy_(skip[rank:W:world])
-                _lib.check(lib.gwin_loglr_batch_strided(
-                    self._plan._h, self.model._mode, n, params.data_ptr() + 8 * rank, world, W,
-                    self._skip_l.data_ptr(), local.data_ptr(), None, None, st))
+                if calib is not None:
+                    _lib.check(lib.gwin_loglr_batch_calib(
+                        self._plan._h, self.model._mode, n, params.data_ptr() + 8 * rank, world, W,
+                        calib.data_ptr() + 8 * rank, world, W,
+                        self._skip_l.data_ptr(), local.data_ptr(), None, None, st))
+                else:
+                    _lib.check(lib.gwin_loglr_batch_strided(
+                        self._plan._h, self.model._mode, n, params.data_ptr() + 8 * rank, world, W,
+                        self._skip_l.data_ptr(), local.data_ptr(), None, None, st))
         self.likelihood_evals += W
+
+    def _calib_buffer(self, W):
+        """[n_values][W] with the static recalib_* values filled in (the sampled ones are written by the
+        prior kernel for every batch)."""
+        torch = self._torch
+        static = dict(self.model.waveform_generator.frozen_params)
+        static.update(self.model.static_params)
+        buf = torch.zeros((len(self._calib_names), W), dtype=torch.float64, device=self._dev)
+        sampled = set(self.model.sampling_params)
+        for v, name in enumerate(self._calib_names):
+            if name in sampled:
+                continue
+            if name not in static:
+                raise KeyError(name)
+            buf[v] = float(static[name])
+        return buf
 
     def _gather(self, W):
         """The one collective of a half-step: every rank's share of the log-likelihoods."""
@@ -293,6 +347,10 @@ class _DeviceEnsemble(BaseMCMCSampler):
         nd = self._ndim
         lo = numpy.array([spec.lo[i] for i in range(nd)])
         hi = numpy.array([spec.hi[i] for i in range(nd)])
+        for i in range(nd):                 # unbounded normals: five standard deviations
+            if spec.type[i] == _lib.PRIOR_GAUSSIAN:
+                lo[i] = max(lo[i], spec.mu[i] - 5.0 * spec.sigma[i])
+                hi[i] = min(hi[i], spec.mu[i] + 5.0 * spec.sigma[i])
         rs = numpy.random.RandomState(12345)
         q = torch.tensor(lo + (hi - lo) * rs.uniform(size=(n, nd)), dtype=torch.float64, device=self._dev)
         logp = torch.empty(n, dtype=torch.float64, device=self._dev)

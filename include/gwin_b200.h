@@ -283,22 +283,25 @@ int gwin_plan_table_blocks(const gwin_plan* plan, int64_t cap, int32_t* start, i
  * `stream`.  Random numbers are Philox4x32-10(seed; iteration, stage, index): every rank of a
  * multi-GPU run regenerates identical numbers, so only log-likelihoods need to be exchanged.
  * ------------------------------------------------------------------------------------------ */
-#define GWIN_ENS_MAXDIM 16
+#define GWIN_ENS_MAXDIM 64
 
 #define GWIN_PRIOR_UNIFORM        0   /* pycbc.distributions.Uniform                          */
 #define GWIN_PRIOR_UNIFORM_ANGLE  1   /* UniformAngle: cyclic on [lo, hi)                      */
 #define GWIN_PRIOR_SIN_ANGLE      2   /* SinAngle: p ~ sin x, reflected into [0, pi]           */
 #define GWIN_PRIOR_COS_ANGLE      3   /* CosAngle: p ~ cos x, reflected into [-pi/2, pi/2]     */
 #define GWIN_PRIOR_UNIFORM_RADIUS 4   /* UniformRadius: p ~ x^2                                */
+#define GWIN_PRIOR_GAUSSIAN       5   /* Gaussian: normal (mu, sigma) truncated to [lo, hi]    */
 
 #define GWIN_TARGET_MCHIRP 100        /* sampling dim is mchirp ...                            */
 #define GWIN_TARGET_Q      101        /* ... / q = m1/m2: mapped to mass1, mass2 on the device */
+#define GWIN_TARGET_CALIB0 200        /* + v: calibration value v of gwin_loglr_batch_calib (the recalib_* parameters) */
 
 typedef struct gwin_prior_spec {
     int32_t ndim;                       /* sampling dimensions                                   */
     int32_t type[GWIN_ENS_MAXDIM];      /* GWIN_PRIOR_*                                          */
     int32_t target[GWIN_ENS_MAXDIM];    /* waveform-parameter column 0..12, or GWIN_TARGET_*     */
     double lo[GWIN_ENS_MAXDIM], hi[GWIN_ENS_MAXDIM];
+    double mu[GWIN_ENS_MAXDIM], sigma[GWIN_ENS_MAXDIM];    /* GWIN_PRIOR_GAUSSIAN                     */
     double fixed[GWIN_NPARAM];          /* static values of the parameters that are not sampled  */
 } gwin_prior_spec;
 
@@ -317,6 +320,12 @@ int gwin_ens_propose(uint64_t seed, uint32_t iter, const uint32_t* iter_dev,
  * (gwin/models/base.py:543-554, 602-621) for the supported distributions. */
 int gwin_ens_prior(const gwin_prior_spec* spec, int64_t W, const double* q,
                    double* logp, uint8_t* skip, double* params, void* stream);
+/* The same for a calibrated model: sampling dimensions with target GWIN_TARGET_CALIB0 + v also write
+ * calib[v * W + w] (value-major [n_calib][W]: feed to gwin_loglr_batch_calib with strides (1, W)).  Values no
+ * sampling dimension writes stay as the caller put them (static recalib_* parameters: fill them once). */
+int gwin_ens_prior_calib(const gwin_prior_spec* spec, int64_t W, const double* q,
+                         double* logp, uint8_t* skip, double* params,
+                         double* calib, int n_calib, void* stream);
 
 /* Accept/reject: ln u < logfac + (beta_k q_logl + q_logp) - lnprob; updates p, logl, lnprob
  * ([ntemps][nwalkers]...) and the per-walker acceptance counters. */

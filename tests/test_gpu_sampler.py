@@ -170,8 +170,10 @@ def test_device_pt_sampler():
     assert np.all(sw >= 0) and np.all(sw <= 1) and sw.sum() > 0
     # hotter chains explore more
     assert pt.chain[3, :, 30:, 1].std() > pt.chain[0, :, 30:, 1].std()
+    class Unknown(D.Uniform):             # a distribution the device prior kernel does not know
+        pass
     with pytest.raises(NotImplementedError):
-        CudaPTSampler(_model(cfg, names, D.JointDistribution(names, D.Gaussian(tc=None), D.Uniform(distance=(1, 2)))), 2, 8)
+        CudaPTSampler(_model(cfg, names, D.JointDistribution(names, Unknown(tc=(0., 1.)), D.Uniform(distance=(1, 2)))), 2, 8)
 
 
 def test_device_sampler_checkpoint_resume(tmp_path):
@@ -230,3 +232,76 @@ def test_graph_replay_equals_host_launched_iterations(ntemps):
     assert graph.likelihood_evals == eager.likelihood_evals
     if ntemps > 1:
         np.testing.assert_array_equal(graph.tswap_acceptance_fraction, eager.tswap_acceptance_fraction)
+
+
+def test_device_sampler_with_calibration_parameters():
+    """A calibrated model (recalib_* parameters with Gaussian priors, gwin/calibration.py:104-173,
+    enabled at bin/gwin:199-204) in the device-resident stepper: 2 + 3 detectors x 2 x 4 = 26 sampled
+    dimensions; the prior kernel fills the calibration matrix, the likelihood takes the calibrated
+    path.  The chain's lnpost is the model's logplr at the stored positions, the host stepper with
+    the same model lands on the same distance, a static recalib_* value is honoured."""
+    from gwin_b200 import calibration
+    from gwin_b200.types import FrequencySeries
+    from gwin_b200.waveform import FDomainCBCGenerator, FDomainDetFrameGenerator
+    cfg = util.c2()
+    n = 4
+    rec = {d: calibration.CubicSpline(20., 1024., n, d.lower()) for d in cfg.dets}
+    cal_names = [nm for d in cfg.dets for nm in rec[d].param_names]
+    fixed_cal = cal_names[-1]                      # one calibration value is static, the others sampled
+    names = ['distance', 'tc'] + cal_names[:-1]
+    dists = [D.UniformRadius(distance=(100., 1000.)),
+             D.Uniform(tc=(cfg.inj['tc'] - 0.01, cfg.inj['tc'] + 0.01))]
+    for nm in cal_names[:-1]:
+        dists.append(D.Gaussian(**{nm: (-0.3, 0.3), nm + "_mean": 0.0, nm + "_var": 0.03 ** 2}))
+    prior = D.JointDistribution(names, *dists)
+    static = {k: v for k, v in cfg.inj.items() if k not in names}
+    static[fixed_cal] = 0.02
+    gen = FDomainDetFrameGenerator(FDomainCBCGenerator, cfg.epoch, detectors=cfg.dets,
+                                   variable_args=tuple(names), delta_f=cfg.delta_f, f_lower=cfg.f_lower,
+                                   recalib=rec)
+    data = {d: FrequencySeries(cfg.data[d], cfg.delta_f, cfg.epoch) for d in cfg.dets}
+    model = models.GaussianNoise(tuple(names), data, gen, cfg.f_lower, psds=cfg.psds(),
+                                 static_params=static, prior=prior)
+    spec = prior_spec_from_model(model)
+    assert spec.ndim == 25 and spec.type[2] == 5 and spec.target[2] == 200 and abs(spec.sigma[2] - 0.03) < 1e-15
+    np.random.seed(5)
+    dev = CudaEnsembleSampler(model, 128, seed=99)
+    dev.set_p0()
+    dev.run(150)
+    assert dev.chain.shape == (128, 150, 25)
+    assert 0.05 < dev.acceptance_fraction.mean() < 0.8
+    call = models.CallModel(model, 'logplr')
+    for it in (0, 75, 149):
+        pts = dev.chain[:16, it, :]
+        ref = call.batch(pts).values
+        assert np.allclose(dev.lnpost[:16, it], ref, rtol=1e-10, atol=1e-7), it
+    # the calibration parameters move (they are sampled), within their truncated priors
+    s = dev.samples
+    x = np.asarray(s[cal_names[0]])
+    assert x.std() > 1e-3 and np.all(np.abs(x) <= 0.3)
+    # the static value matters: a different one gives a different likelihood at the same points
+    static2 = dict(static)
+    static2[fixed_cal] = -0.2
+    gen2 = FDomainDetFrameGenerator(FDomainCBCGenerator, cfg.epoch, detectors=cfg.dets,
+                                    variable_args=tuple(names), delta_f=cfg.delta_f, f_lower=cfg.f_lower,
+                                    recalib=rec)
+    model2 = models.GaussianNoise(tuple(names), data, gen2, cfg.f_lower, psds=cfg.psds(),
+                                  static_params=static2, prior=prior)
+    dev2 = CudaEnsembleSampler(model2, 128, seed=99)
+    np.random.seed(5)
+    dev2.set_p0()
+    dev2.run(2)
+    assert np.max(np.abs(dev2.lnpost[:, 0] - dev.lnpost[:, 0])) > 1e-3
+    pts = dev2.chain[:8, 1, :]
+    assert np.allclose(dev2.lnpost[:8, 1], models.CallModel(model2, 'logplr').batch(pts).values, rtol=1e-10, atol=1e-7)
+    # host stepper, same model: distance agrees statistically
+    np.random.seed(6)
+    host = EmceeEnsembleSampler(model, 128, model_call=models.CallModel(model, 'logplr'))
+    host.set_p0()
+    host.run(150)
+    # (150 iterations in 25 dimensions are not a converged run: the two steppers are held to each
+    #  other's distance estimate, not to a KS test)
+    a = np.asarray(host.samples['distance'])[:, 75::15].ravel()
+    b = np.asarray(s['distance'])[:, 75::15].ravel()
+    assert abs(np.median(a) - np.median(b)) < 0.05 * np.median(a)
+    assert abs(host.acceptance_fraction.mean() - dev.acceptance_fraction.mean()) < 0.1
