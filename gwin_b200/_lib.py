@@ -52,7 +52,7 @@ SYMBOLS = (
 
 ENS_MAXDIM = 64
 PRIOR_UNIFORM, PRIOR_UNIFORM_ANGLE, PRIOR_SIN_ANGLE, PRIOR_COS_ANGLE, \
-    PRIOR_UNIFORM_RADIUS, PRIOR_GAUSSIAN = range(6)
+    PRIOR_UNIFORM_RADIUS, PRIOR_GAUSSIAN, PRIOR_NONE = range(7)
 TARGET_MCHIRP, TARGET_Q, TARGET_CALIB0 = 100, 101, 200
 
 
@@ -65,7 +65,11 @@ class PriorSpec(C.Structure):
                 ("hi", C.c_double * ENS_MAXDIM),
                 ("mu", C.c_double * ENS_MAXDIM),
                 ("sigma", C.c_double * ENS_MAXDIM),
-                ("fixed", C.c_double * GWIN_NPARAM)]
+                ("fixed", C.c_double * GWIN_NPARAM),
+                ("derived_masses", C.c_int32),
+                ("derived_type", C.c_int32 * 2),
+                ("derived_lo", C.c_double * 2), ("derived_hi", C.c_double * 2),
+                ("derived_mu", C.c_double * 2), ("derived_sigma", C.c_double * 2)]
 
 
 _lock = threading.Lock()

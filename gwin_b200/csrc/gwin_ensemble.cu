@@ -104,6 +104,9 @@ struct gwin_prior_spec_dev {
     double lo[GWIN_ENS_MAXDIM], hi[GWIN_ENS_MAXDIM];
     double mu[GWIN_ENS_MAXDIM], sigma[GWIN_ENS_MAXDIM];
     double fixed[GWIN_NPARAM];
+    int derived_masses;
+    int derived_type[2];
+    double derived_lo[2], derived_hi[2], derived_mu[2], derived_sigma[2];
 };
 
 __device__ __forceinline__ double wrap_cyclic(double x, double lo, double hi) {
@@ -120,6 +123,34 @@ __device__ __forceinline__ double wrap_reflect(double x, double lo, double hi) {
     return y + lo;
 }
 
+// boundary condition (x is updated) and log density of one dimension
+__device__ __forceinline__ double prior_term(int type, double& x, double lo, double hi, double mu, double sg) {
+    switch (type) {
+        case GWIN_PRIOR_UNIFORM:
+            return (x >= lo && x <= hi) ? -log(hi - lo) : -INFINITY;
+        case GWIN_PRIOR_UNIFORM_ANGLE:          // cyclic
+            x = wrap_cyclic(x, lo, hi);
+            return -log(hi - lo);
+        case GWIN_PRIOR_SIN_ANGLE:              // p ~ sin x on [lo, hi] within [0, pi], reflected
+            x = wrap_reflect(x, 0.0, G_PI);
+            return (x >= lo && x <= hi) ? log(fabs(sin(x)) / fabs(cos(lo) - cos(hi))) : -INFINITY;
+        case GWIN_PRIOR_COS_ANGLE:              // p ~ cos x on [lo, hi] within [-pi/2, pi/2], reflected
+            x = wrap_reflect(x, -0.5 * G_PI, 0.5 * G_PI);
+            return (x >= lo && x <= hi) ? log(fabs(cos(x)) / fabs(sin(hi) - sin(lo))) : -INFINITY;
+        case GWIN_PRIOR_UNIFORM_RADIUS:         // p ~ x^2
+            return (x >= lo && x <= hi) ? log(3.0 * x * x / (hi * hi * hi - lo * lo * lo)) : -INFINITY;
+        case GWIN_PRIOR_GAUSSIAN: {             // normal (mu, sigma) truncated to [lo, hi]
+            const double z = (x - mu) / sg;
+            const double nrm = 0.5 * (erf((hi - mu) / (sg * 1.4142135623730951)) - erf((lo - mu) / (sg * 1.4142135623730951)));
+            return (x >= lo && x <= hi) ? -0.5 * z * z - log(sg * 2.5066282746310002 * nrm) : -INFINITY;
+        }
+        case GWIN_PRIOR_NONE:
+            return 0.0;
+        default:
+            return -INFINITY;
+    }
+}
+
 // q [W][ndim] (sampling parameters, untouched) -> logp [W], skip [W], params [13][W]
 __global__ void ens_prior_kernel(const __grid_constant__ gwin_prior_spec_dev S, int W, const double* __restrict__ q,
                                  double* __restrict__ logp, uint8_t* __restrict__ skip,
@@ -134,34 +165,7 @@ __global__ void ens_prior_kernel(const __grid_constant__ gwin_prior_spec_dev S, 
     for (int d = 0; d < S.ndim; ++d) {
         double x = q[(size_t)w * S.ndim + d];
         const double lo = S.lo[d], hi = S.hi[d];
-        switch (S.type[d]) {
-            case GWIN_PRIOR_UNIFORM:
-                lp += (x >= lo && x <= hi) ? -log(hi - lo) : -INFINITY;
-                break;
-            case GWIN_PRIOR_UNIFORM_ANGLE:          // cyclic
-                x = wrap_cyclic(x, lo, hi);
-                lp += -log(hi - lo);
-                break;
-            case GWIN_PRIOR_SIN_ANGLE:              // p ~ sin x on [lo, hi] within [0, pi], reflected
-                x = wrap_reflect(x, 0.0, G_PI);
-                lp += (x >= lo && x <= hi) ? log(fabs(sin(x)) / fabs(cos(lo) - cos(hi))) : -INFINITY;
-                break;
-            case GWIN_PRIOR_COS_ANGLE:              // p ~ cos x on [lo, hi] within [-pi/2, pi/2], reflected
-                x = wrap_reflect(x, -0.5 * G_PI, 0.5 * G_PI);
-                lp += (x >= lo && x <= hi) ? log(fabs(cos(x)) / fabs(sin(hi) - sin(lo))) : -INFINITY;
-                break;
-            case GWIN_PRIOR_UNIFORM_RADIUS:         // p ~ x^2
-                lp += (x >= lo && x <= hi) ? log(3.0 * x * x / (hi * hi * hi - lo * lo * lo)) : -INFINITY;
-                break;
-            case GWIN_PRIOR_GAUSSIAN: {             // normal (mu, sigma) truncated to [lo, hi]
-                const double sg = S.sigma[d], z = (x - S.mu[d]) / sg;
-                const double nrm = 0.5 * (erf((hi - S.mu[d]) / (sg * 1.4142135623730951)) - erf((lo - S.mu[d]) / (sg * 1.4142135623730951)));
-                lp += (x >= lo && x <= hi) ? -0.5 * z * z - log(sg * 2.5066282746310002 * nrm) : -INFINITY;
-                break;
-            }
-            default:
-                lp = -INFINITY;
-        }
+        lp += prior_term(S.type[d], x, lo, hi, S.mu[d], S.sigma[d]);
         const int tg = S.target[d];
         if (tg >= 0 && tg < GWIN_NPARAM) row[tg] = x;
         else if (tg == GWIN_TARGET_MCHIRP) mchirp = x;
@@ -172,6 +176,19 @@ __global__ void ens_prior_kernel(const __grid_constant__ gwin_prior_spec_dev S, 
         const double m2 = mchirp * pow(1.0 + qratio, 0.2) / pow(qratio, 0.6);
         row[0] = qratio * m2;
         row[1] = m2;
+    }
+    if (S.derived_masses) {
+        // sampling transform: the walkers move in (mchirp, q), the prior is on (mass1, mass2):
+        // + log |d(m1, m2)/d(mchirp, q)| = log(mchirp ((1 + q) / q^3)^(2/5))
+        if (mchirp > 0.0 && qratio > 0.0) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                lp += prior_term(S.derived_type[i], row[i], S.derived_lo[i], S.derived_hi[i],
+                                 S.derived_mu[i], S.derived_sigma[i]);
+            lp += log(mchirp * pow((1.0 + qratio) / (qratio * qratio * qratio), 0.4));
+        } else {
+            lp = -INFINITY;
+        }
     }
     if (isnan(lp)) lp = -INFINITY;
     logp[w] = lp;
@@ -453,6 +470,12 @@ extern "C" int gwin_ens_prior_calib(const gwin_prior_spec* spec, int64_t W, cons
             return gwin_fail(GWIN_EINVAL, "dimension %d: sigma must be positive", d);
     }
     for (int i = 0; i < GWIN_NPARAM; ++i) S.fixed[i] = spec->fixed[i];
+    S.derived_masses = spec->derived_masses;
+    for (int i = 0; i < 2; ++i) {
+        S.derived_type[i] = spec->derived_type[i];
+        S.derived_lo[i] = spec->derived_lo[i]; S.derived_hi[i] = spec->derived_hi[i];
+        S.derived_mu[i] = spec->derived_mu[i]; S.derived_sigma[i] = spec->derived_sigma[i];
+    }
     ens_prior_kernel<<<(unsigned)((W + 127) / 128), 128, 0, (cudaStream_t)stream>>>(S, (int)W, q, logp, skip, params,
                                                                                     n_calib > 0 ? calib : nullptr);
     CKE(cudaGetLastError());

@@ -12,8 +12,8 @@ torch is used for what the task allows it: owning device memory, the stream and
 ``torch.distributed``.  Restrictions (use the host steppers otherwise): priors
 must be a ``JointDistribution`` of Uniform / UniformAngle / SinAngle / CosAngle /
 UniformRadius / UniformSky / Gaussian without constraints, at most 64 sampled
-dimensions, no sampling transforms, and the only waveform transform understood is
-(mchirp, q) -> (mass1, mass2).  ``recalib_*`` parameters of a calibrated model
+dimensions; the only sampling transform understood is (mass1, mass2) -> (mchirp, q)
+(log-Jacobian on the device), the only waveform transform (mchirp, q) -> (mass1, mass2).  ``recalib_*`` parameters of a calibrated model
 (``gwin/calibration.py``) are sampled like any other: the prior kernel fills the
 kernels' calibration matrix (values are not checked against the regime in which the
 least-squares cubic equals scipy's smoothing spline -- keep their priors inside
@@ -40,8 +40,14 @@ _TYPES = {D.Uniform: _lib.PRIOR_UNIFORM, D.UniformAngle: _lib.PRIOR_UNIFORM_ANGL
 def prior_spec_from_model(model):
     """Translate ``model.prior_distribution`` + static params into the
     ``gwin_prior_spec`` the device kernels understand."""
+    sampled_mchirp_q = False
     if model.sampling_transforms is not None:
-        raise NotImplementedError("sampling transforms are not supported on the device path")
+        st = model.sampling_transforms.sampling_transforms
+        if len(st) == 1 and isinstance(st[0], T.Mass1Mass2ToMchirpQ):
+            sampled_mchirp_q = True             # the walkers move in (mchirp, q), the prior is on the masses
+        else:
+            raise NotImplementedError("the only sampling transform supported on the device path is "
+                                      "mass1, mass2 -> mchirp, q")
     wt = getattr(model, "_waveform_transforms", None)
     mchirp_q = False
     if wt:
@@ -76,6 +82,21 @@ def prior_spec_from_model(model):
             calib_names += list(recalib[det].param_names)
     spec = _lib.PriorSpec()
     spec.ndim = len(names)
+    if sampled_mchirp_q:
+        if mchirp_q:
+            raise NotImplementedError("mchirp, q as both a sampling and a waveform transform")
+        spec.derived_masses = 1
+        for i, name in enumerate(("mass1", "mass2")):
+            kind, lo, hi = per_param[name][:3]
+            spec.derived_type[i], spec.derived_lo[i], spec.derived_hi[i] = kind, lo, hi
+            spec.derived_sigma[i] = 1.0
+            if kind == _lib.PRIOR_GAUSSIAN:
+                spec.derived_mu[i], spec.derived_sigma[i] = per_param[name][3:5]
+        # the sampling parameters themselves: no prior of their own, wide bounds for the coverage draw
+        m1, m2 = per_param["mass1"], per_param["mass2"]
+        mc = lambda a, b: (a * b) ** 0.6 / (a + b) ** 0.2
+        per_param["mchirp"] = (_lib.PRIOR_NONE, mc(m1[1], m2[1]), mc(m1[2], m2[2]))
+        per_param["q"] = (_lib.PRIOR_NONE, m1[1] / m2[2], m1[2] / m2[1])
     for d, name in enumerate(names):
         kind, lo, hi = per_param[name][:3]
         spec.type[d], spec.lo[d], spec.hi[d] = kind, lo, hi
@@ -86,9 +107,9 @@ def prior_spec_from_model(model):
             spec.target[d] = _lib.TARGET_CALIB0 + calib_names.index(name)
         elif name in wf_names:
             spec.target[d] = wf_names.index(name)
-        elif mchirp_q and name == "mchirp":
+        elif (mchirp_q or sampled_mchirp_q) and name == "mchirp":
             spec.target[d] = _lib.TARGET_MCHIRP
-        elif mchirp_q and name == "q":
+        elif (mchirp_q or sampled_mchirp_q) and name == "q":
             spec.target[d] = _lib.TARGET_Q
         else:
             raise NotImplementedError("sampling parameter %r does not map to a waveform parameter" % name)
@@ -99,7 +120,7 @@ def prior_spec_from_model(model):
             spec.fixed[i] = float(static[name])
         elif default is not None:
             spec.fixed[i] = float(default)
-        elif name in names or (mchirp_q and name in ("mass1", "mass2")):
+        elif name in names or ((mchirp_q or sampled_mchirp_q) and name in ("mass1", "mass2")):
             spec.fixed[i] = 0.0
         else:
             raise ValueError("waveform parameter %r is neither sampled nor static" % name)

@@ -291,6 +291,7 @@ int gwin_plan_table_blocks(const gwin_plan* plan, int64_t cap, int32_t* start, i
 #define GWIN_PRIOR_COS_ANGLE      3   /* CosAngle: p ~ cos x, reflected into [-pi/2, pi/2]     */
 #define GWIN_PRIOR_UNIFORM_RADIUS 4   /* UniformRadius: p ~ x^2                                */
 #define GWIN_PRIOR_GAUSSIAN       5   /* Gaussian: normal (mu, sigma) truncated to [lo, hi]    */
+#define GWIN_PRIOR_NONE           6   /* no prior of its own (a sampling parameter whose prior is on derived ones) */
 
 #define GWIN_TARGET_MCHIRP 100        /* sampling dim is mchirp ...                            */
 #define GWIN_TARGET_Q      101        /* ... / q = m1/m2: mapped to mass1, mass2 on the device */
@@ -303,6 +304,13 @@ typedef struct gwin_prior_spec {
     double lo[GWIN_ENS_MAXDIM], hi[GWIN_ENS_MAXDIM];
     double mu[GWIN_ENS_MAXDIM], sigma[GWIN_ENS_MAXDIM];    /* GWIN_PRIOR_GAUSSIAN                     */
     double fixed[GWIN_NPARAM];          /* static values of the parameters that are not sampled  */
+    /* Sampling transform (mass1, mass2) -> (mchirp, q) (gwin/models/base.py:109-220 with
+     * pycbc.transforms.Mass1Mass2ToMchirpQ): the walkers move in mchirp, q (dimensions with target
+     * GWIN_TARGET_MCHIRP / _Q and type GWIN_PRIOR_NONE), the prior is on mass1, mass2 (derived_*[0], [1]:
+     * type, bounds, Gaussian parameters) and log |d(mass1, mass2)/d(mchirp, q)| is added.  0 = none. */
+    int32_t derived_masses;
+    int32_t derived_type[2];
+    double derived_lo[2], derived_hi[2], derived_mu[2], derived_sigma[2];
 } gwin_prior_spec;
 
 /* Stretch-move proposals for one half (0/1) of every temperature.

@@ -305,3 +305,55 @@ def test_device_sampler_with_calibration_parameters():
     b = np.asarray(s['distance'])[:, 75::15].ravel()
     assert abs(np.median(a) - np.median(b)) < 0.05 * np.median(a)
     assert abs(host.acceptance_fraction.mean() - dev.acceptance_fraction.mean()) < 0.1
+
+
+def test_device_prior_with_sampling_transform_and_jacobian():
+    """Sampling transforms on the device (gwin/models/base.py:109-220): the walkers move in
+    (mchirp, q), the prior is uniform in (mass1, mass2); the device prior kernel applies the inverse
+    transform, the priors of the masses and log |d(mass1, mass2)/d(mchirp, q)| exactly as
+    ``_transform_params`` + ``logprior`` (with ``_logjacobian``) do on the host; a short device run
+    reproduces the model's logplr at its stored positions and hands back samples in the masses."""
+    import torch
+    cfg = util.c2()
+    variable = ['mass1', 'mass2', 'distance', 'tc']
+    prior = D.JointDistribution(
+        variable, D.Uniform(mass1=(25., 40.)), D.Uniform(mass2=(20., 35.)),
+        D.UniformRadius(distance=(100., 1000.)), D.Uniform(tc=(cfg.inj['tc'] - 0.1, cfg.inj['tc'] + 0.1)))
+    st = models.SamplingTransforms(variable, ['mchirp', 'q'], ['mass1', 'mass2'], [T.Mass1Mass2ToMchirpQ()])
+    static = {k: v for k, v in cfg.inj.items() if k not in variable}
+    model = cfg.cuda_model(variable_params=tuple(variable), static_params=static, prior=prior,
+                           sampling_transforms=st)
+    assert tuple(model.sampling_params) == ('distance', 'tc', 'mchirp', 'q')
+    spec = prior_spec_from_model(model)
+    assert spec.derived_masses == 1 and spec.type[2] == _lib.PRIOR_NONE and spec.target[3] == _lib.TARGET_Q
+    rng = np.random.RandomState(1)
+    W = 4000
+    q = np.column_stack([rng.uniform(50, 1100, W), cfg.inj['tc'] + rng.uniform(-0.12, 0.12, W),
+                         rng.uniform(18., 34., W), rng.uniform(0.6, 2.2, W)])
+    qd = torch.tensor(q, device="cuda")
+    logp = torch.empty(W, dtype=torch.float64, device="cuda")
+    skip = torch.empty(W, dtype=torch.uint8, device="cuda")
+    params = torch.empty((13, W), dtype=torch.float64, device="cuda")
+    _lib.check(_lib.load().gwin_ens_prior(C.byref(spec), W, qd.data_ptr(), logp.data_ptr(),
+                                          skip.data_ptr(), params.data_ptr(), None))
+    torch.cuda.synchronize()
+    host = models.CallModel(model, 'logprior').batch(q).values          # logprior includes the log-Jacobian
+    dev = logp.cpu().numpy()
+    assert np.array_equal(np.isneginf(host), np.isneginf(dev))
+    ok = np.isfinite(host)
+    assert ok.sum() > 100 and (~ok).sum() > 100
+    assert np.allclose(host[ok], dev[ok], rtol=1e-13, atol=1e-13)
+    assert np.ptp(host[ok]) > 0.5                                       # the Jacobian varies over the box
+    from gwin_b200.waveform import param_rows
+    hp = param_rows(model._transform_params(**{n: q[:, i] for i, n in enumerate(model.sampling_params)}), W,
+                    static=model._static_for_kernel())
+    assert np.allclose(params.cpu().numpy()[:, ok], hp[:, ok], rtol=1e-13, atol=1e-13)
+    np.random.seed(8)
+    dev_s = CudaEnsembleSampler(model, 64, seed=5)
+    dev_s.set_p0()
+    dev_s.run(30)
+    pts = dev_s.chain[:8, -1, :]
+    ref = models.CallModel(model, 'logplr').batch(pts).values
+    assert np.allclose(dev_s.lnpost[:8, -1], ref, rtol=1e-10, atol=1e-8)
+    s = dev_s.samples
+    assert 'mass1' in s.dtype.names and np.all(np.asarray(s['mass1']) >= 25. - 1e-9)
