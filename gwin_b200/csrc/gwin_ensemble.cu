@@ -315,12 +315,13 @@ __global__ void __launch_bounds__(1024)
 ens_swap_all_fast_kernel(uint64_t seed, uint32_t iter, const uint32_t* __restrict__ iter_dev,
                          int ntemps, int nwalkers, int ndim,
                          const double* __restrict__ betas, const int* __restrict__ perms, int64_t perm_stride,
-                         double* __restrict__ p, double* __restrict__ logl, double* __restrict__ lnprob,
-                         int* __restrict__ nswap_accepted) {
+                         double* __restrict__ logl, double* __restrict__ lnprob,
+                         int* __restrict__ nswap_accepted, int* __restrict__ idx_out) {
     extern __shared__ double s_logl[];                       // [ntemps][nwalkers]
+    int* s_idx = reinterpret_cast<int*>(s_logl + (size_t)ntemps * nwalkers);   // row of p that sits at (k, w) now
     __shared__ int s_acc[SWAP_MAXLV + 1];
     if (iter_dev) { iter += *iter_dev; perms += (size_t)(*iter_dev) * perm_stride; }
-    for (int i = threadIdx.x; i < ntemps * nwalkers; i += blockDim.x) s_logl[i] = logl[i];
+    for (int i = threadIdx.x; i < ntemps * nwalkers; i += blockDim.x) { s_logl[i] = logl[i]; s_idx[i] = i; }
     if (threadIdx.x <= SWAP_MAXLV) s_acc[threadIdx.x] = 0;
     const int j0 = threadIdx.x, j1 = threadIdx.x + blockDim.x;
     double lu[SWAP_MAXLV][2];
@@ -371,19 +372,9 @@ ens_swap_all_fast_kernel(uint64_t seed, uint32_t iter, const uint32_t* __restric
                     const int a = level * nwalkers + ca[h], b = (level - 1) * nwalkers + cb[h];
                     const double la = s_logl[a], lb = s_logl[b];
                     if (dbeta * (la - lb) > lu[q][h]) {
-                        // both rows are read before either is written: one round trip to global memory per 8
-                        // coordinates instead of one per coordinate
-                        double* ra = p + (size_t)a * ndim;
-                        double* rb = p + (size_t)b * ndim;
-                        for (int d0 = 0; d0 < ndim; d0 += 8) {
-                            double ta[8], tb[8];
-#pragma unroll
-                            for (int d = 0; d < 8; ++d)
-                                if (d0 + d < ndim) { ta[d] = ra[d0 + d]; tb[d] = rb[d0 + d]; }
-#pragma unroll
-                            for (int d = 0; d < 8; ++d)
-                                if (d0 + d < ndim) { ra[d0 + d] = tb[d]; rb[d0 + d] = ta[d]; }
-                        }
+                        // the positions are not moved here (one SM's load/store queue would be the bottleneck):
+                        // the exchange is recorded and applied to all rows at once afterwards
+                        { const int t = s_idx[a]; s_idx[a] = s_idx[b]; s_idx[b] = t; }
                         const double qa = lnprob[a], qb = lnprob[b];
                         s_logl[a] = lb; s_logl[b] = la;
                         lnprob[a] = qb - dbeta * lb;
@@ -396,8 +387,18 @@ ens_swap_all_fast_kernel(uint64_t seed, uint32_t iter, const uint32_t* __restric
             __syncthreads();            // level l-1 reads what level l wrote to chain l-1
         }
     }
-    for (int i = threadIdx.x; i < ntemps * nwalkers; i += blockDim.x) logl[i] = s_logl[i];
+    for (int i = threadIdx.x; i < ntemps * nwalkers; i += blockDim.x) { logl[i] = s_logl[i]; idx_out[i] = s_idx[i]; }
     if (threadIdx.x < ntemps && s_acc[threadIdx.x]) atomicAdd(nswap_accepted + threadIdx.x, s_acc[threadIdx.x]);
+}
+// rows of p to where the swaps sent them: tmp[r] = p[idx[r]], then p = tmp
+__global__ void ens_rows_gather_kernel(int n, int ndim, const int* __restrict__ idx, const double* __restrict__ p,
+                                       double* __restrict__ tmp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n * ndim) tmp[i] = p[(size_t)idx[i / ndim] * ndim + i % ndim];
+}
+__global__ void ens_rows_copy_kernel(int n, const double* __restrict__ tmp, double* __restrict__ p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = tmp[i];
 }
 
 // History row `it (+ *it_dev)` of the chain [W][niter][ndim], lnprob [W][niter], logl [W][niter]
@@ -516,18 +517,39 @@ extern "C" int gwin_ens_swap_all(uint64_t seed, uint32_t iter, const uint32_t* i
     if (nwalkers < 1 || ndim < 1 || !betas || !perms || !p || !logl || !lnprob || !nswap_accepted)
         return gwin_fail(GWIN_EINVAL, "bad swap arguments");
     const int threads = nwalkers >= 1024 ? 1024 : ((nwalkers + 31) / 32) * 32;
-    const size_t smem = sizeof(double) * (size_t)ntemps * nwalkers;
+    const size_t smem = (sizeof(double) + sizeof(int)) * (size_t)ntemps * nwalkers;
     static const bool fast_on = !(getenv("GWIN_SWAP_FAST") && atoi(getenv("GWIN_SWAP_FAST")) == 0);
-    if (fast_on && ntemps - 1 <= SWAP_MAXLV && nwalkers <= 2 * threads && smem <= 200 * 1024) {
+    if (fast_on && ntemps - 1 <= SWAP_MAXLV && nwalkers <= 2 * threads && smem <= 220 * 1024) {
         int dev = 0;
         cudaGetDevice(&dev);
+        dev &= 63;
         static bool attr_set_dev[64] = {};
-        if (!attr_set_dev[dev & 63]) {
-            cudaFuncSetAttribute(ens_swap_all_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            attr_set_dev[dev & 63] = true;
+        static double* tmp_dev[64] = {};
+        static int* idx_dev[64] = {};
+        static size_t cap_dev[64] = {};
+        if (!attr_set_dev[dev]) {
+            cudaFuncSetAttribute(ens_swap_all_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+            attr_set_dev[dev] = true;
+        }
+        const size_t n = (size_t)ntemps * nwalkers;
+        if (n * ndim > cap_dev[dev]) {
+            // (scratch for the rows on their way: grown outside any stream capture -- a sampler's first
+            //  iteration always runs uncaptured)
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            cudaStreamIsCapturing((cudaStream_t)stream, &cap);
+            if (cap != cudaStreamCaptureStatusNone) return gwin_fail(GWIN_EINVAL, "swap scratch has to grow: not inside a stream capture");
+            CKE(cudaDeviceSynchronize());
+            cudaFree(tmp_dev[dev]); cudaFree(idx_dev[dev]);
+            tmp_dev[dev] = nullptr; idx_dev[dev] = nullptr; cap_dev[dev] = 0;
+            CKE(cudaMalloc(&tmp_dev[dev], sizeof(double) * n * ndim));
+            CKE(cudaMalloc(&idx_dev[dev], sizeof(int) * n * ndim));
+            cap_dev[dev] = n * ndim;
         }
         ens_swap_all_fast_kernel<<<1, threads, smem, (cudaStream_t)stream>>>(seed, iter, iter_dev, ntemps, nwalkers, ndim, betas, perms,
-                                                                             perm_stride, p, logl, lnprob, nswap_accepted);
+                                                                             perm_stride, logl, lnprob, nswap_accepted, idx_dev[dev]);
+        const int nn = (int)(n * ndim);
+        ens_rows_gather_kernel<<<(nn + 255) / 256, 256, 0, (cudaStream_t)stream>>>((int)n, ndim, idx_dev[dev], p, tmp_dev[dev]);
+        ens_rows_copy_kernel<<<(nn + 255) / 256, 256, 0, (cudaStream_t)stream>>>(nn, tmp_dev[dev], p);
     } else {
         ens_swap_all_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(seed, iter, iter_dev, ntemps, nwalkers, ndim, betas, perms,
                                                                      perm_stride, p, logl, lnprob, nswap_accepted);
