@@ -400,15 +400,17 @@ class _DeviceEnsemble(BaseMCMCSampler):
         g0 = self._iterations + self._iter0          # global iteration of this call's first step
         perms = None
         if nt > 1:
-            # replicated host RNG for the swap pairings, keyed by (seed, global iteration):
-            # identical on every rank and independent of how a run is split into run() calls
-            perms = numpy.empty((niterations, nt - 1, 2, nw), dtype=numpy.int32)
+            # pairings of the temperature swaps: per global iteration and level two random permutations of
+            # the walkers, keyed by (seed, global iteration) -- identical on every rank and independent of how
+            # a run is split into run() calls.  Drawn on the device (argsort of uniform keys from torch's
+            # Philox generator): on the host this cost 0.5 ms per iteration, half of a C4 iteration.
+            gen = torch.Generator(device=self._dev)
+            keys = torch.empty((niterations, nt - 1, 2, nw), dtype=torch.float64, device=self._dev)
             for it in range(niterations):
-                rs = numpy.random.RandomState((self._seed * 1000003 + g0 + it) % (2 ** 32))
-                for lv in range(nt - 1):
-                    perms[it, lv, 0] = rs.permutation(nw)
-                    perms[it, lv, 1] = rs.permutation(nw)
-            perms = torch.tensor(perms, device=self._dev)
+                gen.manual_seed((self._seed * 1000003 + g0 + it) % (2 ** 62))
+                torch.rand((nt - 1, 2, nw), generator=gen, dtype=torch.float64, device=self._dev, out=keys[it])
+            perms = keys.argsort(dim=-1).to(torch.int32).contiguous()
+            del keys
         ctr = torch.zeros(1, dtype=torch.int32, device=self._dev)   # iteration within this call
 
         def pre(half):
@@ -463,17 +465,27 @@ class _DeviceEnsemble(BaseMCMCSampler):
                 iteration()
             cur.wait_stream(side)
             torch.cuda.synchronize(self._dev)
-        if use_graph and self._world == 1:
+        # several GPUs: GWIN_SAMPLER_GRAPH_NCCL=1 records the all-gathers too (one graph for everything);
+        # otherwise they stay outside and everything between two of them is one graph
+        nccl_in_graph = self._world > 1 and os.environ.get("GWIN_SAMPLER_GRAPH_NCCL", "0") == "1"
+        if use_graph and (self._world == 1 or nccl_in_graph):
+            # a replay costs the same whatever the graph holds (~0.25 ms between two replays on this stack):
+            # several iterations are recorded per graph; what does not fill a graph runs kernel by kernel
+            per_graph = max(1, min(int(os.environ.get("GWIN_SAMPLER_GRAPH_ITERS", "16")), niterations - 1))
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=side):
-                iteration()
-            for _ in range(niterations - 1):
+            evals0 = self.likelihood_evals
+            with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
+                for _ in range(per_graph):
+                    iteration()
+            self.likelihood_evals = evals0 + 2 * self._Wh          # (the accounting below expects one recorded iteration)
+            n_replay, n_rest = divmod(niterations - 1, per_graph)
+            for _ in range(n_replay):
                 graph.replay()
+            for _ in range(n_rest):
+                iteration()
+            self.likelihood_evals -= 2 * self._Wh * n_rest          # (counted again below)
             self._graph_keepalive = (graph, chain, lnp_h, lnl_h, perms, ctr, q_loglr)
         elif use_graph:
-            # several GPUs: the all-gather stays outside (recording the NCCL call into a graph hung on
-            # this pool: torch 2.11, NCCL 2.28.9), everything between two all-gathers is one graph --
-            # per iteration four graph launches and two collectives instead of ~60 launches
             graphs = []
             for half in (0, 1):
                 for part in (pre, post):
