@@ -541,9 +541,64 @@ class PlanModel(object):
         ph = cls.es_kernel(x, w, beta)
         return (ph[None, :] * np.cos(2 * np.pi * np.asarray(xi)[:, None] * x[None, :])).sum(axis=1) * (w / nq)
 
-    def table_block(self, w, b, d):
+    _dweights = None
+
+    @classmethod
+    def tab_weights(cls, v, derivative=False):
+        """TAB_WEIGHTS / TAB_DWEIGHTS of csrc/tab_poly.inc evaluated as the kernel evaluates them
+        (nested FMAs with the generated literal coefficients)."""
+        import os
+        import re
+        if cls._dweights is None:
+            src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                    "gwin_b200", "csrc", "tab_poly.inc")).read()
+            progs = {}
+            for macro in ("TAB_WEIGHTS", "TAB_DWEIGHTS"):
+                body = src[src.index("#define %s(v, w)" % macro):]
+                body = body[:body.index("} while (0)")]
+                code = "\n".join(ln.strip().rstrip("\\").strip() for ln in body.split("\n")[1:])
+                code = code.replace("const double ", "").replace("double tw_e, tw_o;", "")
+                code = code.replace("(w)", "w").replace("(v)", "v")
+                code = re.sub(r"(-?0x[0-9a-f.]+p[+-]?\d+)", lambda mm: 'float.fromhex("%s")' % mm.group(1), code)
+                progs[macro] = [st.strip() for st in code.split(";") if st.strip()]
+            cls._dweights = progs
+        wts = [0.0] * cls.TAB_W
+        env = {"fma": lambda a, b, c: a * b + c, "w": wts, "v": float(v)}
+        for st in cls._dweights["TAB_DWEIGHTS" if derivative else "TAB_WEIGHTS"]:
+            exec(st, env)
+        return np.array(wts)
+
+    def calib_series(self, coef, d, kc, h):
+        """Taylor coefficients L_1..L_6 in s = (k - kc) / h of log c_d, c_d the calibration factor, as
+        loglr_table_kernel<CALIB> forms them: the two cubics shifted to the centre, then log(1 + r) and
+        atan by their differential equations (no transcendental function); and c_d(z_c)."""
+        zs, z0 = self.cal["zs"][d], self.cal["z0"][d]
+        a, ph = coef[d, 0], coef[d, 1]
+        zc, ez = kc * zs + z0, h * zs
+        A0 = ((a[3] * zc + a[2]) * zc + a[1]) * zc + a[0]
+        P0 = ((ph[3] * zc + ph[2]) * zc + ph[1]) * zc + ph[0]
+        ia = 1.0 / (1.0 + A0)
+        rr = [0.0, ez * ((3 * a[3] * zc + 2 * a[2]) * zc + a[1]) * ia, ez * ez * (3 * a[3] * zc + a[2]) * ia,
+              ez ** 3 * a[3] * ia]
+        xx = [0.5 * P0, 0.5 * ez * ((3 * ph[3] * zc + 2 * ph[2]) * zc + ph[1]),
+              0.5 * ez * ez * (3 * ph[3] * zc + ph[2]), 0.5 * ez ** 3 * ph[3]]
+        qq = [1 + xx[0] ** 2, 2 * xx[0] * xx[1], xx[1] ** 2 + 2 * xx[0] * xx[2], 2 * (xx[0] * xx[3] + xx[1] * xx[2]),
+              xx[2] ** 2 + 2 * xx[1] * xx[3], 2 * xx[2] * xx[3]]
+        ff, gg = [0.0] * 7, [0.0] * 7
+        for n in range(1, 7):
+            sf = sum((n - k) * rr[k] * ff[n - k] for k in range(1, min(n, 4)))
+            sg = sum((n - k) * qq[k] * gg[n - k] for k in range(1, min(n, 6)))
+            ff[n] = (rr[n] if n <= 3 else 0.0) - sf / n
+            gg[n] = ((xx[n] if n <= 3 else 0.0) - sg / n) / qq[0]
+        L = np.array([ff[n] + 2j * gg[n] for n in range(7)])
+        c0 = (1 + A0) / (4 + P0 * P0) * ((4 - P0 * P0) + 4j * P0)
+        return L, c0, 1 + A0
+
+    def table_block(self, w, b, d, coef=None):
         """One full sub-block for one detector: the kernel's arithmetic.  Sets ``last_est`` /
-        ``last_rho`` (what the kernel compares with TAB_EST_MAX / TAB_RHO_MAX)."""
+        ``last_rho`` (what the kernel compares with TAB_EST_MAX / TAB_RHO_MAX).  ``coef``: calibration
+        cubics (calib_coef) -- the CALIB variant: per-detector series with the log-calibration's Taylor
+        coefficients, first moment from the derivative of the interpolation weights."""
         B = self.tblk[b]
         s, m = B['start'], B['m']
         N, W, beta = self.TAB_DEG, self.TAB_W, 2.30 * self.TAB_W
@@ -554,21 +609,34 @@ class PlanModel(object):
         dt = t - B['tref'][r][:self.TAB_NT]
         th0 = t[0] + kc * w['tau'][d]
         nu = t[1] / h + w['tau'][d]
-        u = -2j * PI * dt
+        u = np.zeros(N + 1, dtype=complex)
+        u[2:] = -2j * PI * dt[2:N + 1]
+        c0, extra_est = 1.0, 0.0
+        if coef is not None:
+            Ls, c0, amp = self.calib_series(coef, d, kc, h)
+            u[1:6] += Ls[1:6]
+            extra_est = abs(Ls[6].real) + abs(Ls[6].imag)
+            if not amp > 0.25:
+                extra_est = np.inf
         e = np.zeros(N + 3, dtype=complex)
         e[0] = 1.0
-        for n in range(2, N + 3):
-            e[n] = sum(k * u[k] * e[n - k] for k in range(2, min(n, N) + 1)) / n
+        for n in range(1, N + 3):
+            e[n] = sum(k * u[k] * e[n - k] for k in range(1, min(n, N) + 1)) / n
         eps = h / kc
         self.last_est = float(np.abs(e[N + 1:].real).sum() + np.abs(e[N + 1:].imag).sum()
-                              + 1.2 * eps * abs(u[N]) * (1 + 1.2 * eps))
+                              + 1.2 * eps * abs(TWOPI * dt[N]) * (1 + 1.2 * eps) + extra_est)
         self.last_rho = TWOPI * float(np.sum(np.abs(dt[2:])))
         x = (nu - math.floor(nu)) * L
         g0 = int(math.ceil(x - W / 2.0))
         taps = g0 + np.arange(W)
         wt = self.es_kernel(x - taps, W, beta)
         M = (rows[:, taps % L] * wt[None, :]).sum(axis=1)
-        return np.exp(-2j * PI * (th0 - math.floor(th0))) * np.dot(e[:N + 1], M)
+        if coef is not None:
+            # the first moment is not tabulated (e_1 = 0 without calibration):
+            # M_1 = (i / 2 pi h) dM_0/dnu = (2 i / pi) sum_i w_i' tab_0[g0 + i]
+            dw = self.tab_weights(2.0 * (x - g0) - (W - 1), derivative=True)
+            M[1] = 2j / PI * np.sum(rows[0, taps % L] * dw)
+        return c0 * np.exp(-2j * PI * (th0 - math.floor(th0))) * np.dot(e[:N + 1], M)
 
     @staticmethod
     def fine_decomposition(length, pm, fmin):
@@ -586,12 +654,16 @@ class PlanModel(object):
             ml //= 2
         return taken, length - stretch
 
-    def loglr_table(self, p, marg=False):
+    def loglr_table(self, p, marg=False, calib=None):
         """Returns (loglr, hd, hh) and sets ``slow`` when the walker would leave the table path."""
         w = self.walker(p)
         if not w['valid']:
             return -np.inf, None, None
         ks, ke = w['ks'], w['ke']
+        coef = None
+        if calib is not None:
+            coef = self.calib_coef(calib)
+            w['hh'] = self.calib_hh(w, coef)
         S = np.zeros(self.n_det, dtype=complex)
         self.slow = not (self.cover[0] <= w['a0'] <= self.cover[1])
         self.worst_est = 0.0
@@ -600,7 +672,10 @@ class PlanModel(object):
             k = np.arange(k_lo, k_hi)
             psi = self.phase_turns(w, k)
             for d in range(self.n_det):
-                S[d] += np.sum(self.T[d, k] * np.exp(-2j * PI * (psi + k * w['tau'][d])))
+                u = np.exp(-2j * PI * (psi + k * w['tau'][d]))
+                if coef is not None:
+                    u = u * self.calib_factor(coef, d, k)
+                S[d] += np.sum(self.T[d, k] * u)
         # low band: any exact method (the recurrence kernel on the GPU)
         if min(ke, self.k_split) > ks:
             exact(ks, min(ke, self.k_split))
@@ -609,7 +684,7 @@ class PlanModel(object):
             if B['start'] + B['m'] > ke:
                 break
             for d in range(self.n_det):
-                S[d] += self.table_block(w, b, d)
+                S[d] += self.table_block(w, b, d, coef)
                 self.worst_est = max(self.worst_est, self.last_est)
                 if self.last_est > self.TAB_EST_MAX or self.last_rho > self.TAB_RHO_MAX:
                     self.slow = True

@@ -126,6 +126,60 @@ def test_table_kernel_arithmetic():
         assert abs(b[0] - lr0) <= util.tol(lr0)
 
 
+def test_calibrated_table_kernel_arithmetic():
+    """loglr_table_kernel<CALIB>: the log-calibration's Taylor coefficients about a sub-block's centre
+    (differential equations of log(1 + r) and atan: no transcendental function), the per-detector
+    series with a first-order term, and the first moment from the derivative of the interpolation
+    weights (csrc/tab_poly.inc: TAB_DWEIGHTS) -- against the calibrated direct sum and the oracle's
+    scipy splines (gwin/calibration.py:142-173)."""
+    cfg = util.c3(seglen=32)
+    n = 8
+    rec = {d: O.CubicSpline(20., 2048., n, d.lower()) for d in cfg.dets}
+    pm = _plan(cfg, mchirp_min=1.0)
+    pm.set_calibration([rec[d].spline_points for d in cfg.dets])
+    rng = np.random.default_rng(4)
+    rows = util.draw_bns(rng, 2, cfg)
+    pm.build_tables(pm.cover_stats(rows))
+    # the generated weight polynomials and their derivative against the kernel function itself
+    W, beta = pm.TAB_W, 2.30 * pm.TAB_W
+    for u0 in (-0.49, -0.2, 0.0, 0.31, 0.45):
+        xs = u0 + (W - 1) / 2.0 - np.arange(W)
+        assert np.max(np.abs(pm.tab_weights(2 * u0) - pm.es_kernel(xs, W, beta))) < 1e-12
+        fd = (pm.es_kernel(xs + 1e-6, W, beta) - pm.es_kernel(xs - 1e-6, W, beta)) / 2e-6
+        assert np.max(np.abs(pm.tab_weights(2 * u0, derivative=True) - fd)) < 1e-8
+    # the series of log c_d against numpy's log1p / arctan along a sub-block
+    vals = rng.normal(0, 0.05, (len(cfg.dets), 2, n))
+    coef = pm.calib_coef(vals)
+    B = pm.tblk[len(pm.tblk) // 2]
+    kc, h = B['start'] + B['m'] // 2, B['m'] / 2.0
+    Ls, c0, amp = pm.calib_series(coef, 1, kc, h)
+    k = B['start'] + np.arange(B['m'])
+    s = (k - kc) / h
+    exact = pm.calib_log(coef, 1, k) - pm.calib_log(coef, 1, np.array([kc]))[0]
+    assert np.max(np.abs(sum(Ls[m] * s ** m for m in range(1, 7)) - exact)) < 1e-13
+    assert abs(c0 - pm.calib_factor(coef, 1, np.array([kc]))[0]) < 1e-15 and amp > 0.5
+    orc = cfg.oracle(recalibration=rec)
+    for row in rows:
+        vals = rng.normal(0, 0.05, (len(cfg.dets), 2, n))
+        a = pm.loglr_direct(row, calib=vals)
+        b = pm.loglr_table(row, calib=vals)
+        assert not pm.slow and pm.worst_est <= pm.TAB_EST_MAX
+        assert abs(a[0] - b[0]) < 2e-8 and np.max(np.abs(a[1] - b[1])) < 2e-8
+        kw = dict(zip(util.PARAM_ORDER, row))
+        for i, d in enumerate(cfg.dets):
+            for j in range(n):
+                kw['recalib_amplitude_%s_%d' % (d.lower(), j)] = vals[i, 0, j]
+                kw['recalib_phase_%s_%d' % (d.lower(), j)] = vals[i, 1, j]
+        lr0 = orc.loglr(**kw)[0]
+        assert abs(b[0] - lr0) <= util.tol(lr0)
+        assert abs(pm.loglr_table(row)[0] - b[0]) > 1e-2        # the calibration matters
+    # a detector whose amplitude factor comes near zero leaves the table path
+    bad = np.zeros((len(cfg.dets), 2, n))
+    bad[0, 0, :] = -0.9
+    pm.loglr_table(rows[0], calib=bad)
+    assert pm.slow
+
+
 def test_table_truncation_estimate_flags_uncovered_walkers():
     """A walker outside what the tables were built for -- far in chirp mass, or with spins the
     coverage did not see -- is recognised from its own truncation estimate (the kernel then takes
