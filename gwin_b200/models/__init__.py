@@ -7,7 +7,7 @@ that emcee / kombine issue through ``pool.map`` and adds ``batch(points)``, whic
 ``gwin_b200.pool.BatchPool.map`` uses to turn the whole map into one kernel
 launch.
 """
-from .analytic import TestNormal
+from .analytic import TestEggbox, TestNormal, TestRosenbrock, TestVolcano
 from .base import BaseModel, BatchResult, ModelStats, SamplingTransforms
 from .base_data import BaseDataModel
 from .gaussian_noise import GaussianNoise
@@ -59,7 +59,10 @@ class CallModel(object):
 
 
 models = {_cls.name: _cls for _cls in (
+    TestEggbox,
     TestNormal,
+    TestRosenbrock,
+    TestVolcano,
     GaussianNoise,
     MarginalizedGaussianNoise,
     MarginalizedPhaseGaussianNoise,

@@ -35,6 +35,30 @@ def test_registry_and_names():
     assert set(samplers) == {'emcee', 'emcee_pt', 'emcee_cuda', 'emcee_pt_cuda'}
 
 
+def test_analytic_models_batch_equals_scalar():
+    """The reference's analytic test models (gwin/models/analytic.py:88-193): the formulas as its
+    docstrings state them, and batched evaluation equal to scalar calls."""
+    rng = np.random.RandomState(3)
+    assert {'test_eggbox', 'test_rosenbrock', 'test_volcano'} <= set(models.models)
+    x = rng.uniform(-3, 3, (50, 3))
+    for cls, ref in ((models.TestEggbox, lambda p: (2 + np.prod(np.cos(p / 2.))) ** 5),
+                     (models.TestRosenbrock, lambda p: -sum((1 - p[i]) ** 2 + 100 * (p[i + 1] - p[i] ** 2) ** 2
+                                                            for i in range(len(p) - 1)))):
+        m = cls(['a', 'b', 'c'])
+        call = models.CallModel(m, 'loglikelihood', return_all_stats=False)
+        got = call.batch(x).values
+        assert np.allclose(got, [ref(p) for p in x], rtol=1e-13)
+        assert np.allclose(got, [call(p) for p in x], rtol=1e-13)
+    v = models.TestVolcano(['a', 'b'])
+    call = models.CallModel(v, 'loglikelihood', return_all_stats=False)
+    r = np.hypot(x[:, 0], x[:, 1])
+    ref = 25 * (np.exp(-r / 35) + 1 / (2 * np.sqrt(2 * np.pi)) * np.exp(-0.5 * ((r - 5) / 2) ** 2))
+    assert np.allclose(call.batch(x[:, :2]).values, ref, rtol=1e-13)
+    assert np.allclose([call(p) for p in x[:5, :2]], ref[:5], rtol=1e-13)
+    with pytest.raises(ValueError):
+        models.TestVolcano(['a', 'b', 'c'])
+
+
 def test_distributions_vectorised():
     rng = np.random.RandomState(0)
     u = D.Uniform(a=(1., 3.), b=(-1., 1.))
