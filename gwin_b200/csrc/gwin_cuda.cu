@@ -10,22 +10,25 @@
 //   marginalised-phase combine                 marginalized_gaussian_noise.py:456-511
 //   distance(-phase) marginalisation           marginalized_gaussian_noise.py:431-448
 //   calibration of the template                calibration.py:142-173
-// No intermediate waveform array is ever materialised: one thread owns one
-// walker, a warp shares (broadcast) reads of the pre-weighted data table, and the
+// No intermediate waveform array is ever materialised: one thread owns one walker and the
 // frequency axis is cut into chunks so that the grid fills all 148 SMs.
 //
-// Kernels per batch:  sort_key -> [CUB radix sort of walkers by their last
-// frequency bin, so that the lanes of a warp finish together] -> walker_setup ->
-// loglr_recur over [band0, k_split) -> loglr_recur over every walker's last sub-block ->
-// loglr_table over the sub-blocks above k_split -> combine (-> marg_dist).
-// loglr_direct is an independent second implementation; short segments and calibrated
-// batches run loglr_recur over the whole band.
+// Kernels per batch (long segments, the path the benchmark takes):
+//   sort_key -> bucket_order (walkers ordered by chirp coefficient, tails by last bin) -> walker_setup ->
+//   tail_plan -> loglr_table<FINE=0> over the sub-blocks of the schedule -> loglr_table<FINE=1> over the
+//   tails (fine sub-blocks found in closed form + the last bins) -> loglr_recur over whatever is left ->
+//   combine -> slow_compact / loglr_direct / slow_finish for walkers outside the tables' coverage
+//   (-> marg_dist).
+// Short segments and small batches: loglr_recur over the whole band.  loglr_direct is an independent
+// second implementation (and the slow path).  Calibrated batches take the CALIB variants of all three.
 //
-// The recurrence kernel is FP64-pipe bound -- more precisely bound by the register-file
-// bandwidth that feeds the FP64 pipe: there is no dense contraction here,
-// so no tensor cores; its tables are L2-resident, staged into shared memory per warp by
-// TMA bulk copies and read with warp-uniform 128-bit loads.  The table kernel (DESIGN.md
-// 4.6) replaces the per-bin work above ~100 Hz by interpolation in per-plan moment tables.
+// The table kernel replaces the per-bin work by interpolation in per-plan moment
+// tables of the data relative to a grid of reference chirps: 1299 FP64 operations per (walker,
+// sub-block of up to 8192 bins); its taps x moments product runs on the FP64 tensor cores
+// (mma.m8n8k4.f64: same pipe and peak as DFMA on B200, a fifth of the instructions).  The recurrence
+// kernel is bound by the register-file bandwidth that feeds the FP64 pipe; its tables
+// are L2-resident, staged into shared memory per warp by TMA bulk copies and read with warp-uniform
+// 128-bit loads.  There is no dense contraction anywhere else on this path.
 #include <cuda_runtime.h>
 #include <cub/block/block_radix_sort.cuh>
 #include <cub/block/block_scan.cuh>

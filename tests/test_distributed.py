@@ -58,6 +58,18 @@ def _worker(rank, world, port, out):
     pt = EmceePTSampler(m, 2, 20, pool=pool)
     pt.set_p0()
     pt.run(3)
+    # option_utils.sampler_from_cli with use_mpi: the pool it builds shards over the ranks (reference
+    # gwin/option_utils.py:150-185 with choose_pool(mpi=True)); same seed, same chain as above
+    from types import SimpleNamespace
+    from gwin_b200 import option_utils
+    opts = SimpleNamespace(sampler="emcee", logpost_function="logplr", nprocesses=2, use_mpi=True, nwalkers=20)
+    np.random.seed(123)
+    s2 = option_utils.sampler_from_cli(opts, m)
+    ok = ok and s2._pool.shard is not None and s2._pool.shard.world_size == world and s2._pool.count == 2
+    s2.set_p0()
+    s2.run(5)
+    ok = ok and np.array_equal(s2.chain, s.chain)
+    models._global_instance = None
     out.put((rank, ok, pool.count, s.chain.copy(), pt.chain.copy()))
     dist.barrier()
     dist.destroy_process_group()
