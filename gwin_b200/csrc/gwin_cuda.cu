@@ -1611,40 +1611,17 @@ __global__ void cover_stats_kernel(PlanDev P, int W, const double* __restrict__ 
 #ifndef TAB_SPAN
 #define TAB_SPAN 48
 #endif
-#ifndef TAB_PREFETCH
-#define TAB_PREFETCH 0
-#endif
 #define TAB_KPRE 6           // steps (of 4 window rows) whose B fragments are fetched ahead of the weights
-// TAB_SPAN: table rows a warp stages per detector and sub-block (>= TAB_W + the lanes' spread)
-#ifndef TAB_DMMA
-#define TAB_DMMA 1           // taps x moments on the FP64 tensor cores (mma.m8n8k4.f64) instead of DFMA + broadcast loads
-#endif
-#if TAB_DMMA
-#define TAB_ROWB (TAB_NM * 16 + 32)         // 20 doubles: the B fragments' loads (4 rows x 8 columns per half-warp) hit 16 distinct banks
-#else
-#define TAB_ROWB (TAB_NM * 16 + 16)
-#endif
-#ifndef TAB_BGLOBAL
-#define TAB_BGLOBAL 1        // B fragments (table rows) straight from global memory / L1 instead of a staged copy in shared memory
-#endif
-#define TAB_MD_ALIAS 0        // (1: the moments' hand-over buffer would share the weight matrix' memory)
-#define TAB_STAGE_BYTES(nd) ((TAB_DMMA && TAB_BGLOBAL) ? 0 : (nd) * TAB_SPAN * TAB_ROWB)      // per warp
+// TAB_SPAN: widest window of table rows (TAB_W + the spread of the lanes' first rows) the tensor-core product takes
 #define TAB_WDP 36           // pitch [doubles] of the dense weight matrix [window row][lane]: conflict-free A fragments
 #ifndef TAB_CHUNK_MAX
 #define TAB_CHUNK_MAX 8
 #endif
 // TAB_CHUNK_MAX: sub-blocks per CTA at most (their Taylor matrices are staged in shared memory)
-#ifndef TAB_COEF_SMEM
-#define TAB_COEF_SMEM 1      // per-thread coefficients in shared memory (1) or in registers (0)
-#endif
 #define TAB_CROWS(nd) (NPH + 2 * (nd))      // per-thread coefficient column: phase coefficients, tau_hi/lo per detector
-#if TAB_DMMA
 // per lane (i.e. x 32 per warp) [doubles]: its column of the dense weight matrix [TAB_SPAN][TAB_WDP] and its row of
 // the moments handed back by the tensor cores [32][2 TAB_NM]
-#define TAB_WPITCH ((TAB_SPAN * TAB_WDP + WARP - 1) / WARP + (TAB_MD_ALIAS ? 0 : 2 * TAB_NM))
-#else
-#define TAB_WPITCH TAB_W                    // tap weights per lane [doubles], stored [tap][lane]
-#endif
+#define TAB_WPITCH ((TAB_SPAN * TAB_WDP + WARP - 1) / WARP + 2 * TAB_NM)
 // Thread t works on column col_arr[t] of the per-walker arrays (NULL: t itself): the sub-blocks with
 // several reference chirps are taken with the walkers ordered by a0 (lanes share a reference), the
 // long sub-blocks above them with the walkers ordered by their local time (lanes share table rows:
@@ -1678,36 +1655,22 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
     // FINE: the stretch [tail_s, tail_s + tail_len) goes to fine sub-blocks
     const int tail_s = (FINE && live) ? ks_tail_arr[col] : 0;
     const int tail_len = (FINE && live) ? ks_fine_arr[col] - tail_s : 0;
-    // shared memory: [chunk's Taylor matrices][per-thread coefficient columns][per-warp staging buffers:
-    // ND x TAB_SPAN table rows of TAB_ROWB bytes (128 B of moments + 16 B of padding against bank conflicts)]
+    // shared memory: [chunk's Taylor matrices][per-thread coefficient columns][per warp: the dense weight
+    // matrix [TAB_SPAN][TAB_WDP] of the tensor-core product and the 4 KB buffer its result comes back through]
     extern __shared__ __align__(16) unsigned char s_tab[];
     double* s_c = reinterpret_cast<double*>(s_tab);
     double* s_coef = s_c + (size_t)blocks_per_chunk * NPH * TAB_NTP;
-    double* s_wt = s_coef + (TAB_COEF_SMEM ? TAB_CROWS(ND) : 0) * CTA_THREADS + (size_t)(threadIdx.x / WARP) * WARP * TAB_WPITCH;
-    unsigned char* s_warp = reinterpret_cast<unsigned char*>(s_coef + ((TAB_COEF_SMEM ? TAB_CROWS(ND) : 0) + TAB_WPITCH) * CTA_THREADS)
-                          + (size_t)(threadIdx.x / WARP) * TAB_STAGE_BYTES(ND);
+    double* s_wt = s_coef + TAB_CROWS(ND) * CTA_THREADS + (size_t)(threadIdx.x / WARP) * WARP * TAB_WPITCH;
     if (!FINE)
         for (int i = threadIdx.x; i < (b1 - b0) * NPH * TAB_NTP; i += CTA_THREADS)
             s_c[i] = cmat[(size_t)b0 * NPH * TAB_NTP + i];
-#if TAB_DMMA
     // dense weight matrix [window row][lane] of the tensor-core product: zero outside the lanes' windows
     for (int j = 0; j < TAB_SPAN; ++j) s_wt[j * TAB_WDP + (threadIdx.x & (WARP - 1))] = 0.0;
     int off_prev = -1;
-#endif
-#if TAB_DMMA && !TAB_BGLOBAL
-    // staged rows past a window's end meet zero weights in the tensor-core product: they must hold numbers
-    for (int i = threadIdx.x & (WARP - 1); i < ND * TAB_SPAN * TAB_ROWB / 16; i += WARP)
-        reinterpret_cast<double2*>(s_warp)[i] = make_double2(0.0, 0.0);
-#endif
     // per-thread coefficients live in shared memory (one column per thread, no sharing): they are needed
     // once per sub-block, and keeping them out of the register file keeps the tap loop from spilling
-#if TAB_COEF_SMEM
     double* sa = s_coef + threadIdx.x;
 #define TCOEF(i) sa[(i) * CTA_THREADS]
-#else
-    double sa[TAB_CROWS(ND)];
-#define TCOEF(i) sa[i]
-#endif
 #pragma unroll
     for (int i = 0; i < NPH; ++i) TCOEF(i) = wc[(size_t)i * wpad + col];
 #pragma unroll
@@ -1733,9 +1696,7 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
             const unsigned amask = __ballot_sync(0xffffffffu, act);
             if (!amask) return;
             // ---- reference chirp: the nearest one on the sub-block's grid (a function of the walker alone)
-#if TAB_COEF_SMEM
             asm volatile("" ::: "memory");               // re-read the coefficient column per sub-block: do not hoist
-#endif
             int r = (int)((TCOEF(0) - B.a_lo) * B.inv_da);
             r = max(0, min(r, B.K - 1));
             // ---- Taylor coefficients of the phase about the centre: t_n = sum_i a_i c[i][n]
@@ -1800,9 +1761,9 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
             // The lanes of a warp are neighbours in a0: nearly always they share the reference, and their
             // 13 taps x 128 B live within a few grid points of each other (the walkers' local times differ
             // by less than the grid spacing times a few).  The lanes of one reference are taken together:
-            // the warp copies the union of their rows to shared memory with cp.async (one L2 round trip per
-            // sub-block instead of one per tap group), then each lane reads its taps from there.  A warp
-            // that straddles a boundary of the reference grid makes a second pass for the other reference.
+            // the union of their rows is one window of the reference's table, and taps x moments over that
+            // window is one small matrix product for the whole warp (below).  A warp that straddles a
+            // boundary of the reference grid makes a second pass for the other reference.
             double xs[ND];
             int gs[ND];
 #pragma unroll
@@ -1825,37 +1786,15 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
                 for (int d = 0; d < ND; ++d) {
                     int mn = __reduce_min_sync(0xffffffffu, mine ? gs[d] : 0x7fffffff);
                     const int mx = __reduce_max_sync(0xffffffffu, mine ? gs[d] : -1);
-#if TAB_DMMA
                     // the window starts on a multiple of 4 grid points: which of a lane's 13 taps share a step of
                     // the tensor-core product then depends on the lane alone (its first row mod 4), not on its
                     // neighbours -- a walker's result does not depend on the batch it is evaluated in
                     mn &= ~3;
-#endif
                     lo[d] = mn;
                     const int span = mx - mn + TAB_W;
                     span_d[d] = span;
                     staged[d] = span <= TAB_SPAN;
-#if TAB_DMMA && TAB_BGLOBAL && TAB_PREFETCH
-                    // the window's rows towards L1 while the series and the weights are being evaluated (one 128-byte
-                    // row per lane and instruction)
-                    if (staged[d]) {
-                        const double2* prow = row0 + (((size_t)rL * ND + d) * (L + TAB_W) + mn) * TAB_NM;
-                        for (int j = lane; j < ((span + 3) & ~3); j += WARP)
-                            asm volatile("prefetch.global.L1 [%0];" :: "l"(prow + (size_t)j * TAB_NM));
-                    }
-#endif
-                    if (staged[d] && !(TAB_DMMA && TAB_BGLOBAL)) {
-                        const double2* src = row0 + (((size_t)rL * ND + d) * (L + TAB_W) + mn) * TAB_NM;
-                        const uint32_t dst = smem_u32(s_warp + (size_t)d * TAB_SPAN * TAB_ROWB);
-                        for (int pc16 = lane; pc16 < span * TAB_NM; pc16 += WARP) {
-                            const int rr = pc16 / TAB_NM, c16 = pc16 % TAB_NM;
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
-                                         :: "r"(dst + (uint32_t)(rr * TAB_ROWB + c16 * 16)), "l"(src + pc16) : "memory");
-                        }
-                    }
                 }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                [[maybe_unused]] bool waited = false;
 #pragma unroll
                 for (int d = 0; d < ND; ++d) {
                     double2 Mn[TAB_NM];
@@ -1864,7 +1803,6 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
                     const double v = xs[d];
                     // kernel weights: per pair of mirror taps an even and an odd Horner chain in v^2,
                     // v = 2 (x - g0) - (W - 1); coefficients as literal constants (no loads)
-#if TAB_DMMA && TAB_BGLOBAL
                     // B fragments of all steps, straight from the table (rows shared by the warp's lanes and by
                     // the neighbouring warps: L1 / L2 hits): in flight while the weights are evaluated.  Rows past
                     // the window's end are table rows too (the allocation is padded) and meet zero weights.
@@ -1879,7 +1817,6 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
                             bf[ks][0] = __ldg(pbg + kr); bf[ks][1] = __ldg(pbg + kr + 8);
                         }
                     }
-#endif
                     double2 cfac = make_double2(1.0, 0.0);
                     if (CALIB) {
                         // Calibrated template (gwin/calibration.py:142-173): h_d is multiplied by c_d(f) = exp(L_d),
@@ -1954,16 +1891,16 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
                     double wt[TAB_W];
                     TAB_WEIGHTS(v, wt);
                     if (staged[d]) {
-#if TAB_DMMA
                         // M[lane][c] = sum_j Wd[j][lane] R[j][c] over the window rows j (span = 13 + the spread of
                         // the lanes' first rows, padded to a multiple of 4; Wd holds a lane's 13 weights at its
-                        // own rows and zeros elsewhere; R = the staged rows, 16 reals each): a 32 x K x 16 product
+                        // own rows and zeros elsewhere; R = the table rows, 16 reals each): a 32 x K x 16 product
                         // on the FP64 tensor cores -- 4 x 2 accumulator tiles of mma.m8n8k4, K / 4 steps.  The
-                        // pipe does the same multiply-adds as the DFMA form at its full rate, from 6 shared-memory
-                        // loads per step instead of 9 per row, and 8 instructions per step instead of 16 per row.
+                        // pipe does the same multiply-adds as a DFMA form (one row at a time, broadcast loads) at
+                        // its full rate, from 6 loads per step instead of 9 per row and 8 instructions per step
+                        // instead of 16 per row.
                         const int nks = (span_d[d] + 3) >> 2;
                         double* wd = s_wt;                               // [TAB_SPAN][TAB_WDP]
-                        double* md = s_wt + (TAB_MD_ALIAS ? 0 : TAB_SPAN * TAB_WDP);     // [32][2 TAB_NM], 16-byte units swizzled
+                        double* md = s_wt + TAB_SPAN * TAB_WDP;          // [32][2 TAB_NM], 16-byte units swizzled
                         // A lane's column holds its 13 weights at the rows of its window and zeros everywhere else:
                         // only the rows of the previous window that the new one does not cover are cleared.
                         // (The previous detector's A fragments were all loaded before its lanes passed the
@@ -1979,12 +1916,6 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
                             for (int i = 0; i < TAB_W; ++i) wd[(off + i) * TAB_WDP + lane] = wt[i];
                         }
                         off_prev = mine ? off : -1;
-#if !TAB_BGLOBAL
-                        if (!waited) {                   // the weights above overlapped the copies
-                            asm volatile("cp.async.wait_group 0;" ::: "memory");
-                            waited = true;
-                        }
-#endif
                         __syncwarp();
                         const int l4 = lane & 3, g8 = lane >> 2;
                         const double* pa = wd + l4 * TAB_WDP + g8;
@@ -1993,7 +1924,6 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
                         for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
                             for (int nt = 0; nt < 2; ++nt) cf[mt][nt][0] = cf[mt][nt][1] = 0.0;
-#if TAB_BGLOBAL
 #pragma unroll
                         for (int ks = 0; ks < TAB_KPRE; ++ks) {
                             if (ks < nks) {
@@ -2018,33 +1948,9 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
 #pragma unroll
                                 for (int nt = 0; nt < 2; ++nt) dmma884(cf[mt][nt], fa[mt], fb[nt]);
                         }
-#else
-                        const double* pb = reinterpret_cast<const double*>(s_warp + (size_t)d * TAB_SPAN * TAB_ROWB)
-                                         + l4 * (TAB_ROWB / 8) + g8;
-                        double fa[4], fb[2];
-#pragma unroll
-                        for (int mt = 0; mt < 4; ++mt) fa[mt] = pa[8 * mt];
-                        fb[0] = pb[0]; fb[1] = pb[8];
-                        for (int ks = 0; ks < nks; ++ks) {
-                            // next step's fragments (the last step re-reads its own)
-                            const int kn = min(ks + 1, nks - 1) * 4;
-                            double na[4], nb[2];
-#pragma unroll
-                            for (int mt = 0; mt < 4; ++mt) na[mt] = pa[kn * TAB_WDP + 8 * mt];
-                            nb[0] = pb[kn * (TAB_ROWB / 8)]; nb[1] = pb[kn * (TAB_ROWB / 8) + 8];
-#pragma unroll
-                            for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                                for (int nt = 0; nt < 2; ++nt) dmma884(cf[mt][nt], fa[mt], fb[nt]);
-#pragma unroll
-                            for (int mt = 0; mt < 4; ++mt) fa[mt] = na[mt];
-                            fb[0] = nb[0]; fb[1] = nb[1];
-                        }
-#endif
                         // accumulator tile (mt, nt): walker 8 mt + lane / 4, complex moment 4 nt + lane % 4.  Through
                         // shared memory to the walker's own lane; unit (n + f(walker)) mod 8 of the walker's 128-byte
                         // row, f = 4 (w & 1) + ((w >> 1) & 3): conflict-free 128-bit stores and loads.
-                        if (TAB_MD_ALIAS) __syncwarp();
 #pragma unroll
                         for (int mt = 0; mt < 4; ++mt) {
                             const int wk = 8 * mt + g8;
@@ -2061,38 +1967,6 @@ loglr_table_kernel(PlanDev P, int W, int wpad, int blocks_per_chunk, int blk_lo,
                             for (int n = 0; n < TAB_NM; ++n)
                                 Mn[n] = *reinterpret_cast<const double2*>(md + lane * (2 * TAB_NM) + 2 * ((n + fw) & 7));
                         }
-                        if (TAB_MD_ALIAS) __syncwarp();
-#else
-                        // The staged rows are a window of span = 13 + (spread of the lanes' first rows) rows.
-                        // The warp walks the window row by row: the table row is read with warp-uniform
-                        // 128-bit loads (one shared-memory wavefront each, whatever the spread) and every
-                        // lane multiplies by its own weight for that row -- tap (row - its offset), fetched
-                        // from its column of the weights it parked in shared memory, or 0.
-                        const int span = span_d[d];
-                        double* sw = s_wt + lane;        // [tap][lane]: conflict-free whatever the lanes' offsets
-                        const int off = mine ? gs[d] - lo[d] : -TAB_W;       // this lane's first row in the window
-                        __syncwarp();                    // the previous detector's weights have been read
-#pragma unroll
-                        for (int i = 0; i < TAB_W; ++i) sw[i * WARP] = wt[i];
-                        if (!waited) {                   // the weights above overlapped the copies
-                            asm volatile("cp.async.wait_group 0;" ::: "memory");
-                            waited = true;
-                        }
-                        __syncwarp();
-                        const unsigned char* sr = s_warp + (size_t)d * TAB_SPAN * TAB_ROWB;
-#pragma unroll 2
-                        for (int j = 0; j < span; ++j) {
-                            const int i = j - off;       // this lane's tap on window row j (none: weight 0)
-                            const double w = (unsigned)i < (unsigned)TAB_W ? sw[i * WARP] : 0.0;
-                            const double2* e = reinterpret_cast<const double2*>(sr + j * TAB_ROWB);
-#pragma unroll
-                            for (int n = 0; n < TAB_NM; ++n) {
-                                const double2 q = e[n];
-                                Mn[n].x = fma(w, q.x, Mn[n].x);
-                                Mn[n].y = fma(w, q.y, Mn[n].y);
-                            }
-                        }
-#endif
                     } else if (mine) {                   // lanes too far apart in time: every lane its own rows, from L2
                         // rows are padded with TAB_W wrap-around points: the taps are contiguous
                         const double2* rd = row0 + (((size_t)rL * ND + d) * (L + TAB_W) + gs[d]) * TAB_NM;
@@ -3584,8 +3458,7 @@ static void launch_table(gwin_plan* p, int W, int wpad, int per_chunk, int blk_l
                          bool fine, int slots, cudaStream_t st) {
     if (!fine && blk_hi <= blk_lo) return;
     dim3 grid((W + CTA_THREADS - 1) / CTA_THREADS, fine ? slots : (blk_hi - blk_lo + per_chunk - 1) / per_chunk);
-    const int fixed = ((TAB_COEF_SMEM ? TAB_CROWS(ND) : 0) + TAB_WPITCH) * CTA_THREADS * (int)sizeof(double)
-                    + (CTA_THREADS / WARP) * TAB_STAGE_BYTES(ND);
+    const int fixed = (TAB_CROWS(ND) + TAB_WPITCH) * CTA_THREADS * (int)sizeof(double);
     const int smem = (fine ? 0 : per_chunk) * NPH * TAB_NTP * (int)sizeof(double) + fixed;
     static bool attr_set_dev[64] = {};
     if (!attr_set_dev[p->device & 63]) {
