@@ -2831,6 +2831,9 @@ static int build_tables(gwin_plan* p) {
             cudaGetLastError();                           // not enough device memory: no tables
             return 1;
         }
+        // (those rows meet zero weights in the tensor-core product: they must hold numbers, not whatever the
+        //  allocation left there)
+        CK(cudaMemset(reinterpret_cast<unsigned char*>(p->d_tab) + (size_t)bytes, 0, 1024));
         CK(cudaMemcpy(p->d_tblk, blks.data(), sizeof(TabBlk) * n, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(p->d_cmat, cmat.data(), sizeof(double) * cmat.size(), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(d_pair_blk, pair_blk.data(), sizeof(int) * n_pairs, cudaMemcpyHostToDevice));
