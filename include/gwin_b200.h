@@ -212,8 +212,10 @@ int gwin_loglr_batch_points_host(gwin_plan* plan, int mode, int64_t W,
                                  const int* map, const double* fixed, const uint8_t* skip,
                                  double* loglr, double* hd, double* hh);
 /*
- * The same call in two halves, for callers with more than one batch to evaluate (the halves of a
- * parallel-tempered ensemble, several independent ensembles, pool.map over chunks): _submit queues the
+ * The same call in two halves, for callers with more than one batch to evaluate -- what the reference
+ * gets from a process pool working on several tasks at once (pool.map of CallModel over the points,
+ * gwin/option_utils.py:171-185; the separate prior / likelihood maps of a parallel-tempered ensemble,
+ * gwin/sampler/emcee.py:230-250): _submit queues the
  * host-to-device copy, the kernels and the copy back and returns at once with a ticket; _wait blocks until
  * that call's results are in loglr / hd / hh.  Two calls may be in flight per plan: the copies of one
  * overlap the kernels of the other (separate copy streams, separate staging).  points / skip may be reused
