@@ -45,3 +45,33 @@ def sampler_from_cli(opts, model, pool=None):
         pool = choose_pool(mpi=getattr(opts, "use_mpi", False), processes=opts.nprocesses)
     pool.count = max(int(opts.nprocesses), pool.count)
     return sclass.from_cli(opts, model, pool=pool, model_call=model_call)
+
+
+def _usable_samples(path):
+    """Number of samples per walker in a result file that reads back consistently, else 0."""
+    from .io import InferenceFile, check_integrity
+    try:
+        check_integrity(path)
+        with InferenceFile(path, 'r') as fp:
+            first = '%s/%s' % (fp.samples_group, fp.variable_params[0])
+            return int(fp[first].size)
+    except Exception:        # noqa: BLE001 -- anything a truncated / foreign file can raise on the way in
+        return 0
+
+
+def validate_checkpoint_files(checkpoint_file, backup_file):
+    """The reference's rule for resuming (``gwin/option_utils.py:192-283``): a file is usable when it
+    passes ``check_integrity`` and holds at least one sample; a backup that holds a different number
+    of samples than a usable checkpoint is not.  When exactly one of the two is usable it is copied
+    over the other, so that afterwards both are usable or neither is.  Returns whether a run may
+    resume from them."""
+    import shutil
+    n_chk, n_bak = _usable_samples(checkpoint_file), _usable_samples(backup_file)
+    chk_ok, bak_ok = n_chk > 0, n_bak > 0
+    if chk_ok and bak_ok and n_bak != n_chk:
+        bak_ok = False                              # the checkpoint is taken to be the complete one
+    if chk_ok and not bak_ok:
+        shutil.copy(checkpoint_file, backup_file)
+    elif bak_ok and not chk_ok:
+        shutil.copy(backup_file, checkpoint_file)
+    return chk_ok or bak_ok

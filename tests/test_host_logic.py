@@ -439,3 +439,38 @@ def test_sampler_from_cli_selects_pool_and_global_instance():
             option_utils.sampler_from_cli(opts, m)
     finally:
         models._global_instance = None
+
+
+def test_validate_checkpoint_files(tmp_path):
+    """option_utils.validate_checkpoint_files (reference gwin/option_utils.py:192-283): checkpoint and
+    backup end up both usable or both unusable."""
+    from gwin_b200 import option_utils
+    from gwin_b200.io import InferenceFile
+    prior = D.JointDistribution(['x'], D.Uniform(x=(-5, 5)))
+    m = models.TestNormal(['x'], prior=prior)
+    np.random.seed(1)
+    s = EmceeEnsembleSampler(m, 8)
+    s.set_p0()
+    s.run(6)
+    chk, bak = str(tmp_path / "run.npz"), str(tmp_path / "run.bak.npz")
+    assert not option_utils.validate_checkpoint_files(chk, bak)          # neither exists: start from scratch
+    with InferenceFile(chk, 'w') as fp:
+        s.write_metadata(fp)
+        s.write_results(fp)
+    assert option_utils.validate_checkpoint_files(chk, bak)              # the backup is created from the checkpoint
+    assert InferenceFile(bak, 'r')['samples/x'].shape == (8, 6)
+    with open(chk, 'wb') as f:                                           # a checkpoint cut off mid-write
+        f.write(b'not an archive')
+    assert option_utils.validate_checkpoint_files(chk, bak)              # ... is restored from the backup
+    assert InferenceFile(chk, 'r')['samples/x'].shape == (8, 6)
+    s.run(4)                                                             # the checkpoint moves on, the backup lags
+    with InferenceFile(chk, 'a') as fp:
+        s.write_metadata(fp)
+        s.write_results(fp)
+    assert InferenceFile(chk, 'r')['samples/x'].shape[-1] != InferenceFile(bak, 'r')['samples/x'].shape[-1]
+    assert option_utils.validate_checkpoint_files(chk, bak)
+    assert InferenceFile(bak, 'r')['samples/x'].shape == InferenceFile(chk, 'r')['samples/x'].shape
+    for p in (chk, bak):
+        with open(p, 'wb') as f:
+            f.write(b'')
+    assert not option_utils.validate_checkpoint_files(chk, bak)
