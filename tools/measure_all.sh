@@ -1,3 +1,5 @@
+# development aid: the full single-GPU measurement pass behind profiles/r2_* (GPU tests, bench, reference arm, tc sweep,
+# ncu launch list + full capture of one step's loglr launches, calibrated timing, C4, PT timeline)
 mkdir -p gpurun_out
 timeout 1700 python -m pytest tests -m gpu -x -q > gpurun_out/s3_gputest_full.log 2>&1; echo "pytest rc=$?" >> gpurun_out/s3_gputest_full.log
 tail -4 gpurun_out/s3_gputest_full.log
