@@ -113,6 +113,7 @@ __device__ __forceinline__ double wrap_cyclic(double x, double lo, double hi) {
     const double w = hi - lo;
     double y = fmod(x - lo, w);
     if (y < 0.0) y += w;
+    if (y >= w) y = 0.0;            // (a rounding error below lo wraps to hi itself: the domain is half-open)
     return y + lo;
 }
 __device__ __forceinline__ double wrap_reflect(double x, double lo, double hi) {
@@ -141,7 +142,10 @@ __device__ __forceinline__ double prior_term(int type, double& x, double lo, dou
             return (x >= lo && x <= hi) ? log(3.0 * x * x / (hi * hi * hi - lo * lo * lo)) : -INFINITY;
         case GWIN_PRIOR_GAUSSIAN: {             // normal (mu, sigma) truncated to [lo, hi]
             const double z = (x - mu) / sg;
-            const double nrm = 0.5 * (erf((hi - mu) / (sg * 1.4142135623730951)) - erf((lo - mu) / (sg * 1.4142135623730951)));
+            // mass inside the bounds, from complementary error functions on the side of the mean the interval
+            // lies on (as distributions.Gaussian._norm: erf differences cancel far out in a tail)
+            const double a = (lo - mu) / (sg * 1.4142135623730951), b = (hi - mu) / (sg * 1.4142135623730951);
+            const double nrm = a > 0.0 ? 0.5 * (erfc(a) - erfc(b)) : (b < 0.0 ? 0.5 * (erfc(-b) - erfc(-a)) : 0.5 * (erf(b) - erf(a)));
             return (x >= lo && x <= hi) ? -0.5 * z * z - log(sg * 2.5066282746310002 * nrm) : -INFINITY;
         }
         case GWIN_PRIOR_NONE:

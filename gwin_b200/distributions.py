@@ -106,7 +106,11 @@ class UniformAngle(Uniform):
         for p, b in self._bounds.items():
             if p in out:
                 x = numpy.asarray(out[p], dtype=float)
-                out[p] = (x - b.min) % (b.max - b.min) + b.min
+                w = b.max - b.min
+                y = (x - b.min) % w
+                # (a value a rounding error below the lower bound wraps to the upper bound itself, which is
+                #  outside the half-open domain: it is the lower bound)
+                out[p] = numpy.where(y >= w, 0.0, y) + b.min
         return out
 
 
@@ -185,9 +189,17 @@ class Gaussian(_BoundedDist):
         self._var = {p: float(vars_.get(p, 1.0)) for p in self._params}
 
     def _norm(self, p, b):
-        from scipy.special import erf
+        """Probability mass of the untruncated normal inside the bounds; formed from complementary error
+        functions on the side of the mean the interval lies on, so that an interval far out in a tail keeps
+        its relative accuracy (erf differences there cancel)."""
+        from scipy.special import erf, erfc
         s = numpy.sqrt(2.0 * self._var[p])
-        return 0.5 * (erf((b.max - self._mean[p]) / s) - erf((b.min - self._mean[p]) / s))
+        lo, hi = (b.min - self._mean[p]) / s, (b.max - self._mean[p]) / s
+        if lo > 0.0:
+            return 0.5 * (erfc(lo) - erfc(hi))
+        if hi < 0.0:
+            return 0.5 * (erfc(-hi) - erfc(-lo))
+        return 0.5 * (erf(hi) - erf(lo))
 
     def pdf(self, **kwargs):
         val = 1.0
